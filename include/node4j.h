@@ -1,0 +1,186 @@
+/* node4j.h — C ABI of the B200-native ODE-block engine (libnode4j_b200.so).
+ *
+ * Drop-in boundary for neuralODE4j's ODE-block hot path.  The reference (100 % Java, arithmetic in
+ * un-vendored ND4J/DL4J) has no FFI of its own; its plugin seam for this path is the pair of helper
+ * interfaces installed by OdeVertex.Builder.odeConf/odeForward/odeBackward
+ * (src/main/java/ode/vertex/conf/OdeVertex.java:271-296):
+ *
+ *   INDArray   OdeHelperForward.solve (ComputationGraph, LayerWorkspaceMgr, GraphInput)
+ *                  src/main/java/ode/vertex/impl/helper/forward/OdeHelperForward.java:22
+ *   INDArray[] OdeHelperBackward.solve(ComputationGraph, InputArrays, MiscPar)
+ *                  src/main/java/ode/vertex/impl/helper/backward/OdeHelperBackward.java:55
+ *
+ * A Java shim (Panama downcalls or JNI) implements those two interfaces on top of
+ * the entry points below; FixedStep / InputStep / DormandPrince54Solver / SolverConfig keep their
+ * constructors and JSON shape.  Everything here is plain C: pointers, sizes, POD structs, int status.
+ *
+ * Conventions
+ *  - All tensors are fp32.  Every data pointer may be a HOST pointer or a CUDA DEVICE pointer of the
+ *    engine's device; the engine detects which (cudaPointerGetAttributes) and stages host buffers
+ *    itself.  Outputs are caller-allocated and written in place (SingleStep.java:42, MultiStep.java:42).
+ *  - Tensors use the reference's layouts: state c-order [B,F] or NCHW [B,C,H,W]
+ *    (NoTimeInput.java:32-42); multi-time outputs [B,F,T] / [B,T,C,H,W] (MultiStep.java:49-60);
+ *    parameters and gradients in DL4J's flat view order (dense W [nIn,nOut] f-order then b; conv W
+ *    [Cout,Cin,3,3] c-order; batchnorm gamma,beta,mean,var).
+ *  - Calls are synchronous and a handle is not thread-safe (one caller thread per vertex, like the
+ *    reference's helpers).  Functions return N4J_OK or an error code; node4j_last_error() gives the
+ *    message of the calling thread's last failure.  The library never aborts and has no CPU fallback:
+ *    without a usable CUDA device every compute entry point fails with N4J_ERR_CUDA.
+ */
+#ifndef NODE4J_H
+#define NODE4J_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define N4J_ABI_VERSION 1
+
+/* ---- status codes; the Java shim maps them onto the reference's exception types ---------------- */
+enum {
+    N4J_OK = 0,
+    N4J_ERR_INVALID_ARGUMENT = 1, /* IllegalArgumentException: t.length()!=2 (AdaptiveRungeKuttaSolver.java:108),
+                                     minStep>=maxStep (SolverConfig.java:22), unsorted time (MultiStepAdjoint.java:43) */
+    N4J_ERR_ILLEGAL_STATE = 2,    /* IllegalStateException: NaN detected (NanWatchSolver.java:22), backward before forward */
+    N4J_ERR_UNSUPPORTED = 3,      /* UnsupportedOperationException: layer/vertex outside the native set, rank not 2/4
+                                     (MultiStep.java:57-59) */
+    N4J_ERR_CUDA = 4,             /* CUDA runtime failure or no device */
+    N4J_ERR_MAX_STEPS = 5,        /* step guard tripped (the reference would loop forever) */
+    N4J_ERR_COMM = 6              /* NCCL failure */
+};
+
+/* ---- inner graph description (what OdeVertex.Builder assembled; chain of DL4J layers) ---------- */
+enum { N4J_LAYER_DENSE = 1, N4J_LAYER_CONV3X3 = 2, N4J_LAYER_BATCHNORM = 3, N4J_LAYER_ACTIVATION = 4 };
+enum { N4J_ACT_IDENTITY = 0, N4J_ACT_RELU = 1, N4J_ACT_ELU = 2, N4J_ACT_TANH = 3 };
+
+typedef struct n4j_layer_desc {
+    int32_t kind;       /* N4J_LAYER_* */
+    int32_t activation; /* N4J_ACT_* (every DL4J layer carries one) */
+    int64_t n_in;       /* dense: nIn; conv/batchnorm: channels; 0 = infer from the previous layer */
+    int64_t n_out;      /* dense: nOut; conv: kernels; batchnorm: channels */
+    int32_t has_bias;   /* dense only; conv3x3 is hasBias(false) (examples/mnist/LayerUtil.java:65-72) */
+    float eps;          /* batchnorm epsilon */
+} n4j_layer_desc;
+
+typedef struct n4j_graph_desc {
+    int32_t n_layers;
+    int32_t rank;     /* 2: [B,F]   4: [B,C,H,W] */
+    int64_t shape[4]; /* state shape, batch first (LOCAL batch when sharded, see node4j_comm_init) */
+    const n4j_layer_desc* layers;
+} n4j_graph_desc;
+
+/* ---- solver configuration: SolverConfig.java:17-30 + AdaptiveRungeKuttaStepPolicy.java:43-45 ---- */
+enum {
+    N4J_FLAG_EXACT_STAGE_TIMES = 1u << 0, /* evaluate stage s at t+c_s*h instead of the reference's t+h */
+    N4J_FLAG_NO_GRAPH = 1u << 1,          /* debug: drive the step loop from the host (one sync per trial) instead
+                                             of the device-side CUDA-graph while loop */
+    N4J_FLAG_FAST_TF32 = 1u << 2,         /* single-pass TF32 tensor-core contractions (default: 3xTF32, fp32 parity) */
+    N4J_FLAG_EXACT_CONTRACTIONS = 1u << 3 /* parity mode: every dense/conv contraction accumulates exact fp32 products in
+                                             double and rounds once (order-independent, bit-comparable with the CPU oracle);
+                                             about 2x slower than the default fp32-accumulating kernels */
+};
+
+typedef struct n4j_solver_cfg {
+    double abs_tol, rel_tol, min_step, max_step;
+    double safety, max_growth, min_reduction; /* 0.9, 10, 0.2 */
+    int32_t order;                            /* 5 (DormandPrince54Solver.java:100) */
+    uint32_t flags;                           /* N4J_FLAG_* */
+    int64_t max_trials;                       /* per solve; 0 = default guard (100000) */
+} n4j_solver_cfg;
+
+/* ---- observable side channels: nfe (ForwardPass.java:42), accepted steps (StepListener.step) ---- */
+typedef struct n4j_stats {
+    int64_t nfe;      /* RHS evaluations as the reference counts them: 3 + 6*trials per solve (+1 per time-grad dot) */
+    int64_t accepted; /* accepted steps == StepListener.step callbacks */
+    int64_t rejected;
+    int64_t solves;   /* integrate() calls (segments) */
+    float last_h, last_err;
+    float gpu_ms;      /* device time of the call (CUDA events on the engine's stream) */
+    int32_t gpu_launches; /* kernels this call launched (graph bodies counted per executed iteration) */
+} n4j_stats;
+
+typedef struct n4j_step_rec { /* one entry per TRIAL step, in order */
+    float t;  /* solver time after the trial (advanced only if accepted) */
+    float h;  /* step size that was tried */
+    float err;
+    int32_t accepted;
+} n4j_step_rec;
+
+enum { N4J_TIMEGRAD_NONE = 0, /* FixedStep: NoTimeGrad.java:26-28 */
+       N4J_TIMEGRAD_ZERO = 1, /* InputStep(needTimeGradient=false): ZeroTimeGrad.java:45-55 */
+       N4J_TIMEGRAD_CALC = 2  /* InputStep(needTimeGradient=true):  CalcTimeGrad.java:52-74 */ };
+
+typedef struct n4j_handle n4j_handle;
+
+/* Library / device probes (no compute). */
+int32_t node4j_abi_version(void);
+const char* node4j_last_error(void);
+int32_t node4j_device_count(void);
+
+/* Replaces OdeHelperForward.instantiate()/OdeHelperBackward.instantiate()
+ * (conf/helper/forward/OdeHelperForward.java:17, conf/helper/backward/OdeHelperBackward.java:17): builds the
+ * native helper pair for one OdeVertex on CUDA device `device`. */
+int32_t node4j_create(const n4j_graph_desc* graph, const n4j_solver_cfg* cfg, int32_t device, n4j_handle** out);
+int32_t node4j_destroy(n4j_handle* h);
+
+int64_t node4j_num_params(const n4j_handle* h);      /* ComputationGraph.numParams() of the inner graph */
+int64_t node4j_num_real_params(const n4j_handle* h); /* realGradientView length (GradientViewSelectionFromBlacklisted.java:50-61) */
+int64_t node4j_state_len(const n4j_handle* h);
+
+/* Binds the caller-owned flat parameter buffer shared with DL4J (OdeVertex.java:67-85, :124-129).  The buffer
+ * is re-read at every forward/backward call (the updater changes it between iterations). */
+int32_t node4j_bind_params(n4j_handle* h, const float* params, int64_t n_params);
+
+/* Replaces OdeHelperForward.solve (impl/helper/forward/FixedStep.java:20-29, InputStep.java:29-36):
+ *   nt == 2: SingleStep.solve  — out has the state's shape.
+ *   nt  > 2: MultiStep.solve   — out is [B,F,nt] or [B,nt,C,H,W] and includes z(t0); `interpolate` selects
+ *            InterpolatingMultiStepSolver (one solve + dense output) vs SingleSteppingMultiStepSolver.
+ * The result is also kept on the device as `lastOutput` for node4j_backward (OdeGraphHelper.java:129). */
+int32_t node4j_forward(n4j_handle* h, const float* y0, const float* t, int32_t nt, int32_t interpolate,
+                       float* out, n4j_stats* stats);
+
+/* Replaces OdeHelperBackward.solve (impl/helper/backward/FixedStepAdjoint.java:19-23, InputStepAdjoint.java:29-53,
+ * SingleStepAdjoint.java:37-88, MultiStepAdjoint.java:49-90).
+ *   last_output: z(t1) / all z(t_k) in node4j_forward's output layout, or NULL to use the device-resident copy
+ *                of the previous node4j_forward on this handle.
+ *   dL_dz:       loss gradient (epsilon) in the same layout as the forward output.
+ *   grad_inout:  flat gradient view [num_params]; the theta-adjoint is SEEDED from its current content
+ *                (SingleStepAdjoint.java:59-60) and the result is written back into the real-gradient slots
+ *                (:85); batchnorm mean/var slots are left untouched.
+ *   dL_dy0:      [state shape] epsilon for the vertex input.
+ *   dL_dt:       [nt] time gradient for N4J_TIMEGRAD_ZERO/CALC, may be NULL for N4J_TIMEGRAD_NONE. */
+int32_t node4j_backward(n4j_handle* h, const float* last_output, const float* dL_dz, const float* t, int32_t nt,
+                        int32_t time_grad_mode, float* grad_inout, float* dL_dy0, float* dL_dt, n4j_stats* stats);
+
+/* Replay of StepListener.step (solve/api/StepListener.java:26) for the last forward or backward call: copies up
+ * to `cap` trial records and returns the total number recorded. */
+int64_t node4j_get_step_log(n4j_handle* h, n4j_step_rec* buf, int64_t cap);
+
+/* f(z,t) and its vector-Jacobian products on their own (ForwardPass.calculateDerivative, ForwardPass.java:41-48;
+ * BackpropagateAdjoint.backPropagate, BackpropagateAdjoint.java:87-143).  dreal has num_real_params entries in
+ * realGradientView order. */
+int32_t node4j_rhs(n4j_handle* h, const float* z, float t, float* fz);
+int32_t node4j_rhs_vjp(n4j_handle* h, const float* z, float t, const float* g, float* fz, float* dz, float* dreal);
+
+/* DormandPrince54Mse.estimateMse (solve/impl/DormandPrince54Solver.java:78-93) on caller data: K is [7,n]
+ * row-major.  Exposed for the unit pins of the solver kernels and for bandwidth measurements. */
+int32_t node4j_error_norm(n4j_handle* h, const float* K, const float* y0, const float* y1, float step, int64_t n,
+                          float* err_out);
+
+/* Multi-GPU (new work; the reference is single-device): the minibatch is sharded by rows, one process per GPU.
+ * `nccl_unique_id` is the 128-byte ncclUniqueId created by rank 0 and distributed by the host framework.
+ * After this call the step controller, batchnorm statistics and parameter gradients are global. */
+int32_t node4j_comm_init(n4j_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id, int64_t global_batch);
+int32_t node4j_comm_unique_id(void* out128);
+
+/* Microbenchmark hook used by bench.py for the roofline figure: runs `iters` back-to-back trial-step solver passes
+ * (6 stage combinations + error norm, no RHS) over a state of n floats and returns the average device time of one
+ * pass in microseconds. */
+int32_t node4j_bench_solver_pass(n4j_handle* h, int64_t n, int32_t iters, float* us_per_pass);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NODE4J_H */

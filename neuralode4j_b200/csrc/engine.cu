@@ -1,0 +1,945 @@
+// engine.cu — implementation of the native ODE-block engine and its C ABI (include/node4j.h).
+//
+// Reference call stacks replaced here (all under /root/reference/src/main/java/ode):
+//   vertex/impl/helper/forward/{SingleStep,MultiStep,FixedStep,InputStep}.java     -> Engine::forward
+//   vertex/impl/helper/backward/{SingleStepAdjoint,MultiStepAdjoint,...}.java      -> Engine::backward
+//   vertex/impl/helper/forward/ForwardPass.java:41-102                             -> Engine::enqueue_rhs_fwd
+//   vertex/impl/helper/backward/BackpropagateAdjoint.java:63-143                   -> Engine::enqueue_rhs_aug
+//   solve/impl/AdaptiveRungeKuttaSolver.java:107-181                               -> Engine::run_solve (+ kernels)
+#include "engine.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace n4j {
+
+#define LAUNCH(kernel, grid, block, stream, ...)                      \
+    do {                                                              \
+        kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);        \
+        ++launches_;                                                  \
+    } while (0)
+
+static inline long long round_up4(long long n) { return (n + 3) & ~3LL; }
+
+// =====================================================================================================
+// construction / planning
+// =====================================================================================================
+Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) : device_(device), cfg_(cfg) {
+    if (!(cfg.min_step < cfg.max_step))   // SolverConfig.java:22-24
+        throw Error{N4J_ERR_INVALID_ARGUMENT, "Max step smaller than min step! Swapped arguments? max: " + std::to_string(cfg.max_step) +
+                                                  " min " + std::to_string(cfg.min_step)};
+    if (cfg_.order <= 0) cfg_.order = 5;
+    if (cfg_.safety == 0) cfg_.safety = 0.9;
+    if (cfg_.max_growth == 0) cfg_.max_growth = 10;
+    if (cfg_.min_reduction == 0) cfg_.min_reduction = 0.2;
+    if (cfg_.max_trials <= 0) cfg_.max_trials = 100000;
+    exact_ = (cfg_.flags & N4J_FLAG_EXACT_CONTRACTIONS) != 0;
+    if (g.rank != 2 && g.rank != 4) throw Error{N4J_ERR_UNSUPPORTED, "Rank not supported: " + std::to_string(g.rank)};
+    rank_ = g.rank;
+    B_ = g.shape[0];
+    if (rank_ == 2) { C_ = (int)g.shape[1]; H_ = 1; W_ = 1; }
+    else { C_ = (int)g.shape[1]; H_ = (int)g.shape[2]; W_ = (int)g.shape[3]; }
+    if (B_ <= 0 || C_ <= 0 || H_ <= 0 || W_ <= 0) throw Error{N4J_ERR_INVALID_ARGUMENT, "state shape must be positive"};
+    nz_ = B_ * C_ * H_ * W_;
+    nz_pad_ = round_up4(nz_);
+
+    int c = C_;
+    long long po = 0, go = 0;
+    max_len_ = nz_;
+    const long long rows = B_ * H_ * W_;
+    for (int i = 0; i < g.n_layers; ++i) {
+        LayerPlan lp{};
+        lp.d = g.layers[i];
+        lp.rows = rows; lp.H = H_; lp.W = W_;
+        lp.c_in = c;
+        switch (lp.d.kind) {
+            case N4J_LAYER_DENSE:
+                if (rank_ != 2) throw Error{N4J_ERR_UNSUPPORTED, "dense layer inside a convolutional ODE block is not supported"};
+                if (lp.d.n_in == 0) lp.d.n_in = c;
+                if (lp.d.n_in != c) throw Error{N4J_ERR_INVALID_ARGUMENT, "dense nIn does not match the previous layer"};
+                lp.c_out = (int)lp.d.n_out;
+                lp.p_len = lp.d.n_in * lp.d.n_out + (lp.d.has_bias ? lp.d.n_out : 0);
+                lp.g_len = lp.p_len;
+                lp.exact = lp.d.n_in <= 128 && lp.d.n_out <= 128;
+                break;
+            case N4J_LAYER_CONV3X3:
+                if (rank_ != 4) throw Error{N4J_ERR_UNSUPPORTED, "conv3x3 needs a rank-4 state"};
+                if (lp.d.n_in == 0) lp.d.n_in = c;
+                if (lp.d.n_in != c) throw Error{N4J_ERR_INVALID_ARGUMENT, "conv nIn does not match the previous layer"};
+                if (lp.d.has_bias) throw Error{N4J_ERR_UNSUPPORTED, "conv3x3 with bias is outside the native set"};
+                lp.c_out = (int)lp.d.n_out;
+                lp.p_len = lp.d.n_out * lp.d.n_in * 9;
+                lp.g_len = lp.p_len;
+                break;
+            case N4J_LAYER_BATCHNORM:
+                if (lp.d.n_out == 0) lp.d.n_out = c;
+                if (lp.d.n_out != c) throw Error{N4J_ERR_INVALID_ARGUMENT, "batchnorm size does not match the previous layer"};
+                lp.d.n_in = c;
+                lp.c_out = c;
+                lp.p_len = 4LL * c;    // gamma, beta, mean, var
+                lp.g_len = 2LL * c;    // GradientViewSelectionFromBlacklisted.java:33-37
+                if (lp.d.eps == 0.f) lp.d.eps = 1e-5f;
+                break;
+            case N4J_LAYER_ACTIVATION:
+                lp.c_out = c; lp.p_len = 0; lp.g_len = 0;
+                break;
+            default:
+                throw Error{N4J_ERR_UNSUPPORTED, "layer kind outside the native set {Dense, Convolution2D 3x3 same, BatchNormalization, Activation}"};
+        }
+        lp.in_len = rows * lp.c_in;
+        lp.out_len = rows * lp.c_out;
+        lp.p_off = po; lp.g_off = go;
+        po += lp.p_len; go += lp.g_len;
+        c = lp.c_out;
+        max_len_ = std::max(max_len_, lp.out_len);
+        L_.push_back(lp);
+    }
+    if (L_.empty()) throw Error{N4J_ERR_INVALID_ARGUMENT, "inner graph has no layers"};
+    if (c != C_) throw Error{N4J_ERR_INVALID_ARGUMENT, "inner graph must map the state shape onto itself"};
+    n_params_ = po; n_real_ = go;
+    real_pad_ = round_up4(n_real_);
+    off_a_ = nz_pad_;
+    off_theta_ = 2 * nz_pad_;
+    off_t_ = off_theta_ + real_pad_;
+    n_alloc_ = off_t_ + 4;
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        throw Error{N4J_ERR_CUDA, "no CUDA device available: the node4j engine has no CPU fallback"};
+    if (device < 0 || device >= ndev) throw Error{N4J_ERR_INVALID_ARGUMENT, "bad device index"};
+    N4J_CUDA(cudaSetDevice(device_));
+    N4J_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    N4J_CUDA(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
+    N4J_CUDA(cudaEventCreate(&ev0_));
+    N4J_CUDA(cudaEventCreate(&ev1_));
+    N4J_CUDA(cudaMalloc(&Y_, sizeof(float) * 2 * n_alloc_));
+    N4J_CUDA(cudaMalloc(&K_, sizeof(float) * 7 * n_alloc_));
+    N4J_CUDA(cudaMemsetAsync(Y_, 0, sizeof(float) * 2 * n_alloc_, stream_));
+    N4J_CUDA(cudaMemsetAsync(K_, 0, sizeof(float) * 7 * n_alloc_, stream_));
+    N4J_CUDA(cudaMalloc(&ctrl_, sizeof(Ctrl)));
+    N4J_CUDA(cudaMemsetAsync(ctrl_, 0, sizeof(Ctrl), stream_));
+    N4J_CUDA(cudaHostAlloc(&ctrl_host_, sizeof(Ctrl), cudaHostAllocDefault));
+    N4J_CUDA(cudaMalloc(&log_, sizeof(n4j_step_rec) * log_cap_));
+    max_pairs_ = 4096;
+    N4J_CUDA(cudaMalloc(&tpair_, sizeof(float) * 2 * max_pairs_));
+    N4J_CUDA(cudaHostAlloc(&tpair_host_, sizeof(float) * 2 * max_pairs_, cudaHostAllocDefault));
+    wanted_cap_ = max_pairs_;
+    N4J_CUDA(cudaMalloc(&wanted_, sizeof(float) * wanted_cap_));
+    N4J_CUDA(cudaMalloc(&dot_acc_, sizeof(double)));
+    N4J_CUDA(cudaMemsetAsync(dot_acc_, 0, sizeof(double), stream_));
+    N4J_CUDA(cudaMalloc(&tg_, sizeof(float) * 4));
+    ensure(params_, std::max<long long>(n_params_, 1));
+    ensure(gradflat_, std::max<long long>(n_params_, 1));
+    ensure(theta_tmp_, std::max<long long>(real_pad_, 4));
+    for (auto& b : gb_) ensure(b, max_len_);
+    for (size_t i = 0; i < L_.size(); ++i) {
+        LayerPlan& l = L_[i];
+        if (i + 1 < L_.size()) N4J_CUDA(cudaMalloc(&l.act, sizeof(float) * l.out_len));
+        if (l.d.kind == N4J_LAYER_CONV3X3) {
+            N4J_CUDA(cudaMalloc(&l.wf, sizeof(float) * l.p_len));
+            N4J_CUDA(cudaMalloc(&l.wb, sizeof(float) * l.p_len));
+            ensure(wpart_, 16LL * l.p_len);
+        }
+        if (l.d.kind == N4J_LAYER_BATCHNORM) {
+            const int cc = l.c_out;
+            N4J_CUDA(cudaMalloc(&l.bn.acc, sizeof(double) * 2 * cc));
+            N4J_CUDA(cudaMemsetAsync(l.bn.acc, 0, sizeof(double) * 2 * cc, stream_));
+            N4J_CUDA(cudaMalloc(&l.bn.ticket, sizeof(unsigned int)));
+            N4J_CUDA(cudaMemsetAsync(l.bn.ticket, 0, sizeof(unsigned int), stream_));
+            float* f = nullptr;
+            N4J_CUDA(cudaMalloc(&f, sizeof(float) * 4 * cc));
+            l.bn.mean = f; l.bn.invstd = f + cc; l.bn.m_dy = f + 2 * cc; l.bn.m_dyxh = f + 3 * cc;
+        }
+    }
+    N4J_CUDA(cudaStreamSynchronize(stream_));
+}
+
+Engine::~Engine() {
+    cudaSetDevice(device_);
+    if (stream_) cudaStreamSynchronize(stream_);
+    for (auto& kv : graphs_) {
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    for (auto& l : L_) {
+        cudaFree(l.act); cudaFree(l.wf); cudaFree(l.wb);
+        if (l.d.kind == N4J_LAYER_BATCHNORM) { cudaFree(l.bn.acc); cudaFree(l.bn.ticket); cudaFree(l.bn.mean); }
+    }
+    for (DevBuf* b : {&params_, &gradflat_, &zt_, &gt_, &io_, &io2_, &gb_[0], &gb_[1], &gb_[2], &theta_tmp_, &wpart_, &dldt_}) cudaFree(b->p);
+    cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_);
+    cudaFreeHost(ctrl_host_); cudaFreeHost(tpair_host_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_) cudaStreamDestroy(stream_);
+    if (stream2_) cudaStreamDestroy(stream2_);
+}
+
+// =====================================================================================================
+// small helpers
+// =====================================================================================================
+void Engine::ensure(DevBuf& b, long long n) {
+    if (b.n >= n) return;
+    if (b.p) { N4J_CUDA(cudaStreamSynchronize(stream_)); cudaFree(b.p); }
+    N4J_CUDA(cudaMalloc(&b.p, sizeof(float) * n));
+    b.n = n;
+}
+// zt_ is referenced by captured dense-output kernels: drop the cached graphs when it moves
+void Engine::ensure_zt(long long n) {
+    if (zt_.n >= n) return;
+    ensure(zt_, n);
+    have_last_output_ = false;
+    for (auto& kv : graphs_) {
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    graphs_.clear();
+}
+bool Engine::is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+void Engine::to_device(float* dst, const float* src, long long n) {
+    N4J_CUDA(cudaMemcpyAsync(dst, src, sizeof(float) * n, cudaMemcpyDefault, stream_));
+}
+void Engine::from_device(float* dst, const float* src, long long n) {
+    N4J_CUDA(cudaMemcpyAsync(dst, src, sizeof(float) * n, cudaMemcpyDefault, stream_));
+}
+int Engine::grid_for(long long n, int per_thread) const {
+    long long blocks = (n + 256LL * per_thread - 1) / (256LL * per_thread);
+    blocks = std::max<long long>(1, std::min<long long>(blocks, 148LL * 8));
+    return (int)blocks;
+}
+SolverParams Engine::solver_params(long long n_norm) const {
+    SolverParams p;
+    p.atol = (float)cfg_.abs_tol; p.rtol = (float)cfg_.rel_tol;
+    p.hmin = (float)cfg_.min_step; p.hmax = (float)cfg_.max_step;
+    p.safety = (float)cfg_.safety; p.max_growth = (float)cfg_.max_growth; p.min_reduction = (float)cfg_.min_reduction;
+    p.order = cfg_.order; p.flags = cfg_.flags;
+    p.n_norm = n_norm; p.max_trials = cfg_.max_trials; p.log_cap = log_cap_;
+    return p;
+}
+
+void Engine::bind_params(const float* p, long long n) {
+    if (n != n_params_) throw Error{N4J_ERR_INVALID_ARGUMENT, "parameter vector has " + std::to_string(n) + " entries, inner graph needs " + std::to_string(n_params_)};
+    user_params_ = p;
+}
+
+// re-read the caller's flat parameter buffer (the updater changes it between iterations) and derive the
+// internal conv layouts
+void Engine::upload_params() {
+    if (n_params_ == 0) return;
+    if (!user_params_) throw Error{N4J_ERR_ILLEGAL_STATE, "parameters not bound (node4j_bind_params)"};
+    to_device(params_.p, user_params_, n_params_);
+    for (auto& l : L_)
+        if (l.d.kind == N4J_LAYER_CONV3X3)
+            LAUNCH(k_conv_w_to_internal, grid_for(l.p_len), 256, stream_, params_.p + l.p_off, l.wf, l.wb, l.c_out, l.c_in);
+}
+
+void Engine::state_in(const float* user, float* internal) {
+    if (rank_ == 2) { to_device(internal, user, nz_); return; }
+    ensure(io2_, nz_);
+    to_device(io2_.p, user, nz_);
+    LAUNCH(k_nchw_to_nhwc, grid_for(nz_), 256, stream_, io2_.p, internal, (int)B_, C_, H_ * W_);
+}
+void Engine::state_out(const float* internal, float* user_dev) {
+    if (rank_ == 2) { N4J_CUDA(cudaMemcpyAsync(user_dev, internal, sizeof(float) * nz_, cudaMemcpyDeviceToDevice, stream_)); return; }
+    LAUNCH(k_nhwc_to_nchw, grid_for(nz_), 256, stream_, internal, user_dev, (int)B_, C_, H_ * W_);
+}
+void Engine::theta_flat_to_internal(const float* flat, float* theta) {
+    for (auto& l : L_) {
+        if (l.g_len == 0) continue;
+        if (l.d.kind == N4J_LAYER_CONV3X3) LAUNCH(k_conv_g_flat_to_internal, grid_for(l.g_len), 256, stream_, flat + l.p_off, theta + l.g_off, l.c_out, l.c_in);
+        else N4J_CUDA(cudaMemcpyAsync(theta + l.g_off, flat + l.p_off, sizeof(float) * l.g_len, cudaMemcpyDeviceToDevice, stream_));
+    }
+}
+void Engine::theta_internal_to_flat(const float* theta, float* flat) {
+    for (auto& l : L_) {
+        if (l.g_len == 0) continue;
+        if (l.d.kind == N4J_LAYER_CONV3X3) LAUNCH(k_conv_g_internal_to_flat, grid_for(l.g_len), 256, stream_, theta + l.g_off, flat + l.p_off, l.c_out, l.c_in);
+        else N4J_CUDA(cudaMemcpyAsync(flat + l.p_off, theta + l.g_off, sizeof(float) * l.g_len, cudaMemcpyDeviceToDevice, stream_));
+    }
+}
+void Engine::theta_internal_to_real(const float* theta, float* real) {
+    for (auto& l : L_) {
+        if (l.g_len == 0) continue;
+        if (l.d.kind == N4J_LAYER_CONV3X3) LAUNCH(k_conv_g_internal_to_flat, grid_for(l.g_len), 256, stream_, theta + l.g_off, real + l.g_off, l.c_out, l.c_in);
+        else N4J_CUDA(cudaMemcpyAsync(real + l.g_off, theta + l.g_off, sizeof(float) * l.g_len, cudaMemcpyDeviceToDevice, stream_));
+    }
+}
+
+// =====================================================================================================
+// RHS: f(z,t) and the augmented dynamics
+// =====================================================================================================
+static inline Ref with_off(Ref r, long long off) { r.off += off; return r; }
+
+template <int MODE>
+static void launch_gemm(cudaStream_t s, GemmArgs g, int& launches, bool exact) {
+    if (exact) g.splits = 1;   // double accumulation is only order-independent inside one accumulator chain
+    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.splits);
+    if (exact) k_gemm_tiled<MODE, double><<<grid, 256, 0, s>>>(g);
+    else k_gemm_tiled<MODE, float><<<grid, 256, 0, s>>>(g);
+    ++launches;
+}
+
+void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out) {
+    Ref cur = in;
+    for (size_t i = 0; i < L_.size(); ++i) {
+        LayerPlan& l = L_[i];
+        Ref dst = (i + 1 == L_.size()) ? out : fixed_ref(l.act);
+        switch (l.d.kind) {
+            case N4J_LAYER_DENSE: {
+                const float* Wt = params_.p + l.p_off;
+                const float* bias = l.d.has_bias ? Wt + l.d.n_in * l.d.n_out : nullptr;
+                if (l.exact) {
+                    LAUNCH(k_dense_fwd_exact, grid_for(l.out_len), 256, s, cur, dst, Wt, bias, l.d.activation, l.rows, l.c_in, l.c_out);
+                } else {
+                    GemmArgs g{}; g.a = cur; g.c = dst; g.w = Wt; g.bias = bias; g.M = (int)l.rows; g.N = l.c_out; g.K = l.c_in;
+                    g.act = l.d.activation; g.splits = 1;
+                    launch_gemm<G_DENSE_FWD>(s, g, launches_, exact_);
+                }
+                break;
+            }
+            case N4J_LAYER_CONV3X3: {
+                GemmArgs g{}; g.a = cur; g.c = dst; g.w = l.wf; g.M = (int)l.rows; g.N = l.c_out; g.K = 9 * l.c_in;
+                g.act = l.d.activation; g.H = l.H; g.W = l.W; g.Ci = l.c_in; g.Co = l.c_out; g.splits = 1;
+                launch_gemm<G_CONV_FWD>(s, g, launches_, exact_);
+                break;
+            }
+            case N4J_LAYER_BATCHNORM: {
+                const int cc = l.c_out;
+                const bool vec = (cc % 4 == 0) && (256 % (cc / 4) == 0) && (cc / 4 <= 256);
+                if (vec) {
+                    const int rows_per_iter = 256 / (cc / 4);
+                    int grid = (int)std::max<long long>(1, std::min<long long>(148, (l.rows + rows_per_iter - 1) / rows_per_iter));
+                    LAUNCH(k_bn_stats, grid, 256, s, cur, l.rows, cc, l.d.eps, l.bn);
+                } else {
+                    LAUNCH(k_bn_stats_generic, cc, 256, s, cur, l.rows, cc, l.d.eps, l.bn);
+                }
+                LAUNCH(k_bn_apply, grid_for(l.out_len), 256, s, cur, dst, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn, l.d.activation, l.rows, cc);
+                break;
+            }
+            case N4J_LAYER_ACTIVATION:
+                LAUNCH(k_act_fwd, grid_for(l.out_len), 256, s, cur, dst, l.d.activation, l.out_len);
+                break;
+        }
+        cur = dst;
+    }
+}
+
+// BackpropagateAdjoint.calculateDerivative :63-85 on the layout [z | a | theta | a_t]:
+//   out.z <- f(z,t);  out.a <- (-a)^T df/dz;  out.theta <- (-a)^T df/dtheta;  out.a_t stays 0 (NoTimeInput.java:26-29)
+void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out) {
+    enqueue_rhs_fwd(s, in, out);
+    Ref g = with_off(in, off_a_);
+    float gscale = -1.f;                                 // zAdjoint().negi() :75
+    int gi = 0;
+    const int last = (int)L_.size() - 1;
+    for (int i = last; i >= 0; --i) {
+        LayerPlan& l = L_[i];
+        Ref x = i == 0 ? in : fixed_ref(L_[i - 1].act);
+        Ref y = i == last ? out : fixed_ref(l.act);
+        Ref dx = i == 0 ? with_off(out, off_a_) : fixed_ref(gb_[gi].p);
+        Ref dth = with_off(out, off_theta_ + l.g_off);
+        switch (l.d.kind) {
+            case N4J_LAYER_BATCHNORM: {
+                const int cc = l.c_out;
+                int grid = (cc <= 256 && 256 % cc == 0) ? (int)std::max<long long>(1, std::min<long long>(148, (l.rows + 256 / cc - 1) / (256 / cc))) : 148;
+                LAUNCH(k_bn_bwd_stats, grid, 256, s, g, gscale, y, x, l.bn, l.d.activation, l.rows, cc, dth, with_off(dth, cc));
+                LAUNCH(k_bn_bwd_dx, grid_for(l.in_len), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, l.rows, cc, dx);
+                break;
+            }
+            case N4J_LAYER_ACTIVATION:
+                LAUNCH(k_act_bwd, grid_for(l.out_len), 256, s, g, gscale, y, l.d.activation, dx, l.out_len);
+                break;
+            case N4J_LAYER_DENSE:
+            case N4J_LAYER_CONV3X3: {
+                Ref d = g;
+                if (l.d.activation != N4J_ACT_IDENTITY || gscale != 1.f) {
+                    d = fixed_ref(gb_[2].p);
+                    LAUNCH(k_act_bwd, grid_for(l.out_len), 256, s, g, gscale, y, l.d.activation, d, l.out_len);
+                }
+                if (l.d.kind == N4J_LAYER_DENSE) {
+                    const float* Wt = params_.p + l.p_off;
+                    if (l.exact) {
+                        LAUNCH(k_dense_wgrad_exact, grid_for(l.g_len), 256, s, x, d, dth, l.rows, l.c_in, l.c_out, l.d.has_bias);
+                        LAUNCH(k_dense_dgrad_exact, grid_for(l.in_len), 256, s, d, Wt, dx, l.rows, l.c_in, l.c_out);
+                    } else {
+                        GemmArgs w{}; w.a = d; w.b = x; w.c = dth; w.M = l.c_out; w.N = l.c_in; w.K = (int)l.rows; w.splits = 1;
+                        launch_gemm<G_DENSE_WGRAD>(s, w, launches_, exact_);
+                        if (l.d.has_bias) LAUNCH(k_colsum, grid_for(l.c_out), 256, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
+                        GemmArgs q{}; q.a = d; q.c = dx; q.w = Wt; q.M = (int)l.rows; q.N = l.c_in; q.K = l.c_out; q.splits = 1;
+                        launch_gemm<G_DENSE_DGRAD>(s, q, launches_, exact_);
+                    }
+                } else {
+                    GemmArgs w{}; w.a = x; w.b = d; w.c = fixed_ref(wpart_.p); w.M = 9 * l.c_in; w.N = l.c_out; w.K = (int)l.rows;
+                    w.H = l.H; w.W = l.W; w.Ci = l.c_in; w.Co = l.c_out; w.splits = 16;
+                    if (exact_) w.c = dth;
+                    launch_gemm<G_CONV_WGRAD>(s, w, launches_, exact_);
+                    if (!exact_) LAUNCH(k_splitk_reduce, grid_for(l.g_len), 256, s, wpart_.p, dth, l.g_len, 16);
+                    GemmArgs q{}; q.a = d; q.c = dx; q.w = l.wb; q.M = (int)l.rows; q.N = l.c_in; q.K = 9 * l.c_out;
+                    q.H = l.H; q.W = l.W; q.Ci = l.c_in; q.Co = l.c_out; q.splits = 1;
+                    launch_gemm<G_CONV_DGRAD>(s, q, launches_, exact_);
+                }
+                break;
+            }
+        }
+        g = dx; gscale = 1.f;
+        gi ^= 1;
+    }
+}
+
+// =====================================================================================================
+// the solve: prologue (K0, initial step), trial body (6 stages + error/controller), epilogue
+// =====================================================================================================
+void Engine::enqueue_prologue(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt) {
+    Ref ycur{Y_, &ctrl_->y_cur, n_alloc_, 0, 0};
+    Ref ywork{Y_, &ctrl_->y_cur, n_alloc_, 0, 1};
+    LAUNCH(k_solve_begin, 1, 32, s, ctrl_, tpair_);
+    if (dense_out) LAUNCH(k_dense_edge, grid_for(nz_), 256, s, ctrl_, Y_, n_alloc_, nz_, wanted_, 0, 0, zt_.p + nz_, nz_);
+    enqueue_rhs(s, aug, ycur, Ref{K_, &ctrl_->krow[0], n_alloc_, 0, 0});            // AdaptiveRungeKuttaSolver.java:131
+    LAUNCH(k_init_sums, grid_for(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp);
+    LAUNCH(k_stage_combine<0>, grid_for(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4);  // equation.step(ones(1), step)
+    enqueue_rhs(s, aug, ywork, Ref{K_, &ctrl_->krow[1], n_alloc_, 0, 0});           // policy :112
+    LAUNCH(k_init_final, grid_for(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp, (cudaGraphConditionalHandle)0, 0);
+    (void)nt;
+}
+
+template <int S>
+static void launch_combine(cudaStream_t s, int grid, Ctrl* c, float* Y, float* K, long long stride, long long n4) {
+    k_stage_combine<S><<<grid, 256, 0, s>>>(c, Y, K, stride, n4);
+}
+
+void Engine::enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt,
+                           cudaGraphConditionalHandle cond, int use_cond) {
+    Ref ywork{Y_, &ctrl_->y_cur, n_alloc_, 0, 1};
+    const int grid = grid_for(n4);
+    for (int st = 1; st <= 6; ++st) {
+        switch (st) {
+            case 1: launch_combine<1>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
+            case 2: launch_combine<2>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
+            case 3: launch_combine<3>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
+            case 4: launch_combine<4>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
+            case 5: launch_combine<5>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
+            case 6: launch_combine<6>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
+        }
+        ++launches_;
+        enqueue_rhs(s, aug, ywork, Ref{K_, &ctrl_->krow[st], n_alloc_, 0, 0});
+    }
+    DenseOutArgs dout{dense_out ? wanted_ : nullptr, dense_out ? nt - 1 : 0};
+    LAUNCH(k_error_ctrl, grid, 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp, log_, dout, cond, use_cond);
+    if (dense_out) LAUNCH(k_dense_output, grid_for(nz_), 256, s, ctrl_, Y_, K_, n_alloc_, nz_, wanted_, zt_.p + nz_, nz_);
+}
+
+void Engine::enqueue_epilogue(cudaStream_t s, bool dense_out, int nt) {
+    if (dense_out) LAUNCH(k_dense_edge, grid_for(nz_), 256, s, ctrl_, Y_, n_alloc_, nz_, wanted_, nt - 2, 1, zt_.p + nz_, nz_);
+}
+
+SolveGraph& Engine::get_graph(bool aug, int tslot, bool dense_out, int nt) {
+    const long long key = (aug ? 1 : 0) | (tslot ? 2 : 0) | (dense_out ? 4 : 0) | ((long long)(dense_out ? nt : 0) << 8);
+    auto it = graphs_.find(key);
+    if (it != graphs_.end()) return it->second;
+    SolveGraph sg;
+    const long long n4 = (aug ? n_alloc_ : nz_pad_) / 4;
+    const long long n_norm = aug ? (2 * nz_ + n_params_ + (tslot ? 1 : 0)) : nz_;
+    const SolverParams sp = solver_params(n_norm);
+    const int saved = launches_;
+
+    N4J_CUDA(cudaGraphCreate(&sg.graph, 0));
+    // prologue as a child graph
+    cudaGraph_t pro = nullptr, epi = nullptr;
+    launches_ = 0;
+    N4J_CUDA(cudaStreamBeginCapture(stream2_, cudaStreamCaptureModeRelaxed));
+    enqueue_prologue(stream2_, aug, n4, sp, dense_out, nt);
+    N4J_CUDA(cudaStreamEndCapture(stream2_, &pro));
+    sg.prologue_launches = launches_;
+    cudaGraphNode_t pro_node = nullptr;
+    N4J_CUDA(cudaGraphAddChildGraphNode(&pro_node, sg.graph, nullptr, 0, pro));
+
+    // WHILE node: body = one trial step; the controller (last block of k_error_ctrl) sets the condition
+    cudaGraphConditionalHandle cond;
+    N4J_CUDA(cudaGraphConditionalHandleCreate(&cond, sg.graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.type = cudaGraphNodeTypeConditional;
+    cp.conditional.handle = cond;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t while_node = nullptr;
+    N4J_CUDA(cudaGraphAddNode(&while_node, sg.graph, &pro_node, 1, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    launches_ = 0;
+    N4J_CUDA(cudaStreamBeginCaptureToGraph(stream2_, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed));
+    enqueue_trial(stream2_, aug, n4, sp, dense_out, nt, cond, 1);
+    N4J_CUDA(cudaStreamEndCapture(stream2_, nullptr));
+    sg.body_launches = launches_;
+
+    launches_ = 0;
+    if (dense_out) {
+        N4J_CUDA(cudaStreamBeginCapture(stream2_, cudaStreamCaptureModeRelaxed));
+        enqueue_epilogue(stream2_, dense_out, nt);
+        N4J_CUDA(cudaStreamEndCapture(stream2_, &epi));
+        cudaGraphNode_t epi_node = nullptr;
+        N4J_CUDA(cudaGraphAddChildGraphNode(&epi_node, sg.graph, &while_node, 1, epi));
+    }
+    sg.epilogue_launches = launches_;
+    launches_ = saved;
+    N4J_CUDA(cudaGraphInstantiate(&sg.exec, sg.graph, 0));
+    if (pro) cudaGraphDestroy(pro);
+    if (epi) cudaGraphDestroy(epi);
+    return graphs_.emplace(key, sg).first->second;
+}
+
+// One FirstOrderSolver.integrate(): state in Y[y_cur], time pair taken from tpair_[ctrl.seg_index++].
+void Engine::run_solve(bool aug, int tslot, bool dense_out, int nt) {
+    if (!(cfg_.flags & N4J_FLAG_NO_GRAPH)) {
+        SolveGraph& sg = get_graph(aug, tslot, dense_out, nt);
+        N4J_CUDA(cudaGraphLaunch(sg.exec, stream_));
+        pending_graph_runs_.push_back({&sg, 0});
+        return;
+    }
+    // debug path: the host drives the loop and reads `done` after every trial
+    const long long n4 = (aug ? n_alloc_ : nz_pad_) / 4;
+    const long long n_norm = aug ? (2 * nz_ + n_params_ + (tslot ? 1 : 0)) : nz_;
+    const SolverParams sp = solver_params(n_norm);
+    enqueue_prologue(stream_, aug, n4, sp, dense_out, nt);
+    for (;;) {
+        N4J_CUDA(cudaMemcpyAsync(ctrl_host_, ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_));
+        N4J_CUDA(cudaStreamSynchronize(stream_));
+        if (ctrl_host_->done) break;
+        enqueue_trial(stream_, aug, n4, sp, dense_out, nt, (cudaGraphConditionalHandle)0, 0);
+    }
+    enqueue_epilogue(stream_, dense_out, nt);
+}
+
+__global__ void k_reset_ctrl(Ctrl* c) {
+    if (threadIdx.x == 0) {
+        c->y_cur = 0; c->status = 0; c->log_n = 0; c->seg_index = 0;
+        c->nfe = 0; c->accepted = 0; c->rejected = 0; c->solves = 0; c->trials = 0;
+        c->acc[0] = c->acc[1] = c->acc[2] = c->acc[3] = 0.0;
+        c->ticket[0] = c->ticket[1] = c->ticket[2] = c->ticket[3] = 0u;
+        c->done = 0; c->err = 0.f; c->h = 0.f;
+    }
+}
+
+void Engine::reset_ctrl() {
+    launches_ = 0;
+    pending_graph_runs_.clear();
+    N4J_CUDA(cudaEventRecord(ev0_, stream_));
+    LAUNCH(k_reset_ctrl, 1, 32, stream_, ctrl_);
+}
+
+void Engine::set_time_pairs(const std::vector<float>& pairs) {
+    if ((int)pairs.size() / 2 > max_pairs_) throw Error{N4J_ERR_UNSUPPORTED, "too many time points"};
+    std::memcpy(tpair_host_, pairs.data(), sizeof(float) * pairs.size());
+    N4J_CUDA(cudaMemcpyAsync(tpair_, tpair_host_, sizeof(float) * pairs.size(), cudaMemcpyHostToDevice, stream_));
+}
+
+void Engine::finish_call(n4j_stats* st, int) {
+    N4J_CUDA(cudaMemcpyAsync(ctrl_host_, ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_));
+    N4J_CUDA(cudaEventRecord(ev1_, stream_));
+    N4J_CUDA(cudaStreamSynchronize(stream_));
+    const Ctrl& c = *ctrl_host_;
+    log_count_ = c.log_n;
+    int launches = launches_;
+    if (!pending_graph_runs_.empty()) {
+        SolveGraph* sg = pending_graph_runs_[0].first;
+        launches += (int)pending_graph_runs_.size() * (sg->prologue_launches + sg->epilogue_launches) + (int)c.trials * sg->body_launches;
+    }
+    if (st) {
+        st->nfe = c.nfe; st->accepted = c.accepted; st->rejected = c.rejected; st->solves = c.solves;
+        st->last_h = c.h; st->last_err = c.err;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0_, ev1_);
+        st->gpu_ms = ms;
+        st->gpu_launches = launches;
+    }
+    if (c.status == N4J_ERR_ILLEGAL_STATE) throw Error{N4J_ERR_ILLEGAL_STATE, "Detected NaN!"};   // NanWatchSolver.java:22
+    if (c.status == N4J_ERR_MAX_STEPS) throw Error{N4J_ERR_MAX_STEPS, "step guard tripped: " + std::to_string(cfg_.max_trials) + " trial steps in one solve"};
+}
+
+// =====================================================================================================
+// forward: SingleStep.solve / MultiStep.solve
+// =====================================================================================================
+void Engine::forward(const float* y0, const float* t, int nt, int interpolate, float* out, n4j_stats* st) {
+    N4J_CUDA(cudaSetDevice(device_));
+    if (nt < 2) throw Error{N4J_ERR_INVALID_ARGUMENT, "time must be size 2! Was: " + std::to_string(nt)};
+    if (nt - 1 > max_pairs_) throw Error{N4J_ERR_UNSUPPORTED, "too many time points"};
+    std::vector<float> th(nt);
+    if (is_device_ptr(t)) N4J_CUDA(cudaMemcpy(th.data(), t, sizeof(float) * nt, cudaMemcpyDeviceToHost));
+    else std::memcpy(th.data(), t, sizeof(float) * nt);
+    reset_ctrl();
+    upload_params();
+    ensure_zt((long long)nt * nz_);
+    ensure(io_, (long long)nt * nz_);
+    // Y[0] <- y0 (internal layout); zt_[0] keeps z(t0) for the multi-time output (MultiStep.java:49-60)
+    state_in(y0, zt_.p);
+    N4J_CUDA(cudaMemcpyAsync(Y_, zt_.p, sizeof(float) * nz_, cudaMemcpyDeviceToDevice, stream_));
+    if (nz_pad_ != nz_) N4J_CUDA(cudaMemsetAsync(Y_ + nz_, 0, sizeof(float) * (nz_pad_ - nz_), stream_));
+    const bool dev_out = is_device_ptr(out);
+    if (nt == 2) {
+        set_time_pairs({th[0], th[1]});
+        run_solve(false, 0, false, nt);
+        LAUNCH(k_copy_from_state, grid_for(nz_), 256, stream_, ctrl_, Y_, n_alloc_, 0LL, zt_.p, nz_);   // lastOutput (OdeGraphHelper.java:129)
+        float* o = dev_out ? out : io_.p;
+        state_out(zt_.p, o);
+        if (!dev_out) from_device(out, io_.p, nz_);
+    } else {
+        if (interpolate) {
+            // InterpolatingMultiStepSolver.integrate :28-47
+            N4J_CUDA(cudaMemcpyAsync(wanted_, th.data() + 1, sizeof(float) * (nt - 1), cudaMemcpyHostToDevice, stream_));
+            N4J_CUDA(cudaStreamSynchronize(stream_));   // th is pageable
+            set_time_pairs({th[0], th[nt - 1]});
+            run_solve(false, 0, true, nt);
+        } else {
+            // SingleSteppingMultiStepSolver.integrate :26-43
+            std::vector<float> pairs;
+            for (int k = 1; k < nt; ++k) { pairs.push_back(th[k - 1]); pairs.push_back(th[k]); }
+            set_time_pairs(pairs);
+            for (int k = 1; k < nt; ++k) {
+                run_solve(false, 0, false, nt);
+                LAUNCH(k_copy_from_state, grid_for(nz_), 256, stream_, ctrl_, Y_, n_alloc_, 0LL, zt_.p + (long long)k * nz_, nz_);
+            }
+        }
+        float* o = dev_out ? out : io_.p;
+        LAUNCH(k_timefirst_to_ref, grid_for((long long)nt * nz_), 256, stream_, zt_.p, o, nt, (int)B_, C_, H_ * W_, rank_ == 4 ? 1 : 0);
+        if (!dev_out) from_device(out, io_.p, (long long)nt * nz_);
+    }
+    have_last_output_ = true;
+    last_nt_ = nt;
+    finish_call(st, 0);
+}
+
+// =====================================================================================================
+// backward: SingleStepAdjoint.solve / MultiStepAdjoint.solve with the timegrad.* variants
+// =====================================================================================================
+__global__ void k_tg_step(Ctrl* c, double* dot_acc, float* tg, float* Ybase, long long stride, long long off_t, float* dLdt, int step, int phase) {
+    if (threadIdx.x != 0) return;
+    float* y = Ybase + (long long)c->y_cur * stride;
+    if (phase == 0) {            // CalcTimeGrad.calcTimeAdjointT1 :52-58: lastTime -= <dL/dz(t1), f(z(t1))>; a_t := lastTime
+        const float d = (float)(*dot_acc);
+        *dot_acc = 0.0;
+        tg[0] = __fsub_rn(tg[0], d);
+        tg[1] = d;
+        y[off_t] = tg[0];
+        c->nfe += 1;
+    } else if (phase == 1) {     // CalcTimeGrad.createLossGradient :66-74 + CalcMultiStepTimeGrad.updateStep :51-53
+        dLdt[step - 1] = y[off_t];
+        dLdt[step] = tg[1];
+    } else if (phase == 2) {     // CalcMultiStepTimeGrad.updateLastStep :56-62
+        dLdt[0] = tg[0];
+    } else if (phase == 3) {     // start of a backward call
+        tg[0] = 0.f; tg[1] = 0.f;
+    }
+}
+// a-slot of the state: a <- g (first segment) or a <- g + a (MultiStepTimeGrad.prepareStep)
+__global__ void __launch_bounds__(256) k_adjoint_seed(const Ctrl* __restrict__ c, float* __restrict__ Ybase, long long stride, long long off,
+                                                       const float* __restrict__ g, const float* __restrict__ g2, int add_self, long long n) {
+    float* __restrict__ a = Ybase + (long long)c->y_cur * stride + off;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        float v = g[i];
+        if (add_self) v = __fadd_rn(v, a[i]);
+        if (g2) v = __fadd_rn(v, g2[i]);
+        a[i] = v;
+    }
+}
+__global__ void __launch_bounds__(256) k_add_out(const Ctrl* __restrict__ c, const float* __restrict__ Ybase, long long stride, long long off,
+                                                  const float* __restrict__ add, float* __restrict__ dst, long long n) {
+    const float* __restrict__ a = Ybase + (long long)c->y_cur * stride + off;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) dst[i] = add ? __fadd_rn(a[i], add[i]) : a[i];
+}
+
+void Engine::backward(const float* last_output, const float* dLdz, const float* t, int nt, int tg_mode, float* grad_inout,
+                      float* dLdy0, float* dLdt, n4j_stats* st) {
+    N4J_CUDA(cudaSetDevice(device_));
+    if (nt < 2) throw Error{N4J_ERR_INVALID_ARGUMENT, "time must be size 2! Was: " + std::to_string(nt)};
+    if (nt - 1 > max_pairs_) throw Error{N4J_ERR_UNSUPPORTED, "too many time points"};
+    std::vector<float> th(nt);
+    if (is_device_ptr(t)) N4J_CUDA(cudaMemcpy(th.data(), t, sizeof(float) * nt, cudaMemcpyDeviceToHost));
+    else std::memcpy(th.data(), t, sizeof(float) * nt);
+    if (nt > 2) {   // MultiStepAdjoint.assertSorted :41-46
+        int sgn = 0;
+        for (int i = 0; i + 1 < nt; ++i) sgn += (th[i] > th[i + 1]) - (th[i] < th[i + 1]);
+        if (std::abs(sgn) + 1 != nt) throw Error{N4J_ERR_INVALID_ARGUMENT, "Time must be in ascending or descending order!"};
+    }
+    if (!last_output && (!have_last_output_ || last_nt_ != nt))
+        throw Error{N4J_ERR_ILLEGAL_STATE, "backward without last_output needs a preceding forward with the same time vector length"};
+    if (tg_mode != N4J_TIMEGRAD_NONE && !dLdt) throw Error{N4J_ERR_INVALID_ARGUMENT, "dL_dt buffer required for this time-gradient mode"};
+    const bool tg = tg_mode == N4J_TIMEGRAD_CALC;
+    const int tslot = tg ? 1 : 0;
+    const long long T = nt == 2 ? 1 : nt;          // stored time slices
+    reset_ctrl();
+    upload_params();
+    ensure_zt(std::max<long long>(T, 2) * nz_);
+    ensure(gt_, T * nz_);
+    ensure(io_, T * nz_);
+    ensure(dldt_, nt);
+    // --- inputs to the internal, time-first layout ----------------------------------------------------
+    if (nt == 2) {
+        if (last_output) state_in(last_output, zt_.p);
+        state_in(dLdz, gt_.p);
+    } else {
+        if (last_output) {
+            to_device(io_.p, last_output, T * nz_);
+            LAUNCH(k_ref_to_timefirst, grid_for(T * nz_), 256, stream_, io_.p, zt_.p, nt, (int)B_, C_, H_ * W_, rank_ == 4 ? 1 : 0);
+        }
+        to_device(io_.p, dLdz, T * nz_);
+        LAUNCH(k_ref_to_timefirst, grid_for(T * nz_), 256, stream_, io_.p, gt_.p, nt, (int)B_, C_, H_ * W_, rank_ == 4 ? 1 : 0);
+    }
+    // --- theta-adjoint seeded from the gradient view (SingleStepAdjoint.java:59-60) --------------------
+    N4J_CUDA(cudaMemsetAsync(Y_, 0, sizeof(float) * 2 * n_alloc_, stream_));
+    if (n_params_ > 0) {
+        to_device(gradflat_.p, grad_inout, n_params_);
+        theta_flat_to_internal(gradflat_.p, Y_ + off_theta_);     // y_cur == 0 after reset
+    }
+    LAUNCH(k_tg_step, 1, 32, stream_, ctrl_, dot_acc_, tg_, Y_, n_alloc_, off_t_, dldt_.p, 0, 3);
+    if (dLdt) N4J_CUDA(cudaMemsetAsync(dldt_.p, 0, sizeof(float) * nt, stream_));
+
+    // time pairs, reversed (Nd4j.reverse(time) :81), one per segment from the last to the first
+    std::vector<float> pairs;
+    for (int step = nt - 1; step > 0; --step) { pairs.push_back(th[step]); pairs.push_back(th[step - 1]); }
+    set_time_pairs(pairs);
+
+    bool have_prev = false;
+    for (int step = nt - 1; step > 0; --step) {
+        const long long slice = nt == 2 ? 0 : step;
+        const float* z_k = zt_.p + slice * nz_;
+        const float* g_k = gt_.p + slice * nz_;
+        if (tg) {
+            // d = <dL/dz(t_step) raw, f(z(t_step), t_step)>: one extra RHS evaluation
+            enqueue_rhs_fwd(stream_, fixed_ref(const_cast<float*>(z_k)), fixed_ref(gb_[2].p));
+            LAUNCH(k_dot, grid_for(nz_), 256, stream_, g_k, gb_[2].p, nz_, dot_acc_);
+            LAUNCH(k_tg_step, 1, 32, stream_, ctrl_, dot_acc_, tg_, Y_, n_alloc_, off_t_, dldt_.p, step, 0);
+        }
+        // z-slot <- z(t_step); a-slot <- dL/dz(t_step) (+ running adjoint)
+        LAUNCH(k_copy_to_state, grid_for(nz_), 256, stream_, ctrl_, Y_, n_alloc_, 0LL, z_k, (const float*)nullptr, nz_);
+        LAUNCH(k_adjoint_seed, grid_for(nz_), 256, stream_, ctrl_, Y_, n_alloc_, off_a_, g_k, (const float*)nullptr, have_prev ? 1 : 0, nz_);
+        run_solve(true, tslot, false, nt);
+        if (tg) LAUNCH(k_tg_step, 1, 32, stream_, ctrl_, dot_acc_, tg_, Y_, n_alloc_, off_t_, dldt_.p, step, 1);
+        have_prev = true;
+    }
+    if (tg && nt > 2) LAUNCH(k_tg_step, 1, 32, stream_, ctrl_, dot_acc_, tg_, Y_, n_alloc_, off_t_, dldt_.p, 0, 2);
+
+    // --- outputs ---------------------------------------------------------------------------------------
+    // dL/dy0 = a(t0) (+ dL/dz(t0) for multi-time, *MultiStepTimeGrad.updateLastStep)
+    LAUNCH(k_add_out, grid_for(nz_), 256, stream_, ctrl_, Y_, n_alloc_, off_a_, nt > 2 ? gt_.p : (const float*)nullptr, gb_[0].p, nz_);
+    const bool dev_dy0 = is_device_ptr(dLdy0);
+    ensure(io2_, nz_);
+    if (rank_ == 2) {
+        from_device(dLdy0, gb_[0].p, nz_);
+    } else {
+        float* o = dev_dy0 ? dLdy0 : io_.p;
+        state_out(gb_[0].p, o);
+        if (!dev_dy0) from_device(dLdy0, io_.p, nz_);
+    }
+    if (n_params_ > 0) {
+        LAUNCH(k_copy_from_state, grid_for(real_pad_), 256, stream_, ctrl_, Y_, n_alloc_, off_theta_, theta_tmp_.p, real_pad_);
+        theta_internal_to_flat(theta_tmp_.p, gradflat_.p);     // realParamGrads.assignFrom :85 (mean/var slots untouched)
+        from_device(grad_inout, gradflat_.p, n_params_);
+    }
+    if (dLdt) from_device(dLdt, dldt_.p, nt);
+    finish_call(st, 0);
+}
+
+long long Engine::get_step_log(n4j_step_rec* buf, long long cap) {
+    N4J_CUDA(cudaSetDevice(device_));
+    const long long n = std::min<long long>(log_count_, log_cap_);
+    const long long m = std::min(n, cap);
+    if (buf && m > 0) N4J_CUDA(cudaMemcpy(buf, log_, sizeof(n4j_step_rec) * m, cudaMemcpyDeviceToHost));
+    return log_count_;
+}
+
+// =====================================================================================================
+// RHS on its own, error norm on caller data, solver-pass microbenchmark
+// =====================================================================================================
+void Engine::rhs(const float* z, float, float* fz) {
+    N4J_CUDA(cudaSetDevice(device_));
+    launches_ = 0;
+    upload_params();
+    ensure(io_, nz_);
+    state_in(z, gb_[0].p);
+    enqueue_rhs_fwd(stream_, fixed_ref(gb_[0].p), fixed_ref(gb_[1].p));
+    const bool dev = is_device_ptr(fz);
+    float* o = dev ? fz : io_.p;
+    state_out(gb_[1].p, o);
+    if (!dev) from_device(fz, io_.p, nz_);
+    N4J_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::rhs_vjp(const float* z, float, const float* g, float* fz, float* dz, float* dreal) {
+    N4J_CUDA(cudaSetDevice(device_));
+    reset_ctrl();
+    upload_params();
+    ensure(io_, std::max<long long>(nz_, n_real_));
+    // augmented state with a = -g so that the backpropagated epsilon (-a) equals g
+    N4J_CUDA(cudaMemsetAsync(Y_, 0, sizeof(float) * n_alloc_, stream_));
+    state_in(z, Y_);
+    state_in(g, gb_[0].p);
+    LAUNCH(k_act_bwd, grid_for(nz_), 256, stream_, fixed_ref(gb_[0].p), -1.f, fixed_ref(gb_[0].p), (int)N4J_ACT_IDENTITY, fixed_ref(Y_ + off_a_), nz_);
+    enqueue_rhs_aug(stream_, fixed_ref(Y_), fixed_ref(K_));
+    auto emit = [&](const float* internal, float* user) {
+        const bool dev = is_device_ptr(user);
+        float* o = dev ? user : io_.p;
+        state_out(internal, o);
+        if (!dev) { from_device(user, io_.p, nz_); N4J_CUDA(cudaStreamSynchronize(stream_)); }
+    };
+    emit(K_, fz);
+    emit(K_ + off_a_, dz);
+    if (n_real_ > 0) {
+        theta_internal_to_real(K_ + off_theta_, theta_tmp_.p);
+        from_device(dreal, theta_tmp_.p, n_real_);
+    }
+    N4J_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::error_norm(const float* K, const float* y0, const float* y1, float step, long long n, float* err_out) {
+    N4J_CUDA(cudaSetDevice(device_));
+    DevBuf k, a, b;
+    ensure(k, 7 * n); ensure(a, n); ensure(b, n);
+    to_device(k.p, K, 7 * n); to_device(a.p, y0, n); to_device(b.p, y1, n);
+    N4J_CUDA(cudaMemsetAsync(dot_acc_, 0, sizeof(double), stream_));
+    k_error_only<<<grid_for(n), 256, 0, stream_>>>(k.p, a.p, b.p, n, step, (float)cfg_.abs_tol, (float)cfg_.rel_tol, dot_acc_);
+    double sum = 0;
+    N4J_CUDA(cudaMemcpyAsync(&sum, dot_acc_, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    N4J_CUDA(cudaStreamSynchronize(stream_));
+    N4J_CUDA(cudaMemsetAsync(dot_acc_, 0, sizeof(double), stream_));
+    *err_out = (float)std::sqrt(sum / (double)n);
+    cudaFree(k.p); cudaFree(a.p); cudaFree(b.p);
+}
+
+// 6 stage combinations + error norm over n floats, no RHS: the solver's own HBM traffic (160*n bytes per pass,
+// SURVEY.md section 8d).  The controller is kept from advancing by forcing a rejection-free, non-terminating setup:
+// state and K rows are zero, so err == 0 and h stays clamped at hmax.
+void Engine::bench_solver_pass(long long n, int iters, float* us) {
+    N4J_CUDA(cudaSetDevice(device_));
+    const long long n4 = round_up4(n) / 4, stride = n4 * 4;
+    float *Y = nullptr, *K = nullptr;
+    Ctrl* c = nullptr;
+    N4J_CUDA(cudaMalloc(&Y, sizeof(float) * 2 * stride));
+    N4J_CUDA(cudaMalloc(&K, sizeof(float) * 7 * stride));
+    N4J_CUDA(cudaMalloc(&c, sizeof(Ctrl)));
+    N4J_CUDA(cudaMemsetAsync(Y, 0, sizeof(float) * 2 * stride, stream_));
+    N4J_CUDA(cudaMemsetAsync(K, 0, sizeof(float) * 7 * stride, stream_));
+    N4J_CUDA(cudaMemsetAsync(c, 0, sizeof(Ctrl), stream_));
+    Ctrl hc;
+    std::memset(&hc, 0, sizeof(hc));
+    for (int j = 0; j < 7; ++j) { hc.krow[j] = j; hc.krow_prev[j] = j; }
+    hc.h = 0.01f; hc.t_end = 1e30f;
+    N4J_CUDA(cudaMemcpyAsync(c, &hc, sizeof(Ctrl), cudaMemcpyHostToDevice, stream_));
+    SolverParams sp = solver_params(n);
+    sp.max_trials = 1LL << 60; sp.log_cap = 0;
+    const int grid = grid_for(n4);
+    auto pass = [&]() {
+        launch_combine<1>(stream_, grid, c, Y, K, stride, n4);
+        launch_combine<2>(stream_, grid, c, Y, K, stride, n4);
+        launch_combine<3>(stream_, grid, c, Y, K, stride, n4);
+        launch_combine<4>(stream_, grid, c, Y, K, stride, n4);
+        launch_combine<5>(stream_, grid, c, Y, K, stride, n4);
+        launch_combine<6>(stream_, grid, c, Y, K, stride, n4);
+        k_error_ctrl<<<grid, 256, 0, stream_>>>(c, Y, K, stride, n4, sp, nullptr, DenseOutArgs{nullptr, 0}, (cudaGraphConditionalHandle)0, 0);
+    };
+    for (int i = 0; i < 3; ++i) pass();
+    N4J_CUDA(cudaEventRecord(ev0_, stream_));
+    for (int i = 0; i < iters; ++i) pass();
+    N4J_CUDA(cudaEventRecord(ev1_, stream_));
+    N4J_CUDA(cudaStreamSynchronize(stream_));
+    float ms = 0;
+    N4J_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    *us = ms * 1000.f / (float)iters;
+    cudaFree(Y); cudaFree(K); cudaFree(c);
+}
+
+}  // namespace n4j
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+struct n4j_handle {
+    std::unique_ptr<n4j::Engine> eng;
+    std::vector<n4j_layer_desc> layers;
+};
+
+static thread_local std::string g_last_error;
+
+template <class F>
+static int32_t guarded(F&& f) {
+    try {
+        f();
+        return N4J_OK;
+    } catch (const n4j::Error& e) {
+        g_last_error = e.msg;
+        return e.code;
+    } catch (const std::exception& e) {
+        g_last_error = e.what();
+        return N4J_ERR_ILLEGAL_STATE;
+    }
+}
+
+extern "C" {
+
+int32_t node4j_abi_version(void) { return N4J_ABI_VERSION; }
+const char* node4j_last_error(void) { return g_last_error.c_str(); }
+int32_t node4j_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int32_t node4j_create(const n4j_graph_desc* graph, const n4j_solver_cfg* cfg, int32_t device, n4j_handle** out) {
+    return guarded([&] {
+        if (!graph || !cfg || !out) throw n4j::Error{N4J_ERR_INVALID_ARGUMENT, "null argument"};
+        auto h = std::make_unique<n4j_handle>();
+        h->layers.assign(graph->layers, graph->layers + graph->n_layers);
+        n4j_graph_desc g = *graph;
+        g.layers = h->layers.data();
+        h->eng.reset(new n4j::Engine(g, *cfg, device));
+        *out = h.release();
+    });
+}
+int32_t node4j_destroy(n4j_handle* h) {
+    return guarded([&] { delete h; });
+}
+int64_t node4j_num_params(const n4j_handle* h) { return h ? h->eng->num_params() : -1; }
+int64_t node4j_num_real_params(const n4j_handle* h) { return h ? h->eng->num_real() : -1; }
+int64_t node4j_state_len(const n4j_handle* h) { return h ? h->eng->state_len() : -1; }
+
+int32_t node4j_bind_params(n4j_handle* h, const float* params, int64_t n_params) {
+    return guarded([&] { h->eng->bind_params(params, n_params); });
+}
+int32_t node4j_forward(n4j_handle* h, const float* y0, const float* t, int32_t nt, int32_t interpolate, float* out, n4j_stats* stats) {
+    return guarded([&] { h->eng->forward(y0, t, nt, interpolate, out, stats); });
+}
+int32_t node4j_backward(n4j_handle* h, const float* last_output, const float* dL_dz, const float* t, int32_t nt, int32_t time_grad_mode,
+                        float* grad_inout, float* dL_dy0, float* dL_dt, n4j_stats* stats) {
+    return guarded([&] { h->eng->backward(last_output, dL_dz, t, nt, time_grad_mode, grad_inout, dL_dy0, dL_dt, stats); });
+}
+int64_t node4j_get_step_log(n4j_handle* h, n4j_step_rec* buf, int64_t cap) {
+    int64_t n = -1;
+    guarded([&] { n = h->eng->get_step_log(buf, cap); });
+    return n;
+}
+int32_t node4j_rhs(n4j_handle* h, const float* z, float t, float* fz) {
+    return guarded([&] { h->eng->rhs(z, t, fz); });
+}
+int32_t node4j_rhs_vjp(n4j_handle* h, const float* z, float t, const float* g, float* fz, float* dz, float* dreal) {
+    return guarded([&] { h->eng->rhs_vjp(z, t, g, fz, dz, dreal); });
+}
+int32_t node4j_error_norm(n4j_handle* h, const float* K, const float* y0, const float* y1, float step, int64_t n, float* err_out) {
+    return guarded([&] { h->eng->error_norm(K, y0, y1, step, n, err_out); });
+}
+int32_t node4j_comm_init(n4j_handle*, int32_t, int32_t, const void*, int64_t) {
+    g_last_error = "multi-GPU sharding is not wired up in this build";
+    return N4J_ERR_UNSUPPORTED;
+}
+int32_t node4j_comm_unique_id(void*) {
+    g_last_error = "multi-GPU sharding is not wired up in this build";
+    return N4J_ERR_UNSUPPORTED;
+}
+int32_t node4j_bench_solver_pass(n4j_handle* h, int64_t n, int32_t iters, float* us_per_pass) {
+    return guarded([&] { h->eng->bench_solver_pass(n, iters, us_per_pass); });
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+// engine.cuh — host side of the native OdeHelperForward/OdeHelperBackward pair: plans the inner graph, owns the
+// device buffers, enqueues RHS evaluations and builds the device-driven solve (CUDA graph with a WHILE node whose
+// condition the step controller sets on the GPU).
+#pragma once
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "layer_kernels.cuh"
+#include "solver_kernels.cuh"
+
+namespace n4j {
+
+struct LayerPlan {
+    n4j_layer_desc d;
+    long long rows;          // B*H*W or B
+    int c_in, c_out;         // channels / features in and out
+    int H, W;
+    long long in_len, out_len;
+    long long p_off, p_len;  // slot in the flat DL4J parameter vector
+    long long g_off, g_len;  // slot in the real-gradient vector (== slot inside the theta block of the adjoint state)
+    bool exact;              // dense: double-accumulating exact kernels
+    float* act = nullptr;    // output of this layer (scratch), unused for the last layer
+    float* wf = nullptr;     // conv: [tap][ci][co]
+    float* wb = nullptr;     // conv: [tap][co][ci]
+    BnScratch bn{};
+};
+
+struct DevBuf {
+    float* p = nullptr;
+    long long n = 0;
+};
+
+struct SolveGraph {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int prologue_launches = 0, body_launches = 0, epilogue_launches = 0;
+};
+
+class Engine {
+public:
+    Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device);
+    ~Engine();
+
+    long long num_params() const { return n_params_; }
+    long long num_real() const { return n_real_; }
+    long long state_len() const { return nz_; }
+
+    void bind_params(const float* p, long long n);
+    void forward(const float* y0, const float* t, int nt, int interpolate, float* out, n4j_stats* st);
+    void backward(const float* last_output, const float* dLdz, const float* t, int nt, int tg_mode, float* grad_inout,
+                  float* dLdy0, float* dLdt, n4j_stats* st);
+    long long get_step_log(n4j_step_rec* buf, long long cap);
+    void rhs(const float* z, float t, float* fz);
+    void rhs_vjp(const float* z, float t, const float* g, float* fz, float* dz, float* dreal);
+    void error_norm(const float* K, const float* y0, const float* y1, float step, long long n, float* err_out);
+    void bench_solver_pass(long long n, int iters, float* us);
+
+private:
+    // ---- plan ------------------------------------------------------------------------------------
+    int device_;
+    n4j_solver_cfg cfg_;
+    bool exact_ = false;       // N4J_FLAG_EXACT_CONTRACTIONS
+    std::vector<LayerPlan> L_;
+    int rank_;
+    long long B_;
+    int C_, H_, W_;            // state geometry (rank 4) or C_=F (rank 2), H_=W_=1
+    long long nz_, nz_pad_;    // state length, padded to a multiple of 4
+    long long n_params_, n_real_, real_pad_;
+    long long n_alloc_;        // floats per solver buffer (adjoint layout: z | a | theta | a_t | 0-tail)
+    long long off_a_, off_theta_, off_t_;
+    long long max_len_;        // largest activation
+
+    // ---- device state ----------------------------------------------------------------------------
+    cudaStream_t stream_ = nullptr, stream2_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    float* Y_ = nullptr;       // [2][n_alloc]
+    float* K_ = nullptr;       // [7][n_alloc]
+    Ctrl* ctrl_ = nullptr;
+    Ctrl* ctrl_host_ = nullptr;   // pinned
+    n4j_step_rec* log_ = nullptr;
+    int log_cap_ = 1 << 16;
+    std::vector<n4j_step_rec> log_host_;
+    long long log_count_ = 0;
+    float* tpair_ = nullptr;      // [max_pairs][2]
+    float* tpair_host_ = nullptr; // pinned
+    int max_pairs_ = 0;
+    float* wanted_ = nullptr;     // requested times (device)
+    int wanted_cap_ = 0;
+    double* dot_acc_ = nullptr;
+    float* tg_ = nullptr;         // [0]=lastTime (CalcMultiStepTimeGrad.java:18), [1]=current d
+    DevBuf params_, gradflat_, zt_, gt_, io_, io2_, gb_[3], theta_tmp_, wpart_, dldt_;
+    const float* user_params_ = nullptr;
+    bool have_last_output_ = false;
+    int last_nt_ = 0;
+    std::map<long long, SolveGraph> graphs_;
+    int launches_ = 0;            // launches enqueued since the counter was reset (capture-time accounting)
+
+    // ---- helpers -------------------------------------------------------------------------------------
+    void ensure(DevBuf& b, long long n);
+    void ensure_zt(long long n);
+    static bool is_device_ptr(const void* p);
+    void to_device(float* dst, const float* src, long long n);     // host or device source
+    void from_device(float* dst, const float* src, long long n);   // host or device destination
+    int grid_for(long long n, int per_thread = 1) const;
+    SolverParams solver_params(long long n_norm) const;
+
+    void upload_params();
+    void state_in(const float* user, float* internal);             // reference layout -> internal
+    void state_out(const float* internal, float* user_dev);        // internal -> reference layout (device buffer)
+    void theta_flat_to_internal(const float* flat, float* theta);
+    void theta_internal_to_flat(const float* theta, float* flat);
+    void theta_internal_to_real(const float* theta, float* real);
+
+    void enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out);
+    void enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out);
+    void enqueue_rhs(cudaStream_t s, bool aug, Ref in, Ref out) { aug ? enqueue_rhs_aug(s, in, out) : enqueue_rhs_fwd(s, in, out); }
+    void enqueue_prologue(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt);
+    void enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt,
+                       cudaGraphConditionalHandle cond, int use_cond);
+    void enqueue_epilogue(cudaStream_t s, bool dense_out, int nt);
+    SolveGraph& get_graph(bool aug, int tslot, bool dense_out, int nt);
+    void run_solve(bool aug, int tslot, bool dense_out, int nt);
+    void reset_ctrl();
+    void finish_call(n4j_stats* st, int launches_outside);
+    void set_time_pairs(const std::vector<float>& pairs);
+
+    int calls_launches_ = 0;       // launches of the current API call (incl. executed graph bodies)
+    std::vector<std::pair<SolveGraph*, int>> pending_graph_runs_;
+};
+
+}  // namespace n4j

@@ -1,0 +1,506 @@
+// layer_kernels.cuh — the RHS f(z,t) of the ODE block and its vector-Jacobian products.
+//
+// The reference evaluates the inner ComputationGraph layer by layer through DL4J
+// (ForwardPass.evaluate, src/main/java/ode/vertex/impl/helper/forward/ForwardPass.java:62-102;
+// BackpropagateAdjoint.backPropagate, .../backward/BackpropagateAdjoint.java:87-143).  Here every layer is
+// a CUDA kernel working on the engine's INTERNAL layout: activations are row-major [rows, channels] with
+// rows = B*H*W (NHWC) or B (dense), so BatchNorm statistics are column sums and a 3x3 convolution is nine
+// row-shifted GEMMs.  First/last tensors of the chain are `Ref`s resolved from the control block (the solver's
+// rotating state / K rows), everything in between lives in static scratch buffers.
+//
+// Arithmetic contract shared with oracle/node_oracle.cpp: elementwise math in fp32 without contraction,
+// reductions (BatchNorm statistics, exact dense contractions) in double.  The tiled SGEMM / implicit-GEMM
+// kernels accumulate in fp32 and agree with the oracle to ~1e-6 relative.
+#pragma once
+
+#include "common.cuh"
+
+namespace n4j {
+
+// ---------------------------------------------------------------------------------------------------
+// Layout transforms at the boundary
+// ---------------------------------------------------------------------------------------------------
+// NCHW [B,C,S] -> NHWC [B,S,C]   (S = H*W)
+__global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int S) {
+    const long long n = (long long)B * C * S;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const int c = (int)(i % C);
+        const long long r = i / C;
+        const int s = (int)(r % S);
+        const long long b = r / S;
+        dst[i] = src[(b * C + c) * S + s];
+    }
+}
+__global__ void __launch_bounds__(256) k_nhwc_to_nchw(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int S) {
+    const long long n = (long long)B * C * S;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const int s = (int)(i % S);
+        const long long r = i / S;
+        const int c = (int)(r % C);
+        const long long b = r / C;
+        dst[i] = src[(b * S + s) * C + c];
+    }
+}
+// time-first internal [T][n] <-> reference layouts.  rank 2: [B,F,T]; rank 4: [B,T,C,H,W] (MultiStep.java:49-60)
+__global__ void __launch_bounds__(256) k_timefirst_to_ref(const float* __restrict__ src, float* __restrict__ dst, int T, int B, int C, int S, int rank4) {
+    const long long per = (long long)B * C * S;
+    const long long n = per * T;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        if (rank4) {   // dst index: (((b*T + k)*C + c)*S + s)   src: [k][b][s][c]
+            const int s = (int)(i % S); long long r = i / S;
+            const int c = (int)(r % C); r /= C;
+            const int k = (int)(r % T); const long long b = r / T;
+            dst[i] = src[(long long)k * per + (b * S + s) * C + c];
+        } else {       // dst index: ((b*C + f)*T + k)            src: [k][b][f]
+            const int k = (int)(i % T); long long r = i / T;
+            const int f = (int)(r % C); const long long b = r / C;
+            dst[i] = src[(long long)k * per + b * C + f];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_ref_to_timefirst(const float* __restrict__ src, float* __restrict__ dst, int T, int B, int C, int S, int rank4) {
+    const long long per = (long long)B * C * S;
+    const long long n = per * T;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        if (rank4) {
+            const int s = (int)(i % S); long long r = i / S;
+            const int c = (int)(r % C); r /= C;
+            const int k = (int)(r % T); const long long b = r / T;
+            dst[(long long)k * per + (b * S + s) * C + c] = src[i];
+        } else {
+            const int k = (int)(i % T); long long r = i / T;
+            const int f = (int)(r % C); const long long b = r / C;
+            dst[(long long)k * per + b * C + f] = src[i];
+        }
+    }
+}
+// conv weights: DL4J [Co,Ci,3,3] c-order -> Wf [tap][ci][co] and Wb [tap][co][ci]
+__global__ void __launch_bounds__(256) k_conv_w_to_internal(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wb, int Co, int Ci) {
+    const int n = Co * Ci * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int tap = i % 9; const int r = i / 9; const int ci = r % Ci; const int co = r / Ci;
+        const float v = w[i];
+        wf[(tap * Ci + ci) * Co + co] = v;
+        wb[(tap * Co + co) * Ci + ci] = v;
+    }
+}
+// theta-slot [tap][ci][co] <-> flat gradient view [Co,Ci,3,3]
+__global__ void __launch_bounds__(256) k_conv_g_internal_to_flat(const float* __restrict__ gi, float* __restrict__ gflat, int Co, int Ci) {
+    const int n = Co * Ci * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int tap = i % 9; const int r = i / 9; const int ci = r % Ci; const int co = r / Ci;
+        gflat[i] = gi[(tap * Ci + ci) * Co + co];
+    }
+}
+__global__ void __launch_bounds__(256) k_conv_g_flat_to_internal(const float* __restrict__ gflat, float* __restrict__ gi, int Co, int Ci) {
+    const int n = Co * Ci * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int tap = i % 9; const int r = i / 9; const int ci = r % Ci; const int co = r / Ci;
+        gi[(tap * Ci + ci) * Co + co] = gflat[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Elementwise
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_act_fwd(Ref xin, Ref yout, int act, long long n) {
+    const float* __restrict__ x = resolve(xin);
+    float* __restrict__ y = resolve(yout);
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) y[i] = act_fwd(act, x[i]);
+}
+// g' = act'(y) * (gscale * g)
+__global__ void __launch_bounds__(256) k_act_bwd(Ref gin, float gscale, Ref yref, int act, Ref gout, long long n) {
+    const float* __restrict__ g = resolve(gin);
+    const float* __restrict__ y = resolve(yref);
+    float* __restrict__ o = resolve(gout);
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+        o[i] = act_bwd(act, y[i], __fmul_rn(gscale, g[i]));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// BatchNorm, training mode always (SingleStep.java:37): batch mean / biased variance over rows.
+// Statistics: column sums in double, last block finalises mean and 1/sqrt(var+eps) and re-arms the
+// accumulators.  Requires C % 4 == 0 and (C/4) dividing 256 (vector path) else the generic path.
+// ---------------------------------------------------------------------------------------------------
+struct BnScratch {
+    double* acc;            // [2*C]
+    unsigned int* ticket;   // [1]
+    float* mean;            // [C]
+    float* invstd;          // [C]
+    float* m_dy;            // [C]  backward: mean(dy)
+    float* m_dyxh;          // [C]  backward: mean(dy*xhat)
+};
+
+__global__ void __launch_bounds__(256) k_bn_stats(Ref xin, long long M, int C, float eps, BnScratch sc) {
+    const float* __restrict__ x = resolve(xin);
+    const int cg = C >> 2;                       // float4 groups per row
+    const int rows_per_iter = 256 / cg;
+    const int my_g = threadIdx.x % cg, my_r = threadIdx.x / cg;
+    double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    for (long long r = (long long)blockIdx.x * rows_per_iter + my_r; r < M; r += (long long)gridDim.x * rows_per_iter) {
+        const float4 v = reinterpret_cast<const float4*>(x + r * C)[my_g];
+        s[0] += (double)v.x; ss[0] += (double)v.x * (double)v.x;
+        s[1] += (double)v.y; ss[1] += (double)v.y * (double)v.y;
+        s[2] += (double)v.z; ss[2] += (double)v.z * (double)v.z;
+        s[3] += (double)v.w; ss[3] += (double)v.w * (double)v.w;
+    }
+    // reduce over the rows_per_iter threads that share a channel group
+    __shared__ double sm[2][4][256];
+    __shared__ int s_last;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sm[0][k][threadIdx.x] = s[k]; sm[1][k][threadIdx.x] = ss[k]; }
+    __syncthreads();
+    if (threadIdx.x < cg) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double a = 0, b = 0;
+            for (int r = 0; r < rows_per_iter; ++r) { a += sm[0][k][r * cg + threadIdx.x]; b += sm[1][k][r * cg + threadIdx.x]; }
+            const int c = threadIdx.x * 4 + k;
+            atomicAdd(sc.acc + c, a);
+            atomicAdd(sc.acc + C + c, b);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int tk = atomicAdd(sc.ticket, 1u);
+        s_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const double sum = *((volatile double*)(sc.acc + c)), sq = *((volatile double*)(sc.acc + C + c));
+            const double mean = sum / (double)M;
+            double var = sq / (double)M - mean * mean;
+            if (var < 0) var = 0;
+            sc.mean[c] = (float)mean;
+            sc.invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+            sc.acc[c] = 0.0; sc.acc[C + c] = 0.0;
+        }
+        if (threadIdx.x == 0) *sc.ticket = 0u;
+    }
+}
+// generic channel count: one block per channel
+__global__ void __launch_bounds__(256) k_bn_stats_generic(Ref xin, long long M, int C, float eps, BnScratch sc) {
+    const float* __restrict__ x = resolve(xin);
+    const int c = blockIdx.x;
+    double v[2] = {0, 0};
+    for (long long r = threadIdx.x; r < M; r += blockDim.x) { const double q = (double)x[r * C + c]; v[0] += q; v[1] += q * q; }
+    block_sum<2>(v);
+    if (threadIdx.x == 0) {
+        const double mean = v[0] / (double)M;
+        double var = v[1] / (double)M - mean * mean;
+        if (var < 0) var = 0;
+        sc.mean[c] = (float)mean;
+        sc.invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+}
+// y = act(gamma * ((x - mean) * invstd) + beta)
+__global__ void __launch_bounds__(256) k_bn_apply(Ref xin, Ref yout, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                   BnScratch sc, int act, long long M, int C) {
+    const float* __restrict__ x = resolve(xin);
+    float* __restrict__ y = resolve(yout);
+    const long long n = M * C;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const int c = (int)(i % C);
+        const float d = __fsub_rn(x[i], sc.mean[c]);
+        const float h = __fmul_rn(d, sc.invstd[c]);
+        y[i] = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c], h), beta[c]));
+    }
+}
+// backward statistics: dy = act'(y)*(gscale*g);  sums of dy and dy*xhat (double) -> dgamma, dbeta, means
+__global__ void __launch_bounds__(256) k_bn_bwd_stats(Ref gin, float gscale, Ref yref, Ref xin, BnScratch sc, int act, long long M, int C,
+                                                       Ref dgamma_ref, Ref dbeta_ref) {
+    const float* __restrict__ g = resolve(gin);
+    const float* __restrict__ y = resolve(yref);
+    const float* __restrict__ x = resolve(xin);
+    // generic mapping: thread owns channel (tid % C) when C <= 256 and divides 256, else strided
+    const int c_lane = threadIdx.x % C;
+    const bool fast = (C <= 256) && (256 % C == 0);
+    __shared__ double sm[2][256];
+    __shared__ int s_last;
+    if (fast) {
+        const int rows_per_iter = 256 / C, my_r = threadIdx.x / C;
+        const float mean = sc.mean[c_lane], inv = sc.invstd[c_lane];
+        double a = 0, b = 0;
+        for (long long r = (long long)blockIdx.x * rows_per_iter + my_r; r < M; r += (long long)gridDim.x * rows_per_iter) {
+            const long long i = r * C + c_lane;
+            const float dy = act_bwd(act, y[i], __fmul_rn(gscale, g[i]));
+            const float xh = __fmul_rn(__fsub_rn(x[i], mean), inv);
+            a += (double)dy; b += (double)dy * (double)xh;
+        }
+        sm[0][threadIdx.x] = a; sm[1][threadIdx.x] = b;
+        __syncthreads();
+        if (threadIdx.x < C) {
+            double sa = 0, sb = 0;
+            for (int r = 0; r < rows_per_iter; ++r) { sa += sm[0][r * C + threadIdx.x]; sb += sm[1][r * C + threadIdx.x]; }
+            atomicAdd(sc.acc + threadIdx.x, sa);
+            atomicAdd(sc.acc + C + threadIdx.x, sb);
+            __threadfence();
+        }
+    } else {
+        // slow path: block loops over channels; grid-stride over rows inside
+        for (int c = 0; c < C; ++c) {
+            double v[2] = {0, 0};
+            const float mean = sc.mean[c], inv = sc.invstd[c];
+            for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < M; r += (long long)gridDim.x * blockDim.x) {
+                const long long i = r * C + c;
+                const float dy = act_bwd(act, y[i], __fmul_rn(gscale, g[i]));
+                const float xh = __fmul_rn(__fsub_rn(x[i], mean), inv);
+                v[0] += (double)dy; v[1] += (double)dy * (double)xh;
+            }
+            block_sum<2>(v);
+            if (threadIdx.x == 0) { atomicAdd(sc.acc + c, v[0]); atomicAdd(sc.acc + C + c, v[1]); __threadfence(); }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int tk = atomicAdd(sc.ticket, 1u);
+        s_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        float* __restrict__ dgamma = resolve(dgamma_ref);
+        float* __restrict__ dbeta = resolve(dbeta_ref);
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const double sdy = *((volatile double*)(sc.acc + c)), sdyxh = *((volatile double*)(sc.acc + C + c));
+            dgamma[c] = (float)sdyxh;
+            dbeta[c] = (float)sdy;
+            sc.m_dy[c] = (float)(sdy / (double)M);
+            sc.m_dyxh[c] = (float)(sdyxh / (double)M);
+            sc.acc[c] = 0.0; sc.acc[C + c] = 0.0;
+        }
+        if (threadIdx.x == 0) *sc.ticket = 0u;
+    }
+}
+// dx = gamma*invstd * ((dy - mean(dy)) - xhat*mean(dy*xhat))
+__global__ void __launch_bounds__(256) k_bn_bwd_dx(Ref gin, float gscale, Ref yref, Ref xin, const float* __restrict__ gamma, BnScratch sc,
+                                                    int act, long long M, int C, Ref dxout) {
+    const float* __restrict__ g = resolve(gin);
+    const float* __restrict__ y = resolve(yref);
+    const float* __restrict__ x = resolve(xin);
+    float* __restrict__ dx = resolve(dxout);
+    const long long n = M * C;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const int c = (int)(i % C);
+        const float inv = sc.invstd[c];
+        const float dy = act_bwd(act, y[i], __fmul_rn(gscale, g[i]));
+        const float xh = __fmul_rn(__fsub_rn(x[i], sc.mean[c]), inv);
+        const float k = __fmul_rn(gamma[c], inv);
+        const float t1 = __fsub_rn(dy, sc.m_dy[c]);
+        const float t2 = __fmul_rn(xh, sc.m_dyxh[c]);
+        dx[i] = __fmul_rn(k, __fsub_rn(t1, t2));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Dense, exact path (small layers: spiral 4-20-20-4, the reference's golden 2x2 case): contractions in double,
+// bit-compatible with the oracle.  W is DL4J's f-order [nIn,nOut]: W(i,o) = Wt[i + o*nIn], bias after it.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dense_fwd_exact(Ref xin, Ref yout, const float* __restrict__ Wt, const float* __restrict__ bias,
+                                                          int act, long long B, int nin, int nout) {
+    const float* __restrict__ x = resolve(xin);
+    float* __restrict__ y = resolve(yout);
+    const long long n = B * nout;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += step) {
+        const int o = (int)(idx % nout);
+        const long long b = idx / nout;
+        double acc = bias ? (double)bias[o] : 0.0;
+        const float* xr = x + b * nin;
+        const float* wc = Wt + (long long)o * nin;
+        for (int i = 0; i < nin; ++i) acc += (double)xr[i] * (double)wc[i];
+        y[idx] = act_fwd(act, (float)acc);
+    }
+}
+// dW(i,o) = sum_b x(b,i) d(b,o)  -> out[i + o*nIn];  db(o) = sum_b d(b,o) -> out[nIn*nOut + o]
+__global__ void __launch_bounds__(256) k_dense_wgrad_exact(Ref xin, Ref din, Ref dwout, long long B, int nin, int nout, int has_bias) {
+    const float* __restrict__ x = resolve(xin);
+    const float* __restrict__ d = resolve(din);
+    float* __restrict__ dw = resolve(dwout);
+    const int n = nin * nout + (has_bias ? nout : 0);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+        double acc = 0;
+        if (idx < nin * nout) {
+            const int i = idx % nin, o = idx / nin;
+            for (long long b = 0; b < B; ++b) acc += (double)x[b * nin + i] * (double)d[b * nout + o];
+        } else {
+            const int o = idx - nin * nout;
+            for (long long b = 0; b < B; ++b) acc += (double)d[b * nout + o];
+        }
+        dw[idx] = (float)acc;
+    }
+}
+__global__ void __launch_bounds__(256) k_dense_dgrad_exact(Ref din, const float* __restrict__ Wt, Ref dxout, long long B, int nin, int nout) {
+    const float* __restrict__ d = resolve(din);
+    float* __restrict__ dx = resolve(dxout);
+    const long long n = B * nin;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += step) {
+        const int i = (int)(idx % nin);
+        const long long b = idx / nin;
+        double acc = 0;
+        for (int o = 0; o < nout; ++o) acc += (double)d[b * nout + o] * (double)Wt[i + (long long)o * nin];
+        dx[idx] = (float)acc;
+    }
+}
+__global__ void __launch_bounds__(256) k_colsum(Ref din, Ref out, long long B, int n) {   // bias gradient for the tiled path
+    const float* __restrict__ d = resolve(din);
+    float* __restrict__ o = resolve(out);
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        double acc = 0;
+        for (long long b = 0; b < B; ++b) acc += (double)d[b * n + c];
+        o[c] = (float)acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Tiled fp32 GEMM with pluggable operand addressing: C[M,N] (+bias, act) = A[M,K] * B[K,N].
+// 64x64 block tile, 16-deep K tile, 256 threads, 4x4 register tile.  Serves dense fwd/dgrad/wgrad and the
+// 3x3 convolution as implicit GEMM (fwd, dgrad, wgrad with split-K).  This is the SIMT baseline the tcgen05
+// kernels are checked against; it stays as the fallback for shapes the tensor-core path does not take.
+// ---------------------------------------------------------------------------------------------------
+enum { G_DENSE_FWD = 0, G_DENSE_DGRAD = 1, G_DENSE_WGRAD = 2, G_CONV_FWD = 3, G_CONV_DGRAD = 4, G_CONV_WGRAD = 5 };
+
+struct GemmArgs {
+    Ref a, b, c;
+    const float* w;        // weights when an operand is a static parameter buffer (else null)
+    const float* bias;     // dense fwd
+    int M, N, K;
+    int act;
+    int H, W, Ci, Co;      // conv geometry
+    int splits;            // split-K factor (grid.z); partials go to c + z*M*N when splits > 1
+};
+
+template <int MODE> struct Addr {
+    // value of A(m,k) / B(k,n); pa/pb are the resolved operand base pointers
+    __device__ static __forceinline__ float A(const GemmArgs& g, const float* pa, int m, int k, int hh, int ww) {
+        if (MODE == G_DENSE_FWD || MODE == G_DENSE_DGRAD) return pa[(long long)m * g.K + k];
+        if (MODE == G_DENSE_WGRAD) return pa[(long long)k * g.M + m];
+        if (MODE == G_CONV_FWD || MODE == G_CONV_DGRAD) {
+            const int cin = MODE == G_CONV_FWD ? g.Ci : g.Co;
+            const int tap = k / cin, ch = k - tap * cin;
+            int dh = tap / 3 - 1, dw = tap % 3 - 1;
+            if (MODE == G_CONV_DGRAD) { dh = -dh; dw = -dw; }
+            const int h2 = hh + dh, w2 = ww + dw;
+            if ((unsigned)h2 >= (unsigned)g.H || (unsigned)w2 >= (unsigned)g.W) return 0.f;
+            return pa[((long long)m + dh * g.W + dw) * cin + ch];
+        }
+        // G_CONV_WGRAD: m = tap*Ci + ci, k = pixel row; hh/ww are unused, decode pixel here
+        {
+            const int tap = m / g.Ci, ci = m - tap * g.Ci;
+            const int dh = tap / 3 - 1, dw = tap % 3 - 1;
+            const int s = k % (g.H * g.W);
+            const int h2 = s / g.W + dh, w2 = s % g.W + dw;
+            if ((unsigned)h2 >= (unsigned)g.H || (unsigned)w2 >= (unsigned)g.W) return 0.f;
+            return pa[((long long)k + dh * g.W + dw) * g.Ci + ci];
+        }
+    }
+    __device__ static __forceinline__ float B(const GemmArgs& g, const float* pb, int k, int n) {
+        if (MODE == G_DENSE_FWD) return pb[(long long)n * g.K + k];          // W(i=k,o=n) = Wt[k + n*nIn]
+        if (MODE == G_DENSE_DGRAD) return pb[(long long)k * g.N + n];        // W(i=n,o=k) = Wt[n + k*nIn]
+        if (MODE == G_DENSE_WGRAD) return pb[(long long)k * g.N + n];        // x[b=k, i=n]
+        return pb[(long long)k * g.N + n];                                     // conv: [k][n] row-major
+    }
+};
+
+// AccT = float: fp32 FMA accumulation (default).  AccT = double: exact products, double accumulation, one rounding —
+// order-independent and therefore bit-compatible with the oracle (N4J_FLAG_EXACT_CONTRACTIONS, parity mode).
+template <int MODE, typename AccT>
+__global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const float* __restrict__ pa = (MODE == G_DENSE_WGRAD || MODE == G_CONV_WGRAD || MODE == G_DENSE_FWD || MODE == G_CONV_FWD || MODE == G_DENSE_DGRAD ||
+                                    MODE == G_CONV_DGRAD)
+                                       ? resolve(g.a) : nullptr;
+    const float* __restrict__ pb = g.w ? g.w : resolve(g.b);
+    float* __restrict__ pc = resolve(g.c);
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    // K range of this split
+    const int kchunk = (g.K + g.splits - 1) / g.splits;
+    const int kbeg = blockIdx.z * kchunk, kend = min(g.K, kbeg + kchunk);
+    // loader mapping: A tile 64x16 = 1024 elements, 4 per thread; thread loads rows lm + {0,16,32,48}? -> use (m = tid%64, k = tid/64 + 4*j)
+    const int la_m = threadIdx.x % BM, la_k = threadIdx.x / BM;      // la_k in 0..3
+    const int lb_n = threadIdx.x % BN, lb_k = threadIdx.x / BN;
+    int hh = 0, ww = 0;
+    if (MODE == G_CONV_FWD || MODE == G_CONV_DGRAD) {
+        const int m = m0 + la_m;
+        const int s = m % (g.H * g.W);
+        hh = s / g.W; ww = s % g.W;
+    }
+    AccT acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = (AccT)0;
+
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + la_k + 4 * j, m = m0 + la_m;
+            As[la_k + 4 * j][la_m] = (m < g.M && k < kend) ? Addr<MODE>::A(g, pa, m, k, hh, ww) : 0.f;
+            const int kb = k0 + lb_k + 4 * j, n = n0 + lb_n;
+            Bs[lb_k + 4 * j][lb_n] = (n < g.N && kb < kend) ? Addr<MODE>::B(g, pb, kb, n) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+            const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (sizeof(AccT) == 8) acc[i][j] += (AccT)a[i] * (AccT)b[j];
+                    else acc[i][j] = (AccT)fmaf(a[i], b[j], (float)acc[i][j]);
+                }
+        }
+        __syncthreads();
+    }
+    float* __restrict__ out = pc + (g.splits > 1 ? (long long)blockIdx.z * g.M * g.N : 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= g.N) continue;
+            float v;
+            if (g.splits == 1) {
+                if (sizeof(AccT) == 8) v = (float)(acc[i][j] + (AccT)(g.bias ? g.bias[n] : 0.f));
+                else v = g.bias ? (float)acc[i][j] + g.bias[n] : (float)acc[i][j];
+                v = act_fwd(g.act, v);
+            } else {
+                v = (float)acc[i][j];
+            }
+            out[(long long)m * g.N + n] = v;
+        }
+    }
+}
+
+// deterministic split-K reduction: dst[i] = sum_z part[z][i]
+__global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, Ref dstref, long long n, int splits) {
+    float* __restrict__ dst = resolve(dstref);
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        float s = part[i];
+        for (int z = 1; z < splits; ++z) s += part[(long long)z * n + i];
+        dst[i] = s;
+    }
+}
+
+}  // namespace n4j

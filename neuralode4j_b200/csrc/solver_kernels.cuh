@@ -1,0 +1,428 @@
+// solver_kernels.cuh — the bandwidth-bound half of the hot path: DP5(4) stage combination, error norm,
+// device-side step controller, initial-step heuristic and dense output.  Each is ONE vectorised (128-bit)
+// pass over the concatenated minibatch state; reductions are warp-shuffle + block reduce in double with a
+// last-block finalise that also runs the controller.
+//
+// Replaces (reference file:line, all under /root/reference/src/main/java/ode/solve):
+//   impl/util/FirstOrderEquationWithState.java:42-51   State.step          -> k_stage_combine
+//   impl/DormandPrince54Solver.java:78-93              DormandPrince54Mse  -> k_error_ctrl
+//   impl/AdaptiveRungeKuttaSolver.java:76-103,147-181  accept/reject loop  -> k_error_ctrl (last block)
+//   impl/util/AdaptiveRungeKuttaStepPolicy.java:90-153 initializeStep/step -> k_init_sums, k_init_final
+//   impl/util/InterpolatingStepListener.java:59-150 + Interpolation.java:33-84 -> k_dense_output
+#pragma once
+
+#include "common.cuh"
+
+namespace n4j {
+
+// DormandPrince54Solver.java:27-48 (tableau), rounded to fp32 like ND4J's default data type does.
+__constant__ float c_A[6][6] = {
+    {(float)(1.0 / 5.0), 0, 0, 0, 0, 0},
+    {(float)(3.0 / 40.0), (float)(9.0 / 40.0), 0, 0, 0, 0},
+    {(float)(44.0 / 45.0), (float)(-56.0 / 15.0), (float)(32.0 / 9.0), 0, 0, 0},
+    {(float)(19372.0 / 6561.0), (float)(-25360.0 / 2187.0), (float)(64448.0 / 6561.0), (float)(-212.0 / 729.0), 0, 0},
+    {(float)(9017.0 / 3168.0), (float)(-355.0 / 33.0), (float)(46732.0 / 5247.0), (float)(49.0 / 176.0), (float)(-5103.0 / 18656.0), 0},
+    {(float)(35.0 / 384.0), 0.f, (float)(500.0 / 1113.0), (float)(125.0 / 192.0), (float)(-2187.0 / 6784.0), (float)(11.0 / 84.0)}};
+__constant__ float c_E[7] = {(float)(71.0 / 57600.0), 0.f, (float)(-71.0 / 16695.0), (float)(71.0 / 1920.0),
+                             (float)(-17253.0 / 339200.0), (float)(22.0 / 525.0), (float)(-1.0 / 40.0)};
+__constant__ float c_C[6] = {(float)(1.0 / 5.0), (float)(3.0 / 10.0), (float)(4.0 / 5.0), (float)(8.0 / 9.0), 1.f, 1.f};
+__constant__ float c_CMID[7] = {(float)(6025192743.0 / 30085553152.0 / 2.0), 0.f, (float)(51252292925.0 / 65400821598.0 / 2.0),
+                                (float)(-2691868925.0 / 45128329728.0 / 2.0), (float)(187940372067.0 / 1594534317056.0 / 2.0),
+                                (float)(-1776094331.0 / 19743644256.0 / 2.0), (float)(11237099.0 / 235043384.0 / 2.0)};
+
+__device__ __forceinline__ float4 ld4(const float* p, long long i) { return reinterpret_cast<const float4*>(p)[i]; }
+__device__ __forceinline__ void st4(float* p, long long i, float4 v) { reinterpret_cast<float4*>(p)[i] = v; }
+
+// ---------------------------------------------------------------------------------------------------
+// K1: yWorking = y + (a_S * h) . K[0:S]      S = 1..6;  S = 0 is the init-step probe y + h*K0.
+// Zero coefficients (a_62) are skipped at compile time.  Algorithmic traffic: (nnz + 2) vectors.
+// ---------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256) k_stage_combine(const Ctrl* __restrict__ c, float* __restrict__ Ybase,
+                                                        const float* __restrict__ Kbase, long long stride, long long n4) {
+    const float h = c->h;
+    const int yc = c->y_cur;
+    const float* __restrict__ y = Ybase + (long long)yc * stride;
+    float* __restrict__ yw = Ybase + (long long)(yc ^ 1) * stride;
+    constexpr int NS = S == 0 ? 1 : S;
+    float coef[NS];
+    const float* __restrict__ kr[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        coef[j] = S == 0 ? h : __fmul_rn(c_A[S - 1][j], h);   // stepCoeffPerStage.mul(step)
+        kr[j] = Kbase + (long long)c->krow[j] * stride;
+    }
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+        const float4 yv = ld4(y, i);
+        float4 k0 = ld4(kr[0], i);
+        float4 acc = make_float4(__fmul_rn(coef[0], k0.x), __fmul_rn(coef[0], k0.y), __fmul_rn(coef[0], k0.z), __fmul_rn(coef[0], k0.w));
+#pragma unroll
+        for (int j = 1; j < NS; ++j) {
+            if (S == 6 && j == 1) continue;   // a_62 == 0
+            const float4 kj = ld4(kr[j], i);
+            acc.x = __fmaf_rn(coef[j], kj.x, acc.x);
+            acc.y = __fmaf_rn(coef[j], kj.y, acc.y);
+            acc.z = __fmaf_rn(coef[j], kj.z, acc.z);
+            acc.w = __fmaf_rn(coef[j], kj.w, acc.w);
+        }
+        st4(yw, i, make_float4(__fadd_rn(yv.x, acc.x), __fadd_rn(yv.y, acc.y), __fadd_rn(yv.z, acc.z), __fadd_rn(yv.w, acc.w)));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Scalar controller pieces (run by one thread)
+// ---------------------------------------------------------------------------------------------------
+// AdaptiveRungeKuttaStepPolicy.step :142-153
+__device__ __forceinline__ float next_step(float h, float err, const SolverParams& p) {
+    float fac = __fmul_rn((float)pow((double)err, -1.0 / (double)p.order), p.safety);
+    fac = fminf(p.max_growth, fmaxf(p.min_reduction, fac));
+    const float sign = h > 0.f ? 1.f : (h < 0.f ? -1.f : 0.f);
+    float v = __fmul_rn(__fmul_rn(fac, h), sign);
+    v = fminf(p.hmax, fmaxf(p.hmin, v));
+    return __fmul_rn(v, sign);
+}
+
+// TimeLimitForwards/Backwards.isLastStep, AdaptiveRungeKuttaSolver.java:76-103: clamps c->h for the NEXT trial.
+__device__ __forceinline__ void clamp_to_end(Ctrl* c) {
+    const float tph = __fadd_rn(c->t, c->h);
+    const double tl = (double)c->t_end;
+    const bool hit = c->backward ? ((double)tph <= tl) : ((double)tph >= tl);
+    if (hit) {
+        c->h = (float)(tl - (double)c->t);
+        c->is_last = 1;
+    } else {
+        c->is_last = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2+K3: error norm + accept/reject + new step, one pass.  Reads the 6 K rows with e_j != 0, y and yWorking
+// (8 vectors).  Multi-GPU: `peer_sum` hook is applied by the caller before the controller (see engine).
+// ---------------------------------------------------------------------------------------------------
+struct DenseOutArgs {
+    const float* wanted;   // requested times (device), may be null
+    int n_wanted;
+};
+
+__device__ __forceinline__ void controller_after_error(Ctrl* c, double sum, const SolverParams& p, n4j_step_rec* log,
+                                                       DenseOutArgs dout) {
+    const float err = (float)sqrt(sum / (double)p.n_norm);
+    const float h = c->h;
+    const float t_old = c->t;
+    c->err = err;
+    c->nfe += 6;
+    c->trials += 1;
+    c->trials_this_solve += 1;
+    const bool ok = (double)err < 1.0;                                  // AdaptiveRungeKuttaSolver.java:170
+    c->accepted_now = ok ? 1 : 0;
+    if (ok) {
+        c->t_prev = t_old;
+        c->h_used = h;
+        c->t = __fadd_rn(t_old, h);                                     // update(): time.addi(timeOffset)
+        c->y_cur ^= 1;                                                  // y.assign(yWorking): pointer flip
+#pragma unroll
+        for (int j = 0; j < 7; ++j) c->krow_prev[j] = c->krow[j];
+        const int r0 = c->krow[0];                                      // shiftDerivative(): K0 <- K6
+        c->krow[0] = c->krow[6];
+        c->krow[6] = r0;
+        c->accepted += 1;
+        c->interp_alias = (c->steps_this_solve == 0) ? 1 : 0;
+        c->steps_this_solve += 1;
+        // InterpolatingStepListener.step :72-96 — which requested times fall strictly inside the step
+        int first = -1, cnt = 0;
+        if (dout.wanted) {
+            const double lo = h > 0.f ? (double)t_old : (double)c->t;
+            const double hi = h > 0.f ? (double)c->t : (double)t_old;
+            for (int i = 0; i < dout.n_wanted; ++i) {
+                const double w = (double)dout.wanted[i];
+                if (w > lo && w < hi) { if (first < 0) first = i; ++cnt; }
+            }
+        }
+        c->interp_first = first;
+        c->interp_cnt = cnt;
+    } else {
+        c->rejected += 1;
+        c->interp_cnt = 0;
+    }
+    if (log && c->log_n < p.log_cap) {
+        n4j_step_rec r;
+        r.t = c->t; r.h = h; r.err = err; r.accepted = ok ? 1 : 0;
+        log[c->log_n] = r;
+    }
+    c->log_n += 1;
+    int done = (c->is_last && ok) ? 1 : 0;                               // :161
+    c->h = next_step(h, err, p);                                         // :164
+    if (!done) clamp_to_end(c);                                          // :149 of the next iteration
+    if (!(err == err) || !(c->h == c->h)) { c->status = N4J_ERR_ILLEGAL_STATE; done = 1; }   // NaN guard
+    if (!done && c->trials_this_solve >= p.max_trials) { c->status = N4J_ERR_MAX_STEPS; done = 1; }
+    c->done = done;
+}
+
+__global__ void __launch_bounds__(256) k_error_ctrl(Ctrl* c, const float* __restrict__ Ybase, const float* __restrict__ Kbase,
+                                                     long long stride, long long n4, SolverParams p, n4j_step_rec* log,
+                                                     DenseOutArgs dout, cudaGraphConditionalHandle cond, int use_cond) {
+    const float h = c->h;
+    const int yc = c->y_cur;
+    const float* __restrict__ y0 = Ybase + (long long)yc * stride;
+    const float* __restrict__ y1 = Ybase + (long long)(yc ^ 1) * stride;
+    const float* __restrict__ k0 = Kbase + (long long)c->krow[0] * stride;
+    const float* __restrict__ k2 = Kbase + (long long)c->krow[2] * stride;
+    const float* __restrict__ k3 = Kbase + (long long)c->krow[3] * stride;
+    const float* __restrict__ k4 = Kbase + (long long)c->krow[4] * stride;
+    const float* __restrict__ k5 = Kbase + (long long)c->krow[5] * stride;
+    const float* __restrict__ k6 = Kbase + (long long)c->krow[6] * stride;
+    const float e0 = c_E[0], e2 = c_E[2], e3 = c_E[3], e4 = c_E[4], e5 = c_E[5], e6 = c_E[6];
+    double s[1] = {0.0};
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+        const float4 a0 = ld4(k0, i), a2 = ld4(k2, i), a3 = ld4(k3, i), a4 = ld4(k4, i), a5 = ld4(k5, i), a6 = ld4(k6, i);
+        const float4 u = ld4(y0, i), v = ld4(y1, i);
+#define N4J_ERR_LANE(f)                                                                     \
+        {                                                                                   \
+            float es = __fmul_rn(e0, a0.f);                                                 \
+            es = __fmaf_rn(e2, a2.f, es); es = __fmaf_rn(e3, a3.f, es);                     \
+            es = __fmaf_rn(e4, a4.f, es); es = __fmaf_rn(e5, a5.f, es);                     \
+            es = __fmaf_rn(e6, a6.f, es);                                                   \
+            const float ys = fmaxf(fabsf(u.f), fabsf(v.f));                                 \
+            const float tol = __fadd_rn(__fmul_rn(ys, p.rtol), p.atol);                     \
+            const float ratio = __fmul_rn(__fdiv_rn(es, tol), h);                           \
+            s[0] += (double)ratio * (double)ratio;                                          \
+        }
+        N4J_ERR_LANE(x) N4J_ERR_LANE(y) N4J_ERR_LANE(z) N4J_ERR_LANE(w)
+#undef N4J_ERR_LANE
+    }
+    if (publish_and_elect<1>(s, c->acc, c->ticket)) {
+        if (threadIdx.x == 0) {
+            const double sum = *((volatile double*)c->acc);
+            c->acc[0] = 0.0;
+            c->ticket[0] = 0u;
+            controller_after_error(c, sum, p, log, dout);
+            if (use_cond) cudaGraphSetConditional(cond, c->done ? 0u : 1u);
+        }
+    }
+}
+
+// Variant without the controller: DormandPrince54Mse on caller data (node4j_error_norm).
+__global__ void __launch_bounds__(256) k_error_only(const float* __restrict__ K, const float* __restrict__ y0, const float* __restrict__ y1,
+                                                     long long n, float h, float atol, float rtol, double* acc) {
+    double s[1] = {0.0};
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        float es = __fmul_rn(c_E[0], K[i]);
+        es = __fmaf_rn(c_E[2], K[2 * n + i], es); es = __fmaf_rn(c_E[3], K[3 * n + i], es);
+        es = __fmaf_rn(c_E[4], K[4 * n + i], es); es = __fmaf_rn(c_E[5], K[5 * n + i], es);
+        es = __fmaf_rn(c_E[6], K[6 * n + i], es);
+        const float ys = fmaxf(fabsf(y0[i]), fabsf(y1[i]));
+        const float tol = __fadd_rn(__fmul_rn(ys, rtol), atol);
+        const float ratio = __fmul_rn(__fdiv_rn(es, tol), h);
+        s[0] += (double)ratio * (double)ratio;
+    }
+    block_sum<1>(s);
+    if (threadIdx.x == 0) atomicAdd(acc, s[0]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4: initial step (AdaptiveRungeKuttaStepPolicy.initializeStep :90-139), two reduction passes.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_solve_begin(Ctrl* c, const float* tpair) {
+    // integrate(): new FirstOrderEquationWithState(equation, t[0], yOut.assign(y0)) — state reset for one solve
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int pair_index = c->seg_index;
+        c->seg_index = pair_index + 1;
+        const float t0 = tpair[pair_index * 2], t1 = tpair[pair_index * 2 + 1];
+        c->t = t0; c->t_start = t0; c->t_end = t1;
+        c->backward = !(t1 > t0);                   // t.argMax()==0
+        c->done = 0; c->is_last = 0;   // status stays sticky across the segments of one call
+        c->trials_this_solve = 0; c->steps_this_solve = 0;
+        c->accepted_now = 0; c->interp_cnt = 0; c->interp_alias = 0;
+        for (int j = 0; j < 7; ++j) { c->krow[j] = j; c->krow_prev[j] = j; }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_init_sums(Ctrl* c, const float* __restrict__ Ybase, const float* __restrict__ Kbase,
+                                                    long long stride, long long n4, SolverParams p) {
+    const float* __restrict__ y = Ybase + (long long)c->y_cur * stride;
+    const float* __restrict__ k0 = Kbase + (long long)c->krow[0] * stride;
+    double s[2] = {0.0, 0.0};
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+        const float4 u = ld4(y, i), d = ld4(k0, i);
+#define N4J_LANE(f)                                                               \
+        {                                                                         \
+            const float scal = __fadd_rn(__fmul_rn(fabsf(u.f), p.rtol), p.atol);  \
+            const float r1 = __fdiv_rn(u.f, scal), r2 = __fdiv_rn(d.f, scal);     \
+            s[0] += (double)r1 * (double)r1;                                      \
+            s[1] += (double)r2 * (double)r2;                                      \
+        }
+        N4J_LANE(x) N4J_LANE(y) N4J_LANE(z) N4J_LANE(w)
+#undef N4J_LANE
+    }
+    if (publish_and_elect<2>(s, c->acc, c->ticket)) {
+        if (threadIdx.x == 0) {
+            const float Yr = (float)*((volatile double*)&c->acc[0]);
+            const float Dr = (float)*((volatile double*)&c->acc[1]);
+            c->acc[0] = 0.0; c->acc[1] = 0.0; c->ticket[0] = 0u;
+            float h = ((double)Yr < 1.0e-10 || (double)Dr < 1.0e-10) ? 1e-6f : __fmul_rn(sqrtf(__fdiv_rn(Yr, Dr)), 0.01f);
+            if (c->backward) h = -h;
+            c->h = h;          // probe step for equation.step(ones(1), step)
+            c->init_D = Dr;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_init_final(Ctrl* c, const float* __restrict__ Ybase, const float* __restrict__ Kbase,
+                                                     long long stride, long long n4, SolverParams p,
+                                                     cudaGraphConditionalHandle cond, int use_cond) {
+    const float* __restrict__ y = Ybase + (long long)c->y_cur * stride;
+    const float* __restrict__ k0 = Kbase + (long long)c->krow[0] * stride;
+    const float* __restrict__ k1 = Kbase + (long long)c->krow[1] * stride;
+    double s[1] = {0.0};
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+        const float4 u = ld4(y, i), a = ld4(k0, i), b = ld4(k1, i);
+#define N4J_LANE(f)                                                               \
+        {                                                                         \
+            const float scal = __fadd_rn(__fmul_rn(fabsf(u.f), p.rtol), p.atol);  \
+            const float r = __fdiv_rn(__fsub_rn(b.f, a.f), scal);                 \
+            s[0] += (double)r * (double)r;                                        \
+        }
+        N4J_LANE(x) N4J_LANE(y) N4J_LANE(z) N4J_LANE(w)
+#undef N4J_LANE
+    }
+    if (publish_and_elect<1>(s, c->acc, c->ticket)) {
+        if (threadIdx.x == 0) {
+            const float DDs = (float)*((volatile double*)&c->acc[0]);
+            c->acc[0] = 0.0; c->ticket[0] = 0u;
+            float h = c->h;
+            const float DD = __fdiv_rn(sqrtf(DDs), h);                       // signed (:118,122)
+            const float m = fmaxf(sqrtf(c->init_D), DD);
+            float h1;
+            if ((double)m < 1e-15) h1 = fmaxf(1e-6f, __fmul_rn(fabsf(h), 0.001f));
+            else h1 = (float)pow((double)__fdiv_rn(0.01f, m), 1.0 / (double)p.order);
+            h = fminf(__fmul_rn(fabsf(h), 100.f), h1);
+            h = fmaxf(h, __fmul_rn(fabsf(c->t_start), 1e-12f));
+            h = fmaxf(p.hmin, h);
+            h = fminf(p.hmax, h);
+            if (c->backward) h = -h;
+            c->h = h;
+            c->nfe += 3;                // :131, policy :92 (redundant, not recomputed here), policy :112
+            c->solves += 1;
+            clamp_to_end(c);            // first trial's isLastStep
+            int done = 0;
+            if (!(h == h)) { c->status = N4J_ERR_ILLEGAL_STATE; done = 1; }
+            c->done = done;
+            if (use_cond) cudaGraphSetConditional(cond, done ? 0u : 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5: dense output for the requested times bracketed by the step that was just accepted.
+// out is time-first [n_wanted][n]; launched after k_error_ctrl in every trial of an interpolating solve and
+// returns immediately when there is nothing to do.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_dense_output(const Ctrl* __restrict__ c, const float* __restrict__ Ybase,
+                                                       const float* __restrict__ Kbase, long long stride, long long n,
+                                                       const float* __restrict__ wanted, float* __restrict__ out, long long out_stride) {
+    if (!c->accepted_now || c->interp_cnt <= 0) return;
+    const float h = c->h_used;
+    const double t0 = (double)c->t_prev, t1 = (double)c->t;
+    const int yc = c->y_cur;
+    const float* __restrict__ y1 = Ybase + (long long)yc * stride;
+    const float* __restrict__ y0 = c->interp_alias ? y1 : Ybase + (long long)(yc ^ 1) * stride;
+    const float* __restrict__ kr[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) kr[j] = Kbase + (long long)c->krow_prev[j] * stride;
+    const double dtd = (double)h;
+    const float F0[5] = {(float)(-2 * dtd), (float)(2 * dtd), -8.f, -8.f, 16.f};
+    const float F1[5] = {(float)(5 * dtd), (float)(-3 * dtd), 18.f, 14.f, -32.f};
+    const float F2[5] = {(float)(-4 * dtd), (float)dtd, -11.f, -5.f, 16.f};
+    const int first = c->interp_first, cnt = c->interp_cnt;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        float kv[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) kv[j] = kr[j][i];
+        float o = __fmul_rn(__fmul_rn(kv[0], c_CMID[0]), h);                  // scaledDotProduct :122-128
+#pragma unroll
+        for (int j = 1; j < 7; ++j) o = __fadd_rn(o, __fmul_rn(__fmul_rn(kv[j], c_CMID[j]), h));
+        const float a = y0[i], b = y1[i];
+        const float ymid = __fadd_rn(a, o);
+        const float in[5] = {kv[0], kv[6], a, b, ymid};
+        float cf[5];
+        {
+            float q = __fmul_rn(in[0], F0[0]);
+#pragma unroll
+            for (int j = 1; j < 5; ++j) q = __fadd_rn(q, __fmul_rn(in[j], F0[j]));
+            cf[0] = q;
+            q = __fmul_rn(in[0], F1[0]);
+#pragma unroll
+            for (int j = 1; j < 5; ++j) q = __fadd_rn(q, __fmul_rn(in[j], F1[j]));
+            cf[1] = q;
+            q = __fmul_rn(in[0], F2[0]);
+#pragma unroll
+            for (int j = 1; j < 5; ++j) q = __fadd_rn(q, __fmul_rn(in[j], F2[j]));
+            cf[2] = q;
+        }
+        cf[3] = __fmul_rn(kv[0], h);
+        cf[4] = a;
+        for (int w = first; w < first + cnt; ++w) {
+            const double x = ((double)wanted[w] - t0) / (t1 - t0);                // Interpolation.interpolate :73-84
+            double xs[5]; xs[4] = 1.0;
+#pragma unroll
+            for (int q = 3; q >= 0; --q) xs[q] = xs[q + 1] * x;
+            float r = __fmul_rn(cf[0], (float)xs[0]);
+#pragma unroll
+            for (int q = 1; q < 5; ++q) r = __fadd_rn(r, __fmul_rn(cf[q], (float)xs[q]));
+            out[(long long)w * out_stride + i] = r;
+        }
+    }
+}
+
+// InterpolatingStepListener.begin :59-69 / done :142-150 edge cases: copy the state if a requested time coincides
+// (1e-10) with the start / end time.
+__global__ void __launch_bounds__(256) k_dense_edge(const Ctrl* __restrict__ c, const float* __restrict__ Ybase, long long stride,
+                                                     long long n, const float* __restrict__ wanted, int which_wanted, int at_end,
+                                                     float* __restrict__ out, long long out_stride) {
+    const double tref = at_end ? (double)c->t : (double)c->t_start;
+    if (!(fabs(tref - (double)wanted[which_wanted]) < 1e-10)) return;
+    const float* __restrict__ y = Ybase + (long long)c->y_cur * stride;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+        out[(long long)which_wanted * out_stride + i] = y[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Small helpers around a solve
+// ---------------------------------------------------------------------------------------------------
+// dst <- Y[y_cur]  (the caller's yOut after integrate, AdaptiveRungeKuttaSolver.java:126)
+__global__ void __launch_bounds__(256) k_copy_from_state(const Ctrl* __restrict__ c, const float* __restrict__ Ybase, long long stride,
+                                                          long long off, float* __restrict__ dst, long long n) {
+    const float* __restrict__ y = Ybase + (long long)c->y_cur * stride + off;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) dst[i] = y[i];
+}
+// Y[y_cur][off:off+n] <- src (+ optional add)
+__global__ void __launch_bounds__(256) k_copy_to_state(const Ctrl* __restrict__ c, float* __restrict__ Ybase, long long stride, long long off,
+                                                        const float* __restrict__ src, const float* __restrict__ add, long long n) {
+    float* __restrict__ y = Ybase + (long long)c->y_cur * stride + off;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+        y[i] = add ? __fadd_rn(src[i], add[i]) : src[i];
+}
+__global__ void __launch_bounds__(256) k_fill(float* __restrict__ p, float v, long long n) {
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) p[i] = v;
+}
+
+// <a, b> in double -> (float) out[idx]; used for CalcTimeGrad.calcTimeAdjointT1 :52-58
+__global__ void __launch_bounds__(256) k_dot(const float* __restrict__ a, const float* __restrict__ b, long long n, double* acc) {
+    double s[1] = {0.0};
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) s[0] += (double)a[i] * (double)b[i];
+    block_sum<1>(s);
+    if (threadIdx.x == 0) atomicAdd(acc, s[0]);
+}
+
+}  // namespace n4j

@@ -97,6 +97,16 @@ const double TAB_CMID[7] = {6025192743.0 / 30085553152.0 / 2.0, 0.0, 51252292925
 
 template <class R> inline R rabs(R x) { return x < 0 ? -x : x; }
 
+// Sensitivity probe (tests only): relative perturbation applied to every contraction result, emulating the
+// different summation order of another implementation.  0 = off.
+double g_probe_noise = 0.0;
+inline double probe(double v, int64_t idx) {
+    if (g_probe_noise == 0.0) return v;
+    uint64_t x = (uint64_t)idx * 0x9E3779B97F4A7C15ull; x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 32;
+    const double u = (double)(x & 0xFFFFF) / (double)0xFFFFF * 2.0 - 1.0;
+    return v * (1.0 + g_probe_noise * u);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Inner graph (the RHS f) — restates what ForwardPass.evaluate (J/ode/vertex/impl/helper/forward/
 // ForwardPass.java:62-102) and BackpropagateAdjoint.backPropagate (J/.../backward/
@@ -251,7 +261,7 @@ template <class R> struct Net {
                         }
                 }
                 R* yp = y + (b * Co + co) * H * W;
-                for (int64_t p = 0; p < H * W; ++p) yp[p] = act_fwd<R>(l.d.activation, (R)acc[p]);
+                for (int64_t p = 0; p < H * W; ++p) yp[p] = act_fwd<R>(l.d.activation, (R)probe(acc[p], (b * Co + co) * H * W + p));
             }
     }
     void bn_fwd(size_t li, const LayerPlan& l, const R* x, R* y) {
@@ -373,7 +383,7 @@ template <class R> struct Net {
                                         acc[kh * 3 + kw] += a;
                                     }
                             }
-                            for (int k = 0; k < 9; ++k) dW[(co * Ci + ci) * 9 + k] = (R)acc[k];
+                            for (int k = 0; k < 9; ++k) dW[(co * Ci + ci) * 9 + k] = (R)probe(acc[k], (co * Ci + ci) * 9 + k);
                         }
                     // dgrad: dx[b,ci,y,x] = sum_{co,kh,kw} delta[b,co,y-kh+1,x-kw+1] * W[co,ci,kh,kw]
 #pragma omp parallel for collapse(2)
@@ -396,7 +406,7 @@ template <class R> struct Net {
                                     }
                             }
                             R* op = gout.data() + (b * Ci + ci) * H * W;
-                            for (int64_t p = 0; p < H * W; ++p) op[p] = (R)acc[p];
+                            for (int64_t p = 0; p < H * W; ++p) op[p] = (R)probe(acc[p], (b * Ci + ci) * H * W + p);
                         }
                     break;
                 }
@@ -960,6 +970,7 @@ void orc_tableau(double* a36, double* b7, double* e7, double* c6, double* cmid7)
     for (int j = 0; j < 7; ++j) { b7[j] = TAB_B[j]; e7[j] = TAB_E[j]; cmid7[j] = TAB_CMID[j]; }
     for (int j = 0; j < 6; ++j) c6[j] = TAB_C[j];
 }
+void orc_set_probe_noise(double rel) { g_probe_noise = rel; }
 int orc_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

