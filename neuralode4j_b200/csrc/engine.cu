@@ -225,6 +225,7 @@ SolverParams Engine::solver_params(long long n_norm) const {
 void Engine::bind_params(const float* p, long long n) {
     if (n != n_params_) throw Error{N4J_ERR_INVALID_ARGUMENT, "parameter vector has " + std::to_string(n) + " entries, inner graph needs " + std::to_string(n_params_)};
     user_params_ = p;
+    params_fresh_ = false;
 }
 
 // re-read the caller's flat parameter buffer (the updater changes it between iterations) and derive the
@@ -571,6 +572,7 @@ void Engine::forward(const float* y0, const float* t, int nt, int interpolate, f
     else std::memcpy(th.data(), t, sizeof(float) * nt);
     reset_ctrl();
     upload_params();
+    params_fresh_ = true;
     ensure_zt((long long)nt * nz_);
     ensure(io_, (long long)nt * nz_);
     // Y[0] <- y0 (internal layout); zt_[0] keeps z(t0) for the multi-time output (MultiStep.java:49-60)
@@ -672,7 +674,9 @@ void Engine::backward(const float* last_output, const float* dLdz, const float* 
     const int tslot = tg ? 1 : 0;
     const long long T = nt == 2 ? 1 : nt;          // stored time slices
     reset_ctrl();
-    upload_params();
+    // the forward of this iteration already uploaded the parameters (the updater only runs after the backward pass)
+    if (!params_fresh_) upload_params();
+    params_fresh_ = false;
     ensure_zt(std::max<long long>(T, 2) * nz_);
     ensure(gt_, T * nz_);
     ensure(io_, T * nz_);
@@ -852,6 +856,51 @@ void Engine::bench_solver_pass(long long n, int iters, float* us) {
     cudaFree(Y); cudaFree(K); cudaFree(c);
 }
 
+// Average device time of one launch sequence of a named piece of the hot path on the engine's real buffers.
+void Engine::bench_piece(int what, int iters, float* us) {
+    N4J_CUDA(cudaSetDevice(device_));
+    if (params_fresh_ == false && user_params_) { launches_ = 0; upload_params(); }
+    Ref yin = fixed_ref(Y_), kout = fixed_ref(K_);
+    auto piece = [&]() {
+        switch (what) {
+            case N4J_BENCH_RHS_FWD: enqueue_rhs_fwd(stream_, yin, kout); break;
+            case N4J_BENCH_RHS_AUG: enqueue_rhs_aug(stream_, yin, kout); break;
+            case N4J_BENCH_CONV_FWD:
+            case N4J_BENCH_CONV_DGRAD:
+            case N4J_BENCH_CONV_WGRAD: {
+                LayerPlan* lp = nullptr;
+                for (auto& l : L_) if (l.d.kind == N4J_LAYER_CONV3X3) { lp = &l; break; }
+                if (!lp) throw Error{N4J_ERR_INVALID_ARGUMENT, "inner graph has no conv3x3 layer"};
+                LayerPlan& l = *lp;
+                if (what == N4J_BENCH_CONV_FWD) {
+                    GemmArgs g{}; g.a = fixed_ref(gb_[0].p); g.c = fixed_ref(gb_[1].p); g.w = l.wf; g.M = (int)l.rows; g.N = l.c_out; g.K = 9 * l.c_in;
+                    g.act = 0; g.H = l.H; g.W = l.W; g.Ci = l.c_in; g.Co = l.c_out; g.splits = 1;
+                    launch_gemm<G_CONV_FWD>(stream_, g, launches_, exact_);
+                } else if (what == N4J_BENCH_CONV_DGRAD) {
+                    GemmArgs q{}; q.a = fixed_ref(gb_[0].p); q.c = fixed_ref(gb_[1].p); q.w = l.wb; q.M = (int)l.rows; q.N = l.c_in; q.K = 9 * l.c_out;
+                    q.H = l.H; q.W = l.W; q.Ci = l.c_in; q.Co = l.c_out; q.splits = 1;
+                    launch_gemm<G_CONV_DGRAD>(stream_, q, launches_, exact_);
+                } else {
+                    GemmArgs w{}; w.a = fixed_ref(gb_[0].p); w.b = fixed_ref(gb_[1].p); w.c = fixed_ref(wpart_.p); w.M = 9 * l.c_in; w.N = l.c_out; w.K = (int)l.rows;
+                    w.H = l.H; w.W = l.W; w.Ci = l.c_in; w.Co = l.c_out; w.splits = 16;
+                    launch_gemm<G_CONV_WGRAD>(stream_, w, launches_, exact_);
+                    if (!exact_) LAUNCH(k_splitk_reduce, grid_for(l.g_len), 256, stream_, wpart_.p, fixed_ref(theta_tmp_.p), l.g_len, 16);
+                }
+                break;
+            }
+            default: throw Error{N4J_ERR_INVALID_ARGUMENT, "unknown bench piece"};
+        }
+    };
+    for (int i = 0; i < 3; ++i) piece();
+    N4J_CUDA(cudaEventRecord(ev0_, stream_));
+    for (int i = 0; i < iters; ++i) piece();
+    N4J_CUDA(cudaEventRecord(ev1_, stream_));
+    N4J_CUDA(cudaStreamSynchronize(stream_));
+    float ms = 0;
+    N4J_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    *us = ms * 1000.f / (float)iters;
+}
+
 }  // namespace n4j
 
 // =====================================================================================================
@@ -940,6 +989,12 @@ int32_t node4j_comm_unique_id(void*) {
 }
 int32_t node4j_bench_solver_pass(n4j_handle* h, int64_t n, int32_t iters, float* us_per_pass) {
     return guarded([&] { h->eng->bench_solver_pass(n, iters, us_per_pass); });
+}
+int32_t node4j_bench_piece(n4j_handle* h, int32_t what, int32_t iters, float* us_per_iter) {
+    return guarded([&] { h->eng->bench_piece(what, iters, us_per_iter); });
+}
+int32_t node4j_get_stream(n4j_handle* h, void** stream) {
+    return guarded([&] { *stream = (void*)h->eng->stream(); });
 }
 
 }  // extern "C"

@@ -58,6 +58,8 @@ public:
     void rhs_vjp(const float* z, float t, const float* g, float* fz, float* dz, float* dreal);
     void error_norm(const float* K, const float* y0, const float* y1, float step, long long n, float* err_out);
     void bench_solver_pass(long long n, int iters, float* us);
+    void bench_piece(int what, int iters, float* us);
+    cudaStream_t stream() const { return stream_; }
 
 private:
     // ---- plan ------------------------------------------------------------------------------------
@@ -94,6 +96,7 @@ private:
     float* tg_ = nullptr;         // [0]=lastTime (CalcMultiStepTimeGrad.java:18), [1]=current d
     DevBuf params_, gradflat_, zt_, gt_, io_, io2_, gb_[3], theta_tmp_, wpart_, dldt_;
     const float* user_params_ = nullptr;
+    bool params_fresh_ = false;   // device copy of the parameters is current (set by forward, consumed by backward)
     bool have_last_output_ = false;
     int last_nt_ = 0;
     std::map<long long, SolveGraph> graphs_;

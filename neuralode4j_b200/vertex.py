@@ -354,6 +354,16 @@ class OdeVertexImpl:
         _lib.check(self._L.node4j_error_norm(self._h, _ptr(K), _ptr(y0), _ptr(y1), float(h), n, C.byref(out)))
         return out.value
 
+    def bench_piece(self, what: int, iters: int = 20) -> float:
+        us = C.c_float()
+        _lib.check(self._L.node4j_bench_piece(self._h, what, iters, C.byref(us)))
+        return us.value
+
+    def cuda_stream(self) -> int:
+        s = C.c_void_p()
+        _lib.check(self._L.node4j_get_stream(self._h, C.byref(s)))
+        return int(s.value or 0)
+
     def bench_solver_pass(self, n: int, iters: int = 20) -> float:
         us = C.c_float()
         _lib.check(self._L.node4j_bench_solver_pass(self._h, n, iters, C.byref(us)))

@@ -1,0 +1,128 @@
+"""CPU tests of the host-side mirror of the reference interface and of the C-ABI library surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import neuralode4j_b200 as N
+from neuralode4j_b200 import _lib, build as nbuild
+from neuralode4j_b200 import workloads as W
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "node4j.h")).read()
+    declared = sorted(set(re.findall(r"\b(node4j_[a-z_0-9]+)\s*\(", header)))
+    assert declared, "no entry points found in include/node4j.h"
+    L = _lib.load()
+    for name in declared:
+        assert hasattr(L, name), f"libnode4j_b200.so does not export {name}"
+    assert sorted(_lib.EXPORTS) == declared
+    assert L.node4j_abi_version() == 1
+
+
+def test_library_is_built_for_sm_100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "--list-elf", nbuild.LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    assert not re.search(r"sm_(?!100a)\d+", out)
+
+
+def test_no_cpu_fallback_without_device():
+    L = _lib.load()
+    if L.node4j_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    w = W.golden_linear()
+    with pytest.raises(_lib.Node4jError) as e:
+        w.conf.instantiate(w.shape)
+    assert e.value.code == _lib.ERR_CUDA
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "neuralode4j_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("bit-compatible with the oracle", "").replace("bit-comparable with the CPU oracle", "") \
+                    .replace("the oracle", "").replace("CPU oracle", "").replace("oracle/node_oracle.cpp", "").replace("to the oracle", ""), f
+    assert "oracle" not in open(os.path.join(ROOT, "include", "node4j.h")).read().replace("CPU oracle", "")
+
+
+def test_solver_config_validation_and_equality():
+    with pytest.raises(ValueError):                       # SolverConfig.java:22-24
+        N.SolverConfig(1e-3, 1e-3, 1.0, 1.0)
+    a = N.DormandPrince54Solver(N.SolverConfig(1e-3, 1e-4, 1e-10, 10))
+    b = a.clone()
+    assert a == b and a is not b and a.config is not b.config
+    assert N.DormandPrince54Solver().config == N.SolverConfig(1e-3, 1e-3, 1e-10, 100)   # DormandPrince54Solver.java:31-33
+    a.addListeners(N.StepCounter())
+    assert a.clone().listeners == []                      # listeners are not cloned (:46-52)
+
+
+def test_conf_json_round_trip():
+    # AbstractConfTest.java:21-43 / OdeVertexTest.java:56-120: serialise, deserialise, equal
+    for w in (W.mnist_block(batch=2), W.spiral_block(batch=2), W.golden_linear()):
+        d = w.conf.to_json()
+        back = N.OdeVertex.from_json(d)
+        assert back == w.conf
+        assert back.to_json() == d
+        assert back.clone() == w.conf
+    d = W.golden_linear().conf.to_json()
+    assert d["odeForwardConf"]["@class"] == "ode.vertex.conf.helper.InputStep"
+    assert d["odeForwardConf"]["solverConf"]["@class"] == "ode.solve.conf.DormandPrince54Solver"
+    assert set(d["odeForwardConf"]["solverConf"]["config"]) == {"absoluteTolerance", "relativeTolerance", "minStep", "maxStep"}
+
+
+def test_builder_rejects_what_is_outside_the_native_set():
+    b = N.OdeVertex.Builder(None, "a", N.DenseLayer(4, 4))
+    with pytest.raises(NotImplementedError):
+        b.addLayer("b", N.DenseLayer(4, 4), "nonexistent")
+    with pytest.raises(NotImplementedError):
+        b.addVertex("v", object(), "a")
+    with pytest.raises(NotImplementedError):
+        b.addTimeLayer("t", N.DenseLayer(4, 4))
+    with pytest.raises(NotImplementedError):
+        N.Convolution2D(8, kernelSize=(5, 5))
+    with pytest.raises(NotImplementedError):
+        N.Convolution2D(8, hasBias=True)
+    with pytest.raises(NotImplementedError):
+        N.DenseLayer(3, 3, activation="softmax").desc()
+
+
+def test_default_ode_conf_matches_reference_default():
+    v = N.OdeVertex.Builder(None, "a", N.DenseLayer(4, 4)).build()   # OdeVertex.java:168-169
+    assert isinstance(v.odeForwardConf, N.FixedStep)
+    np.testing.assert_array_equal(v.odeForwardConf.time, [0, 1])
+    assert v.odeForwardConf.interpolateForwardIfMultiStep is True
+
+
+def test_num_params_matches_layout():
+    w = W.mnist_block(batch=2)
+    assert w.conf.numParams(w.shape) == 2 * 36864 + 3 * 256 == w.params.size          # 74 496
+    s = W.spiral_block(batch=2)
+    assert s.conf.numParams(s.shape) == 4 * 20 + 20 + 20 * 20 + 20 + 20 * 4 + 4 == s.params.size   # 604
+
+
+def test_step_counter_and_mask_semantics():
+    # StepCounter.java:46-63, Mask.java:24-47
+    got = []
+    c = N.StepCounter(2, "avg: ", consumer=lambda steps, solves: got.append((steps, solves)))
+    fwd_only = N.Mask.backward(c)            # "masks backward": passes forward-in-time solves
+    for t, nsteps in (([0, 1], 3), ([1, 0], 5), ([0, 2], 4)):
+        fwd_only.begin(np.array(t, dtype=np.float32), None)
+        for _ in range(nsteps):
+            fwd_only.step(None, 0.1, 0.5)
+        fwd_only.done()
+    assert got == [(7, 2)]
+
+
+def test_workload_shapes():
+    w = W.mnist_block()
+    assert w.shape == (128, 64, 7, 7) and int(np.prod(w.shape)) == 401408
+    assert 2 * 401408 + w.params.size == 877312                                          # N_aug of SURVEY.md section 8a
+    s = W.spiral_block()
+    assert s.time.size == 100 and abs(s.time[1] - 6 * np.pi / 499) < 1e-6
