@@ -152,7 +152,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     w = _workload()
-    v = w.conf.instantiate(w.shape, device=local_rank)
+    v = w.conf.instantiate(w.shape, device=local_rank, flags=args.flags)
     stream = torch.cuda.ExternalStream(v.cuda_stream(), device=local_rank)
     dev = torch.device("cuda", local_rank)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -314,6 +314,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--flags", type=int, default=0, help="N4J_FLAG_* bits for the engine (2 = host-driven step loop, which is "
+                    "what ncu can see: kernels inside a CUDA graph with a conditional node are not profilable)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,248 @@
+// conv_tc.cuh — 3x3 "same" convolution (64 -> 64 channels) as an implicit GEMM on the 5th-generation tensor cores.
+//
+// Replaces DL4J's ConvolutionLayer forward / backpropGradient reached from ForwardPass.java:81 and
+// BackpropagateAdjoint.java:109 (cuDNN / im2col+GEMM in the reference).
+//
+//   D[pixel, co] = sum_{tap} A[pixel + shift(tap), ci] * W_tap[ci, co]          fp32-faithful via 3xTF32:
+//   a*b ~= a_hi*b_hi + a_hi*b_lo + a_lo*b_hi   with hi = tf32(x), lo = x - hi, accumulated in fp32 in TMEM.
+//
+// The activation operand lives in global memory as a zero-padded, chunk-major image (tc_common.cuh):
+//   img[hl][chunk 0..15][guard + b*(H+2)*(W+2) + ph*(W+2) + pw][4]      hl = 0 (hi) / 1 (lo)
+// written by the producing BatchNorm-apply (or BatchNorm-backward) kernel, border pixels stay zero.  One CTA computes
+// 128 consecutive padded pixels x 64 output channels: the tile plus a halo of W+3 rows is staged ONCE by 32 bulk copies and
+// the nine taps are nine row-shifted shared-memory descriptors into it.  Weights stream per tap (hi+lo = 32 KB) through a
+// 4-deep mbarrier ring.  Warp roles: warp 0 = bulk-copy producer (+TMEM alloc), warp 1 = MMA issuer, warps 2-5 = epilogue
+// (TMEM -> registers -> compact NHWC rows, optional fused BatchNorm statistics for the next layer).
+#pragma once
+
+#include "common.cuh"
+#include "layer_kernels.cuh"
+#include "tc_common.cuh"
+
+namespace n4j {
+
+struct ConvGeom {
+    int B, H, W;      // logical
+    int PH, PW;       // padded: H+2, W+2
+    int halo;         // PW + 1 rows on each side of a tile
+    int guard;        // zero rows in front of / behind the image (>= halo, multiple of 4)
+    long long mpad;   // B*PH*PW padded pixels
+    long long rows;   // guard + round_up(mpad,128) + guard : rows per chunk of one hi/lo image
+    int tiles;        // ceil(mpad / 128)
+};
+
+inline ConvGeom make_conv_geom(int B, int H, int W) {
+    ConvGeom g;
+    g.B = B; g.H = H; g.W = W; g.PH = H + 2; g.PW = W + 2;
+    g.halo = g.PW + 1;
+    g.guard = (g.halo + 3) & ~3;
+    g.mpad = (long long)B * g.PH * g.PW;
+    g.tiles = (int)((g.mpad + 127) / 128);
+    g.rows = g.guard + (long long)g.tiles * 128 + g.guard;
+    return g;
+}
+inline long long conv_image_floats(const ConvGeom& g) { return 2LL * 16 * g.rows * 4; }   // hi + lo
+
+constexpr int CONV_TC_THREADS = 192;
+constexpr int CONV_TC_STAGES = 4;
+constexpr int CONV_TC_WSTAGE_BYTES = 2 * 16 * 64 * 16;   // hi+lo image of one tap: 32 KB
+
+inline size_t conv_tc_smem_bytes(const ConvGeom& g) {
+    const int rt = 128 + 2 * g.halo;
+    return (size_t)2 * 16 * rt * 16 + (size_t)CONV_TC_STAGES * CONV_TC_WSTAGE_BYTES + 256;
+}
+
+// weights: DL4J [Co,Ci,3,3] -> per-tap shared-memory images, hi then lo:  wimg[tap][hl][chunk = k/4][n][k%4]
+//   forward (mode 0): n = co, k = ci, tap as is              B_tap[ci,co] = W[co,ci,tap]
+//   dgrad   (mode 1): n = ci, k = co, tap flipped (8 - tap)  B_tap'[co,ci] = W[co,ci,8-tap']
+__global__ void __launch_bounds__(256) k_conv_w_to_tc(const float* __restrict__ w, float* __restrict__ wimg, int mode) {
+    const int n_el = 64 * 64 * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
+        const int tap = i % 9; const int r = i / 9; const int ci = r % 64; const int co = r / 64;
+        float hi, lo;
+        tc::split_tf32(w[i], hi, lo);
+        const int t2 = mode == 0 ? tap : 8 - tap;
+        const int n = mode == 0 ? co : ci;
+        const int k = mode == 0 ? ci : co;
+        const long long base = (long long)t2 * 2 * 4096 + ((k >> 2) * 64 + n) * 4 + (k & 3);
+        wimg[base] = hi;
+        wimg[base + 4096] = lo;
+    }
+}
+
+struct ConvTcArgs {
+    const float* img;     // operand image (hi then lo)
+    const float* wimg;    // weight images [9][2][4096]
+    Ref out;              // compact NHWC [B*H*W][64]
+    ConvGeom g;
+    int act;              // activation of the conv layer (identity in the reference's blocks)
+    // optional fused BatchNorm statistics of the OUTPUT (for a following BatchNorm layer)
+    double* stat_acc;     // [128] sum, sum of squares per channel, or null
+};
+
+template <int PASSES>
+__global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const ConvGeom& g = a.g;
+    const int rt = 128 + 2 * g.halo;                     // staged rows per chunk
+    const uint32_t a_chunk_bytes = (uint32_t)rt * 16;    // one chunk of one hi/lo image
+    const uint32_t a_img_bytes = 16 * a_chunk_bytes;
+    uint8_t* sA = smem_raw;                              // [2][16][rt][16B]
+    uint8_t* sW = sA + 2 * a_img_bytes;                  // [STAGES][2][16][64][16B]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + CONV_TC_STAGES * CONV_TC_WSTAGE_BYTES);
+    uint64_t* w_full = bars;                             // [STAGES]
+    uint64_t* w_empty = bars + CONV_TC_STAGES;           // [STAGES]
+    uint64_t* a_full = bars + 2 * CONV_TC_STAGES;
+    uint64_t* d_full = bars + 2 * CONV_TC_STAGES + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * CONV_TC_STAGES + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long m0 = (long long)blockIdx.x * 128;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CONV_TC_STAGES; ++s) { tc::mbar_init(&w_full[s], 1); tc::mbar_init(&w_empty[s], 1); }
+        tc::mbar_init(a_full, 1);
+        tc::mbar_init(d_full, 1);
+        tc::fence_barrier_init();
+    }
+    if (warp == 0) tc::tmem_alloc<64>(tmem_slot);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- producer: activation tile + halo once, then the nine weight taps through the ring ----
+            tc::mbar_arrive_expect_tx(a_full, 2 * a_img_bytes);
+            const long long row0 = g.guard + m0 - g.halo;
+            for (int hl = 0; hl < 2; ++hl)
+                for (int c = 0; c < 16; ++c)
+                    tc::bulk_g2s(sA + hl * a_img_bytes + c * a_chunk_bytes, a.img + (((long long)hl * 16 + c) * g.rows + row0) * 4,
+                                 a_chunk_bytes, a_full);
+            for (int tap = 0; tap < 9; ++tap) {
+                const int s = tap % CONV_TC_STAGES;
+                if (tap >= CONV_TC_STAGES) tc::mbar_wait(&w_empty[s], ((tap / CONV_TC_STAGES) - 1) & 1);
+                tc::mbar_arrive_expect_tx(&w_full[s], CONV_TC_WSTAGE_BYTES);
+                tc::bulk_g2s(sW + s * CONV_TC_WSTAGE_BYTES, a.wimg + (long long)tap * 2 * 4096, CONV_TC_WSTAGE_BYTES, &w_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer: 9 taps x 8 k-steps x 3 TF32 products, all into one 128x64 fp32 accumulator in TMEM ----
+            constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+            const uint32_t sA_u = tc::smem_u32(sA), sW_u = tc::smem_u32(sW);
+            tc::mbar_wait(a_full, 0);
+            uint32_t acc = 0;
+            for (int tap = 0; tap < 9; ++tap) {
+                const int s = tap % CONV_TC_STAGES;
+                tc::mbar_wait(&w_full[s], (tap / CONV_TC_STAGES) & 1);
+                tc::tc_fence_after();
+                const int shift = (tap / 3 - 1) * g.PW + (tap % 3 - 1);
+                const uint32_t a_row = (uint32_t)(g.halo + shift) * 16;
+                const uint32_t w_base = sW_u + s * CONV_TC_WSTAGE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < 8; ++kk) {
+                    const uint32_t a_hi = sA_u + (2 * kk) * a_chunk_bytes + a_row;
+                    const uint32_t a_lo = a_hi + a_img_bytes;
+                    const uint32_t b_hi = w_base + (2 * kk) * 1024;
+                    const uint32_t b_lo = b_hi + 16384;
+                    const uint64_t dAh = tc::smem_desc(a_hi, a_chunk_bytes, 128), dAl = tc::smem_desc(a_lo, a_chunk_bytes, 128);
+                    const uint64_t dBh = tc::smem_desc(b_hi, 1024, 128), dBl = tc::smem_desc(b_lo, 1024, 128);
+                    if (PASSES == 3) {
+                        tc::mma_tf32(tmem, dAh, dBl, idesc, acc); acc = 1;
+                        tc::mma_tf32(tmem, dAl, dBh, idesc, 1);
+                    }
+                    if (PASSES >= 1) { tc::mma_tf32(tmem, dAh, dBh, idesc, acc); acc = 1; }
+                }
+                tc::mma_commit(&w_empty[s]);
+            }
+            tc::mma_commit(d_full);
+        }
+    } else {
+        // ---- epilogue: TMEM lane = tile row; each thread owns one padded pixel and its 64 output channels ----
+        const int q = warp & 3;                    // TMEM lane quadrant this warp may read
+        const int row = q * 32 + lane;
+        const long long m = m0 + row;
+        bool valid = m < g.mpad;
+        long long crow = 0;
+        if (valid) {
+            const int per = g.PH * g.PW;
+            const int b = (int)(m / per);
+            const int rem = (int)(m - (long long)b * per);
+            const int ph = rem / g.PW, pw = rem - ph * g.PW;
+            valid = ph >= 1 && ph <= g.H && pw >= 1 && pw <= g.W;
+            crow = ((long long)b * g.H + (ph - 1)) * g.W + (pw - 1);
+        }
+        float* __restrict__ out = resolve(a.out);
+        tc::mbar_wait(d_full, 0);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + half * 32, v);
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(out + crow * 64 + half * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(act_fwd(a.act, v[4 * j]), act_fwd(a.act, v[4 * j + 1]), act_fwd(a.act, v[4 * j + 2]), act_fwd(a.act, v[4 * j + 3]));
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Operand producers: write the zero-padded chunk-major hi/lo image the tensor kernels read
+// ---------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ long long padded_row(const ConvGeom& g, long long crow) {
+    const int hw = g.H * g.W;
+    const int b = (int)(crow / hw);
+    const int rem = (int)(crow - (long long)b * hw);
+    const int h = rem / g.W, w = rem - h * g.W;
+    return g.guard + ((long long)b * g.PH + h + 1) * g.PW + (w + 1);
+}
+__device__ __forceinline__ void store_split4(float* __restrict__ img, const ConvGeom& g, int chunk, long long prow, float4 y) {
+    float4 hi, lo;
+    tc::split_tf32(y.x, hi.x, lo.x); tc::split_tf32(y.y, hi.y, lo.y); tc::split_tf32(y.z, hi.z, lo.z); tc::split_tf32(y.w, hi.w, lo.w);
+    float4* p = reinterpret_cast<float4*>(img + ((long long)chunk * g.rows + prow) * 4);
+    p[0] = hi;
+    reinterpret_cast<float4*>(img + ((long long)(16 + chunk) * g.rows + prow) * 4)[0] = lo;
+}
+
+// y = act(gamma*((x-mean)*invstd)+beta) -> operand image (and optionally the compact activation as well)
+__global__ void __launch_bounds__(256) k_bn_apply_to_image(Ref xin, const float* __restrict__ gamma, const float* __restrict__ beta, BnScratch sc,
+                                                            int act, ConvGeom g, float* __restrict__ img, float* __restrict__ compact) {
+    const float* __restrict__ x = resolve(xin);
+    const long long n4 = (long long)g.B * g.H * g.W * 16;     // float4 groups: [crow][chunk]
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+        const int chunk = (int)(i & 15);
+        const long long crow = i >> 4;
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        const int c = chunk * 4;
+        float4 y;
+        y.x = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c], __fmul_rn(__fsub_rn(v.x, sc.mean[c]), sc.invstd[c])), beta[c]));
+        y.y = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c + 1], __fmul_rn(__fsub_rn(v.y, sc.mean[c + 1]), sc.invstd[c + 1])), beta[c + 1]));
+        y.z = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c + 2], __fmul_rn(__fsub_rn(v.z, sc.mean[c + 2]), sc.invstd[c + 2])), beta[c + 2]));
+        y.w = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c + 3], __fmul_rn(__fsub_rn(v.w, sc.mean[c + 3]), sc.invstd[c + 3])), beta[c + 3]));
+        store_split4(img, g, chunk, padded_row(g, crow), y);
+        if (compact) reinterpret_cast<float4*>(compact)[i] = y;
+    }
+}
+
+// compact NHWC [rows][64] -> operand image (used for gradients that feed dgrad/wgrad and by the unit probe)
+__global__ void __launch_bounds__(256) k_compact_to_image(Ref xin, ConvGeom g, float* __restrict__ img) {
+    const float* __restrict__ x = resolve(xin);
+    const long long n4 = (long long)g.B * g.H * g.W * 16;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+        const int chunk = (int)(i & 15);
+        const long long crow = i >> 4;
+        store_split4(img, g, chunk, padded_row(g, crow), reinterpret_cast<const float4*>(x)[i]);
+    }
+}
+
+}  // namespace n4j

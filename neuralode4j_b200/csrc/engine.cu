@@ -141,6 +141,21 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
             N4J_CUDA(cudaMalloc(&l.wf, sizeof(float) * l.p_len));
             N4J_CUDA(cudaMalloc(&l.wb, sizeof(float) * l.p_len));
             ensure(wpart_, 16LL * l.p_len);
+            // tensor-core path: 64->64 channels, identity activation, default (non-parity) mode
+            l.tc = !exact_ && !(cfg_.flags & N4J_FLAG_NO_TENSOR) && l.c_in == 64 && l.c_out == 64 && l.d.activation == N4J_ACT_IDENTITY;
+            if (l.tc) {
+                geom_ = make_conv_geom((int)B_, H_, W_);
+                conv_smem_ = conv_tc_smem_bytes(geom_);
+                const size_t img_bytes = sizeof(float) * conv_image_floats(geom_);
+                N4J_CUDA(cudaMalloc(&l.img, img_bytes));
+                N4J_CUDA(cudaMalloc(&l.gimg, img_bytes));
+                N4J_CUDA(cudaMemsetAsync(l.img, 0, img_bytes, stream_));    // zero padding is written once and never touched
+                N4J_CUDA(cudaMemsetAsync(l.gimg, 0, img_bytes, stream_));
+                N4J_CUDA(cudaMalloc(&l.wimg_f, sizeof(float) * 9 * 2 * 4096));
+                N4J_CUDA(cudaMalloc(&l.wimg_b, sizeof(float) * 9 * 2 * 4096));
+                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
+                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
+            }
         }
         if (l.d.kind == N4J_LAYER_BATCHNORM) {
             const int cc = l.c_out;
@@ -164,7 +179,7 @@ Engine::~Engine() {
         if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
     }
     for (auto& l : L_) {
-        cudaFree(l.act); cudaFree(l.wf); cudaFree(l.wb);
+        cudaFree(l.act); cudaFree(l.wf); cudaFree(l.wb); cudaFree(l.img); cudaFree(l.gimg); cudaFree(l.wimg_f); cudaFree(l.wimg_b);
         if (l.d.kind == N4J_LAYER_BATCHNORM) { cudaFree(l.bn.acc); cudaFree(l.bn.ticket); cudaFree(l.bn.mean); }
     }
     for (DevBuf* b : {&params_, &gradflat_, &zt_, &gt_, &io_, &io2_, &gb_[0], &gb_[1], &gb_[2], &theta_tmp_, &wpart_, &dldt_}) cudaFree(b->p);
@@ -235,8 +250,13 @@ void Engine::upload_params() {
     if (!user_params_) throw Error{N4J_ERR_ILLEGAL_STATE, "parameters not bound (node4j_bind_params)"};
     to_device(params_.p, user_params_, n_params_);
     for (auto& l : L_)
-        if (l.d.kind == N4J_LAYER_CONV3X3)
+        if (l.d.kind == N4J_LAYER_CONV3X3) {
             LAUNCH(k_conv_w_to_internal, grid_for(l.p_len), 256, stream_, params_.p + l.p_off, l.wf, l.wb, l.c_out, l.c_in);
+            if (l.tc) {
+                LAUNCH(k_conv_w_to_tc, 64, 256, stream_, params_.p + l.p_off, l.wimg_f, 0);
+                LAUNCH(k_conv_w_to_tc, 64, 256, stream_, params_.p + l.p_off, l.wimg_b, 1);
+            }
+        }
 }
 
 void Engine::state_in(const float* user, float* internal) {
@@ -285,8 +305,17 @@ static void launch_gemm(cudaStream_t s, GemmArgs g, int& launches, bool exact) {
     ++launches;
 }
 
-void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out) {
+void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act) {
+    ConvTcArgs a{};
+    a.img = img; a.wimg = wimg; a.out = out; a.g = geom_; a.act = act; a.stat_acc = nullptr;
+    if (cfg_.flags & N4J_FLAG_FAST_TF32) k_conv3x3_tc<1><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
+    else k_conv3x3_tc<3><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
+    ++launches_;
+}
+
+void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact) {
     Ref cur = in;
+    bool image_ready = false;   // the previous layer already wrote the operand image of this (tensor-core) conv
     for (size_t i = 0; i < L_.size(); ++i) {
         LayerPlan& l = L_[i];
         Ref dst = (i + 1 == L_.size()) ? out : fixed_ref(l.act);
@@ -304,6 +333,12 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out) {
                 break;
             }
             case N4J_LAYER_CONV3X3: {
+                if (l.tc) {
+                    if (!image_ready) LAUNCH(k_compact_to_image, grid_for(l.in_len / 4), 256, s, cur, geom_, l.img);
+                    launch_conv_tc(s, l.img, l.wimg_f, dst, l.d.activation);
+                    image_ready = false;
+                    break;
+                }
                 GemmArgs g{}; g.a = cur; g.c = dst; g.w = l.wf; g.M = (int)l.rows; g.N = l.c_out; g.K = 9 * l.c_in;
                 g.act = l.d.activation; g.H = l.H; g.W = l.W; g.Ci = l.c_in; g.Co = l.c_out; g.splits = 1;
                 launch_gemm<G_CONV_FWD>(s, g, launches_, exact_);
@@ -312,6 +347,7 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out) {
             case N4J_LAYER_BATCHNORM: {
                 const int cc = l.c_out;
                 const bool vec = (cc % 4 == 0) && (256 % (cc / 4) == 0) && (cc / 4 <= 256);
+                const bool feeds_tc = i + 1 < L_.size() && L_[i + 1].d.kind == N4J_LAYER_CONV3X3 && L_[i + 1].tc;
                 if (vec) {
                     const int rows_per_iter = 256 / (cc / 4);
                     int grid = (int)std::max<long long>(1, std::min<long long>(148, (l.rows + rows_per_iter - 1) / rows_per_iter));
@@ -319,7 +355,15 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out) {
                 } else {
                     LAUNCH(k_bn_stats_generic, cc, 256, s, cur, l.rows, cc, l.d.eps, l.bn);
                 }
-                LAUNCH(k_bn_apply, grid_for(l.out_len), 256, s, cur, dst, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn, l.d.activation, l.rows, cc);
+                if (feeds_tc) {
+                    // BatchNorm-apply writes the next conv's operand image directly (hi/lo split, zero-padded, chunk-major);
+                    // the compact activation is only needed by the backward pass
+                    LAUNCH(k_bn_apply_to_image, grid_for(l.out_len / 4), 256, s, cur, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn,
+                           l.d.activation, geom_, L_[i + 1].img, need_compact ? l.act : (float*)nullptr);
+                    image_ready = true;
+                } else {
+                    LAUNCH(k_bn_apply, grid_for(l.out_len), 256, s, cur, dst, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn, l.d.activation, l.rows, cc);
+                }
                 break;
             }
             case N4J_LAYER_ACTIVATION:
@@ -333,7 +377,7 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out) {
 // BackpropagateAdjoint.calculateDerivative :63-85 on the layout [z | a | theta | a_t]:
 //   out.z <- f(z,t);  out.a <- (-a)^T df/dz;  out.theta <- (-a)^T df/dtheta;  out.a_t stays 0 (NoTimeInput.java:26-29)
 void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out) {
-    enqueue_rhs_fwd(s, in, out);
+    enqueue_rhs_fwd(s, in, out, true);
     Ref g = with_off(in, off_a_);
     float gscale = -1.f;                                 // zAdjoint().negi() :75
     int gi = 0;
@@ -380,9 +424,14 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out) {
                     if (exact_) w.c = dth;
                     launch_gemm<G_CONV_WGRAD>(s, w, launches_, exact_);
                     if (!exact_) LAUNCH(k_splitk_reduce, grid_for(l.g_len), 256, s, wpart_.p, dth, l.g_len, 16);
-                    GemmArgs q{}; q.a = d; q.c = dx; q.w = l.wb; q.M = (int)l.rows; q.N = l.c_in; q.K = 9 * l.c_out;
-                    q.H = l.H; q.W = l.W; q.Ci = l.c_in; q.Co = l.c_out; q.splits = 1;
-                    launch_gemm<G_CONV_DGRAD>(s, q, launches_, exact_);
+                    if (l.tc) {
+                        LAUNCH(k_compact_to_image, grid_for(l.out_len / 4), 256, s, d, geom_, l.gimg);
+                        launch_conv_tc(s, l.gimg, l.wimg_b, dx, N4J_ACT_IDENTITY);
+                    } else {
+                        GemmArgs q{}; q.a = d; q.c = dx; q.w = l.wb; q.M = (int)l.rows; q.N = l.c_in; q.K = 9 * l.c_out;
+                        q.H = l.H; q.W = l.W; q.Ci = l.c_in; q.Co = l.c_out; q.splits = 1;
+                        launch_gemm<G_CONV_DGRAD>(s, q, launches_, exact_);
+                    }
                 }
                 break;
             }
@@ -872,7 +921,11 @@ void Engine::bench_piece(int what, int iters, float* us) {
                 for (auto& l : L_) if (l.d.kind == N4J_LAYER_CONV3X3) { lp = &l; break; }
                 if (!lp) throw Error{N4J_ERR_INVALID_ARGUMENT, "inner graph has no conv3x3 layer"};
                 LayerPlan& l = *lp;
-                if (what == N4J_BENCH_CONV_FWD) {
+                if (l.tc && what == N4J_BENCH_CONV_FWD) {
+                    launch_conv_tc(stream_, l.img, l.wimg_f, fixed_ref(gb_[1].p), N4J_ACT_IDENTITY);
+                } else if (l.tc && what == N4J_BENCH_CONV_DGRAD) {
+                    launch_conv_tc(stream_, l.gimg, l.wimg_b, fixed_ref(gb_[1].p), N4J_ACT_IDENTITY);
+                } else if (what == N4J_BENCH_CONV_FWD) {
                     GemmArgs g{}; g.a = fixed_ref(gb_[0].p); g.c = fixed_ref(gb_[1].p); g.w = l.wf; g.M = (int)l.rows; g.N = l.c_out; g.K = 9 * l.c_in;
                     g.act = 0; g.H = l.H; g.W = l.W; g.Ci = l.c_in; g.Co = l.c_out; g.splits = 1;
                     launch_gemm<G_CONV_FWD>(stream_, g, launches_, exact_);

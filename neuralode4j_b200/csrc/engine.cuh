@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv_tc.cuh"
 #include "layer_kernels.cuh"
 #include "solver_kernels.cuh"
 
@@ -26,6 +27,11 @@ struct LayerPlan {
     float* act = nullptr;    // output of this layer (scratch), unused for the last layer
     float* wf = nullptr;     // conv: [tap][ci][co]
     float* wb = nullptr;     // conv: [tap][co][ci]
+    bool tc = false;         // conv runs on the tcgen05 path
+    float* img = nullptr;    // conv: operand image of the layer input (hi/lo, padded, chunk-major)
+    float* gimg = nullptr;   // conv: operand image of the gradient w.r.t. the layer output
+    float* wimg_f = nullptr; // conv: per-tap weight images, forward
+    float* wimg_b = nullptr; // conv: per-tap weight images, dgrad (flipped taps, transposed)
     BnScratch bn{};
 };
 
@@ -66,6 +72,8 @@ private:
     int device_;
     n4j_solver_cfg cfg_;
     bool exact_ = false;       // N4J_FLAG_EXACT_CONTRACTIONS
+    ConvGeom geom_{};          // padded geometry shared by all conv layers of the block
+    size_t conv_smem_ = 0;
     std::vector<LayerPlan> L_;
     int rank_;
     long long B_;
@@ -118,9 +126,10 @@ private:
     void theta_internal_to_flat(const float* theta, float* flat);
     void theta_internal_to_real(const float* theta, float* real);
 
-    void enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out);
+    void enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact = true);
     void enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out);
-    void enqueue_rhs(cudaStream_t s, bool aug, Ref in, Ref out) { aug ? enqueue_rhs_aug(s, in, out) : enqueue_rhs_fwd(s, in, out); }
+    void launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act);
+    void enqueue_rhs(cudaStream_t s, bool aug, Ref in, Ref out) { aug ? enqueue_rhs_aug(s, in, out) : enqueue_rhs_fwd(s, in, out, false); }
     void enqueue_prologue(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt);
     void enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt,
                        cudaGraphConditionalHandle cond, int use_cond);

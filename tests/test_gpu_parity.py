@@ -91,6 +91,21 @@ def test_rhs_conv_bn():
     _rhs_case(W.mnist_block(batch=16, channels=64), exact=False)
 
 
+def test_tensor_core_conv_matches_simt_conv():
+    """The tcgen05 3xTF32 implicit-GEMM convolution against the fp32 SIMT kernels on the same engine (config #2 block)."""
+    w = W.mnist_block(batch=128, channels=64)
+    rng = np.random.default_rng(5)
+    g = rng.standard_normal(w.shape).astype(np.float32)
+    res = []
+    for flags in (0, _lib.FLAG_NO_TENSOR):
+        v = w.conf.instantiate(w.shape, flags=flags)
+        v.setParams(w.params)
+        res.append(v.rhs_vjp(w.y0, g))
+        v.close()
+    for a, b, name in zip(res[0], res[1], ("f(z)", "g^T df/dz", "g^T df/dtheta")):
+        assert np.abs(a - b).max() <= 3e-5 * np.abs(b).max(), name
+
+
 def test_rhs_conv_bn_ragged_channels():
     _rhs_case(W.mnist_block(batch=5, channels=24, hw=5), exact=False)
 
