@@ -52,7 +52,8 @@ inline size_t conv_tc_smem_bytes(const ConvGeom& g) {
     return (size_t)2 * 16 * rt * 16 + (size_t)CONV_TC_STAGES * CONV_TC_WSTAGE_BYTES + 256;
 }
 
-// weights: DL4J [Co,Ci,3,3] -> per-tap shared-memory images, hi then lo:  wimg[tap][hl][chunk = k/4][n][k%4]
+// weights: DL4J [Co,Ci,3,3] -> per-tap shared-memory images with hi and lo stacked along N:
+//   wimg[tap][chunk = k/4][hl*64 + n][k%4]      (one UMMA with N=128 then yields a_hi*b_hi | a_hi*b_lo side by side)
 //   forward (mode 0): n = co, k = ci, tap as is              B_tap[ci,co] = W[co,ci,tap]
 //   dgrad   (mode 1): n = ci, k = co, tap flipped (8 - tap)  B_tap'[co,ci] = W[co,ci,8-tap']
 __global__ void __launch_bounds__(256) k_conv_w_to_tc(const float* __restrict__ w, float* __restrict__ wimg, int mode) {
@@ -64,9 +65,9 @@ __global__ void __launch_bounds__(256) k_conv_w_to_tc(const float* __restrict__ 
         const int t2 = mode == 0 ? tap : 8 - tap;
         const int n = mode == 0 ? co : ci;
         const int k = mode == 0 ? ci : co;
-        const long long base = (long long)t2 * 2 * 4096 + ((k >> 2) * 64 + n) * 4 + (k & 3);
+        const long long base = (long long)t2 * 8192 + ((k >> 2) * 128 + n) * 4 + (k & 3);
         wimg[base] = hi;
-        wimg[base + 4096] = lo;
+        wimg[base + 64 * 4] = lo;
     }
 }
 
@@ -76,11 +77,15 @@ struct ConvTcArgs {
     Ref out;              // compact NHWC [B*H*W][64]
     ConvGeom g;
     int act;              // activation of the conv layer (identity in the reference's blocks)
-    // optional fused BatchNorm statistics of the OUTPUT (for a following BatchNorm layer)
-    double* stat_acc;     // [128] sum, sum of squares per channel, or null
+    // optional fused BatchNorm statistics of the OUTPUT (for a following BatchNorm layer): column sums in the epilogue,
+    // last CTA finalises mean / invstd and re-arms the accumulators (same contract as k_bn_stats)
+    int fuse_stats;
+    BnScratch bn;
+    float bn_eps;
+    long long bn_rows;    // B*H*W
 };
 
-template <int PASSES>
+template <int PASSES, bool FUSE>
 __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const ConvGeom& g = a.g;
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
         tc::mbar_init(d_full, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc<64>(tmem_slot);
+    if (warp == 0) tc::tmem_alloc<128>(tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -124,13 +129,15 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
                 const int s = tap % CONV_TC_STAGES;
                 if (tap >= CONV_TC_STAGES) tc::mbar_wait(&w_empty[s], ((tap / CONV_TC_STAGES) - 1) & 1);
                 tc::mbar_arrive_expect_tx(&w_full[s], CONV_TC_WSTAGE_BYTES);
-                tc::bulk_g2s(sW + s * CONV_TC_WSTAGE_BYTES, a.wimg + (long long)tap * 2 * 4096, CONV_TC_WSTAGE_BYTES, &w_full[s]);
+                tc::bulk_g2s(sW + s * CONV_TC_WSTAGE_BYTES, a.wimg + (long long)tap * 8192, CONV_TC_WSTAGE_BYTES, &w_full[s]);
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            // ---- MMA issuer: 9 taps x 8 k-steps x 3 TF32 products, all into one 128x64 fp32 accumulator in TMEM ----
-            constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 0, 0);
+            // ---- MMA issuer: per tap and k-step (K=8):  D[:,0:128] += A_hi * [B_hi | B_lo]   (one N=128 instruction)
+            //                                             D[:,0:64]  += A_lo * B_hi            (N=64)
+            // the epilogue adds the two 64-column halves.  The a_lo*b_lo term (2^-22 relative) is dropped.
+            constexpr uint32_t idesc128 = tc::idesc_tf32(128, 128, 0, 0), idesc64 = tc::idesc_tf32(128, 64, 0, 0);
             const uint32_t sA_u = tc::smem_u32(sA), sW_u = tc::smem_u32(sW);
             tc::mbar_wait(a_full, 0);
             uint32_t acc = 0;
@@ -145,15 +152,15 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
                 for (int kk = 0; kk < 8; ++kk) {
                     const uint32_t a_hi = sA_u + (2 * kk) * a_chunk_bytes + a_row;
                     const uint32_t a_lo = a_hi + a_img_bytes;
-                    const uint32_t b_hi = w_base + (2 * kk) * 1024;
-                    const uint32_t b_lo = b_hi + 16384;
+                    const uint32_t b = w_base + (2 * kk) * 2048;
                     const uint64_t dAh = tc::smem_desc(a_hi, a_chunk_bytes, 128), dAl = tc::smem_desc(a_lo, a_chunk_bytes, 128);
-                    const uint64_t dBh = tc::smem_desc(b_hi, 1024, 128), dBl = tc::smem_desc(b_lo, 1024, 128);
+                    const uint64_t dB = tc::smem_desc(b, 2048, 128);
                     if (PASSES == 3) {
-                        tc::mma_tf32(tmem, dAh, dBl, idesc, acc); acc = 1;
-                        tc::mma_tf32(tmem, dAl, dBh, idesc, 1);
+                        tc::mma_tf32(tmem, dAh, dB, idesc128, acc); acc = 1;
+                        tc::mma_tf32(tmem, dAl, dB, idesc64, 1);
+                    } else if (PASSES == 1) {
+                        tc::mma_tf32(tmem, dAh, dB, idesc64, acc); acc = 1;
                     }
-                    if (PASSES >= 1) { tc::mma_tf32(tmem, dAh, dBh, idesc, acc); acc = 1; }
                 }
                 tc::mma_commit(&w_empty[s]);
             }
@@ -175,23 +182,63 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
             crow = ((long long)b * g.H + (ph - 1)) * g.W + (pw - 1);
         }
         float* __restrict__ out = resolve(a.out);
+        float* sT = reinterpret_cast<float*>(sW);      // [128][65] transpose buffer; the weight ring is idle once d_full fires
         tc::mbar_wait(d_full, 0);
         tc::tc_fence_after();
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             float v[32];
             tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + half * 32, v);
-            if (valid) {
+            if (PASSES == 3) {
+                float u[32];
+                tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 64 + half * 32, u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += u[j];
+            }
+            if (valid) {   // the tensor path only takes identity-activation convolutions (the reference's blocks)
                 float4* dst = reinterpret_cast<float4*>(out + crow * 64 + half * 32);
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    dst[j] = make_float4(act_fwd(a.act, v[4 * j]), act_fwd(a.act, v[4 * j + 1]), act_fwd(a.act, v[4 * j + 2]), act_fwd(a.act, v[4 * j + 3]));
+                for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if constexpr (FUSE) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sT[row * 65 + half * 32 + j] = valid ? v[j] : 0.f;
+            }
+        }
+        if constexpr (FUSE) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+            const int et = threadIdx.x - 64;                     // 0..127
+            const int c = et & 63, r0 = (et >> 6) * 64;
+            double s1 = 0.0, s2 = 0.0;
+            for (int r = r0; r < r0 + 64; ++r) { const double x = (double)sT[r * 65 + c]; s1 += x; s2 += x * x; }
+            atomicAdd(a.bn.acc + c, s1);
+            atomicAdd(a.bn.acc + 64 + c, s2);
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            __shared__ int s_last;
+            if (et == 0) {
+                const unsigned int tk = atomicAdd(a.bn.ticket, 1u);
+                s_last = (tk == gridDim.x - 1);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (s_last) {
+                __threadfence();
+                if (et < 64) {
+                    const double sum = *((volatile double*)(a.bn.acc + et)), sq = *((volatile double*)(a.bn.acc + 64 + et));
+                    const double mean = sum / (double)a.bn_rows;
+                    double var = sq / (double)a.bn_rows - mean * mean;
+                    if (var < 0) var = 0;
+                    a.bn.mean[et] = (float)mean;
+                    a.bn.invstd[et] = (float)(1.0 / sqrt(var + (double)a.bn_eps));
+                    a.bn.acc[et] = 0.0; a.bn.acc[64 + et] = 0.0;
+                }
+                if (et == 0) *a.bn.ticket = 0u;
             }
         }
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<64>(tmem);
+    if (warp == 0) tc::tmem_dealloc<128>(tmem);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
@@ -242,6 +289,121 @@ __global__ void __launch_bounds__(256) k_compact_to_image(Ref xin, ConvGeom g, f
         const int chunk = (int)(i & 15);
         const long long crow = i >> 4;
         store_split4(img, g, chunk, padded_row(g, crow), reinterpret_cast<const float4*>(x)[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Weight gradient of the 64->64 3x3 convolution:  dW[tap][ci][co] = sum_{pixels} X[p + shift(tap)][ci] * G[p][co]
+// (DL4J ConvolutionLayer.backpropGradient's weight-gradient GEMM).  The contraction runs over pixels, the output is nine
+// 64x64 blocks: one CTA per image keeps all 9*64*64 partial sums in registers (144 per thread), stages the zero-padded
+// image and its gradient in shared memory, and writes one partial per image; k_wgrad_reduce sums the partials in a fixed
+// order (deterministic).  fp32 FMA on the CUDA cores — the tensor-core formulation needs nine 64-column TMEM accumulators
+// (576 > 512 columns) and a 147 KB epilogue per CTA, which costs more than it saves at this size; the kernel runs on a side
+// branch of the graph, concurrently with the dgrad/BatchNorm chain.
+// ---------------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 1) k_conv_wgrad64(Ref xin, Ref gin, ConvGeom g, float* __restrict__ part, int images_per_cta) {
+    extern __shared__ __align__(16) float smw[];
+    const int hw = g.H * g.W, pp = g.PH * g.PW;
+    float* Xs = smw;                 // [PH*PW][64], zero border
+    float* Gs = smw + pp * 64;       // [H*W][64]
+    const int tci = threadIdx.x >> 4, tco = threadIdx.x & 15;
+    float acc[9][4][4];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
+    for (int i = threadIdx.x; i < pp * 16; i += 256) reinterpret_cast<float4*>(Xs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int img = blockIdx.x * images_per_cta; img < min(g.B, (blockIdx.x + 1) * images_per_cta); ++img) {
+        const float* __restrict__ x = resolve(xin) + (long long)img * hw * 64;
+        const float* __restrict__ gr = resolve(gin) + (long long)img * hw * 64;
+        __syncthreads();             // previous image fully consumed (and the border zeroing visible)
+        for (int i = threadIdx.x; i < hw * 16; i += 256) {
+            const int p = i >> 4, c4 = i & 15;
+            const int h = p / g.W, w = p - h * g.W;
+            reinterpret_cast<float4*>(Xs)[((h + 1) * g.PW + (w + 1)) * 16 + c4] = reinterpret_cast<const float4*>(x)[i];
+            reinterpret_cast<float4*>(Gs)[i] = reinterpret_cast<const float4*>(gr)[i];
+        }
+        __syncthreads();
+        for (int p = 0; p < hw; ++p) {
+            const int h = p / g.W, w = p - h * g.W;
+            const int center = (h + 1) * g.PW + (w + 1);
+            const float4 gv = reinterpret_cast<const float4*>(Gs)[p * 16 + tco];
+            const float gj[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int q = center + (t / 3 - 1) * g.PW + (t % 3 - 1);
+                const float4 xv = reinterpret_cast<const float4*>(Xs)[q * 16 + tci];
+                const float xi[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[t][i][j] = fmaf(xi[i], gj[j], acc[t][i][j]);
+            }
+        }
+    }
+    float* __restrict__ out = part + (long long)blockIdx.x * 9 * 4096;
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            reinterpret_cast<float4*>(out + (t * 64 + tci * 4 + i) * 64)[tco] = make_float4(acc[t][i][0], acc[t][i][1], acc[t][i][2], acc[t][i][3]);
+}
+inline size_t conv_wgrad_smem_bytes(const ConvGeom& g) { return sizeof(float) * 64 * ((size_t)g.PH * g.PW + (size_t)g.H * g.W); }
+
+// dst[i] = sum_b part[b][i]  (fixed order), i over 9*64*64.  Block = 64 float4 columns x 4 partial groups.
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ part, Ref dstref, int nparts) {
+    float* __restrict__ dst = resolve(dstref);
+    const int n4 = 9 * 4096 / 4;
+    const int col = blockIdx.x * 64 + (threadIdx.x & 63), grp = threadIdx.x >> 6;
+    __shared__ float4 sm[4][64];
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int per = (nparts + 3) / 4;
+    const int b0 = grp * per, b1 = min(nparts, b0 + per);
+    if (col < n4) {
+#pragma unroll 4
+        for (int b = b0; b < b1; ++b) {
+            const float4 v = reinterpret_cast<const float4*>(part)[(long long)b * n4 + col];
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+    }
+    sm[grp][threadIdx.x & 63] = s;
+    __syncthreads();
+    if (grp == 0 && col < n4) {
+        float4 t = sm[0][threadIdx.x];
+#pragma unroll
+        for (int q = 1; q < 4; ++q) { const float4 v = sm[q][threadIdx.x]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+        reinterpret_cast<float4*>(dst)[col] = t;
+    }
+}
+
+// BatchNorm backward dx written as the compact gradient AND as the operand image of the following dgrad convolution
+__global__ void __launch_bounds__(256) k_bn_bwd_dx_to_image(Ref gin, float gscale, Ref yref, Ref xin, const float* __restrict__ gamma, BnScratch sc,
+                                                             int act, ConvGeom g, float* __restrict__ dx_compact, float* __restrict__ img) {
+    const float* __restrict__ gg = resolve(gin);
+    const float* __restrict__ y = resolve(yref);
+    const float* __restrict__ x = resolve(xin);
+    const long long n4 = (long long)g.B * g.H * g.W * 16;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+        const int chunk = (int)(i & 15);
+        const long long crow = i >> 4;
+        const float4 gv = reinterpret_cast<const float4*>(gg)[i], yv = reinterpret_cast<const float4*>(y)[i], xv = reinterpret_cast<const float4*>(x)[i];
+        const float ga[4] = {gv.x, gv.y, gv.z, gv.w}, ya[4] = {yv.x, yv.y, yv.z, yv.w}, xa[4] = {xv.x, xv.y, xv.z, xv.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = chunk * 4 + k;
+            const float inv = sc.invstd[c];
+            const float dy = act_bwd(act, ya[k], __fmul_rn(gscale, ga[k]));
+            const float xh = __fmul_rn(__fsub_rn(xa[k], sc.mean[c]), inv);
+            const float kk = __fmul_rn(gamma[c], inv);
+            o[k] = __fmul_rn(kk, __fsub_rn(__fsub_rn(dy, sc.m_dy[c]), __fmul_rn(xh, sc.m_dyxh[c])));
+        }
+        const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4*>(dx_compact)[i] = ov;
+        store_split4(img, g, chunk, padded_row(g, crow), ov);
     }
 }
 

@@ -112,6 +112,9 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
     N4J_CUDA(cudaSetDevice(device_));
     N4J_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     N4J_CUDA(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
+    N4J_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    for (auto& e : ev_pool_) N4J_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : slot_event_) N4J_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     N4J_CUDA(cudaEventCreate(&ev0_));
     N4J_CUDA(cudaEventCreate(&ev1_));
     N4J_CUDA(cudaMalloc(&Y_, sizeof(float) * 2 * n_alloc_));
@@ -136,7 +139,12 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
     for (auto& b : gb_) ensure(b, max_len_);
     for (size_t i = 0; i < L_.size(); ++i) {
         LayerPlan& l = L_[i];
-        if (i + 1 < L_.size()) N4J_CUDA(cudaMalloc(&l.act, sizeof(float) * l.out_len));
+        for (int sl = 0; sl < 2; ++sl) {   // two sets: consecutive stage evaluations alternate, so a weight-gradient kernel of
+                                           // stage s may still read its inputs while stage s+1 runs
+            if (i + 1 < L_.size()) N4J_CUDA(cudaMalloc(&l.act2[sl], sizeof(float) * l.out_len));
+            if (i > 0) N4J_CUDA(cudaMalloc(&l.gin2[sl], sizeof(float) * l.in_len));
+        }
+        l.act = l.act2[0]; l.gin = l.gin2[0];
         if (l.d.kind == N4J_LAYER_CONV3X3) {
             N4J_CUDA(cudaMalloc(&l.wf, sizeof(float) * l.p_len));
             N4J_CUDA(cudaMalloc(&l.wb, sizeof(float) * l.p_len));
@@ -153,8 +161,15 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
                 N4J_CUDA(cudaMemsetAsync(l.gimg, 0, img_bytes, stream_));
                 N4J_CUDA(cudaMalloc(&l.wimg_f, sizeof(float) * 9 * 2 * 4096));
                 N4J_CUDA(cudaMalloc(&l.wimg_b, sizeof(float) * 9 * 2 * 4096));
-                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
-                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
+                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
+                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
+                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
+                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
+                side_capable_ = true;
+                wgrad_smem_ = conv_wgrad_smem_bytes(geom_);
+                if (wgrad_smem_ > 200 * 1024) throw Error{N4J_ERR_UNSUPPORTED, "feature map too large for the native conv weight-gradient kernel"};
+                N4J_CUDA(cudaFuncSetAttribute(k_conv_wgrad64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_));
+                ensure(wpart_, (long long)B_ * 9 * 4096);
             }
         }
         if (l.d.kind == N4J_LAYER_BATCHNORM) {
@@ -179,7 +194,8 @@ Engine::~Engine() {
         if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
     }
     for (auto& l : L_) {
-        cudaFree(l.act); cudaFree(l.wf); cudaFree(l.wb); cudaFree(l.img); cudaFree(l.gimg); cudaFree(l.wimg_f); cudaFree(l.wimg_b);
+        for (int sl = 0; sl < 2; ++sl) { cudaFree(l.act2[sl]); cudaFree(l.gin2[sl]); }
+        cudaFree(l.wf); cudaFree(l.wb); cudaFree(l.img); cudaFree(l.gimg); cudaFree(l.wimg_f); cudaFree(l.wimg_b);
         if (l.d.kind == N4J_LAYER_BATCHNORM) { cudaFree(l.bn.acc); cudaFree(l.bn.ticket); cudaFree(l.bn.mean); }
     }
     for (DevBuf* b : {&params_, &gradflat_, &zt_, &gt_, &io_, &io2_, &gb_[0], &gb_[1], &gb_[2], &theta_tmp_, &wpart_, &dldt_}) cudaFree(b->p);
@@ -189,6 +205,9 @@ Engine::~Engine() {
     if (ev1_) cudaEventDestroy(ev1_);
     if (stream_) cudaStreamDestroy(stream_);
     if (stream2_) cudaStreamDestroy(stream2_);
+    if (side_) cudaStreamDestroy(side_);
+    for (auto& e : ev_pool_) if (e) cudaEventDestroy(e);
+    for (auto& e : slot_event_) if (e) cudaEventDestroy(e);
 }
 
 // =====================================================================================================
@@ -226,6 +245,22 @@ int Engine::grid_for(long long n, int per_thread) const {
     long long blocks = (n + 256LL * per_thread - 1) / (256LL * per_thread);
     blocks = std::max<long long>(1, std::min<long long>(blocks, 148LL * 8));
     return (int)blocks;
+}
+// Grid for kernels that end in a cross-block reduction (double atomics + ticket on a handful of addresses): same-address
+// atomics serialise in L2, so the block count is capped at one per SM and shrinks with the problem.
+int Engine::grid_red(long long n4) const {
+    long long blocks = (n4 + 256LL * 4 - 1) / (256LL * 4);
+    blocks = std::max<long long>(1, std::min<long long>(blocks, n4 > (4LL << 20) ? 148 * 8 : 148));   // HBM-sized states need the extra loads in flight
+    return (int)blocks;
+}
+// stage combination + statistics of a leading 64-channel BatchNorm in one pass
+BnFuse Engine::bn_fuse() const {
+    BnFuse bf{};
+    const LayerPlan& l = L_[0];
+    if (rank_ == 4 && l.d.kind == N4J_LAYER_BATCHNORM && l.c_out == 64 && nz_ % 4 == 0) {
+        bf.enabled = 1; bf.sc = l.bn; bf.eps = l.d.eps; bf.rows = l.rows; bf.nz4 = nz_ / 4;
+    }
+    return bf;
 }
 SolverParams Engine::solver_params(long long n_norm) const {
     SolverParams p;
@@ -305,17 +340,26 @@ static void launch_gemm(cudaStream_t s, GemmArgs g, int& launches, bool exact) {
     ++launches;
 }
 
-void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act) {
+void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act, const LayerPlan* next_bn) {
     ConvTcArgs a{};
-    a.img = img; a.wimg = wimg; a.out = out; a.g = geom_; a.act = act; a.stat_acc = nullptr;
-    if (cfg_.flags & N4J_FLAG_FAST_TF32) k_conv3x3_tc<1><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
-    else k_conv3x3_tc<3><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
+    a.img = img; a.wimg = wimg; a.out = out; a.g = geom_; a.act = act;
+    a.fuse_stats = next_bn ? 1 : 0;
+    if (next_bn) { a.bn = next_bn->bn; a.bn_eps = next_bn->d.eps; a.bn_rows = next_bn->rows; }
+    const bool fast = (cfg_.flags & N4J_FLAG_FAST_TF32) != 0;
+    if (next_bn) {
+        if (fast) k_conv3x3_tc<1, true><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
+        else k_conv3x3_tc<3, true><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
+    } else {
+        if (fast) k_conv3x3_tc<1, false><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
+        else k_conv3x3_tc<3, false><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
+    }
     ++launches_;
 }
 
-void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact) {
+void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact, bool bn1_ready) {
     Ref cur = in;
     bool image_ready = false;   // the previous layer already wrote the operand image of this (tensor-core) conv
+    bool stats_ready = bn1_ready;   // the previous kernel (conv epilogue / stage combination) already produced this BatchNorm's mean / invstd
     for (size_t i = 0; i < L_.size(); ++i) {
         LayerPlan& l = L_[i];
         Ref dst = (i + 1 == L_.size()) ? out : fixed_ref(l.act);
@@ -335,8 +379,11 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact)
             case N4J_LAYER_CONV3X3: {
                 if (l.tc) {
                     if (!image_ready) LAUNCH(k_compact_to_image, grid_for(l.in_len / 4), 256, s, cur, geom_, l.img);
-                    launch_conv_tc(s, l.img, l.wimg_f, dst, l.d.activation);
+                    // a BatchNorm right after the conv gets its batch statistics from the conv epilogue
+                    const bool bn_next = i + 1 < L_.size() && L_[i + 1].d.kind == N4J_LAYER_BATCHNORM && L_[i + 1].c_out == 64;
+                    launch_conv_tc(s, l.img, l.wimg_f, dst, l.d.activation, bn_next ? &L_[i + 1] : nullptr);
                     image_ready = false;
+                    stats_ready = bn_next;
                     break;
                 }
                 GemmArgs g{}; g.a = cur; g.c = dst; g.w = l.wf; g.M = (int)l.rows; g.N = l.c_out; g.K = 9 * l.c_in;
@@ -348,9 +395,11 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact)
                 const int cc = l.c_out;
                 const bool vec = (cc % 4 == 0) && (256 % (cc / 4) == 0) && (cc / 4 <= 256);
                 const bool feeds_tc = i + 1 < L_.size() && L_[i + 1].d.kind == N4J_LAYER_CONV3X3 && L_[i + 1].tc;
-                if (vec) {
+                if (stats_ready) {
+                    stats_ready = false;
+                } else if (vec) {
                     const int rows_per_iter = 256 / (cc / 4);
-                    int grid = (int)std::max<long long>(1, std::min<long long>(148, (l.rows + rows_per_iter - 1) / rows_per_iter));
+                    int grid = (int)std::max<long long>(1, std::min<long long>(74, (l.rows + 4 * rows_per_iter - 1) / (4 * rows_per_iter)));
                     LAUNCH(k_bn_stats, grid, 256, s, cur, l.rows, cc, l.d.eps, l.bn);
                 } else {
                     LAUNCH(k_bn_stats_generic, cc, 256, s, cur, l.rows, cc, l.d.eps, l.bn);
@@ -361,6 +410,9 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact)
                     LAUNCH(k_bn_apply_to_image, grid_for(l.out_len / 4), 256, s, cur, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn,
                            l.d.activation, geom_, L_[i + 1].img, need_compact ? l.act : (float*)nullptr);
                     image_ready = true;
+                } else if (need_compact && fuse_last_bn_ok_ && i + 1 == L_.size() && cc == 64) {
+                    // augmented evaluation: the last BatchNorm's apply is done by the first backward kernel (k_bn_bwd_stats64)
+                    fwd_left_last_bn_ = true;
                 } else {
                     LAUNCH(k_bn_apply, grid_for(l.out_len), 256, s, cur, dst, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn, l.d.activation, l.rows, cc);
                 }
@@ -376,24 +428,60 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact)
 
 // BackpropagateAdjoint.calculateDerivative :63-85 on the layout [z | a | theta | a_t]:
 //   out.z <- f(z,t);  out.a <- (-a)^T df/dz;  out.theta <- (-a)^T df/dtheta;  out.a_t stays 0 (NoTimeInput.java:26-29)
-void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out) {
-    enqueue_rhs_fwd(s, in, out, true);
+void Engine::join_side(cudaStream_t s) {
+    if (side_busy_) {
+        cudaEvent_t ej = ev_pool_[(ev_next_++) % EV_POOL];
+        N4J_CUDA(cudaEventRecord(ej, side_));
+        N4J_CUDA(cudaStreamWaitEvent(s, ej, 0));
+        side_busy_ = false;
+    }
+    slot_event_valid_[0] = slot_event_valid_[1] = false;
+}
+
+// slot: which activation / gradient buffer set this evaluation uses; defer_join: leave the weight-gradient kernels running on
+// the side branch (the caller joins before it touches the theta block of the K rows).
+void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, int slot, bool defer_join) {
+    for (auto& l : L_) { l.act = l.act2[slot]; l.gin = l.gin2[slot]; }
+    if (slot_event_valid_[slot]) {   // the evaluation that used this buffer set before must have finished its side work
+        N4J_CUDA(cudaStreamWaitEvent(s, slot_event_[slot], 0));
+        slot_event_valid_[slot] = false;
+    }
+    fwd_left_last_bn_ = false;
+    fuse_last_bn_ok_ = true;
+    enqueue_rhs_fwd(s, in, out, true, bn1_ready);
+    fuse_last_bn_ok_ = false;
     Ref g = with_off(in, off_a_);
     float gscale = -1.f;                                 // zAdjoint().negi() :75
-    int gi = 0;
     const int last = (int)L_.size() - 1;
+    bool gimg_ready = false;     // the BatchNorm above already wrote the operand image of this conv's output gradient
+    bool forked = false;
     for (int i = last; i >= 0; --i) {
         LayerPlan& l = L_[i];
         Ref x = i == 0 ? in : fixed_ref(L_[i - 1].act);
         Ref y = i == last ? out : fixed_ref(l.act);
-        Ref dx = i == 0 ? with_off(out, off_a_) : fixed_ref(gb_[gi].p);
+        // every layer owns the buffer of the gradient w.r.t. its input: nothing is recycled inside one evaluation, so the
+        // weight-gradient kernels can run on a side branch while the dgrad/BatchNorm chain moves on
+        Ref dx = i == 0 ? with_off(out, off_a_) : fixed_ref(l.gin);
         Ref dth = with_off(out, off_theta_ + l.g_off);
         switch (l.d.kind) {
             case N4J_LAYER_BATCHNORM: {
                 const int cc = l.c_out;
-                int grid = (cc <= 256 && 256 % cc == 0) ? (int)std::max<long long>(1, std::min<long long>(148, (l.rows + 256 / cc - 1) / (256 / cc))) : 148;
-                LAUNCH(k_bn_bwd_stats, grid, 256, s, g, gscale, y, x, l.bn, l.d.activation, l.rows, cc, dth, with_off(dth, cc));
-                LAUNCH(k_bn_bwd_dx, grid_for(l.in_len), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, l.rows, cc, dx);
+                int grid = (cc <= 256 && 256 % cc == 0) ? (int)std::max<long long>(1, std::min<long long>(74, (l.rows + 4 * (256 / cc) - 1) / (4 * (256 / cc)))) : 74;
+                if (cc == 64) {
+                    const int g64 = (int)std::max<long long>(1, std::min<long long>(148, (l.rows + 15) / 16));
+                    LAUNCH(k_bn_bwd_stats64, g64, 256, s, g, gscale, y, x, l.bn, l.d.activation, l.rows, dth, with_off(dth, cc),
+                           params_.p + l.p_off, params_.p + l.p_off + cc, (i == last && fwd_left_last_bn_) ? 1 : 0);
+                } else {
+                    LAUNCH(k_bn_bwd_stats, grid, 256, s, g, gscale, y, x, l.bn, l.d.activation, l.rows, cc, dth, with_off(dth, cc));
+                }
+                const bool feeds_tc = i > 0 && L_[i - 1].d.kind == N4J_LAYER_CONV3X3 && L_[i - 1].tc;
+                if (feeds_tc) {
+                    LAUNCH(k_bn_bwd_dx_to_image, grid_for(l.in_len / 4), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, geom_,
+                           l.gin, L_[i - 1].gimg);
+                    gimg_ready = true;
+                } else {
+                    LAUNCH(k_bn_bwd_dx, grid_for(l.in_len), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, l.rows, cc, dx);
+                }
                 break;
             }
             case N4J_LAYER_ACTIVATION:
@@ -405,6 +493,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out) {
                 if (l.d.activation != N4J_ACT_IDENTITY || gscale != 1.f) {
                     d = fixed_ref(gb_[2].p);
                     LAUNCH(k_act_bwd, grid_for(l.out_len), 256, s, g, gscale, y, l.d.activation, d, l.out_len);
+                    gimg_ready = false;
                 }
                 if (l.d.kind == N4J_LAYER_DENSE) {
                     const float* Wt = params_.p + l.p_off;
@@ -418,27 +507,45 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out) {
                         GemmArgs q{}; q.a = d; q.c = dx; q.w = Wt; q.M = (int)l.rows; q.N = l.c_in; q.K = l.c_out; q.splits = 1;
                         launch_gemm<G_DENSE_DGRAD>(s, q, launches_, exact_);
                     }
+                } else if (l.tc) {
+                    // weight gradient on the side branch (fork), dgrad on the main chain
+                    cudaEvent_t ef = ev_pool_[(ev_next_++) % EV_POOL];
+                    N4J_CUDA(cudaEventRecord(ef, s));
+                    N4J_CUDA(cudaStreamWaitEvent(side_, ef, 0));
+                    // at most 64 CTAs: they share the chip with the 81 CTAs of the concurrent dgrad convolution
+                    const int ipc = (int)((B_ + 63) / 64), wg_ctas = (int)((B_ + ipc - 1) / ipc);
+                    k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, side_>>>(x, d, geom_, wpart_.p, ipc);
+                    ++launches_;
+                    LAUNCH(k_wgrad_reduce, 144, 256, side_, wpart_.p, dth, wg_ctas);
+                    forked = true;
+                    side_busy_ = true;
+                    if (!gimg_ready) LAUNCH(k_compact_to_image, grid_for(l.out_len / 4), 256, s, d, geom_, l.gimg);
+                    launch_conv_tc(s, l.gimg, l.wimg_b, dx, N4J_ACT_IDENTITY);
                 } else {
                     GemmArgs w{}; w.a = x; w.b = d; w.c = fixed_ref(wpart_.p); w.M = 9 * l.c_in; w.N = l.c_out; w.K = (int)l.rows;
                     w.H = l.H; w.W = l.W; w.Ci = l.c_in; w.Co = l.c_out; w.splits = 16;
                     if (exact_) w.c = dth;
                     launch_gemm<G_CONV_WGRAD>(s, w, launches_, exact_);
                     if (!exact_) LAUNCH(k_splitk_reduce, grid_for(l.g_len), 256, s, wpart_.p, dth, l.g_len, 16);
-                    if (l.tc) {
-                        LAUNCH(k_compact_to_image, grid_for(l.out_len / 4), 256, s, d, geom_, l.gimg);
-                        launch_conv_tc(s, l.gimg, l.wimg_b, dx, N4J_ACT_IDENTITY);
-                    } else {
-                        GemmArgs q{}; q.a = d; q.c = dx; q.w = l.wb; q.M = (int)l.rows; q.N = l.c_in; q.K = 9 * l.c_out;
-                        q.H = l.H; q.W = l.W; q.Ci = l.c_in; q.Co = l.c_out; q.splits = 1;
-                        launch_gemm<G_CONV_DGRAD>(s, q, launches_, exact_);
-                    }
+                    GemmArgs q{}; q.a = d; q.c = dx; q.w = l.wb; q.M = (int)l.rows; q.N = l.c_in; q.K = 9 * l.c_out;
+                    q.H = l.H; q.W = l.W; q.Ci = l.c_in; q.Co = l.c_out; q.splits = 1;
+                    launch_gemm<G_CONV_DGRAD>(s, q, launches_, exact_);
                 }
+                gimg_ready = false;
                 break;
             }
         }
         g = dx; gscale = 1.f;
-        gi ^= 1;
     }
+    if (forked) {
+        if (defer_join) {
+            N4J_CUDA(cudaEventRecord(slot_event_[slot], side_));
+            slot_event_valid_[slot] = true;
+        } else {
+            join_side(s);
+        }
+    }
+    for (auto& l : L_) { l.act = l.act2[0]; l.gin = l.gin2[0]; }
 }
 
 // =====================================================================================================
@@ -450,36 +557,50 @@ void Engine::enqueue_prologue(cudaStream_t s, bool aug, long long n4, const Solv
     LAUNCH(k_solve_begin, 1, 32, s, ctrl_, tpair_);
     if (dense_out) LAUNCH(k_dense_edge, grid_for(nz_), 256, s, ctrl_, Y_, n_alloc_, nz_, wanted_, 0, 0, zt_.p + nz_, nz_);
     enqueue_rhs(s, aug, ycur, Ref{K_, &ctrl_->krow[0], n_alloc_, 0, 0});            // AdaptiveRungeKuttaSolver.java:131
-    LAUNCH(k_init_sums, grid_for(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp);
-    LAUNCH(k_stage_combine<0>, grid_for(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4);  // equation.step(ones(1), step)
-    enqueue_rhs(s, aug, ywork, Ref{K_, &ctrl_->krow[1], n_alloc_, 0, 0});           // policy :112
-    LAUNCH(k_init_final, grid_for(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp, (cudaGraphConditionalHandle)0, 0);
+    LAUNCH(k_init_sums, grid_red(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp);
+    const BnFuse bf = bn_fuse();
+    LAUNCH(k_stage_combine<0>, bf.enabled ? grid_red(n4) : grid_for(n4), 256, s, ctrl_, Y_, K_, n_alloc_, 0LL, n4, bf);  // equation.step(ones(1), step)
+    enqueue_rhs(s, aug, ywork, Ref{K_, &ctrl_->krow[1], n_alloc_, 0, 0}, bf.enabled != 0);   // policy :112
+    LAUNCH(k_init_final, grid_red(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp, (cudaGraphConditionalHandle)0, 0);
     (void)nt;
 }
 
 template <int S>
-static void launch_combine(cudaStream_t s, int grid, Ctrl* c, float* Y, float* K, long long stride, long long n4) {
-    k_stage_combine<S><<<grid, 256, 0, s>>>(c, Y, K, stride, n4);
+static void launch_combine(cudaStream_t s, int grid, Ctrl* c, float* Y, float* K, long long stride, long long i0, long long i1, const BnFuse& bf) {
+    k_stage_combine<S><<<grid, 256, 0, s>>>(c, Y, K, stride, i0, i1, bf);
 }
 
 void Engine::enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt,
                            cudaGraphConditionalHandle cond, int use_cond) {
     Ref ywork{Y_, &ctrl_->y_cur, n_alloc_, 0, 1};
-    const int grid = grid_for(n4);
+    const BnFuse bf = bn_fuse();
+    // Adjoint solves: f and the vjp only read the z and a blocks of the stage state, so stages 1-6 combine just those
+    // (n4_main); the theta block of y1 is combined once, right before the error norm, after the side branch (weight
+    // gradients of all six stages) has been joined.
+    const bool split = aug && side_capable_;
+    const long long n4_main = split ? (2 * nz_pad_) / 4 : n4;
+    const int grid = bf.enabled ? grid_red(n4_main) : grid_for(n4_main);
+    BnFuse nobf{};
     for (int st = 1; st <= 6; ++st) {
         switch (st) {
-            case 1: launch_combine<1>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
-            case 2: launch_combine<2>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
-            case 3: launch_combine<3>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
-            case 4: launch_combine<4>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
-            case 5: launch_combine<5>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
-            case 6: launch_combine<6>(s, grid, ctrl_, Y_, K_, n_alloc_, n4); break;
+            case 1: launch_combine<1>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
+            case 2: launch_combine<2>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
+            case 3: launch_combine<3>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
+            case 4: launch_combine<4>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
+            case 5: launch_combine<5>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
+            case 6: launch_combine<6>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
         }
         ++launches_;
-        enqueue_rhs(s, aug, ywork, Ref{K_, &ctrl_->krow[st], n_alloc_, 0, 0});
+        if (aug) enqueue_rhs_aug(s, ywork, Ref{K_, &ctrl_->krow[st], n_alloc_, 0, 0}, bf.enabled != 0, st & 1, split);
+        else enqueue_rhs_fwd(s, ywork, Ref{K_, &ctrl_->krow[st], n_alloc_, 0, 0}, false, bf.enabled != 0);
+    }
+    if (split) {
+        join_side(s);
+        launch_combine<6>(s, grid_for(n4 - n4_main), ctrl_, Y_, K_, n_alloc_, n4_main, n4, nobf);   // theta | a_t block of y1
+        ++launches_;
     }
     DenseOutArgs dout{dense_out ? wanted_ : nullptr, dense_out ? nt - 1 : 0};
-    LAUNCH(k_error_ctrl, grid, 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp, log_, dout, cond, use_cond);
+    LAUNCH(k_error_ctrl, grid_red(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp, log_, dout, cond, use_cond);
     if (dense_out) LAUNCH(k_dense_output, grid_for(nz_), 256, s, ctrl_, Y_, K_, n_alloc_, nz_, wanted_, zt_.p + nz_, nz_);
 }
 
@@ -885,14 +1006,15 @@ void Engine::bench_solver_pass(long long n, int iters, float* us) {
     SolverParams sp = solver_params(n);
     sp.max_trials = 1LL << 60; sp.log_cap = 0;
     const int grid = grid_for(n4);
+    BnFuse nobf{};
     auto pass = [&]() {
-        launch_combine<1>(stream_, grid, c, Y, K, stride, n4);
-        launch_combine<2>(stream_, grid, c, Y, K, stride, n4);
-        launch_combine<3>(stream_, grid, c, Y, K, stride, n4);
-        launch_combine<4>(stream_, grid, c, Y, K, stride, n4);
-        launch_combine<5>(stream_, grid, c, Y, K, stride, n4);
-        launch_combine<6>(stream_, grid, c, Y, K, stride, n4);
-        k_error_ctrl<<<grid, 256, 0, stream_>>>(c, Y, K, stride, n4, sp, nullptr, DenseOutArgs{nullptr, 0}, (cudaGraphConditionalHandle)0, 0);
+        launch_combine<1>(stream_, grid, c, Y, K, stride, 0, n4, nobf);
+        launch_combine<2>(stream_, grid, c, Y, K, stride, 0, n4, nobf);
+        launch_combine<3>(stream_, grid, c, Y, K, stride, 0, n4, nobf);
+        launch_combine<4>(stream_, grid, c, Y, K, stride, 0, n4, nobf);
+        launch_combine<5>(stream_, grid, c, Y, K, stride, 0, n4, nobf);
+        launch_combine<6>(stream_, grid, c, Y, K, stride, 0, n4, nobf);
+        k_error_ctrl<<<grid_red(n4), 256, 0, stream_>>>(c, Y, K, stride, n4, sp, nullptr, DenseOutArgs{nullptr, 0}, (cudaGraphConditionalHandle)0, 0);
     };
     for (int i = 0; i < 3; ++i) pass();
     N4J_CUDA(cudaEventRecord(ev0_, stream_));
@@ -933,6 +1055,11 @@ void Engine::bench_piece(int what, int iters, float* us) {
                     GemmArgs q{}; q.a = fixed_ref(gb_[0].p); q.c = fixed_ref(gb_[1].p); q.w = l.wb; q.M = (int)l.rows; q.N = l.c_in; q.K = 9 * l.c_out;
                     q.H = l.H; q.W = l.W; q.Ci = l.c_in; q.Co = l.c_out; q.splits = 1;
                     launch_gemm<G_CONV_DGRAD>(stream_, q, launches_, exact_);
+                } else if (l.tc) {
+                    const int ipc = (int)((B_ + 63) / 64), wg_ctas = (int)((B_ + ipc - 1) / ipc);
+                    k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, stream_>>>(fixed_ref(gb_[0].p), fixed_ref(gb_[1].p), geom_, wpart_.p, ipc);
+                    ++launches_;
+                    LAUNCH(k_wgrad_reduce, 144, 256, stream_, wpart_.p, fixed_ref(theta_tmp_.p), wg_ctas);
                 } else {
                     GemmArgs w{}; w.a = fixed_ref(gb_[0].p); w.b = fixed_ref(gb_[1].p); w.c = fixed_ref(wpart_.p); w.M = 9 * l.c_in; w.N = l.c_out; w.K = (int)l.rows;
                     w.H = l.H; w.W = l.W; w.Ci = l.c_in; w.Co = l.c_out; w.splits = 16;

@@ -25,6 +25,9 @@ struct LayerPlan {
     long long g_off, g_len;  // slot in the real-gradient vector (== slot inside the theta block of the adjoint state)
     bool exact;              // dense: double-accumulating exact kernels
     float* act = nullptr;    // output of this layer (scratch), unused for the last layer
+    float* gin = nullptr;    // gradient w.r.t. this layer's input (scratch), unused for the first layer
+    float* act2[2] = {nullptr, nullptr};   // the two buffer sets act / gin point into
+    float* gin2[2] = {nullptr, nullptr};
     float* wf = nullptr;     // conv: [tap][ci][co]
     float* wb = nullptr;     // conv: [tap][co][ci]
     bool tc = false;         // conv runs on the tcgen05 path
@@ -86,6 +89,17 @@ private:
 
     // ---- device state ----------------------------------------------------------------------------
     cudaStream_t stream_ = nullptr, stream2_ = nullptr;
+    cudaStream_t side_ = nullptr;          // side branch: weight-gradient kernels overlap the dgrad/BatchNorm chain
+    static constexpr int EV_POOL = 16;
+    cudaEvent_t ev_pool_[EV_POOL] = {};
+    int ev_next_ = 0;
+    cudaEvent_t slot_event_[2] = {};
+    bool slot_event_valid_[2] = {false, false};
+    bool side_busy_ = false;
+    bool side_capable_ = false;
+    size_t wgrad_smem_ = 0;
+    bool fuse_last_bn_ok_ = false;   // set while enqueueing the forward half of an augmented evaluation
+    bool fwd_left_last_bn_ = false;  // ... and the forward half left the last BatchNorm apply to the backward statistics kernel
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     float* Y_ = nullptr;       // [2][n_alloc]
     float* K_ = nullptr;       // [7][n_alloc]
@@ -117,6 +131,7 @@ private:
     void to_device(float* dst, const float* src, long long n);     // host or device source
     void from_device(float* dst, const float* src, long long n);   // host or device destination
     int grid_for(long long n, int per_thread = 1) const;
+    int grid_red(long long n4) const;
     SolverParams solver_params(long long n_norm) const;
 
     void upload_params();
@@ -126,10 +141,14 @@ private:
     void theta_internal_to_flat(const float* theta, float* flat);
     void theta_internal_to_real(const float* theta, float* real);
 
-    void enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact = true);
-    void enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out);
-    void launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act);
-    void enqueue_rhs(cudaStream_t s, bool aug, Ref in, Ref out) { aug ? enqueue_rhs_aug(s, in, out) : enqueue_rhs_fwd(s, in, out, false); }
+    void enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact = true, bool bn1_ready = false);
+    void enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready = false, int slot = 0, bool defer_join = false);
+    void join_side(cudaStream_t s);
+    void launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act, const LayerPlan* next_bn = nullptr);
+    void enqueue_rhs(cudaStream_t s, bool aug, Ref in, Ref out, bool bn1_ready = false) {
+        aug ? enqueue_rhs_aug(s, in, out, bn1_ready) : enqueue_rhs_fwd(s, in, out, false, bn1_ready);
+    }
+    BnFuse bn_fuse() const;
     void enqueue_prologue(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt);
     void enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt,
                        cudaGraphConditionalHandle cond, int use_cond);

@@ -282,6 +282,81 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats(Ref gin, float gscale, Ref
         if (threadIdx.x == 0) *sc.ticket = 0u;
     }
 }
+// 64-channel fast path of the backward statistics: float4 loads, 16 rows per block iteration, one block per SM.
+// Optionally also applies the FORWARD BatchNorm (fuse_fwd): y = act(gamma*xhat+beta) is written to `yout` in the same pass,
+// which merges the last forward kernel of an augmented evaluation with the first backward one.
+__global__ void __launch_bounds__(256) k_bn_bwd_stats64(Ref gin, float gscale, Ref yref, Ref xin, BnScratch sc, int act, long long M,
+                                                         Ref dgamma_ref, Ref dbeta_ref, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int fuse_fwd) {
+    const float* __restrict__ g = resolve(gin);
+    float* __restrict__ y = resolve(yref);
+    const float* __restrict__ x = resolve(xin);
+    const int chunk = threadIdx.x & 15, rg = threadIdx.x >> 4;
+    float mean[4], inv[4], ga[4], be[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        mean[k] = sc.mean[chunk * 4 + k]; inv[k] = sc.invstd[chunk * 4 + k];
+        ga[k] = fuse_fwd ? gamma[chunk * 4 + k] : 0.f; be[k] = fuse_fwd ? beta[chunk * 4 + k] : 0.f;
+    }
+    double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    for (long long r = (long long)blockIdx.x * 16 + rg; r < M; r += (long long)gridDim.x * 16) {
+        const long long i = r * 16 + chunk;
+        const float4 gv = reinterpret_cast<const float4*>(g)[i], xv = reinterpret_cast<const float4*>(x)[i];
+        const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+        float yy[4];
+        if (fuse_fwd) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) yy[k] = act_fwd(act, __fadd_rn(__fmul_rn(ga[k], __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k])), be[k]));
+            reinterpret_cast<float4*>(y)[i] = make_float4(yy[0], yy[1], yy[2], yy[3]);
+        } else {
+            const float4 yv = reinterpret_cast<const float4*>(y)[i];
+            yy[0] = yv.x; yy[1] = yv.y; yy[2] = yv.z; yy[3] = yv.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float dy = act_bwd(act, yy[k], __fmul_rn(gscale, gg[k]));
+            const float xh = __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k]);
+            a[k] += (double)dy; b[k] += (double)dy * (double)xh;
+        }
+    }
+    __shared__ double sm[2][4][256];
+    __shared__ int s_last;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sm[0][k][threadIdx.x] = a[k]; sm[1][k][threadIdx.x] = b[k]; }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double sa = 0, sb = 0;
+            for (int r = 0; r < 16; ++r) { sa += sm[0][k][r * 16 + threadIdx.x]; sb += sm[1][k][r * 16 + threadIdx.x]; }
+            atomicAdd(sc.acc + threadIdx.x * 4 + k, sa);
+            atomicAdd(sc.acc + 64 + threadIdx.x * 4 + k, sb);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int tk = atomicAdd(sc.ticket, 1u);
+        s_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        float* __restrict__ dgamma = resolve(dgamma_ref);
+        float* __restrict__ dbeta = resolve(dbeta_ref);
+        if (threadIdx.x < 64) {
+            const int c = threadIdx.x;
+            const double sdy = *((volatile double*)(sc.acc + c)), sdyxh = *((volatile double*)(sc.acc + 64 + c));
+            dgamma[c] = (float)sdyxh;
+            dbeta[c] = (float)sdy;
+            sc.m_dy[c] = (float)(sdy / (double)M);
+            sc.m_dyxh[c] = (float)(sdyxh / (double)M);
+            sc.acc[c] = 0.0; sc.acc[64 + c] = 0.0;
+        }
+        if (threadIdx.x == 0) *sc.ticket = 0u;
+    }
+}
+
 // dx = gamma*invstd * ((dy - mean(dy)) - xhat*mean(dy*xhat))
 __global__ void __launch_bounds__(256) k_bn_bwd_dx(Ref gin, float gscale, Ref yref, Ref xin, const float* __restrict__ gamma, BnScratch sc,
                                                     int act, long long M, int C, Ref dxout) {

@@ -12,6 +12,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "layer_kernels.cuh"
 
 namespace n4j {
 
@@ -37,9 +38,21 @@ __device__ __forceinline__ void st4(float* p, long long i, float4 v) { reinterpr
 // K1: yWorking = y + (a_S * h) . K[0:S]      S = 1..6;  S = 0 is the init-step probe y + h*K0.
 // Zero coefficients (a_62) are skipped at compile time.  Algorithmic traffic: (nnz + 2) vectors.
 // ---------------------------------------------------------------------------------------------------
+// Optional fusion: when the inner graph starts with a 64-channel BatchNorm, the pass that writes yWorking also produces
+// that layer's batch statistics (column sums of the NHWC state in double, last block finalises mean / invstd), so the
+// RHS evaluation that follows starts directly with the BatchNorm apply.
+struct BnFuse {
+    int enabled;
+    BnScratch sc;
+    float eps;
+    long long rows;   // B*H*W
+    long long nz4;    // float4 count of the z block of the state (the adjoint state has more blocks behind it)
+};
+
 template <int S>
 __global__ void __launch_bounds__(256) k_stage_combine(const Ctrl* __restrict__ c, float* __restrict__ Ybase,
-                                                        const float* __restrict__ Kbase, long long stride, long long n4) {
+                                                        const float* __restrict__ Kbase, long long stride, long long i_begin, long long n4,
+                                                        BnFuse bf) {
     const float h = c->h;
     const int yc = c->y_cur;
     const float* __restrict__ y = Ybase + (long long)yc * stride;
@@ -52,8 +65,9 @@ __global__ void __launch_bounds__(256) k_stage_combine(const Ctrl* __restrict__ 
         coef[j] = S == 0 ? h : __fmul_rn(c_A[S - 1][j], h);   // stepCoeffPerStage.mul(step)
         kr[j] = Kbase + (long long)c->krow[j] * stride;
     }
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
     const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+    for (long long i = i_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {   // float4 range [i_begin, n4)
         const float4 yv = ld4(y, i);
         float4 k0 = ld4(kr[0], i);
         float4 acc = make_float4(__fmul_rn(coef[0], k0.x), __fmul_rn(coef[0], k0.y), __fmul_rn(coef[0], k0.z), __fmul_rn(coef[0], k0.w));
@@ -66,7 +80,52 @@ __global__ void __launch_bounds__(256) k_stage_combine(const Ctrl* __restrict__ 
             acc.z = __fmaf_rn(coef[j], kj.z, acc.z);
             acc.w = __fmaf_rn(coef[j], kj.w, acc.w);
         }
-        st4(yw, i, make_float4(__fadd_rn(yv.x, acc.x), __fadd_rn(yv.y, acc.y), __fadd_rn(yv.z, acc.z), __fadd_rn(yv.w, acc.w)));
+        const float4 o = make_float4(__fadd_rn(yv.x, acc.x), __fadd_rn(yv.y, acc.y), __fadd_rn(yv.z, acc.z), __fadd_rn(yv.w, acc.w));
+        st4(yw, i, o);
+        if (bf.enabled && i < bf.nz4) {      // 64 channels = 16 float4 per row; this thread always sees chunk (threadIdx.x & 15)
+            s1[0] += (double)o.x; s2[0] += (double)o.x * (double)o.x;
+            s1[1] += (double)o.y; s2[1] += (double)o.y * (double)o.y;
+            s1[2] += (double)o.z; s2[2] += (double)o.z * (double)o.z;
+            s1[3] += (double)o.w; s2[3] += (double)o.w * (double)o.w;
+        }
+    }
+    if (bf.enabled) {
+        __shared__ double sm[2][4][256];
+        __shared__ int s_last;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { sm[0][k][threadIdx.x] = s1[k]; sm[1][k][threadIdx.x] = s2[k]; }
+        __syncthreads();
+        if (threadIdx.x < 16) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double a = 0, b = 0;
+                for (int r = 0; r < 16; ++r) { a += sm[0][k][r * 16 + threadIdx.x]; b += sm[1][k][r * 16 + threadIdx.x]; }
+                const int ch = threadIdx.x * 4 + k;
+                atomicAdd(bf.sc.acc + ch, a);
+                atomicAdd(bf.sc.acc + 64 + ch, b);
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int tk = atomicAdd(bf.sc.ticket, 1u);
+            s_last = (tk == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            if (threadIdx.x < 64) {
+                const int ch = threadIdx.x;
+                const double sum = *((volatile double*)(bf.sc.acc + ch)), sq = *((volatile double*)(bf.sc.acc + 64 + ch));
+                const double mean = sum / (double)bf.rows;
+                double var = sq / (double)bf.rows - mean * mean;
+                if (var < 0) var = 0;
+                bf.sc.mean[ch] = (float)mean;
+                bf.sc.invstd[ch] = (float)(1.0 / sqrt(var + (double)bf.eps));
+                bf.sc.acc[ch] = 0.0; bf.sc.acc[64 + ch] = 0.0;
+            }
+            if (threadIdx.x == 0) *bf.sc.ticket = 0u;
+        }
     }
 }
 

@@ -32,6 +32,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Bounded wait: a lost arrival traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
         uint32_t ok;
         asm volatile(
