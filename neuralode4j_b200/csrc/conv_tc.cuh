@@ -211,8 +211,8 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
             const int c = et & 63, r0 = (et >> 6) * 64;
             double s1 = 0.0, s2 = 0.0;
             for (int r = r0; r < r0 + 64; ++r) { const double x = (double)sT[r * 65 + c]; s1 += x; s2 += x * x; }
-            atomicAdd(a.bn.acc + c, s1);
-            atomicAdd(a.bn.acc + 64 + c, s2);
+            atomicAdd(a.bn.acc + c * ACC_STRIDE, s1);
+            atomicAdd(a.bn.acc + (64 + c) * ACC_STRIDE, s2);
             __threadfence();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             __shared__ int s_last;
@@ -224,13 +224,13 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
             if (s_last) {
                 __threadfence();
                 if (et < 64) {
-                    const double sum = *((volatile double*)(a.bn.acc + et)), sq = *((volatile double*)(a.bn.acc + 64 + et));
+                    const double sum = *((volatile double*)(a.bn.acc + et * ACC_STRIDE)), sq = *((volatile double*)(a.bn.acc + (64 + et) * ACC_STRIDE));
                     const double mean = sum / (double)a.bn_rows;
                     double var = sq / (double)a.bn_rows - mean * mean;
                     if (var < 0) var = 0;
                     a.bn.mean[et] = (float)mean;
                     a.bn.invstd[et] = (float)(1.0 / sqrt(var + (double)a.bn_eps));
-                    a.bn.acc[et] = 0.0; a.bn.acc[64 + et] = 0.0;
+                    a.bn.acc[et * ACC_STRIDE] = 0.0; a.bn.acc[(64 + et) * ACC_STRIDE] = 0.0;
                 }
                 if (et == 0) *a.bn.ticket = 0u;
             }

@@ -123,6 +123,9 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
     N4J_CUDA(cudaMemsetAsync(K_, 0, sizeof(float) * 7 * n_alloc_, stream_));
     N4J_CUDA(cudaMalloc(&ctrl_, sizeof(Ctrl)));
     N4J_CUDA(cudaMemsetAsync(ctrl_, 0, sizeof(Ctrl), stream_));
+    N4J_CUDA(cudaMalloc(&red_acc_, sizeof(double) * 4 * ACC_SLOTS * ACC_STRIDE));
+    N4J_CUDA(cudaMemsetAsync(red_acc_, 0, sizeof(double) * 4 * ACC_SLOTS * ACC_STRIDE, stream_));
+    N4J_CUDA(cudaMemcpyAsync(&ctrl_->red_acc, &red_acc_, sizeof(double*), cudaMemcpyHostToDevice, stream_));
     N4J_CUDA(cudaHostAlloc(&ctrl_host_, sizeof(Ctrl), cudaHostAllocDefault));
     N4J_CUDA(cudaMalloc(&log_, sizeof(n4j_step_rec) * log_cap_));
     max_pairs_ = 4096;
@@ -174,8 +177,8 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
         }
         if (l.d.kind == N4J_LAYER_BATCHNORM) {
             const int cc = l.c_out;
-            N4J_CUDA(cudaMalloc(&l.bn.acc, sizeof(double) * 2 * cc));
-            N4J_CUDA(cudaMemsetAsync(l.bn.acc, 0, sizeof(double) * 2 * cc, stream_));
+            N4J_CUDA(cudaMalloc(&l.bn.acc, sizeof(double) * 2 * cc * ACC_STRIDE));
+            N4J_CUDA(cudaMemsetAsync(l.bn.acc, 0, sizeof(double) * 2 * cc * ACC_STRIDE, stream_));
             N4J_CUDA(cudaMalloc(&l.bn.ticket, sizeof(unsigned int)));
             N4J_CUDA(cudaMemsetAsync(l.bn.ticket, 0, sizeof(unsigned int), stream_));
             float* f = nullptr;
@@ -199,7 +202,7 @@ Engine::~Engine() {
         if (l.d.kind == N4J_LAYER_BATCHNORM) { cudaFree(l.bn.acc); cudaFree(l.bn.ticket); cudaFree(l.bn.mean); }
     }
     for (DevBuf* b : {&params_, &gradflat_, &zt_, &gt_, &io_, &io2_, &gb_[0], &gb_[1], &gb_[2], &theta_tmp_, &wpart_, &dldt_}) cudaFree(b->p);
-    cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_);
+    cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(red_acc_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_);
     cudaFreeHost(ctrl_host_); cudaFreeHost(tpair_host_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -688,7 +691,6 @@ __global__ void k_reset_ctrl(Ctrl* c) {
     if (threadIdx.x == 0) {
         c->y_cur = 0; c->status = 0; c->log_n = 0; c->seg_index = 0;
         c->nfe = 0; c->accepted = 0; c->rejected = 0; c->solves = 0; c->trials = 0;
-        c->acc[0] = c->acc[1] = c->acc[2] = c->acc[3] = 0.0;
         c->ticket[0] = c->ticket[1] = c->ticket[2] = c->ticket[3] = 0u;
         c->done = 0; c->err = 0.f; c->h = 0.f;
     }
@@ -1002,6 +1004,7 @@ void Engine::bench_solver_pass(long long n, int iters, float* us) {
     std::memset(&hc, 0, sizeof(hc));
     for (int j = 0; j < 7; ++j) { hc.krow[j] = j; hc.krow_prev[j] = j; }
     hc.h = 0.01f; hc.t_end = 1e30f;
+    hc.red_acc = red_acc_;
     N4J_CUDA(cudaMemcpyAsync(c, &hc, sizeof(Ctrl), cudaMemcpyHostToDevice, stream_));
     SolverParams sp = solver_params(n);
     sp.max_trials = 1LL << 60; sp.log_cap = 0;

@@ -104,6 +104,7 @@ private:
     float* Y_ = nullptr;       // [2][n_alloc]
     float* K_ = nullptr;       // [7][n_alloc]
     Ctrl* ctrl_ = nullptr;
+    double* red_acc_ = nullptr;   // strided accumulators of the scalar reductions (error norm, initial step)
     Ctrl* ctrl_host_ = nullptr;   // pinned
     n4j_step_rec* log_ = nullptr;
     int log_cap_ = 1 << 16;

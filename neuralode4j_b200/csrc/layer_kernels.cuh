@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k_act_bwd(Ref gin, float gscale, Ref yref
 // accumulators.  Requires C % 4 == 0 and (C/4) dividing 256 (vector path) else the generic path.
 // ---------------------------------------------------------------------------------------------------
 struct BnScratch {
-    double* acc;            // [2*C]
+    double* acc;            // [2*C] accumulators, ACC_STRIDE doubles apart
     unsigned int* ticket;   // [1]
     float* mean;            // [C]
     float* invstd;          // [C]
@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(256) k_bn_stats(Ref xin, long long M, int C, f
             double a = 0, b = 0;
             for (int r = 0; r < rows_per_iter; ++r) { a += sm[0][k][r * cg + threadIdx.x]; b += sm[1][k][r * cg + threadIdx.x]; }
             const int c = threadIdx.x * 4 + k;
-            atomicAdd(sc.acc + c, a);
-            atomicAdd(sc.acc + C + c, b);
+            atomicAdd(sc.acc + c * ACC_STRIDE, a);
+            atomicAdd(sc.acc + (C + c) * ACC_STRIDE, b);
         }
         __threadfence();
     }
@@ -176,13 +176,13 @@ __global__ void __launch_bounds__(256) k_bn_stats(Ref xin, long long M, int C, f
     if (s_last) {
         __threadfence();
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const double sum = *((volatile double*)(sc.acc + c)), sq = *((volatile double*)(sc.acc + C + c));
+            const double sum = *((volatile double*)(sc.acc + c * ACC_STRIDE)), sq = *((volatile double*)(sc.acc + (C + c) * ACC_STRIDE));
             const double mean = sum / (double)M;
             double var = sq / (double)M - mean * mean;
             if (var < 0) var = 0;
             sc.mean[c] = (float)mean;
             sc.invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-            sc.acc[c] = 0.0; sc.acc[C + c] = 0.0;
+            sc.acc[c * ACC_STRIDE] = 0.0; sc.acc[(C + c) * ACC_STRIDE] = 0.0;
         }
         if (threadIdx.x == 0) *sc.ticket = 0u;
     }
@@ -242,8 +242,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats(Ref gin, float gscale, Ref
         if (threadIdx.x < C) {
             double sa = 0, sb = 0;
             for (int r = 0; r < rows_per_iter; ++r) { sa += sm[0][r * C + threadIdx.x]; sb += sm[1][r * C + threadIdx.x]; }
-            atomicAdd(sc.acc + threadIdx.x, sa);
-            atomicAdd(sc.acc + C + threadIdx.x, sb);
+            atomicAdd(sc.acc + threadIdx.x * ACC_STRIDE, sa);
+            atomicAdd(sc.acc + (C + threadIdx.x) * ACC_STRIDE, sb);
             __threadfence();
         }
     } else {
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats(Ref gin, float gscale, Ref
                 v[0] += (double)dy; v[1] += (double)dy * (double)xh;
             }
             block_sum<2>(v);
-            if (threadIdx.x == 0) { atomicAdd(sc.acc + c, v[0]); atomicAdd(sc.acc + C + c, v[1]); __threadfence(); }
+            if (threadIdx.x == 0) { atomicAdd(sc.acc + c * ACC_STRIDE, v[0]); atomicAdd(sc.acc + (C + c) * ACC_STRIDE, v[1]); __threadfence(); }
         }
     }
     __syncthreads();
@@ -272,12 +272,12 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats(Ref gin, float gscale, Ref
         float* __restrict__ dgamma = resolve(dgamma_ref);
         float* __restrict__ dbeta = resolve(dbeta_ref);
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const double sdy = *((volatile double*)(sc.acc + c)), sdyxh = *((volatile double*)(sc.acc + C + c));
+            const double sdy = *((volatile double*)(sc.acc + c * ACC_STRIDE)), sdyxh = *((volatile double*)(sc.acc + (C + c) * ACC_STRIDE));
             dgamma[c] = (float)sdyxh;
             dbeta[c] = (float)sdy;
             sc.m_dy[c] = (float)(sdy / (double)M);
             sc.m_dyxh[c] = (float)(sdyxh / (double)M);
-            sc.acc[c] = 0.0; sc.acc[C + c] = 0.0;
+            sc.acc[c * ACC_STRIDE] = 0.0; sc.acc[(C + c) * ACC_STRIDE] = 0.0;
         }
         if (threadIdx.x == 0) *sc.ticket = 0u;
     }
@@ -329,8 +329,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats64(Ref gin, float gscale, R
         for (int k = 0; k < 4; ++k) {
             double sa = 0, sb = 0;
             for (int r = 0; r < 16; ++r) { sa += sm[0][k][r * 16 + threadIdx.x]; sb += sm[1][k][r * 16 + threadIdx.x]; }
-            atomicAdd(sc.acc + threadIdx.x * 4 + k, sa);
-            atomicAdd(sc.acc + 64 + threadIdx.x * 4 + k, sb);
+            atomicAdd(sc.acc + (threadIdx.x * 4 + k) * ACC_STRIDE, sa);
+            atomicAdd(sc.acc + (64 + threadIdx.x * 4 + k) * ACC_STRIDE, sb);
         }
         __threadfence();
     }
@@ -346,12 +346,12 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats64(Ref gin, float gscale, R
         float* __restrict__ dbeta = resolve(dbeta_ref);
         if (threadIdx.x < 64) {
             const int c = threadIdx.x;
-            const double sdy = *((volatile double*)(sc.acc + c)), sdyxh = *((volatile double*)(sc.acc + 64 + c));
+            const double sdy = *((volatile double*)(sc.acc + c * ACC_STRIDE)), sdyxh = *((volatile double*)(sc.acc + (64 + c) * ACC_STRIDE));
             dgamma[c] = (float)sdyxh;
             dbeta[c] = (float)sdy;
             sc.m_dy[c] = (float)(sdy / (double)M);
             sc.m_dyxh[c] = (float)(sdyxh / (double)M);
-            sc.acc[c] = 0.0; sc.acc[64 + c] = 0.0;
+            sc.acc[c * ACC_STRIDE] = 0.0; sc.acc[(64 + c) * ACC_STRIDE] = 0.0;
         }
         if (threadIdx.x == 0) *sc.ticket = 0u;
     }

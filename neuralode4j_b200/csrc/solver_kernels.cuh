@@ -101,8 +101,8 @@ __global__ void __launch_bounds__(256) k_stage_combine(const Ctrl* __restrict__ 
                 double a = 0, b = 0;
                 for (int r = 0; r < 16; ++r) { a += sm[0][k][r * 16 + threadIdx.x]; b += sm[1][k][r * 16 + threadIdx.x]; }
                 const int ch = threadIdx.x * 4 + k;
-                atomicAdd(bf.sc.acc + ch, a);
-                atomicAdd(bf.sc.acc + 64 + ch, b);
+                atomicAdd(bf.sc.acc + ch * ACC_STRIDE, a);
+                atomicAdd(bf.sc.acc + (64 + ch) * ACC_STRIDE, b);
             }
             __threadfence();
         }
@@ -116,13 +116,13 @@ __global__ void __launch_bounds__(256) k_stage_combine(const Ctrl* __restrict__ 
             __threadfence();
             if (threadIdx.x < 64) {
                 const int ch = threadIdx.x;
-                const double sum = *((volatile double*)(bf.sc.acc + ch)), sq = *((volatile double*)(bf.sc.acc + 64 + ch));
+                const double sum = *((volatile double*)(bf.sc.acc + ch * ACC_STRIDE)), sq = *((volatile double*)(bf.sc.acc + (64 + ch) * ACC_STRIDE));
                 const double mean = sum / (double)bf.rows;
                 double var = sq / (double)bf.rows - mean * mean;
                 if (var < 0) var = 0;
                 bf.sc.mean[ch] = (float)mean;
                 bf.sc.invstd[ch] = (float)(1.0 / sqrt(var + (double)bf.eps));
-                bf.sc.acc[ch] = 0.0; bf.sc.acc[64 + ch] = 0.0;
+                bf.sc.acc[ch * ACC_STRIDE] = 0.0; bf.sc.acc[(64 + ch) * ACC_STRIDE] = 0.0;
             }
             if (threadIdx.x == 0) *bf.sc.ticket = 0u;
         }
@@ -251,11 +251,9 @@ __global__ void __launch_bounds__(256) k_error_ctrl(Ctrl* c, const float* __rest
         N4J_ERR_LANE(x) N4J_ERR_LANE(y) N4J_ERR_LANE(z) N4J_ERR_LANE(w)
 #undef N4J_ERR_LANE
     }
-    if (publish_and_elect<1>(s, c->acc, c->ticket)) {
+    if (publish_and_elect<1>(s, c->red_acc, c->ticket)) {
         if (threadIdx.x == 0) {
-            const double sum = *((volatile double*)c->acc);
-            c->acc[0] = 0.0;
-            c->ticket[0] = 0u;
+            const double sum = s[0];
             controller_after_error(c, sum, p, log, dout);
             if (use_cond) cudaGraphSetConditional(cond, c->done ? 0u : 1u);
         }
@@ -317,11 +315,10 @@ __global__ void __launch_bounds__(256) k_init_sums(Ctrl* c, const float* __restr
         N4J_LANE(x) N4J_LANE(y) N4J_LANE(z) N4J_LANE(w)
 #undef N4J_LANE
     }
-    if (publish_and_elect<2>(s, c->acc, c->ticket)) {
+    if (publish_and_elect<2>(s, c->red_acc, c->ticket)) {
         if (threadIdx.x == 0) {
-            const float Yr = (float)*((volatile double*)&c->acc[0]);
-            const float Dr = (float)*((volatile double*)&c->acc[1]);
-            c->acc[0] = 0.0; c->acc[1] = 0.0; c->ticket[0] = 0u;
+            const float Yr = (float)s[0];
+            const float Dr = (float)s[1];
             float h = ((double)Yr < 1.0e-10 || (double)Dr < 1.0e-10) ? 1e-6f : __fmul_rn(sqrtf(__fdiv_rn(Yr, Dr)), 0.01f);
             if (c->backward) h = -h;
             c->h = h;          // probe step for equation.step(ones(1), step)
@@ -349,10 +346,9 @@ __global__ void __launch_bounds__(256) k_init_final(Ctrl* c, const float* __rest
         N4J_LANE(x) N4J_LANE(y) N4J_LANE(z) N4J_LANE(w)
 #undef N4J_LANE
     }
-    if (publish_and_elect<1>(s, c->acc, c->ticket)) {
+    if (publish_and_elect<1>(s, c->red_acc, c->ticket)) {
         if (threadIdx.x == 0) {
-            const float DDs = (float)*((volatile double*)&c->acc[0]);
-            c->acc[0] = 0.0; c->ticket[0] = 0u;
+            const float DDs = (float)s[0];
             float h = c->h;
             const float DD = __fdiv_rn(sqrtf(DDs), h);                       // signed (:118,122)
             const float m = fmaxf(sqrtf(c->init_D), DD);
