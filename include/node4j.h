@@ -170,11 +170,15 @@ int32_t node4j_rhs_vjp(n4j_handle* h, const float* z, float t, const float* g, f
 int32_t node4j_error_norm(n4j_handle* h, const float* K, const float* y0, const float* y1, float step, int64_t n,
                           float* err_out);
 
-/* Multi-GPU (new work; the reference is single-device): the minibatch is sharded by rows, one process per GPU.
- * `nccl_unique_id` is the 128-byte ncclUniqueId created by rank 0 and distributed by the host framework.
- * After this call the step controller, batchnorm statistics and parameter gradients are global. */
-int32_t node4j_comm_init(n4j_handle* h, int32_t rank, int32_t world, const void* nccl_unique_id, int64_t global_batch);
-int32_t node4j_comm_unique_id(void* out128);
+/* Multi-GPU (new work; the reference is single-device): the minibatch is sharded by rows, one process per GPU of one
+ * NVLink/NVSwitch box.  The couplings of the path (error-norm scalar, BatchNorm statistics, parameter gradients) are
+ * exchanged by one-shot all-reduces over peer-mapped memory written into the kernels themselves, so there is no NCCL
+ * call on the data path.  Setup: every rank calls node4j_comm_export (64-byte cudaIpcMemHandle_t of its exchange region),
+ * the host framework all-gathers the handles (rank order), every rank calls node4j_comm_init with all of them.
+ * Afterwards the step controller, BatchNorm statistics and the parameter gradients are global: `graph.shape[0]` is the
+ * LOCAL batch, global_batch = world * local batch. */
+int32_t node4j_comm_export(n4j_handle* h, void* handle64);
+int32_t node4j_comm_init(n4j_handle* h, int32_t rank, int32_t world, const void* all_handles, int64_t global_batch);
 
 /* Microbenchmark hook used by bench.py for the roofline figure: runs `iters` back-to-back trial-step solver passes
  * (6 stage combinations + error norm, no RHS) over a state of n floats and returns the average device time of one

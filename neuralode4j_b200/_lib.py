@@ -22,7 +22,7 @@ EXPORTS = [
     "node4j_abi_version", "node4j_last_error", "node4j_device_count", "node4j_create", "node4j_destroy",
     "node4j_num_params", "node4j_num_real_params", "node4j_state_len", "node4j_bind_params", "node4j_forward",
     "node4j_backward", "node4j_get_step_log", "node4j_rhs", "node4j_rhs_vjp", "node4j_error_norm",
-    "node4j_comm_init", "node4j_comm_unique_id", "node4j_bench_solver_pass", "node4j_bench_piece", "node4j_get_stream",
+    "node4j_comm_init", "node4j_comm_export", "node4j_bench_solver_pass", "node4j_bench_piece", "node4j_get_stream",
 ]
 BENCH_RHS_FWD, BENCH_RHS_AUG, BENCH_CONV_FWD, BENCH_CONV_DGRAD, BENCH_CONV_WGRAD = 1, 2, 3, 4, 5
 
@@ -103,8 +103,8 @@ def load():
     L.node4j_error_norm.argtypes = [vp, vp, vp, vp, f32, i64, C.POINTER(f32)]
     L.node4j_comm_init.restype = i32
     L.node4j_comm_init.argtypes = [vp, i32, i32, vp, i64]
-    L.node4j_comm_unique_id.restype = i32
-    L.node4j_comm_unique_id.argtypes = [vp]
+    L.node4j_comm_export.restype = i32
+    L.node4j_comm_export.argtypes = [vp, vp]
     L.node4j_bench_solver_pass.restype = i32
     L.node4j_bench_solver_pass.argtypes = [vp, i64, i32, C.POINTER(f32)]
     L.node4j_bench_piece.restype = i32

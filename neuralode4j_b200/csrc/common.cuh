@@ -10,6 +10,8 @@
 
 namespace n4j {
 
+struct CommDev;
+
 // ---------------------------------------------------------------------------------------------------
 // Device-resident control block of one solve.  The step controller lives on the GPU: kernels read the
 // current step size / buffer rotation from here and the last block of the error-norm kernel updates it,
@@ -41,6 +43,7 @@ struct Ctrl {
     float init_D;
     // --- reductions (accumulators: separate strided buffer, see ACC_STRIDE) --------------------------------
     double* red_acc;
+    CommDev* comm;            // nullptr on a single GPU
     unsigned int ticket[4];
     // --- counters (n4j_stats) ----------------------------------------------------------------------------
     long long nfe, accepted, rejected, solves, trials, trials_this_solve;
@@ -55,6 +58,9 @@ struct SolverParams {
     long long n_norm;      // N of the reference's mean (includes the BatchNorm-stat pad of the adjoint state)
     long long max_trials;
     int log_cap;
+    // multi-GPU: float4 index where the rank-replicated part of the state (theta, a_t) begins; only rank 0 counts it
+    long long rep_begin4;
+    int count_rep;
 };
 
 // Indirect tensor reference: the address is resolved on the device from the control block, which is how
@@ -74,6 +80,74 @@ __device__ __forceinline__ float* resolve(const Ref& r) {
 }
 
 inline Ref fixed_ref(float* p, long long off = 0) { return Ref{p, nullptr, 0, off, 0}; }
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-GPU exchange over NVLink peer memory (one process per GPU, CUDA IPC).  The path's couplings are tiny — the
+// error-norm scalar, 2*C BatchNorm sums, and the parameter-gradient block — so they are exchanged by a ONE-SHOT
+// all-reduce written into the kernels themselves: every rank stores its partial values straight into every peer's
+// mailbox, raises a flag, waits for the peers' flags in its own mailbox and sums the contributions in rank order
+// (bitwise identical totals on all ranks => identical controller decisions).  Two parities alternate; a rank can only
+// be one exchange ahead of its slowest peer, so two buffers are enough.
+// ---------------------------------------------------------------------------------------------------
+constexpr int COMM_MAX_WORLD = 8;
+constexpr int COMM_SLOT = 256;                                   // doubles per rank per small exchange
+constexpr long long COMM_OFF_FLAGS = 0;                          // uint64 flag[2][8]
+constexpr long long COMM_OFF_XFLAGS = 256;                       // uint64 xflag[2][8]
+constexpr long long COMM_OFF_MBOX = 512;                         // double mbox[2][8][COMM_SLOT]
+constexpr long long COMM_OFF_XBUF = COMM_OFF_MBOX + 2LL * COMM_MAX_WORLD * COMM_SLOT * 8;   // float xbuf[2][xcap]
+
+struct CommDev {
+    int rank, world;
+    int status;                       // != 0: a peer did not show up in time
+    int pad_;
+    unsigned long long seq_small;     // small exchanges completed
+    unsigned long long seq_x;         // vector exchanges completed
+    unsigned int xticket;
+    unsigned int pad2_;
+    long long xcap;                   // floats per parity in xbuf
+    char* peer[COMM_MAX_WORLD];       // base of every rank's comm region (peer[rank] is the local one)
+};
+
+__device__ __forceinline__ bool comm_wait_flag(volatile unsigned long long* f, unsigned long long seq, CommDev* cm) {
+    for (unsigned int spin = 0; spin < (1u << 28); ++spin) {
+        if (*f >= seq) return true;
+        if ((spin & 1023) == 1023) __nanosleep(64);
+    }
+    cm->status = 1;
+    return false;
+}
+
+// All threads of ONE block (blockDim >= world); vals[n] (shared memory, n <= COMM_SLOT) in -> global totals out.
+__device__ __forceinline__ void comm_allreduce_block(CommDev* cm, double* vals, int n) {
+    __shared__ unsigned long long s_seq;
+    if (threadIdx.x == 0) { s_seq = cm->seq_small + 1; cm->seq_small = s_seq; }
+    __syncthreads();
+    const unsigned long long seq = s_seq;
+    const int par = (int)(seq & 1), me = cm->rank, W = cm->world;
+    for (int idx = threadIdx.x; idx < W * n; idx += blockDim.x) {
+        const int pr = idx / n, i = idx - pr * n;
+        double* dst = reinterpret_cast<double*>(cm->peer[pr] + COMM_OFF_MBOX) + ((par * COMM_MAX_WORLD + me) * COMM_SLOT + i);
+        *reinterpret_cast<volatile double*>(dst) = vals[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < W) {
+        volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(cm->peer[threadIdx.x] + COMM_OFF_FLAGS) + par * COMM_MAX_WORLD + me;
+        *f = seq;
+        __threadfence_system();
+        volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(cm->peer[me] + COMM_OFF_FLAGS) + par * COMM_MAX_WORLD + threadIdx.x;
+        comm_wait_flag(mine, seq, cm);
+    }
+    __syncthreads();
+    __threadfence_system();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double t = 0.0;
+        for (int q = 0; q < W; ++q)
+            t += *reinterpret_cast<volatile double*>(reinterpret_cast<double*>(cm->peer[me] + COMM_OFF_MBOX) + ((par * COMM_MAX_WORLD + q) * COMM_SLOT + i));
+        vals[i] = t;
+    }
+    __syncthreads();
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Reduction helpers (warp shuffle + block reduce in double)
@@ -114,8 +188,9 @@ constexpr int ACC_SLOTS = 8;    // scalar reductions are spread over 8 slots per
 // Publishes this block's partial sums and returns true (block-uniform) in the last block to arrive; in that block
 // thread 0 holds the grand totals in v[] and the accumulators are re-armed (zeroed).
 template <int NV>
-__device__ __forceinline__ bool publish_and_elect(double (&v)[NV], double* acc, unsigned int* ticket) {
+__device__ __forceinline__ bool publish_and_elect(double (&v)[NV], double* acc, unsigned int* ticket, CommDev* cm = nullptr) {
     __shared__ int s_last;
+    __shared__ double s_tot[NV];
     block_sum<NV>(v);
     if (threadIdx.x == 0) {
         const int slot = blockIdx.x & (ACC_SLOTS - 1);
@@ -135,11 +210,19 @@ __device__ __forceinline__ bool publish_and_elect(double (&v)[NV], double* acc, 
                     *a = 0.0;
                 }
                 v[k] = t;
+                s_tot[k] = t;
             }
             *ticket = 0u;
         }
     }
     __syncthreads();
+    if (s_last && cm) {   // multi-GPU: the last block of every rank exchanges its totals
+        comm_allreduce_block(cm, s_tot, NV);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = s_tot[k];
+        }
+    }
     return s_last != 0;
 }
 

@@ -71,6 +71,38 @@ __global__ void __launch_bounds__(256) k_conv_w_to_tc(const float* __restrict__ 
     }
 }
 
+// comm_allreduce_block for the four epilogue warps of the conv kernel (named barrier 1 instead of __syncthreads)
+__device__ __forceinline__ void comm_allreduce_epilogue(CommDev* cm, double* vals, int n, int et) {
+    __shared__ unsigned long long s_seq;
+    if (et == 0) { s_seq = cm->seq_small + 1; cm->seq_small = s_seq; }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    const unsigned long long seq = s_seq;
+    const int par = (int)(seq & 1), me = cm->rank, W = cm->world;
+    for (int idx = et; idx < W * n; idx += 128) {
+        const int pr = idx / n, i = idx - pr * n;
+        double* dst = reinterpret_cast<double*>(cm->peer[pr] + COMM_OFF_MBOX) + ((par * COMM_MAX_WORLD + me) * COMM_SLOT + i);
+        *reinterpret_cast<volatile double*>(dst) = vals[i];
+    }
+    __threadfence_system();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (et < W) {
+        volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(cm->peer[et] + COMM_OFF_FLAGS) + par * COMM_MAX_WORLD + me;
+        *f = seq;
+        __threadfence_system();
+        volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(cm->peer[me] + COMM_OFF_FLAGS) + par * COMM_MAX_WORLD + et;
+        comm_wait_flag(mine, seq, cm);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    __threadfence_system();
+    for (int i = et; i < n; i += 128) {
+        double t = 0.0;
+        for (int q = 0; q < W; ++q)
+            t += *reinterpret_cast<volatile double*>(reinterpret_cast<double*>(cm->peer[me] + COMM_OFF_MBOX) + ((par * COMM_MAX_WORLD + q) * COMM_SLOT + i));
+        vals[i] = t;
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 struct ConvTcArgs {
     const float* img;     // operand image (hi then lo)
     const float* wimg;    // weight images [9][2][4096]
@@ -223,14 +255,18 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (s_last) {
                 __threadfence();
+                double* tot = reinterpret_cast<double*>(sT);          // 128 doubles, transposition buffer is free again
+                tot[et] = *((volatile double*)(a.bn.acc + et * ACC_STRIDE));
+                a.bn.acc[et * ACC_STRIDE] = 0.0;
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (a.bn.cm) comm_allreduce_epilogue(a.bn.cm, tot, 128, et);
+                const double Mt = a.bn.cm ? (double)a.bn.rows_total : (double)a.bn_rows;
                 if (et < 64) {
-                    const double sum = *((volatile double*)(a.bn.acc + et * ACC_STRIDE)), sq = *((volatile double*)(a.bn.acc + (64 + et) * ACC_STRIDE));
-                    const double mean = sum / (double)a.bn_rows;
-                    double var = sq / (double)a.bn_rows - mean * mean;
+                    const double mean = tot[et] / Mt;
+                    double var = tot[64 + et] / Mt - mean * mean;
                     if (var < 0) var = 0;
                     a.bn.mean[et] = (float)mean;
                     a.bn.invstd[et] = (float)(1.0 / sqrt(var + (double)a.bn_eps));
-                    a.bn.acc[et * ACC_STRIDE] = 0.0; a.bn.acc[(64 + et) * ACC_STRIDE] = 0.0;
                 }
                 if (et == 0) *a.bn.ticket = 0u;
             }

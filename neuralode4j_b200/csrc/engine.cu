@@ -202,6 +202,8 @@ Engine::~Engine() {
         if (l.d.kind == N4J_LAYER_BATCHNORM) { cudaFree(l.bn.acc); cudaFree(l.bn.ticket); cudaFree(l.bn.mean); }
     }
     for (DevBuf* b : {&params_, &gradflat_, &zt_, &gt_, &io_, &io2_, &gb_[0], &gb_[1], &gb_[2], &theta_tmp_, &wpart_, &dldt_}) cudaFree(b->p);
+    for (void* pp : peer_ptrs_) cudaIpcCloseMemHandle(pp);
+    cudaFree(comm_region_); cudaFree(comm_dev_);
     cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(red_acc_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_);
     cudaFreeHost(ctrl_host_); cudaFreeHost(tpair_host_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -272,6 +274,7 @@ SolverParams Engine::solver_params(long long n_norm) const {
     p.safety = (float)cfg_.safety; p.max_growth = (float)cfg_.max_growth; p.min_reduction = (float)cfg_.min_reduction;
     p.order = cfg_.order; p.flags = cfg_.flags;
     p.n_norm = n_norm; p.max_trials = cfg_.max_trials; p.log_cap = log_cap_;
+    p.rep_begin4 = 1LL << 60; p.count_rep = 1;
     return p;
 }
 
@@ -502,11 +505,13 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     const float* Wt = params_.p + l.p_off;
                     if (l.exact) {
                         LAUNCH(k_dense_wgrad_exact, grid_for(l.g_len), 256, s, x, d, dth, l.rows, l.c_in, l.c_out, l.d.has_bias);
+                        if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, s, comm_dev_, dth, l.g_len);
                         LAUNCH(k_dense_dgrad_exact, grid_for(l.in_len), 256, s, d, Wt, dx, l.rows, l.c_in, l.c_out);
                     } else {
                         GemmArgs w{}; w.a = d; w.b = x; w.c = dth; w.M = l.c_out; w.N = l.c_in; w.K = (int)l.rows; w.splits = 1;
                         launch_gemm<G_DENSE_WGRAD>(s, w, launches_, exact_);
                         if (l.d.has_bias) LAUNCH(k_colsum, grid_for(l.c_out), 256, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
+                        if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, s, comm_dev_, dth, l.g_len);
                         GemmArgs q{}; q.a = d; q.c = dx; q.w = Wt; q.M = (int)l.rows; q.N = l.c_in; q.K = l.c_out; q.splits = 1;
                         launch_gemm<G_DENSE_DGRAD>(s, q, launches_, exact_);
                     }
@@ -520,6 +525,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, side_>>>(x, d, geom_, wpart_.p, ipc);
                     ++launches_;
                     LAUNCH(k_wgrad_reduce, 144, 256, side_, wpart_.p, dth, wg_ctas);
+                    if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, side_, comm_dev_, dth, l.g_len);
                     forked = true;
                     side_busy_ = true;
                     if (!gimg_ready) LAUNCH(k_compact_to_image, grid_for(l.out_len / 4), 256, s, d, geom_, l.gimg);
@@ -530,6 +536,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     if (exact_) w.c = dth;
                     launch_gemm<G_CONV_WGRAD>(s, w, launches_, exact_);
                     if (!exact_) LAUNCH(k_splitk_reduce, grid_for(l.g_len), 256, s, wpart_.p, dth, l.g_len, 16);
+                    if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, s, comm_dev_, dth, l.g_len);
                     GemmArgs q{}; q.a = d; q.c = dx; q.w = l.wb; q.M = (int)l.rows; q.N = l.c_in; q.K = 9 * l.c_out;
                     q.H = l.H; q.W = l.W; q.Ci = l.c_in; q.Co = l.c_out; q.splits = 1;
                     launch_gemm<G_CONV_DGRAD>(s, q, launches_, exact_);
@@ -617,8 +624,10 @@ SolveGraph& Engine::get_graph(bool aug, int tslot, bool dense_out, int nt) {
     if (it != graphs_.end()) return it->second;
     SolveGraph sg;
     const long long n4 = (aug ? n_alloc_ : nz_pad_) / 4;
-    const long long n_norm = aug ? (2 * nz_ + n_params_ + (tslot ? 1 : 0)) : nz_;
-    const SolverParams sp = solver_params(n_norm);
+    const long long n_norm = aug ? (2 * nz_ * world_ + n_params_ + (tslot ? 1 : 0)) : nz_ * world_;
+    SolverParams sp = solver_params(n_norm);
+    sp.rep_begin4 = aug ? (2 * nz_pad_) / 4 : n4;
+    sp.count_rep = (rank_id_ == 0) ? 1 : 0;
     const int saved = launches_;
 
     N4J_CUDA(cudaGraphCreate(&sg.graph, 0));
@@ -675,8 +684,10 @@ void Engine::run_solve(bool aug, int tslot, bool dense_out, int nt) {
     }
     // debug path: the host drives the loop and reads `done` after every trial
     const long long n4 = (aug ? n_alloc_ : nz_pad_) / 4;
-    const long long n_norm = aug ? (2 * nz_ + n_params_ + (tslot ? 1 : 0)) : nz_;
-    const SolverParams sp = solver_params(n_norm);
+    const long long n_norm = aug ? (2 * nz_ * world_ + n_params_ + (tslot ? 1 : 0)) : nz_ * world_;
+    SolverParams sp = solver_params(n_norm);
+    sp.rep_begin4 = aug ? (2 * nz_pad_) / 4 : n4;
+    sp.count_rep = (rank_id_ == 0) ? 1 : 0;
     enqueue_prologue(stream_, aug, n4, sp, dense_out, nt);
     for (;;) {
         N4J_CUDA(cudaMemcpyAsync(ctrl_host_, ctrl_, sizeof(Ctrl), cudaMemcpyDeviceToHost, stream_));
@@ -730,6 +741,64 @@ void Engine::finish_call(n4j_stats* st, int) {
     }
     if (c.status == N4J_ERR_ILLEGAL_STATE) throw Error{N4J_ERR_ILLEGAL_STATE, "Detected NaN!"};   // NanWatchSolver.java:22
     if (c.status == N4J_ERR_MAX_STEPS) throw Error{N4J_ERR_MAX_STEPS, "step guard tripped: " + std::to_string(cfg_.max_trials) + " trial steps in one solve"};
+}
+
+// =====================================================================================================
+// multi-GPU setup: exchange buffers in peer-mapped memory (CUDA IPC, one process per GPU)
+// =====================================================================================================
+int Engine::comm_grid(long long n) const { return (int)std::max<long long>(1, std::min<long long>(64, (n + 1023) / 1024)); }
+
+void Engine::comm_export(void* handle64) {
+    N4J_CUDA(cudaSetDevice(device_));
+    if (!comm_region_) {
+        long long xcap = 4;
+        for (auto& l : L_) xcap = std::max(xcap, round_up4(l.g_len));
+        comm_xcap_ = xcap;
+        comm_bytes_ = (size_t)COMM_OFF_XBUF + sizeof(float) * 2 * (size_t)xcap;
+        N4J_CUDA(cudaMalloc(&comm_region_, comm_bytes_));
+        N4J_CUDA(cudaMemset(comm_region_, 0, comm_bytes_));
+    }
+    cudaIpcMemHandle_t hnd;
+    N4J_CUDA(cudaIpcGetMemHandle(&hnd, comm_region_));
+    static_assert(sizeof(hnd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(handle64, &hnd, 64);
+}
+
+void Engine::comm_init(int rank, int world, const void* handles, long long global_batch) {
+    N4J_CUDA(cudaSetDevice(device_));
+    if (world < 1 || world > COMM_MAX_WORLD || rank < 0 || rank >= world) throw Error{N4J_ERR_INVALID_ARGUMENT, "bad rank/world (1..8 ranks)"};
+    if (global_batch != B_ * world) throw Error{N4J_ERR_INVALID_ARGUMENT, "global batch must be world x the local batch (equal row shards)"};
+    if (!comm_region_) throw Error{N4J_ERR_ILLEGAL_STATE, "node4j_comm_export must be called first"};
+    for (auto& l : L_)
+        if (l.d.kind == N4J_LAYER_BATCHNORM && (l.c_out > 128 || l.c_out % 4 != 0 || 256 % (l.c_out / 4) != 0))
+            throw Error{N4J_ERR_UNSUPPORTED, "sharded BatchNorm needs a channel count that is a multiple of 4, divides 1024 and is <= 128"};
+    CommDev cd;
+    std::memset(&cd, 0, sizeof(cd));
+    cd.rank = rank; cd.world = world; cd.xcap = comm_xcap_;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { cd.peer[r] = (char*)comm_region_; continue; }
+        cudaIpcMemHandle_t hnd;
+        std::memcpy(&hnd, (const char*)handles + 64 * r, 64);
+        void* p = nullptr;
+        N4J_CUDA(cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess));
+        cd.peer[r] = (char*)p;
+        peer_ptrs_.push_back(p);
+    }
+    if (!comm_dev_) N4J_CUDA(cudaMalloc(&comm_dev_, sizeof(CommDev)));
+    N4J_CUDA(cudaMemcpy(comm_dev_, &cd, sizeof(CommDev), cudaMemcpyHostToDevice));
+    world_ = world; rank_id_ = rank;
+    if (world > 1) {
+        N4J_CUDA(cudaMemcpy(&ctrl_->comm, &comm_dev_, sizeof(CommDev*), cudaMemcpyHostToDevice));
+        for (auto& l : L_) { l.bn.cm = comm_dev_; l.bn.rows_total = l.rows * world; }
+    } else {
+        cudaFree(comm_dev_); comm_dev_ = nullptr;
+    }
+    // kernel arguments are baked into the captured graphs
+    for (auto& kv : graphs_) {
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+    }
+    graphs_.clear();
 }
 
 // =====================================================================================================
@@ -789,6 +858,13 @@ void Engine::forward(const float* y0, const float* t, int nt, int interpolate, f
 // backward: SingleStepAdjoint.solve / MultiStepAdjoint.solve with the timegrad.* variants
 // =====================================================================================================
 __global__ void k_tg_step(Ctrl* c, double* dot_acc, float* tg, float* Ybase, long long stride, long long off_t, float* dLdt, int step, int phase) {
+    if (phase == 0 && c->comm) {     // multi-GPU: the dot product runs over all ranks' rows
+        __shared__ double v[1];
+        if (threadIdx.x == 0) v[0] = *dot_acc;
+        __syncthreads();
+        comm_allreduce_block(c->comm, v, 1);
+        if (threadIdx.x == 0) *dot_acc = v[0];
+    }
     if (threadIdx.x != 0) return;
     float* y = Ybase + (long long)c->y_cur * stride;
     if (phase == 0) {            // CalcTimeGrad.calcTimeAdjointT1 :52-58: lastTime -= <dL/dz(t1), f(z(t1))>; a_t := lastTime
@@ -1162,13 +1238,11 @@ int32_t node4j_rhs_vjp(n4j_handle* h, const float* z, float t, const float* g, f
 int32_t node4j_error_norm(n4j_handle* h, const float* K, const float* y0, const float* y1, float step, int64_t n, float* err_out) {
     return guarded([&] { h->eng->error_norm(K, y0, y1, step, n, err_out); });
 }
-int32_t node4j_comm_init(n4j_handle*, int32_t, int32_t, const void*, int64_t) {
-    g_last_error = "multi-GPU sharding is not wired up in this build";
-    return N4J_ERR_UNSUPPORTED;
+int32_t node4j_comm_export(n4j_handle* h, void* handle64) {
+    return guarded([&] { h->eng->comm_export(handle64); });
 }
-int32_t node4j_comm_unique_id(void*) {
-    g_last_error = "multi-GPU sharding is not wired up in this build";
-    return N4J_ERR_UNSUPPORTED;
+int32_t node4j_comm_init(n4j_handle* h, int32_t rank, int32_t world, const void* all_handles, int64_t global_batch) {
+    return guarded([&] { h->eng->comm_init(rank, world, all_handles, global_batch); });
 }
 int32_t node4j_bench_solver_pass(n4j_handle* h, int64_t n, int32_t iters, float* us_per_pass) {
     return guarded([&] { h->eng->bench_solver_pass(n, iters, us_per_pass); });

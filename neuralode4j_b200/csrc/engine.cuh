@@ -68,6 +68,8 @@ public:
     void error_norm(const float* K, const float* y0, const float* y1, float step, long long n, float* err_out);
     void bench_solver_pass(long long n, int iters, float* us);
     void bench_piece(int what, int iters, float* us);
+    void comm_export(void* handle64);
+    void comm_init(int rank, int world, const void* handles, long long global_batch);
     cudaStream_t stream() const { return stream_; }
 
 private:
@@ -104,7 +106,15 @@ private:
     float* Y_ = nullptr;       // [2][n_alloc]
     float* K_ = nullptr;       // [7][n_alloc]
     Ctrl* ctrl_ = nullptr;
-    double* red_acc_ = nullptr;   // strided accumulators of the scalar reductions (error norm, initial step)
+    double* red_acc_ = nullptr;
+    // multi-GPU (row-sharded minibatch)
+    int world_ = 1, rank_id_ = 0;
+    void* comm_region_ = nullptr;
+    size_t comm_bytes_ = 0;
+    long long comm_xcap_ = 0;
+    CommDev* comm_dev_ = nullptr;
+    std::vector<void*> peer_ptrs_;
+    int comm_grid(long long n) const;   // strided accumulators of the scalar reductions (error norm, initial step)
     Ctrl* ctrl_host_ = nullptr;   // pinned
     n4j_step_rec* log_ = nullptr;
     int log_cap_ = 1 << 16;

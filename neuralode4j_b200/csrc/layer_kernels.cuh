@@ -135,7 +135,19 @@ struct BnScratch {
     float* invstd;          // [C]
     float* m_dy;            // [C]  backward: mean(dy)
     float* m_dyxh;          // [C]  backward: mean(dy*xhat)
+    CommDev* cm;            // multi-GPU: statistics are summed over all ranks' rows (nullptr on a single GPU)
+    long long rows_total;   // rows over all ranks
 };
+
+// Last block, all threads: gather the 2*C strided accumulators into tot[] (shared), re-arm them, and (multi-GPU) sum over the ranks.
+__device__ __forceinline__ void bn_collect(const BnScratch& sc, int C, double* tot) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        tot[i] = *((volatile double*)(sc.acc + i * ACC_STRIDE));
+        sc.acc[i * ACC_STRIDE] = 0.0;
+    }
+    __syncthreads();
+    if (sc.cm) comm_allreduce_block(sc.cm, tot, 2 * C);
+}
 
 __global__ void __launch_bounds__(256) k_bn_stats(Ref xin, long long M, int C, float eps, BnScratch sc) {
     const float* __restrict__ x = resolve(xin);
@@ -175,14 +187,15 @@ __global__ void __launch_bounds__(256) k_bn_stats(Ref xin, long long M, int C, f
     __syncthreads();
     if (s_last) {
         __threadfence();
+        double* tot = &sm[0][0][0];                 // 2048 doubles, free again
+        bn_collect(sc, C, tot);
+        const double Mt = sc.cm ? (double)sc.rows_total : (double)M;
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const double sum = *((volatile double*)(sc.acc + c * ACC_STRIDE)), sq = *((volatile double*)(sc.acc + (C + c) * ACC_STRIDE));
-            const double mean = sum / (double)M;
-            double var = sq / (double)M - mean * mean;
+            const double mean = tot[c] / Mt;
+            double var = tot[C + c] / Mt - mean * mean;
             if (var < 0) var = 0;
             sc.mean[c] = (float)mean;
             sc.invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
-            sc.acc[c * ACC_STRIDE] = 0.0; sc.acc[(C + c) * ACC_STRIDE] = 0.0;
         }
         if (threadIdx.x == 0) *sc.ticket = 0u;
     }
@@ -271,13 +284,15 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats(Ref gin, float gscale, Ref
         __threadfence();
         float* __restrict__ dgamma = resolve(dgamma_ref);
         float* __restrict__ dbeta = resolve(dbeta_ref);
+        __shared__ double tot[512];
+        bn_collect(sc, C, tot);
+        const double Mt = sc.cm ? (double)sc.rows_total : (double)M;
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const double sdy = *((volatile double*)(sc.acc + c * ACC_STRIDE)), sdyxh = *((volatile double*)(sc.acc + (C + c) * ACC_STRIDE));
+            const double sdy = tot[c], sdyxh = tot[C + c];
             dgamma[c] = (float)sdyxh;
             dbeta[c] = (float)sdy;
-            sc.m_dy[c] = (float)(sdy / (double)M);
-            sc.m_dyxh[c] = (float)(sdyxh / (double)M);
-            sc.acc[c * ACC_STRIDE] = 0.0; sc.acc[(C + c) * ACC_STRIDE] = 0.0;
+            sc.m_dy[c] = (float)(sdy / Mt);
+            sc.m_dyxh[c] = (float)(sdyxh / Mt);
         }
         if (threadIdx.x == 0) *sc.ticket = 0u;
     }
@@ -344,14 +359,16 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats64(Ref gin, float gscale, R
         __threadfence();
         float* __restrict__ dgamma = resolve(dgamma_ref);
         float* __restrict__ dbeta = resolve(dbeta_ref);
+        double* tot = &sm[0][0][0];
+        bn_collect(sc, 64, tot);
+        const double Mt = sc.cm ? (double)sc.rows_total : (double)M;
         if (threadIdx.x < 64) {
             const int c = threadIdx.x;
-            const double sdy = *((volatile double*)(sc.acc + c * ACC_STRIDE)), sdyxh = *((volatile double*)(sc.acc + (64 + c) * ACC_STRIDE));
+            const double sdy = tot[c], sdyxh = tot[64 + c];
             dgamma[c] = (float)sdyxh;
             dbeta[c] = (float)sdy;
-            sc.m_dy[c] = (float)(sdy / (double)M);
-            sc.m_dyxh[c] = (float)(sdyxh / (double)M);
-            sc.acc[c * ACC_STRIDE] = 0.0; sc.acc[(64 + c) * ACC_STRIDE] = 0.0;
+            sc.m_dy[c] = (float)(sdy / Mt);
+            sc.m_dyxh[c] = (float)(sdyxh / Mt);
         }
         if (threadIdx.x == 0) *sc.ticket = 0u;
     }

@@ -114,15 +114,16 @@ __global__ void __launch_bounds__(256) k_stage_combine(const Ctrl* __restrict__ 
         __syncthreads();
         if (s_last) {
             __threadfence();
+            double* tot = &sm[0][0][0];
+            bn_collect(bf.sc, 64, tot);
+            const double Mt = bf.sc.cm ? (double)bf.sc.rows_total : (double)bf.rows;
             if (threadIdx.x < 64) {
                 const int ch = threadIdx.x;
-                const double sum = *((volatile double*)(bf.sc.acc + ch * ACC_STRIDE)), sq = *((volatile double*)(bf.sc.acc + (64 + ch) * ACC_STRIDE));
-                const double mean = sum / (double)bf.rows;
-                double var = sq / (double)bf.rows - mean * mean;
+                const double mean = tot[ch] / Mt;
+                double var = tot[64 + ch] / Mt - mean * mean;
                 if (var < 0) var = 0;
                 bf.sc.mean[ch] = (float)mean;
                 bf.sc.invstd[ch] = (float)(1.0 / sqrt(var + (double)bf.eps));
-                bf.sc.acc[ch * ACC_STRIDE] = 0.0; bf.sc.acc[(64 + ch) * ACC_STRIDE] = 0.0;
             }
             if (threadIdx.x == 0) *bf.sc.ticket = 0u;
         }
@@ -234,7 +235,8 @@ __global__ void __launch_bounds__(256) k_error_ctrl(Ctrl* c, const float* __rest
     const float e0 = c_E[0], e2 = c_E[2], e3 = c_E[3], e4 = c_E[4], e5 = c_E[5], e6 = c_E[6];
     double s[1] = {0.0};
     const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+    const long long n4_eff = p.count_rep ? n4 : min(n4, p.rep_begin4);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_eff; i += step) {
         const float4 a0 = ld4(k0, i), a2 = ld4(k2, i), a3 = ld4(k3, i), a4 = ld4(k4, i), a5 = ld4(k5, i), a6 = ld4(k6, i);
         const float4 u = ld4(y0, i), v = ld4(y1, i);
 #define N4J_ERR_LANE(f)                                                                     \
@@ -251,7 +253,7 @@ __global__ void __launch_bounds__(256) k_error_ctrl(Ctrl* c, const float* __rest
         N4J_ERR_LANE(x) N4J_ERR_LANE(y) N4J_ERR_LANE(z) N4J_ERR_LANE(w)
 #undef N4J_ERR_LANE
     }
-    if (publish_and_elect<1>(s, c->red_acc, c->ticket)) {
+    if (publish_and_elect<1>(s, c->red_acc, c->ticket, c->comm)) {
         if (threadIdx.x == 0) {
             const double sum = s[0];
             controller_after_error(c, sum, p, log, dout);
@@ -303,7 +305,8 @@ __global__ void __launch_bounds__(256) k_init_sums(Ctrl* c, const float* __restr
     const float* __restrict__ k0 = Kbase + (long long)c->krow[0] * stride;
     double s[2] = {0.0, 0.0};
     const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+    const long long n4_eff = p.count_rep ? n4 : min(n4, p.rep_begin4);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_eff; i += step) {
         const float4 u = ld4(y, i), d = ld4(k0, i);
 #define N4J_LANE(f)                                                               \
         {                                                                         \
@@ -315,7 +318,7 @@ __global__ void __launch_bounds__(256) k_init_sums(Ctrl* c, const float* __restr
         N4J_LANE(x) N4J_LANE(y) N4J_LANE(z) N4J_LANE(w)
 #undef N4J_LANE
     }
-    if (publish_and_elect<2>(s, c->red_acc, c->ticket)) {
+    if (publish_and_elect<2>(s, c->red_acc, c->ticket, c->comm)) {
         if (threadIdx.x == 0) {
             const float Yr = (float)s[0];
             const float Dr = (float)s[1];
@@ -335,7 +338,8 @@ __global__ void __launch_bounds__(256) k_init_final(Ctrl* c, const float* __rest
     const float* __restrict__ k1 = Kbase + (long long)c->krow[1] * stride;
     double s[1] = {0.0};
     const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+    const long long n4_eff = p.count_rep ? n4 : min(n4, p.rep_begin4);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_eff; i += step) {
         const float4 u = ld4(y, i), a = ld4(k0, i), b = ld4(k1, i);
 #define N4J_LANE(f)                                                               \
         {                                                                         \
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(256) k_init_final(Ctrl* c, const float* __rest
         N4J_LANE(x) N4J_LANE(y) N4J_LANE(z) N4J_LANE(w)
 #undef N4J_LANE
     }
-    if (publish_and_elect<1>(s, c->red_acc, c->ticket)) {
+    if (publish_and_elect<1>(s, c->red_acc, c->ticket, c->comm)) {
         if (threadIdx.x == 0) {
             const float DDs = (float)s[0];
             float h = c->h;
@@ -478,6 +482,55 @@ __global__ void __launch_bounds__(256) k_dot(const float* __restrict__ a, const 
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) s[0] += (double)a[i] * (double)b[i];
     block_sum<1>(s);
     if (threadIdx.x == 0) atomicAdd(acc, s[0]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-GPU: all-reduce (sum) of a parameter-gradient slot over the ranks — the "parameter-gradient allreduce" of the
+// adjoint solve, done per RHS evaluation so that the theta block of the state (and its error-norm term) stays global.
+// One-shot over NVLink peer memory: copy to the local exchange buffer, signal every peer, wait for all, sum the peers'
+// buffers in rank order.  Grid <= 64 blocks so every block is resident while it waits.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_comm_allreduce_vec(CommDev* cm, Ref bufref, long long n) {
+    float* __restrict__ buf = resolve(bufref);
+    __shared__ int s_last;
+    const unsigned long long seq = cm->seq_x + 1;
+    const int par = (int)(seq & 1), me = cm->rank, W = cm->world;
+    float* xb = reinterpret_cast<float*>(cm->peer[me] + COMM_OFF_XBUF) + (long long)par * cm->xcap;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) xb[i] = buf[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int tk = atomicAdd(&cm->xticket, 1u);
+        s_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < W) {
+            volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(cm->peer[threadIdx.x] + COMM_OFF_XFLAGS) + par * COMM_MAX_WORLD + me;
+            *f = seq;
+            __threadfence_system();
+        }
+    }
+    if (threadIdx.x < W) {
+        volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(cm->peer[me] + COMM_OFF_XFLAGS) + par * COMM_MAX_WORLD + threadIdx.x;
+        comm_wait_flag(mine, seq, cm);
+    }
+    __syncthreads();
+    __threadfence_system();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        float t = 0.f;
+        for (int q = 0; q < W; ++q)
+            t += *reinterpret_cast<volatile float*>(reinterpret_cast<float*>(cm->peer[q] + COMM_OFF_XBUF) + (long long)par * cm->xcap + i);
+        buf[i] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int tk = atomicAdd(&cm->pad2_, 1u);      // second ticket: the last block to LEAVE bumps the sequence number
+        if (tk == gridDim.x - 1) { cm->xticket = 0u; cm->pad2_ = 0u; __threadfence(); cm->seq_x = seq; }
+    }
 }
 
 }  // namespace n4j

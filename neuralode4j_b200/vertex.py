@@ -325,6 +325,22 @@ class OdeVertexImpl:
         epsilons[(helper.time_input_index + 1) % 2] = dy0
         return self._grad, epsilons
 
+    # ---- multi-GPU ---------------------------------------------------------------------------------------------
+    def init_comm(self, group=None):
+        """Row-sharded minibatch over the ranks of a torch.distributed process group (one process per GPU, one box).
+        torch.distributed is only the host-side plumbing that carries the 64-byte IPC handles; the data path exchanges
+        run inside the engine's kernels over NVLink peer memory."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        mine = C.create_string_buffer(64)
+        _lib.check(self._L.node4j_comm_export(self._h, mine))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine.raw, group=group)
+        allh = C.create_string_buffer(b"".join(gathered), 64 * world)
+        _lib.check(self._L.node4j_comm_init(self._h, rank, world, allh, self.shape[0] * world))
+        dist.barrier(group)
+        return rank, world
+
     # ---- extras ------------------------------------------------------------------------------------------------
     def step_log(self):
         n = int(self._L.node4j_get_step_log(self._h, None, 0))
