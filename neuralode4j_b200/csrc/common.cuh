@@ -93,8 +93,8 @@ constexpr int COMM_MAX_WORLD = 8;
 constexpr int COMM_SLOT = 256;                                   // doubles per rank per small exchange
 constexpr long long COMM_OFF_FLAGS = 0;                          // uint64 flag[2][8]
 constexpr long long COMM_OFF_XFLAGS = 256;                       // uint64 xflag[2][8]
-constexpr long long COMM_OFF_MBOX = 512;                         // double mbox[2][8][COMM_SLOT]
-constexpr long long COMM_OFF_XBUF = COMM_OFF_MBOX + 2LL * COMM_MAX_WORLD * COMM_SLOT * 8;   // float xbuf[2][xcap]
+constexpr long long COMM_OFF_MBOX = 512;                         // uint64 cell[2][8][COMM_SLOT][2]  (tag<<32 | half of the double)
+constexpr long long COMM_OFF_XBUF = COMM_OFF_MBOX + 2LL * COMM_MAX_WORLD * COMM_SLOT * 16;  // float xbuf[2][xcap]
 
 struct CommDev {
     int rank, world;
@@ -117,36 +117,51 @@ __device__ __forceinline__ bool comm_wait_flag(volatile unsigned long long* f, u
     return false;
 }
 
-// All threads of ONE block (blockDim >= world); vals[n] (shared memory, n <= COMM_SLOT) in -> global totals out.
-__device__ __forceinline__ void comm_allreduce_block(CommDev* cm, double* vals, int n) {
+// Small all-reduce, LL style: every 8-byte cell carries 4 bytes of payload and the 4-byte sequence tag, so a value is
+// complete exactly when its two cells show the current tag — no flags, no system fences on the critical path (one NVLink
+// store latency per exchange).  Called by `nthr` threads (tid 0..nthr-1) that can synchronise through `sync()`;
+// vals[n] (shared memory, n <= COMM_SLOT) in -> global totals out (summed in rank order, identical on every rank).
+template <class SyncFn>
+__device__ __forceinline__ void comm_allreduce_small(CommDev* cm, double* vals, int n, int tid, int nthr, SyncFn sync) {
     __shared__ unsigned long long s_seq;
-    if (threadIdx.x == 0) { s_seq = cm->seq_small + 1; cm->seq_small = s_seq; }
-    __syncthreads();
+    if (tid == 0) { s_seq = cm->seq_small + 1; cm->seq_small = s_seq; }
+    sync();
     const unsigned long long seq = s_seq;
+    const unsigned int tag = (unsigned int)seq;
     const int par = (int)(seq & 1), me = cm->rank, W = cm->world;
-    for (int idx = threadIdx.x; idx < W * n; idx += blockDim.x) {
+    // push: cell[(par, me, 2*i + half)] on every rank (including the local one)
+    for (int idx = tid; idx < W * n; idx += nthr) {
         const int pr = idx / n, i = idx - pr * n;
-        double* dst = reinterpret_cast<double*>(cm->peer[pr] + COMM_OFF_MBOX) + ((par * COMM_MAX_WORLD + me) * COMM_SLOT + i);
-        *reinterpret_cast<volatile double*>(dst) = vals[i];
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[i]);
+        volatile unsigned long long* cell = reinterpret_cast<unsigned long long*>(cm->peer[pr] + COMM_OFF_MBOX) +
+                                            ((long long)(par * COMM_MAX_WORLD + me) * COMM_SLOT + i) * 2;
+        cell[0] = ((unsigned long long)tag << 32) | (bits & 0xFFFFFFFFull);
+        cell[1] = ((unsigned long long)tag << 32) | (bits >> 32);
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < W) {
-        volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(cm->peer[threadIdx.x] + COMM_OFF_FLAGS) + par * COMM_MAX_WORLD + me;
-        *f = seq;
-        __threadfence_system();
-        volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(cm->peer[me] + COMM_OFF_FLAGS) + par * COMM_MAX_WORLD + threadIdx.x;
-        comm_wait_flag(mine, seq, cm);
-    }
-    __syncthreads();
-    __threadfence_system();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    sync();
+    // pull: wait for the tag on every contribution, sum in rank order
+    for (int i = tid; i < n; i += nthr) {
         double t = 0.0;
-        for (int q = 0; q < W; ++q)
-            t += *reinterpret_cast<volatile double*>(reinterpret_cast<double*>(cm->peer[me] + COMM_OFF_MBOX) + ((par * COMM_MAX_WORLD + q) * COMM_SLOT + i));
+        for (int q = 0; q < W; ++q) {
+            volatile unsigned long long* cell = reinterpret_cast<unsigned long long*>(cm->peer[me] + COMM_OFF_MBOX) +
+                                                ((long long)(par * COMM_MAX_WORLD + q) * COMM_SLOT + i) * 2;
+            unsigned long long c0 = 0, c1 = 0;
+            bool ok = false;
+            for (unsigned int spin = 0; spin < (1u << 28); ++spin) {
+                c0 = cell[0]; c1 = cell[1];
+                if ((unsigned int)(c0 >> 32) == tag && (unsigned int)(c1 >> 32) == tag) { ok = true; break; }
+                if ((spin & 255) == 255) __nanosleep(32);
+            }
+            if (!ok) cm->status = 1;
+            t += __longlong_as_double((long long)((c0 & 0xFFFFFFFFull) | (c1 << 32)));
+        }
         vals[i] = t;
     }
-    __syncthreads();
+    sync();
+}
+struct BlockSyncFn { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+__device__ __forceinline__ void comm_allreduce_block(CommDev* cm, double* vals, int n) {
+    comm_allreduce_small(cm, vals, n, (int)threadIdx.x, (int)blockDim.x, BlockSyncFn{});
 }
 
 // ---------------------------------------------------------------------------------------------------

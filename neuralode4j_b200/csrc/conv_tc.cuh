@@ -71,36 +71,10 @@ __global__ void __launch_bounds__(256) k_conv_w_to_tc(const float* __restrict__ 
     }
 }
 
-// comm_allreduce_block for the four epilogue warps of the conv kernel (named barrier 1 instead of __syncthreads)
+// small all-reduce by the four epilogue warps of the conv kernel (named barrier 1 instead of __syncthreads)
+struct EpilogueSyncFn { __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 1, 128;" ::: "memory"); } };
 __device__ __forceinline__ void comm_allreduce_epilogue(CommDev* cm, double* vals, int n, int et) {
-    __shared__ unsigned long long s_seq;
-    if (et == 0) { s_seq = cm->seq_small + 1; cm->seq_small = s_seq; }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    const unsigned long long seq = s_seq;
-    const int par = (int)(seq & 1), me = cm->rank, W = cm->world;
-    for (int idx = et; idx < W * n; idx += 128) {
-        const int pr = idx / n, i = idx - pr * n;
-        double* dst = reinterpret_cast<double*>(cm->peer[pr] + COMM_OFF_MBOX) + ((par * COMM_MAX_WORLD + me) * COMM_SLOT + i);
-        *reinterpret_cast<volatile double*>(dst) = vals[i];
-    }
-    __threadfence_system();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    if (et < W) {
-        volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(cm->peer[et] + COMM_OFF_FLAGS) + par * COMM_MAX_WORLD + me;
-        *f = seq;
-        __threadfence_system();
-        volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(cm->peer[me] + COMM_OFF_FLAGS) + par * COMM_MAX_WORLD + et;
-        comm_wait_flag(mine, seq, cm);
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    __threadfence_system();
-    for (int i = et; i < n; i += 128) {
-        double t = 0.0;
-        for (int q = 0; q < W; ++q)
-            t += *reinterpret_cast<volatile double*>(reinterpret_cast<double*>(cm->peer[me] + COMM_OFF_MBOX) + ((par * COMM_MAX_WORLD + q) * COMM_SLOT + i));
-        vals[i] = t;
-    }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    comm_allreduce_small(cm, vals, n, et, 128, EpilogueSyncFn{});
 }
 
 struct ConvTcArgs {
