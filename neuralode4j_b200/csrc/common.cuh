@@ -13,6 +13,17 @@ namespace n4j {
 struct CommDev;
 
 // ---------------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel of the engine is launched with programmaticStreamSerialization and starts
+// with pdl_begin(): it lets ITS dependents be scheduled right away (their blocks become resident and park in
+// griddepcontrol.wait) and then waits until everything it depends on has completed and flushed.  Dependencies stay exactly
+// those of plain stream order; what is gained is the launch latency between the ~1000 small dependent kernels of a step.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_begin() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Device-resident control block of one solve.  The step controller lives on the GPU: kernels read the
 // current step size / buffer rotation from here and the last block of the error-norm kernel updates it,
 // so a whole adaptive solve runs without a host round trip (replaces the host reads at

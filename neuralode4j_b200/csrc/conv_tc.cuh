@@ -57,6 +57,7 @@ inline size_t conv_tc_smem_bytes(const ConvGeom& g) {
 //   forward (mode 0): n = co, k = ci, tap as is              B_tap[ci,co] = W[co,ci,tap]
 //   dgrad   (mode 1): n = ci, k = co, tap flipped (8 - tap)  B_tap'[co,ci] = W[co,ci,8-tap']
 __global__ void __launch_bounds__(256) k_conv_w_to_tc(const float* __restrict__ w, float* __restrict__ wimg, int mode) {
+    pdl_begin();
     const int n_el = 64 * 64 * 9;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += gridDim.x * blockDim.x) {
         const int tap = i % 9; const int r = i / 9; const int ci = r % 64; const int co = r / 64;
@@ -93,6 +94,7 @@ struct ConvTcArgs {
 
 template <int PASSES, bool FUSE>
 __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // dependents may be scheduled; they park in their own wait
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const ConvGeom& g = a.g;
     const int rt = 128 + 2 * g.halo;                     // staged rows per chunk
@@ -121,6 +123,8 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // barrier init and the TMEM allocation above overlap the tail of the producing kernel; global memory is touched from here on
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         if (lane == 0) {
@@ -272,6 +276,7 @@ __device__ __forceinline__ void store_split4(float* __restrict__ img, const Conv
 // y = act(gamma*((x-mean)*invstd)+beta) -> operand image (and optionally the compact activation as well)
 __global__ void __launch_bounds__(256) k_bn_apply_to_image(Ref xin, const float* __restrict__ gamma, const float* __restrict__ beta, BnScratch sc,
                                                             int act, ConvGeom g, float* __restrict__ img, float* __restrict__ compact) {
+    pdl_begin();
     const float* __restrict__ x = resolve(xin);
     const long long n4 = (long long)g.B * g.H * g.W * 16;     // float4 groups: [crow][chunk]
     const long long step = (long long)gridDim.x * blockDim.x;
@@ -292,6 +297,7 @@ __global__ void __launch_bounds__(256) k_bn_apply_to_image(Ref xin, const float*
 
 // compact NHWC [rows][64] -> operand image (used for gradients that feed dgrad/wgrad and by the unit probe)
 __global__ void __launch_bounds__(256) k_compact_to_image(Ref xin, ConvGeom g, float* __restrict__ img) {
+    pdl_begin();
     const float* __restrict__ x = resolve(xin);
     const long long n4 = (long long)g.B * g.H * g.W * 16;
     const long long step = (long long)gridDim.x * blockDim.x;
@@ -312,6 +318,7 @@ __global__ void __launch_bounds__(256) k_compact_to_image(Ref xin, ConvGeom g, f
 // branch of the graph, concurrently with the dgrad/BatchNorm chain.
 // ---------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1) k_conv_wgrad64(Ref xin, Ref gin, ConvGeom g, float* __restrict__ part, int images_per_cta) {
+    pdl_begin();
     extern __shared__ __align__(16) float smw[];
     const int hw = g.H * g.W, pp = g.PH * g.PW;
     float* Xs = smw;                 // [PH*PW][64], zero border
@@ -364,6 +371,7 @@ inline size_t conv_wgrad_smem_bytes(const ConvGeom& g) { return sizeof(float) * 
 
 // dst[i] = sum_b part[b][i]  (fixed order), i over 9*64*64.  Block = 64 float4 columns x 4 partial groups.
 __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ part, Ref dstref, int nparts) {
+    pdl_begin();
     float* __restrict__ dst = resolve(dstref);
     const int n4 = 9 * 4096 / 4;
     const int col = blockIdx.x * 64 + (threadIdx.x & 63), grp = threadIdx.x >> 6;
@@ -391,6 +399,7 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
 // BatchNorm backward dx written as the compact gradient AND as the operand image of the following dgrad convolution
 __global__ void __launch_bounds__(256) k_bn_bwd_dx_to_image(Ref gin, float gscale, Ref yref, Ref xin, const float* __restrict__ gamma, BnScratch sc,
                                                              int act, ConvGeom g, float* __restrict__ dx_compact, float* __restrict__ img) {
+    pdl_begin();
     const float* __restrict__ gg = resolve(gin);
     const float* __restrict__ y = resolve(yref);
     const float* __restrict__ x = resolve(xin);

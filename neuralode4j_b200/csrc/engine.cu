@@ -15,10 +15,25 @@
 
 namespace n4j {
 
-#define LAUNCH(kernel, grid, block, stream, ...)                      \
-    do {                                                              \
-        kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__);        \
-        ++launches_;                                                  \
+static thread_local bool t_pdl = true;   // engine-wide switch (N4J_FLAG_NO_PDL), refreshed at the start of every API call
+
+// Every kernel goes out through cudaLaunchKernelEx with programmatic stream serialization (see pdl_begin in common.cuh).
+template <typename... KArgs, typename... Args>
+static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl && t_pdl) ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+    if (e != cudaSuccess) throw Error{N4J_ERR_CUDA, std::string("kernel launch failed: ") + cudaGetErrorString(e)};
+}
+
+#define LAUNCH(kernel, grid, block, stream, ...)                                              \
+    do {                                                                                      \
+        launch_k(kernel, dim3(grid), dim3(block), 0, (stream), pdl_, __VA_ARGS__);            \
+        ++launches_;                                                                          \
     } while (0)
 
 static inline long long round_up4(long long n) { return (n + 3) & ~3LL; }
@@ -36,6 +51,7 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
     if (cfg_.min_reduction == 0) cfg_.min_reduction = 0.2;
     if (cfg_.max_trials <= 0) cfg_.max_trials = 100000;
     exact_ = (cfg_.flags & N4J_FLAG_EXACT_CONTRACTIONS) != 0;
+    pdl_ = (cfg_.flags & N4J_FLAG_NO_PDL) == 0;
     if (g.rank != 2 && g.rank != 4) throw Error{N4J_ERR_UNSUPPORTED, "Rank not supported: " + std::to_string(g.rank)};
     rank_ = g.rank;
     B_ = g.shape[0];
@@ -341,8 +357,8 @@ template <int MODE>
 static void launch_gemm(cudaStream_t s, GemmArgs g, int& launches, bool exact) {
     if (exact) g.splits = 1;   // double accumulation is only order-independent inside one accumulator chain
     dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.splits);
-    if (exact) k_gemm_tiled<MODE, double><<<grid, 256, 0, s>>>(g);
-    else k_gemm_tiled<MODE, float><<<grid, 256, 0, s>>>(g);
+    if (exact) launch_k(k_gemm_tiled<MODE, double>, grid, dim3(256), 0, s, true, g);
+    else launch_k(k_gemm_tiled<MODE, float>, grid, dim3(256), 0, s, true, g);
     ++launches;
 }
 
@@ -352,12 +368,13 @@ void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg,
     a.fuse_stats = next_bn ? 1 : 0;
     if (next_bn) { a.bn = next_bn->bn; a.bn_eps = next_bn->d.eps; a.bn_rows = next_bn->rows; }
     const bool fast = (cfg_.flags & N4J_FLAG_FAST_TF32) != 0;
+    const dim3 grid(geom_.tiles), block(CONV_TC_THREADS);
     if (next_bn) {
-        if (fast) k_conv3x3_tc<1, true><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
-        else k_conv3x3_tc<3, true><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
+        if (fast) launch_k(k_conv3x3_tc<1, true>, grid, block, conv_smem_, s, pdl_, a);
+        else launch_k(k_conv3x3_tc<3, true>, grid, block, conv_smem_, s, pdl_, a);
     } else {
-        if (fast) k_conv3x3_tc<1, false><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
-        else k_conv3x3_tc<3, false><<<geom_.tiles, CONV_TC_THREADS, conv_smem_, s>>>(a);
+        if (fast) launch_k(k_conv3x3_tc<1, false>, grid, block, conv_smem_, s, pdl_, a);
+        else launch_k(k_conv3x3_tc<3, false>, grid, block, conv_smem_, s, pdl_, a);
     }
     ++launches_;
 }
@@ -577,7 +594,7 @@ void Engine::enqueue_prologue(cudaStream_t s, bool aug, long long n4, const Solv
 
 template <int S>
 static void launch_combine(cudaStream_t s, int grid, Ctrl* c, float* Y, float* K, long long stride, long long i0, long long i1, const BnFuse& bf) {
-    k_stage_combine<S><<<grid, 256, 0, s>>>(c, Y, K, stride, i0, i1, bf);
+    launch_k(k_stage_combine<S>, dim3(grid), dim3(256), 0, s, true, c, Y, K, stride, i0, i1, bf);
 }
 
 void Engine::enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt,
@@ -630,6 +647,11 @@ SolveGraph& Engine::get_graph(bool aug, int tslot, bool dense_out, int nt) {
     sp.count_rep = (rank_id_ == 0) ? 1 : 0;
     const int saved = launches_;
 
+    // Measured on B200: inside the captured graph programmatic edges do not pay (6.97 ms vs 6.67 ms per step) — graph
+    // replay already hides the launch latency and early-resident dependents only take SM slots — so PDL is used for the
+    // eager paths (host-driven loop, RHS probes) and switched off while capturing.
+    const bool saved_pdl = t_pdl;
+    t_pdl = false;
     N4J_CUDA(cudaGraphCreate(&sg.graph, 0));
     // prologue as a child graph
     cudaGraph_t pro = nullptr, epi = nullptr;
@@ -668,6 +690,7 @@ SolveGraph& Engine::get_graph(bool aug, int tslot, bool dense_out, int nt) {
     }
     sg.epilogue_launches = launches_;
     launches_ = saved;
+    t_pdl = saved_pdl;
     N4J_CUDA(cudaGraphInstantiate(&sg.exec, sg.graph, 0));
     if (pro) cudaGraphDestroy(pro);
     if (epi) cudaGraphDestroy(epi);
@@ -699,6 +722,7 @@ void Engine::run_solve(bool aug, int tslot, bool dense_out, int nt) {
 }
 
 __global__ void k_reset_ctrl(Ctrl* c) {
+    pdl_begin();
     if (threadIdx.x == 0) {
         c->y_cur = 0; c->status = 0; c->log_n = 0; c->seg_index = 0;
         c->nfe = 0; c->accepted = 0; c->rejected = 0; c->solves = 0; c->trials = 0;
@@ -708,6 +732,7 @@ __global__ void k_reset_ctrl(Ctrl* c) {
 }
 
 void Engine::reset_ctrl() {
+    t_pdl = pdl_;
     launches_ = 0;
     pending_graph_runs_.clear();
     N4J_CUDA(cudaEventRecord(ev0_, stream_));
@@ -858,6 +883,7 @@ void Engine::forward(const float* y0, const float* t, int nt, int interpolate, f
 // backward: SingleStepAdjoint.solve / MultiStepAdjoint.solve with the timegrad.* variants
 // =====================================================================================================
 __global__ void k_tg_step(Ctrl* c, double* dot_acc, float* tg, float* Ybase, long long stride, long long off_t, float* dLdt, int step, int phase) {
+    pdl_begin();
     if (phase == 0 && c->comm) {     // multi-GPU: the dot product runs over all ranks' rows
         __shared__ double v[1];
         if (threadIdx.x == 0) v[0] = *dot_acc;
@@ -886,6 +912,7 @@ __global__ void k_tg_step(Ctrl* c, double* dot_acc, float* tg, float* Ybase, lon
 // a-slot of the state: a <- g (first segment) or a <- g + a (MultiStepTimeGrad.prepareStep)
 __global__ void __launch_bounds__(256) k_adjoint_seed(const Ctrl* __restrict__ c, float* __restrict__ Ybase, long long stride, long long off,
                                                        const float* __restrict__ g, const float* __restrict__ g2, int add_self, long long n) {
+    pdl_begin();
     float* __restrict__ a = Ybase + (long long)c->y_cur * stride + off;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
@@ -897,6 +924,7 @@ __global__ void __launch_bounds__(256) k_adjoint_seed(const Ctrl* __restrict__ c
 }
 __global__ void __launch_bounds__(256) k_add_out(const Ctrl* __restrict__ c, const float* __restrict__ Ybase, long long stride, long long off,
                                                   const float* __restrict__ add, float* __restrict__ dst, long long n) {
+    pdl_begin();
     const float* __restrict__ a = Ybase + (long long)c->y_cur * stride + off;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) dst[i] = add ? __fadd_rn(a[i], add[i]) : a[i];
@@ -1009,6 +1037,7 @@ long long Engine::get_step_log(n4j_step_rec* buf, long long cap) {
 // =====================================================================================================
 void Engine::rhs(const float* z, float, float* fz) {
     N4J_CUDA(cudaSetDevice(device_));
+    t_pdl = pdl_;
     launches_ = 0;
     upload_params();
     ensure(io_, nz_);
@@ -1067,6 +1096,7 @@ void Engine::error_norm(const float* K, const float* y0, const float* y1, float 
 // state and K rows are zero, so err == 0 and h stays clamped at hmax.
 void Engine::bench_solver_pass(long long n, int iters, float* us) {
     N4J_CUDA(cudaSetDevice(device_));
+    t_pdl = pdl_;
     const long long n4 = round_up4(n) / 4, stride = n4 * 4;
     float *Y = nullptr, *K = nullptr;
     Ctrl* c = nullptr;
@@ -1109,6 +1139,7 @@ void Engine::bench_solver_pass(long long n, int iters, float* us) {
 // Average device time of one launch sequence of a named piece of the hot path on the engine's real buffers.
 void Engine::bench_piece(int what, int iters, float* us) {
     N4J_CUDA(cudaSetDevice(device_));
+    t_pdl = pdl_;
     if (params_fresh_ == false && user_params_) { launches_ = 0; upload_params(); }
     Ref yin = fixed_ref(Y_), kout = fixed_ref(K_);
     auto piece = [&]() {

@@ -77,6 +77,7 @@ private:
     int device_;
     n4j_solver_cfg cfg_;
     bool exact_ = false;       // N4J_FLAG_EXACT_CONTRACTIONS
+    bool pdl_ = true;          // programmatic dependent launch on every kernel (N4J_FLAG_NO_PDL turns it off)
     ConvGeom geom_{};          // padded geometry shared by all conv layers of the block
     size_t conv_smem_ = 0;
     std::vector<LayerPlan> L_;

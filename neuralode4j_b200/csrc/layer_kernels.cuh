@@ -22,6 +22,7 @@ namespace n4j {
 // ---------------------------------------------------------------------------------------------------
 // NCHW [B,C,S] -> NHWC [B,S,C]   (S = H*W)
 __global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int S) {
+    pdl_begin();
     const long long n = (long long)B * C * S;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float* __restrict__ 
     }
 }
 __global__ void __launch_bounds__(256) k_nhwc_to_nchw(const float* __restrict__ src, float* __restrict__ dst, int B, int C, int S) {
+    pdl_begin();
     const long long n = (long long)B * C * S;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
@@ -45,6 +47,7 @@ __global__ void __launch_bounds__(256) k_nhwc_to_nchw(const float* __restrict__ 
 }
 // time-first internal [T][n] <-> reference layouts.  rank 2: [B,F,T]; rank 4: [B,T,C,H,W] (MultiStep.java:49-60)
 __global__ void __launch_bounds__(256) k_timefirst_to_ref(const float* __restrict__ src, float* __restrict__ dst, int T, int B, int C, int S, int rank4) {
+    pdl_begin();
     const long long per = (long long)B * C * S;
     const long long n = per * T;
     const long long step = (long long)gridDim.x * blockDim.x;
@@ -62,6 +65,7 @@ __global__ void __launch_bounds__(256) k_timefirst_to_ref(const float* __restric
     }
 }
 __global__ void __launch_bounds__(256) k_ref_to_timefirst(const float* __restrict__ src, float* __restrict__ dst, int T, int B, int C, int S, int rank4) {
+    pdl_begin();
     const long long per = (long long)B * C * S;
     const long long n = per * T;
     const long long step = (long long)gridDim.x * blockDim.x;
@@ -80,6 +84,7 @@ __global__ void __launch_bounds__(256) k_ref_to_timefirst(const float* __restric
 }
 // conv weights: DL4J [Co,Ci,3,3] c-order -> Wf [tap][ci][co] and Wb [tap][co][ci]
 __global__ void __launch_bounds__(256) k_conv_w_to_internal(const float* __restrict__ w, float* __restrict__ wf, float* __restrict__ wb, int Co, int Ci) {
+    pdl_begin();
     const int n = Co * Ci * 9;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int tap = i % 9; const int r = i / 9; const int ci = r % Ci; const int co = r / Ci;
@@ -90,6 +95,7 @@ __global__ void __launch_bounds__(256) k_conv_w_to_internal(const float* __restr
 }
 // theta-slot [tap][ci][co] <-> flat gradient view [Co,Ci,3,3]
 __global__ void __launch_bounds__(256) k_conv_g_internal_to_flat(const float* __restrict__ gi, float* __restrict__ gflat, int Co, int Ci) {
+    pdl_begin();
     const int n = Co * Ci * 9;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int tap = i % 9; const int r = i / 9; const int ci = r % Ci; const int co = r / Ci;
@@ -97,6 +103,7 @@ __global__ void __launch_bounds__(256) k_conv_g_internal_to_flat(const float* __
     }
 }
 __global__ void __launch_bounds__(256) k_conv_g_flat_to_internal(const float* __restrict__ gflat, float* __restrict__ gi, int Co, int Ci) {
+    pdl_begin();
     const int n = Co * Ci * 9;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int tap = i % 9; const int r = i / 9; const int ci = r % Ci; const int co = r / Ci;
@@ -108,6 +115,7 @@ __global__ void __launch_bounds__(256) k_conv_g_flat_to_internal(const float* __
 // Elementwise
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_act_fwd(Ref xin, Ref yout, int act, long long n) {
+    pdl_begin();
     const float* __restrict__ x = resolve(xin);
     float* __restrict__ y = resolve(yout);
     const long long step = (long long)gridDim.x * blockDim.x;
@@ -115,6 +123,7 @@ __global__ void __launch_bounds__(256) k_act_fwd(Ref xin, Ref yout, int act, lon
 }
 // g' = act'(y) * (gscale * g)
 __global__ void __launch_bounds__(256) k_act_bwd(Ref gin, float gscale, Ref yref, int act, Ref gout, long long n) {
+    pdl_begin();
     const float* __restrict__ g = resolve(gin);
     const float* __restrict__ y = resolve(yref);
     float* __restrict__ o = resolve(gout);
@@ -150,6 +159,7 @@ __device__ __forceinline__ void bn_collect(const BnScratch& sc, int C, double* t
 }
 
 __global__ void __launch_bounds__(256) k_bn_stats(Ref xin, long long M, int C, float eps, BnScratch sc) {
+    pdl_begin();
     const float* __restrict__ x = resolve(xin);
     const int cg = C >> 2;                       // float4 groups per row
     const int rows_per_iter = 256 / cg;
@@ -202,6 +212,7 @@ __global__ void __launch_bounds__(256) k_bn_stats(Ref xin, long long M, int C, f
 }
 // generic channel count: one block per channel
 __global__ void __launch_bounds__(256) k_bn_stats_generic(Ref xin, long long M, int C, float eps, BnScratch sc) {
+    pdl_begin();
     const float* __restrict__ x = resolve(xin);
     const int c = blockIdx.x;
     double v[2] = {0, 0};
@@ -218,6 +229,7 @@ __global__ void __launch_bounds__(256) k_bn_stats_generic(Ref xin, long long M, 
 // y = act(gamma * ((x - mean) * invstd) + beta)
 __global__ void __launch_bounds__(256) k_bn_apply(Ref xin, Ref yout, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                    BnScratch sc, int act, long long M, int C) {
+    pdl_begin();
     const float* __restrict__ x = resolve(xin);
     float* __restrict__ y = resolve(yout);
     const long long n = M * C;
@@ -232,6 +244,7 @@ __global__ void __launch_bounds__(256) k_bn_apply(Ref xin, Ref yout, const float
 // backward statistics: dy = act'(y)*(gscale*g);  sums of dy and dy*xhat (double) -> dgamma, dbeta, means
 __global__ void __launch_bounds__(256) k_bn_bwd_stats(Ref gin, float gscale, Ref yref, Ref xin, BnScratch sc, int act, long long M, int C,
                                                        Ref dgamma_ref, Ref dbeta_ref) {
+    pdl_begin();
     const float* __restrict__ g = resolve(gin);
     const float* __restrict__ y = resolve(yref);
     const float* __restrict__ x = resolve(xin);
@@ -303,6 +316,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats(Ref gin, float gscale, Ref
 __global__ void __launch_bounds__(256) k_bn_bwd_stats64(Ref gin, float gscale, Ref yref, Ref xin, BnScratch sc, int act, long long M,
                                                          Ref dgamma_ref, Ref dbeta_ref, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, int fuse_fwd) {
+    pdl_begin();
     const float* __restrict__ g = resolve(gin);
     float* __restrict__ y = resolve(yref);
     const float* __restrict__ x = resolve(xin);
@@ -377,6 +391,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats64(Ref gin, float gscale, R
 // dx = gamma*invstd * ((dy - mean(dy)) - xhat*mean(dy*xhat))
 __global__ void __launch_bounds__(256) k_bn_bwd_dx(Ref gin, float gscale, Ref yref, Ref xin, const float* __restrict__ gamma, BnScratch sc,
                                                     int act, long long M, int C, Ref dxout) {
+    pdl_begin();
     const float* __restrict__ g = resolve(gin);
     const float* __restrict__ y = resolve(yref);
     const float* __restrict__ x = resolve(xin);
@@ -401,6 +416,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_dx(Ref gin, float gscale, Ref yr
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_dense_fwd_exact(Ref xin, Ref yout, const float* __restrict__ Wt, const float* __restrict__ bias,
                                                           int act, long long B, int nin, int nout) {
+    pdl_begin();
     const float* __restrict__ x = resolve(xin);
     float* __restrict__ y = resolve(yout);
     const long long n = B * nout;
@@ -417,6 +433,7 @@ __global__ void __launch_bounds__(256) k_dense_fwd_exact(Ref xin, Ref yout, cons
 }
 // dW(i,o) = sum_b x(b,i) d(b,o)  -> out[i + o*nIn];  db(o) = sum_b d(b,o) -> out[nIn*nOut + o]
 __global__ void __launch_bounds__(256) k_dense_wgrad_exact(Ref xin, Ref din, Ref dwout, long long B, int nin, int nout, int has_bias) {
+    pdl_begin();
     const float* __restrict__ x = resolve(xin);
     const float* __restrict__ d = resolve(din);
     float* __restrict__ dw = resolve(dwout);
@@ -434,6 +451,7 @@ __global__ void __launch_bounds__(256) k_dense_wgrad_exact(Ref xin, Ref din, Ref
     }
 }
 __global__ void __launch_bounds__(256) k_dense_dgrad_exact(Ref din, const float* __restrict__ Wt, Ref dxout, long long B, int nin, int nout) {
+    pdl_begin();
     const float* __restrict__ d = resolve(din);
     float* __restrict__ dx = resolve(dxout);
     const long long n = B * nin;
@@ -446,7 +464,8 @@ __global__ void __launch_bounds__(256) k_dense_dgrad_exact(Ref din, const float*
         dx[idx] = (float)acc;
     }
 }
-__global__ void __launch_bounds__(256) k_colsum(Ref din, Ref out, long long B, int n) {   // bias gradient for the tiled path
+__global__ void __launch_bounds__(256) k_colsum(Ref din, Ref out, long long B, int n) {
+    pdl_begin();   // bias gradient for the tiled path
     const float* __restrict__ d = resolve(din);
     float* __restrict__ o = resolve(out);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
@@ -510,6 +529,7 @@ template <int MODE> struct Addr {
 // order-independent and therefore bit-compatible with the oracle (N4J_FLAG_EXACT_CONTRACTIONS, parity mode).
 template <int MODE, typename AccT>
 __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
+    pdl_begin();
     constexpr int BM = 64, BN = 64, BK = 16;
     __shared__ float As[BK][BM + 4];
     __shared__ float Bs[BK][BN + 4];
@@ -586,6 +606,7 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
 
 // deterministic split-K reduction: dst[i] = sum_z part[z][i]
 __global__ void __launch_bounds__(256) k_splitk_reduce(const float* __restrict__ part, Ref dstref, long long n, int splits) {
+    pdl_begin();
     float* __restrict__ dst = resolve(dstref);
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {

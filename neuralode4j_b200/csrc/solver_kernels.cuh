@@ -53,6 +53,7 @@ template <int S>
 __global__ void __launch_bounds__(256) k_stage_combine(const Ctrl* __restrict__ c, float* __restrict__ Ybase,
                                                         const float* __restrict__ Kbase, long long stride, long long i_begin, long long n4,
                                                         BnFuse bf) {
+    pdl_begin();
     const float h = c->h;
     const int yc = c->y_cur;
     const float* __restrict__ y = Ybase + (long long)yc * stride;
@@ -222,6 +223,7 @@ __device__ __forceinline__ void controller_after_error(Ctrl* c, double sum, cons
 __global__ void __launch_bounds__(256) k_error_ctrl(Ctrl* c, const float* __restrict__ Ybase, const float* __restrict__ Kbase,
                                                      long long stride, long long n4, SolverParams p, n4j_step_rec* log,
                                                      DenseOutArgs dout, cudaGraphConditionalHandle cond, int use_cond) {
+    pdl_begin();
     const float h = c->h;
     const int yc = c->y_cur;
     const float* __restrict__ y0 = Ybase + (long long)yc * stride;
@@ -265,6 +267,7 @@ __global__ void __launch_bounds__(256) k_error_ctrl(Ctrl* c, const float* __rest
 // Variant without the controller: DormandPrince54Mse on caller data (node4j_error_norm).
 __global__ void __launch_bounds__(256) k_error_only(const float* __restrict__ K, const float* __restrict__ y0, const float* __restrict__ y1,
                                                      long long n, float h, float atol, float rtol, double* acc) {
+    pdl_begin();
     double s[1] = {0.0};
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
@@ -285,6 +288,7 @@ __global__ void __launch_bounds__(256) k_error_only(const float* __restrict__ K,
 // K4: initial step (AdaptiveRungeKuttaStepPolicy.initializeStep :90-139), two reduction passes.
 // ---------------------------------------------------------------------------------------------------
 __global__ void k_solve_begin(Ctrl* c, const float* tpair) {
+    pdl_begin();
     // integrate(): new FirstOrderEquationWithState(equation, t[0], yOut.assign(y0)) — state reset for one solve
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const int pair_index = c->seg_index;
@@ -301,6 +305,7 @@ __global__ void k_solve_begin(Ctrl* c, const float* tpair) {
 
 __global__ void __launch_bounds__(256) k_init_sums(Ctrl* c, const float* __restrict__ Ybase, const float* __restrict__ Kbase,
                                                     long long stride, long long n4, SolverParams p) {
+    pdl_begin();
     const float* __restrict__ y = Ybase + (long long)c->y_cur * stride;
     const float* __restrict__ k0 = Kbase + (long long)c->krow[0] * stride;
     double s[2] = {0.0, 0.0};
@@ -333,6 +338,7 @@ __global__ void __launch_bounds__(256) k_init_sums(Ctrl* c, const float* __restr
 __global__ void __launch_bounds__(256) k_init_final(Ctrl* c, const float* __restrict__ Ybase, const float* __restrict__ Kbase,
                                                      long long stride, long long n4, SolverParams p,
                                                      cudaGraphConditionalHandle cond, int use_cond) {
+    pdl_begin();
     const float* __restrict__ y = Ybase + (long long)c->y_cur * stride;
     const float* __restrict__ k0 = Kbase + (long long)c->krow[0] * stride;
     const float* __restrict__ k1 = Kbase + (long long)c->krow[1] * stride;
@@ -384,6 +390,7 @@ __global__ void __launch_bounds__(256) k_init_final(Ctrl* c, const float* __rest
 __global__ void __launch_bounds__(256) k_dense_output(const Ctrl* __restrict__ c, const float* __restrict__ Ybase,
                                                        const float* __restrict__ Kbase, long long stride, long long n,
                                                        const float* __restrict__ wanted, float* __restrict__ out, long long out_stride) {
+    pdl_begin();
     if (!c->accepted_now || c->interp_cnt <= 0) return;
     const float h = c->h_used;
     const double t0 = (double)c->t_prev, t1 = (double)c->t;
@@ -444,6 +451,7 @@ __global__ void __launch_bounds__(256) k_dense_output(const Ctrl* __restrict__ c
 __global__ void __launch_bounds__(256) k_dense_edge(const Ctrl* __restrict__ c, const float* __restrict__ Ybase, long long stride,
                                                      long long n, const float* __restrict__ wanted, int which_wanted, int at_end,
                                                      float* __restrict__ out, long long out_stride) {
+    pdl_begin();
     const double tref = at_end ? (double)c->t : (double)c->t_start;
     if (!(fabs(tref - (double)wanted[which_wanted]) < 1e-10)) return;
     const float* __restrict__ y = Ybase + (long long)c->y_cur * stride;
@@ -458,6 +466,7 @@ __global__ void __launch_bounds__(256) k_dense_edge(const Ctrl* __restrict__ c, 
 // dst <- Y[y_cur]  (the caller's yOut after integrate, AdaptiveRungeKuttaSolver.java:126)
 __global__ void __launch_bounds__(256) k_copy_from_state(const Ctrl* __restrict__ c, const float* __restrict__ Ybase, long long stride,
                                                           long long off, float* __restrict__ dst, long long n) {
+    pdl_begin();
     const float* __restrict__ y = Ybase + (long long)c->y_cur * stride + off;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) dst[i] = y[i];
@@ -465,18 +474,21 @@ __global__ void __launch_bounds__(256) k_copy_from_state(const Ctrl* __restrict_
 // Y[y_cur][off:off+n] <- src (+ optional add)
 __global__ void __launch_bounds__(256) k_copy_to_state(const Ctrl* __restrict__ c, float* __restrict__ Ybase, long long stride, long long off,
                                                         const float* __restrict__ src, const float* __restrict__ add, long long n) {
+    pdl_begin();
     float* __restrict__ y = Ybase + (long long)c->y_cur * stride + off;
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
         y[i] = add ? __fadd_rn(src[i], add[i]) : src[i];
 }
 __global__ void __launch_bounds__(256) k_fill(float* __restrict__ p, float v, long long n) {
+    pdl_begin();
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) p[i] = v;
 }
 
 // <a, b> in double -> (float) out[idx]; used for CalcTimeGrad.calcTimeAdjointT1 :52-58
 __global__ void __launch_bounds__(256) k_dot(const float* __restrict__ a, const float* __restrict__ b, long long n, double* acc) {
+    pdl_begin();
     double s[1] = {0.0};
     const long long step = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) s[0] += (double)a[i] * (double)b[i];
@@ -491,6 +503,7 @@ __global__ void __launch_bounds__(256) k_dot(const float* __restrict__ a, const 
 // buffers in rank order.  Grid <= 64 blocks so every block is resident while it waits.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_comm_allreduce_vec(CommDev* cm, Ref bufref, long long n) {
+    pdl_begin();
     float* __restrict__ buf = resolve(bufref);
     __shared__ int s_last;
     const unsigned long long seq = cm->seq_x + 1;
