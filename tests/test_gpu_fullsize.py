@@ -1,0 +1,121 @@
+"""GPU tests at BASELINE.json's FULL sizes, where the CPU oracle would take minutes: size-independent properties of the path
+(round trips, equivariance, identities between the reference's own code paths, determinism, counters)."""
+import numpy as np
+import pytest
+
+from neuralode4j_b200 import _lib
+from neuralode4j_b200 import workloads as W
+from neuralode4j_b200.conf import DormandPrince54Solver, FixedStep, SolverConfig
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _forward(w, y0=None, time=None, flags=0):
+    v = w.conf.instantiate(w.shape, flags=flags)
+    try:
+        v.setParams(w.params)
+        y0 = w.y0 if y0 is None else y0
+        if w.time_is_input:
+            v.setInputs(y0, w.time if time is None else time)
+        else:
+            v.setInputs(y0)
+        out = v.doForward(True)
+        return out, (v.fwd_stats.nfe, v.fwd_stats.accepted, v.fwd_stats.rejected)
+    finally:
+        v.close()
+
+
+def test_mnist_full_counters_determinism_and_modes():
+    """Config #2 at batch 128: nfe = 3 + 6*trials, bitwise run-to-run determinism, graph loop == host loop,
+    device pointers == host pointers."""
+    w = W.mnist_block()
+    a = H.run_cuda(w)
+    b = H.run_cuda(w)
+    c = H.run_cuda(w, flags=_lib.FLAG_NO_GRAPH)
+    d = H.run_cuda(w, device_tensors=True)
+    for r in (a, b, c, d):
+        assert r["fwd_stats"][0] == 3 + 6 * (r["fwd_stats"][1] + r["fwd_stats"][2])
+        assert r["bwd_stats"][0] == 3 + 6 * (r["bwd_stats"][1] + r["bwd_stats"][2])
+    for k in ("out", "dy0"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]) and np.array_equal(a[k], d[k]), k
+    # the weight-gradient partials are summed in a fixed order: gradients are reproducible too
+    assert np.array_equal(a["grad"], b["grad"]) and np.array_equal(a["grad"], c["grad"])
+    assert np.isfinite(a["grad"]).all() and np.abs(a["grad"]).max() > 0
+    C = 64
+    assert not a["grad"][2 * C:4 * C].any()            # BatchNorm mean/var slots are not gradients
+
+
+def test_mnist_full_time_round_trip():
+    """Integrating t: 0 -> 1 and then 1 -> 0 with the same f returns to y0 within the solver tolerance (atol = rtol = 1e-3)."""
+    w = W.mnist_block()
+    out, _ = _forward(w)
+    solver = DormandPrince54Solver(SolverConfig(1e-3, 1e-3, 1e-20, 100))
+    wb = W.mnist_block()
+    wb.conf.odeForwardConf = FixedStep(solver, np.array([1.0, 0.0]))
+    wb.conf.odeBackwardConf = wb.conf.odeForwardConf
+    back, _ = _forward(wb, y0=out)
+    err = np.abs(back - w.y0)
+    assert err.max() < 5e-2 and np.sqrt(np.mean(err ** 2)) < 5e-3, (err.max(), np.sqrt(np.mean(err ** 2)))
+
+
+def test_mnist_full_batch_permutation_equivariance():
+    """BatchNorm statistics are sums over the batch: permuting the rows of the minibatch permutes the result."""
+    w = W.mnist_block()
+    perm = np.random.default_rng(3).permutation(w.shape[0])
+    a, sa = _forward(w)
+    b, sb = _forward(w, y0=np.ascontiguousarray(w.y0[perm]))
+    assert sa == sb
+    np.testing.assert_allclose(b, a[perm], rtol=2e-5, atol=2e-5)
+
+
+def test_mnist_full_parity_mode_close_to_default_mode():
+    """Forward state of the tensor-core (3xTF32) path vs the double-accumulating parity path at full size: rtol 1e-4."""
+    w = W.mnist_block()
+    a, sa = _forward(w)
+    b, sb = _forward(w, flags=_lib.FLAG_EXACT_CONTRACTIONS)
+    assert sa == sb
+    H.assert_close(a, b, 1e-4, 1e-5 * np.abs(b).max(), "default vs parity mode")
+
+
+def test_spiral_full_interpolating_equals_single_stepping():
+    """Config #1 at its full size (1000 x 4, 100 time points): InterpolatingMultiStepSolverTest's identity (1e-4)."""
+    w = W.spiral_block()
+    a, sa = _forward(w)
+    w2 = W.spiral_block()
+    w2.conf.odeForwardConf.interpolateForwardIfMultiStep = False
+    b, sb = _forward(w2)
+    assert a.shape == (1000, 4, 100)
+    np.testing.assert_array_equal(a[:, :, 0], w.y0)                 # z(t0) is prepended (MultiStep.java:49-60)
+    np.testing.assert_allclose(a, b, rtol=1e-3, atol=1e-4)
+    assert sb[0] > sa[0]                                            # one solve + dense output needs fewer RHS evaluations
+
+
+def test_spiral_full_backward_runs_99_segments():
+    w = W.spiral_block()
+    r = H.run_cuda(w)
+    assert r["out"].shape == (1000, 4, 100) and r["dy0"].shape == (1000, 4)
+    assert np.isfinite(r["grad"]).all() and np.isfinite(r["dy0"]).all()
+    assert np.all(r["dt"] == 0)                                     # needTimeGradient=false -> ZeroMultiStepTimeGrad
+    assert r["bwd_stats"][0] >= 99 * 9                              # 99 segments, each at least one trial
+
+
+def test_timeseries_full_time_gradient_identity():
+    """Config #5 at timing size: for an autonomous f the time gradients of the reference satisfy dL/dt[0] = -sum(dL/dt[1:])
+    (CalcMultiStepTimeGrad.java:45-68 with a_t' = 0)."""
+    w = W.timeseries_block()
+    r = H.run_cuda(w)
+    dt = r["dt"].astype(np.float64)
+    assert abs(dt[0] + dt[1:].sum()) <= 1e-4 * np.abs(dt[1:]).sum()
+    assert np.isfinite(r["grad"]).all()
+
+
+def test_mlp_full_forward_and_adjoint_finite():
+    """Config #3 (1024 x 4096, two dense layers): runs at full size; adjoint of a linear-ish block stays finite and the
+    real-gradient count is the whole parameter vector (no BatchNorm)."""
+    w = W.mlp_block()
+    r = H.run_cuda(w)
+    assert r["out"].shape == (1024, 4096)
+    assert np.isfinite(r["out"]).all() and np.isfinite(r["dy0"]).all() and np.isfinite(r["grad"]).all()
+    assert r["fwd_stats"][0] == 3 + 6 * (r["fwd_stats"][1] + r["fwd_stats"][2])
