@@ -38,6 +38,45 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 
 static inline long long round_up4(long long n) { return (n + 3) & ~3LL; }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p)
+            throw Error{N4J_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver"};
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// activation image [2*nch][rows][4 floats] with a {4, box_rows, box_chunks} box
+static CUtensorMap make_image_map(float* img, long long rows, long long nch2, int box_rows, int box_chunks) {
+    CUtensorMap tm;
+    const cuuint64_t dims[3] = {4, (cuuint64_t)rows, (cuuint64_t)nch2};
+    const cuuint64_t strides[2] = {16, (cuuint64_t)rows * 16};
+    const cuuint32_t box[3] = {4, (cuuint32_t)box_rows, (cuuint32_t)box_chunks};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode_tiled_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error{N4J_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"};
+    return tm;
+}
+// stacked weight image [nblocks][nch][256][4 floats] with a {4, 256, 8, 1} box
+static CUtensorMap make_weight_map(float* img, long long nch, long long nblocks) {
+    CUtensorMap tm;
+    const cuuint64_t dims[4] = {4, 256, (cuuint64_t)nch, (cuuint64_t)nblocks};
+    const cuuint64_t strides[3] = {16, 256 * 16, (cuuint64_t)nch * 256 * 16};
+    const cuuint32_t box[4] = {4, 256, 8, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode_tiled_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error{N4J_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"};
+    return tm;
+}
+
 // =====================================================================================================
 // construction / planning
 // =====================================================================================================
@@ -191,6 +230,31 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
                 ensure(wpart_, (long long)B_ * 9 * 4096);
             }
         }
+        if (l.d.kind == N4J_LAYER_DENSE && !l.exact && !exact_ && !(cfg_.flags & N4J_FLAG_NO_TENSOR) && l.c_in % 32 == 0 && l.c_out % 32 == 0 &&
+            (l.rows * l.c_in * l.c_out >= (1LL << 27) || (cfg_.flags & N4J_FLAG_FORCE_TENSOR))) {   // small layers: launch latency beats the tensor pipe
+            // tensor-core dense path: split images of the layer input / output delta and stacked weight images, moved by TMA
+            l.tcd = true;
+            l.img_rows = (l.rows + 127) / 128 * 128;
+            const size_t xb = sizeof(float) * 2 * l.c_in * l.img_rows, db = sizeof(float) * 2 * l.c_out * l.img_rows;
+            const long long nbf = (l.c_out + 127) / 128, nbb = (l.c_in + 127) / 128;
+            const size_t wfb = sizeof(float) * nbf * (l.c_in / 4) * 256 * 4, wbb = sizeof(float) * nbb * (l.c_out / 4) * 256 * 4;
+            N4J_CUDA(cudaMalloc(&l.ximg, xb)); N4J_CUDA(cudaMemsetAsync(l.ximg, 0, xb, stream_));
+            N4J_CUDA(cudaMalloc(&l.dimg, db)); N4J_CUDA(cudaMemsetAsync(l.dimg, 0, db, stream_));
+            N4J_CUDA(cudaMalloc(&l.wsf, wfb)); N4J_CUDA(cudaMemsetAsync(l.wsf, 0, wfb, stream_));
+            N4J_CUDA(cudaMalloc(&l.wsb, wbb)); N4J_CUDA(cudaMemsetAsync(l.wsb, 0, wbb, stream_));
+            const long long oc_pad = (l.c_out + 127) / 128 * 128;
+            const size_t dtb = sizeof(float) * 2 * l.img_rows * oc_pad, xtb = sizeof(float) * nbb * (l.img_rows / 4) * 256 * 4;
+            N4J_CUDA(cudaMalloc(&l.dTimg, dtb)); N4J_CUDA(cudaMemsetAsync(l.dTimg, 0, dtb, stream_));
+            N4J_CUDA(cudaMalloc(&l.xTimg, xtb)); N4J_CUDA(cudaMemsetAsync(l.xTimg, 0, xtb, stream_));
+            l.tm_x_k = make_image_map(l.ximg, l.img_rows, 2 * (l.c_in / 4), 128, 8);
+            l.tm_d_k = make_image_map(l.dimg, l.img_rows, 2 * (l.c_out / 4), 128, 8);
+            l.tm_dT = make_image_map(l.dTimg, oc_pad, 2 * (l.img_rows / 4), 128, 8);
+            l.tm_xT = make_weight_map(l.xTimg, l.img_rows / 4, nbb);
+            l.tm_wf = make_weight_map(l.wsf, l.c_in / 4, nbf);
+            l.tm_wb = make_weight_map(l.wsb, l.c_out / 4, nbb);
+            N4J_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TC_SMEM));
+        }
+        if (l.d.kind == N4J_LAYER_DENSE && !l.exact && !l.tcd && (long long)l.c_in * l.c_out <= (1LL << 22)) ensure(wpart_, 8LL * l.c_in * l.c_out);
         if (l.d.kind == N4J_LAYER_BATCHNORM) {
             const int cc = l.c_out;
             N4J_CUDA(cudaMalloc(&l.bn.acc, sizeof(double) * 2 * cc * ACC_STRIDE));
@@ -214,6 +278,7 @@ Engine::~Engine() {
     }
     for (auto& l : L_) {
         for (int sl = 0; sl < 2; ++sl) { cudaFree(l.act2[sl]); cudaFree(l.gin2[sl]); }
+        cudaFree(l.ximg); cudaFree(l.dimg); cudaFree(l.dTimg); cudaFree(l.xTimg); cudaFree(l.wsf); cudaFree(l.wsb);
         cudaFree(l.wf); cudaFree(l.wb); cudaFree(l.img); cudaFree(l.gimg); cudaFree(l.wimg_f); cudaFree(l.wimg_b);
         if (l.d.kind == N4J_LAYER_BATCHNORM) { cudaFree(l.bn.acc); cudaFree(l.bn.ticket); cudaFree(l.bn.mean); }
     }
@@ -307,6 +372,12 @@ void Engine::upload_params() {
     if (!user_params_) throw Error{N4J_ERR_ILLEGAL_STATE, "parameters not bound (node4j_bind_params)"};
     to_device(params_.p, user_params_, n_params_);
     for (auto& l : L_)
+        if (l.tcd) {
+            const float* Wt = params_.p + l.p_off;     // [nOut][nIn] (DL4J's f-order [nIn,nOut])
+            LAUNCH(k_weights_to_stacked_image, grid_for((long long)l.c_in * l.c_out), 256, stream_, Wt, l.wsf, l.c_in, l.c_out, 0);
+            LAUNCH(k_weights_to_stacked_image, grid_for((long long)l.c_in * l.c_out), 256, stream_, Wt, l.wsb, l.c_out, l.c_in, 1);
+        }
+    for (auto& l : L_)
         if (l.d.kind == N4J_LAYER_CONV3X3) {
             LAUNCH(k_conv_w_to_internal, grid_for(l.p_len), 256, stream_, params_.p + l.p_off, l.wf, l.wb, l.c_out, l.c_in);
             if (l.tc) {
@@ -362,6 +433,12 @@ static void launch_gemm(cudaStream_t s, GemmArgs g, int& launches, bool exact) {
     ++launches;
 }
 
+void Engine::launch_gemm_tc(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& a) {
+    const dim3 grid(((a.M + 127) / 128) * ((a.N + 127) / 128)), block(GEMM_TC_THREADS);
+    launch_k(k_gemm_tc, grid, block, GEMM_TC_SMEM, s, pdl_, ta, tb, a);
+    ++launches_;
+}
+
 void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act, const LayerPlan* next_bn) {
     ConvTcArgs a{};
     a.img = img; a.wimg = wimg; a.out = out; a.g = geom_; a.act = act;
@@ -392,6 +469,11 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                 const float* bias = l.d.has_bias ? Wt + l.d.n_in * l.d.n_out : nullptr;
                 if (l.exact) {
                     LAUNCH(k_dense_fwd_exact, grid_for(l.out_len), 256, s, cur, dst, Wt, bias, l.d.activation, l.rows, l.c_in, l.c_out);
+                } else if (l.tcd) {
+                    LAUNCH(k_rowmajor_to_image, grid_for(l.in_len / 4), 256, s, cur, 1.f, l.ximg, l.rows, l.c_in, l.img_rows);
+                    GemmTcArgs ga{};
+                    ga.M = (int)l.rows; ga.N = l.c_out; ga.kblocks = l.c_in / 32; ga.a_nch = l.c_in / 4; ga.out = dst; ga.bias = bias; ga.act = l.d.activation;
+                    launch_gemm_tc(s, l.tm_x_k, l.tm_wf, ga);
                 } else {
                     GemmArgs g{}; g.a = cur; g.c = dst; g.w = Wt; g.bias = bias; g.M = (int)l.rows; g.N = l.c_out; g.K = l.c_in;
                     g.act = l.d.activation; g.splits = 1;
@@ -521,13 +603,32 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                 if (l.d.kind == N4J_LAYER_DENSE) {
                     const float* Wt = params_.p + l.p_off;
                     if (l.exact) {
-                        LAUNCH(k_dense_wgrad_exact, grid_for(l.g_len), 256, s, x, d, dth, l.rows, l.c_in, l.c_out, l.d.has_bias);
+                        LAUNCH(k_dense_wgrad_exact, (int)std::min<long long>(l.g_len, 148 * 8), 128, s, x, d, dth, l.rows, l.c_in, l.c_out, l.d.has_bias);
                         if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, s, comm_dev_, dth, l.g_len);
                         LAUNCH(k_dense_dgrad_exact, grid_for(l.in_len), 256, s, d, Wt, dx, l.rows, l.c_in, l.c_out);
+                    } else if (l.tcd) {
+                        LAUNCH(k_rowmajor_to_image, grid_for(l.out_len / 4), 256, s, d, 1.f, l.dimg, l.rows, l.c_out, l.img_rows);
+                        // dW^T[o,i] = sum_b delta[b,o] x[b,i]: K-major GEMM over the batch on the transposed images
+                        LAUNCH(k_rowmajor_to_image_T, grid_for((l.img_rows / 4) * l.c_out), 256, s, d, l.dTimg, l.rows, l.c_out, l.img_rows,
+                               (long long)((l.c_out + 127) / 128 * 128), 0);
+                        LAUNCH(k_rowmajor_to_image_T, grid_for((l.img_rows / 4) * l.c_in), 256, s, x, l.xTimg, l.rows, l.c_in, l.img_rows, 0LL, 1);
+                        GemmTcArgs wa{};
+                        wa.M = l.c_out; wa.N = l.c_in; wa.kblocks = (int)(l.img_rows / 32); wa.a_nch = (int)(l.img_rows / 4); wa.out = dth;
+                        launch_gemm_tc(s, l.tm_dT, l.tm_xT, wa);
+                        if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 256, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
+                        if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, s, comm_dev_, dth, l.g_len);
+                        GemmTcArgs qa{};     // dx[b,i] = sum_o delta[b,o] W(i,o)
+                        qa.M = (int)l.rows; qa.N = l.c_in; qa.kblocks = l.c_out / 32; qa.a_nch = l.c_out / 4; qa.out = dx;
+                        launch_gemm_tc(s, l.tm_d_k, l.tm_wb, qa);
                     } else {
                         GemmArgs w{}; w.a = d; w.b = x; w.c = dth; w.M = l.c_out; w.N = l.c_in; w.K = (int)l.rows; w.splits = 1;
+                        const long long tiles = (long long)((l.c_out + 63) / 64) * ((l.c_in + 63) / 64);
+                        if (!exact_ && tiles < 148 && l.rows >= 256 && wpart_.n >= 8LL * l.c_in * l.c_out) {   // few output tiles, long K: split the batch
+                            w.splits = 8; w.c = fixed_ref(wpart_.p);
+                        }
                         launch_gemm<G_DENSE_WGRAD>(s, w, launches_, exact_);
-                        if (l.d.has_bias) LAUNCH(k_colsum, grid_for(l.c_out), 256, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
+                        if (w.splits > 1) LAUNCH(k_splitk_reduce, grid_for((long long)l.c_in * l.c_out), 256, s, wpart_.p, dth, (long long)l.c_in * l.c_out, 8);
+                        if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 256, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
                         if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, s, comm_dev_, dth, l.g_len);
                         GemmArgs q{}; q.a = d; q.c = dx; q.w = Wt; q.M = (int)l.rows; q.N = l.c_in; q.K = l.c_out; q.splits = 1;
                         launch_gemm<G_DENSE_DGRAD>(s, q, launches_, exact_);

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "gemm_tc.cuh"
 #include "layer_kernels.cuh"
 #include "solver_kernels.cuh"
 
@@ -30,6 +31,16 @@ struct LayerPlan {
     float* gin2[2] = {nullptr, nullptr};
     float* wf = nullptr;     // conv: [tap][ci][co]
     float* wb = nullptr;     // conv: [tap][co][ci]
+    // dense layer on the tcgen05 path (gemm_tc.cuh)
+    bool tcd = false;
+    long long img_rows = 0;          // batch rows padded to a multiple of 128
+    float* ximg = nullptr;           // split image of the layer input  [2*nIn/4][img_rows][4]
+    float* dimg = nullptr;           // split image of the output delta [2*nOut/4][img_rows][4]
+    float* dTimg = nullptr;          // split image of delta^T [2*img_rows/4][nOut padded][4]      (wgrad A operand)
+    float* xTimg = nullptr;          // stacked image of x^T   [nIn/128 blocks][img_rows/4][256][4] (wgrad B operand)
+    float* wsf = nullptr;            // stacked weight image, forward  (rows = out features, K = in features)
+    float* wsb = nullptr;            // stacked weight image, dgrad    (rows = in features,  K = out features)
+    CUtensorMap tm_x_k, tm_d_k, tm_dT, tm_xT, tm_wf, tm_wb;
     bool tc = false;         // conv runs on the tcgen05 path
     float* img = nullptr;    // conv: operand image of the layer input (hi/lo, padded, chunk-major)
     float* gimg = nullptr;   // conv: operand image of the gradient w.r.t. the layer output
@@ -156,6 +167,7 @@ private:
     void enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact = true, bool bn1_ready = false);
     void enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready = false, int slot = 0, bool defer_join = false);
     void join_side(cudaStream_t s);
+    void launch_gemm_tc(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& a);
     void launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act, const LayerPlan* next_bn = nullptr);
     void enqueue_rhs(cudaStream_t s, bool aug, Ref in, Ref out, bool bn1_ready = false) {
         aug ? enqueue_rhs_aug(s, in, out, bn1_ready) : enqueue_rhs_fwd(s, in, out, false, bn1_ready);

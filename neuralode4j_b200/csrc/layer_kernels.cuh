@@ -432,22 +432,24 @@ __global__ void __launch_bounds__(256) k_dense_fwd_exact(Ref xin, Ref yout, cons
     }
 }
 // dW(i,o) = sum_b x(b,i) d(b,o)  -> out[i + o*nIn];  db(o) = sum_b d(b,o) -> out[nIn*nOut + o]
-__global__ void __launch_bounds__(256) k_dense_wgrad_exact(Ref xin, Ref din, Ref dwout, long long B, int nin, int nout, int has_bias) {
+// one block per output element: the batch is split over the 128 threads (double partial sums, block reduce)
+__global__ void __launch_bounds__(128) k_dense_wgrad_exact(Ref xin, Ref din, Ref dwout, long long B, int nin, int nout, int has_bias) {
     pdl_begin();
     const float* __restrict__ x = resolve(xin);
     const float* __restrict__ d = resolve(din);
     float* __restrict__ dw = resolve(dwout);
     const int n = nin * nout + (has_bias ? nout : 0);
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-        double acc = 0;
+    for (int idx = blockIdx.x; idx < n; idx += gridDim.x) {
+        double acc[1] = {0.0};
         if (idx < nin * nout) {
             const int i = idx % nin, o = idx / nin;
-            for (long long b = 0; b < B; ++b) acc += (double)x[b * nin + i] * (double)d[b * nout + o];
+            for (long long b = threadIdx.x; b < B; b += blockDim.x) acc[0] += (double)x[b * nin + i] * (double)d[b * nout + o];
         } else {
             const int o = idx - nin * nout;
-            for (long long b = 0; b < B; ++b) acc += (double)d[b * nout + o];
+            for (long long b = threadIdx.x; b < B; b += blockDim.x) acc[0] += (double)d[b * nout + o];
         }
-        dw[idx] = (float)acc;
+        block_sum<1>(acc);
+        if (threadIdx.x == 0) dw[idx] = (float)acc[0];
     }
 }
 __global__ void __launch_bounds__(256) k_dense_dgrad_exact(Ref din, const float* __restrict__ Wt, Ref dxout, long long B, int nin, int nout) {
@@ -464,14 +466,22 @@ __global__ void __launch_bounds__(256) k_dense_dgrad_exact(Ref din, const float*
         dx[idx] = (float)acc;
     }
 }
-__global__ void __launch_bounds__(256) k_colsum(Ref din, Ref out, long long B, int n) {
-    pdl_begin();   // bias gradient for the tiled path
+__global__ void __launch_bounds__(256) k_colsum(Ref din, Ref out, long long B, int n) {   // bias gradient: column sums in double
+    pdl_begin();
     const float* __restrict__ d = resolve(din);
     float* __restrict__ o = resolve(out);
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
-        double acc = 0;
-        for (long long b = 0; b < B; ++b) acc += (double)d[b * n + c];
-        o[c] = (float)acc;
+    __shared__ double sm[8][33];
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31), rg = threadIdx.x >> 5;
+    double acc = 0;
+    if (c < n)
+        for (long long b = rg; b < B; b += 8) acc += (double)d[b * n + c];
+    sm[rg][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (rg == 0 && c < n) {
+        double t = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) t += sm[r][threadIdx.x];
+        o[c] = (float)t;
     }
 }
 

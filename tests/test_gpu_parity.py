@@ -60,11 +60,11 @@ def test_error_norm_large_ragged():
 # ---------------------------------------------------------------------------------------------------------------
 # RHS and its vjp (ForwardPassTest analogue)
 # ---------------------------------------------------------------------------------------------------------------
-def _rhs_case(w, exact):
+def _rhs_case(w, exact, flags=0):
     orc = H.oracle_for(w)
     rng = np.random.default_rng(11)
     g = rng.standard_normal(w.shape).astype(np.float32)
-    v = w.conf.instantiate(w.shape)
+    v = w.conf.instantiate(w.shape, flags=flags)
     v.setParams(w.params)
     fz = v.rhs(w.y0)
     fz2, dz, dreal = v.rhs_vjp(w.y0, g)
@@ -85,6 +85,12 @@ def test_rhs_dense_exact():
 
 def test_rhs_dense_tiled():
     _rhs_case(W.mlp_block(batch=96, dim=320), exact=False)
+
+
+def test_rhs_dense_tensor_core():
+    """tcgen05 3xTF32 dense GEMMs (forward, dgrad, wgrad through TMA-fed split images) against the oracle, ragged tile edges."""
+    _rhs_case(W.mlp_block(batch=96, dim=320), exact=False, flags=_lib.FLAG_FORCE_TENSOR)
+    _rhs_case(W.mlp_block(batch=300, dim=160, act="elu"), exact=False, flags=_lib.FLAG_FORCE_TENSOR)
 
 
 def test_rhs_conv_bn():
@@ -217,6 +223,7 @@ def test_mnist_block_conv_stem_size():
 def test_mlp_block_small():
     _e2e(W.mlp_block(batch=64, dim=192))
     _e2e(W.mlp_block(batch=64, dim=192), flags=EXACT)
+    _e2e(W.mlp_block(batch=64, dim=192), flags=_lib.FLAG_FORCE_TENSOR)
 
 
 def test_spiral_block_small():
