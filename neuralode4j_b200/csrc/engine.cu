@@ -872,7 +872,7 @@ void Engine::finish_call(n4j_stats* st, int) {
 // =====================================================================================================
 // multi-GPU setup: exchange buffers in peer-mapped memory (CUDA IPC, one process per GPU)
 // =====================================================================================================
-int Engine::comm_grid(long long n) const { return (int)std::max<long long>(1, std::min<long long>(64, (n + 1023) / 1024)); }
+int Engine::comm_grid(long long n) const { return (int)std::max<long long>(1, std::min<long long>(64, (n + 511) / 512)); }
 
 void Engine::comm_export(void* handle64) {
     N4J_CUDA(cudaSetDevice(device_));

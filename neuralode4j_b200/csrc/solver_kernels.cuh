@@ -510,7 +510,10 @@ __global__ void __launch_bounds__(256) k_comm_allreduce_vec(CommDev* cm, Ref buf
     const int par = (int)(seq & 1), me = cm->rank, W = cm->world;
     float* xb = reinterpret_cast<float*>(cm->peer[me] + COMM_OFF_XBUF) + (long long)par * cm->xcap;
     const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) xb[i] = buf[i];
+    const long long n4 = (((size_t)buf & 15) == 0) ? (n >> 2) : 0;     // 128-bit path when the slot is 16-byte aligned; the rest is scalar
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step)
+        reinterpret_cast<float4*>(xb)[i] = reinterpret_cast<const float4*>(buf)[i];
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) xb[i] = buf[i];
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -523,7 +526,6 @@ __global__ void __launch_bounds__(256) k_comm_allreduce_vec(CommDev* cm, Ref buf
         if (threadIdx.x < W) {
             volatile unsigned long long* f = reinterpret_cast<unsigned long long*>(cm->peer[threadIdx.x] + COMM_OFF_XFLAGS) + par * COMM_MAX_WORLD + me;
             *f = seq;
-            __threadfence_system();
         }
     }
     if (threadIdx.x < W) {
@@ -532,7 +534,19 @@ __global__ void __launch_bounds__(256) k_comm_allreduce_vec(CommDev* cm, Ref buf
     }
     __syncthreads();
     __threadfence_system();
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+    // pull: all peers' contributions for one float4 are requested before any is used (W independent 16-byte NVLink loads in flight)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
+        float4 v[COMM_MAX_WORLD];
+#pragma unroll
+        for (int q = 0; q < COMM_MAX_WORLD; ++q)
+            if (q < W) v[q] = __ldcv(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(cm->peer[q] + COMM_OFF_XBUF) + (long long)par * cm->xcap) + i);
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < COMM_MAX_WORLD; ++q)
+            if (q < W) { t.x += v[q].x; t.y += v[q].y; t.z += v[q].z; t.w += v[q].w; }
+        reinterpret_cast<float4*>(buf)[i] = t;
+    }
+    for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
         float t = 0.f;
         for (int q = 0; q < W; ++q)
             t += *reinterpret_cast<volatile float*>(reinterpret_cast<float*>(cm->peer[q] + COMM_OFF_XBUF) + (long long)par * cm->xcap + i);
