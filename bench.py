@@ -42,6 +42,24 @@ def _peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def _conv_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the conv kernel, from the committed `ncu --set full` summary."""
+    path = os.path.join(ROOT, "profiles", "r01_conv3x3_tc_full.txt")
+    try:
+        vals = []
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v = float(f[1])
+                v *= {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(f[2], 1.0)
+                vals.append((f[0], v))
+        reads = [v for k, v in vals if k.startswith("dram__bytes_read")]
+        writes = [v for k, v in vals if k.startswith("dram__bytes_write")]
+        return (sum(reads) / len(reads) + sum(writes) / len(writes)) if reads and writes else None
+    except OSError:
+        return None
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -92,7 +110,7 @@ def _config(n_gpus):
             f"minibatch row-sharded over {n_gpus} GPUs (one process per GPU): global step controller, sync BatchNorm statistics and "
             "parameter-gradient sums exchanged by one-shot all-reduces over NVLink peer memory inside the kernels",
             "l2": "flushed between timed steps (256 MiB write); the step's own ~40 MB working set is L2-resident by nature",
-            "contractions": "fp32-accumulating SIMT implicit GEMM (default mode)"}
+            "contractions": "tcgen05 3xTF32 implicit-GEMM convolutions (fp32-faithful), fp32 FMA weight gradients (default mode)"}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -292,10 +310,13 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(n_launch) * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "k_gemm_tiled<G_CONV_FWD> (3x3 conv as implicit GEMM, M=6272 N=64 K=576)",
+        "roofline": {"bound": "tensor", "kernel": "k_conv3x3_tc<3,*> (tcgen05 3xTF32 implicit-GEMM conv3x3, M=6272 pixels N=64 K=576; 234 launches/step)",
                      "achieved": achieved_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf_sust"],
-                     "traffic": None, "peak_source": f"{peaks['src']} bf16 sustained (kernel runs inside a long step); fp32 SIMT kernel, no tensor pipe yet",
-                     "us_per_launch": conv_us, "share_of_step": conv_share},
+                     "traffic": _conv_traffic_bytes(),
+                     "peak_source": f"{peaks['src']} bf16 sustained (kernel runs inside a long step). The kernel issues 3 TF32 passes per product "
+                                    "(TF32 peak = bf16/2), so fp32-faithful algorithmic flops can reach at most peak/6; 81 CTAs of 148 SMs, "
+                                    "latency-bound at this size (see DESIGN.md section 4)",
+                     "algorithmic_flops_per_launch": conv_flops, "us_per_launch": conv_us, "share_of_step": conv_share},
         "roofline_solver": {"bound": "hbm", "kernel": "6x k_stage_combine + k_error_ctrl (one trial step, 160*N bytes)",
                             "n_fwd": nz, "us_fwd": pass_fwd_us, "gbs_fwd": 160.0 * nz / (pass_fwd_us * 1e-6) / 1e9,
                             "n_aug": n_aug, "us_aug": pass_aug_us, "gbs_aug": 160.0 * n_aug / (pass_aug_us * 1e-6) / 1e9,
