@@ -90,9 +90,20 @@ struct ConvTcArgs {
     BnScratch bn;
     float bn_eps;
     long long bn_rows;    // B*H*W
+    // fused operand prologue (PRO != 0): the four epilogue warps build the A tile in shared memory from compact NHWC tensors
+    //   PRO = 1  forward : A = act(gamma * ((x - mean) * invstd) + beta)                      (BatchNorm apply of the layer in front)
+    //   PRO = 2  backward: A = gamma*invstd * ((dy - mean(dy)) - xhat * mean(dy*xhat)),  dy = act'(y) * gscale * g
+    //                      (BatchNorm backward of the layer BEHIND the conv whose dgrad this launch computes)
+    Ref px, py, pg;       // x: BatchNorm input, y: BatchNorm output (PRO 2), g: gradient w.r.t. the BatchNorm output (PRO 2)
+    float pgscale;
+    const float* pgamma;
+    const float* pbeta;
+    BnScratch pbn;        // statistics of that BatchNorm (mean, invstd, m_dy, m_dyxh)
+    int pact;
+    float* pcompact;      // optional: also store the produced tensor compactly (activation for the backward pass / gradient for wgrad)
 };
 
-template <int PASSES, bool FUSE>
+template <int PASSES, bool FUSE, int PRO>
 __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // dependents may be scheduled; they park in their own wait
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -114,7 +125,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < CONV_TC_STAGES; ++s) { tc::mbar_init(&w_full[s], 1); tc::mbar_init(&w_empty[s], 1); }
-        tc::mbar_init(a_full, 1);
+        tc::mbar_init(a_full, PRO == 0 ? 1 : 128);
         tc::mbar_init(d_full, 1);
         tc::fence_barrier_init();
     }
@@ -129,12 +140,14 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
     if (warp == 0) {
         if (lane == 0) {
             // ---- producer: activation tile + halo once, then the nine weight taps through the ring ----
-            tc::mbar_arrive_expect_tx(a_full, 2 * a_img_bytes);
-            const long long row0 = g.guard + m0 - g.halo;
-            for (int hl = 0; hl < 2; ++hl)
-                for (int c = 0; c < 16; ++c)
-                    tc::bulk_g2s(sA + hl * a_img_bytes + c * a_chunk_bytes, a.img + (((long long)hl * 16 + c) * g.rows + row0) * 4,
-                                 a_chunk_bytes, a_full);
+            if (PRO == 0) {
+                tc::mbar_arrive_expect_tx(a_full, 2 * a_img_bytes);
+                const long long row0 = g.guard + m0 - g.halo;
+                for (int hl = 0; hl < 2; ++hl)
+                    for (int c = 0; c < 16; ++c)
+                        tc::bulk_g2s(sA + hl * a_img_bytes + c * a_chunk_bytes, a.img + (((long long)hl * 16 + c) * g.rows + row0) * 4,
+                                     a_chunk_bytes, a_full);
+            }
             for (int tap = 0; tap < 9; ++tap) {
                 const int s = tap % CONV_TC_STAGES;
                 if (tap >= CONV_TC_STAGES) tc::mbar_wait(&w_empty[s], ((tap / CONV_TC_STAGES) - 1) & 1);
@@ -190,6 +203,81 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
             const int ph = rem / g.PW, pw = rem - ph * g.PW;
             valid = ph >= 1 && ph <= g.H && pw >= 1 && pw <= g.W;
             crow = ((long long)b * g.H + (ph - 1)) * g.W + (pw - 1);
+        }
+        if (PRO != 0) {
+            // ---- fused operand prologue: BatchNorm apply (+ReLU) or BatchNorm backward, TF32 hi/lo split, zero padding ----
+            const int et = threadIdx.x - 64;           // 0..127; (et & 15) is this thread's channel chunk for every item
+            const int chunk = et & 15, c0 = chunk * 4;
+            const float* __restrict__ px = resolve(a.px);
+            const float* __restrict__ py = PRO == 2 ? resolve(a.py) : nullptr;
+            const float* __restrict__ pg = PRO == 2 ? resolve(a.pg) : nullptr;
+            float mean[4], inv[4], gam[4], bet[4], mdy[4], mdyxh[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                mean[k] = a.pbn.mean[c0 + k]; inv[k] = a.pbn.invstd[c0 + k]; gam[k] = a.pgamma[c0 + k];
+                bet[k] = PRO == 1 ? a.pbeta[c0 + k] : 0.f;
+                mdy[k] = PRO == 2 ? a.pbn.m_dy[c0 + k] : 0.f; mdyxh[k] = PRO == 2 ? a.pbn.m_dyxh[c0 + k] : 0.f;
+            }
+            const int per = g.PH * g.PW;
+            // rows are processed in batches of U: all global loads of a batch are issued before the first use, so a thread
+            // pays the L2 latency once per batch (19 rows per thread -> 4 batches) instead of once per row
+            constexpr int U = 5;
+            for (int r0 = et >> 4; r0 < rt; r0 += 8 * U) {
+                long long i4[U];
+                bool inside[U];
+                float4 xv[U], gv[U], yv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int r = r0 + 8 * u;
+                    const long long pr = m0 - g.halo + r;
+                    inside[u] = false;
+                    i4[u] = 0;
+                    if (r < rt && pr >= 0 && pr < g.mpad) {
+                        const int b = (int)(pr / per);
+                        const int rem = (int)(pr - (long long)b * per);
+                        const int ph = rem / g.PW, pw = rem - ph * g.PW;
+                        if (ph >= 1 && ph <= g.H && pw >= 1 && pw <= g.W) {
+                            inside[u] = true;
+                            i4[u] = (((long long)b * g.H + (ph - 1)) * g.W + (pw - 1)) * 16 + chunk;
+                        }
+                    }
+                    if (inside[u]) {
+                        xv[u] = reinterpret_cast<const float4*>(px)[i4[u]];
+                        if (PRO == 2) { gv[u] = reinterpret_cast<const float4*>(pg)[i4[u]]; yv[u] = reinterpret_cast<const float4*>(py)[i4[u]]; }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int r = r0 + 8 * u;
+                    if (r >= rt) break;
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (inside[u]) {
+                        const float xx[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                        float oo[4];
+                        if (PRO == 1) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                oo[k] = act_fwd(a.pact, __fadd_rn(__fmul_rn(gam[k], __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k])), bet[k]));
+                        } else {
+                            const float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w}, yy[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float dy = act_bwd(a.pact, yy[k], __fmul_rn(a.pgscale, gg[k]));
+                                const float xh = __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k]);
+                                oo[k] = __fmul_rn(__fmul_rn(gam[k], inv[k]), __fsub_rn(__fsub_rn(dy, mdy[k]), __fmul_rn(xh, mdyxh[k])));
+                            }
+                        }
+                        o = make_float4(oo[0], oo[1], oo[2], oo[3]);
+                        if (a.pcompact && r >= g.halo && r < g.halo + 128) reinterpret_cast<float4*>(a.pcompact)[i4[u]] = o;   // rows this tile owns
+                    }
+                    float4 hi, lo;
+                    tc::split_tf32(o.x, hi.x, lo.x); tc::split_tf32(o.y, hi.y, lo.y); tc::split_tf32(o.z, hi.z, lo.z); tc::split_tf32(o.w, hi.w, lo.w);
+                    *reinterpret_cast<float4*>(sA + chunk * a_chunk_bytes + r * 16) = hi;
+                    *reinterpret_cast<float4*>(sA + a_img_bytes + chunk * a_chunk_bytes + r * 16) = lo;
+                }
+            }
+            tc::fence_proxy_async();          // generic-proxy writes above -> visible to the tensor core (async proxy)
+            tc::mbar_arrive(a_full);
         }
         float* __restrict__ out = resolve(a.out);
         float* sT = reinterpret_cast<float*>(sW);      // [128][65] transpose buffer; the weight ring is idle once d_full fires

@@ -37,6 +37,7 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     } while (0)
 
 static inline long long round_up4(long long n) { return (n + 3) & ~3LL; }
+template <int PRO> static void set_conv_smem(size_t smem);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -219,10 +220,7 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
                 N4J_CUDA(cudaMemsetAsync(l.gimg, 0, img_bytes, stream_));
                 N4J_CUDA(cudaMalloc(&l.wimg_f, sizeof(float) * 9 * 2 * 4096));
                 N4J_CUDA(cudaMalloc(&l.wimg_b, sizeof(float) * 9 * 2 * 4096));
-                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
-                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
-                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
-                N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_));
+                set_conv_smem<0>(conv_smem_); set_conv_smem<1>(conv_smem_); set_conv_smem<2>(conv_smem_);
                 side_capable_ = true;
                 wgrad_smem_ = conv_wgrad_smem_bytes(geom_);
                 if (wgrad_smem_ > 200 * 1024) throw Error{N4J_ERR_UNSUPPORTED, "feature map too large for the native conv weight-gradient kernel"};
@@ -333,10 +331,12 @@ int Engine::grid_for(long long n, int per_thread) const {
     return (int)blocks;
 }
 // Grid for kernels that end in a cross-block reduction (double atomics + ticket on a handful of addresses): same-address
-// atomics serialise in L2, so the block count is capped at one per SM and shrinks with the problem.
+// atomics serialise in L2, so the block count is capped at two per SM (measured best on B200, r01) and shrinks with the problem.
 int Engine::grid_red(long long n4) const {
-    long long blocks = (n4 + 256LL * 4 - 1) / (256LL * 4);
-    blocks = std::max<long long>(1, std::min<long long>(blocks, n4 > (4LL << 20) ? 148 * 8 : 148));   // HBM-sized states need the extra loads in flight
+    static const int per = getenv("N4J_GRID_RED_PER") ? atoi(getenv("N4J_GRID_RED_PER")) : 2;
+    static const int cap = getenv("N4J_GRID_RED_CAP") ? atoi(getenv("N4J_GRID_RED_CAP")) : 296;
+    long long blocks = (n4 + 256LL * per - 1) / (256LL * per);
+    blocks = std::max<long long>(1, std::min<long long>(blocks, n4 > (4LL << 20) ? 148 * 8 : cap));   // HBM-sized states need the extra loads in flight
     return (int)blocks;
 }
 // stage combination + statistics of a leading 64-channel BatchNorm in one pass
@@ -439,26 +439,45 @@ void Engine::launch_gemm_tc(cudaStream_t s, const CUtensorMap& ta, const CUtenso
     ++launches_;
 }
 
-void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act, const LayerPlan* next_bn) {
+template <int PRO>
+static void launch_conv_variant(const ConvTcArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, bool fast, bool fuse) {
+    if (fuse) {
+        if (fast) launch_k(k_conv3x3_tc<1, true, PRO>, grid, block, smem, s, pdl, a);
+        else launch_k(k_conv3x3_tc<3, true, PRO>, grid, block, smem, s, pdl, a);
+    } else {
+        if (fast) launch_k(k_conv3x3_tc<1, false, PRO>, grid, block, smem, s, pdl, a);
+        else launch_k(k_conv3x3_tc<3, false, PRO>, grid, block, smem, s, pdl, a);
+    }
+}
+template <int PRO>
+static void set_conv_smem(size_t smem) {
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, true, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, true, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, false, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, false, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+
+// pro/pro_kind: fused operand prologue (1 = BatchNorm apply in front of a forward conv, 2 = BatchNorm backward in front of a dgrad)
+void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act, const LayerPlan* next_bn,
+                            const ConvTcArgs* pro, int pro_kind) {
     ConvTcArgs a{};
+    if (pro) a = *pro;
     a.img = img; a.wimg = wimg; a.out = out; a.g = geom_; a.act = act;
     a.fuse_stats = next_bn ? 1 : 0;
     if (next_bn) { a.bn = next_bn->bn; a.bn_eps = next_bn->d.eps; a.bn_rows = next_bn->rows; }
     const bool fast = (cfg_.flags & N4J_FLAG_FAST_TF32) != 0;
     const dim3 grid(geom_.tiles), block(CONV_TC_THREADS);
-    if (next_bn) {
-        if (fast) launch_k(k_conv3x3_tc<1, true>, grid, block, conv_smem_, s, pdl_, a);
-        else launch_k(k_conv3x3_tc<3, true>, grid, block, conv_smem_, s, pdl_, a);
-    } else {
-        if (fast) launch_k(k_conv3x3_tc<1, false>, grid, block, conv_smem_, s, pdl_, a);
-        else launch_k(k_conv3x3_tc<3, false>, grid, block, conv_smem_, s, pdl_, a);
-    }
+    if (pro_kind == 1) launch_conv_variant<1>(a, grid, block, conv_smem_, s, pdl_, fast, next_bn != nullptr);
+    else if (pro_kind == 2) launch_conv_variant<2>(a, grid, block, conv_smem_, s, pdl_, fast, next_bn != nullptr);
+    else launch_conv_variant<0>(a, grid, block, conv_smem_, s, pdl_, fast, next_bn != nullptr);
     ++launches_;
 }
 
 void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact, bool bn1_ready) {
     Ref cur = in;
     bool image_ready = false;   // the previous layer already wrote the operand image of this (tensor-core) conv
+    bool pro_pending = false;   // ... or left its BatchNorm apply to the conv kernel's operand prologue
+    ConvTcArgs pro_args{};
     bool stats_ready = bn1_ready;   // the previous kernel (conv epilogue / stage combination) already produced this BatchNorm's mean / invstd
     for (size_t i = 0; i < L_.size(); ++i) {
         LayerPlan& l = L_[i];
@@ -486,7 +505,9 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                     if (!image_ready) LAUNCH(k_compact_to_image, grid_for(l.in_len / 4), 256, s, cur, geom_, l.img);
                     // a BatchNorm right after the conv gets its batch statistics from the conv epilogue
                     const bool bn_next = i + 1 < L_.size() && L_[i + 1].d.kind == N4J_LAYER_BATCHNORM && L_[i + 1].c_out == 64;
-                    launch_conv_tc(s, l.img, l.wimg_f, dst, l.d.activation, bn_next ? &L_[i + 1] : nullptr);
+                    launch_conv_tc(s, l.img, l.wimg_f, dst, l.d.activation, bn_next ? &L_[i + 1] : nullptr, pro_pending ? &pro_args : nullptr,
+                                   pro_pending ? 1 : 0);
+                    pro_pending = false;
                     image_ready = false;
                     stats_ready = bn_next;
                     break;
@@ -509,7 +530,14 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                 } else {
                     LAUNCH(k_bn_stats_generic, cc, 256, s, cur, l.rows, cc, l.d.eps, l.bn);
                 }
-                if (feeds_tc) {
+                if (feeds_tc && (cfg_.flags & N4J_FLAG_PROLOGUE_FUSION)) {
+                    // the BatchNorm apply (+ReLU, TF32 split, zero padding) runs as the operand prologue of the conv kernel itself
+                    pro_pending = true;
+                    pro_args = ConvTcArgs{};
+                    pro_args.px = cur; pro_args.pgamma = params_.p + l.p_off; pro_args.pbeta = params_.p + l.p_off + cc; pro_args.pbn = l.bn;
+                    pro_args.pact = l.d.activation; pro_args.pcompact = need_compact ? l.act : (float*)nullptr;
+                    image_ready = true;
+                } else if (feeds_tc) {
                     // BatchNorm-apply writes the next conv's operand image directly (hi/lo split, zero-padded, chunk-major);
                     // the compact activation is only needed by the backward pass
                     LAUNCH(k_bn_apply_to_image, grid_for(l.out_len / 4), 256, s, cur, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn,
@@ -559,6 +587,8 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
     float gscale = -1.f;                                 // zAdjoint().negi() :75
     const int last = (int)L_.size() - 1;
     bool gimg_ready = false;     // the BatchNorm above already wrote the operand image of this conv's output gradient
+    bool bpro_pending = false;   // ... or left its backward to the dgrad kernel's operand prologue
+    ConvTcArgs bpro_args{};
     bool forked = false;
     for (int i = last; i >= 0; --i) {
         LayerPlan& l = L_[i];
@@ -580,7 +610,14 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     LAUNCH(k_bn_bwd_stats, grid, 256, s, g, gscale, y, x, l.bn, l.d.activation, l.rows, cc, dth, with_off(dth, cc));
                 }
                 const bool feeds_tc = i > 0 && L_[i - 1].d.kind == N4J_LAYER_CONV3X3 && L_[i - 1].tc;
-                if (feeds_tc) {
+                if (feeds_tc && (cfg_.flags & N4J_FLAG_PROLOGUE_FUSION)) {
+                    // BatchNorm backward dx is produced by the operand prologue of the dgrad conv (and stored compactly for wgrad)
+                    bpro_pending = true;
+                    bpro_args = ConvTcArgs{};
+                    bpro_args.px = x; bpro_args.py = y; bpro_args.pg = g; bpro_args.pgscale = gscale; bpro_args.pgamma = params_.p + l.p_off;
+                    bpro_args.pbn = l.bn; bpro_args.pact = l.d.activation; bpro_args.pcompact = l.gin;
+                    gimg_ready = true;
+                } else if (feeds_tc) {
                     LAUNCH(k_bn_bwd_dx_to_image, grid_for(l.in_len / 4), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, geom_,
                            l.gin, L_[i - 1].gimg);
                     gimg_ready = true;
@@ -634,11 +671,16 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                         launch_gemm<G_DENSE_DGRAD>(s, q, launches_, exact_);
                     }
                 } else if (l.tc) {
-                    // weight gradient on the side branch (fork), dgrad on the main chain
+                    // dgrad on the main chain.  With the fused prologue the dgrad kernel also materialises `d` (the BatchNorm
+                    // backward of the layer behind this conv) compactly, so the weight gradient forks AFTER it.
+                    if (!gimg_ready) LAUNCH(k_compact_to_image, grid_for(l.out_len / 4), 256, s, d, geom_, l.gimg);
+                    launch_conv_tc(s, l.gimg, l.wimg_b, dx, N4J_ACT_IDENTITY, nullptr, bpro_pending ? &bpro_args : nullptr, bpro_pending ? 2 : 0);
+                    bpro_pending = false;
+                    // weight gradient on the side branch (fork)
                     cudaEvent_t ef = ev_pool_[(ev_next_++) % EV_POOL];
                     N4J_CUDA(cudaEventRecord(ef, s));
                     N4J_CUDA(cudaStreamWaitEvent(side_, ef, 0));
-                    // at most 64 CTAs: they share the chip with the 81 CTAs of the concurrent dgrad convolution
+                    // at most 64 CTAs: they share the chip with the CTAs of the main chain
                     const int ipc = (int)((B_ + 63) / 64), wg_ctas = (int)((B_ + ipc - 1) / ipc);
                     k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, side_>>>(x, d, geom_, wpart_.p, ipc);
                     ++launches_;
@@ -646,8 +688,6 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, side_, comm_dev_, dth, l.g_len);
                     forked = true;
                     side_busy_ = true;
-                    if (!gimg_ready) LAUNCH(k_compact_to_image, grid_for(l.out_len / 4), 256, s, d, geom_, l.gimg);
-                    launch_conv_tc(s, l.gimg, l.wimg_b, dx, N4J_ACT_IDENTITY);
                 } else {
                     GemmArgs w{}; w.a = x; w.b = d; w.c = fixed_ref(wpart_.p); w.M = 9 * l.c_in; w.N = l.c_out; w.K = (int)l.rows;
                     w.H = l.H; w.W = l.W; w.Ci = l.c_in; w.Co = l.c_out; w.splits = 16;
