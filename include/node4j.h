@@ -79,7 +79,7 @@ enum {
     N4J_FLAG_FAST_TF32 = 1u << 2,         /* single-pass TF32 tensor-core contractions (default: 3xTF32, fp32 parity) */
     N4J_FLAG_NO_TENSOR = 1u << 4,         /* keep convolutions on the fp32 SIMT kernels (used to cross-check the tcgen05 path) */
     N4J_FLAG_FORCE_TENSOR = 1u << 6,      /* take the tcgen05 dense path even for layers below the size threshold (tests) */
-    N4J_FLAG_PROLOGUE_FUSION = 1u << 7, /* experimental: BatchNorm apply / backward dx built inside the conv operand prologue (fewer launches, measured slower in r01) */
+    N4J_FLAG_NO_PROLOGUE_FUSION = 1u << 7, /* run BatchNorm apply / backward dx as separate kernels instead of inside the conv operand prologue */
     N4J_FLAG_NO_PDL = 1u << 5,            /* launch kernels without programmatic dependent launch (debug / A-B timing) */
     N4J_FLAG_EXACT_CONTRACTIONS = 1u << 3 /* parity mode: every dense/conv contraction accumulates exact fp32 products in
                                              double and rounds once (order-independent, bit-comparable with the CPU oracle);

@@ -43,7 +43,9 @@ inline ConvGeom make_conv_geom(int B, int H, int W) {
 }
 inline long long conv_image_floats(const ConvGeom& g) { return 2LL * 16 * g.rows * 4; }   // hi + lo
 
-constexpr int CONV_TC_THREADS = 192;
+constexpr int CONV_TC_THREADS = 192;       // producer warp, MMA warp, four epilogue warps
+constexpr int CONV_TC_THREADS_PRO = 256;   // fused operand prologue: two more warps, and ALL eight build the A tile
+constexpr int conv_tc_threads(int pro) { return pro ? CONV_TC_THREADS_PRO : CONV_TC_THREADS; }
 constexpr int CONV_TC_STAGES = 4;
 constexpr int CONV_TC_WSTAGE_BYTES = 2 * 16 * 64 * 16;   // hi+lo image of one tap: 32 KB
 
@@ -90,7 +92,7 @@ struct ConvTcArgs {
     BnScratch bn;
     float bn_eps;
     long long bn_rows;    // B*H*W
-    // fused operand prologue (PRO != 0): the four epilogue warps build the A tile in shared memory from compact NHWC tensors
+    // fused operand prologue (PRO != 0): all eight warps of a 256-thread CTA build the A tile in shared memory from compact NHWC tensors
     //   PRO = 1  forward : A = act(gamma * ((x - mean) * invstd) + beta)                      (BatchNorm apply of the layer in front)
     //   PRO = 2  backward: A = gamma*invstd * ((dy - mean(dy)) - xhat * mean(dy*xhat)),  dy = act'(y) * gscale * g
     //                      (BatchNorm backward of the layer BEHIND the conv whose dgrad this launch computes)
@@ -104,7 +106,7 @@ struct ConvTcArgs {
 };
 
 template <int PASSES, bool FUSE, int PRO>
-__global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a) {
+__global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // dependents may be scheduled; they park in their own wait
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const ConvGeom& g = a.g;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < CONV_TC_STAGES; ++s) { tc::mbar_init(&w_full[s], 1); tc::mbar_init(&w_empty[s], 1); }
-        tc::mbar_init(a_full, PRO == 0 ? 1 : 128);
+        tc::mbar_init(a_full, PRO == 0 ? 1 : CONV_TC_THREADS_PRO / 32);
         tc::mbar_init(d_full, 1);
         tc::fence_barrier_init();
     }
@@ -136,6 +138,98 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
     const uint32_t tmem = *tmem_slot;
     // barrier init and the TMEM allocation above overlap the tail of the producing kernel; global memory is touched from here on
     asm volatile("griddepcontrol.wait;" ::: "memory");
+
+    if constexpr (PRO != 0) {
+        // ---- fused operand prologue, all eight warps: BatchNorm apply (+ReLU) or BatchNorm backward dx, TF32 hi/lo split,
+        // zero padding.  The weight ring is already being filled (below) while this runs.  A warp owns blocks of 8 rows x 4
+        // channel chunks: per quarter warp the shared-memory stores are 128 contiguous bytes (no bank conflicts) and the
+        // global loads are 64 contiguous bytes per row.  All loads of a thread are issued before the first use (one L2
+        // latency per thread, not one per row).
+        if (threadIdx.x == 0) {
+            for (int tap = 0; tap < CONV_TC_STAGES; ++tap) {
+                tc::mbar_arrive_expect_tx(&w_full[tap], CONV_TC_WSTAGE_BYTES);
+                tc::bulk_g2s(sW + tap * CONV_TC_WSTAGE_BYTES, a.wimg + (long long)tap * 8192, CONV_TC_WSTAGE_BYTES, &w_full[tap]);
+            }
+        }
+        const int chunk = (warp & 3) * 4 + (lane >> 3), c0 = chunk * 4;
+        const float* __restrict__ px = resolve(a.px);
+        const float* __restrict__ py = PRO == 2 ? resolve(a.py) : nullptr;
+        const float* __restrict__ pg = PRO == 2 ? resolve(a.pg) : nullptr;
+        // only ReLU / identity are fused (the engine keeps the separate kernels for ELU / tanh): no transcendental code in this kernel
+        const bool relu = a.pact == N4J_ACT_RELU;
+        float mean[4], inv[4], gam[4], bet[4], mdy[4], mdyxh[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            mean[k] = a.pbn.mean[c0 + k]; inv[k] = a.pbn.invstd[c0 + k]; gam[k] = a.pgamma[c0 + k];
+            bet[k] = PRO == 1 ? a.pbeta[c0 + k] : 0.f;
+            mdy[k] = PRO == 2 ? a.pbn.m_dy[c0 + k] : 0.f; mdyxh[k] = PRO == 2 ? a.pbn.m_dyxh[c0 + k] : 0.f;
+        }
+        const int per = g.PH * g.PW;
+        const float inv_pw = 1.0f / (float)g.PW;
+        constexpr int U = 10;                        // rows r = (warp >> 2) * 8 + (lane & 7) + 16 u: 160 >= 128 + 2 * halo for W <= 14
+        const int rbase = (warp >> 2) * 8 + (lane & 7);
+        for (int rr = rbase; rr < rt; rr += 16 * U) {
+            int i4[U];
+            float4 xv[U], gv[U], yv[U];
+            const int pr0 = (int)m0 - g.halo + rr;     // padded rows fit 31 bits (checked where the tensor path is enabled)
+            // image index / position inside the padded image of the first row, advanced by 16 rows per item
+            int bq = pr0 >= 0 ? (int)((unsigned)pr0 / (unsigned)per) : -1;
+            int rem = pr0 >= 0 ? pr0 - bq * per : pr0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = rr + 16 * u;
+                i4[u] = -1;
+                if (r < rt && rem >= 0 && bq < g.B) {
+                    const int ph = __float2int_rz(((float)rem + 0.5f) * inv_pw), pw = rem - ph * g.PW;
+                    if (ph >= 1 && ph <= g.H && pw >= 1 && pw <= g.W) i4[u] = ((bq * g.H + (ph - 1)) * g.W + (pw - 1)) * 16 + chunk;
+                }
+                if (i4[u] >= 0) {
+                    xv[u] = reinterpret_cast<const float4*>(px)[i4[u]];
+                    if (PRO == 2) { gv[u] = reinterpret_cast<const float4*>(pg)[i4[u]]; yv[u] = reinterpret_cast<const float4*>(py)[i4[u]]; }
+                }
+                rem += 16;
+                if (rem >= 0 && bq < 0) bq = 0;
+                while (rem >= per) { rem -= per; ++bq; }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = rr + 16 * u;
+                if (r < rt) {
+                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (i4[u] >= 0) {
+                        const float xx[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                        float oo[4];
+                        if (PRO == 1) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                            {
+                                const float v = __fadd_rn(__fmul_rn(gam[k], __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k])), bet[k]);
+                                oo[k] = (relu && !(v > 0.f)) ? 0.f : v;
+                            }
+                        } else {
+                            const float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w}, yy[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const float gs = __fmul_rn(a.pgscale, gg[k]);
+                                const float dy = (relu && !(yy[k] > 0.f)) ? 0.f : gs;
+                                const float xh = __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k]);
+                                oo[k] = __fmul_rn(__fmul_rn(gam[k], inv[k]), __fsub_rn(__fsub_rn(dy, mdy[k]), __fmul_rn(xh, mdyxh[k])));
+                            }
+                        }
+                        o = make_float4(oo[0], oo[1], oo[2], oo[3]);
+                        if (a.pcompact && r >= g.halo && r < g.halo + 128) reinterpret_cast<float4*>(a.pcompact)[i4[u]] = o;   // rows this tile owns
+                    }
+                    float4 hi, lo;
+                    tc::split_tf32(o.x, hi.x, lo.x); tc::split_tf32(o.y, hi.y, lo.y); tc::split_tf32(o.z, hi.z, lo.z); tc::split_tf32(o.w, hi.w, lo.w);
+                    *reinterpret_cast<float4*>(sA + chunk * a_chunk_bytes + r * 16) = hi;
+                    *reinterpret_cast<float4*>(sA + a_img_bytes + chunk * a_chunk_bytes + r * 16) = lo;
+                }
+            }
+        }
+        tc::fence_proxy_async();          // generic-proxy writes above -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(a_full);
+    }
 
     if (warp == 0) {
         if (lane == 0) {
@@ -148,7 +242,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
                         tc::bulk_g2s(sA + hl * a_img_bytes + c * a_chunk_bytes, a.img + (((long long)hl * 16 + c) * g.rows + row0) * 4,
                                      a_chunk_bytes, a_full);
             }
-            for (int tap = 0; tap < 9; ++tap) {
+            for (int tap = PRO == 0 ? 0 : CONV_TC_STAGES; tap < 9; ++tap) {   // with a prologue the first STAGES taps are already in flight
                 const int s = tap % CONV_TC_STAGES;
                 if (tap >= CONV_TC_STAGES) tc::mbar_wait(&w_empty[s], ((tap / CONV_TC_STAGES) - 1) & 1);
                 tc::mbar_arrive_expect_tx(&w_full[s], CONV_TC_WSTAGE_BYTES);
@@ -189,7 +283,7 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
             }
             tc::mma_commit(d_full);
         }
-    } else {
+    } else if (warp < 6) {
         // ---- epilogue: TMEM lane = tile row; each thread owns one padded pixel and its 64 output channels ----
         const int q = warp & 3;                    // TMEM lane quadrant this warp may read
         const int row = q * 32 + lane;
@@ -203,81 +297,6 @@ __global__ void __launch_bounds__(CONV_TC_THREADS, 1) k_conv3x3_tc(ConvTcArgs a)
             const int ph = rem / g.PW, pw = rem - ph * g.PW;
             valid = ph >= 1 && ph <= g.H && pw >= 1 && pw <= g.W;
             crow = ((long long)b * g.H + (ph - 1)) * g.W + (pw - 1);
-        }
-        if (PRO != 0) {
-            // ---- fused operand prologue: BatchNorm apply (+ReLU) or BatchNorm backward, TF32 hi/lo split, zero padding ----
-            const int et = threadIdx.x - 64;           // 0..127; (et & 15) is this thread's channel chunk for every item
-            const int chunk = et & 15, c0 = chunk * 4;
-            const float* __restrict__ px = resolve(a.px);
-            const float* __restrict__ py = PRO == 2 ? resolve(a.py) : nullptr;
-            const float* __restrict__ pg = PRO == 2 ? resolve(a.pg) : nullptr;
-            float mean[4], inv[4], gam[4], bet[4], mdy[4], mdyxh[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                mean[k] = a.pbn.mean[c0 + k]; inv[k] = a.pbn.invstd[c0 + k]; gam[k] = a.pgamma[c0 + k];
-                bet[k] = PRO == 1 ? a.pbeta[c0 + k] : 0.f;
-                mdy[k] = PRO == 2 ? a.pbn.m_dy[c0 + k] : 0.f; mdyxh[k] = PRO == 2 ? a.pbn.m_dyxh[c0 + k] : 0.f;
-            }
-            const int per = g.PH * g.PW;
-            // rows are processed in batches of U: all global loads of a batch are issued before the first use, so a thread
-            // pays the L2 latency once per batch (19 rows per thread -> 4 batches) instead of once per row
-            constexpr int U = 5;
-            for (int r0 = et >> 4; r0 < rt; r0 += 8 * U) {
-                long long i4[U];
-                bool inside[U];
-                float4 xv[U], gv[U], yv[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int r = r0 + 8 * u;
-                    const long long pr = m0 - g.halo + r;
-                    inside[u] = false;
-                    i4[u] = 0;
-                    if (r < rt && pr >= 0 && pr < g.mpad) {
-                        const int b = (int)(pr / per);
-                        const int rem = (int)(pr - (long long)b * per);
-                        const int ph = rem / g.PW, pw = rem - ph * g.PW;
-                        if (ph >= 1 && ph <= g.H && pw >= 1 && pw <= g.W) {
-                            inside[u] = true;
-                            i4[u] = (((long long)b * g.H + (ph - 1)) * g.W + (pw - 1)) * 16 + chunk;
-                        }
-                    }
-                    if (inside[u]) {
-                        xv[u] = reinterpret_cast<const float4*>(px)[i4[u]];
-                        if (PRO == 2) { gv[u] = reinterpret_cast<const float4*>(pg)[i4[u]]; yv[u] = reinterpret_cast<const float4*>(py)[i4[u]]; }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int r = r0 + 8 * u;
-                    if (r >= rt) break;
-                    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (inside[u]) {
-                        const float xx[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
-                        float oo[4];
-                        if (PRO == 1) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                oo[k] = act_fwd(a.pact, __fadd_rn(__fmul_rn(gam[k], __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k])), bet[k]));
-                        } else {
-                            const float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w}, yy[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const float dy = act_bwd(a.pact, yy[k], __fmul_rn(a.pgscale, gg[k]));
-                                const float xh = __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k]);
-                                oo[k] = __fmul_rn(__fmul_rn(gam[k], inv[k]), __fsub_rn(__fsub_rn(dy, mdy[k]), __fmul_rn(xh, mdyxh[k])));
-                            }
-                        }
-                        o = make_float4(oo[0], oo[1], oo[2], oo[3]);
-                        if (a.pcompact && r >= g.halo && r < g.halo + 128) reinterpret_cast<float4*>(a.pcompact)[i4[u]] = o;   // rows this tile owns
-                    }
-                    float4 hi, lo;
-                    tc::split_tf32(o.x, hi.x, lo.x); tc::split_tf32(o.y, hi.y, lo.y); tc::split_tf32(o.z, hi.z, lo.z); tc::split_tf32(o.w, hi.w, lo.w);
-                    *reinterpret_cast<float4*>(sA + chunk * a_chunk_bytes + r * 16) = hi;
-                    *reinterpret_cast<float4*>(sA + a_img_bytes + chunk * a_chunk_bytes + r * 16) = lo;
-                }
-            }
-            tc::fence_proxy_async();          // generic-proxy writes above -> visible to the tensor core (async proxy)
-            tc::mbar_arrive(a_full);
         }
         float* __restrict__ out = resolve(a.out);
         float* sT = reinterpret_cast<float*>(sW);      // [128][65] transpose buffer; the weight ring is idle once d_full fires

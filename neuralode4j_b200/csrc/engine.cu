@@ -210,6 +210,7 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
             ensure(wpart_, 16LL * l.p_len);
             // tensor-core path: 64->64 channels, identity activation, default (non-parity) mode
             l.tc = !exact_ && !(cfg_.flags & N4J_FLAG_NO_TENSOR) && l.c_in == 64 && l.c_out == 64 && l.d.activation == N4J_ACT_IDENTITY;
+            if (l.tc && (long long)B_ * (H_ + 2) * (W_ + 2) * 64 >= (1LL << 31)) l.tc = false;   // the tensor kernels index padded pixels x channels in 32 bits
             if (l.tc) {
                 geom_ = make_conv_geom((int)B_, H_, W_);
                 conv_smem_ = conv_tc_smem_bytes(geom_);
@@ -466,7 +467,7 @@ void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg,
     a.fuse_stats = next_bn ? 1 : 0;
     if (next_bn) { a.bn = next_bn->bn; a.bn_eps = next_bn->d.eps; a.bn_rows = next_bn->rows; }
     const bool fast = (cfg_.flags & N4J_FLAG_FAST_TF32) != 0;
-    const dim3 grid(geom_.tiles), block(CONV_TC_THREADS);
+    const dim3 grid(geom_.tiles), block(conv_tc_threads(pro_kind));
     if (pro_kind == 1) launch_conv_variant<1>(a, grid, block, conv_smem_, s, pdl_, fast, next_bn != nullptr);
     else if (pro_kind == 2) launch_conv_variant<2>(a, grid, block, conv_smem_, s, pdl_, fast, next_bn != nullptr);
     else launch_conv_variant<0>(a, grid, block, conv_smem_, s, pdl_, fast, next_bn != nullptr);
@@ -530,7 +531,7 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                 } else {
                     LAUNCH(k_bn_stats_generic, cc, 256, s, cur, l.rows, cc, l.d.eps, l.bn);
                 }
-                if (feeds_tc && (cfg_.flags & N4J_FLAG_PROLOGUE_FUSION)) {
+                if (feeds_tc && !(cfg_.flags & N4J_FLAG_NO_PROLOGUE_FUSION) && (l.d.activation == N4J_ACT_RELU || l.d.activation == N4J_ACT_IDENTITY)) {
                     // the BatchNorm apply (+ReLU, TF32 split, zero padding) runs as the operand prologue of the conv kernel itself
                     pro_pending = true;
                     pro_args = ConvTcArgs{};
@@ -610,7 +611,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     LAUNCH(k_bn_bwd_stats, grid, 256, s, g, gscale, y, x, l.bn, l.d.activation, l.rows, cc, dth, with_off(dth, cc));
                 }
                 const bool feeds_tc = i > 0 && L_[i - 1].d.kind == N4J_LAYER_CONV3X3 && L_[i - 1].tc;
-                if (feeds_tc && (cfg_.flags & N4J_FLAG_PROLOGUE_FUSION)) {
+                if (feeds_tc && !(cfg_.flags & N4J_FLAG_NO_PROLOGUE_FUSION) && (l.d.activation == N4J_ACT_RELU || l.d.activation == N4J_ACT_IDENTITY)) {
                     // BatchNorm backward dx is produced by the operand prologue of the dgrad conv (and stored compactly for wgrad)
                     bpro_pending = true;
                     bpro_args = ConvTcArgs{};

@@ -207,12 +207,13 @@ def test_mnist_block_small_default_mode():
     assert _rel_l2(r["grad"], o["grad"]) < 1e-2
 
 
+
 def test_mnist_block_prologue_fusion_matches_separate_kernels():
-    """Opt-in N4J_FLAG_PROLOGUE_FUSION (BatchNorm apply / backward dx built inside the conv operand prologue) computes the
-    same fp32 expressions in the same order as the separate kernels: forward state and step counts identical."""
+    """The conv operand prologue (BatchNorm apply / backward dx built inside the conv kernel; default) against the separate
+    kernels (N4J_FLAG_NO_PROLOGUE_FUSION): same fp32 expressions in the same order, so forward state and step counts agree."""
     w = W.mnist_block(batch=16, channels=64)
     a = H.run_cuda(w)
-    b = H.run_cuda(w, flags=_lib.FLAG_PROLOGUE_FUSION)
+    b = H.run_cuda(w, flags=_lib.FLAG_NO_PROLOGUE_FUSION)
     assert a["fwd_stats"] == b["fwd_stats"] and a["bwd_stats"] == b["bwd_stats"]
     np.testing.assert_allclose(b["out"], a["out"], rtol=1e-5, atol=1e-6)
     assert _rel_l2(b["dy0"], a["dy0"]) < 1e-3
