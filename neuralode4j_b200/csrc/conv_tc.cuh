@@ -103,9 +103,15 @@ struct ConvTcArgs {
     BnScratch pbn;        // statistics of that BatchNorm (mean, invstd, m_dy, m_dyxh)
     int pact;
     float* pcompact;      // optional: also store the produced tensor compactly (activation for the backward pass / gradient for wgrad)
+    // fused BatchNorm BACKWARD statistics in the epilogue (EPI == 2, dgrad launches): the output of this launch is the gradient
+    // w.r.t. the output of the BatchNorm layer in front of the conv; sums of dy and dy*xhat over the batch, last CTA writes
+    // dgamma / dbeta / mean(dy) / mean(dy*xhat) (same contract as k_bn_bwd_stats64).  `bn`, `bn_rows` describe that layer.
+    Ref ey, ex;           // its output (post activation) and its input, compact NHWC
+    int eact;             // its activation (ReLU or identity)
+    Ref edgamma, edbeta;
 };
 
-template <int PASSES, bool FUSE, int PRO>
+template <int PASSES, int EPI, int PRO>
 __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcArgs a) {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // dependents may be scheduled; they park in their own wait
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -299,7 +305,40 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             crow = ((long long)b * g.H + (ph - 1)) * g.W + (pw - 1);
         }
         float* __restrict__ out = resolve(a.out);
-        float* sT = reinterpret_cast<float*>(sW);      // [128][65] transpose buffer; the weight ring is idle once d_full fires
+        float* sT = reinterpret_cast<float*>(sW);      // [128][65] transpose buffer(s); the weight ring is idle once d_full fires
+        float* sT2 = sT + 128 * 65;
+        const int et = threadIdx.x - 64;               // 0..127
+        // EPI 2: while the tensor core works, fetch this pixel's row of the BatchNorm input / output and keep xhat and the
+        // activation mask in registers
+        float xh[EPI == 2 ? 64 : 1];
+        unsigned long long mask = 0ull;
+        if constexpr (EPI == 2) {
+            __shared__ float s_mi[128];
+            if (et < 64) s_mi[et] = a.bn.mean[et]; else s_mi[et] = a.bn.invstd[et - 64];
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool relu = a.eact == N4J_ACT_RELU;
+            mask = relu ? 0ull : ~0ull;
+            if (valid) {
+                const float4* __restrict__ xr = reinterpret_cast<const float4*>(resolve(a.ex) + crow * 64);
+                const float4* __restrict__ yr = reinterpret_cast<const float4*>(resolve(a.ey) + crow * 64);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 xv = xr[j];
+                    xh[4 * j + 0] = __fmul_rn(__fsub_rn(xv.x, s_mi[4 * j + 0]), s_mi[64 + 4 * j + 0]);
+                    xh[4 * j + 1] = __fmul_rn(__fsub_rn(xv.y, s_mi[4 * j + 1]), s_mi[64 + 4 * j + 1]);
+                    xh[4 * j + 2] = __fmul_rn(__fsub_rn(xv.z, s_mi[4 * j + 2]), s_mi[64 + 4 * j + 2]);
+                    xh[4 * j + 3] = __fmul_rn(__fsub_rn(xv.w, s_mi[4 * j + 3]), s_mi[64 + 4 * j + 3]);
+                    if (relu) {
+                        const float4 yv = yr[j];
+                        mask |= (unsigned long long)((yv.x > 0.f ? 1u : 0u) | (yv.y > 0.f ? 2u : 0u) | (yv.z > 0.f ? 4u : 0u) | (yv.w > 0.f ? 8u : 0u)) << (4 * j);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) xh[j] = 0.f;
+                mask = 0ull;
+            }
+        }
         tc::mbar_wait(d_full, 0);
         tc::tc_fence_after();
 #pragma unroll
@@ -317,17 +356,27 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
-            if constexpr (FUSE) {
+            if constexpr (EPI == 1) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sT[row * 65 + half * 32 + j] = valid ? v[j] : 0.f;
             }
+            if constexpr (EPI == 2) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    sT[row * 65 + half * 32 + j] = ((mask >> (half * 32 + j)) & 1ull) ? v[j] : 0.f;     // dy = act'(y) * g
+                    sT2[row * 65 + half * 32 + j] = xh[half * 32 + j];
+                }
+            }
         }
-        if constexpr (FUSE) {
+        if constexpr (EPI != 0) {
             asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
-            const int et = threadIdx.x - 64;                     // 0..127
             const int c = et & 63, r0 = (et >> 6) * 64;
             double s1 = 0.0, s2 = 0.0;
-            for (int r = r0; r < r0 + 64; ++r) { const double x = (double)sT[r * 65 + c]; s1 += x; s2 += x * x; }
+            if constexpr (EPI == 1) {
+                for (int r = r0; r < r0 + 64; ++r) { const double x = (double)sT[r * 65 + c]; s1 += x; s2 += x * x; }
+            } else {
+                for (int r = r0; r < r0 + 64; ++r) { const double dy = (double)sT[r * 65 + c]; s1 += dy; s2 += dy * (double)sT2[r * 65 + c]; }
+            }
             atomicAdd(a.bn.acc + c * ACC_STRIDE, s1);
             atomicAdd(a.bn.acc + (64 + c) * ACC_STRIDE, s2);
             __threadfence();
@@ -347,11 +396,19 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 if (a.bn.cm) comm_allreduce_epilogue(a.bn.cm, tot, 128, et);
                 const double Mt = a.bn.cm ? (double)a.bn.rows_total : (double)a.bn_rows;
                 if (et < 64) {
-                    const double mean = tot[et] / Mt;
-                    double var = tot[64 + et] / Mt - mean * mean;
-                    if (var < 0) var = 0;
-                    a.bn.mean[et] = (float)mean;
-                    a.bn.invstd[et] = (float)(1.0 / sqrt(var + (double)a.bn_eps));
+                    if constexpr (EPI == 1) {
+                        const double mean = tot[et] / Mt;
+                        double var = tot[64 + et] / Mt - mean * mean;
+                        if (var < 0) var = 0;
+                        a.bn.mean[et] = (float)mean;
+                        a.bn.invstd[et] = (float)(1.0 / sqrt(var + (double)a.bn_eps));
+                    } else {
+                        const double sdy = tot[et], sdyxh = tot[64 + et];
+                        resolve(a.edgamma)[et] = (float)sdyxh;
+                        resolve(a.edbeta)[et] = (float)sdy;
+                        a.bn.m_dy[et] = (float)(sdy / Mt);
+                        a.bn.m_dyxh[et] = (float)(sdyxh / Mt);
+                    }
                 }
                 if (et == 0) *a.bn.ticket = 0u;
             }

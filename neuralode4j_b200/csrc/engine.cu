@@ -37,7 +37,7 @@ static inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     } while (0)
 
 static inline long long round_up4(long long n) { return (n + 3) & ~3LL; }
-template <int PRO> static void set_conv_smem(size_t smem);
+static void set_conv_smem_all(size_t smem);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -221,7 +221,7 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
                 N4J_CUDA(cudaMemsetAsync(l.gimg, 0, img_bytes, stream_));
                 N4J_CUDA(cudaMalloc(&l.wimg_f, sizeof(float) * 9 * 2 * 4096));
                 N4J_CUDA(cudaMalloc(&l.wimg_b, sizeof(float) * 9 * 2 * 4096));
-                set_conv_smem<0>(conv_smem_); set_conv_smem<1>(conv_smem_); set_conv_smem<2>(conv_smem_);
+                set_conv_smem_all(conv_smem_);
                 side_capable_ = true;
                 wgrad_smem_ = conv_wgrad_smem_bytes(geom_);
                 if (wgrad_smem_ > 200 * 1024) throw Error{N4J_ERR_UNSUPPORTED, "feature map too large for the native conv weight-gradient kernel"};
@@ -440,37 +440,44 @@ void Engine::launch_gemm_tc(cudaStream_t s, const CUtensorMap& ta, const CUtenso
     ++launches_;
 }
 
-template <int PRO>
-static void launch_conv_variant(const ConvTcArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, bool fast, bool fuse) {
-    if (fuse) {
-        if (fast) launch_k(k_conv3x3_tc<1, true, PRO>, grid, block, smem, s, pdl, a);
-        else launch_k(k_conv3x3_tc<3, true, PRO>, grid, block, smem, s, pdl, a);
-    } else {
-        if (fast) launch_k(k_conv3x3_tc<1, false, PRO>, grid, block, smem, s, pdl, a);
-        else launch_k(k_conv3x3_tc<3, false, PRO>, grid, block, smem, s, pdl, a);
-    }
+template <int PRO, int EPI>
+static void launch_conv_variant(const ConvTcArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, bool fast) {
+    if (fast) launch_k(k_conv3x3_tc<1, EPI, PRO>, grid, block, smem, s, pdl, a);
+    else launch_k(k_conv3x3_tc<3, EPI, PRO>, grid, block, smem, s, pdl, a);
 }
-template <int PRO>
+template <int PRO, int EPI>
 static void set_conv_smem(size_t smem) {
-    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, true, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, true, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, false, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, false, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, EPI, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, EPI, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+}
+// the (prologue, epilogue) combinations the engine launches: forward convs take PRO 0/1 with EPI 0/1, dgrad convs PRO 0/2 with EPI 0/2
+static void set_conv_smem_all(size_t smem) {
+    set_conv_smem<0, 0>(smem); set_conv_smem<0, 1>(smem); set_conv_smem<1, 0>(smem); set_conv_smem<1, 1>(smem);
+    set_conv_smem<0, 2>(smem); set_conv_smem<2, 0>(smem); set_conv_smem<2, 2>(smem);
 }
 
-// pro/pro_kind: fused operand prologue (1 = BatchNorm apply in front of a forward conv, 2 = BatchNorm backward in front of a dgrad)
+// pro_kind: fused operand prologue (1 = BatchNorm apply in front of a forward conv, 2 = BatchNorm backward in front of a dgrad)
+// epi_kind: fused epilogue statistics (1 = forward statistics for next_bn, 2 = backward statistics of the BatchNorm in front, fields in *extra)
 void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act, const LayerPlan* next_bn,
-                            const ConvTcArgs* pro, int pro_kind) {
+                            const ConvTcArgs* extra, int pro_kind, int epi_kind) {
     ConvTcArgs a{};
-    if (pro) a = *pro;
+    if (extra) a = *extra;
     a.img = img; a.wimg = wimg; a.out = out; a.g = geom_; a.act = act;
-    a.fuse_stats = next_bn ? 1 : 0;
-    if (next_bn) { a.bn = next_bn->bn; a.bn_eps = next_bn->d.eps; a.bn_rows = next_bn->rows; }
+    if (next_bn) { epi_kind = 1; a.bn = next_bn->bn; a.bn_eps = next_bn->d.eps; a.bn_rows = next_bn->rows; }
+    a.fuse_stats = epi_kind;
     const bool fast = (cfg_.flags & N4J_FLAG_FAST_TF32) != 0;
     const dim3 grid(geom_.tiles), block(conv_tc_threads(pro_kind));
-    if (pro_kind == 1) launch_conv_variant<1>(a, grid, block, conv_smem_, s, pdl_, fast, next_bn != nullptr);
-    else if (pro_kind == 2) launch_conv_variant<2>(a, grid, block, conv_smem_, s, pdl_, fast, next_bn != nullptr);
-    else launch_conv_variant<0>(a, grid, block, conv_smem_, s, pdl_, fast, next_bn != nullptr);
+    const int combo = pro_kind * 3 + epi_kind;
+    switch (combo) {
+        case 0: launch_conv_variant<0, 0>(a, grid, block, conv_smem_, s, pdl_, fast); break;
+        case 1: launch_conv_variant<0, 1>(a, grid, block, conv_smem_, s, pdl_, fast); break;
+        case 2: launch_conv_variant<0, 2>(a, grid, block, conv_smem_, s, pdl_, fast); break;
+        case 3: launch_conv_variant<1, 0>(a, grid, block, conv_smem_, s, pdl_, fast); break;
+        case 4: launch_conv_variant<1, 1>(a, grid, block, conv_smem_, s, pdl_, fast); break;
+        case 6: launch_conv_variant<2, 0>(a, grid, block, conv_smem_, s, pdl_, fast); break;
+        case 8: launch_conv_variant<2, 2>(a, grid, block, conv_smem_, s, pdl_, fast); break;
+        default: throw Error{N4J_ERR_ILLEGAL_STATE, "conv kernel variant not instantiated"};
+    }
     ++launches_;
 }
 
@@ -591,6 +598,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
     bool bpro_pending = false;   // ... or left its backward to the dgrad kernel's operand prologue
     ConvTcArgs bpro_args{};
     bool forked = false;
+    bool bstats_ready = false;   // the dgrad kernel behind this BatchNorm already reduced its backward statistics (EPI 2)
     for (int i = last; i >= 0; --i) {
         LayerPlan& l = L_[i];
         Ref x = i == 0 ? in : fixed_ref(L_[i - 1].act);
@@ -603,7 +611,9 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
             case N4J_LAYER_BATCHNORM: {
                 const int cc = l.c_out;
                 int grid = (cc <= 256 && 256 % cc == 0) ? (int)std::max<long long>(1, std::min<long long>(74, (l.rows + 4 * (256 / cc) - 1) / (4 * (256 / cc)))) : 74;
-                if (cc == 64) {
+                if (bstats_ready) {
+                    bstats_ready = false;
+                } else if (cc == 64) {
                     const int g64 = (int)std::max<long long>(1, std::min<long long>(148, (l.rows + 15) / 16));
                     LAUNCH(k_bn_bwd_stats64, g64, 256, s, g, gscale, y, x, l.bn, l.d.activation, l.rows, dth, with_off(dth, cc),
                            params_.p + l.p_off, params_.p + l.p_off + cc, (i == last && fwd_left_last_bn_) ? 1 : 0);
@@ -675,7 +685,23 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     // dgrad on the main chain.  With the fused prologue the dgrad kernel also materialises `d` (the BatchNorm
                     // backward of the layer behind this conv) compactly, so the weight gradient forks AFTER it.
                     if (!gimg_ready) LAUNCH(k_compact_to_image, grid_for(l.out_len / 4), 256, s, d, geom_, l.gimg);
-                    launch_conv_tc(s, l.gimg, l.wimg_b, dx, N4J_ACT_IDENTITY, nullptr, bpro_pending ? &bpro_args : nullptr, bpro_pending ? 2 : 0);
+                    // ... and, when a 64-channel BatchNorm sits in front of the conv, its backward statistics in the epilogue
+                    int epi = 0;
+                    if (i > 0 && !(cfg_.flags & N4J_FLAG_NO_BWD_STATS_FUSION)) {
+                        const LayerPlan& b = L_[i - 1];
+                        if (b.d.kind == N4J_LAYER_BATCHNORM && b.c_out == 64 && (b.d.activation == N4J_ACT_RELU || b.d.activation == N4J_ACT_IDENTITY)) {
+                            if (!bpro_pending) bpro_args = ConvTcArgs{};
+                            bpro_args.ey = fixed_ref(b.act);                        // i - 1 < last: its output is a saved activation
+                            bpro_args.ex = i - 1 == 0 ? in : fixed_ref(L_[i - 2].act);
+                            bpro_args.eact = b.d.activation;
+                            bpro_args.edgamma = with_off(out, off_theta_ + b.g_off);
+                            bpro_args.edbeta = with_off(out, off_theta_ + b.g_off + 64);
+                            bpro_args.bn = b.bn; bpro_args.bn_rows = b.rows;
+                            epi = 2;
+                            bstats_ready = true;
+                        }
+                    }
+                    launch_conv_tc(s, l.gimg, l.wimg_b, dx, N4J_ACT_IDENTITY, nullptr, (bpro_pending || epi) ? &bpro_args : nullptr, bpro_pending ? 2 : 0, epi);
                     bpro_pending = false;
                     // weight gradient on the side branch (fork)
                     cudaEvent_t ef = ev_pool_[(ev_next_++) % EV_POOL];

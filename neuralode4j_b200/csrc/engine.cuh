@@ -169,7 +169,7 @@ private:
     void join_side(cudaStream_t s);
     void launch_gemm_tc(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& a);
     void launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act, const LayerPlan* next_bn = nullptr,
-                        const ConvTcArgs* pro = nullptr, int pro_kind = 0);
+                        const ConvTcArgs* extra = nullptr, int pro_kind = 0, int epi_kind = 0);
     void enqueue_rhs(cudaStream_t s, bool aug, Ref in, Ref out, bool bn1_ready = false) {
         aug ? enqueue_rhs_aug(s, in, out, bn1_ready) : enqueue_rhs_fwd(s, in, out, false, bn1_ready);
     }

@@ -52,10 +52,10 @@ static int run(int B, int H, int W, int mode) {
     ConvTcArgs a{};
     a.img = dimg; a.wimg = dwimg; a.out = fixed_ref(dout); a.g = g; a.act = 0; a.fuse_stats = 0;
     const size_t smem = conv_tc_smem_bytes(g);
-    CK(cudaFuncSetAttribute(k_conv3x3_tc<3, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_conv3x3_tc<1, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k_conv3x3_tc<0, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_conv3x3_tc<3, false, 0><<<g.tiles, CONV_TC_THREADS, smem>>>(a);
+    CK(cudaFuncSetAttribute(k_conv3x3_tc<3, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_conv3x3_tc<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k_conv3x3_tc<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_conv3x3_tc<3, 0, 0><<<g.tiles, CONV_TC_THREADS, smem>>>(a);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost));
     double maxerr = 0, maxref = 0;
@@ -69,19 +69,19 @@ static int run(int B, int H, int W, int mode) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     const int iters = 100;
     float ms = 0, ms1 = 0, ms0 = 0, msE = 0;
-    for (int i = 0; i < 5; ++i) k_conv3x3_tc<3, false, 0><<<g.tiles, CONV_TC_THREADS, smem>>>(a);
+    for (int i = 0; i < 5; ++i) k_conv3x3_tc<3, 0, 0><<<g.tiles, CONV_TC_THREADS, smem>>>(a);
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) k_conv3x3_tc<3, false, 0><<<g.tiles, CONV_TC_THREADS, smem>>>(a);
+    for (int i = 0; i < iters; ++i) k_conv3x3_tc<3, 0, 0><<<g.tiles, CONV_TC_THREADS, smem>>>(a);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) k_conv3x3_tc<1, false, 0><<<g.tiles, CONV_TC_THREADS, smem>>>(a);
+    for (int i = 0; i < iters; ++i) k_conv3x3_tc<1, 0, 0><<<g.tiles, CONV_TC_THREADS, smem>>>(a);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms1, e0, e1);
     cudaEventRecord(e0);
-    for (int i = 0; i < iters; ++i) k_conv3x3_tc<0, false, 0><<<g.tiles, CONV_TC_THREADS, smem>>>(a);
+    for (int i = 0; i < iters; ++i) k_conv3x3_tc<0, 0, 0><<<g.tiles, CONV_TC_THREADS, smem>>>(a);
     cudaEventRecord(e1);
     CK(cudaDeviceSynchronize());
     cudaEventElapsedTime(&ms0, e0, e1);
