@@ -52,7 +52,19 @@ enum {
 };
 
 /* ---- inner graph description (what OdeVertex.Builder assembled; chain of DL4J layers) ---------- */
-enum { N4J_LAYER_DENSE = 1, N4J_LAYER_CONV3X3 = 2, N4J_LAYER_BATCHNORM = 3, N4J_LAYER_ACTIVATION = 4 };
+enum {
+    N4J_LAYER_DENSE = 1,
+    N4J_LAYER_CONV3X3 = 2,
+    N4J_LAYER_BATCHNORM = 3,
+    N4J_LAYER_ACTIVATION = 4,
+    /* Time-dependent f: the reference's "timeConc" first vertex, ShapeMatchVertex(MergeVertex, {1: n_out}) fed by
+     * TimeInput (ode/vertex/conf/OdeVertex.java:251, ode/vertex/impl/ShapeMatchVertex.java:50-79,
+     * ode/vertex/impl/helper/TimeInput.java:27-50): n_out channels (features) holding the solver's current time are
+     * appended to the state along dimension 1.  Only valid as layer 0.  The adjoint's time slot then carries
+     * -a^T df/dt (TimeInput.update), and the reference's stage-time quirk (every stage is evaluated at t+h,
+     * FirstOrderEquationWithState.java:45,82) becomes observable; N4J_FLAG_EXACT_STAGE_TIMES selects t+c_s*h instead. */
+    N4J_LAYER_TIME_CONCAT = 5
+};
 enum { N4J_ACT_IDENTITY = 0, N4J_ACT_RELU = 1, N4J_ACT_ELU = 2, N4J_ACT_TANH = 3 };
 
 typedef struct n4j_layer_desc {
@@ -168,6 +180,8 @@ int64_t node4j_get_step_log(n4j_handle* h, n4j_step_rec* buf, int64_t cap);
  * realGradientView order. */
 int32_t node4j_rhs(n4j_handle* h, const float* z, float t, float* fz);
 int32_t node4j_rhs_vjp(n4j_handle* h, const float* z, float t, const float* g, float* fz, float* dz, float* dreal);
+/* Same, and also g^T df/dt, the epsilon of the time input (TimeInput.java:46-50); 0 for graphs without a time vertex. */
+int32_t node4j_rhs_vjp_time(n4j_handle* h, const float* z, float t, const float* g, float* fz, float* dz, float* dreal, float* dt);
 
 /* DormandPrince54Mse.estimateMse (solve/impl/DormandPrince54Solver.java:78-93) on caller data: K is [7,n]
  * row-major.  Exposed for the unit pins of the solver kernels and for bandwidth measurements. */

@@ -13,7 +13,7 @@ from . import build as _build
 
 N4J_OK, ERR_INVALID_ARGUMENT, ERR_ILLEGAL_STATE, ERR_UNSUPPORTED, ERR_CUDA, ERR_MAX_STEPS, ERR_COMM = range(7)
 
-LAYER_DENSE, LAYER_CONV3X3, LAYER_BATCHNORM, LAYER_ACTIVATION = 1, 2, 3, 4
+LAYER_DENSE, LAYER_CONV3X3, LAYER_BATCHNORM, LAYER_ACTIVATION, LAYER_TIME_CONCAT = 1, 2, 3, 4, 5
 ACT = {"identity": 0, "relu": 1, "elu": 2, "tanh": 3}
 FLAG_EXACT_STAGE_TIMES, FLAG_NO_GRAPH, FLAG_FAST_TF32, FLAG_EXACT_CONTRACTIONS, FLAG_NO_TENSOR, FLAG_NO_PDL, FLAG_FORCE_TENSOR, FLAG_NO_PROLOGUE_FUSION, FLAG_NO_BWD_STATS_FUSION = 1, 2, 4, 8, 16, 32, 64, 128, 256
 TIMEGRAD_NONE, TIMEGRAD_ZERO, TIMEGRAD_CALC = 0, 1, 2
@@ -21,7 +21,7 @@ TIMEGRAD_NONE, TIMEGRAD_ZERO, TIMEGRAD_CALC = 0, 1, 2
 EXPORTS = [
     "node4j_abi_version", "node4j_last_error", "node4j_device_count", "node4j_create", "node4j_destroy",
     "node4j_num_params", "node4j_num_real_params", "node4j_state_len", "node4j_bind_params", "node4j_forward",
-    "node4j_backward", "node4j_get_step_log", "node4j_rhs", "node4j_rhs_vjp", "node4j_error_norm",
+    "node4j_backward", "node4j_get_step_log", "node4j_rhs", "node4j_rhs_vjp", "node4j_rhs_vjp_time", "node4j_error_norm",
     "node4j_comm_init", "node4j_comm_export", "node4j_bench_solver_pass", "node4j_bench_piece", "node4j_get_stream",
 ]
 BENCH_RHS_FWD, BENCH_RHS_AUG, BENCH_CONV_FWD, BENCH_CONV_DGRAD, BENCH_CONV_WGRAD = 1, 2, 3, 4, 5
@@ -99,6 +99,8 @@ def load():
     L.node4j_rhs.argtypes = [vp, vp, f32, vp]
     L.node4j_rhs_vjp.restype = i32
     L.node4j_rhs_vjp.argtypes = [vp, vp, f32, vp, vp, vp, vp]
+    L.node4j_rhs_vjp_time.restype = i32
+    L.node4j_rhs_vjp_time.argtypes = [vp, vp, f32, vp, vp, vp, vp, C.POINTER(C.c_float)]
     L.node4j_error_norm.restype = i32
     L.node4j_error_norm.argtypes = [vp, vp, vp, vp, f32, i64, C.POINTER(f32)]
     L.node4j_comm_init.restype = i32

@@ -290,7 +290,7 @@ class Layer:
 
     def spec(self) -> dict:
         """Plain description (what tests hand to the oracle)."""
-        kind = {1: "dense", 2: "conv3x3", 3: "batchnorm", 4: "activation"}[self.kind]
+        kind = {1: "dense", 2: "conv3x3", 3: "batchnorm", 4: "activation", 5: "time_concat"}[self.kind]
         return {"kind": kind, "n_in": self.nIn, "n_out": self.nOut, "activation": self.activation,
                 "has_bias": self.hasBias, "eps": self.eps}
 
@@ -313,3 +313,35 @@ def BatchNormalization(nOut: int = 0, activation: str = "identity", eps: float =
 
 def ActivationLayer(activation: str) -> Layer:
     return Layer(_lib.LAYER_ACTIVATION, 0, 0, activation, False)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# time as input to the inner graph: the reference's "timeConc" first vertex
+# ----------------------------------------------------------------------------------------------------------
+class MergeVertex:
+    """org.deeplearning4j.nn.conf.graph.MergeVertex: concatenation along dimension 1 (the only vertex ShapeMatchVertex wraps natively)."""
+
+    def __eq__(self, o):
+        return isinstance(o, MergeVertex)
+
+
+class ShapeMatchVertex:
+    """ode.vertex.conf.ShapeMatchVertex (ShapeMatchVertex.java:35-50): duplicates the LAST input (the solver's current time) to the
+    shape of the first one, with the sizes in ``overrideSizeDims`` replaced, and hands all inputs to the wrapped vertex.
+    ``ShapeMatchVertex(MergeVertex())`` defaults to ``{1: 1}`` (one time channel / feature), the cifar10 block uses ``{1: 10}``
+    (examples/cifar10/OdeBlockTime.java:38)."""
+
+    def __init__(self, graphVertex, overrideSizeDims=None):
+        if not isinstance(graphVertex, MergeVertex):
+            # ShapeMatchVertex(ElementWiseVertex ...) etc. exist in the reference; only the merge is in the native set
+            raise NotImplementedError("only ShapeMatchVertex(MergeVertex) is in the native set")
+        self.graphVertex = graphVertex
+        self.overrideSizeDims = {1: 1} if overrideSizeDims is None else {int(k): int(v) for k, v in overrideSizeDims.items()}
+        if set(self.overrideSizeDims) != {1} or self.overrideSizeDims[1] < 1:
+            raise NotImplementedError("the native time merge overrides the size of dimension 1 only")
+
+    def __eq__(self, o):
+        return isinstance(o, ShapeMatchVertex) and self.overrideSizeDims == o.overrideSizeDims
+
+    def layer(self) -> Layer:
+        return Layer(_lib.LAYER_TIME_CONCAT, 0, self.overrideSizeDims[1], "identity", False)

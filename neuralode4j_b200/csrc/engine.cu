@@ -141,8 +141,16 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
             case N4J_LAYER_ACTIVATION:
                 lp.c_out = c; lp.p_len = 0; lp.g_len = 0;
                 break;
+            case N4J_LAYER_TIME_CONCAT:
+                // OdeVertex.Builder(conf, name, vertex, addTimeAsInput = true, ...): only the first vertex is fed the time
+                if (i != 0) throw Error{N4J_ERR_UNSUPPORTED, "time concat is only supported as the first vertex of the inner graph"};
+                if (lp.d.n_out <= 0) lp.d.n_out = 1;       // ShapeMatchVertex(MergeVertex): overrideSizeDims {1: 1}
+                lp.d.n_in = c; lp.d.activation = N4J_ACT_IDENTITY;
+                lp.c_out = c + (int)lp.d.n_out; lp.p_len = 0; lp.g_len = 0;
+                time_input_ = true;
+                break;
             default:
-                throw Error{N4J_ERR_UNSUPPORTED, "layer kind outside the native set {Dense, Convolution2D 3x3 same, BatchNormalization, Activation}"};
+                throw Error{N4J_ERR_UNSUPPORTED, "layer kind outside the native set {Dense, Convolution2D 3x3 same, BatchNormalization, Activation, time concat}"};
         }
         lp.in_len = rows * lp.c_in;
         lp.out_len = rows * lp.c_out;
@@ -192,6 +200,10 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
     N4J_CUDA(cudaMalloc(&dot_acc_, sizeof(double)));
     N4J_CUDA(cudaMemsetAsync(dot_acc_, 0, sizeof(double), stream_));
     N4J_CUDA(cudaMalloc(&tg_, sizeof(float) * 4));
+    N4J_CUDA(cudaMalloc(&tcat_acc_, sizeof(double) * ACC_SLOTS * ACC_STRIDE));
+    N4J_CUDA(cudaMemsetAsync(tcat_acc_, 0, sizeof(double) * ACC_SLOTS * ACC_STRIDE, stream_));
+    N4J_CUDA(cudaMalloc(&tcat_misc_, 16));      // [0]: ticket, [1]: last g^T df/dt
+    N4J_CUDA(cudaMemsetAsync(tcat_misc_, 0, 16, stream_));
     ensure(params_, std::max<long long>(n_params_, 1));
     ensure(gradflat_, std::max<long long>(n_params_, 1));
     ensure(theta_tmp_, std::max<long long>(real_pad_, 4));
@@ -284,7 +296,7 @@ Engine::~Engine() {
     for (DevBuf* b : {&params_, &gradflat_, &zt_, &gt_, &io_, &io2_, &gb_[0], &gb_[1], &gb_[2], &theta_tmp_, &wpart_, &dldt_}) cudaFree(b->p);
     for (void* pp : peer_ptrs_) cudaIpcCloseMemHandle(pp);
     cudaFree(comm_region_); cudaFree(comm_dev_);
-    cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(red_acc_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_);
+    cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(red_acc_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_); cudaFree(tcat_acc_); cudaFree(tcat_misc_);
     cudaFreeHost(ctrl_host_); cudaFreeHost(tpair_host_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -508,6 +520,9 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                 }
                 break;
             }
+            case N4J_LAYER_TIME_CONCAT:
+                LAUNCH(k_time_concat_fwd, grid_for(l.out_len), 256, s, ctrl_, tspec_, cur, dst, l.rows, l.c_in, l.c_out - l.c_in);
+                break;
             case N4J_LAYER_CONV3X3: {
                 if (l.tc) {
                     if (!image_ready) LAUNCH(k_compact_to_image, grid_for(l.in_len / 4), 256, s, cur, geom_, l.img);
@@ -640,6 +655,13 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
             case N4J_LAYER_ACTIVATION:
                 LAUNCH(k_act_bwd, grid_for(l.out_len), 256, s, g, gscale, y, l.d.activation, dx, l.out_len);
                 break;
+            case N4J_LAYER_TIME_CONCAT:
+                // TimeInput.update (TimeInput.java:46-50): the state part is the z-adjoint derivative, the summed time part the
+                // derivative of the time slot (dropped when the solve carries none: NoTimeGrad's empty tAdjoint)
+                LAUNCH(k_time_concat_bwd, (int)std::min<long long>(grid_red(l.out_len / 4 + 1), 148), 256, s, g, gscale, dx, l.rows, l.c_in,
+                       l.c_out - l.c_in, tcat_acc_, reinterpret_cast<unsigned int*>(tcat_misc_), comm_dev_, tcat_misc_ + 1,
+                       with_off(out, off_t_), aug_tslot_ ? 1 : 0);
+                break;
             case N4J_LAYER_DENSE:
             case N4J_LAYER_CONV3X3: {
                 Ref d = g;
@@ -751,10 +773,12 @@ void Engine::enqueue_prologue(cudaStream_t s, bool aug, long long n4, const Solv
     Ref ywork{Y_, &ctrl_->y_cur, n_alloc_, 0, 1};
     LAUNCH(k_solve_begin, 1, 32, s, ctrl_, tpair_);
     if (dense_out) LAUNCH(k_dense_edge, grid_for(nz_), 256, s, ctrl_, Y_, n_alloc_, nz_, wanted_, 0, 0, zt_.p + nz_, nz_);
+    tspec_ = TimeSpec{0, 0.f, 0.f};                                                  // time + timeOffset(0)
     enqueue_rhs(s, aug, ycur, Ref{K_, &ctrl_->krow[0], n_alloc_, 0, 0});            // AdaptiveRungeKuttaSolver.java:131
     LAUNCH(k_init_sums, grid_red(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp);
     const BnFuse bf = bn_fuse();
     LAUNCH(k_stage_combine<0>, bf.enabled ? grid_red(n4) : grid_for(n4), 256, s, ctrl_, Y_, K_, n_alloc_, 0LL, n4, bf);  // equation.step(ones(1), step)
+    tspec_ = TimeSpec{1, 0.f, 0.f};                                                  // timeOffset = the first guess (equation.step above)
     enqueue_rhs(s, aug, ywork, Ref{K_, &ctrl_->krow[1], n_alloc_, 0, 0}, bf.enabled != 0);   // policy :112
     LAUNCH(k_init_final, grid_red(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp, (cudaGraphConditionalHandle)0, 0);
     (void)nt;
@@ -786,6 +810,10 @@ void Engine::enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverP
             case 6: launch_combine<6>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
         }
         ++launches_;
+        // quirk A.3: State.step stores the FULL step in timeOffset, so every stage is evaluated at t + h
+        // (FirstOrderEquationWithState.java:45,82); N4J_FLAG_EXACT_STAGE_TIMES uses the tableau's c_s instead
+        static const double kC[6] = {1.0 / 5.0, 3.0 / 10.0, 4.0 / 5.0, 8.0 / 9.0, 1.0, 1.0};
+        tspec_ = (cfg_.flags & N4J_FLAG_EXACT_STAGE_TIMES) ? TimeSpec{2, (float)kC[st - 1], 0.f} : TimeSpec{1, 0.f, 0.f};
         if (aug) enqueue_rhs_aug(s, ywork, Ref{K_, &ctrl_->krow[st], n_alloc_, 0, 0}, bf.enabled != 0, st & 1, split);
         else enqueue_rhs_fwd(s, ywork, Ref{K_, &ctrl_->krow[st], n_alloc_, 0, 0}, false, bf.enabled != 0);
     }
@@ -807,6 +835,7 @@ SolveGraph& Engine::get_graph(bool aug, int tslot, bool dense_out, int nt) {
     const long long key = (aug ? 1 : 0) | (tslot ? 2 : 0) | (dense_out ? 4 : 0) | ((long long)(dense_out ? nt : 0) << 8);
     auto it = graphs_.find(key);
     if (it != graphs_.end()) return it->second;
+    aug_tslot_ = tslot != 0;
     SolveGraph sg;
     const long long n4 = (aug ? n_alloc_ : nz_pad_) / 4;
     const long long n_norm = aug ? (2 * nz_ * world_ + n_params_ + (tslot ? 1 : 0)) : nz_ * world_;
@@ -874,6 +903,7 @@ void Engine::run_solve(bool aug, int tslot, bool dense_out, int nt) {
         return;
     }
     // debug path: the host drives the loop and reads `done` after every trial
+    aug_tslot_ = tslot != 0;
     const long long n4 = (aug ? n_alloc_ : nz_pad_) / 4;
     const long long n_norm = aug ? (2 * nz_ * world_ + n_params_ + (tslot ? 1 : 0)) : nz_ * world_;
     SolverParams sp = solver_params(n_norm);
@@ -1158,6 +1188,7 @@ void Engine::backward(const float* last_output, const float* dLdz, const float* 
         const float* g_k = gt_.p + slice * nz_;
         if (tg) {
             // d = <dL/dz(t_step) raw, f(z(t_step), t_step)>: one extra RHS evaluation
+            tspec_ = TimeSpec{3, 0.f, th[step]};      // CalcTimeGrad.java:52: calculateDerivative(zt1, time.getColumn(1), ...)
             enqueue_rhs_fwd(stream_, fixed_ref(const_cast<float*>(z_k)), fixed_ref(gb_[2].p));
             LAUNCH(k_dot, grid_for(nz_), 256, stream_, g_k, gb_[2].p, nz_, dot_acc_);
             LAUNCH(k_tg_step, 1, 32, stream_, ctrl_, dot_acc_, tg_, Y_, n_alloc_, off_t_, dldt_.p, step, 0);
@@ -1203,13 +1234,14 @@ long long Engine::get_step_log(n4j_step_rec* buf, long long cap) {
 // =====================================================================================================
 // RHS on its own, error norm on caller data, solver-pass microbenchmark
 // =====================================================================================================
-void Engine::rhs(const float* z, float, float* fz) {
+void Engine::rhs(const float* z, float t, float* fz) {
     N4J_CUDA(cudaSetDevice(device_));
     t_pdl = pdl_;
     launches_ = 0;
     upload_params();
     ensure(io_, nz_);
     state_in(z, gb_[0].p);
+    tspec_ = TimeSpec{3, 0.f, t};
     enqueue_rhs_fwd(stream_, fixed_ref(gb_[0].p), fixed_ref(gb_[1].p));
     const bool dev = is_device_ptr(fz);
     float* o = dev ? fz : io_.p;
@@ -1218,7 +1250,7 @@ void Engine::rhs(const float* z, float, float* fz) {
     N4J_CUDA(cudaStreamSynchronize(stream_));
 }
 
-void Engine::rhs_vjp(const float* z, float, const float* g, float* fz, float* dz, float* dreal) {
+void Engine::rhs_vjp(const float* z, float t, const float* g, float* fz, float* dz, float* dreal, float* dt) {
     N4J_CUDA(cudaSetDevice(device_));
     reset_ctrl();
     upload_params();
@@ -1228,6 +1260,8 @@ void Engine::rhs_vjp(const float* z, float, const float* g, float* fz, float* dz
     state_in(z, Y_);
     state_in(g, gb_[0].p);
     LAUNCH(k_act_bwd, grid_for(nz_), 256, stream_, fixed_ref(gb_[0].p), -1.f, fixed_ref(gb_[0].p), (int)N4J_ACT_IDENTITY, fixed_ref(Y_ + off_a_), nz_);
+    tspec_ = TimeSpec{3, 0.f, t};
+    aug_tslot_ = false;
     enqueue_rhs_aug(stream_, fixed_ref(Y_), fixed_ref(K_));
     auto emit = [&](const float* internal, float* user) {
         const bool dev = is_device_ptr(user);
@@ -1240,6 +1274,9 @@ void Engine::rhs_vjp(const float* z, float, const float* g, float* fz, float* dz
     if (n_real_ > 0) {
         theta_internal_to_real(K_ + off_theta_, theta_tmp_.p);
         from_device(dreal, theta_tmp_.p, n_real_);
+    }
+    if (dt) {
+        if (time_input_) from_device(dt, tcat_misc_ + 1, 1); else *dt = 0.f;
     }
     N4J_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -1432,7 +1469,10 @@ int32_t node4j_rhs(n4j_handle* h, const float* z, float t, float* fz) {
     return guarded([&] { h->eng->rhs(z, t, fz); });
 }
 int32_t node4j_rhs_vjp(n4j_handle* h, const float* z, float t, const float* g, float* fz, float* dz, float* dreal) {
-    return guarded([&] { h->eng->rhs_vjp(z, t, g, fz, dz, dreal); });
+    return guarded([&] { h->eng->rhs_vjp(z, t, g, fz, dz, dreal, nullptr); });
+}
+int32_t node4j_rhs_vjp_time(n4j_handle* h, const float* z, float t, const float* g, float* fz, float* dz, float* dreal, float* dt) {
+    return guarded([&] { h->eng->rhs_vjp(z, t, g, fz, dz, dreal, dt); });
 }
 int32_t node4j_error_norm(n4j_handle* h, const float* K, const float* y0, const float* y1, float step, int64_t n, float* err_out) {
     return guarded([&] { h->eng->error_norm(K, y0, y1, step, n, err_out); });

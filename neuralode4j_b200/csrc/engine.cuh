@@ -75,7 +75,7 @@ public:
                   float* dLdy0, float* dLdt, n4j_stats* st);
     long long get_step_log(n4j_step_rec* buf, long long cap);
     void rhs(const float* z, float t, float* fz);
-    void rhs_vjp(const float* z, float t, const float* g, float* fz, float* dz, float* dreal);
+    void rhs_vjp(const float* z, float t, const float* g, float* fz, float* dz, float* dreal, float* dt);
     void error_norm(const float* K, const float* y0, const float* y1, float step, long long n, float* err_out);
     void bench_solver_pass(long long n, int iters, float* us);
     void bench_piece(int what, int iters, float* us);
@@ -138,6 +138,12 @@ private:
     float* wanted_ = nullptr;     // requested times (device)
     int wanted_cap_ = 0;
     double* dot_acc_ = nullptr;
+    // time input (N4J_LAYER_TIME_CONCAT)
+    bool time_input_ = false;
+    bool aug_tslot_ = false;      // the adjoint solve being enqueued carries a time slot (CalcTimeGrad)
+    TimeSpec tspec_{0, 0.f, 0.f}; // how the RHS evaluation being enqueued derives its time from the control block
+    double* tcat_acc_ = nullptr;
+    float* tcat_misc_ = nullptr;  // [0] ticket (as unsigned), [1] last g^T df/dt
     float* tg_ = nullptr;         // [0]=lastTime (CalcMultiStepTimeGrad.java:18), [1]=current d
     DevBuf params_, gradflat_, zt_, gt_, io_, io2_, gb_[3], theta_tmp_, wpart_, dldt_;
     const float* user_params_ = nullptr;

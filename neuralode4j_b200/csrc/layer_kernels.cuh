@@ -133,6 +133,64 @@ __global__ void __launch_bounds__(256) k_act_bwd(Ref gin, float gscale, Ref yref
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Time input: the reference's "timeConc" first vertex, ShapeMatchVertex(MergeVertex) fed by TimeInput
+// (ode/vertex/impl/ShapeMatchVertex.java:50-79, util/preproc/DuplicateScalarToShape.java:41-60,
+// ode/vertex/impl/helper/TimeInput.java:27-50): k channels holding the current time are appended to every row.
+// The time of an evaluation is derived on the device from the control block, the way the reference derives it
+// from `time.add(state.timeOffset)` (FirstOrderEquationWithState.java:78-85).
+// ---------------------------------------------------------------------------------------------------
+struct TimeSpec {
+    int mode;      // 0: t   1: t + h (every stage, quirk A.3)   2: t + coef*h (N4J_FLAG_EXACT_STAGE_TIMES)   3: value
+    float coef;
+    float value;
+};
+__device__ __forceinline__ float eval_time(const Ctrl* c, const TimeSpec& ts) {
+    switch (ts.mode) {
+        case 0: return c->t;
+        case 1: return __fadd_rn(c->t, c->h);
+        case 2: return __fadd_rn(c->t, __fmul_rn(ts.coef, c->h));
+        default: return ts.value;
+    }
+}
+// out[r][0:C] = in[r][0:C];  out[r][C:C+k] = t
+__global__ void __launch_bounds__(256) k_time_concat_fwd(const Ctrl* c, TimeSpec ts, Ref xin, Ref yout, long long rows, int C, int k) {
+    pdl_begin();
+    const float* __restrict__ x = resolve(xin);
+    float* __restrict__ y = resolve(yout);
+    const float t = eval_time(c, ts);
+    const int Co = C + k;
+    const long long n = rows * Co;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const long long r = i / Co;
+        const int ch = (int)(i - r * Co);
+        y[i] = ch < C ? x[r * C + ch] : t;
+    }
+}
+// dx[r][0:C] = gscale*g[r][0:C];  dt = sum_r sum_{j<k} gscale*g[r][C+j]  (DuplicateScalarToShape.backprop: output.sum()).
+// The sum goes to *dt_out and, when the adjoint state carries a time slot, to its K row (TimeInput.update: tAdjoint.assign).
+__global__ void __launch_bounds__(256) k_time_concat_bwd(Ref gin, float gscale, Ref dxout, long long rows, int C, int k, double* acc,
+                                                          unsigned int* ticket, CommDev* cm, float* dt_out, Ref slot, int write_slot) {
+    pdl_begin();
+    const float* __restrict__ g = resolve(gin);
+    float* __restrict__ dx = resolve(dxout);
+    const int Co = C + k;
+    const long long n = rows * Co;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    double v[1] = {0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const long long r = i / Co;
+        const int ch = (int)(i - r * Co);
+        const float gv = __fmul_rn(gscale, g[i]);
+        if (ch < C) dx[r * C + ch] = gv; else v[0] += (double)gv;
+    }
+    if (publish_and_elect<1>(v, acc, ticket, cm) && threadIdx.x == 0) {
+        *dt_out = (float)v[0];
+        if (write_slot) *resolve(slot) = (float)v[0];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // BatchNorm, training mode always (SingleStep.java:37): batch mean / biased variance over rows.
 // Statistics: column sums in double, last block finalises mean and 1/sqrt(var+eps) and re-arms the
 // accumulators.  Requires C % 4 == 0 and (C/4) dividing 256 (vector path) else the generic path.

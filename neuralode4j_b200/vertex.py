@@ -18,7 +18,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from .conf import (DormandPrince54Solver, FixedStep, InputStep, Layer, _ReplayState, ode_helper_from_json)
+from .conf import (DormandPrince54Solver, FixedStep, InputStep, Layer, ShapeMatchVertex, _ReplayState, ode_helper_from_json)
 
 
 def _is_torch(x) -> bool:
@@ -63,15 +63,18 @@ class OdeVertex:
     class Builder:
         """OdeVertex.Builder(globalConf, name, layer) (OdeVertex.java:164-336)."""
 
-        def __init__(self, globalConf, name: str, layer: Layer, *_unused):
-            if not isinstance(layer, Layer):
-                # Builder(globalConf, name, vertex, timeAsInput, ...) :190-204 — arbitrary GraphVertex
-                raise NotImplementedError("Can only build native ODE blocks from layers of the native set")
+        def __init__(self, globalConf, name: str, layer, timeAsInput: bool = False, *otherInputs):
             self.globalConf = globalConf
             self.first = name
-            self._names = [name]
-            self._layers = [layer]
-            self._inputs = {name: ()}
+            self._names = []
+            self._layers = []
+            if isinstance(layer, Layer):          # Builder(globalConf, name, layer) :178-185
+                self._names.append(name)
+                self._layers.append(layer)
+            elif timeAsInput:                      # Builder(globalConf, name, vertex, timeAsInput, ...) :194-208
+                self.addTimeVertex(name, layer, "input")
+            else:
+                self.addVertex(name, layer, "input")
             default = FixedStep(DormandPrince54Solver(), np.arange(2), True)   # :168-169
             self.odeForwardConf = default
             self.odeBackwardConf = default
@@ -84,13 +87,22 @@ class OdeVertex:
             return self
 
         def addVertex(self, name, vertex, *inputs):
-            raise NotImplementedError("GraphVertex inside an ODE block is outside the native set")
+            raise NotImplementedError("GraphVertex inside an ODE block is outside the native set (except the time merge, addTimeVertex)")
 
         def addTimeLayer(self, name, layer):
-            raise NotImplementedError("time as input to the inner graph (TimeInput) is not native yet")
+            raise NotImplementedError("a layer fed by the time alone (addTimeLayer) is outside the native set; use the time merge vertex")
 
         def addTimeVertex(self, name, vertex, *inputs):
-            raise NotImplementedError("time as input to the inner graph (TimeInput) is not native yet")
+            """addTimeVertex (OdeVertex.java:243-246): the vertex also receives the solver's current time as its last input.  Native
+            for ShapeMatchVertex(MergeVertex) as the FIRST vertex of the block (the reference's examples/anode and examples/cifar10
+            blocks, OdeBlockWithTime.java:30-36, OdeBlockTime.java:35-41)."""
+            if not isinstance(vertex, ShapeMatchVertex):
+                raise NotImplementedError("only ShapeMatchVertex(MergeVertex) can take the time input natively")
+            if self._names:
+                raise NotImplementedError("the time merge is only supported as the first vertex of the inner graph")
+            self._names.append(name)
+            self._layers.append(vertex.layer())
+            return self
 
         def odeConf(self, odeConf):            # :271-274
             self.odeForward(odeConf.forward())
@@ -128,6 +140,8 @@ class OdeVertex:
                 c = l.nOut
             elif l.kind == _lib.LAYER_BATCHNORM:
                 n += 4 * c
+            elif l.kind == _lib.LAYER_TIME_CONCAT:
+                c += l.nOut
         return n
 
     def graph_spec(self) -> List[dict]:
@@ -141,7 +155,7 @@ class OdeVertex:
     @staticmethod
     def from_json(d):
         kinds = {"dense": _lib.LAYER_DENSE, "conv3x3": _lib.LAYER_CONV3X3, "batchnorm": _lib.LAYER_BATCHNORM,
-                 "activation": _lib.LAYER_ACTIVATION}
+                 "activation": _lib.LAYER_ACTIVATION, "time_concat": _lib.LAYER_TIME_CONCAT}
         layers = [Layer(kinds[l["kind"]], l["n_in"], l["n_out"], l["activation"], l["has_bias"], l["eps"]) for l in d["layers"]]
         return OdeVertex([l["name"] for l in d["layers"]], layers, d["first"], ode_helper_from_json(d["odeForwardConf"]),
                          ode_helper_from_json(d["odeBackwardConf"]))
@@ -362,6 +376,15 @@ class OdeVertexImpl:
         dreal = np.zeros(max(self._n_real, 1), dtype=np.float32)
         _lib.check(self._L.node4j_rhs_vjp(self._h, _ptr(z), float(t), _ptr(g), _ptr(fz), _ptr(dz), _ptr(dreal)))
         return fz, dz, dreal[: self._n_real]
+
+    def rhs_vjp_time(self, z, g, t: float = 0.0):
+        """(f(z,t), g^T df/dz, g^T df/dtheta_real, g^T df/dt): the last entry is the epsilon of the time input (TimeInput.java:46-50)."""
+        z, g = _as_f32(z), _as_f32(g)
+        fz, dz = _empty_like(z, self.shape), _empty_like(z, self.shape)
+        dreal = np.zeros(max(self._n_real, 1), dtype=np.float32)
+        dt = C.c_float()
+        _lib.check(self._L.node4j_rhs_vjp_time(self._h, _ptr(z), float(t), _ptr(g), _ptr(fz), _ptr(dz), _ptr(dreal), C.byref(dt)))
+        return fz, dz, dreal[: self._n_real], dt.value
 
     def error_norm(self, K, y0, y1, h):
         K, y0, y1 = _as_f32(K), _as_f32(y0), _as_f32(y1)

@@ -7,7 +7,8 @@ from typing import Optional
 
 import numpy as np
 
-from .conf import (BatchNormalization, Convolution2D, DenseLayer, DormandPrince54Solver, FixedStep, InputStep, SolverConfig)
+from .conf import (ActivationLayer, BatchNormalization, Convolution2D, DenseLayer, DormandPrince54Solver, FixedStep, InputStep,
+                   MergeVertex, ShapeMatchVertex, SolverConfig)
 from .vertex import OdeVertex
 
 
@@ -96,6 +97,45 @@ def timeseries_block(batch: int = 1024, dim: int = 256, nt: int = 32, seed: int 
     y0 = np.random.default_rng(6).standard_normal((batch, dim)).astype(np.float32)
     t = np.linspace(0, 4, nt).astype(np.float32)
     return Workload("timeseries_inputstep", conf, (batch, dim), params, y0, t, 7, 1.0, time_is_input=True)
+
+
+def anode_time_block(batch: int = 256, dim: int = 3, hidden: int = 32, time_input: bool = False, nt: int = 2, seed: int = 11,
+                     abs_tol=1e-3, rel_tol=1e-3) -> Workload:
+    """Time-dependent f, dense: the reference's ANODE block (examples/anode/OdeBlockWithTime.java:26-40 around MlpBlock.java:42-60):
+    "timeConc" = ShapeMatchVertex(MergeVertex) with the time as last input, then Dense(hidden, ReLU) x2 and Dense(dim).
+    `time_input=True` drives it through InputStep with needTimeGradient (the adjoint's time slot then integrates -a^T df/dt)."""
+    solver = DormandPrince54Solver(SolverConfig(abs_tol, rel_tol, 1e-20, 100))
+    b = (OdeVertex.Builder(None, "timeConc", ShapeMatchVertex(MergeVertex()), True)
+         .addLayer("h1", DenseLayer(hidden, dim + 1, "relu"), "timeConc")
+         .addLayer("h2", DenseLayer(hidden, hidden, "relu"), "h1")
+         .addLayer("out", DenseLayer(dim, hidden, "identity"), "h2"))
+    t = np.linspace(0, 1, nt).astype(np.float32)
+    conf = b.odeConf(InputStep(solver, 1, True, True) if time_input else FixedStep(solver, t, True)).build()
+    rng = np.random.default_rng(seed)
+    params = np.concatenate([_uniform(rng, (dim + 1) * hidden, dim + 1), _uniform(rng, hidden, dim + 1),
+                             _uniform(rng, hidden * hidden, hidden), _uniform(rng, hidden, hidden),
+                             _uniform(rng, hidden * dim, hidden), _uniform(rng, dim, hidden)]) * np.float32(2.0)
+    y0 = np.random.default_rng(seed + 1).standard_normal((batch, dim)).astype(np.float32)
+    return Workload("anode_time_block", conf, (batch, dim), params, y0, t, seed + 2, 1.0, time_is_input=time_input)
+
+
+def conv_time_block(batch: int = 8, channels: int = 16, hw: int = 6, time_channels: int = 10, seed: int = 21,
+                    abs_tol=1e-3, rel_tol=1e-3) -> Workload:
+    """Time-dependent f, convolutional: the vertex of examples/cifar10/OdeBlockTime.java:35-45 — ShapeMatchVertex(MergeVertex,
+    {1: 10}) appends ten time channels, then a chain conv3x3 - BN/ReLU - conv3x3 and the trailing ReLU ActivationLayer (:45)."""
+    solver = DormandPrince54Solver(SolverConfig(abs_tol, rel_tol, 1e-20, 100))
+    C, k = channels, time_channels
+    conf = (OdeVertex.Builder(None, "timeConc", ShapeMatchVertex(MergeVertex(), {1: k}), True)
+            .addLayer("conv1", Convolution2D(C, C + k), "timeConc")
+            .addLayer("bn1", BatchNormalization(C, "relu"), "conv1")
+            .addLayer("conv2", Convolution2D(C, C), "bn1")
+            .addLayer("relu", ActivationLayer("relu"), "conv2")
+            .odeConf(FixedStep(solver, np.arange(2))).build())
+    rng = np.random.default_rng(seed)
+    bn = np.concatenate([np.ones(C), np.zeros(C), np.zeros(C), np.ones(C)]).astype(np.float32)
+    params = np.concatenate([_uniform(rng, C * (C + k) * 9, (C + k) * 9), bn, _uniform(rng, C * C * 9, C * 9)])
+    y0 = np.random.default_rng(seed + 1).standard_normal((batch, C, hw, hw)).astype(np.float32)
+    return Workload("conv_time_block", conf, (batch, C, hw, hw), params, y0, np.array([0, 1], dtype=np.float32), seed + 2, 1e-1)
 
 
 def golden_linear(sign: int = 1) -> Workload:

@@ -39,7 +39,10 @@ namespace {
 // ---------------------------------------------------------------------------------------------
 // Public POD types (mirrored by oracle/oracle.py)
 // ---------------------------------------------------------------------------------------------
-enum LayerKind { L_DENSE = 1, L_CONV3X3 = 2, L_BATCHNORM = 3, L_ACTIVATION = 4 };
+// L_TIME_CONCAT: the reference's "timeConc" first vertex, ShapeMatchVertex(MergeVertex) fed by TimeInput
+// (J/ode/vertex/impl/ShapeMatchVertex.java:50-79, J/util/preproc/DuplicateScalarToShape.java:41-60, J/ode/vertex/impl/helper/TimeInput.java:27-50):
+// n_out channels (features) holding the current time are appended to the state along dimension 1.
+enum LayerKind { L_DENSE = 1, L_CONV3X3 = 2, L_BATCHNORM = 3, L_ACTIVATION = 4, L_TIME_CONCAT = 5 };
 enum Activation { A_IDENTITY = 0, A_RELU = 1, A_ELU = 2, A_TANH = 3 };
 enum TimeGradMode { TG_NONE = 0, TG_ZERO = 1, TG_CALC = 2 };
 
@@ -125,6 +128,7 @@ struct NetPlan {
     std::vector<LayerPlan> L;
     int rank = 2;
     int64_t B = 0, n_state = 0, n_params = 0, n_real = 0;
+    bool time_input = false;   // TimeInputFactory (J/ode/vertex/conf/OdeVertex.java:251)
     std::string err;
 };
 
@@ -172,6 +176,16 @@ bool plan_net(const OrcGraphDesc& g, NetPlan& P) {
             case L_ACTIVATION:
                 lp.p_len = 0; lp.g_len = 0;
                 break;
+            case L_TIME_CONCAT:
+                // OdeVertex.Builder(conf, name, vertex, addTimeAsInput=true, ...): only the FIRST vertex sees the time input
+                if (i != 0) { P.err = "time concat is only supported as the first vertex of the inner graph"; return false; }
+                if (lp.d.n_out <= 0) lp.d.n_out = 1;            // ShapeMatchVertex(MergeVertex): overrideSizeDims {1: 1}
+                lp.d.n_in = g.rank == 2 ? F : C;
+                lp.d.activation = A_IDENTITY;
+                lp.p_len = 0; lp.g_len = 0;
+                if (g.rank == 2) F += lp.d.n_out; else C += lp.d.n_out;
+                P.time_input = true;
+                break;
             default:
                 P.err = "unknown layer kind"; return false;
         }
@@ -213,6 +227,7 @@ template <class R> struct Net {
     std::vector<R> x0;                     // copy of the graph input (needed by backward)
     std::vector<R> gbuf[2];
     int64_t nfe = 0;
+    R dt_last = 0;                         // gradient w.r.t. the time input of the last backward() (TimeInput.update)
 
     void init(const NetPlan& p) {
         P = p;
@@ -297,7 +312,7 @@ template <class R> struct Net {
     }
 
     // f(z, t): ForwardPass.calculateDerivative, J/.../forward/ForwardPass.java:41-48 (nfe++ at :42)
-    void forward(const R* z, R /*t*/, R* out) {
+    void forward(const R* z, R t, R* out) {
         ++nfe;
         std::memcpy(x0.data(), z, sizeof(R) * P.n_state);
         const R* cur = x0.data();
@@ -311,6 +326,15 @@ template <class R> struct Net {
                 case L_ACTIVATION:
                     for (int64_t k = 0; k < l.out_len; ++k) y[k] = act_fwd<R>(l.d.activation, cur[k]);
                     break;
+                case L_TIME_CONCAT: {
+                    // MergeVertex along dimension 1 of [state, t duplicated to the state's shape with n_out channels]
+                    const int64_t Cs = l.d.n_in, k = l.d.n_out, S = P.rank == 4 ? l.H * l.W : 1;
+                    for (int64_t b = 0; b < P.B; ++b) {
+                        std::memcpy(y + b * (Cs + k) * S, cur + b * Cs * S, sizeof(R) * Cs * S);
+                        for (int64_t q = 0; q < k * S; ++q) y[(b * (Cs + k) + Cs) * S + q] = t;
+                    }
+                    break;
+                }
             }
             cur = y;
         }
@@ -323,6 +347,7 @@ template <class R> struct Net {
     // Layer gradients are sums over the batch (no 1/B).
     void backward(const R* g_out, R* dx, R* dreal) {
         gbuf[0].assign(g_out, g_out + P.n_state);
+        dt_last = 0;
         int cur = 0;
         for (int64_t i = (int64_t)P.L.size() - 1; i >= 0; --i) {
             const LayerPlan& l = P.L[i];
@@ -440,6 +465,17 @@ template <class R> struct Net {
                 case L_ACTIVATION:
                     std::copy(gin.begin(), gin.begin() + l.in_len, gout.begin());
                     break;
+                case L_TIME_CONCAT: {
+                    // MergeVertex.doBackward splits the epsilon; DuplicateScalarToShape.backprop sums the time part (:60-62)
+                    const int64_t Cs = l.d.n_in, k = l.d.n_out, S = P.rank == 4 ? l.H * l.W : 1;
+                    double acc = 0;
+                    for (int64_t b = 0; b < P.B; ++b) {
+                        std::memcpy(gout.data() + b * Cs * S, gin.data() + b * (Cs + k) * S, sizeof(R) * Cs * S);
+                        for (int64_t q = 0; q < k * S; ++q) acc += (double)gin[(b * (Cs + k) + Cs) * S + q];
+                    }
+                    dt_last = (R)acc;
+                    break;
+                }
             }
             cur ^= 1;
         }
@@ -711,7 +747,9 @@ template <class R> struct AdjEq : Equation<R> {
         std::memcpy(out, fz.data(), sizeof(R) * nz);
         std::memcpy(out + nz, da.data(), sizeof(R) * nz);      // :79 updateZAdjoint
         std::memcpy(out + 2 * nz, dth.data(), sizeof(R) * nreal);
-        for (int64_t i = 0; i < nt; ++i) out[2 * nz + nreal + i] = 0;   // NoTimeInput.update: tAdjoint := 0
+        // NoTimeInput.update (NoTimeInput.java:26-29): tAdjoint := 0;  TimeInput.update (TimeInput.java:46-50): tAdjoint := the
+        // epsilon of the time input (an assign into the empty array of NoTimeGrad when nt == 0, i.e. dropped)
+        for (int64_t i = 0; i < nt; ++i) out[2 * nz + nreal + i] = net->P.time_input ? net->dt_last : R(0);
     }
 };
 
@@ -871,6 +909,8 @@ void orc_destroy(void* hh) { delete (AnyHandle*)hh; }
 
 int64_t orc_num_params(void* hh) { auto* h = (AnyHandle*)hh; return h->use_double ? h->d->plan.n_params : h->f->plan.n_params; }
 int64_t orc_num_real_params(void* hh) { auto* h = (AnyHandle*)hh; return h->use_double ? h->d->plan.n_real : h->f->plan.n_real; }
+// gradient w.r.t. the time input left by the last rhs_vjp / augmented evaluation (0 without a time-concat vertex)
+double orc_last_dt(void* hh) { auto* h = (AnyHandle*)hh; return h->use_double ? (double)h->d->net.dt_last : (double)h->f->net.dt_last; }
 int64_t orc_state_len(void* hh) { auto* h = (AnyHandle*)hh; return h->use_double ? h->d->plan.n_state : h->f->plan.n_state; }
 
 int orc_forward(void* hh, const void* params, const void* y0, const void* t, int nt, int interpolate, void* out, OrcStats* st) {

@@ -21,7 +21,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libnode_oracle.so")
 
-KIND = {"dense": 1, "conv3x3": 2, "batchnorm": 3, "activation": 4}
+KIND = {"dense": 1, "conv3x3": 2, "batchnorm": 3, "activation": 4, "time_concat": 5}
 ACT = {"identity": 0, "relu": 1, "elu": 2, "tanh": 3}
 TG_NONE, TG_ZERO, TG_CALC = 0, 1, 2
 
@@ -73,6 +73,8 @@ def lib():
         for f in (L.orc_num_params, L.orc_num_real_params, L.orc_state_len):
             f.restype = C.c_int64
             f.argtypes = [C.c_void_p]
+        L.orc_last_dt.restype = C.c_double
+        L.orc_last_dt.argtypes = [C.c_void_p]
         L.orc_forward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(Stats)]
         L.orc_backward.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Stats)]
@@ -207,6 +209,10 @@ class Oracle:
         out = np.empty_like(z)
         lib().orc_rhs(self._h, _p(params), _p(z), float(t), _p(out))
         return out
+
+    def last_dt(self):
+        """g^T df/dt of the last :meth:`rhs_vjp` (the epsilon of the time input, TimeInput.java:46-50); 0 for autonomous graphs."""
+        return float(lib().orc_last_dt(self._h))
 
     def rhs_vjp(self, params, z, g, t=0.0):
         """Returns (f(z), g^T df/dz, g^T df/dtheta_real[n_real])."""

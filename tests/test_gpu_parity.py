@@ -249,6 +249,66 @@ def test_timeseries_block_small():
     _e2e(W.timeseries_block(batch=32, dim=48, nt=6), counts=False)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# time as input to the inner graph (TimeInput + ShapeMatchVertex(MergeVertex))
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("w", [W.anode_time_block(batch=32), W.conv_time_block(batch=4, channels=8, hw=5, time_channels=3)],
+                         ids=["dense", "conv"])
+def test_rhs_with_time_input(w):
+    """f(z,t) depends on t, and rhs_vjp_time returns g^T df/dt (TimeInput.java:46-50) next to the state / parameter products."""
+    orc = H.oracle_for(w)
+    rng = np.random.default_rng(13)
+    g = rng.standard_normal(w.shape).astype(np.float32)
+    v = w.conf.instantiate(w.shape, flags=EXACT)
+    v.setParams(w.params)
+    try:
+        f0, f1 = v.rhs(w.y0, 0.25), v.rhs(w.y0, 1.5)
+        fz, dz, dreal, dt = v.rhs_vjp_time(w.y0, g, 0.25)
+    finally:
+        v.close()
+    assert np.abs(f0 - f1).max() > 1e-3
+    scale = lambda a: np.abs(a).max() + 1e-30
+    for t, f in ((0.25, f0), (1.5, f1)):
+        assert np.abs(f - orc.rhs(w.params, w.y0, t=t)).max() <= 2e-5 * scale(f)
+    ofz, odz, odreal = orc.rhs_vjp(w.params, w.y0, g, t=0.25)
+    assert np.array_equal(fz, f0)
+    assert np.abs(dz - odz).max() <= 2e-5 * scale(odz)
+    assert np.abs(dreal - odreal).max() <= 2e-5 * scale(odreal)
+    assert abs(dt - orc.last_dt()) <= 2e-5 * max(1.0, abs(orc.last_dt()))
+
+
+def test_anode_time_block_fixed_step():
+    """examples/anode OdeBlockWithTime under FixedStep(t=[0,1]): no time slot in the adjoint (NoTimeGrad), step-for-step parity."""
+    _e2e(W.anode_time_block(batch=64), flags=EXACT)
+    _e2e(W.anode_time_block(batch=64))
+
+
+def test_anode_time_block_input_step_time_gradients():
+    """Same block under InputStep with needTimeGradient: the adjoint's time slot now integrates -a^T df/dt, enters the error norm
+    (so it moves the step sequence) and comes back as dL/dt."""
+    r, o = _e2e(W.anode_time_block(batch=64, time_input=True, nt=2), flags=EXACT)
+    assert r["dt"].shape == (2,) and np.abs(r["dt"]).min() > 0
+    _e2e(W.anode_time_block(batch=64, time_input=True, nt=5), flags=EXACT)
+
+
+def test_conv_time_block():
+    """examples/cifar10 OdeBlockTime-style block: ten time channels merged in front of conv3x3 - BN/ReLU - conv3x3 - ReLU."""
+    _e2e(W.conv_time_block(batch=6, channels=16, hw=6, time_channels=10), flags=EXACT)
+
+
+def test_exact_stage_times_flag_matches_oracle_variant():
+    """N4J_FLAG_EXACT_STAGE_TIMES (stage s at t + c_s*h) against the oracle's exact_stage_times switch; differs from the default
+    (reference quirk A.3: every stage at t + h) for a time-dependent f."""
+    w = W.anode_time_block(batch=32)
+    a = H.run_cuda(w, flags=EXACT)
+    b = H.run_cuda(w, flags=EXACT | _lib.FLAG_EXACT_STAGE_TIMES)
+    assert np.abs(a["out"] - b["out"]).max() > 1e-5
+    orc = H.oracle_for(w, exact_stage_times=True)
+    out = orc.forward(w.params, w.y0, w.time, interpolate=True)
+    assert b["fwd_stats"] == (orc.stats.nfe, orc.stats.accepted, orc.stats.rejected)
+    H.assert_close(b["out"], out, RTOL, 1e-5 * np.abs(out).max(), "exact stage times")
+
+
 def test_single_stepping_equals_interpolating():
     # InterpolatingMultiStepSolverTest.java:26-37: both multi-step solvers agree to 1e-4
     w = W.golden_linear(1)

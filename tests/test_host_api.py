@@ -86,11 +86,32 @@ def test_builder_rejects_what_is_outside_the_native_set():
     with pytest.raises(NotImplementedError):
         b.addTimeLayer("t", N.DenseLayer(4, 4))
     with pytest.raises(NotImplementedError):
+        b.addTimeVertex("tv", N.ShapeMatchVertex(N.MergeVertex()), "a")       # the time merge must be the first vertex
+    with pytest.raises(NotImplementedError):
+        N.ShapeMatchVertex(object())                                           # only the MergeVertex is wrapped natively
+    with pytest.raises(NotImplementedError):
+        N.ShapeMatchVertex(N.MergeVertex(), {2: 3})
+    with pytest.raises(NotImplementedError):
+        N.OdeVertex.Builder(None, "v", N.ShapeMatchVertex(N.MergeVertex()), False)   # vertex without the time input
+    with pytest.raises(NotImplementedError):
         N.Convolution2D(8, kernelSize=(5, 5))
     with pytest.raises(NotImplementedError):
         N.Convolution2D(8, hasBias=True)
     with pytest.raises(NotImplementedError):
         N.DenseLayer(3, 3, activation="softmax").desc()
+
+
+def test_time_vertex_builder_mirrors_reference():
+    # OdeVertexTest.fitWithFirstTimeVertex (OdeVertexTest.java:226-254) / examples OdeBlockWithTime, OdeBlockTime
+    v = (N.OdeVertex.Builder(None, "ode0", N.ShapeMatchVertex(N.MergeVertex()), True)
+         .addLayer("ode1", N.DenseLayer(8), "ode0").build())
+    assert [l.kind for l in v.layers] == [_lib.LAYER_TIME_CONCAT, _lib.LAYER_DENSE]
+    assert v.layers[0].nOut == 1                                  # ShapeMatchVertex(MergeVertex): overrideSizeDims {1: 1}
+    assert v.numParams((5, 8)) == 9 * 8 + 8                       # the dense layer sees nIn + 1 inputs
+    assert N.ShapeMatchVertex(N.MergeVertex(), {1: 10}).layer().nOut == 10    # cifar10/OdeBlockTime.java:38
+    for w in (W.anode_time_block(batch=2), W.conv_time_block(batch=2)):
+        back = N.OdeVertex.from_json(w.conf.to_json())
+        assert back == w.conf and w.conf.numParams(w.shape) == w.params.size
 
 
 def test_default_ode_conf_matches_reference_default():

@@ -344,3 +344,98 @@ def test_time_must_be_sorted():
         orc.backward(w.params, ys, np.zeros_like(ys), t, time_grad=O.TG_CALC)
     with pytest.raises(ValueError):                             # SolverConfig.java:22-24
         O.Oracle(w.conf.graph_spec(), w.shape, O.solver_cfg(1e-3, 1e-3, 1.0, 0.5))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# time as input to the inner graph: TimeInput + ShapeMatchVertex(MergeVertex)
+# ---------------------------------------------------------------------------------------------------------------------
+def test_time_input_forward_pass_reference_case():
+    """ForwardPassTest.calculateDerivativeWithTimeDependency (ForwardPassTest.java:60-91): all-ones weights, so every output is
+    sum(input) + t."""
+    layers = [dict(kind="time_concat", n_out=1), dict(kind="dense", n_out=5, has_bias=False, activation="identity")]
+    o = O.Oracle(layers, (1, 5), dtype=np.float64)
+    inp = np.arange(5, dtype=np.float64).reshape(1, 5)
+    fz = o.rhs(np.ones(o.n_params), inp, t=7.89)
+    np.testing.assert_allclose(fz, np.full((1, 5), inp.sum() + 7.89), rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", ["dense", "conv"])
+def test_time_input_vjp_matches_finite_differences(case):
+    """g^T df/dt (DuplicateScalarToShape.backprop = sum of the time part of the merged epsilon) against central differences, fp64."""
+    rng = np.random.default_rng(0)
+    if case == "dense":
+        layers = [dict(kind="time_concat", n_out=2), dict(kind="dense", n_out=7, activation="tanh"), dict(kind="dense", n_out=4)]
+        shape = (3, 4)
+    else:
+        layers = [dict(kind="time_concat", n_out=3), dict(kind="conv3x3", n_out=5, has_bias=False, activation="tanh"),
+                  dict(kind="batchnorm", activation="relu"), dict(kind="conv3x3", n_out=4, has_bias=False)]
+        shape = (2, 4, 5, 5)
+    o = O.Oracle(layers, shape, dtype=np.float64)
+    th = rng.standard_normal(o.n_params) * 0.4
+    z, g = rng.standard_normal(shape), rng.standard_normal(shape)
+    _, dz, _ = o.rhs_vjp(th, z, g, t=0.3)
+    dt = o.last_dt()
+    e = 1e-6
+    fd = (np.sum(g * o.rhs(th, z, t=0.3 + e)) - np.sum(g * o.rhs(th, z, t=0.3 - e))) / (2 * e)
+    assert abs(dt - fd) < 1e-6 * max(1.0, abs(fd))
+    idx = tuple(s // 2 for s in shape)
+    zp, zm = z.copy(), z.copy()
+    zp[idx] += e
+    zm[idx] -= e
+    fdz = (np.sum(g * o.rhs(th, zp, t=0.3)) - np.sum(g * o.rhs(th, zm, t=0.3))) / (2 * e)
+    assert abs(dz[idx] - fdz) < 1e-6 * max(1.0, abs(fdz))
+
+
+def test_time_input_adjoint_time_gradients():
+    """With a time-dependent f the adjoint's time slot integrates -a^T df/dt (TimeInput.update).  Single step: both entries of
+    dL/dt equal central differences of the loss.  Multi step: interior and last entries do; the FIRST entry is the reference's
+    `lastTime` accumulator, -sum(dL/dt[1:]) (CalcMultiStepTimeGrad.java:58-63 writes lastTime, not the integrated slot), which is
+    only the true derivative for autonomous f — restated as it is."""
+    rng = np.random.default_rng(1)
+    layers = [dict(kind="time_concat", n_out=1), dict(kind="dense", n_out=6, activation="tanh"), dict(kind="dense", n_out=3)]
+    o = O.Oracle(layers, (2, 3), O.solver_cfg(1e-11, 1e-11, 1e-20, 100), dtype=np.float64)
+    th = rng.standard_normal(o.n_params) * 0.7
+    y0, w = rng.standard_normal((2, 3)), rng.standard_normal((2, 3))
+    e = 1e-5
+
+    t = np.array([0.2, 1.1])
+    out = o.forward(th, y0, t, interpolate=False)
+    _, _, dt = o.backward(th, out, w, t, time_grad=O.TG_CALC)
+    loss = lambda t0, t1: float(np.sum(w * o.forward(th, y0, np.array([t0, t1]), interpolate=False)))
+    fd0 = (loss(t[0] + e, t[1]) - loss(t[0] - e, t[1])) / (2 * e)
+    fd1 = (loss(t[0], t[1] + e) - loss(t[0], t[1] - e)) / (2 * e)
+    np.testing.assert_allclose(dt, [fd0, fd1], rtol=2e-5)
+
+    tt = np.linspace(0.1, 1.3, 5)
+    out = o.forward(th, y0, tt, interpolate=True)
+    wm = rng.standard_normal(out.shape)
+    _, _, dtm = o.backward(th, out, wm, tt, time_grad=O.TG_CALC)
+    lm = lambda ts: float(np.sum(wm * o.forward(th, y0, ts, interpolate=True)))
+    for k in range(1, 5):
+        a, b = tt.copy(), tt.copy()
+        a[k] += e
+        b[k] -= e
+        assert abs(dtm[k] - (lm(a) - lm(b)) / (2 * e)) < 3e-4 * max(1.0, abs(dtm[k]))   # dense-output (4th order) error included
+    assert abs(dtm[0] + dtm[1:].sum()) < 1e-9 * np.abs(dtm).sum()
+
+
+def test_stage_time_quirk_is_observable_only_with_time_input():
+    """Quirk A.3 (every stage evaluated at t+h, FirstOrderEquationWithState.java:45,82): irrelevant for autonomous f, visible with
+    a time input — and both variants still converge to the same solution as the tolerance shrinks."""
+    w = W.anode_time_block(batch=8)
+    a = H.oracle_for(w).forward(w.params, w.y0, w.time, interpolate=True)
+    b = H.oracle_for(w, exact_stage_times=True).forward(w.params, w.y0, w.time, interpolate=True)
+    assert np.abs(a - b).max() > 1e-5
+    s = W.spiral_block(batch=8, nt=4)
+    a2 = H.oracle_for(s).forward(s.params, s.y0, s.time, interpolate=True)
+    b2 = H.oracle_for(s, exact_stage_times=True).forward(s.params, s.y0, s.time, interpolate=True)
+    np.testing.assert_array_equal(a2, b2)
+    wt = W.anode_time_block(batch=8, abs_tol=1e-9, rel_tol=1e-9)
+    c = H.oracle_for(wt, np.float64).forward(wt.params, wt.y0, wt.time, interpolate=True)
+    d = H.oracle_for(wt, np.float64, exact_stage_times=True).forward(wt.params, wt.y0, wt.time, interpolate=True)
+    assert np.abs(c - d).max() < 1e-3          # the quirk makes the scheme first-order consistent in t only: slow convergence
+
+
+def test_time_concat_must_be_first():
+    with pytest.raises(Exception):
+        O.Oracle([dict(kind="dense", n_out=4), dict(kind="time_concat", n_out=1), dict(kind="dense", n_out=4)], (2, 4))
