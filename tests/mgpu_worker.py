@@ -31,6 +31,8 @@ def main():
         wg = W.mnist_block(batch=local * world, channels=64)
     elif which == "mlp":
         wg = W.mlp_block(batch=local * world, dim=96)
+    elif which == "anode_time":      # time-dependent f with time gradients: the summed time epsilon crosses the ranks as well
+        wg = W.anode_time_block(batch=local * world, time_input=True, nt=3)
     else:
         wg = W.golden_linear(1)
         local = 1
