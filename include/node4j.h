@@ -205,7 +205,15 @@ int32_t node4j_bench_solver_pass(n4j_handle* h, int64_t n, int32_t iters, float*
 
 /* Same idea for pieces of the RHS on the handle's own shapes: average device time (CUDA events on the engine's
  * stream) of one f(z,t) evaluation, one augmented evaluation, or one launch of a conv kernel. */
-enum { N4J_BENCH_RHS_FWD = 1, N4J_BENCH_RHS_AUG = 2, N4J_BENCH_CONV_FWD = 3, N4J_BENCH_CONV_DGRAD = 4, N4J_BENCH_CONV_WGRAD = 5 };
+enum {
+    N4J_BENCH_RHS_FWD = 1,
+    N4J_BENCH_RHS_AUG = 2,
+    N4J_BENCH_CONV_FWD = 3,         /* bare conv kernel on a prepared operand image */
+    N4J_BENCH_CONV_DGRAD = 4,
+    N4J_BENCH_CONV_WGRAD = 5,
+    N4J_BENCH_CONV_FWD_FUSED = 6,   /* the forward conv launch exactly as an evaluation issues it: BatchNorm-apply prologue + statistics epilogue */
+    N4J_BENCH_CONV_DGRAD_FUSED = 7  /* the dgrad launch as issued: BatchNorm-backward prologue + backward-statistics epilogue */
+};
 int32_t node4j_bench_piece(n4j_handle* h, int32_t what, int32_t iters, float* us_per_iter);
 
 /* The CUDA stream (cudaStream_t) all work of this handle is enqueued on, so that a host framework can record

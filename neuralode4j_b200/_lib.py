@@ -24,7 +24,7 @@ EXPORTS = [
     "node4j_backward", "node4j_get_step_log", "node4j_rhs", "node4j_rhs_vjp", "node4j_rhs_vjp_time", "node4j_error_norm",
     "node4j_comm_init", "node4j_comm_export", "node4j_bench_solver_pass", "node4j_bench_piece", "node4j_get_stream",
 ]
-BENCH_RHS_FWD, BENCH_RHS_AUG, BENCH_CONV_FWD, BENCH_CONV_DGRAD, BENCH_CONV_WGRAD = 1, 2, 3, 4, 5
+BENCH_RHS_FWD, BENCH_RHS_AUG, BENCH_CONV_FWD, BENCH_CONV_DGRAD, BENCH_CONV_WGRAD, BENCH_CONV_FWD_FUSED, BENCH_CONV_DGRAD_FUSED = 1, 2, 3, 4, 5, 6, 7
 
 
 class LayerDesc(C.Structure):

@@ -477,6 +477,10 @@ void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg,
     a.img = img; a.wimg = wimg; a.out = out; a.g = geom_; a.act = act;
     if (next_bn) { epi_kind = 1; a.bn = next_bn->bn; a.bn_eps = next_bn->d.eps; a.bn_rows = next_bn->rows; }
     a.fuse_stats = epi_kind;
+    if (conv_rec_) conv_rec_->push_back(ConvRec{a, pro_kind, epi_kind});
+    launch_conv_args(s, a, pro_kind, epi_kind);
+}
+void Engine::launch_conv_args(cudaStream_t s, const ConvTcArgs& a, int pro_kind, int epi_kind) {
     const bool fast = (cfg_.flags & N4J_FLAG_FAST_TF32) != 0;
     const dim3 grid(geom_.tiles), block(conv_tc_threads(pro_kind));
     const int combo = pro_kind * 3 + epi_kind;
@@ -1347,6 +1351,7 @@ void Engine::bench_piece(int what, int iters, float* us) {
     t_pdl = pdl_;
     if (params_fresh_ == false && user_params_) { launches_ = 0; upload_params(); }
     Ref yin = fixed_ref(Y_), kout = fixed_ref(K_);
+    ConvRec rec{};
     auto piece = [&]() {
         switch (what) {
             case N4J_BENCH_RHS_FWD: enqueue_rhs_fwd(stream_, yin, kout); break;
@@ -1383,9 +1388,31 @@ void Engine::bench_piece(int what, int iters, float* us) {
                 }
                 break;
             }
+            case N4J_BENCH_CONV_FWD_FUSED:
+            case N4J_BENCH_CONV_DGRAD_FUSED:
+                launch_conv_args(stream_, rec.a, rec.pro, rec.epi);
+                ++launches_;
+                break;
             default: throw Error{N4J_ERR_INVALID_ARGUMENT, "unknown bench piece"};
         }
     };
+    if (what == N4J_BENCH_CONV_FWD_FUSED || what == N4J_BENCH_CONV_DGRAD_FUSED) {
+        // the conv launches exactly as one augmented evaluation issues them (operand prologue + statistics epilogue included):
+        // record them from a real evaluation, then replay the first forward / dgrad one
+        std::vector<ConvRec> recs;
+        conv_rec_ = &recs;
+        tspec_ = TimeSpec{3, 0.f, 0.f};
+        aug_tslot_ = false;
+        enqueue_rhs_aug(stream_, yin, kout);
+        conv_rec_ = nullptr;
+        const bool want_dgrad = what == N4J_BENCH_CONV_DGRAD_FUSED;
+        bool found = false;
+        for (auto& r : recs) {
+            const bool is_dgrad = r.a.wimg != nullptr && r.pro != 1 && (r.pro == 2 || r.epi == 2);
+            if (is_dgrad == want_dgrad && (want_dgrad || r.pro == 1 || r.epi == 1)) { rec = r; found = true; break; }
+        }
+        if (!found) throw Error{N4J_ERR_INVALID_ARGUMENT, "no fused tensor-core conv launch in this inner graph"};
+    }
     for (int i = 0; i < 3; ++i) piece();
     N4J_CUDA(cudaEventRecord(ev0_, stream_));
     for (int i = 0; i < iters; ++i) piece();

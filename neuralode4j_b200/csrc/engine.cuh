@@ -176,6 +176,9 @@ private:
     void launch_gemm_tc(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& a);
     void launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act, const LayerPlan* next_bn = nullptr,
                         const ConvTcArgs* extra = nullptr, int pro_kind = 0, int epi_kind = 0);
+    struct ConvRec { ConvTcArgs a; int pro, epi; };
+    std::vector<ConvRec>* conv_rec_ = nullptr;   // bench_piece: records the conv launches of one evaluation
+    void launch_conv_args(cudaStream_t s, const ConvTcArgs& a, int pro_kind, int epi_kind);
     void enqueue_rhs(cudaStream_t s, bool aug, Ref in, Ref out, bool bn1_ready = false) {
         aug ? enqueue_rhs_aug(s, in, out, bn1_ready) : enqueue_rhs_fwd(s, in, out, false, bn1_ready);
     }
