@@ -103,6 +103,7 @@ struct ConvTcArgs {
     BnScratch pbn;        // statistics of that BatchNorm (mean, invstd, m_dy, m_dyxh)
     int pact;
     float* pcompact;      // optional: also store the produced tensor compactly (activation for the backward pass / gradient for wgrad)
+    Ref pdgamma, pdbeta;  // PRO 2 with deferred statistics: where dgamma / dbeta of that BatchNorm go
     // fused BatchNorm BACKWARD statistics in the epilogue (EPI == 2, dgrad launches): the output of this launch is the gradient
     // w.r.t. the output of the BatchNorm layer in front of the conv; sums of dy and dy*xhat over the batch, last CTA writes
     // dgamma / dbeta / mean(dy) / mean(dy*xhat) (same contract as k_bn_bwd_stats64).  `bn`, `bn_rows` describe that layer.
@@ -163,12 +164,26 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         const float* __restrict__ pg = PRO == 2 ? resolve(a.pg) : nullptr;
         // only ReLU / identity are fused (the engine keeps the separate kernels for ELU / tanh): no transcendental code in this kernel
         const bool relu = a.pact == N4J_ACT_RELU;
+        // deferred statistics: the producing kernel only accumulated.  64 threads finalise one channel each from the raw double sums
+        // (double division / square root are long instruction sequences: once per CTA, not once per thread); the loads of the sums
+        // are issued here, the arithmetic runs after the operand loads below are in flight.  CTA 0 publishes dgamma / dbeta, which
+        // the last block of the statistics kernel used to do.
+        __shared__ float s_fin[4][64];     // mean, invstd, mean(dy), mean(dy*xhat)
+        double raw[4] = {0.0, 0.0, 0.0, 0.0};
+        if (a.pbn.deferred && threadIdx.x < 64) {
+            raw[0] = a.pbn.accf[threadIdx.x * ACC_STRIDE]; raw[1] = a.pbn.accf[(64 + threadIdx.x) * ACC_STRIDE];
+            if (PRO == 2) { raw[2] = a.pbn.accb[threadIdx.x * ACC_STRIDE]; raw[3] = a.pbn.accb[(64 + threadIdx.x) * ACC_STRIDE]; }
+        }
         float mean[4], inv[4], gam[4], bet[4], mdy[4], mdyxh[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            mean[k] = a.pbn.mean[c0 + k]; inv[k] = a.pbn.invstd[c0 + k]; gam[k] = a.pgamma[c0 + k];
+            gam[k] = a.pgamma[c0 + k];
             bet[k] = PRO == 1 ? a.pbeta[c0 + k] : 0.f;
-            mdy[k] = PRO == 2 ? a.pbn.m_dy[c0 + k] : 0.f; mdyxh[k] = PRO == 2 ? a.pbn.m_dyxh[c0 + k] : 0.f;
+            mdy[k] = 0.f; mdyxh[k] = 0.f;
+            if (!a.pbn.deferred) {
+                mean[k] = a.pbn.mean[c0 + k]; inv[k] = a.pbn.invstd[c0 + k];
+                if (PRO == 2) { mdy[k] = a.pbn.m_dy[c0 + k]; mdyxh[k] = a.pbn.m_dyxh[c0 + k]; }
+            }
         }
         const int per = g.PH * g.PW;
         const float inv_pw = 1.0f / (float)g.PW;
@@ -196,6 +211,28 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 rem += 16;
                 if (rem >= 0 && bq < 0) bq = 0;
                 while (rem >= per) { rem -= per; ++bq; }
+            }
+            if (a.pbn.deferred && rr == rbase) {       // first (for W <= 14: only) pass; every thread of the CTA gets here
+                if (threadIdx.x < 64) {
+                    const int c = threadIdx.x;
+                    const double M = (double)a.pbn.rows;
+                    const double m = raw[0] / M;
+                    double var = raw[1] / M - m * m;
+                    if (var < 0) var = 0;
+                    s_fin[0][c] = (float)m;
+                    s_fin[1][c] = (float)(1.0 / sqrt(var + (double)a.pbn.eps));
+                    if (PRO == 2) {
+                        s_fin[2][c] = (float)(raw[2] / M);
+                        s_fin[3][c] = (float)(raw[3] / M);
+                        if (blockIdx.x == 0) { resolve(a.pdgamma)[c] = (float)raw[3]; resolve(a.pdbeta)[c] = (float)raw[2]; }
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    mean[k] = s_fin[0][c0 + k]; inv[k] = s_fin[1][c0 + k];
+                    if (PRO == 2) { mdy[k] = s_fin[2][c0 + k]; mdyxh[k] = s_fin[3][c0 + k]; }
+                }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -314,7 +351,11 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         unsigned long long mask = 0ull;
         if constexpr (EPI == 2) {
             __shared__ float s_mi[128];
-            if (et < 64) s_mi[et] = a.bn.mean[et]; else s_mi[et] = a.bn.invstd[et - 64];
+            if (a.bn.deferred) {
+                if (et < 64) bn_fwd_final(a.bn, et, s_mi[et], s_mi[64 + et]);
+            } else {
+                if (et < 64) s_mi[et] = a.bn.mean[et]; else s_mi[et] = a.bn.invstd[et - 64];
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const bool relu = a.eact == N4J_ACT_RELU;
             mask = relu ? 0ull : ~0ull;
@@ -377,6 +418,12 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             } else {
                 for (int r = r0; r < r0 + 64; ++r) { const double dy = (double)sT[r * 65 + c]; s1 += dy; s2 += dy * (double)sT2[r * 65 + c]; }
             }
+            if (a.bn.deferred) {      // accumulate only; the consumers finalise, CTA 0 re-arms the next evaluation's set
+                double* acc = EPI == 1 ? a.bn.accf : a.bn.accb;
+                atomicAdd(acc + c * ACC_STRIDE, s1);
+                atomicAdd(acc + (64 + c) * ACC_STRIDE, s2);
+                bn_rearm(EPI == 1 ? a.bn.accf_other : a.bn.accb_other, et);
+            } else {
             atomicAdd(a.bn.acc + c * ACC_STRIDE, s1);
             atomicAdd(a.bn.acc + (64 + c) * ACC_STRIDE, s2);
             __threadfence();
@@ -412,6 +459,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 }
                 if (et == 0) *a.bn.ticket = 0u;
             }
+            }   // legacy (multi-GPU / non-deferred) finalisation
         }
     }
     tc::tc_fence_before();
@@ -444,16 +492,22 @@ __global__ void __launch_bounds__(256) k_bn_apply_to_image(Ref xin, const float*
     const float* __restrict__ x = resolve(xin);
     const long long n4 = (long long)g.B * g.H * g.W * 16;     // float4 groups: [crow][chunk]
     const long long step = (long long)gridDim.x * blockDim.x;
+    __shared__ float s_mean[64], s_inv[64];
+    if (threadIdx.x < 64) {
+        if (sc.deferred) bn_fwd_final(sc, threadIdx.x, s_mean[threadIdx.x], s_inv[threadIdx.x]);
+        else { s_mean[threadIdx.x] = sc.mean[threadIdx.x]; s_inv[threadIdx.x] = sc.invstd[threadIdx.x]; }
+    }
+    __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
         const int chunk = (int)(i & 15);
         const long long crow = i >> 4;
         const float4 v = reinterpret_cast<const float4*>(x)[i];
         const int c = chunk * 4;
         float4 y;
-        y.x = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c], __fmul_rn(__fsub_rn(v.x, sc.mean[c]), sc.invstd[c])), beta[c]));
-        y.y = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c + 1], __fmul_rn(__fsub_rn(v.y, sc.mean[c + 1]), sc.invstd[c + 1])), beta[c + 1]));
-        y.z = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c + 2], __fmul_rn(__fsub_rn(v.z, sc.mean[c + 2]), sc.invstd[c + 2])), beta[c + 2]));
-        y.w = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c + 3], __fmul_rn(__fsub_rn(v.w, sc.mean[c + 3]), sc.invstd[c + 3])), beta[c + 3]));
+        y.x = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c], __fmul_rn(__fsub_rn(v.x, s_mean[c]), s_inv[c])), beta[c]));
+        y.y = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c + 1], __fmul_rn(__fsub_rn(v.y, s_mean[c + 1]), s_inv[c + 1])), beta[c + 1]));
+        y.z = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c + 2], __fmul_rn(__fsub_rn(v.z, s_mean[c + 2]), s_inv[c + 2])), beta[c + 2]));
+        y.w = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c + 3], __fmul_rn(__fsub_rn(v.w, s_mean[c + 3]), s_inv[c + 3])), beta[c + 3]));
         store_split4(img, g, chunk, padded_row(g, crow), y);
         if (compact) reinterpret_cast<float4*>(compact)[i] = y;
     }
@@ -562,13 +616,27 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
 
 // BatchNorm backward dx written as the compact gradient AND as the operand image of the following dgrad convolution
 __global__ void __launch_bounds__(256) k_bn_bwd_dx_to_image(Ref gin, float gscale, Ref yref, Ref xin, const float* __restrict__ gamma, BnScratch sc,
-                                                             int act, ConvGeom g, float* __restrict__ dx_compact, float* __restrict__ img) {
+                                                             int act, ConvGeom g, float* __restrict__ dx_compact, float* __restrict__ img,
+                                                             Ref dgamma_ref, Ref dbeta_ref) {
     pdl_begin();
     const float* __restrict__ gg = resolve(gin);
     const float* __restrict__ y = resolve(yref);
     const float* __restrict__ x = resolve(xin);
     const long long n4 = (long long)g.B * g.H * g.W * 16;
     const long long step = (long long)gridDim.x * blockDim.x;
+    __shared__ float s_st[4][64];      // mean, invstd, mean(dy), mean(dy*xhat)
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        if (sc.deferred) {
+            float dg, db;
+            bn_fwd_final(sc, c, s_st[0][c], s_st[1][c]);
+            bn_bwd_final(sc, c, s_st[2][c], s_st[3][c], dg, db);
+            if (blockIdx.x == 0) { resolve(dgamma_ref)[c] = dg; resolve(dbeta_ref)[c] = db; }
+        } else {
+            s_st[0][c] = sc.mean[c]; s_st[1][c] = sc.invstd[c]; s_st[2][c] = sc.m_dy[c]; s_st[3][c] = sc.m_dyxh[c];
+        }
+    }
+    __syncthreads();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += step) {
         const int chunk = (int)(i & 15);
         const long long crow = i >> 4;
@@ -578,11 +646,11 @@ __global__ void __launch_bounds__(256) k_bn_bwd_dx_to_image(Ref gin, float gscal
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int c = chunk * 4 + k;
-            const float inv = sc.invstd[c];
+            const float inv = s_st[1][c];
             const float dy = act_bwd(act, ya[k], __fmul_rn(gscale, ga[k]));
-            const float xh = __fmul_rn(__fsub_rn(xa[k], sc.mean[c]), inv);
+            const float xh = __fmul_rn(__fsub_rn(xa[k], s_st[0][c]), inv);
             const float kk = __fmul_rn(gamma[c], inv);
-            o[k] = __fmul_rn(kk, __fsub_rn(__fsub_rn(dy, sc.m_dy[c]), __fmul_rn(xh, sc.m_dyxh[c])));
+            o[k] = __fmul_rn(kk, __fsub_rn(__fsub_rn(dy, s_st[2][c]), __fmul_rn(xh, s_st[3][c])));
         }
         const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
         reinterpret_cast<float4*>(dx_compact)[i] = ov;

@@ -208,6 +208,7 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
     ensure(gradflat_, std::max<long long>(n_params_, 1));
     ensure(theta_tmp_, std::max<long long>(real_pad_, 4));
     for (auto& b : gb_) ensure(b, max_len_);
+    int n_def = 0;
     for (size_t i = 0; i < L_.size(); ++i) {
         LayerPlan& l = L_[i];
         for (int sl = 0; sl < 2; ++sl) {   // two sets: consecutive stage evaluations alternate, so a weight-gradient kernel of
@@ -275,7 +276,19 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
             float* f = nullptr;
             N4J_CUDA(cudaMalloc(&f, sizeof(float) * 4 * cc));
             l.bn.mean = f; l.bn.invstd = f + cc; l.bn.m_dy = f + 2 * cc; l.bn.m_dyxh = f + 3 * cc;
+            l.bn.eps = l.d.eps; l.bn.rows = l.rows;
+            l.bn_deferred_ok = (cc == 64) && !(cfg_.flags & N4J_FLAG_NO_DEFERRED_STATS);
+            if (l.bn_deferred_ok) ++n_def;
         }
+    }
+    // deferred statistics: [layer][forward|backward][set 0|1][2*64 strided doubles], one allocation so that one memset re-arms it
+    if (n_def > 0) {
+        bn_pool_len_ = (size_t)n_def * 4 * 128 * ACC_STRIDE;
+        N4J_CUDA(cudaMalloc(&bn_pool_, sizeof(double) * bn_pool_len_));
+        N4J_CUDA(cudaMemsetAsync(bn_pool_, 0, sizeof(double) * bn_pool_len_, stream_));
+        int k = 0;
+        for (auto& l : L_) if (l.d.kind == N4J_LAYER_BATCHNORM && l.bn_deferred_ok) { l.bn_pool = bn_pool_ + (size_t)(k++) * 4 * 128 * ACC_STRIDE; l.bn.deferred = 1; }
+        set_bn_slot(0);
     }
     N4J_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -296,7 +309,7 @@ Engine::~Engine() {
     for (DevBuf* b : {&params_, &gradflat_, &zt_, &gt_, &io_, &io2_, &gb_[0], &gb_[1], &gb_[2], &theta_tmp_, &wpart_, &dldt_}) cudaFree(b->p);
     for (void* pp : peer_ptrs_) cudaIpcCloseMemHandle(pp);
     cudaFree(comm_region_); cudaFree(comm_dev_);
-    cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(red_acc_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_); cudaFree(tcat_acc_); cudaFree(tcat_misc_);
+    cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(red_acc_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_); cudaFree(tcat_acc_); cudaFree(tcat_misc_); cudaFree(bn_pool_);
     cudaFreeHost(ctrl_host_); cudaFreeHost(tpair_host_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -351,6 +364,30 @@ int Engine::grid_red(long long n4) const {
     long long blocks = (n4 + 256LL * per - 1) / (256LL * per);
     blocks = std::max<long long>(1, std::min<long long>(blocks, n4 > (4LL << 20) ? 148 * 8 : cap));   // HBM-sized states need the extra loads in flight
     return (int)blocks;
+}
+// Deferred BatchNorm statistics: which accumulator set the evaluation being enqueued uses.  Consecutive evaluations alternate;
+// every solve (prologue: 2 evaluations, trial body: 6) starts on set 1 and ends on set 0, so the captured graphs bake a
+// position-independent pattern.  Eager one-off evaluations re-arm everything afterwards (bn_rearm_all).
+void Engine::set_bn_slot(int slot) {
+    bn_slot_ = slot;
+    for (auto& l : L_) {
+        if (l.d.kind != N4J_LAYER_BATCHNORM || !l.bn_pool) continue;
+        double* base = l.bn_pool;
+        const size_t set = 128 * ACC_STRIDE;
+        l.bn.accf = base + (size_t)(0 * 2 + slot) * set;
+        l.bn.accf_other = base + (size_t)(0 * 2 + (slot ^ 1)) * set;
+        l.bn.accb = base + (size_t)(1 * 2 + slot) * set;
+        l.bn.accb_other = base + (size_t)(1 * 2 + (slot ^ 1)) * set;
+    }
+}
+void Engine::begin_eval() {
+    if (eval_begun_) { eval_begun_ = false; return; }   // the caller already switched sets (stage combination in front of the evaluation)
+    set_bn_slot(bn_slot_ ^ 1);
+}
+void Engine::bn_rearm_all(cudaStream_t s) {
+    if (bn_pool_) N4J_CUDA(cudaMemsetAsync(bn_pool_, 0, sizeof(double) * bn_pool_len_, s));
+    set_bn_slot(0);
+    eval_begun_ = false;
 }
 // stage combination + statistics of a leading 64-channel BatchNorm in one pass
 BnFuse Engine::bn_fuse() const {
@@ -501,6 +538,7 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
     Ref cur = in;
     bool image_ready = false;   // the previous layer already wrote the operand image of this (tensor-core) conv
     bool pro_pending = false;   // ... or left its BatchNorm apply to the conv kernel's operand prologue
+    if (!in_aug_) begin_eval();
     ConvTcArgs pro_args{};
     bool stats_ready = bn1_ready;   // the previous kernel (conv epilogue / stage combination) already produced this BatchNorm's mean / invstd
     for (size_t i = 0; i < L_.size(); ++i) {
@@ -608,7 +646,10 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
     }
     fwd_left_last_bn_ = false;
     fuse_last_bn_ok_ = true;
+    begin_eval();
+    in_aug_ = true;
     enqueue_rhs_fwd(s, in, out, true, bn1_ready);
+    in_aug_ = false;
     fuse_last_bn_ok_ = false;
     Ref g = with_off(in, off_a_);
     float gscale = -1.f;                                 // zAdjoint().negi() :75
@@ -646,13 +687,14 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     bpro_args = ConvTcArgs{};
                     bpro_args.px = x; bpro_args.py = y; bpro_args.pg = g; bpro_args.pgscale = gscale; bpro_args.pgamma = params_.p + l.p_off;
                     bpro_args.pbn = l.bn; bpro_args.pact = l.d.activation; bpro_args.pcompact = l.gin;
+                    bpro_args.pdgamma = dth; bpro_args.pdbeta = with_off(dth, cc);
                     gimg_ready = true;
                 } else if (feeds_tc) {
                     LAUNCH(k_bn_bwd_dx_to_image, grid_for(l.in_len / 4), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, geom_,
-                           l.gin, L_[i - 1].gimg);
+                           l.gin, L_[i - 1].gimg, dth, with_off(dth, cc));
                     gimg_ready = true;
                 } else {
-                    LAUNCH(k_bn_bwd_dx, grid_for(l.in_len), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, l.rows, cc, dx);
+                    LAUNCH(k_bn_bwd_dx, grid_for(l.in_len), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, l.rows, cc, dx, dth, with_off(dth, cc));
                 }
                 break;
             }
@@ -775,11 +817,13 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
 void Engine::enqueue_prologue(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt) {
     Ref ycur{Y_, &ctrl_->y_cur, n_alloc_, 0, 0};
     Ref ywork{Y_, &ctrl_->y_cur, n_alloc_, 0, 1};
+    set_bn_slot(0); eval_begun_ = false;                // every solve starts on statistics set 1 (see set_bn_slot)
     LAUNCH(k_solve_begin, 1, 32, s, ctrl_, tpair_);
     if (dense_out) LAUNCH(k_dense_edge, grid_for(nz_), 256, s, ctrl_, Y_, n_alloc_, nz_, wanted_, 0, 0, zt_.p + nz_, nz_);
     tspec_ = TimeSpec{0, 0.f, 0.f};                                                  // time + timeOffset(0)
     enqueue_rhs(s, aug, ycur, Ref{K_, &ctrl_->krow[0], n_alloc_, 0, 0});            // AdaptiveRungeKuttaSolver.java:131
     LAUNCH(k_init_sums, grid_red(n4), 256, s, ctrl_, Y_, K_, n_alloc_, n4, sp);
+    set_bn_slot(bn_slot_ ^ 1); eval_begun_ = true;      // the combination below already produces statistics of the NEXT evaluation
     const BnFuse bf = bn_fuse();
     LAUNCH(k_stage_combine<0>, bf.enabled ? grid_red(n4) : grid_for(n4), 256, s, ctrl_, Y_, K_, n_alloc_, 0LL, n4, bf);  // equation.step(ones(1), step)
     tspec_ = TimeSpec{1, 0.f, 0.f};                                                  // timeOffset = the first guess (equation.step above)
@@ -796,15 +840,18 @@ static void launch_combine(cudaStream_t s, int grid, Ctrl* c, float* Y, float* K
 void Engine::enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverParams& sp, bool dense_out, int nt,
                            cudaGraphConditionalHandle cond, int use_cond) {
     Ref ywork{Y_, &ctrl_->y_cur, n_alloc_, 0, 1};
-    const BnFuse bf = bn_fuse();
+    set_bn_slot(0); eval_begun_ = false;                // six evaluations: sets 1,0,1,0,1,0 — the body ends where it started
+    const BnFuse bf0 = bn_fuse();
     // Adjoint solves: f and the vjp only read the z and a blocks of the stage state, so stages 1-6 combine just those
     // (n4_main); the theta block of y1 is combined once, right before the error norm, after the side branch (weight
     // gradients of all six stages) has been joined.
     const bool split = aug && side_capable_;
     const long long n4_main = split ? (2 * nz_pad_) / 4 : n4;
-    const int grid = bf.enabled ? grid_red(n4_main) : grid_for(n4_main);
+    const int grid = bf0.enabled ? grid_red(n4_main) : grid_for(n4_main);
     BnFuse nobf{};
     for (int st = 1; st <= 6; ++st) {
+        set_bn_slot(bn_slot_ ^ 1); eval_begun_ = true;  // the combination produces the first BatchNorm's statistics of this stage's evaluation
+        const BnFuse bf = bn_fuse();
         switch (st) {
             case 1: launch_combine<1>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
             case 2: launch_combine<2>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
@@ -1016,7 +1063,7 @@ void Engine::comm_init(int rank, int world, const void* handles, long long globa
     world_ = world; rank_id_ = rank;
     if (world > 1) {
         N4J_CUDA(cudaMemcpy(&ctrl_->comm, &comm_dev_, sizeof(CommDev*), cudaMemcpyHostToDevice));
-        for (auto& l : L_) { l.bn.cm = comm_dev_; l.bn.rows_total = l.rows * world; }
+        for (auto& l : L_) { l.bn.cm = comm_dev_; l.bn.rows_total = l.rows * world; l.bn.deferred = 0; }   // the last block exchanges the sums: legacy finalisation
     } else {
         cudaFree(comm_dev_); comm_dev_ = nullptr;
     }
@@ -1194,6 +1241,7 @@ void Engine::backward(const float* last_output, const float* dLdz, const float* 
             // d = <dL/dz(t_step) raw, f(z(t_step), t_step)>: one extra RHS evaluation
             tspec_ = TimeSpec{3, 0.f, th[step]};      // CalcTimeGrad.java:52: calculateDerivative(zt1, time.getColumn(1), ...)
             enqueue_rhs_fwd(stream_, fixed_ref(const_cast<float*>(z_k)), fixed_ref(gb_[2].p));
+            bn_rearm_all(stream_);
             LAUNCH(k_dot, grid_for(nz_), 256, stream_, g_k, gb_[2].p, nz_, dot_acc_);
             LAUNCH(k_tg_step, 1, 32, stream_, ctrl_, dot_acc_, tg_, Y_, n_alloc_, off_t_, dldt_.p, step, 0);
         }
@@ -1247,6 +1295,7 @@ void Engine::rhs(const float* z, float t, float* fz) {
     state_in(z, gb_[0].p);
     tspec_ = TimeSpec{3, 0.f, t};
     enqueue_rhs_fwd(stream_, fixed_ref(gb_[0].p), fixed_ref(gb_[1].p));
+    bn_rearm_all(stream_);
     const bool dev = is_device_ptr(fz);
     float* o = dev ? fz : io_.p;
     state_out(gb_[1].p, o);
@@ -1267,6 +1316,7 @@ void Engine::rhs_vjp(const float* z, float t, const float* g, float* fz, float* 
     tspec_ = TimeSpec{3, 0.f, t};
     aug_tslot_ = false;
     enqueue_rhs_aug(stream_, fixed_ref(Y_), fixed_ref(K_));
+    bn_rearm_all(stream_);
     auto emit = [&](const float* internal, float* user) {
         const bool dev = is_device_ptr(user);
         float* o = dev ? user : io_.p;
@@ -1421,6 +1471,8 @@ void Engine::bench_piece(int what, int iters, float* us) {
     float ms = 0;
     N4J_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
     *us = ms * 1000.f / (float)iters;
+    bn_rearm_all(stream_);
+    N4J_CUDA(cudaStreamSynchronize(stream_));
 }
 
 }  // namespace n4j

@@ -47,6 +47,8 @@ struct LayerPlan {
     float* wimg_f = nullptr; // conv: per-tap weight images, forward
     float* wimg_b = nullptr; // conv: per-tap weight images, dgrad (flipped taps, transposed)
     BnScratch bn{};
+    double* bn_pool = nullptr;     // deferred statistics: this layer's four accumulator sets inside Engine::bn_pool_
+    bool bn_deferred_ok = false;
 };
 
 struct DevBuf {
@@ -138,6 +140,14 @@ private:
     float* wanted_ = nullptr;     // requested times (device)
     int wanted_cap_ = 0;
     double* dot_acc_ = nullptr;
+    // deferred BatchNorm statistics (layer_kernels.cuh: BnScratch)
+    double* bn_pool_ = nullptr;
+    size_t bn_pool_len_ = 0;
+    int bn_slot_ = 0;
+    bool eval_begun_ = false, in_aug_ = false;
+    void set_bn_slot(int slot);
+    void begin_eval();
+    void bn_rearm_all(cudaStream_t s);
     // time input (N4J_LAYER_TIME_CONCAT)
     bool time_input_ = false;
     bool aug_tslot_ = false;      // the adjoint solve being enqueued carries a time slot (CalcTimeGrad)

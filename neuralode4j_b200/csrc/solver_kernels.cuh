@@ -102,11 +102,12 @@ __global__ void __launch_bounds__(256) k_stage_combine(const Ctrl* __restrict__ 
                 double a = 0, b = 0;
                 for (int r = 0; r < 16; ++r) { a += sm[0][k][r * 16 + threadIdx.x]; b += sm[1][k][r * 16 + threadIdx.x]; }
                 const int ch = threadIdx.x * 4 + k;
-                atomicAdd(bf.sc.acc + ch * ACC_STRIDE, a);
-                atomicAdd(bf.sc.acc + (64 + ch) * ACC_STRIDE, b);
+                atomicAdd((bf.sc.deferred ? bf.sc.accf : bf.sc.acc) + ch * ACC_STRIDE, a);
+                atomicAdd((bf.sc.deferred ? bf.sc.accf : bf.sc.acc) + (64 + ch) * ACC_STRIDE, b);
             }
             __threadfence();
         }
+        if (bf.sc.deferred) { bn_rearm(bf.sc.accf_other, threadIdx.x); return; }   // the consumers finalise (layer_kernels.cuh: BnScratch)
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned int tk = atomicAdd(bf.sc.ticket, 1u);
