@@ -43,9 +43,10 @@ inline ConvGeom make_conv_geom(int B, int H, int W) {
 }
 inline long long conv_image_floats(const ConvGeom& g) { return 2LL * 16 * g.rows * 4; }   // hi + lo
 
-constexpr int CONV_TC_THREADS = 192;       // producer warp, MMA warp, four epilogue warps
-constexpr int CONV_TC_THREADS_PRO = 256;   // fused operand prologue: two more warps, and ALL eight build the A tile
+constexpr int CONV_TC_THREADS = 320;       // producer warp, MMA warp, eight epilogue warps (two per TMEM lane quadrant: 32 columns each)
+constexpr int CONV_TC_THREADS_PRO = 512;   // fused operand prologue: ALL sixteen warps build the A tile (latency-bound code: more warps, less work each)
 constexpr int conv_tc_threads(int pro) { return pro ? CONV_TC_THREADS_PRO : CONV_TC_THREADS; }
+constexpr int CONV_TC_EPI_THREADS = 256;
 constexpr int CONV_TC_STAGES = 4;
 constexpr int CONV_TC_WSTAGE_BYTES = 2 * 16 * 64 * 16;   // hi+lo image of one tap: 32 KB
 
@@ -74,8 +75,8 @@ __global__ void __launch_bounds__(256) k_conv_w_to_tc(const float* __restrict__ 
     }
 }
 
-// small all-reduce by the four epilogue warps of the conv kernel (named barrier 1 instead of __syncthreads)
-struct EpilogueSyncFn { __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 1, 128;" ::: "memory"); } };
+// small all-reduce by the first four epilogue warps of the conv kernel (named barrier 2 instead of __syncthreads)
+struct EpilogueSyncFn { __device__ __forceinline__ void operator()() const { asm volatile("bar.sync 2, 128;" ::: "memory"); } };
 __device__ __forceinline__ void comm_allreduce_epilogue(CommDev* cm, double* vals, int n, int et) {
     comm_allreduce_small(cm, vals, n, et, 128, EpilogueSyncFn{});
 }
@@ -147,7 +148,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
     asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if constexpr (PRO != 0) {
-        // ---- fused operand prologue, all eight warps: BatchNorm apply (+ReLU) or BatchNorm backward dx, TF32 hi/lo split,
+        // ---- fused operand prologue, all sixteen warps: BatchNorm apply (+ReLU) or BatchNorm backward dx, TF32 hi/lo split,
         // zero padding.  The weight ring is already being filled (below) while this runs.  A warp owns blocks of 8 rows x 4
         // channel chunks: per quarter warp the shared-memory stores are 128 contiguous bytes (no bank conflicts) and the
         // global loads are 64 contiguous bytes per row.  All loads of a thread are issued before the first use (one L2
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         // the last block of the statistics kernel used to do.
         __shared__ float s_fin[4][64];     // mean, invstd, mean(dy), mean(dy*xhat)
         double raw[4] = {0.0, 0.0, 0.0, 0.0};
-        if (a.pbn.deferred && threadIdx.x < 64) {
+        if (a.pbn.deferred && warp < 2) {      // warp-uniform on purpose: a real branch, not predicated double-precision code in all warps
             raw[0] = a.pbn.accf[threadIdx.x * ACC_STRIDE]; raw[1] = a.pbn.accf[(64 + threadIdx.x) * ACC_STRIDE];
             if (PRO == 2) { raw[2] = a.pbn.accb[threadIdx.x * ACC_STRIDE]; raw[3] = a.pbn.accb[(64 + threadIdx.x) * ACC_STRIDE]; }
         }
@@ -187,18 +188,18 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         }
         const int per = g.PH * g.PW;
         const float inv_pw = 1.0f / (float)g.PW;
-        constexpr int U = 10;                        // rows r = (warp >> 2) * 8 + (lane & 7) + 16 u: 160 >= 128 + 2 * halo for W <= 14
+        constexpr int U = 5;                         // rows r = (warp >> 2) * 8 + (lane & 7) + 32 u: 160 >= 128 + 2 * halo for W <= 14
         const int rbase = (warp >> 2) * 8 + (lane & 7);
-        for (int rr = rbase; rr < rt; rr += 16 * U) {
+        for (int rr = rbase; rr < rt; rr += 32 * U) {
             int i4[U];
             float4 xv[U], gv[U], yv[U];
             const int pr0 = (int)m0 - g.halo + rr;     // padded rows fit 31 bits (checked where the tensor path is enabled)
-            // image index / position inside the padded image of the first row, advanced by 16 rows per item
+            // image index / position inside the padded image of the first row, advanced by 32 rows per item
             int bq = pr0 >= 0 ? (int)((unsigned)pr0 / (unsigned)per) : -1;
             int rem = pr0 >= 0 ? pr0 - bq * per : pr0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int r = rr + 16 * u;
+                const int r = rr + 32 * u;
                 i4[u] = -1;
                 if (r < rt && rem >= 0 && bq < g.B) {
                     const int ph = __float2int_rz(((float)rem + 0.5f) * inv_pw), pw = rem - ph * g.PW;
@@ -208,12 +209,12 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                     xv[u] = reinterpret_cast<const float4*>(px)[i4[u]];
                     if (PRO == 2) { gv[u] = reinterpret_cast<const float4*>(pg)[i4[u]]; yv[u] = reinterpret_cast<const float4*>(py)[i4[u]]; }
                 }
-                rem += 16;
+                rem += 32;
                 if (rem >= 0 && bq < 0) bq = 0;
                 while (rem >= per) { rem -= per; ++bq; }
             }
             if (a.pbn.deferred && rr == rbase) {       // first (for W <= 14: only) pass; every thread of the CTA gets here
-                if (threadIdx.x < 64) {
+                if (warp < 2) {
                     const int c = threadIdx.x;
                     const double M = (double)a.pbn.rows;
                     const double m = raw[0] / M;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int r = rr + 16 * u;
+                const int r = rr + 32 * u;
                 if (r < rt) {
                     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (i4[u] >= 0) {
@@ -326,9 +327,11 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             }
             tc::mma_commit(d_full);
         }
-    } else if (warp < 6) {
-        // ---- epilogue: TMEM lane = tile row; each thread owns one padded pixel and its 64 output channels ----
-        const int q = warp & 3;                    // TMEM lane quadrant this warp may read
+    } else if (warp < 10) {
+        // ---- epilogue, eight warps: TMEM lane = tile row = one padded pixel; a warp reads its lane quadrant (warp & 3, fixed by the
+        // hardware) and ONE 32-column half of the 64 output channels, so every quadrant is served by two warps ----
+        const int q = warp & 3;
+        const int half = (warp - 2) >> 2;            // warps 2-5: channels 0-31, warps 6-9: channels 32-63
         const int row = q * 32 + lane;
         const long long m = m0 + row;
         bool valid = m < g.mpad;
@@ -344,46 +347,48 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         float* __restrict__ out = resolve(a.out);
         float* sT = reinterpret_cast<float*>(sW);      // [128][65] transpose buffer(s); the weight ring is idle once d_full fires
         float* sT2 = sT + 128 * 65;
-        const int et = threadIdx.x - 64;               // 0..127
-        // EPI 2: while the tensor core works, fetch this pixel's row of the BatchNorm input / output and keep xhat and the
+        double* sP = reinterpret_cast<double*>(sT2 + 128 * 65);   // [4][128] partial column sums
+        const int et = threadIdx.x - 64;               // 0..255
+        // EPI 2: while the tensor core works, fetch this pixel's half row of the BatchNorm input / output and keep xhat and the
         // activation mask in registers
-        float xh[EPI == 2 ? 64 : 1];
-        unsigned long long mask = 0ull;
+        float xh[EPI == 2 ? 32 : 1];
+        unsigned int mask = 0u;
         if constexpr (EPI == 2) {
             __shared__ float s_mi[128];
             if (a.bn.deferred) {
                 if (et < 64) bn_fwd_final(a.bn, et, s_mi[et], s_mi[64 + et]);
             } else {
-                if (et < 64) s_mi[et] = a.bn.mean[et]; else s_mi[et] = a.bn.invstd[et - 64];
+                if (et < 64) s_mi[et] = a.bn.mean[et]; else if (et < 128) s_mi[et] = a.bn.invstd[et - 64];
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const bool relu = a.eact == N4J_ACT_RELU;
-            mask = relu ? 0ull : ~0ull;
+            mask = relu ? 0u : ~0u;
             if (valid) {
-                const float4* __restrict__ xr = reinterpret_cast<const float4*>(resolve(a.ex) + crow * 64);
-                const float4* __restrict__ yr = reinterpret_cast<const float4*>(resolve(a.ey) + crow * 64);
+                const float4* __restrict__ xr = reinterpret_cast<const float4*>(resolve(a.ex) + crow * 64 + half * 32);
+                const float4* __restrict__ yr = reinterpret_cast<const float4*>(resolve(a.ey) + crow * 64 + half * 32);
+                const float* smean = s_mi + half * 32;
+                const float* sinv = s_mi + 64 + half * 32;
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     const float4 xv = xr[j];
-                    xh[4 * j + 0] = __fmul_rn(__fsub_rn(xv.x, s_mi[4 * j + 0]), s_mi[64 + 4 * j + 0]);
-                    xh[4 * j + 1] = __fmul_rn(__fsub_rn(xv.y, s_mi[4 * j + 1]), s_mi[64 + 4 * j + 1]);
-                    xh[4 * j + 2] = __fmul_rn(__fsub_rn(xv.z, s_mi[4 * j + 2]), s_mi[64 + 4 * j + 2]);
-                    xh[4 * j + 3] = __fmul_rn(__fsub_rn(xv.w, s_mi[4 * j + 3]), s_mi[64 + 4 * j + 3]);
+                    xh[4 * j + 0] = __fmul_rn(__fsub_rn(xv.x, smean[4 * j + 0]), sinv[4 * j + 0]);
+                    xh[4 * j + 1] = __fmul_rn(__fsub_rn(xv.y, smean[4 * j + 1]), sinv[4 * j + 1]);
+                    xh[4 * j + 2] = __fmul_rn(__fsub_rn(xv.z, smean[4 * j + 2]), sinv[4 * j + 2]);
+                    xh[4 * j + 3] = __fmul_rn(__fsub_rn(xv.w, smean[4 * j + 3]), sinv[4 * j + 3]);
                     if (relu) {
                         const float4 yv = yr[j];
-                        mask |= (unsigned long long)((yv.x > 0.f ? 1u : 0u) | (yv.y > 0.f ? 2u : 0u) | (yv.z > 0.f ? 4u : 0u) | (yv.w > 0.f ? 8u : 0u)) << (4 * j);
+                        mask |= ((yv.x > 0.f ? 1u : 0u) | (yv.y > 0.f ? 2u : 0u) | (yv.z > 0.f ? 4u : 0u) | (yv.w > 0.f ? 8u : 0u)) << (4 * j);
                     }
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 64; ++j) xh[j] = 0.f;
-                mask = 0ull;
+                for (int j = 0; j < 32; ++j) xh[j] = 0.f;
+                mask = 0u;
             }
         }
         tc::mbar_wait(d_full, 0);
         tc::tc_fence_after();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {
             float v[32];
             tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + half * 32, v);
             if (PASSES == 3) {
@@ -404,62 +409,67 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             if constexpr (EPI == 2) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    sT[row * 65 + half * 32 + j] = ((mask >> (half * 32 + j)) & 1ull) ? v[j] : 0.f;     // dy = act'(y) * g
-                    sT2[row * 65 + half * 32 + j] = xh[half * 32 + j];
+                    sT[row * 65 + half * 32 + j] = ((mask >> j) & 1u) ? v[j] : 0.f;     // dy = act'(y) * g
+                    sT2[row * 65 + half * 32 + j] = xh[j];
                 }
             }
         }
         if constexpr (EPI != 0) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
-            const int c = et & 63, r0 = (et >> 6) * 64;
-            double s1 = 0.0, s2 = 0.0;
-            if constexpr (EPI == 1) {
-                for (int r = r0; r < r0 + 64; ++r) { const double x = (double)sT[r * 65 + c]; s1 += x; s2 += x * x; }
-            } else {
-                for (int r = r0; r < r0 + 64; ++r) { const double dy = (double)sT[r * 65 + c]; s1 += dy; s2 += dy * (double)sT2[r * 65 + c]; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps only
+            {   // column sums: 256 threads = 64 columns x 4 row quarters, combined through shared memory (one atomic per address and CTA)
+                const int c = et & 63, r0 = (et >> 6) * 32;
+                double p1 = 0.0, p2 = 0.0;
+                if constexpr (EPI == 1) {
+                    for (int r = r0; r < r0 + 32; ++r) { const double x = (double)sT[r * 65 + c]; p1 += x; p2 += x * x; }
+                } else {
+                    for (int r = r0; r < r0 + 32; ++r) { const double dy = (double)sT[r * 65 + c]; p1 += dy; p2 += dy * (double)sT2[r * 65 + c]; }
+                }
+                sP[(et >> 6) * 128 + c] = p1;
+                sP[(et >> 6) * 128 + 64 + c] = p2;
             }
-            if (a.bn.deferred) {      // accumulate only; the consumers finalise, CTA 0 re-arms the next evaluation's set
-                double* acc = EPI == 1 ? a.bn.accf : a.bn.accb;
-                atomicAdd(acc + c * ACC_STRIDE, s1);
-                atomicAdd(acc + (64 + c) * ACC_STRIDE, s2);
-                bn_rearm(EPI == 1 ? a.bn.accf_other : a.bn.accb_other, et);
-            } else {
-            atomicAdd(a.bn.acc + c * ACC_STRIDE, s1);
-            atomicAdd(a.bn.acc + (64 + c) * ACC_STRIDE, s2);
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            __shared__ int s_last;
-            if (et == 0) {
-                const unsigned int tk = atomicAdd(a.bn.ticket, 1u);
-                s_last = (tk == gridDim.x - 1);
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (s_last) {
-                __threadfence();
-                double* tot = reinterpret_cast<double*>(sT);          // 128 doubles, transposition buffer is free again
-                tot[et] = *((volatile double*)(a.bn.acc + et * ACC_STRIDE));
-                a.bn.acc[et * ACC_STRIDE] = 0.0;
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (a.bn.cm) comm_allreduce_epilogue(a.bn.cm, tot, 128, et);
-                const double Mt = a.bn.cm ? (double)a.bn.rows_total : (double)a.bn_rows;
-                if (et < 64) {
-                    if constexpr (EPI == 1) {
-                        const double mean = tot[et] / Mt;
-                        double var = tot[64 + et] / Mt - mean * mean;
-                        if (var < 0) var = 0;
-                        a.bn.mean[et] = (float)mean;
-                        a.bn.invstd[et] = (float)(1.0 / sqrt(var + (double)a.bn_eps));
-                    } else {
-                        const double sdy = tot[et], sdyxh = tot[64 + et];
-                        resolve(a.edgamma)[et] = (float)sdyxh;
-                        resolve(a.edbeta)[et] = (float)sdy;
-                        a.bn.m_dy[et] = (float)(sdy / Mt);
-                        a.bn.m_dyxh[et] = (float)(sdyxh / Mt);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et < 128) {
+                const double tsum = (sP[et] + sP[128 + et]) + (sP[256 + et] + sP[384 + et]);     // et < 64: first sums, else second sums
+                if (a.bn.deferred) {      // accumulate only; the consumers finalise, CTA 0 re-arms the next evaluation's set
+                    atomicAdd((EPI == 1 ? a.bn.accf : a.bn.accb) + et * ACC_STRIDE, tsum);
+                    bn_rearm(EPI == 1 ? a.bn.accf_other : a.bn.accb_other, et);
+                } else {                  // legacy / multi-GPU: the last CTA finalises (and exchanges the sums between the ranks)
+                    atomicAdd(a.bn.acc + et * ACC_STRIDE, tsum);
+                    __threadfence();
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    __shared__ int s_last;
+                    if (et == 0) {
+                        const unsigned int tk = atomicAdd(a.bn.ticket, 1u);
+                        s_last = (tk == gridDim.x - 1);
+                    }
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (s_last) {
+                        __threadfence();
+                        double* tot = reinterpret_cast<double*>(sT);          // 128 doubles, transposition buffer is free again
+                        tot[et] = *((volatile double*)(a.bn.acc + et * ACC_STRIDE));
+                        a.bn.acc[et * ACC_STRIDE] = 0.0;
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
+                        if (a.bn.cm) comm_allreduce_epilogue(a.bn.cm, tot, 128, et);
+                        const double Mt = a.bn.cm ? (double)a.bn.rows_total : (double)a.bn_rows;
+                        if (et < 64) {
+                            if constexpr (EPI == 1) {
+                                const double mean = tot[et] / Mt;
+                                double var = tot[64 + et] / Mt - mean * mean;
+                                if (var < 0) var = 0;
+                                a.bn.mean[et] = (float)mean;
+                                a.bn.invstd[et] = (float)(1.0 / sqrt(var + (double)a.bn_eps));
+                            } else {
+                                const double sdy = tot[et], sdyxh = tot[64 + et];
+                                resolve(a.edgamma)[et] = (float)sdyxh;
+                                resolve(a.edbeta)[et] = (float)sdy;
+                                a.bn.m_dy[et] = (float)(sdy / Mt);
+                                a.bn.m_dyxh[et] = (float)(sdyxh / Mt);
+                            }
+                        }
+                        if (et == 0) *a.bn.ticket = 0u;
                     }
                 }
-                if (et == 0) *a.bn.ticket = 0u;
             }
-            }   // legacy (multi-GPU / non-deferred) finalisation
         }
     }
     tc::tc_fence_before();
