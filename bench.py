@@ -269,8 +269,11 @@ def run_ours(args):
     conv_us = v.bench_piece(_lib.BENCH_CONV_FWD, 50)
     dgrad_us = v.bench_piece(_lib.BENCH_CONV_DGRAD, 50)
     wgrad_us = v.bench_piece(_lib.BENCH_CONV_WGRAD, 50)
-    conv_fused_us = v.bench_piece(_lib.BENCH_CONV_FWD_FUSED, 50)      # as launched inside an evaluation: BN-apply prologue + stats epilogue
-    dgrad_fused_us = v.bench_piece(_lib.BENCH_CONV_DGRAD_FUSED, 50)  # BN-backward prologue + backward-stats epilogue
+    try:
+        conv_fused_us = v.bench_piece(_lib.BENCH_CONV_FWD_FUSED, 50)      # as launched inside an evaluation: BN-apply prologue + stats epilogue
+        dgrad_fused_us = v.bench_piece(_lib.BENCH_CONV_DGRAD_FUSED, 50)  # BN-backward prologue + backward-stats epilogue
+    except ValueError:                                                    # every fusion switched off by --flags: the bare kernels are the launches
+        conv_fused_us, dgrad_fused_us = conv_us, dgrad_us
     rhs_us = v.bench_piece(_lib.BENCH_RHS_FWD, 50)
     aug_us = v.bench_piece(_lib.BENCH_RHS_AUG, 50)
     n_aug = 2 * nz + v.numParams()

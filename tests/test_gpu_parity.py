@@ -220,6 +220,34 @@ def test_mnist_block_prologue_fusion_matches_separate_kernels():
     assert _rel_l2(b["grad"], a["grad"]) < 1e-3
 
 
+@pytest.mark.parametrize("batch,hw", [(5, 5), (3, 14), (16, 9), (33, 4)])
+def test_tensor_conv_block_odd_geometries(batch, hw):
+    """The fused tcgen05 conv launches (operand prologue, statistics epilogues, deferred statistics) on geometries that do not
+    line up with the 128-pixel tiles: odd batch sizes, feature maps from 4x4 to 14x14 (halo of 16 rows: the prologue's second
+    pass), tiles that straddle images.  Forward state against the oracle (rtol 1e-4), adjoint against the parity-mode engine."""
+    w = W.mnist_block(batch=batch, channels=64, hw=hw)
+    r = H.run_cuda(w)
+    o = H.run_oracle(w, r["eps"])
+    assert r["fwd_stats"] == o["fwd_stats"]
+    H.assert_close(r["out"], o["out"], RTOL, 1e-5 * np.abs(o["out"]).max(), "out")
+    e = H.run_cuda(w, flags=EXACT)
+    assert e["bwd_stats"] == o["bwd_stats"]
+    H.assert_close(e["dy0"], o["dy0"], RTOL, 1e-5 * np.abs(o["dy0"]).max(), "dy0 (parity mode)")
+    # ReLU+BatchNorm adjoint sensitivity (see test_mnist_block_small_default_mode) grows as the batch statistics get fewer rows
+    assert _rel_l2(r["dy0"], o["dy0"]) < 5e-2 and _rel_l2(r["grad"], o["grad"]) < 5e-2
+    rng = np.random.default_rng(17)
+    g = rng.standard_normal(w.shape).astype(np.float32)
+    v = w.conf.instantiate(w.shape)
+    v.setParams(w.params)
+    try:
+        fz, dz, dreal = v.rhs_vjp(w.y0, g)
+    finally:
+        v.close()
+    ofz, odz, odreal = H.oracle_for(w).rhs_vjp(w.params, w.y0, g)
+    for a, b, name in ((fz, ofz, "f"), (dz, odz, "dz"), (dreal, odreal, "dtheta")):
+        assert np.abs(a - b).max() <= 3e-5 * np.abs(b).max(), name
+
+
 def test_mnist_block_smooth_activation_default_mode():
     """BatchNorm+tanh variant: smooth adjoint, so the default mode meets rtol 1e-4 as well."""
     w = W.mnist_block(batch=16, channels=64)
