@@ -337,6 +337,36 @@ def test_exact_stage_times_flag_matches_oracle_variant():
     H.assert_close(b["out"], out, RTOL, 1e-5 * np.abs(out).max(), "exact stage times")
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# committed fixtures (tests/golden/oracle_vectors.npz, written by tests/golden/make_golden.py)
+# ---------------------------------------------------------------------------------------------------------------
+def _golden_cases():
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, np.load(os.path.join(here, "oracle_vectors.npz"))
+
+
+@pytest.mark.parametrize("name", ["mnist_b4_hw5", "mnist_c8_b3_hw4", "spiral_b8_nt5", "anode_time_input_b16_nt3",
+                                  "anode_time_fixed_b16", "conv_time_b2_c8_hw4_k3"])
+def test_cuda_matches_committed_fixtures(name):
+    """The CUDA path (parity mode) against the COMMITTED oracle vectors: independent of the oracle build on the box."""
+    mod, fx = _golden_cases()
+    w = mod.cases()[name]
+    r = H.run_cuda(w, flags=EXACT)
+    if not name.startswith("spiral"):       # atol 1e-12: accept/reject at rounding level (see test_spiral_block_small)
+        assert list(r["fwd_stats"]) + list(r["bwd_stats"]) == fx[name + "/counts"].tolist()
+    H.assert_close(r["out"], fx[name + "/out"], RTOL, 1e-5 * np.abs(fx[name + "/out"]).max(), "out")
+    H.assert_close(r["dy0"], fx[name + "/dy0"], RTOL, 1e-5 * np.abs(fx[name + "/dy0"]).max(), "dy0")
+    g, gs = np.asarray(r["grad"]), fx[name + "/grad_sample"]
+    H.assert_close(g[mod.grad_sample_index(g.size)], gs, RTOL, 1e-5 * np.abs(gs).max(), "grad sample")
+    if name + "/dt" in fx and r["dt"] is not None:
+        H.assert_close(r["dt"], fx[name + "/dt"], RTOL, 1e-5 * max(np.abs(fx[name + "/dt"]).max(), 1e-30), "dt")
+
+
 def test_single_stepping_equals_interpolating():
     # InterpolatingMultiStepSolverTest.java:26-37: both multi-step solvers agree to 1e-4
     w = W.golden_linear(1)

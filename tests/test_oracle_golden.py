@@ -439,3 +439,41 @@ def test_stage_time_quirk_is_observable_only_with_time_input():
 def test_time_concat_must_be_first():
     with pytest.raises(Exception):
         O.Oracle([dict(kind="dense", n_out=4), dict(kind="time_concat", n_out=1), dict(kind="dense", n_out=4)], (2, 4))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# committed fixtures (tests/golden/)
+# ---------------------------------------------------------------------------------------------------------------------
+def _golden():
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, np.load(os.path.join(here, "oracle_vectors.npz")), os.path.join(here, "reference_vectors.json")
+
+
+def test_reference_vector_fixture_is_what_the_oracle_is_pinned_against():
+    import json
+    _, _, path = _golden()
+    ref = json.load(open(path))
+    np.testing.assert_array_equal(np.array(ref["ys_fwd"]), H.GOLDEN_YS_FWD)
+    np.testing.assert_array_equal(np.array(ref["dtheta_bwd"]), H.GOLDEN_DTHETA_BWD)
+    np.testing.assert_array_equal(np.array(ref["dt_fwd"]), H.GOLDEN_DT_FWD)
+
+
+def test_oracle_reproduces_committed_fixtures():
+    """tests/golden/oracle_vectors.npz was written by tests/golden/make_golden.py from this oracle; a change of its arithmetic shows
+    up here (same compiler flags, no contraction: reproducible to the last bits; 1e-6 leaves room for a different libm)."""
+    mod, fx, _ = _golden()
+    for name, w in mod.cases().items():
+        interp = w.conf.odeForwardConf.interpolateForwardIfMultiStep
+        out = H.oracle_for(w).forward(w.params, w.y0, w.time, interpolate=interp)
+        o = H.run_oracle(w, w.epsilon(out.shape))
+        assert list(o["fwd_stats"]) + list(o["bwd_stats"]) == fx[name + "/counts"].tolist(), name
+        np.testing.assert_allclose(o["out"], fx[name + "/out"], rtol=1e-6, atol=1e-7, err_msg=name)
+        np.testing.assert_allclose(o["dy0"], fx[name + "/dy0"], rtol=1e-5, atol=1e-7 * np.abs(fx[name + "/dy0"]).max(), err_msg=name)
+        g = np.asarray(o["grad"], np.float32)
+        gs = fx[name + "/grad_sample"]
+        np.testing.assert_allclose(g[mod.grad_sample_index(g.size)], gs, rtol=1e-5, atol=1e-6 * np.abs(gs).max(), err_msg=name)
