@@ -161,6 +161,7 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
         L_.push_back(lp);
     }
     if (L_.empty()) throw Error{N4J_ERR_INVALID_ARGUMENT, "inner graph has no layers"};
+    for (int i = (int)L_.size() - 1; i >= 0; --i) if (L_[i].d.kind == N4J_LAYER_CONV3X3) first_conv_ = i;
     if (c != C_) throw Error{N4J_ERR_INVALID_ARGUMENT, "inner graph must map the state shape onto itself"};
     n_params_ = po; n_real_ = go;
     real_pad_ = round_up4(n_real_);
@@ -638,7 +639,7 @@ void Engine::join_side(cudaStream_t s) {
 
 // slot: which activation / gradient buffer set this evaluation uses; defer_join: leave the weight-gradient kernels running on
 // the side branch (the caller joins before it touches the theta block of the K rows).
-void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, int slot, bool defer_join) {
+void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, int slot, bool defer_join, bool last_of_trial) {
     for (auto& l : L_) { l.act = l.act2[slot]; l.gin = l.gin2[slot]; }
     if (slot_event_valid_[slot]) {   // the evaluation that used this buffer set before must have finished its side work
         N4J_CUDA(cudaStreamWaitEvent(s, slot_event_[slot], 0));
@@ -776,7 +777,10 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     N4J_CUDA(cudaEventRecord(ef, s));
                     N4J_CUDA(cudaStreamWaitEvent(side_, ef, 0));
                     // at most 64 CTAs: they share the chip with the CTAs of the main chain
-                    const int ipc = (int)((B_ + 63) / 64), wg_ctas = (int)((B_ + ipc - 1) / ipc);
+                    // ... except the very last weight gradient of a trial step: the main chain has nothing heavy left and waits for
+                    // the join, so that launch takes one image per CTA (half the latency)
+                    const bool wide = last_of_trial && i == first_conv_;
+                    const int ipc = wide ? 1 : (int)((B_ + 63) / 64), wg_ctas = (int)((B_ + ipc - 1) / ipc);
                     k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, side_>>>(x, d, geom_, wpart_.p, ipc);
                     ++launches_;
                     LAUNCH(k_wgrad_reduce, 144, 256, side_, wpart_.p, dth, wg_ctas);
@@ -865,7 +869,7 @@ void Engine::enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverP
         // (FirstOrderEquationWithState.java:45,82); N4J_FLAG_EXACT_STAGE_TIMES uses the tableau's c_s instead
         static const double kC[6] = {1.0 / 5.0, 3.0 / 10.0, 4.0 / 5.0, 8.0 / 9.0, 1.0, 1.0};
         tspec_ = (cfg_.flags & N4J_FLAG_EXACT_STAGE_TIMES) ? TimeSpec{2, (float)kC[st - 1], 0.f} : TimeSpec{1, 0.f, 0.f};
-        if (aug) enqueue_rhs_aug(s, ywork, Ref{K_, &ctrl_->krow[st], n_alloc_, 0, 0}, bf.enabled != 0, st & 1, split);
+        if (aug) enqueue_rhs_aug(s, ywork, Ref{K_, &ctrl_->krow[st], n_alloc_, 0, 0}, bf.enabled != 0, st & 1, split, st == 6);
         else enqueue_rhs_fwd(s, ywork, Ref{K_, &ctrl_->krow[st], n_alloc_, 0, 0}, false, bf.enabled != 0);
     }
     if (split) {
@@ -986,6 +990,7 @@ void Engine::reset_ctrl() {
     pending_graph_runs_.clear();
     N4J_CUDA(cudaEventRecord(ev0_, stream_));
     LAUNCH(k_reset_ctrl, 1, 32, stream_, ctrl_);
+    bn_rearm_all(stream_);     // every API call starts from clean statistics sets, whatever a failed call may have left behind
 }
 
 void Engine::set_time_pairs(const std::vector<float>& pairs) {

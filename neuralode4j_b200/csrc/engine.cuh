@@ -181,7 +181,8 @@ private:
     void theta_internal_to_real(const float* theta, float* real);
 
     void enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact = true, bool bn1_ready = false);
-    void enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready = false, int slot = 0, bool defer_join = false);
+    void enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready = false, int slot = 0, bool defer_join = false, bool last_of_trial = false);
+    int first_conv_ = -1;
     void join_side(cudaStream_t s);
     void launch_gemm_tc(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& a);
     void launch_conv_tc(cudaStream_t s, const float* img, const float* wimg, Ref out, int act, const LayerPlan* next_bn = nullptr,
