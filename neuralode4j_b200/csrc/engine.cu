@@ -226,6 +226,12 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
             l.tc = !exact_ && !(cfg_.flags & N4J_FLAG_NO_TENSOR) && l.c_in == 64 && l.c_out == 64 && l.d.activation == N4J_ACT_IDENTITY;
             if (l.tc && (long long)B_ * (H_ + 2) * (W_ + 2) * 64 >= (1LL << 31)) l.tc = false;   // the tensor kernels index padded pixels x channels in 32 bits
             if (l.tc) {
+                // large feature maps: the staged tile (+halo) or the per-image weight-gradient staging would not fit one SM's shared
+                // memory -> the fp32 SIMT kernels take the layer
+                const ConvGeom gg = make_conv_geom((int)B_, H_, W_);
+                if (conv_tc_smem_bytes(gg) + 4096 > 227 * 1024 || conv_wgrad_smem_bytes(gg) > 200 * 1024) l.tc = false;
+            }
+            if (l.tc) {
                 geom_ = make_conv_geom((int)B_, H_, W_);
                 conv_smem_ = conv_tc_smem_bytes(geom_);
                 const size_t img_bytes = sizeof(float) * conv_image_floats(geom_);
@@ -238,7 +244,6 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
                 set_conv_smem_all(conv_smem_);
                 side_capable_ = true;
                 wgrad_smem_ = conv_wgrad_smem_bytes(geom_);
-                if (wgrad_smem_ > 200 * 1024) throw Error{N4J_ERR_UNSUPPORTED, "feature map too large for the native conv weight-gradient kernel"};
                 N4J_CUDA(cudaFuncSetAttribute(k_conv_wgrad64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_));
                 ensure(wpart_, (long long)B_ * 9 * 4096);
             }

@@ -220,11 +220,11 @@ def test_mnist_block_prologue_fusion_matches_separate_kernels():
     assert _rel_l2(b["grad"], a["grad"]) < 1e-3
 
 
-@pytest.mark.parametrize("batch,hw", [(5, 5), (3, 14), (16, 9), (33, 4)])
+@pytest.mark.parametrize("batch,hw", [(5, 5), (3, 14), (16, 9), (33, 4), (2, 20)])
 def test_tensor_conv_block_odd_geometries(batch, hw):
     """The fused tcgen05 conv launches (operand prologue, statistics epilogues, deferred statistics) on geometries that do not
     line up with the 128-pixel tiles: odd batch sizes, feature maps from 4x4 to 14x14 (halo of 16 rows: the prologue's second
-    pass), tiles that straddle images.  Forward state against the oracle (rtol 1e-4), adjoint against the parity-mode engine."""
+    pass), tiles that straddle images; 20x20 does not fit the shared-memory staging and must fall back to the SIMT kernels.  Forward state against the oracle (rtol 1e-4), adjoint against the parity-mode engine."""
     w = W.mnist_block(batch=batch, channels=64, hw=hw)
     r = H.run_cuda(w)
     o = H.run_oracle(w, r["eps"])
