@@ -335,6 +335,7 @@ def run_ours(args):
                             "n_aug": n_aug, "us_aug": pass_aug_us, "gbs_aug": 160.0 * n_aug / (pass_aug_us * 1e-6) / 1e9,
                             "n_hbm": 1 << 26, "us_hbm": pass_big_us, "achieved": 160.0 * (1 << 26) / (pass_big_us * 1e-6) / 1e9,
                             "peak": peaks["hbm"], "unit": "GB/s", "frac": 160.0 * (1 << 26) / (pass_big_us * 1e-6) / 1e9 / peaks["hbm"],
+                            "frac_of_nominal_8TBs": 160.0 * (1 << 26) / (pass_big_us * 1e-6) / 1e9 / 8000.0,
                             "note": "fwd/aug sizes are L2-resident (algorithmic GB/s can exceed HBM peak); n_hbm is the HBM-resident measurement"},
         "cpu_baseline": cpu,
         "solver": {"fwd": {"nfe": fwd_stats[0], "accepted": fwd_stats[1], "rejected": fwd_stats[2]},

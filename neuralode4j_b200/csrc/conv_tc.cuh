@@ -97,7 +97,7 @@ struct ConvTcArgs {
     //   PRO = 1  forward : A = act(gamma * ((x - mean) * invstd) + beta)                      (BatchNorm apply of the layer in front)
     //   PRO = 2  backward: A = gamma*invstd * ((dy - mean(dy)) - xhat * mean(dy*xhat)),  dy = act'(y) * gscale * g
     //                      (BatchNorm backward of the layer BEHIND the conv whose dgrad this launch computes)
-    Ref px, py, pg;       // x: BatchNorm input, y: BatchNorm output (PRO 2), g: gradient w.r.t. the BatchNorm output (PRO 2)
+    Ref px, pg;           // x: BatchNorm input, g: gradient w.r.t. the BatchNorm output (PRO 2; its output y is recomputed from x)
     float pgscale;
     const float* pgamma;
     const float* pbeta;
@@ -108,7 +108,9 @@ struct ConvTcArgs {
     // fused BatchNorm BACKWARD statistics in the epilogue (EPI == 2, dgrad launches): the output of this launch is the gradient
     // w.r.t. the output of the BatchNorm layer in front of the conv; sums of dy and dy*xhat over the batch, last CTA writes
     // dgamma / dbeta / mean(dy) / mean(dy*xhat) (same contract as k_bn_bwd_stats64).  `bn`, `bn_rows` describe that layer.
-    Ref ey, ex;           // its output (post activation) and its input, compact NHWC
+    Ref ex;               // its input, compact NHWC (its output's sign is recomputed from it)
+    const float* egamma;
+    const float* ebeta;
     int eact;             // its activation (ReLU or identity)
     Ref edgamma, edbeta;
 };
@@ -161,7 +163,6 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         }
         const int chunk = (warp & 3) * 4 + (lane >> 3), c0 = chunk * 4;
         const float* __restrict__ px = resolve(a.px);
-        const float* __restrict__ py = PRO == 2 ? resolve(a.py) : nullptr;
         const float* __restrict__ pg = PRO == 2 ? resolve(a.pg) : nullptr;
         // only ReLU / identity are fused (the engine keeps the separate kernels for ELU / tanh): no transcendental code in this kernel
         const bool relu = a.pact == N4J_ACT_RELU;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             gam[k] = a.pgamma[c0 + k];
-            bet[k] = PRO == 1 ? a.pbeta[c0 + k] : 0.f;
+            bet[k] = a.pbeta[c0 + k];
             mdy[k] = 0.f; mdyxh[k] = 0.f;
             if (!a.pbn.deferred) {
                 mean[k] = a.pbn.mean[c0 + k]; inv[k] = a.pbn.invstd[c0 + k];
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         const int rbase = (warp >> 2) * 8 + (lane & 7);
         for (int rr = rbase; rr < rt; rr += 32 * U) {
             int i4[U];
-            float4 xv[U], gv[U], yv[U];
+            float4 xv[U], gv[U];
             const int pr0 = (int)m0 - g.halo + rr;     // padded rows fit 31 bits (checked where the tensor path is enabled)
             // image index / position inside the padded image of the first row, advanced by 32 rows per item
             int bq = pr0 >= 0 ? (int)((unsigned)pr0 / (unsigned)per) : -1;
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 }
                 if (i4[u] >= 0) {
                     xv[u] = reinterpret_cast<const float4*>(px)[i4[u]];
-                    if (PRO == 2) { gv[u] = reinterpret_cast<const float4*>(pg)[i4[u]]; yv[u] = reinterpret_cast<const float4*>(py)[i4[u]]; }
+                    if (PRO == 2) gv[u] = reinterpret_cast<const float4*>(pg)[i4[u]];
                 }
                 rem += 32;
                 if (rem >= 0 && bq < 0) bq = 0;
@@ -251,12 +252,15 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                                 oo[k] = (relu && !(v > 0.f)) ? 0.f : v;
                             }
                         } else {
-                            const float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w}, yy[4] = {yv[u].x, yv[u].y, yv[u].z, yv[u].w};
+                            const float gg[4] = {gv[u].x, gv[u].y, gv[u].z, gv[u].w};
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const float gs = __fmul_rn(a.pgscale, gg[k]);
-                                const float dy = (relu && !(yy[k] > 0.f)) ? 0.f : gs;
                                 const float xh = __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k]);
+                                // the ReLU mask is recomputed from x with the forward pass's own expression (bit-identical to y > 0),
+                                // which saves loading the layer output
+                                const float yk = __fadd_rn(__fmul_rn(gam[k], xh), bet[k]);
+                                const float dy = (relu && !(yk > 0.f)) ? 0.f : gs;
                                 oo[k] = __fmul_rn(__fmul_rn(gam[k], inv[k]), __fsub_rn(__fsub_rn(dy, mdy[k]), __fmul_rn(xh, mdyxh[k])));
                             }
                         }
@@ -354,30 +358,32 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         float xh[EPI == 2 ? 32 : 1];
         unsigned int mask = 0u;
         if constexpr (EPI == 2) {
-            __shared__ float s_mi[128];
+            __shared__ float s_mi[256];      // mean, invstd, gamma, beta of the BatchNorm in front
             if (a.bn.deferred) {
                 if (et < 64) bn_fwd_final(a.bn, et, s_mi[et], s_mi[64 + et]);
             } else {
                 if (et < 64) s_mi[et] = a.bn.mean[et]; else if (et < 128) s_mi[et] = a.bn.invstd[et - 64];
             }
+            if (et >= 128 && et < 192) s_mi[et] = a.egamma[et - 128]; else if (et >= 192) s_mi[et] = a.ebeta[et - 192];
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const bool relu = a.eact == N4J_ACT_RELU;
             mask = relu ? 0u : ~0u;
             if (valid) {
                 const float4* __restrict__ xr = reinterpret_cast<const float4*>(resolve(a.ex) + crow * 64 + half * 32);
-                const float4* __restrict__ yr = reinterpret_cast<const float4*>(resolve(a.ey) + crow * 64 + half * 32);
                 const float* smean = s_mi + half * 32;
                 const float* sinv = s_mi + 64 + half * 32;
+                const float* sgam = s_mi + 128 + half * 32;
+                const float* sbet = s_mi + 192 + half * 32;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float4 xv = xr[j];
-                    xh[4 * j + 0] = __fmul_rn(__fsub_rn(xv.x, smean[4 * j + 0]), sinv[4 * j + 0]);
-                    xh[4 * j + 1] = __fmul_rn(__fsub_rn(xv.y, smean[4 * j + 1]), sinv[4 * j + 1]);
-                    xh[4 * j + 2] = __fmul_rn(__fsub_rn(xv.z, smean[4 * j + 2]), sinv[4 * j + 2]);
-                    xh[4 * j + 3] = __fmul_rn(__fsub_rn(xv.w, smean[4 * j + 3]), sinv[4 * j + 3]);
-                    if (relu) {
-                        const float4 yv = yr[j];
-                        mask |= ((yv.x > 0.f ? 1u : 0u) | (yv.y > 0.f ? 2u : 0u) | (yv.z > 0.f ? 4u : 0u) | (yv.w > 0.f ? 8u : 0u)) << (4 * j);
+                    const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int c = 4 * j + k;
+                        xh[c] = __fmul_rn(__fsub_rn(xs[k], smean[c]), sinv[c]);
+                        // ReLU mask from the forward expression y = gamma * xhat + beta (bit-identical to the stored output's sign)
+                        if (relu && __fadd_rn(__fmul_rn(sgam[c], xh[c]), sbet[c]) > 0.f) mask |= 1u << c;
                     }
                 }
             } else {

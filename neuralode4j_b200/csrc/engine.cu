@@ -691,7 +691,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     // BatchNorm backward dx is produced by the operand prologue of the dgrad conv (and stored compactly for wgrad)
                     bpro_pending = true;
                     bpro_args = ConvTcArgs{};
-                    bpro_args.px = x; bpro_args.py = y; bpro_args.pg = g; bpro_args.pgscale = gscale; bpro_args.pgamma = params_.p + l.p_off;
+                    bpro_args.px = x; bpro_args.pg = g; bpro_args.pgscale = gscale; bpro_args.pgamma = params_.p + l.p_off; bpro_args.pbeta = params_.p + l.p_off + cc;
                     bpro_args.pbn = l.bn; bpro_args.pact = l.d.activation; bpro_args.pcompact = l.gin;
                     bpro_args.pdgamma = dth; bpro_args.pdbeta = with_off(dth, cc);
                     gimg_ready = true;
@@ -700,7 +700,8 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                            l.gin, L_[i - 1].gimg, dth, with_off(dth, cc));
                     gimg_ready = true;
                 } else {
-                    LAUNCH(k_bn_bwd_dx, grid_for(l.in_len), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, l.rows, cc, dx, dth, with_off(dth, cc));
+                    LAUNCH(k_bn_bwd_dx, grid_for(l.in_len), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, l.rows, cc, dx, dth, with_off(dth, cc),
+                           params_.p + l.p_off + cc);
                 }
                 break;
             }
@@ -765,8 +766,8 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                         const LayerPlan& b = L_[i - 1];
                         if (b.d.kind == N4J_LAYER_BATCHNORM && b.c_out == 64 && (b.d.activation == N4J_ACT_RELU || b.d.activation == N4J_ACT_IDENTITY)) {
                             if (!bpro_pending) bpro_args = ConvTcArgs{};
-                            bpro_args.ey = fixed_ref(b.act);                        // i - 1 < last: its output is a saved activation
                             bpro_args.ex = i - 1 == 0 ? in : fixed_ref(L_[i - 2].act);
+                            bpro_args.egamma = params_.p + b.p_off; bpro_args.ebeta = params_.p + b.p_off + 64;
                             bpro_args.eact = b.d.activation;
                             bpro_args.edgamma = with_off(out, off_theta_ + b.g_off);
                             bpro_args.edbeta = with_off(out, off_theta_ + b.g_off + 64);
