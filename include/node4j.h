@@ -92,6 +92,7 @@ enum {
     N4J_FLAG_NO_TENSOR = 1u << 4,         /* keep convolutions on the fp32 SIMT kernels (used to cross-check the tcgen05 path) */
     N4J_FLAG_FORCE_TENSOR = 1u << 6,      /* take the tcgen05 dense path even for layers below the size threshold (tests) */
     N4J_FLAG_NO_PROLOGUE_FUSION = 1u << 7, /* run BatchNorm apply / backward dx as separate kernels instead of inside the conv operand prologue */
+    N4J_FLAG_NO_MLP_FUSION = 1u << 10,     /* small dense inner graphs layer by layer instead of one fused launch per evaluation */
     N4J_FLAG_NO_DEFERRED_STATS = 1u << 9,  /* BatchNorm statistics finalised by the last block of the producing kernel (always so on multi-GPU) instead of by the consumers */
     N4J_FLAG_NO_BWD_STATS_FUSION = 1u << 8, /* reduce BatchNorm backward statistics in their own kernel instead of the dgrad conv epilogue */
     N4J_FLAG_NO_PDL = 1u << 5,            /* launch kernels without programmatic dependent launch (debug / A-B timing) */

@@ -15,7 +15,7 @@ N4J_OK, ERR_INVALID_ARGUMENT, ERR_ILLEGAL_STATE, ERR_UNSUPPORTED, ERR_CUDA, ERR_
 
 LAYER_DENSE, LAYER_CONV3X3, LAYER_BATCHNORM, LAYER_ACTIVATION, LAYER_TIME_CONCAT = 1, 2, 3, 4, 5
 ACT = {"identity": 0, "relu": 1, "elu": 2, "tanh": 3}
-FLAG_EXACT_STAGE_TIMES, FLAG_NO_GRAPH, FLAG_FAST_TF32, FLAG_EXACT_CONTRACTIONS, FLAG_NO_TENSOR, FLAG_NO_PDL, FLAG_FORCE_TENSOR, FLAG_NO_PROLOGUE_FUSION, FLAG_NO_BWD_STATS_FUSION, FLAG_NO_DEFERRED_STATS = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
+FLAG_EXACT_STAGE_TIMES, FLAG_NO_GRAPH, FLAG_FAST_TF32, FLAG_EXACT_CONTRACTIONS, FLAG_NO_TENSOR, FLAG_NO_PDL, FLAG_FORCE_TENSOR, FLAG_NO_PROLOGUE_FUSION, FLAG_NO_BWD_STATS_FUSION, FLAG_NO_DEFERRED_STATS, FLAG_NO_MLP_FUSION = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024
 TIMEGRAD_NONE, TIMEGRAD_ZERO, TIMEGRAD_CALC = 0, 1, 2
 
 EXPORTS = [

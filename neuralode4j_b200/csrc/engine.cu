@@ -296,6 +296,40 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
         for (auto& l : L_) if (l.d.kind == N4J_LAYER_BATCHNORM && l.bn_deferred_ok) { l.bn_pool = bn_pool_ + (size_t)(k++) * 4 * 128 * ACC_STRIDE; l.bn.deferred = 1; }
         set_bn_slot(0);
     }
+    // small dense inner graph (optionally behind the time merge): one fused launch per evaluation (mlp_small.cuh)
+    {
+        bool ok = !(cfg_.flags & N4J_FLAG_NO_MLP_FUSION) && rank_ == 2 && n_params_ == n_real_ && n_params_ <= 12288;
+        MlpSmallArgs m{};
+        int feat = C_;
+        for (size_t i = 0; ok && i < L_.size(); ++i) {
+            const LayerPlan& l = L_[i];
+            if (l.d.kind == N4J_LAYER_TIME_CONCAT) { m.tcat_k = l.c_out - l.c_in; feat = l.c_out; continue; }
+            if (l.d.kind != N4J_LAYER_DENSE || !l.exact || m.nl >= MLP_MAX_LAYERS) { ok = false; break; }
+            const int k = m.nl++;
+            m.nin[k] = l.c_in; m.nout[k] = l.c_out; m.act[k] = l.d.activation; m.has_bias[k] = l.d.has_bias; m.p_off[k] = (int)l.p_off;
+            m.a_off[k] = k == 0 ? 0 : m.a_off[k - 1] + m.nin[k - 1];
+            feat = l.c_out;
+        }
+        if (ok && m.nl > 0) {
+            m.a_off[m.nl] = m.a_off[m.nl - 1] + m.nin[m.nl - 1];
+            m.a_tot = m.a_off[m.nl] + C_;
+            m.D = C_; m.n_params = (int)n_params_; m.B = B_;
+            m.off_a = off_a_; m.off_theta = off_theta_; m.off_t = off_t_;
+            // rows per block: as few blocks as shared memory allows (their partial parameter gradients are summed by ONE block)
+            mlp_smem_ = mlp_small_smem_bytes(m);
+            if (mlp_smem_ <= 200 * 1024 && feat == C_) {
+                const int blocks = (int)((B_ + MLP_ROWS - 1) / MLP_ROWS);
+                N4J_CUDA(cudaMalloc(&mlp_part_, sizeof(double) * (size_t)blocks * (n_params_ + 1)));
+                N4J_CUDA(cudaMalloc(&mlp_ticket_, sizeof(unsigned int)));
+                N4J_CUDA(cudaMemsetAsync(mlp_ticket_, 0, sizeof(unsigned int), stream_));
+                N4J_CUDA(cudaFuncSetAttribute(k_mlp_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem_));
+                N4J_CUDA(cudaFuncSetAttribute(k_mlp_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem_));
+                m.part = mlp_part_; m.ticket = mlp_ticket_; m.dt_out = tcat_misc_ + 1; m.c = ctrl_;
+                mlp_args_ = m;
+                mlp_fused_ = true;
+            }
+        }
+    }
     N4J_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -315,7 +349,7 @@ Engine::~Engine() {
     for (DevBuf* b : {&params_, &gradflat_, &zt_, &gt_, &io_, &io2_, &gb_[0], &gb_[1], &gb_[2], &theta_tmp_, &wpart_, &dldt_}) cudaFree(b->p);
     for (void* pp : peer_ptrs_) cudaIpcCloseMemHandle(pp);
     cudaFree(comm_region_); cudaFree(comm_dev_);
-    cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(red_acc_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_); cudaFree(tcat_acc_); cudaFree(tcat_misc_); cudaFree(bn_pool_);
+    cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(red_acc_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_); cudaFree(tcat_acc_); cudaFree(tcat_misc_); cudaFree(bn_pool_); cudaFree(mlp_part_); cudaFree(mlp_ticket_);
     cudaFreeHost(ctrl_host_); cudaFreeHost(tpair_host_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -544,6 +578,7 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
     Ref cur = in;
     bool image_ready = false;   // the previous layer already wrote the operand image of this (tensor-core) conv
     bool pro_pending = false;   // ... or left its BatchNorm apply to the conv kernel's operand prologue
+    if (mlp_fused_ && !comm_dev_ && !in_aug_) { begin_eval(); enqueue_mlp_small(s, in, out, false); return; }
     if (!in_aug_) begin_eval();
     ConvTcArgs pro_args{};
     bool stats_ready = bn1_ready;   // the previous kernel (conv epilogue / stage combination) already produced this BatchNorm's mean / invstd
@@ -644,7 +679,17 @@ void Engine::join_side(cudaStream_t s) {
 
 // slot: which activation / gradient buffer set this evaluation uses; defer_join: leave the weight-gradient kernels running on
 // the side branch (the caller joins before it touches the theta block of the K rows).
+void Engine::enqueue_mlp_small(cudaStream_t s, Ref in, Ref out, bool aug) {
+    MlpSmallArgs m = mlp_args_;
+    m.params = params_.p; m.in = in; m.out = out; m.ts = tspec_; m.write_t = (aug && aug_tslot_) ? 1 : 0;
+    const dim3 grid((unsigned)((B_ + MLP_ROWS - 1) / MLP_ROWS)), block(MLP_THREADS);
+    if (aug) launch_k(k_mlp_small<true>, grid, block, mlp_smem_, s, pdl_, m);
+    else launch_k(k_mlp_small<false>, grid, block, mlp_smem_, s, pdl_, m);
+    ++launches_;
+}
+
 void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, int slot, bool defer_join, bool last_of_trial) {
+    if (mlp_fused_ && !comm_dev_) { begin_eval(); enqueue_mlp_small(s, in, out, true); return; }
     for (auto& l : L_) { l.act = l.act2[slot]; l.gin = l.gin2[slot]; }
     if (slot_event_valid_[slot]) {   // the evaluation that used this buffer set before must have finished its side work
         N4J_CUDA(cudaStreamWaitEvent(s, slot_event_[slot], 0));

@@ -12,6 +12,7 @@
 #include "conv_tc.cuh"
 #include "gemm_tc.cuh"
 #include "layer_kernels.cuh"
+#include "mlp_small.cuh"
 #include "solver_kernels.cuh"
 
 namespace n4j {
@@ -140,6 +141,13 @@ private:
     float* wanted_ = nullptr;     // requested times (device)
     int wanted_cap_ = 0;
     double* dot_acc_ = nullptr;
+    // small dense inner graphs: one launch per evaluation (mlp_small.cuh)
+    bool mlp_fused_ = false;
+    MlpSmallArgs mlp_args_{};
+    size_t mlp_smem_ = 0;
+    double* mlp_part_ = nullptr;
+    unsigned int* mlp_ticket_ = nullptr;
+    void enqueue_mlp_small(cudaStream_t s, Ref in, Ref out, bool aug);
     // deferred BatchNorm statistics (layer_kernels.cuh: BnScratch)
     double* bn_pool_ = nullptr;
     size_t bn_pool_len_ = 0;

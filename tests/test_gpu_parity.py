@@ -367,6 +367,23 @@ def test_cuda_matches_committed_fixtures(name):
         H.assert_close(r["dt"], fx[name + "/dt"], RTOL, 1e-5 * max(np.abs(fx[name + "/dt"]).max(), 1e-30), "dt")
 
 
+@pytest.mark.parametrize("w", [W.spiral_block(batch=300, nt=6), W.anode_time_block(batch=200, time_input=True, nt=3), W.golden_linear(1)],
+                         ids=["spiral", "anode_time", "golden"])
+def test_fused_small_mlp_equals_layerwise_kernels(w):
+    """mlp_small.cuh (one launch per evaluation, default for small dense blocks) against the per-layer exact kernels
+    (N4J_FLAG_NO_MLP_FUSION): same double-accumulated contractions, so states, gradients and step sequences agree; the fused
+    path needs several times fewer launches."""
+    eps = W.golden_lossgrad() if w.name == "golden_linear" else None
+    a = H.run_cuda(w, eps=eps)
+    b = H.run_cuda(w, eps=eps, flags=_lib.FLAG_NO_MLP_FUSION)
+    assert a["fwd_stats"] == b["fwd_stats"] and a["bwd_stats"] == b["bwd_stats"]
+    for k in ("out", "dy0", "grad"):
+        np.testing.assert_allclose(a[k], b[k], rtol=2e-6, atol=1e-7 * np.abs(b[k]).max(), err_msg=k)
+    if a["dt"] is not None:
+        np.testing.assert_allclose(a["dt"], b["dt"], rtol=2e-6, atol=1e-7 * max(np.abs(b["dt"]).max(), 1e-30))
+    assert a["bwd_launches"] * 2 < b["bwd_launches"]
+
+
 def test_single_stepping_equals_interpolating():
     # InterpolatingMultiStepSolverTest.java:26-37: both multi-step solvers agree to 1e-4
     w = W.golden_linear(1)
