@@ -11,7 +11,7 @@
 // written by the producing BatchNorm-apply (or BatchNorm-backward) kernel, border pixels stay zero.  One CTA computes
 // 128 consecutive padded pixels x 64 output channels: the tile plus a halo of W+3 rows is staged ONCE by 32 bulk copies and
 // the nine taps are nine row-shifted shared-memory descriptors into it.  Weights stream per tap (hi+lo = 32 KB) through a
-// 4-deep mbarrier ring.  Warp roles: warp 0 = bulk-copy producer (+TMEM alloc), warp 1 = MMA issuer, warps 2-5 = epilogue
+// 4-deep mbarrier ring.  Warp roles: warp 0 = bulk-copy producer (+TMEM alloc), warp 1 = MMA issuer, warps 2-9 = epilogue
 // (TMEM -> registers -> compact NHWC rows, optional fused BatchNorm statistics for the next layer).
 #pragma once
 
@@ -93,7 +93,7 @@ struct ConvTcArgs {
     BnScratch bn;
     float bn_eps;
     long long bn_rows;    // B*H*W
-    // fused operand prologue (PRO != 0): all eight warps of a 256-thread CTA build the A tile in shared memory from compact NHWC tensors
+    // fused operand prologue (PRO != 0): all sixteen warps of a 512-thread CTA build the A tile in shared memory from compact NHWC tensors
     //   PRO = 1  forward : A = act(gamma * ((x - mean) * invstd) + beta)                      (BatchNorm apply of the layer in front)
     //   PRO = 2  backward: A = gamma*invstd * ((dy - mean(dy)) - xhat * mean(dy*xhat)),  dy = act'(y) * gscale * g
     //                      (BatchNorm backward of the layer BEHIND the conv whose dgrad this launch computes)
