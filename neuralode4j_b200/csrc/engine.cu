@@ -595,6 +595,7 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                     LAUNCH(k_rowmajor_to_image, grid_for(l.in_len / 4), 256, s, cur, 1.f, l.ximg, l.rows, l.c_in, l.img_rows);
                     GemmTcArgs ga{};
                     ga.M = (int)l.rows; ga.N = l.c_out; ga.kblocks = l.c_in / 32; ga.a_nch = l.c_in / 4; ga.out = dst; ga.bias = bias; ga.act = l.d.activation;
+                    ga.a_img = l.ximg; ga.a_rows = l.img_rows; ga.b_img = l.wsf; ga.b_nch = l.c_in / 4;
                     launch_gemm_tc(s, l.tm_x_k, l.tm_wf, ga);
                 } else {
                     GemmArgs g{}; g.a = cur; g.c = dst; g.w = Wt; g.bias = bias; g.M = (int)l.rows; g.N = l.c_out; g.K = l.c_in;
@@ -782,11 +783,13 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                         LAUNCH(k_rowmajor_to_image_T, grid_for((l.img_rows / 4) * l.c_in), 256, s, x, l.xTimg, l.rows, l.c_in, l.img_rows, 0LL, 1);
                         GemmTcArgs wa{};
                         wa.M = l.c_out; wa.N = l.c_in; wa.kblocks = (int)(l.img_rows / 32); wa.a_nch = (int)(l.img_rows / 4); wa.out = dth;
+                        wa.a_img = l.dTimg; wa.a_rows = (long long)((l.c_out + 127) / 128 * 128); wa.b_img = l.xTimg; wa.b_nch = (int)(l.img_rows / 4);
                         launch_gemm_tc(s, l.tm_dT, l.tm_xT, wa);
                         if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 256, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
                         if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, s, comm_dev_, dth, l.g_len);
                         GemmTcArgs qa{};     // dx[b,i] = sum_o delta[b,o] W(i,o)
                         qa.M = (int)l.rows; qa.N = l.c_in; qa.kblocks = l.c_out / 32; qa.a_nch = l.c_out / 4; qa.out = dx;
+                        qa.a_img = l.dimg; qa.a_rows = l.img_rows; qa.b_img = l.wsb; qa.b_nch = l.c_out / 4;
                         launch_gemm_tc(s, l.tm_d_k, l.tm_wb, qa);
                     } else {
                         GemmArgs w{}; w.a = d; w.b = x; w.c = dth; w.M = l.c_out; w.N = l.c_in; w.K = (int)l.rows; w.splits = 1;

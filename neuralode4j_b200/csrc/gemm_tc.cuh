@@ -52,6 +52,13 @@ struct GemmTcArgs {
     int act;              // activation applied to the result (forward)
     Ref dact_y;           // optional: multiply the result by act'(y) with y row-major [M][N] (dgrad through the previous layer's
     int dact;             //           activation); dact = activation kind, dact_y.base == null -> off
+    // operand images in global memory, moved with 1-D bulk copies (2 KB per chunk of the A tile, ONE 32 KB copy for the stacked B
+    // tile).  The 3-d/4-d tensor-map path needed one TMA element per 16-byte row (4096 per stage) and bounded the kernel at ~4000
+    // cycles per K block against 816 cycles of MMA: 620 -> see DESIGN.md.
+    const float* a_img;   // [2*a_nch][a_rows][4]
+    long long a_rows;
+    const float* b_img;   // [nblocks][b_nch][256][4]
+    int b_nch;
     float* out_img;       // optional: also write the result as a split image [2*ceil(N/4)][img_rows][4] for the next GEMM
     long long out_img_rows;
 };
@@ -92,9 +99,14 @@ __global__ void __launch_bounds__(GEMM_TC_THREADS, 1) k_gemm_tc(const __grid_con
                 uint8_t* sB = sA + 32768;
                 tc::mbar_arrive_expect_tx(&full[s], GEMM_TC_STAGE_BYTES);
                 // A: [8 chunks][128 rows] hi then lo;  B: [8 chunks][256 stacked rows] in one 4-d box
-                tc::tma_load_3d(sA, &tmA, 0, m0, kb * 8, &full[s]);
-                tc::tma_load_3d(sA + 16384, &tmA, 0, m0, a.a_nch + kb * 8, &full[s]);
-                tc::tma_load_4d(sB, &tmB, 0, 0, kb * 8, tn, &full[s]);
+                const float* ah = a.a_img + ((long long)(kb * 8) * a.a_rows + m0) * 4;
+                const float* al = a.a_img + ((long long)(a.a_nch + kb * 8) * a.a_rows + m0) * 4;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    tc::bulk_g2s(sA + c * 2048, ah + (long long)c * a.a_rows * 4, 2048, &full[s]);
+                    tc::bulk_g2s(sA + 16384 + c * 2048, al + (long long)c * a.a_rows * 4, 2048, &full[s]);
+                }
+                tc::bulk_g2s(sB, a.b_img + ((long long)tn * a.b_nch + kb * 8) * 1024, 32768, &full[s]);
             }
         }
     } else if (warp == 1) {
