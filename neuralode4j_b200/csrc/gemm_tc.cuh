@@ -5,7 +5,9 @@
 //
 // Operands are pre-split (hi = tf32(x), lo = x - hi) chunk-major images in global memory (tc_common.cuh):
 //     img[hl*nch + chunk][row][4 floats]         chunk = 4 consecutive features, row = sample (or weight row)
-// moved by TMA (cp.async.bulk.tensor.3d/4d, SWIZZLE_NONE) straight into the canonical no-swizzle UMMA layout.
+// moved by 1-D bulk copies (cp.async.bulk: 2 KB per chunk of an A tile, one 32 KB copy per stacked B tile) straight into the
+// canonical no-swizzle UMMA layout.  (The tensor-map variant, cp.async.bulk.tensor.3d/4d with 16-byte innermost rows, was
+// TMA-element-bound: 620 us instead of 219 us for 1024 x 4096 x 4096.)
 // One K-major kernel serves all three contractions of a dense layer:
 //   C[m, n] = sum_k A[m, k] * W[n, k]
 //   forward: A = x image,        W = stacked weight image [nOut][nIn]
@@ -13,7 +15,7 @@
 //   wgrad  : A = delta^T image (rows = out features, K = batch), W = stacked x^T image  ->  dW^T[o, i] = sum_b delta[b, o] x[b, i]
 // (an MN-major variant that reads the untransposed images was tried first: with SWIZZLE_NONE descriptors it returned zeros on
 //  B200, so the transposed images are produced explicitly by k_rowmajor_to_image_T — one extra pass over x and delta.)
-// Tile 128 x 128, K block of 32, 3-stage TMA/mbarrier ring, 3xTF32 as  A_hi*[B_hi | B_lo]  (N = 256) + A_lo*B_hi (N = 128)
+// Tile 128 x 128, K block of 32, 3-stage bulk-copy/mbarrier ring, 3xTF32 as  A_hi*[B_hi | B_lo]  (N = 256) + A_lo*B_hi (N = 128)
 // into 256 TMEM columns; the epilogue adds the two halves, applies bias / activation / activation derivative and writes
 // row-major fp32 (and, optionally, the split image the next GEMM reads).
 #pragma once
