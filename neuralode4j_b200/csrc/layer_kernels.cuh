@@ -588,8 +588,18 @@ __global__ void __launch_bounds__(256) k_colsum(Ref din, Ref out, long long B, i
     __shared__ double sm[8][33];
     const int c = blockIdx.x * 32 + (threadIdx.x & 31), rg = threadIdx.x >> 5;
     double acc = 0;
-    if (c < n)
-        for (long long b = rg; b < B; b += 8) acc += (double)d[b * n + c];
+    if (c < n) {
+        // rows b = rg, rg + 8, ... summed in order; eight independent loads in flight per trip (the loop is latency-bound)
+        long long b = rg;
+        for (; b + 56 < B; b += 64) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] = d[(b + 8 * q) * n + c];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc += (double)v[q];
+        }
+        for (; b < B; b += 8) acc += (double)d[b * n + c];
+    }
     sm[rg][threadIdx.x & 31] = acc;
     __syncthreads();
     if (rg == 0 && c < n) {
@@ -683,15 +693,26 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = (AccT)0;
 
-    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    // register prefetch: the loads of K tile i+1 are in flight while tile i is multiplied (the summation order is unchanged)
+    float ra[4], rb[4];
+    auto fetch = [&](int k0) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = k0 + la_k + 4 * j, m = m0 + la_m;
-            As[la_k + 4 * j][la_m] = (m < g.M && k < kend) ? Addr<MODE>::A(g, pa, m, k, hh, ww) : 0.f;
+            ra[j] = (m < g.M && k < kend) ? Addr<MODE>::A(g, pa, m, k, hh, ww) : 0.f;
             const int kb = k0 + lb_k + 4 * j, n = n0 + lb_n;
-            Bs[lb_k + 4 * j][lb_n] = (n < g.N && kb < kend) ? Addr<MODE>::B(g, pb, kb, n) : 0.f;
+            rb[j] = (n < g.N && kb < kend) ? Addr<MODE>::B(g, pb, kb, n) : 0.f;
+        }
+    };
+    fetch(kbeg);
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            As[la_k + 4 * j][la_m] = ra[j];
+            Bs[lb_k + 4 * j][lb_n] = rb[j];
         }
         __syncthreads();
+        if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
             const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
