@@ -270,7 +270,8 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
             l.tm_xT = make_weight_map(l.xTimg, l.img_rows / 4, nbb);
             l.tm_wf = make_weight_map(l.wsf, l.c_in / 4, nbf);
             l.tm_wb = make_weight_map(l.wsb, l.c_out / 4, nbb);
-            N4J_CUDA(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TC_SMEM));
+            N4J_CUDA(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TC_SMEM));
+            N4J_CUDA(cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_TC2_SMEM));
         }
         if (l.d.kind == N4J_LAYER_DENSE && !l.exact && !l.tcd && (long long)l.c_in * l.c_out <= (1LL << 22)) ensure(wpart_, 8LL * l.c_in * l.c_out);
         if (l.d.kind == N4J_LAYER_BATCHNORM) {
@@ -523,9 +524,16 @@ static void launch_gemm(cudaStream_t s, GemmArgs g, int& launches, bool exact) {
     ++launches;
 }
 
-void Engine::launch_gemm_tc(cudaStream_t s, const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcArgs& a) {
-    const dim3 grid(((a.M + 127) / 128) * ((a.N + 127) / 128)), block(GEMM_TC_THREADS);
-    launch_k(k_gemm_tc, grid, block, GEMM_TC_SMEM, s, pdl_, ta, tb, a);
+void Engine::launch_gemm_tc(cudaStream_t s, const CUtensorMap&, const CUtensorMap&, const GemmTcArgs& a) {
+    const int tiles_n = (a.N + 127) / 128, tiles_m = (a.M + 127) / 128;
+    // enough 128 x 128 tiles to fill the chip: pair the M tiles (256 x 128 per CTA, every B tile feeds two accumulators)
+    if ((long long)tiles_m * tiles_n >= 148 && tiles_m >= 2) {
+        const dim3 grid(((tiles_m + 1) / 2) * tiles_n), block(GEMM_TC_THREADS);
+        launch_k(k_gemm_tc<2>, grid, block, GEMM_TC2_SMEM, s, pdl_, a);
+    } else {
+        const dim3 grid(tiles_m * tiles_n), block(GEMM_TC_THREADS);
+        launch_k(k_gemm_tc<1>, grid, block, GEMM_TC_SMEM, s, pdl_, a);
+    }
     ++launches_;
 }
 

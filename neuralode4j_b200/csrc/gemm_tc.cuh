@@ -4,8 +4,8 @@
 // BackpropagateAdjoint.java:109 (cuBLAS sgemm / OpenBLAS in the reference).
 //
 // Operands are pre-split (hi = tf32(x), lo = x - hi) chunk-major images in global memory (tc_common.cuh):
-//     img[hl*nch + chunk][row][4 floats]         chunk = 4 consecutive features, row = sample (or weight row)
-// moved by 1-D bulk copies (cp.async.bulk: 2 KB per chunk of an A tile, one 32 KB copy per stacked B tile) straight into the
+//     img[row / 128][hl*nch + chunk][row % 128][4 floats]     chunk = 4 consecutive features, row = sample (or weight row)
+// moved by 1-D bulk copies (cp.async.bulk: one copy per hi / lo A tile, one per stacked B tile) straight into the
 // canonical no-swizzle UMMA layout.  (The tensor-map variant, cp.async.bulk.tensor.3d/4d with 16-byte innermost rows, was
 // TMA-element-bound: 620 us instead of 219 us for 1024 x 4096 x 4096.)
 // One K-major kernel serves all three contractions of a dense layer:
@@ -29,8 +29,14 @@ namespace n4j {
 
 constexpr int GEMM_TC_THREADS = 192;
 constexpr int GEMM_TC_STAGES = 3;
-constexpr int GEMM_TC_STAGE_BYTES = 65536;                 // A (hi+lo) 32 KB + B (hi+lo) 32 KB
+constexpr int GEMM_TC_STAGE_BYTES = 65536;                 // MH = 1: K block 32, A (hi+lo) 32 KB + B (hi+lo) 32 KB
 constexpr size_t GEMM_TC_SMEM = (size_t)GEMM_TC_STAGES * GEMM_TC_STAGE_BYTES + 256;
+// MH = 2 (256 x 128 tile: two M halves share every B tile): K block 16, A 2 x (hi+lo) x 8 KB + B 16 KB = 48 KB, four stages.
+// The kernel is bounded by the L2 -> SM ingest (measured ~42 B/clk per SM with all SMs pulling): 64 KB per 816 MMA cycles with
+// MH = 1, 48 KB per 816 cycles with MH = 2.
+constexpr int GEMM_TC2_STAGES = 4;
+constexpr int GEMM_TC2_STAGE_BYTES = 49152;
+constexpr size_t GEMM_TC2_SMEM = (size_t)GEMM_TC2_STAGES * GEMM_TC2_STAGE_BYTES + 256;
 
 namespace tc {
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
@@ -57,7 +63,7 @@ struct GemmTcArgs {
     // operand images in global memory, moved with 1-D bulk copies (2 KB per chunk of the A tile, ONE 32 KB copy for the stacked B
     // tile).  The 3-d/4-d tensor-map path needed one TMA element per 16-byte row (4096 per stage) and bounded the kernel at ~4000
     // cycles per K block against 816 cycles of MMA: 620 -> see DESIGN.md.
-    const float* a_img;   // [2*a_nch][a_rows][4]
+    const float* a_img;   // [a_rows / 128][2*a_nch][128][4]  (row-tile-major: the chunks of one 128-row tile are contiguous)
     long long a_rows;
     const float* b_img;   // [nblocks][b_nch][256][4]
     int b_nch;
@@ -66,26 +72,33 @@ struct GemmTcArgs {
 };
 
 // tmA = activation image (3-d), tmB = stacked image (4-d: {4, 256, nchunks, nblocks}).
-__global__ void __launch_bounds__(GEMM_TC_THREADS, 1) k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                                                                  GemmTcArgs a) {
+template <int MH>
+__global__ void __launch_bounds__(GEMM_TC_THREADS, 1) k_gemm_tc(GemmTcArgs a) {
+    constexpr int STAGES = MH == 1 ? GEMM_TC_STAGES : GEMM_TC2_STAGES;
+    constexpr int STAGE_BYTES = MH == 1 ? GEMM_TC_STAGE_BYTES : GEMM_TC2_STAGE_BYTES;
+    constexpr int KCH = MH == 1 ? 8 : 4;                  // 16-byte chunks (4 floats of K) per stage
+    constexpr int A_HALF_BYTES = KCH * 2048;              // one hi or lo tile of one M half
+    constexpr int B_OFF = MH * 2 * A_HALF_BYTES;          // stacked B tile behind the A tiles
+    constexpr int TCOLS = MH * 256;
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + GEMM_TC_STAGES * GEMM_TC_STAGE_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + STAGES * STAGE_BYTES);
     uint64_t* full = bars;
-    uint64_t* empty = bars + GEMM_TC_STAGES;
-    uint64_t* d_full = bars + 2 * GEMM_TC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM_TC_STAGES + 1);
+    uint64_t* empty = bars + STAGES;
+    uint64_t* d_full = bars + 2 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_n = (a.N + 127) / 128;
     const int tm = blockIdx.x / tiles_n, tn = blockIdx.x % tiles_n;
-    const int m0 = tm * 128, n0 = tn * 128;
+    const int m0 = tm * 128 * MH, n0 = tn * 128;
+    const bool second = MH == 2 && (long long)m0 + 128 < a.a_rows;      // the A image is padded to 128 rows, not 256
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GEMM_TC_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
         tc::mbar_init(d_full, 1);
         tc::fence_barrier_init();
     }
-    if (warp == 0) tc::tmem_alloc<256>(tmem_slot);
+    if (warp == 0) tc::tmem_alloc<TCOLS>(tmem_slot);
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
@@ -94,21 +107,22 @@ __global__ void __launch_bounds__(GEMM_TC_THREADS, 1) k_gemm_tc(const __grid_con
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < a.kblocks; ++kb) {
-                const int s = kb % GEMM_TC_STAGES;
-                if (kb >= GEMM_TC_STAGES) tc::mbar_wait(&empty[s], ((kb / GEMM_TC_STAGES) - 1) & 1);
-                uint8_t* sA = smem_raw + s * GEMM_TC_STAGE_BYTES;
-                uint8_t* sB = sA + 32768;
-                tc::mbar_arrive_expect_tx(&full[s], GEMM_TC_STAGE_BYTES);
-                // A: [8 chunks][128 rows] hi then lo;  B: [8 chunks][256 stacked rows] in one 4-d box
-                const float* ah = a.a_img + ((long long)(kb * 8) * a.a_rows + m0) * 4;
-                const float* al = a.a_img + ((long long)(a.a_nch + kb * 8) * a.a_rows + m0) * 4;
+            const int kblocks = a.kblocks * (8 / KCH);          // a.kblocks counts K blocks of 32
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES;
+                if (kb >= STAGES) tc::mbar_wait(&empty[s], ((kb / STAGES) - 1) & 1);
+                uint8_t* sA = smem_raw + s * STAGE_BYTES;
+                uint8_t* sB = sA + B_OFF;
+                tc::mbar_arrive_expect_tx(&full[s], (second || MH == 1) ? STAGE_BYTES : STAGE_BYTES - 2 * A_HALF_BYTES);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    tc::bulk_g2s(sA + c * 2048, ah + (long long)c * a.a_rows * 4, 2048, &full[s]);
-                    tc::bulk_g2s(sA + 16384 + c * 2048, al + (long long)c * a.a_rows * 4, 2048, &full[s]);
+                for (int h = 0; h < MH; ++h) {
+                    if (h == 1 && !second) break;
+                    // tile-major image: the KCH chunks of one row tile are contiguous -> one copy per hi / lo tile
+                    const float* ah = a.a_img + (((long long)(m0 / 128 + h) * (2 * a.a_nch) + kb * KCH) * 128) * 4;
+                    tc::bulk_g2s(sA + (2 * h) * A_HALF_BYTES, ah, A_HALF_BYTES, &full[s]);
+                    tc::bulk_g2s(sA + (2 * h + 1) * A_HALF_BYTES, ah + (long long)a.a_nch * 512, A_HALF_BYTES, &full[s]);
                 }
-                tc::bulk_g2s(sB, a.b_img + ((long long)tn * a.b_nch + kb * 8) * 1024, 32768, &full[s]);
+                tc::bulk_g2s(sB, a.b_img + ((long long)tn * a.b_nch + kb * KCH) * 1024, KCH * 4096, &full[s]);
             }
         }
     } else if (warp == 1) {
@@ -116,19 +130,25 @@ __global__ void __launch_bounds__(GEMM_TC_THREADS, 1) k_gemm_tc(const __grid_con
             constexpr uint32_t id256 = tc::idesc_tf32(128, 256, 0, 0);
             constexpr uint32_t id128 = tc::idesc_tf32(128, 128, 0, 0);
             uint32_t acc = 0;
-            for (int kb = 0; kb < a.kblocks; ++kb) {
-                const int s = kb % GEMM_TC_STAGES;
-                tc::mbar_wait(&full[s], (kb / GEMM_TC_STAGES) & 1);
+            const int kblocks = a.kblocks * (8 / KCH);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                const int s = kb % STAGES;
+                tc::mbar_wait(&full[s], (kb / STAGES) & 1);
                 tc::tc_fence_after();
-                const uint32_t sA = tc::smem_u32(smem_raw + s * GEMM_TC_STAGE_BYTES), sB = sA + 32768;
+                const uint32_t sA = tc::smem_u32(smem_raw + s * STAGE_BYTES), sB = sA + B_OFF;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < KCH / 2; ++j) {
                     // K-major: chunk stride = LBO, 8-row groups packed (SBO = 128)
-                    const uint64_t dAh = tc::smem_desc(sA + (2 * j) * 2048, 2048, 128);
-                    const uint64_t dAl = tc::smem_desc(sA + 16384 + (2 * j) * 2048, 2048, 128);
                     const uint64_t dB = tc::smem_desc(sB + (2 * j) * 4096, 4096, 128);
-                    tc::mma_tf32(tmem, dAh, dB, id256, acc); acc = 1;
-                    tc::mma_tf32(tmem, dAl, dB, id128, 1);
+#pragma unroll
+                    for (int h = 0; h < MH; ++h) {
+                        if (h == 1 && !second) break;
+                        const uint64_t dAh = tc::smem_desc(sA + (2 * h) * A_HALF_BYTES + (2 * j) * 2048, 2048, 128);
+                        const uint64_t dAl = tc::smem_desc(sA + (2 * h + 1) * A_HALF_BYTES + (2 * j) * 2048, 2048, 128);
+                        tc::mma_tf32(tmem + h * 256, dAh, dB, id256, acc);
+                        tc::mma_tf32(tmem + h * 256, dAl, dB, id128, 1);
+                    }
+                    acc = 1;
                 }
                 tc::mma_commit(&empty[s]);
             }
@@ -137,16 +157,18 @@ __global__ void __launch_bounds__(GEMM_TC_THREADS, 1) k_gemm_tc(const __grid_con
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int m = m0 + row;
         float* __restrict__ out = resolve(a.out);
         const float* __restrict__ yprev = a.dact_y.base ? resolve(a.dact_y) : nullptr;
         tc::mbar_wait(d_full, 0);
         tc::tc_fence_after();
 #pragma unroll 1
-        for (int c32 = 0; c32 < 4; ++c32) {
+        for (int hc = 0; hc < MH * 4; ++hc) {
+            const int h = hc >> 2, c32 = hc & 3;
+            if (h == 1 && !second) break;
+            const int m = m0 + h * 128 + row;
             float v[32], u[32];
-            tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c32 * 32, v);
-            tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 128 + c32 * 32, u);
+            tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * 256 + c32 * 32, v);
+            tc::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + h * 256 + 128 + c32 * 32, u);
             const int nb = n0 + c32 * 32;
             if (m < a.M) {
 #pragma unroll
@@ -171,8 +193,9 @@ __global__ void __launch_bounds__(GEMM_TC_THREADS, 1) k_gemm_tc(const __grid_con
                         tc::split_tf32(r[0], hi.x, lo.x); tc::split_tf32(r[1], hi.y, lo.y);
                         tc::split_tf32(r[2], hi.z, lo.z); tc::split_tf32(r[3], hi.w, lo.w);
                         const long long nch = (a.N + 3) / 4, ch = n >> 2;
-                        *reinterpret_cast<float4*>(a.out_img + (ch * a.out_img_rows + m) * 4) = hi;
-                        *reinterpret_cast<float4*>(a.out_img + ((nch + ch) * a.out_img_rows + m) * 4) = lo;
+                        const long long base = ((((long long)m >> 7) * (2 * nch) + ch) * 128 + (m & 127)) * 4;
+                        *reinterpret_cast<float4*>(a.out_img + base) = hi;
+                        *reinterpret_cast<float4*>(a.out_img + base + nch * 512) = lo;
                     }
                 }
             }
@@ -180,7 +203,7 @@ __global__ void __launch_bounds__(GEMM_TC_THREADS, 1) k_gemm_tc(const __grid_con
     }
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc<256>(tmem);
+    if (warp == 0) tc::tmem_dealloc<TCOLS>(tmem);
 }
 
 // ---- operand image producers ---------------------------------------------------------------------------------------------------
@@ -198,8 +221,9 @@ __global__ void __launch_bounds__(256) k_rowmajor_to_image(Ref xin, float scale,
         v.x = __fmul_rn(v.x, scale); v.y = __fmul_rn(v.y, scale); v.z = __fmul_rn(v.z, scale); v.w = __fmul_rn(v.w, scale);
         float4 hi, lo;
         tc::split_tf32(v.x, hi.x, lo.x); tc::split_tf32(v.y, hi.y, lo.y); tc::split_tf32(v.z, hi.z, lo.z); tc::split_tf32(v.w, hi.w, lo.w);
-        *reinterpret_cast<float4*>(img + ((long long)ch * img_rows + r) * 4) = hi;
-        *reinterpret_cast<float4*>(img + ((long long)(nch + ch) * img_rows + r) * 4) = lo;
+        const long long base = (((r >> 7) * (2 * nch) + ch) * 128 + (r & 127)) * 4;      // [row tile][hl*nch + chunk][row % 128][4]
+        *reinterpret_cast<float4*>(img + base) = hi;
+        *reinterpret_cast<float4*>(img + base + (long long)nch * 512) = lo;
     }
 }
 // row-major [rows][cols] -> split image of the TRANSPOSE: chunk = 4 consecutive rows (samples), image row = column (feature).
@@ -222,8 +246,9 @@ __global__ void __launch_bounds__(256) k_rowmajor_to_image_T(Ref xin, float* __r
         float4 hi, lo;
         tc::split_tf32(v[0], hi.x, lo.x); tc::split_tf32(v[1], hi.y, lo.y); tc::split_tf32(v[2], hi.z, lo.z); tc::split_tf32(v[3], hi.w, lo.w);
         if (!stacked) {
-            *reinterpret_cast<float4*>(img + (ch * img_cols + f) * 4) = hi;
-            *reinterpret_cast<float4*>(img + ((nchT + ch) * img_cols + f) * 4) = lo;
+            const long long base = (((long long)(f >> 7) * (2 * nchT) + ch) * 128 + (f & 127)) * 4;   // tile-major like k_rowmajor_to_image
+            *reinterpret_cast<float4*>(img + base) = hi;
+            *reinterpret_cast<float4*>(img + base + nchT * 512) = lo;
         } else {
             const long long base = (((long long)(f >> 7) * nchT + ch) * 256 + (f & 127)) * 4;
             *reinterpret_cast<float4*>(img + base) = hi;
