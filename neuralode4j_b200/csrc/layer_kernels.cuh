@@ -515,9 +515,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_dx(Ref gin, float gscale, Ref yr
         const int c = (int)(i % C);
         const float inv = sc.deferred ? s_st[1][c] : sc.invstd[c];
         const float xh = __fmul_rn(__fsub_rn(x[i], sc.deferred ? s_st[0][c] : sc.mean[c]), inv);
-        // ReLU: the sign of the layer output is recomputed from x with the forward expression (bit-identical), no load of y
-        const float yv = act == N4J_ACT_RELU ? __fadd_rn(__fmul_rn(gamma[c], xh), beta[c]) : y[i];
-        const float dy = act_bwd(act, yv, __fmul_rn(gscale, g[i]));
+        const float dy = act_bwd(act, y[i], __fmul_rn(gscale, g[i]));      // (recomputing the ReLU mask from x measured slower here: 7.6 vs 6.4 us)
         const float k = __fmul_rn(gamma[c], inv);
         const float t1 = __fsub_rn(dy, sc.deferred ? s_st[2][c] : sc.m_dy[c]);
         const float t2 = __fmul_rn(xh, sc.deferred ? s_st[3][c] : sc.m_dyxh[c]);
