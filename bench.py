@@ -124,6 +124,10 @@ def cpu_step(batch):
     from neuralode4j_b200 import workloads as W
     w = W.mnist_block(batch=batch)
     c = w.conf.odeForwardConf.solver.config
+    try:                                   # all the host threads this process may use, whatever OMP_NUM_THREADS the launcher exported
+        O.set_num_threads(len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        O.set_num_threads(os.cpu_count() or 1)
     orc = O.Oracle(w.conf.graph_spec(), w.shape, O.solver_cfg(c.absTol, c.relTol, c.minStep, c.maxStep))
     eps = w.epsilon(w.shape)
     t0 = time.perf_counter()

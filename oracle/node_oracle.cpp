@@ -1011,6 +1011,14 @@ void orc_tableau(double* a36, double* b7, double* e7, double* c6, double* cmid7)
     for (int j = 0; j < 6; ++j) c6[j] = TAB_C[j];
 }
 void orc_set_probe_noise(double rel) { g_probe_noise = rel; }
+// launchers such as torchrun export OMP_NUM_THREADS=1 for their children: the CPU baseline asks for the host's cores explicitly
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int orc_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

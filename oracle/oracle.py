@@ -263,3 +263,8 @@ def tableau():
 
 def num_threads() -> int:
     return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    """Overrides OMP_NUM_THREADS (torchrun exports 1 for its children) for the calls that follow."""
+    lib().orc_set_num_threads(int(n))
