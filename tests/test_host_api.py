@@ -147,3 +147,23 @@ def test_workload_shapes():
     assert 2 * 401408 + w.params.size == 877312                                          # N_aug of SURVEY.md section 8a
     s = W.spiral_block()
     assert s.time.size == 100 and abs(s.time[1] - 6 * np.pi / 499) < 1e-6
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU leg of the driver's contract) prints ONE JSON line with the agreed keys; it must not
+    need a GPU.  One bounded step of the oracle port on a 32-row slice (a few seconds)."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, OMP_NUM_THREADS="1")        # what torchrun exports: the arm must still use the host's cores
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "samples/s" and line["higher_is_better"] is True
+    for k in ("metric", "value", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["vs_baseline"] is None and line["cpu_baseline"]["kind"] == "port"
+    assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"]
