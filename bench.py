@@ -242,6 +242,37 @@ def run_ours(args):
     bwd_stats = (v.bwd_stats.nfe, v.bwd_stats.accepted, v.bwd_stats.rejected)
     n_launch = launches[0]
 
+    # ---- second protocol of the timing rules: no flush, but INPUTS larger than L2 — a different (y0, dL/dz) pair every step, the
+    # set of pairs being larger than the 126 MB L2.  Models a training loop: fresh minibatch from HBM every step, the engine's own
+    # weights / state / code warm.  Reported next to the (conservative) flushed number, never instead of it.
+    pair_bytes = 2 * d_y0.numel() * 4
+    n_pairs = int(140e6 // pair_bytes) + 1
+    rot_y0 = [d_y0.clone() for _ in range(n_pairs)]
+    rot_eps = [d_eps.clone() for _ in range(n_pairs)]
+    rot_i = [0]
+
+    def step_rotating():
+        i = rot_i[0] % n_pairs
+        rot_i[0] += 1
+        d_grad.zero_()
+        v.setInputs(rot_y0[i])
+        v.doForward(True)
+        v.setEpsilon(rot_eps[i])
+        v.doBackward()
+
+    for _ in range(3):
+        step_rotating()
+    barrier()
+    er0 = torch.cuda.Event(enable_timing=True); er1 = torch.cuda.Event(enable_timing=True)
+    er0.record(stream)
+    for _ in range(args.steps):
+        step_rotating()
+    er1.record(stream)
+    er1.synchronize()
+    rot_ms = er0.elapsed_time(er1)
+    del rot_y0, rot_eps
+    barrier()
+
     # ---- end-to-end arm: pinned host buffers through the same API --------------------------------------------------------
     h_params = torch.from_numpy(w.params).pin_memory()
     h_y0 = torch.from_numpy(w.y0).pin_memory()
@@ -287,10 +318,10 @@ def run_ours(args):
     v.close()
 
     # ---- reduce over ranks (max time) ----------------------------------------------------------------------------------------
-    t = torch.tensor([res_ms, e2e_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([res_ms, e2e_ms, rot_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    res_ms, e2e_ms = float(t[0]), float(t[1])
+    res_ms, e2e_ms, rot_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -325,6 +356,9 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(n_launch) * args.steps,
+        "resident_rotating_inputs": {"value": world * BATCH / (rot_ms / args.steps / 1e3), "unit": UNIT, "ms_per_step": rot_ms / args.steps,
+                                     "protocol": f"no L2 flush; {n_pairs} distinct (y0, dL/dz) pairs = {n_pairs * pair_bytes / 1e6:.0f} MB > L2, one per step; "
+                                                 "engine state and weights stay warm (the headline `value` flushes everything)"},
         "roofline": {"bound": "tensor", "kernel": "k_conv3x3_tc<3,1,1> as launched in the step (BatchNorm-apply operand prologue + tcgen05 3xTF32 implicit-GEMM conv3x3, "
                                "M=6272 pixels N=64 K=576 + BatchNorm-statistics epilogue); the dgrad variant <3,2,2> is timed next to it",
                      "achieved": achieved_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf_sust"],
