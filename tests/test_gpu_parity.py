@@ -97,9 +97,17 @@ def test_rhs_conv_bn():
     _rhs_case(W.mnist_block(batch=16, channels=64), exact=False)
 
 
-def test_tensor_core_conv_matches_simt_conv():
-    """The tcgen05 3xTF32 implicit-GEMM convolution against the fp32 SIMT kernels on the same engine (config #2 block)."""
+@pytest.mark.parametrize("act", ["relu", "identity", "tanh"])
+def test_tensor_core_conv_matches_simt_conv(act):
+    """The tcgen05 3xTF32 implicit-GEMM convolution (with its fused BatchNorm prologue / statistics epilogues for ReLU and identity,
+    separate kernels for tanh) against the fp32 SIMT kernels on the same engine (config #2 block, batch 128).
+    f(z) agrees to 3e-5 of its maximum for every activation.  The vjp does too when the activation is smooth; with ReLU a single
+    mask flip at an element whose pre-activation is below the fp32 accumulation noise (~3e-6 here) moves a per-channel BatchNorm
+    backward sum by ~1e-2 (see test_mnist_block_small_default_mode), so the gradients are compared in relative L2."""
     w = W.mnist_block(batch=128, channels=64)
+    for l in w.conf.layers:
+        if l.kind == _lib.LAYER_BATCHNORM:
+            l.activation = act
     rng = np.random.default_rng(5)
     g = rng.standard_normal(w.shape).astype(np.float32)
     res = []
@@ -108,8 +116,12 @@ def test_tensor_core_conv_matches_simt_conv():
         v.setParams(w.params)
         res.append(v.rhs_vjp(w.y0, g))
         v.close()
-    for a, b, name in zip(res[0], res[1], ("f(z)", "g^T df/dz", "g^T df/dtheta")):
-        assert np.abs(a - b).max() <= 3e-5 * np.abs(b).max(), name
+    assert np.abs(res[0][0] - res[1][0]).max() <= 3e-5 * np.abs(res[1][0]).max(), "f(z)"
+    for a, b, name in zip(res[0][1:], res[1][1:], ("g^T df/dz", "g^T df/dtheta")):
+        if act == "relu":
+            assert _rel_l2(a, b) < 1e-2, name
+        else:
+            assert np.abs(a - b).max() <= 3e-5 * np.abs(b).max(), name
 
 
 def test_rhs_conv_bn_ragged_channels():
