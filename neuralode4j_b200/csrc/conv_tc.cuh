@@ -113,10 +113,39 @@ struct ConvTcArgs {
     const float* ebeta;
     int eact;             // its activation (ReLU or identity)
     Ref edgamma, edbeta;
+    long long* dbg;       // optional (N4J_CONV_DBG): SM-clock timestamps of CTA 0's phases, see engine.cu: bench_piece
 };
+
+// Finalisation of the deferred BatchNorm statistics for the operand prologue: one channel per thread of warps 0-1.  Deliberately
+// NOT inlined (and fed by value): inlined, the compiler hoists the loop-invariant double-precision reciprocal / division sequences in front of the
+// operand loads of ALL warps (measured: the loads were issued 2700 cycles after kernel entry instead of ~1000).
+template <int PRO>
+__device__ __noinline__ void conv_finalize_stats(double r0, double r1, double r2, double r3, long long rows, float eps, float (*s_fin)[64],
+                                                  float* dgamma, float* dbeta) {      // everything by value: no local copy of the kernel arguments
+    const int c = threadIdx.x;
+    const double M = (double)rows;
+    const double m = r0 / M;
+    double var = r1 / M - m * m;
+    if (var < 0) var = 0;
+    s_fin[0][c] = (float)m;
+    s_fin[1][c] = (float)(1.0 / sqrt(var + (double)eps));
+    if (PRO == 2) {
+        s_fin[2][c] = (float)(r2 / M);
+        s_fin[3][c] = (float)(r3 / M);
+        if (dgamma) { dgamma[c] = (float)r3; dbeta[c] = (float)r2; }
+    }
+}
+
+__device__ __forceinline__ void conv_stamp(const ConvTcArgs& a, int slot) {
+    if (a.dbg && blockIdx.x == 0) a.dbg[slot] = clock64();
+}
+__device__ __forceinline__ void conv_stamp_max(const ConvTcArgs& a, int slot) {
+    if (a.dbg && blockIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(a.dbg + slot), (unsigned long long)clock64());
+}
 
 template <int PASSES, int EPI, int PRO>
 __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcArgs a) {
+    if (threadIdx.x == 0) conv_stamp(a, 0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // dependents may be scheduled; they park in their own wait
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const ConvGeom& g = a.g;
@@ -148,6 +177,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
     const uint32_t tmem = *tmem_slot;
     // barrier init and the TMEM allocation above overlap the tail of the producing kernel; global memory is touched from here on
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) conv_stamp(a, 1);
 
     if constexpr (PRO != 0) {
         // ---- fused operand prologue, all sixteen warps: BatchNorm apply (+ReLU) or BatchNorm backward dx, TF32 hi/lo split,
@@ -214,22 +244,13 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 if (rem >= 0 && bq < 0) bq = 0;
                 while (rem >= per) { rem -= per; ++bq; }
             }
+            if (threadIdx.x == 0) conv_stamp(a, 2);
             if (a.pbn.deferred && rr == rbase) {       // first (for W <= 14: only) pass; every thread of the CTA gets here
-                if (warp < 2) {
-                    const int c = threadIdx.x;
-                    const double M = (double)a.pbn.rows;
-                    const double m = raw[0] / M;
-                    double var = raw[1] / M - m * m;
-                    if (var < 0) var = 0;
-                    s_fin[0][c] = (float)m;
-                    s_fin[1][c] = (float)(1.0 / sqrt(var + (double)a.pbn.eps));
-                    if (PRO == 2) {
-                        s_fin[2][c] = (float)(raw[2] / M);
-                        s_fin[3][c] = (float)(raw[3] / M);
-                        if (blockIdx.x == 0) { resolve(a.pdgamma)[c] = (float)raw[3]; resolve(a.pdbeta)[c] = (float)raw[2]; }
-                    }
-                }
+                if (warp < 2)
+                    conv_finalize_stats<PRO>(raw[0], raw[1], raw[2], raw[3], a.pbn.rows, a.pbn.eps, s_fin,
+                                             (PRO == 2 && blockIdx.x == 0) ? resolve(a.pdgamma) : nullptr, (PRO == 2 && blockIdx.x == 0) ? resolve(a.pdbeta) : nullptr);
                 __syncthreads();
+                if (threadIdx.x == 0) conv_stamp(a, 3);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     mean[k] = s_fin[0][c0 + k]; inv[k] = s_fin[1][c0 + k];
@@ -274,9 +295,10 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 }
             }
         }
+        if (threadIdx.x == 0) conv_stamp(a, 4);
         tc::fence_proxy_async();          // generic-proxy writes above -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(a_full);
+        if (lane == 0) { tc::mbar_arrive(a_full); conv_stamp_max(a, 5); }
     }
 
     if (warp == 0) {
@@ -305,6 +327,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             constexpr uint32_t idesc128 = tc::idesc_tf32(128, 128, 0, 0), idesc64 = tc::idesc_tf32(128, 64, 0, 0);
             const uint32_t sA_u = tc::smem_u32(sA), sW_u = tc::smem_u32(sW);
             tc::mbar_wait(a_full, 0);
+            conv_stamp(a, 6);
             uint32_t acc = 0;
             for (int tap = 0; tap < 9; ++tap) {
                 const int s = tap % CONV_TC_STAGES;
@@ -330,6 +353,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 tc::mma_commit(&w_empty[s]);
             }
             tc::mma_commit(d_full);
+            conv_stamp(a, 7);
         }
     } else if (warp < 10) {
         // ---- epilogue, eight warps: TMEM lane = tile row = one padded pixel; a warp reads its lane quadrant (warp & 3, fixed by the
@@ -393,6 +417,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             }
         }
         tc::mbar_wait(d_full, 0);
+        if (threadIdx.x == 64) conv_stamp(a, 8);
         tc::tc_fence_after();
         {
             float v[32];
@@ -420,6 +445,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 }
             }
         }
+        if (threadIdx.x == 64) conv_stamp(a, 9);
         if constexpr (EPI != 0) {
             asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps only
             {   // column sums: 256 threads = 64 columns x 4 row quarters, combined through shared memory (one atomic per address and CTA)
@@ -478,9 +504,11 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             }
         }
     }
+    if (threadIdx.x == 64) conv_stamp(a, 10);
     tc::tc_fence_before();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<128>(tmem);
+    if (threadIdx.x == 0) conv_stamp(a, 11);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------

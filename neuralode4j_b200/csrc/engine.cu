@@ -1530,6 +1530,25 @@ void Engine::bench_piece(int what, int iters, float* us) {
         }
         if (!found) throw Error{N4J_ERR_INVALID_ARGUMENT, "no fused tensor-core conv launch in this inner graph"};
     }
+    if ((what == N4J_BENCH_CONV_FWD_FUSED || what == N4J_BENCH_CONV_DGRAD_FUSED) && getenv("N4J_CONV_DBG")) {
+        // debug aid: SM-clock timestamps of CTA 0's phases (conv_stamp in conv_tc.cuh), printed relative to kernel entry
+        long long* d = nullptr;
+        N4J_CUDA(cudaMalloc(&d, sizeof(long long) * 16));
+        ConvRec r2 = rec;
+        r2.a.dbg = d;
+        for (int rep = 0; rep < 3; ++rep) {
+            N4J_CUDA(cudaMemsetAsync(d, 0, sizeof(long long) * 16, stream_));
+            launch_conv_args(stream_, r2.a, r2.pro, r2.epi);
+            long long h[16];
+            N4J_CUDA(cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, stream_));
+            N4J_CUDA(cudaStreamSynchronize(stream_));
+            fprintf(stderr, "[conv dbg pro=%d epi=%d] cycles since entry: setup %lld | loads issued %lld | finals barrier %lld | t0 prologue done %lld | "
+                            "last warp arrived %lld | mma start %lld | mma issued %lld | d_full seen %lld | out stored %lld | stats done %lld | exit %lld\n",
+                    r2.pro, r2.epi, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0], h[9] - h[0],
+                    h[10] - h[0], h[11] - h[0]);
+        }
+        cudaFree(d);
+    }
     for (int i = 0; i < 3; ++i) piece();
     N4J_CUDA(cudaEventRecord(ev0_, stream_));
     for (int i = 0; i < iters; ++i) piece();
