@@ -662,7 +662,8 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                     // augmented evaluation: the last BatchNorm's apply is done by the first backward kernel (k_bn_bwd_stats64)
                     fwd_left_last_bn_ = true;
                 } else {
-                    LAUNCH(k_bn_apply, grid_for(l.out_len), 256, s, cur, dst, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn, l.d.activation, l.rows, cc);
+                    if (cc == 64) LAUNCH(k_bn_apply64, grid_for(l.out_len / 4), 256, s, cur, dst, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn, l.d.activation, l.rows);
+                    else LAUNCH(k_bn_apply, grid_for(l.out_len), 256, s, cur, dst, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn, l.d.activation, l.rows, cc);
                 }
                 break;
             }
@@ -754,8 +755,12 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                            l.gin, L_[i - 1].gimg, dth, with_off(dth, cc));
                     gimg_ready = true;
                 } else {
-                    LAUNCH(k_bn_bwd_dx, grid_for(l.in_len), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, l.rows, cc, dx, dth, with_off(dth, cc),
-                           params_.p + l.p_off + cc);
+                    if (cc == 64)
+                        LAUNCH(k_bn_bwd_dx64, grid_for(l.in_len / 4), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, l.rows, dx, dth,
+                               with_off(dth, cc));
+                    else
+                        LAUNCH(k_bn_bwd_dx, grid_for(l.in_len), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, l.rows, cc, dx, dth,
+                               with_off(dth, cc), params_.p + l.p_off + cc);
                 }
                 break;
             }

@@ -335,6 +335,83 @@ __global__ void __launch_bounds__(256) k_bn_apply(Ref xin, Ref yout, const float
         y[i] = act_fwd(act, __fadd_rn(__fmul_rn(gamma[c], h), beta[c]));
     }
 }
+// 64-channel float4 forms of the two elementwise BatchNorm kernels left on the MNIST chain.  A thread owns one 4-channel chunk
+// (threadIdx & 15) and rows (global thread / 16) + k * (threads / 16).  With deferred statistics the loads of the FIRST item are
+// issued before the finalisation (64 threads, double division / sqrt, ~0.7-1.5 us) so that the two latencies overlap.
+__global__ void __launch_bounds__(256) k_bn_apply64(Ref xin, Ref yout, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     BnScratch sc, int act, long long M) {
+    pdl_begin();
+    const float4* __restrict__ x = reinterpret_cast<const float4*>(resolve(xin));
+    float4* __restrict__ y = reinterpret_cast<float4*>(resolve(yout));
+    const long long n4 = M * 16, step = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c0 = (threadIdx.x & 15) * 4;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) xv = x[i];
+    __shared__ float s_mean[64], s_inv[64];
+    if (threadIdx.x < 64) {
+        if (sc.deferred) bn_fwd_final(sc, threadIdx.x, s_mean[threadIdx.x], s_inv[threadIdx.x]);
+        else { s_mean[threadIdx.x] = sc.mean[threadIdx.x]; s_inv[threadIdx.x] = sc.invstd[threadIdx.x]; }
+    }
+    __syncthreads();
+    float mean[4], inv[4], ga[4], be[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { mean[k] = s_mean[c0 + k]; inv[k] = s_inv[c0 + k]; ga[k] = gamma[c0 + k]; be[k] = beta[c0 + k]; }
+    for (; i < n4; i += step) {
+        const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+        if (i + step < n4) xv = x[i + step];
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = act_fwd(act, __fadd_rn(__fmul_rn(ga[k], __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k])), be[k]));
+        y[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+// dx = gamma*invstd * ((dy - mean(dy)) - xhat*mean(dy*xhat)),  dy = act'(y) * (gscale*g)
+__global__ void __launch_bounds__(256) k_bn_bwd_dx64(Ref gin, float gscale, Ref yref, Ref xin, const float* __restrict__ gamma, BnScratch sc,
+                                                      int act, long long M, Ref dxout, Ref dgamma_ref, Ref dbeta_ref) {
+    pdl_begin();
+    const float4* __restrict__ g = reinterpret_cast<const float4*>(resolve(gin));
+    const float4* __restrict__ y = reinterpret_cast<const float4*>(resolve(yref));
+    const float4* __restrict__ x = reinterpret_cast<const float4*>(resolve(xin));
+    float4* __restrict__ dx = reinterpret_cast<float4*>(resolve(dxout));
+    const long long n4 = M * 16, step = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c0 = (threadIdx.x & 15) * 4;
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), yv = gv, xv = gv;
+    if (i < n4) { gv = g[i]; yv = y[i]; xv = x[i]; }
+    __shared__ float s_st[4][64];      // mean, invstd, mean(dy), mean(dy*xhat)
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        if (sc.deferred) {
+            float dg, db;
+            bn_fwd_final(sc, c, s_st[0][c], s_st[1][c]);
+            bn_bwd_final(sc, c, s_st[2][c], s_st[3][c], dg, db);
+            if (blockIdx.x == 0) { resolve(dgamma_ref)[c] = dg; resolve(dbeta_ref)[c] = db; }
+        } else {
+            s_st[0][c] = sc.mean[c]; s_st[1][c] = sc.invstd[c]; s_st[2][c] = sc.m_dy[c]; s_st[3][c] = sc.m_dyxh[c];
+        }
+    }
+    __syncthreads();
+    float mean[4], inv[4], kk[4], mdy[4], mdyxh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        mean[k] = s_st[0][c0 + k]; inv[k] = s_st[1][c0 + k]; mdy[k] = s_st[2][c0 + k]; mdyxh[k] = s_st[3][c0 + k];
+        kk[k] = __fmul_rn(gamma[c0 + k], inv[k]);
+    }
+    for (; i < n4; i += step) {
+        const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
+        if (i + step < n4) { gv = g[i + step]; yv = y[i + step]; xv = x[i + step]; }
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float dy = act_bwd(act, yy[k], __fmul_rn(gscale, gg[k]));
+            const float xh = __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k]);
+            o[k] = __fmul_rn(kk[k], __fsub_rn(__fsub_rn(dy, mdy[k]), __fmul_rn(xh, mdyxh[k])));
+        }
+        dx[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 // backward statistics: dy = act'(y)*(gscale*g);  sums of dy and dy*xhat (double) -> dgamma, dbeta, means
 __global__ void __launch_bounds__(256) k_bn_bwd_stats(Ref gin, float gscale, Ref yref, Ref xin, BnScratch sc, int act, long long M, int C,
                                                        Ref dgamma_ref, Ref dbeta_ref) {
@@ -415,31 +492,42 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats64(Ref gin, float gscale, R
     float* __restrict__ y = resolve(yref);
     const float* __restrict__ x = resolve(xin);
     const int chunk = threadIdx.x & 15, rg = threadIdx.x >> 4;
+    const long long rstep = (long long)gridDim.x * 16;
+    long long r = (long long)blockIdx.x * 16 + rg;
+    // the loads of the first row are issued before the statistics are finalised (the two latencies overlap)
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f), xv = gv, yv = gv;
+    if (r < M) {
+        gv = reinterpret_cast<const float4*>(g)[r * 16 + chunk];
+        xv = reinterpret_cast<const float4*>(x)[r * 16 + chunk];
+        if (!fuse_fwd) yv = reinterpret_cast<const float4*>(y)[r * 16 + chunk];
+    }
     float mean[4], inv[4], ga[4], be[4];
-#pragma unroll
     __shared__ float s_mi[2][64];
     if (sc.deferred) {       // one channel per thread, once per block (double division / square root are long sequences)
         if (threadIdx.x < 64) bn_fwd_final(sc, threadIdx.x, s_mi[0][threadIdx.x], s_mi[1][threadIdx.x]);
         __syncthreads();
     }
+#pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (sc.deferred) { mean[k] = s_mi[0][chunk * 4 + k]; inv[k] = s_mi[1][chunk * 4 + k]; }
         else { mean[k] = sc.mean[chunk * 4 + k]; inv[k] = sc.invstd[chunk * 4 + k]; }
         ga[k] = fuse_fwd ? gamma[chunk * 4 + k] : 0.f; be[k] = fuse_fwd ? beta[chunk * 4 + k] : 0.f;
     }
     double a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
-    for (long long r = (long long)blockIdx.x * 16 + rg; r < M; r += (long long)gridDim.x * 16) {
+    for (; r < M; r += rstep) {
         const long long i = r * 16 + chunk;
-        const float4 gv = reinterpret_cast<const float4*>(g)[i], xv = reinterpret_cast<const float4*>(x)[i];
         const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, xx[4] = {xv.x, xv.y, xv.z, xv.w};
-        float yy[4];
+        float yy[4] = {yv.x, yv.y, yv.z, yv.w};
+        if (r + rstep < M) {
+            const long long in = (r + rstep) * 16 + chunk;
+            gv = reinterpret_cast<const float4*>(g)[in];
+            xv = reinterpret_cast<const float4*>(x)[in];
+            if (!fuse_fwd) yv = reinterpret_cast<const float4*>(y)[in];
+        }
         if (fuse_fwd) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) yy[k] = act_fwd(act, __fadd_rn(__fmul_rn(ga[k], __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k])), be[k]));
             reinterpret_cast<float4*>(y)[i] = make_float4(yy[0], yy[1], yy[2], yy[3]);
-        } else {
-            const float4 yv = reinterpret_cast<const float4*>(y)[i];
-            yy[0] = yv.x; yy[1] = yv.y; yy[2] = yv.z; yy[3] = yv.w;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
