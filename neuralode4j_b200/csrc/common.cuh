@@ -116,6 +116,8 @@ struct CommDev {
     unsigned int xticket;
     unsigned int pad2_;
     long long xcap;                   // floats per parity in xbuf
+    long long xll_off;                // LL vector exchange: uint64 cell[2 parities][8 ranks][xll_cap] at this byte offset of every comm region
+    long long xll_cap;                // cells (floats) per (parity, rank); 0: no LL buffer
     char* peer[COMM_MAX_WORLD];       // base of every rank's comm region (peer[rank] is the local one)
 };
 
@@ -129,43 +131,53 @@ __device__ __forceinline__ bool comm_wait_flag(volatile unsigned long long* f, u
 }
 
 // Small all-reduce, LL style: every 8-byte cell carries 4 bytes of payload and the 4-byte sequence tag, so a value is
-// complete exactly when its two cells show the current tag — no flags, no system fences on the critical path (one NVLink
-// store latency per exchange).  Called by `nthr` threads (tid 0..nthr-1) that can synchronise through `sync()`;
+// complete exactly when its two cells (one 16-byte store) show the current tag — no flags, no system fences on the critical path
+// (one NVLink store latency per exchange).  Called by `nthr` threads (tid 0..nthr-1) that can synchronise through `sync()`;
 // vals[n] (shared memory, n <= COMM_SLOT) in -> global totals out (summed in rank order, identical on every rank).
 template <class SyncFn>
 __device__ __forceinline__ void comm_allreduce_small(CommDev* cm, double* vals, int n, int tid, int nthr, SyncFn sync) {
-    __shared__ unsigned long long s_seq;
-    if (tid == 0) { s_seq = cm->seq_small + 1; cm->seq_small = s_seq; }
-    sync();
-    const unsigned long long seq = s_seq;
+    // Latency matters here, not bandwidth: every thread reads the sequence number, rank, world and its peer bases itself (independent
+    // loads of one cache line, no broadcast through shared memory in front of the stores), the own contribution never leaves shared
+    // memory, and the peers' cells of a value are requested together and re-requested until all carry the tag.
+    const unsigned long long seq = *((volatile unsigned long long*)&cm->seq_small) + 1;
+    const int me = cm->rank, W = cm->world;
     const unsigned int tag = (unsigned int)seq;
-    const int par = (int)(seq & 1), me = cm->rank, W = cm->world;
-    // push: cell[(par, me, 2*i + half)] on every rank (including the local one)
-    for (int idx = tid; idx < W * n; idx += nthr) {
-        const int pr = idx / n, i = idx - pr * n;
+    const int par = (int)(seq & 1);
+    // push: cell[(par, me, 2*i + half)] on every peer
+    for (int idx = tid; idx < (W - 1) * n; idx += nthr) {
+        const int p = idx / n, i = idx - p * n, pr = p + (p >= me ? 1 : 0);
         const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[i]);
-        volatile unsigned long long* cell = reinterpret_cast<unsigned long long*>(cm->peer[pr] + COMM_OFF_MBOX) +
-                                            ((long long)(par * COMM_MAX_WORLD + me) * COMM_SLOT + i) * 2;
-        cell[0] = ((unsigned long long)tag << 32) | (bits & 0xFFFFFFFFull);
-        cell[1] = ((unsigned long long)tag << 32) | (bits >> 32);
+        unsigned long long* cell = reinterpret_cast<unsigned long long*>(cm->peer[pr] + COMM_OFF_MBOX) + ((long long)(par * COMM_MAX_WORLD + me) * COMM_SLOT + i) * 2;
+        const ulonglong2 c = make_ulonglong2(((unsigned long long)tag << 32) | (bits & 0xFFFFFFFFull), ((unsigned long long)tag << 32) | (bits >> 32));
+        asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(cell), "l"(c.x), "l"(c.y) : "memory");
     }
-    sync();
-    // pull: wait for the tag on every contribution, sum in rank order
+    sync();      // every thread has read seq_small
+    if (tid == 0) cm->seq_small = seq;
+    // pull: sum in rank order
+    const unsigned long long* mbox = reinterpret_cast<const unsigned long long*>(cm->peer[me] + COMM_OFF_MBOX) + (long long)par * COMM_MAX_WORLD * COMM_SLOT * 2;
     for (int i = tid; i < n; i += nthr) {
-        double t = 0.0;
-        for (int q = 0; q < W; ++q) {
-            volatile unsigned long long* cell = reinterpret_cast<unsigned long long*>(cm->peer[me] + COMM_OFF_MBOX) +
-                                                ((long long)(par * COMM_MAX_WORLD + q) * COMM_SLOT + i) * 2;
-            unsigned long long c0 = 0, c1 = 0;
-            bool ok = false;
-            for (unsigned int spin = 0; spin < (1u << 28); ++spin) {
-                c0 = cell[0]; c1 = cell[1];
-                if ((unsigned int)(c0 >> 32) == tag && (unsigned int)(c1 >> 32) == tag) { ok = true; break; }
-                if ((spin & 255) == 255) __nanosleep(32);
+        unsigned long long c0[COMM_MAX_WORLD], c1[COMM_MAX_WORLD];
+        bool ok = false;
+        for (unsigned int spin = 0; spin < (1u << 26) && !ok; ++spin) {
+            ok = true;
+#pragma unroll
+            for (int q = 0; q < COMM_MAX_WORLD; ++q) {
+                if (q < W && q != me) {
+                    const unsigned long long* cell = mbox + ((long long)q * COMM_SLOT + i) * 2;
+                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(c0[q]), "=l"(c1[q]) : "l"(cell) : "memory");
+                }
             }
-            if (!ok) cm->status = 1;
-            t += __longlong_as_double((long long)((c0 & 0xFFFFFFFFull) | (c1 << 32)));
+#pragma unroll
+            for (int q = 0; q < COMM_MAX_WORLD; ++q)
+                if (q < W && q != me && ((unsigned int)(c0[q] >> 32) != tag || (unsigned int)(c1[q] >> 32) != tag)) ok = false;
+            if (!ok && (spin & 255) == 255) __nanosleep(32);
         }
+        if (!ok) cm->status = 1;
+        const double mine = vals[i];
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < COMM_MAX_WORLD; ++q)
+            if (q < W) t += q == me ? mine : __longlong_as_double((long long)((c0[q] & 0xFFFFFFFFull) | (c1[q] << 32)));
         vals[i] = t;
     }
     sync();
@@ -173,6 +185,53 @@ __device__ __forceinline__ void comm_allreduce_small(CommDev* cm, double* vals, 
 struct BlockSyncFn { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
 __device__ __forceinline__ void comm_allreduce_block(CommDev* cm, double* vals, int n) {
     comm_allreduce_small(cm, vals, n, (int)threadIdx.x, (int)blockDim.x, BlockSyncFn{});
+}
+
+// LL all-reduce of four consecutive floats of a vector (parameter-gradient slots): every float travels as an 8-byte cell
+// {payload, tag}, two cells per 16-byte store, straight into every peer's cell[parity][my rank][i..i+3]; the caller's own cells
+// are then polled for the peers' tags and summed in rank order (bitwise identical on all ranks).  No tickets, flags or fences on
+// the way: one NVLink store latency.  i is a float index (multiple of 4) below xll_cap; tag = the exchange's sequence number.
+__device__ __forceinline__ float4 comm_ll_allreduce4(const CommDev* cm, unsigned int tag, int par, long long i, float4 v) {
+    const int me = cm->rank, W = cm->world;
+    const unsigned long long hi = (unsigned long long)tag << 32;
+    const ulonglong2 c01 = make_ulonglong2(hi | __float_as_uint(v.x), hi | __float_as_uint(v.y));
+    const ulonglong2 c23 = make_ulonglong2(hi | __float_as_uint(v.z), hi | __float_as_uint(v.w));
+    const long long slot = ((long long)(par * COMM_MAX_WORLD + me) * cm->xll_cap + i) * 8;
+#pragma unroll
+    for (int q = 0; q < COMM_MAX_WORLD; ++q) {
+        if (q < W && q != me) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(cm->peer[q] + cm->xll_off + slot);
+            dst[0] = c01;
+            dst[1] = c23;
+        }
+    }
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < W; ++q) {
+        float4 u = v;
+        if (q != me) {
+            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(cm->peer[me] + cm->xll_off +
+                                                                                        ((long long)(par * COMM_MAX_WORLD + q) * cm->xll_cap + i) * 8);
+            unsigned long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            bool ok = false;
+            for (unsigned int spin = 0; spin < (1u << 26); ++spin) {
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(src) : "memory");
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a2), "=l"(a3) : "l"(src + 2) : "memory");
+                if ((unsigned int)(a0 >> 32) == tag && (unsigned int)(a1 >> 32) == tag && (unsigned int)(a2 >> 32) == tag && (unsigned int)(a3 >> 32) == tag) { ok = true; break; }
+                if ((spin & 255) == 255) __nanosleep(32);
+            }
+            if (!ok) const_cast<CommDev*>(cm)->status = 1;
+            u = make_float4(__uint_as_float((unsigned int)a0), __uint_as_float((unsigned int)a1), __uint_as_float((unsigned int)a2), __uint_as_float((unsigned int)a3));
+        }
+        t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    return t;
+}
+// every block of an LL vector exchange calls this when it leaves: the last one bumps the sequence number for the next exchange
+__device__ __forceinline__ void comm_ll_leave(CommDev* cm, unsigned long long seq) {
+    if (threadIdx.x == 0) {
+        const unsigned int tk = atomicAdd(&cm->pad2_, 1u);
+        if (tk == gridDim.x - 1) { cm->pad2_ = 0u; __threadfence(); cm->seq_x = seq; }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

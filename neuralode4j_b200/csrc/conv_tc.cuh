@@ -632,9 +632,11 @@ __global__ void __launch_bounds__(256, 1) k_conv_wgrad64(Ref xin, Ref gin, ConvG
 inline size_t conv_wgrad_smem_bytes(const ConvGeom& g) { return sizeof(float) * 64 * ((size_t)g.PH * g.PW + (size_t)g.H * g.W); }
 
 // dst[i] = sum_b part[b][i]  (fixed order), i over 9*64*64.  Block = 64 float4 columns x 4 partial groups.
-__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ part, Ref dstref, int nparts) {
+// cm != nullptr (sharded path): the sum over the ranks rides on the same launch (LL exchange of the finished float4).
+__global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ part, Ref dstref, int nparts, CommDev* cm) {
     pdl_begin();
     float* __restrict__ dst = resolve(dstref);
+    const unsigned long long seq = cm ? cm->seq_x + 1 : 0ull;
     const int n4 = 9 * 4096 / 4;
     const int col = blockIdx.x * 64 + (threadIdx.x & 63), grp = threadIdx.x >> 6;
     __shared__ float4 sm[4][64];
@@ -654,8 +656,10 @@ __global__ void __launch_bounds__(256) k_wgrad_reduce(const float* __restrict__ 
         float4 t = sm[0][threadIdx.x];
 #pragma unroll
         for (int q = 1; q < 4; ++q) { const float4 v = sm[q][threadIdx.x]; t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+        if (cm) t = comm_ll_allreduce4(cm, (unsigned int)seq, (int)(seq & 1), (long long)col * 4, t);
         reinterpret_cast<float4*>(dst)[col] = t;
     }
+    if (cm) { __syncthreads(); comm_ll_leave(cm, seq); }
 }
 
 // BatchNorm backward dx written as the compact gradient AND as the operand image of the following dgrad convolution

@@ -786,7 +786,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     const float* Wt = params_.p + l.p_off;
                     if (l.exact) {
                         LAUNCH(k_dense_wgrad_exact, (int)std::min<long long>(l.g_len, 148 * 8), 128, s, x, d, dth, l.rows, l.c_in, l.c_out, l.d.has_bias);
-                        if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, s, comm_dev_, dth, l.g_len);
+                        if (comm_dev_) enqueue_vec_allreduce(s, dth, l.g_len);
                         LAUNCH(k_dense_dgrad_exact, grid_for(l.in_len), 256, s, d, Wt, dx, l.rows, l.c_in, l.c_out);
                     } else if (l.tcd) {
                         LAUNCH(k_rowmajor_to_image, grid_for(l.out_len / 4), 256, s, d, 1.f, l.dimg, l.rows, l.c_out, l.img_rows);
@@ -799,7 +799,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                         wa.a_img = l.dTimg; wa.a_rows = (long long)((l.c_out + 127) / 128 * 128); wa.b_img = l.xTimg; wa.b_nch = (int)(l.img_rows / 4);
                         launch_gemm_tc(s, l.tm_dT, l.tm_xT, wa);
                         if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 256, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
-                        if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, s, comm_dev_, dth, l.g_len);
+                        if (comm_dev_) enqueue_vec_allreduce(s, dth, l.g_len);
                         GemmTcArgs qa{};     // dx[b,i] = sum_o delta[b,o] W(i,o)
                         qa.M = (int)l.rows; qa.N = l.c_in; qa.kblocks = l.c_out / 32; qa.a_nch = l.c_out / 4; qa.out = dx;
                         qa.a_img = l.dimg; qa.a_rows = l.img_rows; qa.b_img = l.wsb; qa.b_nch = l.c_out / 4;
@@ -813,7 +813,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                         launch_gemm<G_DENSE_WGRAD>(s, w, launches_, exact_);
                         if (w.splits > 1) LAUNCH(k_splitk_reduce, grid_for((long long)l.c_in * l.c_out), 256, s, wpart_.p, dth, (long long)l.c_in * l.c_out, 8);
                         if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 256, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
-                        if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, s, comm_dev_, dth, l.g_len);
+                        if (comm_dev_) enqueue_vec_allreduce(s, dth, l.g_len);
                         GemmArgs q{}; q.a = d; q.c = dx; q.w = Wt; q.M = (int)l.rows; q.N = l.c_in; q.K = l.c_out; q.splits = 1;
                         launch_gemm<G_DENSE_DGRAD>(s, q, launches_, exact_);
                     }
@@ -850,8 +850,10 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     const int ipc = wide ? 1 : (int)((B_ + 63) / 64), wg_ctas = (int)((B_ + ipc - 1) / ipc);
                     k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, side_>>>(x, d, geom_, wpart_.p, ipc);
                     ++launches_;
-                    LAUNCH(k_wgrad_reduce, 144, 256, side_, wpart_.p, dth, wg_ctas);
-                    if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, side_, comm_dev_, dth, l.g_len);
+                    // sharded path: the sum over the ranks rides on the reduction (LL exchange of every finished float4)
+                    const bool ll = comm_dev_ && vec_allreduce_ll_ && l.g_len <= comm_xll_cap_ && !skip_vec_allreduce_;
+                    LAUNCH(k_wgrad_reduce, 144, 256, side_, wpart_.p, dth, wg_ctas, ll ? comm_dev_ : (CommDev*)nullptr);
+                    if (comm_dev_ && !ll) enqueue_vec_allreduce(side_, dth, l.g_len);
                     forked = true;
                     side_busy_ = true;
                 } else {
@@ -860,7 +862,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     if (exact_) w.c = dth;
                     launch_gemm<G_CONV_WGRAD>(s, w, launches_, exact_);
                     if (!exact_) LAUNCH(k_splitk_reduce, grid_for(l.g_len), 256, s, wpart_.p, dth, l.g_len, 16);
-                    if (comm_dev_) LAUNCH(k_comm_allreduce_vec, comm_grid(l.g_len), 256, s, comm_dev_, dth, l.g_len);
+                    if (comm_dev_) enqueue_vec_allreduce(s, dth, l.g_len);
                     GemmArgs q{}; q.a = d; q.c = dx; q.w = l.wb; q.M = (int)l.rows; q.N = l.c_in; q.K = 9 * l.c_out;
                     q.H = l.H; q.W = l.W; q.Ci = l.c_in; q.Co = l.c_out; q.splits = 1;
                     launch_gemm<G_CONV_DGRAD>(s, q, launches_, exact_);
@@ -1092,6 +1094,15 @@ void Engine::finish_call(n4j_stats* st, int) {
 // =====================================================================================================
 // multi-GPU setup: exchange buffers in peer-mapped memory (CUDA IPC, one process per GPU)
 // =====================================================================================================
+// all-reduce (sum over the ranks) of a parameter-gradient slot, in place
+void Engine::enqueue_vec_allreduce(cudaStream_t s, Ref slot, long long n) {
+    if (skip_vec_allreduce_) return;      // N4J_DBG_SKIP_VEC_ALLREDUCE: timing experiments only (wrong gradients)
+    const bool aligned = (slot.off % 4 == 0) && (slot.stride % 4 == 0);
+    if (vec_allreduce_ll_ && n % 4 == 0 && n <= comm_xll_cap_ && aligned)
+        LAUNCH(k_comm_allreduce_vec_ll, (int)std::max<long long>(1, std::min<long long>(296, (n / 4 + 255) / 256)), 256, s, comm_dev_, slot, n);
+    else
+        LAUNCH(k_comm_allreduce_vec, comm_grid(n), 256, s, comm_dev_, slot, n);
+}
 int Engine::comm_grid(long long n) const { return (int)std::max<long long>(1, std::min<long long>(64, (n + 511) / 512)); }
 
 void Engine::comm_export(void* handle64) {
@@ -1101,6 +1112,11 @@ void Engine::comm_export(void* handle64) {
         for (auto& l : L_) xcap = std::max(xcap, round_up4(l.g_len));
         comm_xcap_ = xcap;
         comm_bytes_ = (size_t)COMM_OFF_XBUF + sizeof(float) * 2 * (size_t)xcap;
+        // LL cells for parameter-gradient slots up to 256k floats (8 bytes per float and source rank, two parities); longer
+        // slots (config #3's 4096 x 4096 layers) keep the bandwidth-efficient pull exchange through xbuf
+        comm_xll_cap_ = std::min<long long>(xcap, 1LL << 18);
+        comm_xll_off_ = (long long)comm_bytes_;
+        comm_bytes_ += (size_t)2 * COMM_MAX_WORLD * (size_t)comm_xll_cap_ * 8;
         N4J_CUDA(cudaMalloc(&comm_region_, comm_bytes_));
         N4J_CUDA(cudaMemset(comm_region_, 0, comm_bytes_));
     }
@@ -1120,7 +1136,7 @@ void Engine::comm_init(int rank, int world, const void* handles, long long globa
             throw Error{N4J_ERR_UNSUPPORTED, "sharded BatchNorm needs a channel count that is a multiple of 4, divides 1024 and is <= 128"};
     CommDev cd;
     std::memset(&cd, 0, sizeof(cd));
-    cd.rank = rank; cd.world = world; cd.xcap = comm_xcap_;
+    cd.rank = rank; cd.world = world; cd.xcap = comm_xcap_; cd.xll_off = comm_xll_off_; cd.xll_cap = comm_xll_cap_;
     for (int r = 0; r < world; ++r) {
         if (r == rank) { cd.peer[r] = (char*)comm_region_; continue; }
         cudaIpcMemHandle_t hnd;
@@ -1501,7 +1517,7 @@ void Engine::bench_piece(int what, int iters, float* us) {
                     const int ipc = (int)((B_ + 63) / 64), wg_ctas = (int)((B_ + ipc - 1) / ipc);
                     k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, stream_>>>(fixed_ref(gb_[0].p), fixed_ref(gb_[1].p), geom_, wpart_.p, ipc);
                     ++launches_;
-                    LAUNCH(k_wgrad_reduce, 144, 256, stream_, wpart_.p, fixed_ref(theta_tmp_.p), wg_ctas);
+                    LAUNCH(k_wgrad_reduce, 144, 256, stream_, wpart_.p, fixed_ref(theta_tmp_.p), wg_ctas, (CommDev*)nullptr);
                 } else {
                     GemmArgs w{}; w.a = fixed_ref(gb_[0].p); w.b = fixed_ref(gb_[1].p); w.c = fixed_ref(wpart_.p); w.M = 9 * l.c_in; w.N = l.c_out; w.K = (int)l.rows;
                     w.H = l.H; w.W = l.W; w.Ci = l.c_in; w.Co = l.c_out; w.splits = 16;

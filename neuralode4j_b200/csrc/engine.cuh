@@ -126,7 +126,10 @@ private:
     int world_ = 1, rank_id_ = 0;
     void* comm_region_ = nullptr;
     size_t comm_bytes_ = 0;
-    long long comm_xcap_ = 0;
+    long long comm_xcap_ = 0, comm_xll_off_ = 0, comm_xll_cap_ = 0;
+    bool vec_allreduce_ll_ = getenv("N4J_NO_LL_VEC_ALLREDUCE") == nullptr;        // A/B switch: pull exchange through xbuf instead
+    bool skip_vec_allreduce_ = getenv("N4J_DBG_SKIP_VEC_ALLREDUCE") != nullptr;   // timing experiments only
+    void enqueue_vec_allreduce(cudaStream_t s, Ref slot, long long n);
     CommDev* comm_dev_ = nullptr;
     std::vector<void*> peer_ptrs_;
     int comm_grid(long long n) const;   // strided accumulators of the scalar reductions (error norm, initial step)

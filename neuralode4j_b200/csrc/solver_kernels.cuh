@@ -561,4 +561,18 @@ __global__ void __launch_bounds__(256) k_comm_allreduce_vec(CommDev* cm, Ref buf
     }
 }
 
+// The same all-reduce in the LL form (comm_ll_allreduce4): n % 4 == 0, n <= xll_cap, 16-byte aligned slot.  No block waits for
+// another block of its own rank, so the grid is not limited to co-resident blocks.
+__global__ void __launch_bounds__(256) k_comm_allreduce_vec_ll(CommDev* cm, Ref bufref, long long n) {
+    pdl_begin();
+    float4* __restrict__ buf = reinterpret_cast<float4*>(resolve(bufref));
+    const unsigned long long seq = cm->seq_x + 1;
+    const int par = (int)(seq & 1);
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2); i += step)
+        buf[i] = comm_ll_allreduce4(cm, (unsigned int)seq, par, i * 4, buf[i]);
+    __syncthreads();
+    comm_ll_leave(cm, seq);
+}
+
 }  // namespace n4j

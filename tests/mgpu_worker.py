@@ -27,6 +27,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dist.init_process_group("gloo")
     local = 8
+    default_mode = which == "mnist_default"      # the production kernels: tcgen05 convolutions with fused prologue / epilogue exchanges
+    if default_mode:
+        which, flags = "mnist", _lib.FLAG_FORCE_TENSOR
     if which == "mnist":
         wg = W.mnist_block(batch=local * world, channels=64)
     elif which == "mlp":
@@ -79,8 +82,14 @@ def main():
                 if dt is not None:
                     assert np.array_equal(r["dt"], gathered[0]["dt"])
             H.assert_close(outs, o["out"], 1e-4, 1e-5 * np.abs(o["out"]).max(), "out")
-            H.assert_close(dy0s, o["dy0"], 1e-4, 1e-5 * np.abs(o["dy0"]).max(), "dy0")
-            H.assert_close(gathered[0]["grad"], o["grad"], 1e-4, 1e-5 * np.abs(o["grad"]).max(), "grad")
+            if default_mode:
+                # fp32-accumulating contractions on a ReLU + BatchNorm block: gradients agree in relative L2 only
+                for k, got in (("dy0", dy0s), ("grad", gathered[0]["grad"])):
+                    rel = np.linalg.norm(got - o[k]) / np.linalg.norm(o[k])
+                    assert rel < 1e-2, (k, rel)
+            else:
+                H.assert_close(dy0s, o["dy0"], 1e-4, 1e-5 * np.abs(o["dy0"]).max(), "dy0")
+                H.assert_close(gathered[0]["grad"], o["grad"], 1e-4, 1e-5 * np.abs(o["grad"]).max(), "grad")
             if dt is not None:
                 H.assert_close(gathered[0]["dt"], o["dt"], 1e-4, 1e-5 * np.abs(o["dt"]).max(), "dt")
             print(f"MGPU PARITY OK ({which}, world={world}): fwd {gathered[0]['fs']} bwd {gathered[0]['bs']}")

@@ -25,7 +25,7 @@ def _ngpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("which", ["mnist", "mlp", "golden", "anode_time"])
+@pytest.mark.parametrize("which", ["mnist", "mnist_default", "mlp", "golden", "anode_time"])
 def test_sharded_parity(which):
     if _ngpu() < 2:
         pytest.skip("needs two GPUs on one box")
