@@ -105,6 +105,7 @@ struct ConvTcArgs {
     int pact;
     float* pcompact;      // optional: also store the produced tensor compactly (activation for the backward pass / gradient for wgrad)
     Ref pdgamma, pdbeta;  // PRO 2 with deferred statistics: where dgamma / dbeta of that BatchNorm go
+    int prearm;           // PRO 1: CTA 0 re-arms pbn.accf_other (the stage combination in front still read that set: k_stage_combine_last MODE 2)
     // fused BatchNorm BACKWARD statistics in the epilogue (EPI == 2, dgrad launches): the output of this launch is the gradient
     // w.r.t. the output of the BatchNorm layer in front of the conv; sums of dy and dy*xhat over the batch, last CTA writes
     // dgamma / dbeta / mean(dy) / mean(dy*xhat) (same contract as k_bn_bwd_stats64).  `bn`, `bn_rows` describe that layer.
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         // the last block of the statistics kernel used to do.
         __shared__ float s_fin[4][64];     // mean, invstd, mean(dy), mean(dy*xhat)
         double raw[4] = {0.0, 0.0, 0.0, 0.0};
+        if (PRO == 1 && a.prearm && blockIdx.x == 0 && warp >= 2 && warp < 6) a.pbn.accf_other[(threadIdx.x - 64) * ACC_STRIDE] = 0.0;
         if (a.pbn.deferred && warp < 2) {      // warp-uniform on purpose: a real branch, not predicated double-precision code in all warps
             raw[0] = a.pbn.accf[threadIdx.x * ACC_STRIDE]; raw[1] = a.pbn.accf[(64 + threadIdx.x) * ACC_STRIDE];
             if (PRO == 2) { raw[2] = a.pbn.accb[threadIdx.x * ACC_STRIDE]; raw[3] = a.pbn.accb[(64 + threadIdx.x) * ACC_STRIDE]; }

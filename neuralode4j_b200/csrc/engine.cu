@@ -651,6 +651,7 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                     pro_args = ConvTcArgs{};
                     pro_args.px = cur; pro_args.pgamma = params_.p + l.p_off; pro_args.pbeta = params_.p + l.p_off + cc; pro_args.pbn = l.bn;
                     pro_args.pact = l.d.activation; pro_args.pcompact = need_compact ? l.act : (float*)nullptr;
+                    if (i == 0 && prearm_next_) { pro_args.prearm = 1; prearm_next_ = false; }
                     image_ready = true;
                 } else if (feeds_tc) {
                     // BatchNorm-apply writes the next conv's operand image directly (hi/lo split, zero-padded, chunk-major);
@@ -661,6 +662,11 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                 } else if (need_compact && fuse_last_bn_ok_ && i + 1 == L_.size() && cc == 64) {
                     // augmented evaluation: the last BatchNorm's apply is done by the first backward kernel (k_bn_bwd_stats64)
                     fwd_left_last_bn_ = true;
+                } else if (leave_last_ && !need_compact && i + 1 == L_.size() && cc == 64 && l.bn.deferred == 1) {
+                    // forward solve, stages 1-5: the stage combination that follows applies this BatchNorm and writes the K row
+                    left_ = FuseLast{};
+                    left_.mode = 1; left_.act = l.d.activation; left_.x = cur; left_.gamma = params_.p + l.p_off; left_.beta = params_.p + l.p_off + cc;
+                    left_.bn = l.bn;
                 } else {
                     if (cc == 64) LAUNCH(k_bn_apply64, grid_for(l.out_len / 4), 256, s, cur, dst, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn, l.d.activation, l.rows);
                     else LAUNCH(k_bn_apply, grid_for(l.out_len), 256, s, cur, dst, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn, l.d.activation, l.rows, cc);
@@ -754,6 +760,11 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     LAUNCH(k_bn_bwd_dx_to_image, grid_for(l.in_len / 4), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, geom_,
                            l.gin, L_[i - 1].gimg, dth, with_off(dth, cc));
                     gimg_ready = true;
+                } else if (leave_last_ && i == 0 && cc == 64 && l.bn.deferred == 1) {
+                    // adjoint solve, stages 1-5: the stage combination that follows computes this dx and writes the a block of the K row
+                    left_ = FuseLast{};
+                    left_.mode = 2; left_.act = l.d.activation; left_.g = g; left_.gscale = gscale; left_.y = y; left_.gamma = params_.p + l.p_off;
+                    left_.beta = params_.p + l.p_off + cc; left_.bn = l.bn; left_.a4 = off_a_ / 4; left_.dgamma_off = off_theta_ + l.g_off;
                 } else {
                     if (cc == 64)
                         LAUNCH(k_bn_bwd_dx64, grid_for(l.in_len / 4), 256, s, g, gscale, y, x, params_.p + l.p_off, l.bn, l.d.activation, l.rows, dx, dth,
@@ -922,9 +933,37 @@ void Engine::enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverP
     const long long n4_main = split ? (2 * nz_pad_) / 4 : n4;
     const int grid = bf0.enabled ? grid_red(n4_main) : grid_for(n4_main);
     BnFuse nobf{};
+    // Stages 1-5 of a 64-channel BatchNorm-first / BatchNorm-last block on one GPU: the evaluation leaves its last elementwise kernel
+    // to the combination of the next stage (k_stage_combine_last).  The adjoint form needs the split layout (z | a combined here, theta late).
+    const bool can_leave = combine_fusion_ && bf0.enabled && bf0.sc.deferred == 1 && !comm_dev_ && nz_ % 64 == 0 && off_a_ % 4 == 0 &&
+                           L_.size() >= 2 && L_.back().d.kind == N4J_LAYER_BATCHNORM && L_.back().c_out == 64 &&
+                           (!aug || (split && L_[1].d.kind == N4J_LAYER_CONV3X3 && L_[1].tc && !(cfg_.flags & N4J_FLAG_NO_PROLOGUE_FUSION) &&
+                                     (L_[0].d.activation == N4J_ACT_RELU || L_[0].d.activation == N4J_ACT_IDENTITY)));   // the operand prologue of that conv takes the re-arm
+    const int grid_last = grid_red(bf0.nz4);
+    left_ = FuseLast{};
     for (int st = 1; st <= 6; ++st) {
         set_bn_slot(bn_slot_ ^ 1); eval_begun_ = true;  // the combination produces the first BatchNorm's statistics of this stage's evaluation
         const BnFuse bf = bn_fuse();
+        if (left_.mode == 1) {
+            switch (st) {
+                case 2: launch_k(k_stage_combine_last<2, 1>, dim3(grid_last), dim3(256), 0, s, true, ctrl_, Y_, K_, n_alloc_, bf, left_); break;
+                case 3: launch_k(k_stage_combine_last<3, 1>, dim3(grid_last), dim3(256), 0, s, true, ctrl_, Y_, K_, n_alloc_, bf, left_); break;
+                case 4: launch_k(k_stage_combine_last<4, 1>, dim3(grid_last), dim3(256), 0, s, true, ctrl_, Y_, K_, n_alloc_, bf, left_); break;
+                case 5: launch_k(k_stage_combine_last<5, 1>, dim3(grid_last), dim3(256), 0, s, true, ctrl_, Y_, K_, n_alloc_, bf, left_); break;
+                case 6: launch_k(k_stage_combine_last<6, 1>, dim3(grid_last), dim3(256), 0, s, true, ctrl_, Y_, K_, n_alloc_, bf, left_); break;
+                default: throw Error{N4J_ERR_ILLEGAL_STATE, "stage 1 has no evaluation in front of it"};
+            }
+        } else if (left_.mode == 2) {
+            switch (st) {
+                case 2: launch_k(k_stage_combine_last<2, 2>, dim3(grid_last), dim3(256), 0, s, true, ctrl_, Y_, K_, n_alloc_, bf, left_); break;
+                case 3: launch_k(k_stage_combine_last<3, 2>, dim3(grid_last), dim3(256), 0, s, true, ctrl_, Y_, K_, n_alloc_, bf, left_); break;
+                case 4: launch_k(k_stage_combine_last<4, 2>, dim3(grid_last), dim3(256), 0, s, true, ctrl_, Y_, K_, n_alloc_, bf, left_); break;
+                case 5: launch_k(k_stage_combine_last<5, 2>, dim3(grid_last), dim3(256), 0, s, true, ctrl_, Y_, K_, n_alloc_, bf, left_); break;
+                case 6: launch_k(k_stage_combine_last<6, 2>, dim3(grid_last), dim3(256), 0, s, true, ctrl_, Y_, K_, n_alloc_, bf, left_); break;
+                default: throw Error{N4J_ERR_ILLEGAL_STATE, "stage 1 has no evaluation in front of it"};
+            }
+            prearm_next_ = true;     // that kernel still read the set its block 0 would have re-armed
+        } else
         switch (st) {
             case 1: launch_combine<1>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
             case 2: launch_combine<2>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
@@ -934,13 +973,18 @@ void Engine::enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverP
             case 6: launch_combine<6>(s, grid, ctrl_, Y_, K_, n_alloc_, 0, n4_main, bf); break;
         }
         ++launches_;
+        left_ = FuseLast{};
+        leave_last_ = can_leave && st < 6;
         // quirk A.3: State.step stores the FULL step in timeOffset, so every stage is evaluated at t + h
         // (FirstOrderEquationWithState.java:45,82); N4J_FLAG_EXACT_STAGE_TIMES uses the tableau's c_s instead
         static const double kC[6] = {1.0 / 5.0, 3.0 / 10.0, 4.0 / 5.0, 8.0 / 9.0, 1.0, 1.0};
         tspec_ = (cfg_.flags & N4J_FLAG_EXACT_STAGE_TIMES) ? TimeSpec{2, (float)kC[st - 1], 0.f} : TimeSpec{1, 0.f, 0.f};
         if (aug) enqueue_rhs_aug(s, ywork, Ref{K_, &ctrl_->krow[st], n_alloc_, 0, 0}, bf.enabled != 0, st & 1, split, st == 6);
         else enqueue_rhs_fwd(s, ywork, Ref{K_, &ctrl_->krow[st], n_alloc_, 0, 0}, false, bf.enabled != 0);
+        leave_last_ = false;
+        if (prearm_next_) throw Error{N4J_ERR_ILLEGAL_STATE, "no operand prologue took the statistics re-arm"};
     }
+    if (left_.mode) throw Error{N4J_ERR_ILLEGAL_STATE, "stage 6 left work behind"};
     if (split) {
         join_side(s);
         launch_combine<6>(s, grid_for(n4 - n4_main), ctrl_, Y_, K_, n_alloc_, n4_main, n4, nobf);   // theta | a_t block of y1

@@ -115,6 +115,12 @@ private:
     bool side_busy_ = false;
     bool side_capable_ = false;
     size_t wgrad_smem_ = 0;
+    // k_stage_combine_last: the evaluation of stages 1-5 leaves its last elementwise kernel (forward: the last BatchNorm's apply,
+    // adjoint: the first BatchNorm's backward dx) to the stage combination that follows
+    bool leave_last_ = false;        // request to the evaluation being enqueued
+    FuseLast left_{};                // what it left (mode 0: nothing)
+    bool prearm_next_ = false;       // the next PRO 1 convolution re-arms the first BatchNorm's statistics set (see ConvTcArgs::prearm)
+    bool combine_fusion_ = getenv("N4J_NO_COMBINE_FUSION") == nullptr;
     bool fuse_last_bn_ok_ = false;   // set while enqueueing the forward half of an augmented evaluation
     bool fwd_left_last_bn_ = false;  // ... and the forward half left the last BatchNorm apply to the backward statistics kernel
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;

@@ -133,6 +133,145 @@ __global__ void __launch_bounds__(256) k_stage_combine(const Ctrl* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Stage combination that also FINISHES the evaluation in front of it (64-channel NHWC blocks, deferred statistics): the last
+// elementwise kernel of that evaluation only feeds this pass, so it runs inside it and the K row is written from here.
+//   MODE 1 (forward solves): K[S-1].z = act(BatchNorm_last(x))                      (was k_bn_apply64)
+//   MODE 2 (adjoint solves): K[S-1].a = BatchNorm_first backward dx                 (was k_bn_bwd_dx64; K[S-1].z is already there)
+// The arithmetic is the unfused kernels' expression for expression (the K value is used from the register instead of being
+// re-loaded), so results are bit-identical.  MODE 2 reads the BatchNorm input x from the z block of yWorking, which this very
+// pass overwrites: one thread owns float4 i of the z block AND of the a block, and reads x before it writes.
+// ---------------------------------------------------------------------------------------------------
+struct FuseLast {
+    int mode;                 // 0: nothing left over
+    int act;
+    Ref x;                    // MODE 1: input of the last BatchNorm
+    Ref g, y;                 // MODE 2: gradient w.r.t. the first BatchNorm's output, that output (compact)
+    float gscale;
+    const float* gamma;
+    const float* beta;
+    BnScratch bn;             // statistics sets of the evaluation being finished
+    long long a4;             // MODE 2: float4 offset of the a block inside a state vector
+    long long dgamma_off;     // MODE 2: element offset of dgamma inside the K row (dbeta follows 64 floats later)
+};
+
+template <int S, int MODE>
+__global__ void __launch_bounds__(256) k_stage_combine_last(const Ctrl* __restrict__ c, float* __restrict__ Ybase, float* __restrict__ Kbase,
+                                                             long long stride, BnFuse bf, FuseLast fl) {
+    static_assert(S >= 2, "the first stage reads the FSAL row");
+    pdl_begin();
+    const float h = c->h;
+    const int yc = c->y_cur;
+    const float* __restrict__ y = Ybase + (long long)yc * stride;
+    float* __restrict__ yw = Ybase + (long long)(yc ^ 1) * stride;
+    float coef[S];
+    const float* __restrict__ kr[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+        coef[j] = __fmul_rn(c_A[S - 1][j], h);
+        kr[j] = Kbase + (long long)c->krow[j] * stride;
+    }
+    float* __restrict__ klast = Kbase + (long long)c->krow[S - 1] * stride;
+    const int c0 = (threadIdx.x & 15) * 4;      // grid stride is a multiple of 16 float4: a thread stays on one 4-channel chunk
+    __shared__ float s_st[4][64];               // mean, invstd, mean(dy), mean(dy*xhat) of the BatchNorm being finished
+    if (threadIdx.x < 64) {
+        const int ch = threadIdx.x;
+        bn_fwd_final(fl.bn, ch, s_st[0][ch], s_st[1][ch]);
+        if (MODE == 2) {
+            float dg, db;
+            bn_bwd_final(fl.bn, ch, s_st[2][ch], s_st[3][ch], dg, db);
+            if (blockIdx.x == 0) { klast[fl.dgamma_off + ch] = dg; klast[fl.dgamma_off + 64 + ch] = db; }
+        }
+    }
+    __syncthreads();
+    float mean[4], inv[4], ga[4], be[4], mdy[4], mdyxh[4], kk[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        mean[k] = s_st[0][c0 + k]; inv[k] = s_st[1][c0 + k];
+        ga[k] = fl.gamma[c0 + k]; be[k] = MODE == 1 ? fl.beta[c0 + k] : 0.f;
+        mdy[k] = MODE == 2 ? s_st[2][c0 + k] : 0.f; mdyxh[k] = MODE == 2 ? s_st[3][c0 + k] : 0.f;
+        kk[k] = __fmul_rn(ga[k], inv[k]);
+    }
+    const float* __restrict__ xin = MODE == 1 ? resolve(fl.x) : yw;
+    const float* __restrict__ gin = MODE == 2 ? resolve(fl.g) : nullptr;
+    const float* __restrict__ yin = MODE == 2 ? resolve(fl.y) : nullptr;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < bf.nz4; i += step) {
+        const float4 xv = ld4(xin, i);
+        const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+        float kl[4];
+        if (MODE == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) kl[k] = act_fwd(fl.act, __fadd_rn(__fmul_rn(ga[k], __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k])), be[k]));
+            st4(klast, i, make_float4(kl[0], kl[1], kl[2], kl[3]));
+        } else {
+            const float4 gv = ld4(gin, i), yv = ld4(yin, i);
+            const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float dy = act_bwd(fl.act, yy[k], __fmul_rn(fl.gscale, gg[k]));
+                const float xh = __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k]);
+                kl[k] = __fmul_rn(kk[k], __fsub_rn(__fsub_rn(dy, mdy[k]), __fmul_rn(xh, mdyxh[k])));
+            }
+            st4(klast, fl.a4 + i, make_float4(kl[0], kl[1], kl[2], kl[3]));
+        }
+        // z block
+        const float4 yv0 = ld4(y, i);
+        float4 k0 = ld4(kr[0], i);
+        float4 acc = make_float4(__fmul_rn(coef[0], k0.x), __fmul_rn(coef[0], k0.y), __fmul_rn(coef[0], k0.z), __fmul_rn(coef[0], k0.w));
+#pragma unroll
+        for (int j = 1; j < S; ++j) {
+            if (S == 6 && j == 1) continue;   // a_62 == 0
+            const float4 kj = (MODE == 1 && j == S - 1) ? make_float4(kl[0], kl[1], kl[2], kl[3]) : ld4(kr[j], i);
+            acc.x = __fmaf_rn(coef[j], kj.x, acc.x);
+            acc.y = __fmaf_rn(coef[j], kj.y, acc.y);
+            acc.z = __fmaf_rn(coef[j], kj.z, acc.z);
+            acc.w = __fmaf_rn(coef[j], kj.w, acc.w);
+        }
+        const float4 o = make_float4(__fadd_rn(yv0.x, acc.x), __fadd_rn(yv0.y, acc.y), __fadd_rn(yv0.z, acc.z), __fadd_rn(yv0.w, acc.w));
+        st4(yw, i, o);
+        s1[0] += (double)o.x; s2[0] += (double)o.x * (double)o.x;
+        s1[1] += (double)o.y; s2[1] += (double)o.y * (double)o.y;
+        s1[2] += (double)o.z; s2[2] += (double)o.z * (double)o.z;
+        s1[3] += (double)o.w; s2[3] += (double)o.w * (double)o.w;
+        if (MODE == 2) {      // a block
+            const long long ia = fl.a4 + i;
+            const float4 ya = ld4(y, ia);
+            k0 = ld4(kr[0], ia);
+            acc = make_float4(__fmul_rn(coef[0], k0.x), __fmul_rn(coef[0], k0.y), __fmul_rn(coef[0], k0.z), __fmul_rn(coef[0], k0.w));
+#pragma unroll
+            for (int j = 1; j < S; ++j) {
+                if (S == 6 && j == 1) continue;
+                const float4 kj = j == S - 1 ? make_float4(kl[0], kl[1], kl[2], kl[3]) : ld4(kr[j], ia);
+                acc.x = __fmaf_rn(coef[j], kj.x, acc.x);
+                acc.y = __fmaf_rn(coef[j], kj.y, acc.y);
+                acc.z = __fmaf_rn(coef[j], kj.z, acc.z);
+                acc.w = __fmaf_rn(coef[j], kj.w, acc.w);
+            }
+            st4(yw, ia, make_float4(__fadd_rn(ya.x, acc.x), __fadd_rn(ya.y, acc.y), __fadd_rn(ya.z, acc.z), __fadd_rn(ya.w, acc.w)));
+        }
+    }
+    // statistics of the first BatchNorm for the evaluation that follows: accumulate only (deferred statistics, BnScratch)
+    __shared__ double sm[2][4][256];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sm[0][k][threadIdx.x] = s1[k]; sm[1][k][threadIdx.x] = s2[k]; }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double a = 0, b = 0;
+            for (int r = 0; r < 16; ++r) { a += sm[0][k][r * 16 + threadIdx.x]; b += sm[1][k][r * 16 + threadIdx.x]; }
+            const int ch = threadIdx.x * 4 + k;
+            atomicAdd(bf.sc.accf + ch * ACC_STRIDE, a);
+            atomicAdd(bf.sc.accf + (64 + ch) * ACC_STRIDE, b);
+        }
+    }
+    // MODE 2 still reads the set behind accf_other (the first BatchNorm's sums of the evaluation being finished) in every block:
+    // the operand prologue of the next convolution re-arms it instead (ConvTcArgs::prearm)
+    if (MODE == 1) bn_rearm(bf.sc.accf_other, threadIdx.x);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Scalar controller pieces (run by one thread)
 // ---------------------------------------------------------------------------------------------------
 // AdaptiveRungeKuttaStepPolicy.step :142-153
