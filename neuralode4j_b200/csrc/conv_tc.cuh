@@ -581,12 +581,12 @@ __global__ void __launch_bounds__(256) k_compact_to_image(Ref xin, ConvGeom g, f
 // (576 > 512 columns) and a 147 KB epilogue per CTA, which costs more than it saves at this size; the kernel runs on a side
 // branch of the graph, concurrently with the dgrad/BatchNorm chain.
 // ---------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1) k_conv_wgrad64(Ref xin, Ref gin, ConvGeom g, float* __restrict__ part, int images_per_cta) {
+__global__ void __launch_bounds__(256, 1) k_conv_wgrad64(Ref xin, Ref gin, ConvGeom g, float* __restrict__ part, int images_per_cta, int nbuf_avail) {
     pdl_begin();
     extern __shared__ __align__(16) float smw[];
     const int hw = g.H * g.W, pp = g.PH * g.PW;
-    float* Xs = smw;                 // [PH*PW][64], zero border
-    float* Gs = smw + pp * 64;       // [H*W][64]
+    // two staging buffers (when they fit): image n+1 arrives by cp.async while image n is being contracted
+    const int buf_floats = (pp + hw) * 64;
     const int tci = threadIdx.x >> 4, tco = threadIdx.x & 15;
     float acc[9][4][4];
 #pragma unroll
@@ -595,34 +595,56 @@ __global__ void __launch_bounds__(256, 1) k_conv_wgrad64(Ref xin, Ref gin, ConvG
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.f;
-    for (int i = threadIdx.x; i < pp * 16; i += 256) reinterpret_cast<float4*>(Xs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int img = blockIdx.x * images_per_cta; img < min(g.B, (blockIdx.x + 1) * images_per_cta); ++img) {
-        const float* __restrict__ x = resolve(xin) + (long long)img * hw * 64;
-        const float* __restrict__ gr = resolve(gin) + (long long)img * hw * 64;
-        __syncthreads();             // previous image fully consumed (and the border zeroing visible)
+    const int img0 = blockIdx.x * images_per_cta, img1 = min(g.B, (blockIdx.x + 1) * images_per_cta);
+    const int nbuf = (img1 - img0 > 1 && nbuf_avail == 2) ? 2 : 1;
+    for (int i = threadIdx.x; i < pp * 16; i += 256) {      // zero borders (the interiors are overwritten by every image)
+        reinterpret_cast<float4*>(smw)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nbuf == 2) reinterpret_cast<float4*>(smw + buf_floats)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const float* __restrict__ xbase = resolve(xin);
+    const float* __restrict__ gbase = resolve(gin);
+    auto stage = [&](int img, int b) {
+        float* Xs = smw + b * buf_floats;           // [PH*PW][64], zero border
+        float* Gs = Xs + pp * 64;                   // [H*W][64]
+        const float4* x = reinterpret_cast<const float4*>(xbase + (long long)img * hw * 64);
+        const float4* gr = reinterpret_cast<const float4*>(gbase + (long long)img * hw * 64);
         for (int i = threadIdx.x; i < hw * 16; i += 256) {
             const int p = i >> 4, c4 = i & 15;
             const int h = p / g.W, w = p - h * g.W;
-            reinterpret_cast<float4*>(Xs)[((h + 1) * g.PW + (w + 1)) * 16 + c4] = reinterpret_cast<const float4*>(x)[i];
-            reinterpret_cast<float4*>(Gs)[i] = reinterpret_cast<const float4*>(gr)[i];
+            const uint32_t dx = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<float4*>(Xs) + ((h + 1) * g.PW + (w + 1)) * 16 + c4);
+            const uint32_t dg = (uint32_t)__cvta_generic_to_shared(reinterpret_cast<float4*>(Gs) + i);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dx), "l"(x + i) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dg), "l"(gr + i) : "memory");
         }
-        __syncthreads();
-        for (int p = 0; p < hw; ++p) {
-            const int h = p / g.W, w = p - h * g.W;
-            const int center = (h + 1) * g.PW + (w + 1);
-            const float4 gv = reinterpret_cast<const float4*>(Gs)[p * 16 + tco];
-            const float gj[4] = {gv.x, gv.y, gv.z, gv.w};
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (img0 < img1) stage(img0, 0);
+    for (int img = img0; img < img1; ++img) {
+        const int b = nbuf == 2 ? (img - img0) & 1 : 0;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();             // image `img` is in buffer b for everybody; buffer b^1 (image img-1) is fully consumed
+        if (nbuf == 2 && img + 1 < img1) stage(img + 1, b ^ 1);
+        const float* Xs = smw + b * buf_floats;
+        const float* Gs = Xs + pp * 64;
+        for (int h = 0; h < g.H; ++h) {
+            for (int w = 0; w < g.W; ++w) {
+                const int center = (h + 1) * g.PW + (w + 1);
+                const float4 gv = reinterpret_cast<const float4*>(Gs)[(h * g.W + w) * 16 + tco];
+                const float gj[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-                const int q = center + (t / 3 - 1) * g.PW + (t % 3 - 1);
-                const float4 xv = reinterpret_cast<const float4*>(Xs)[q * 16 + tci];
-                const float xi[4] = {xv.x, xv.y, xv.z, xv.w};
+                for (int t = 0; t < 9; ++t) {
+                    const int q = center + (t / 3 - 1) * g.PW + (t % 3 - 1);
+                    const float4 xv = reinterpret_cast<const float4*>(Xs)[q * 16 + tci];
+                    const float xi[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[t][i][j] = fmaf(xi[i], gj[j], acc[t][i][j]);
+                        for (int j = 0; j < 4; ++j) acc[t][i][j] = fmaf(xi[i], gj[j], acc[t][i][j]);
+                }
             }
         }
+        if (nbuf == 1 && img + 1 < img1) { __syncthreads(); stage(img + 1, 0); }
     }
     float* __restrict__ out = part + (long long)blockIdx.x * 9 * 4096;
 #pragma unroll
@@ -631,7 +653,7 @@ __global__ void __launch_bounds__(256, 1) k_conv_wgrad64(Ref xin, Ref gin, ConvG
         for (int i = 0; i < 4; ++i)
             reinterpret_cast<float4*>(out + (t * 64 + tci * 4 + i) * 64)[tco] = make_float4(acc[t][i][0], acc[t][i][1], acc[t][i][2], acc[t][i][3]);
 }
-inline size_t conv_wgrad_smem_bytes(const ConvGeom& g) { return sizeof(float) * 64 * ((size_t)g.PH * g.PW + (size_t)g.H * g.W); }
+inline size_t conv_wgrad_smem_bytes(const ConvGeom& g) { return sizeof(float) * 64 * ((size_t)g.PH * g.PW + (size_t)g.H * g.W); }   // one staging buffer
 
 // dst[i] = sum_b part[b][i]  (fixed order), i over 9*64*64.  Block = 64 float4 columns x 4 partial groups.
 // cm != nullptr (sharded path): the sum over the ranks rides on the same launch (LL exchange of the finished float4).

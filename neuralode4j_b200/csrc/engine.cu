@@ -244,6 +244,8 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
                 set_conv_smem_all(conv_smem_);
                 side_capable_ = true;
                 wgrad_smem_ = conv_wgrad_smem_bytes(geom_);
+                wgrad_nbuf_ = 2 * wgrad_smem_ <= 200 * 1024 ? 2 : 1;      // second staging buffer when it fits
+                wgrad_smem_ *= wgrad_nbuf_;
                 N4J_CUDA(cudaFuncSetAttribute(k_conv_wgrad64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_));
                 ensure(wpart_, (long long)B_ * 9 * 4096);
             }
@@ -859,7 +861,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     // the join, so that launch takes one image per CTA (half the latency)
                     const bool wide = last_of_trial && i == first_conv_;
                     const int ipc = wide ? 1 : (int)((B_ + 63) / 64), wg_ctas = (int)((B_ + ipc - 1) / ipc);
-                    k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, side_>>>(x, d, geom_, wpart_.p, ipc);
+                    k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, side_>>>(x, d, geom_, wpart_.p, ipc, wgrad_nbuf_);
                     ++launches_;
                     // sharded path: the sum over the ranks rides on the reduction (LL exchange of every finished float4)
                     const bool ll = comm_dev_ && vec_allreduce_ll_ && l.g_len <= comm_xll_cap_ && !skip_vec_allreduce_;
@@ -1559,7 +1561,7 @@ void Engine::bench_piece(int what, int iters, float* us) {
                     launch_gemm<G_CONV_DGRAD>(stream_, q, launches_, exact_);
                 } else if (l.tc) {
                     const int ipc = (int)((B_ + 63) / 64), wg_ctas = (int)((B_ + ipc - 1) / ipc);
-                    k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, stream_>>>(fixed_ref(gb_[0].p), fixed_ref(gb_[1].p), geom_, wpart_.p, ipc);
+                    k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, stream_>>>(fixed_ref(gb_[0].p), fixed_ref(gb_[1].p), geom_, wpart_.p, ipc, wgrad_nbuf_);
                     ++launches_;
                     LAUNCH(k_wgrad_reduce, 144, 256, stream_, wpart_.p, fixed_ref(theta_tmp_.p), wg_ctas, (CommDev*)nullptr);
                 } else {

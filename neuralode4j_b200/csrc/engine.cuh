@@ -115,6 +115,7 @@ private:
     bool side_busy_ = false;
     bool side_capable_ = false;
     size_t wgrad_smem_ = 0;
+    int wgrad_nbuf_ = 1;
     // k_stage_combine_last: the evaluation of stages 1-5 leaves its last elementwise kernel (forward: the last BatchNorm's apply,
     // adjoint: the first BatchNorm's backward dx) to the stage combination that follows
     bool leave_last_ = false;        // request to the evaluation being enqueued
