@@ -5,9 +5,9 @@ Only the hot path of the reference lives here: DormandPrince54 adaptive integrat
 This package is the host-side mirror of the reference's configuration/vertex interface for that path.
 """
 from .conf import (ActivationLayer, BatchNormalization, Convolution2D, DenseLayer, DormandPrince54Solver, FixedStep,
-                   InputStep, Layer, Mask, MergeVertex, ShapeMatchVertex, SolverConfig, StepCounter, StepListener)
+                   InputStep, InputType, Layer, Mask, MergeVertex, ShapeMatchVertex, SolverConfig, StepCounter, StepListener)
 from .vertex import OdeVertex, OdeVertexImpl
 from . import _lib
 
 __all__ = ["ActivationLayer", "BatchNormalization", "Convolution2D", "DenseLayer", "DormandPrince54Solver", "FixedStep",
-           "InputStep", "Layer", "Mask", "MergeVertex", "ShapeMatchVertex", "SolverConfig", "StepCounter", "StepListener", "OdeVertex", "OdeVertexImpl"]
+           "InputStep", "InputType", "Layer", "Mask", "MergeVertex", "ShapeMatchVertex", "SolverConfig", "StepCounter", "StepListener", "OdeVertex", "OdeVertexImpl"]

@@ -24,6 +24,56 @@ from . import _lib
 
 
 # ----------------------------------------------------------------------------------------------------------
+# activation types (DL4J's InputType, the part OdeVertex.getOutputType needs)
+# ----------------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class InputType:
+    """org.deeplearning4j.nn.conf.inputs.InputType restricted to what the ODE block's output-type inference touches
+    (ode/vertex/conf/helper/forward/OutputTypeFromConfig.java:27-35, OutputTypeAddTimeAsDimension.java:47-53).
+    ``shape`` is per example: FF (size,), RNN (size, timeSeriesLength), CNN (channels, height, width),
+    CNN3D in NDHWC (depth, height, width, channels)."""
+    kind: str
+    shape: tuple
+
+    @staticmethod
+    def feedForward(size): return InputType("FF", (int(size),))
+    @staticmethod
+    def recurrent(size, timeSeriesLength): return InputType("RNN", (int(size), int(timeSeriesLength)))
+    @staticmethod
+    def convolutional(height, width, channels): return InputType("CNN", (int(channels), int(height), int(width)))
+    @staticmethod
+    def convolutional3D(depth, height, width, channels): return InputType("CNN3D", (int(depth), int(height), int(width), int(channels)))
+    @staticmethod
+    def inferInputType(array): return InputType.feedForward(np.asarray(array).size)     # a time vector [1,T] is FF(T)
+
+    def arrayElementsPerExample(self) -> int:
+        return int(np.prod(self.shape))
+
+
+def _output_type_from_config(vertex, inputs):
+    """OutputTypeFromConfig.java:27-35: the inner graph's single output must have the input's shape."""
+    if len(inputs) != 1:
+        raise ValueError("Can only support one single output!")
+    out = vertex.activationType(inputs[0])
+    if out != inputs[0]:
+        raise ValueError(f"input shape must match output shape! Got input {inputs[0]} and output: {out}!")
+    return out
+
+
+def _add_time_dim(out: InputType, time: InputType) -> InputType:
+    """OutputTypeAddTimeAsDimension.java:25-53: FF -> recurrent(size, T); CNN -> convolutional3D(NDHWC, T, h, w, c)."""
+    if time.kind != "FF":
+        raise ValueError("Time must be 1D!")
+    t = time.arrayElementsPerExample()
+    if out.kind == "FF":
+        return InputType.recurrent(out.arrayElementsPerExample(), t)
+    if out.kind == "CNN":
+        c, h, w = out.shape
+        return InputType.convolutional3D(t, h, w, c)
+    raise ValueError("Input type not supported with time as input!")
+
+
+# ----------------------------------------------------------------------------------------------------------
 # solver configuration
 # ----------------------------------------------------------------------------------------------------------
 class SolverConfig:
@@ -214,6 +264,15 @@ class FixedStep:
     time_input_index = None
     needTimeGradient = False
 
+    def nrofTimeInputs(self) -> int:          # conf/helper/forward/FixedStep.java:45-47
+        return 0
+
+    def getOutputType(self, vertex, *vertexInputs):
+        """conf/helper/forward/FixedStep.java:55-67: two time points keep the input's type, more add the time dimension."""
+        if self.time.size == 2:
+            return _output_type_from_config(vertex, vertexInputs)
+        return _add_time_dim(_output_type_from_config(vertex, vertexInputs), InputType.inferInputType(self.time))
+
     def clone(self):
         return FixedStep(self.solver.clone(), self.time, self.interpolateForwardIfMultiStep)
 
@@ -245,6 +304,18 @@ class InputStep:
 
     def forward(self): return self
     def backward(self): return self
+
+    def nrofTimeInputs(self) -> int:          # conf/helper/forward/InputStep.java: one of the vertex inputs is the time
+        return 1
+
+    def getOutputType(self, vertex, *vertexInputs):
+        """conf/helper/forward/InputStep.java:50-66."""
+        if len(vertexInputs) <= self.time_input_index:
+            raise ValueError("Time input index was not part of input types!!")
+        time = vertexInputs[self.time_input_index]
+        rest = [v for i, v in enumerate(vertexInputs) if i != self.time_input_index]
+        out = _output_type_from_config(vertex, rest)
+        return _add_time_dim(out, time) if time.arrayElementsPerExample() > 2 else out
 
     def clone(self):
         return InputStep(self.solver.clone(), self.time_input_index, self.interpolateForwardIfMultiStep, self.needTimeGradient)

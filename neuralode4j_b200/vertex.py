@@ -144,6 +144,29 @@ class OdeVertex:
                 c += l.nOut
         return n
 
+    def activationType(self, inp):
+        """Type of the inner graph's output for one input (ComputationGraphConfiguration.getLayerActivationTypes restricted to the
+        chain of layers the native set allows): 3x3 Same stride-1 convolutions keep height and width, the time merge adds features."""
+        kind, shape = inp.kind, list(inp.shape)
+        if kind not in ("FF", "CNN"):
+            raise ValueError(f"input type {inp} is not supported inside a native OdeVertex")
+        for l in self.layers:
+            if l.kind == _lib.LAYER_DENSE:
+                if kind != "FF":
+                    raise ValueError("DenseLayer inside an OdeVertex needs feed-forward activations")
+                shape[0] = l.nOut
+            elif l.kind == _lib.LAYER_CONV3X3:
+                if kind != "CNN":
+                    raise ValueError("Convolution2D inside an OdeVertex needs convolutional activations")
+                shape[0] = l.nOut
+            elif l.kind == _lib.LAYER_TIME_CONCAT:
+                shape[0] += l.nOut
+        return type(inp)(kind, tuple(shape))
+
+    def getOutputType(self, layerIndex, *vertexInputs):
+        """OdeVertex.getOutputType (conf/OdeVertex.java:151-154): delegated to the forward helper conf."""
+        return self.odeForwardConf.getOutputType(self, *vertexInputs)
+
     def graph_spec(self) -> List[dict]:
         return [l.spec() for l in self.layers]
 

@@ -232,6 +232,23 @@ def test_mnist_block_prologue_fusion_matches_separate_kernels():
     assert _rel_l2(b["grad"], a["grad"]) < 1e-3
 
 
+@pytest.mark.parametrize("batch,flags", [(16, 0), (128, 0), (16, EXACT)])
+def test_stage_combine_fusion_is_bit_identical(batch, flags, monkeypatch):
+    """k_stage_combine_last (the stage combination finishes the evaluation in front of it: last BatchNorm apply in forward solves,
+    first BatchNorm's backward dx in adjoint solves) against the separate kernels (N4J_NO_COMBINE_FUSION, read when the engine is
+    created): same expressions in the same order on the same values, so everything is bitwise equal — and fewer kernels launch."""
+    w = W.mnist_block(batch=batch, channels=64)
+    monkeypatch.delenv("N4J_NO_COMBINE_FUSION", raising=False)
+    a = H.run_cuda(w, flags=flags)
+    monkeypatch.setenv("N4J_NO_COMBINE_FUSION", "1")
+    b = H.run_cuda(w, flags=flags)
+    assert a["fwd_stats"] == b["fwd_stats"] and a["bwd_stats"] == b["bwd_stats"]
+    for k in ("out", "dy0", "grad"):
+        assert np.array_equal(a[k], b[k]), k
+    assert a["fwd_launches"] < b["fwd_launches"]
+    assert a["bwd_launches"] < b["bwd_launches"] or flags == EXACT      # parity mode keeps the SIMT convolutions: no adjoint fusion there
+
+
 @pytest.mark.parametrize("batch,hw", [(5, 5), (3, 14), (16, 9), (33, 4), (2, 20)])
 def test_tensor_conv_block_odd_geometries(batch, hw):
     """The fused tcgen05 conv launches (operand prologue, statistics epilogues, deferred statistics) on geometries that do not

@@ -167,3 +167,33 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert "workload" in line["config"]
+
+
+def test_output_type_inference_mirrors_reference():
+    """OdeVertex.getOutputType (conf/OdeVertex.java:151-154) -> FixedStep / InputStep.getOutputType
+    (conf/helper/forward/FixedStep.java:55-67, InputStep.java:50-66, OutputTypeAddTimeAsDimension.java:25-53, OutputTypeFromConfig.java:27-35)."""
+    from neuralode4j_b200 import (BatchNormalization, Convolution2D, DenseLayer, DormandPrince54Solver, FixedStep, InputStep, InputType,
+                                  OdeVertex, SolverConfig)
+    solver = DormandPrince54Solver(SolverConfig(1e-3, 1e-3, 1e-10, 10))
+    conv = lambda helper: (OdeVertex.Builder(None, "bn", BatchNormalization(6, "relu")).addLayer("c", Convolution2D(6), "bn").odeConf(helper).build())
+    dense = lambda helper: (OdeVertex.Builder(None, "d", DenseLayer(5, 5, "tanh")).odeConf(helper).build())
+    cnn, ff = InputType.convolutional(9, 9, 6), InputType.feedForward(5)
+    # two time points: the input's own type
+    assert conv(FixedStep(solver, [0, 1])).getOutputType(0, cnn) == cnn
+    assert dense(FixedStep(solver, [0, 1])).getOutputType(0, ff) == ff
+    # more: time becomes a dimension — recurrent(size, T) for dense, NDHWC convolutional3D(T, h, w, c) for conv states
+    assert dense(FixedStep(solver, np.linspace(0, 1, 7))).getOutputType(0, ff) == InputType.recurrent(5, 7)
+    assert conv(FixedStep(solver, np.linspace(0, 1, 4))).getOutputType(0, cnn) == InputType.convolutional3D(4, 9, 9, 6)
+    # InputStep: the time is one of the vertex inputs
+    assert dense(InputStep(solver, 1)).getOutputType(0, ff, InputType.feedForward(2)) == ff
+    assert dense(InputStep(solver, 1)).getOutputType(0, ff, InputType.feedForward(10)) == InputType.recurrent(5, 10)
+    assert conv(InputStep(solver, 0)).getOutputType(0, InputType.feedForward(3), cnn) == InputType.convolutional3D(3, 9, 9, 6)
+    with pytest.raises(ValueError, match="Time input index"):
+        dense(InputStep(solver, 1)).getOutputType(0, ff)
+    with pytest.raises(ValueError, match="Time must be 1D"):
+        dense(InputStep(solver, 1)).getOutputType(0, ff, InputType.recurrent(3, 4))
+    # the block must map its input type onto itself (OutputTypeFromConfig.java:27-35)
+    widening = OdeVertex.Builder(None, "d", DenseLayer(7, 5, "tanh")).odeConf(FixedStep(solver, [0, 1])).build()
+    with pytest.raises(ValueError, match="must match output shape"):
+        widening.getOutputType(0, ff)
+    assert FixedStep(solver, [0, 1]).nrofTimeInputs() == 0 and InputStep(solver, 1).nrofTimeInputs() == 1
