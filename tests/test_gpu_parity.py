@@ -460,3 +460,28 @@ def test_errors():
     v.close()
     with pytest.raises(NotImplementedError):
         w.conf.instantiate((2, 2, 2))
+
+
+def test_nan_and_step_guard():
+    """NaN anywhere in the state ends the solve with IllegalStateException("Detected NaN!") like NanWatchSolver.java:22,52; the
+    step guard (absent in the reference, which would loop forever: SURVEY.md section 5) reports N4J_ERR_MAX_STEPS.  The handle
+    stays usable after either."""
+    w = W.golden_linear(1)
+    v = w.conf.instantiate(w.shape)
+    v.setParams(w.params)
+    bad = w.y0.copy()
+    bad[1, 0] = np.nan
+    v.setInputs(bad, w.time.copy())
+    with pytest.raises(RuntimeError, match="NaN"):
+        v.doForward()
+    v.setInputs(w.y0, w.time.copy())
+    good = v.doForward()
+    assert np.abs(good - H.GOLDEN_YS_FWD).max() < 1e-3
+    v.close()
+    g = w.conf.instantiate(w.shape, max_trials=3)
+    g.setParams(w.params)
+    g.setInputs(w.y0, w.time.copy())
+    with pytest.raises(_lib.Node4jError) as e:
+        g.doForward()
+    assert e.value.code == _lib.ERR_MAX_STEPS
+    g.close()
