@@ -95,10 +95,11 @@ inline Ref fixed_ref(float* p, long long off = 0) { return Ref{p, nullptr, 0, of
 // ---------------------------------------------------------------------------------------------------
 // Multi-GPU exchange over NVLink peer memory (one process per GPU, CUDA IPC).  The path's couplings are tiny — the
 // error-norm scalar, 2*C BatchNorm sums, and the parameter-gradient block — so they are exchanged by a ONE-SHOT
-// all-reduce written into the kernels themselves: every rank stores its partial values straight into every peer's
-// mailbox, raises a flag, waits for the peers' flags in its own mailbox and sums the contributions in rank order
-// (bitwise identical totals on all ranks => identical controller decisions).  Two parities alternate; a rank can only
-// be one exchange ahead of its slowest peer, so two buffers are enough.
+// all-reduce written into the kernels themselves: every rank stores its partial values, each tagged with the exchange's
+// sequence number, straight into every peer's mailbox, waits until its own mailbox shows the peers' tags and sums the
+// contributions in rank order (bitwise identical totals on all ranks => identical controller decisions).  Two parities
+// alternate; a rank can only be one exchange ahead of its slowest peer, so two buffers are enough.  Only the long
+// parameter-gradient slots (k_comm_allreduce_vec) still use a flag per rank and pull the data.
 // ---------------------------------------------------------------------------------------------------
 constexpr int COMM_MAX_WORLD = 8;
 constexpr int COMM_SLOT = 256;                                   // doubles per rank per small exchange
