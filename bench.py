@@ -136,6 +136,53 @@ def cpu_step(batch):
     return time.perf_counter() - t0, O.num_threads()
 
 
+def cpu_blas_grade_estimate(fwd_evals, aug_evals, threads):
+    """Context for the port's number, not the reference arm: the same f(z) and augmented RHS (f + vjp w.r.t. z and theta) with
+    PyTorch's CPU operators (oneDNN convolutions) — the class of kernels a BLAS-backed CPU path such as ND4J-native runs — timed per
+    evaluation and multiplied by the step's evaluation counts.  Solver passes, layout copies and the adjoint bookkeeping are NOT
+    included, so this is an upper bound on what such a path reaches.  The oracle accumulates every contraction in double with
+    direct loops (its job is exactness), which is several times slower than this."""
+    import torch
+    import torch.nn.functional as F
+    torch.set_num_threads(max(1, threads))
+    B, C, H = BATCH, 64, 7
+    g0 = torch.Generator().manual_seed(0)
+    z = torch.randn(B, C, H, H, generator=g0, requires_grad=True)
+    a = torch.randn(B, C, H, H, generator=g0)
+    ws = [(torch.rand(C, C, 3, 3, generator=g0) * 2 - 1) / 24.0 for _ in range(2)]
+    for wt in ws:
+        wt.requires_grad_()
+    gam = [torch.ones(C, requires_grad=True) for _ in range(3)]
+    bet = [torch.zeros(C, requires_grad=True) for _ in range(3)]
+
+    def f(x):
+        x = torch.relu(F.batch_norm(x, None, None, gam[0], bet[0], True))
+        x = F.conv2d(x, ws[0], padding=1)
+        x = torch.relu(F.batch_norm(x, None, None, gam[1], bet[1], True))
+        x = F.conv2d(x, ws[1], padding=1)
+        return torch.relu(F.batch_norm(x, None, None, gam[2], bet[2], True))
+
+    def t_fwd():
+        with torch.no_grad():
+            f(z)
+
+    def t_aug():
+        torch.autograd.grad((f(z) * a).sum(), [z] + ws + gam + bet)
+
+    out = []
+    for fn in (t_fwd, t_aug):
+        for _ in range(3):
+            fn()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            fn()
+        out.append((time.perf_counter() - t0) / 10)
+    step_s = fwd_evals * out[0] + aug_evals * out[1]
+    return {"value": BATCH / step_s, "unit": UNIT, "cores": threads, "ms_per_rhs_fwd": out[0] * 1e3, "ms_per_rhs_aug": out[1] * 1e3,
+            "what": f"estimate: {fwd_evals} f(z) + {aug_evals} augmented evaluations of the block with PyTorch CPU operators (oneDNN), "
+                    "per-evaluation time x counts, solver passes excluded; context for the port's number, not the reference arm"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -348,6 +395,10 @@ def run_ours(args):
             tot += dt
         cpu = {"value": reps * BATCH / tot, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{reps} full steps (fwd + adjoint bwd, batch {BATCH}) of the same workload on the CPU oracle after one warm-up: {tot:.1f} s"}
+        try:      # evaluations the solves actually compute: nfe counts one K0 per solve that is not recomputed
+            cpu["blas_grade_estimate"] = cpu_blas_grade_estimate(int(fwd_stats[0]) - 1, int(bwd_stats[0]) - 1, cores)
+        except Exception as e:      # context only: never fail the bench line over it
+            cpu["blas_grade_estimate"] = {"unavailable": repr(e)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
