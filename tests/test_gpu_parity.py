@@ -249,7 +249,7 @@ def test_stage_combine_fusion_is_bit_identical(batch, flags, monkeypatch):
     assert a["bwd_launches"] < b["bwd_launches"] or flags == EXACT      # parity mode keeps the SIMT convolutions: no adjoint fusion there
 
 
-@pytest.mark.parametrize("batch,hw", [(5, 5), (3, 14), (16, 9), (33, 4), (2, 20)])
+@pytest.mark.parametrize("batch,hw", [(5, 5), (3, 14), (16, 9), (33, 4), (2, 20), (70, 14)])      # (70, 14): two images per weight-gradient CTA, one staging buffer
 def test_tensor_conv_block_odd_geometries(batch, hw):
     """The fused tcgen05 conv launches (operand prologue, statistics epilogues, deferred statistics) on geometries that do not
     line up with the 128-pixel tiles: odd batch sizes, feature maps from 4x4 to 14x14 (halo of 16 rows: the prologue's second
