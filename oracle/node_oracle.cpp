@@ -254,29 +254,41 @@ template <class R> struct Net {
                 y[b * nout + o] = act_fwd<R>(l.d.activation, (R)acc);
             }
     }
+    // The three convolution loops keep, for every output element, exactly the order of additions of the plain nested-loop form
+    // ((ci, kh, kw) for the forward, (co, kh, kw) for dgrad, images then pixels for wgrad) — exact fp32 products accumulated in
+    // double — but run the innermost loop over the channel dimension that is NOT reduced, on a transposed copy of the weights /
+    // gradient, so that it vectorises.  Same bits, several times faster.
     void conv_fwd(const LayerPlan& l, const R* x, R* y) const {
         const int64_t B = P.B, Ci = l.d.n_in, Co = l.d.n_out, H = l.H, W = l.W;
         const R* Wt = theta + l.p_off;            // W[Cout,Cin,3,3] c-order, cross-correlation, pad 1
+        std::vector<double> wT((size_t)Ci * 9 * Co);          // [ci][tap][co]
+        for (int64_t co = 0; co < Co; ++co)
+            for (int64_t ci = 0; ci < Ci; ++ci)
+                for (int k = 0; k < 9; ++k) wT[((size_t)ci * 9 + k) * Co + co] = (double)Wt[(co * Ci + ci) * 9 + k];
 #pragma omp parallel for collapse(2)
         for (int64_t b = 0; b < B; ++b)
-            for (int64_t co = 0; co < Co; ++co) {
-                double acc[32 * 32];
-                for (int64_t p = 0; p < H * W; ++p) acc[p] = 0.0;
+            for (int64_t p = 0; p < H * W; ++p) {
+                const int64_t h = p / W, ww = p - h * W;
+                std::vector<double> acc((size_t)Co, 0.0);
+                double* __restrict__ ac = acc.data();
                 for (int64_t ci = 0; ci < Ci; ++ci) {
                     const R* xp = x + (b * Ci + ci) * H * W;
-                    const R* wp = Wt + (co * Ci + ci) * 9;
-                    for (int kh = 0; kh < 3; ++kh)
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const int64_t hh = h + kh - 1;
+                        if (hh < 0 || hh >= H) continue;
                         for (int kw = 0; kw < 3; ++kw) {
-                            const double w = (double)wp[kh * 3 + kw];
-                            const int64_t h0 = std::max<int64_t>(0, 1 - kh), h1 = std::min<int64_t>(H, H + 1 - kh);
-                            const int64_t w0 = std::max<int64_t>(0, 1 - kw), w1 = std::min<int64_t>(W, W + 1 - kw);
-                            for (int64_t h = h0; h < h1; ++h)
-                                for (int64_t ww = w0; ww < w1; ++ww)
-                                    acc[h * W + ww] += w * (double)xp[(h + kh - 1) * W + (ww + kw - 1)];
+                            const int64_t wc = ww + kw - 1;
+                            if (wc < 0 || wc >= W) continue;
+                            const double xv = (double)xp[hh * W + wc];
+                            const double* __restrict__ wr = wT.data() + ((size_t)ci * 9 + kh * 3 + kw) * Co;
+                            for (int64_t co = 0; co < Co; ++co) ac[co] += wr[co] * xv;
                         }
+                    }
                 }
-                R* yp = y + (b * Co + co) * H * W;
-                for (int64_t p = 0; p < H * W; ++p) yp[p] = act_fwd<R>(l.d.activation, (R)probe(acc[p], (b * Co + co) * H * W + p));
+                for (int64_t co = 0; co < Co; ++co) {
+                    const int64_t idx = (b * Co + co) * H * W + p;
+                    y[idx] = act_fwd<R>(l.d.activation, (R)probe(ac[co], idx));
+                }
             }
     }
     void bn_fwd(size_t li, const LayerPlan& l, const R* x, R* y) {
@@ -389,49 +401,63 @@ template <class R> struct Net {
                     const int64_t B = P.B, Ci = l.d.n_in, Co = l.d.n_out, H = l.H, W = l.W;
                     const R* Wt = theta + l.p_off;
                     R* dW = dreal + l.g_off;
-                    // wgrad: dW[co,ci,kh,kw] = sum_{b,h,w} x[b,ci,h+kh-1,w+kw-1] * delta[b,co,h,w]
+                    // wgrad: dW[co,ci,kh,kw] = sum_b ( sum_{h,w} x[b,ci,h+kh-1,w+kw-1] * delta[b,co,h,w] )   (per-image sums, then images)
+                    std::vector<double> gT((size_t)B * H * W * Co);      // delta as [b][pixel][co]
+#pragma omp parallel for
+                    for (int64_t b = 0; b < B; ++b)
+                        for (int64_t co = 0; co < Co; ++co)
+                            for (int64_t q = 0; q < H * W; ++q) gT[((size_t)b * H * W + q) * Co + co] = (double)gin[(b * Co + co) * H * W + q];
 #pragma omp parallel for collapse(2)
-                    for (int64_t co = 0; co < Co; ++co)
-                        for (int64_t ci = 0; ci < Ci; ++ci) {
-                            double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    for (int64_t ci = 0; ci < Ci; ++ci)
+                        for (int k = 0; k < 9; ++k) {
+                            const int kh = k / 3, kw = k % 3;
+                            const int64_t h0 = std::max<int64_t>(0, 1 - kh), h1 = std::min<int64_t>(H, H + 1 - kh);
+                            const int64_t w0 = std::max<int64_t>(0, 1 - kw), w1 = std::min<int64_t>(W, W + 1 - kw);
+                            std::vector<double> accv((size_t)Co, 0.0), av((size_t)Co);
+                            double* __restrict__ acc = accv.data();
+                            double* __restrict__ a = av.data();
                             for (int64_t b = 0; b < B; ++b) {
                                 const R* xp = xin + (b * Ci + ci) * H * W;
-                                const R* gp = gin.data() + (b * Co + co) * H * W;
-                                for (int kh = 0; kh < 3; ++kh)
-                                    for (int kw = 0; kw < 3; ++kw) {
-                                        const int64_t h0 = std::max<int64_t>(0, 1 - kh), h1 = std::min<int64_t>(H, H + 1 - kh);
-                                        const int64_t w0 = std::max<int64_t>(0, 1 - kw), w1 = std::min<int64_t>(W, W + 1 - kw);
-                                        double a = 0;
-                                        for (int64_t h = h0; h < h1; ++h)
-                                            for (int64_t ww = w0; ww < w1; ++ww)
-                                                a += (double)xp[(h + kh - 1) * W + (ww + kw - 1)] * (double)gp[h * W + ww];
-                                        acc[kh * 3 + kw] += a;
+                                for (int64_t co = 0; co < Co; ++co) a[co] = 0.0;
+                                for (int64_t h = h0; h < h1; ++h)
+                                    for (int64_t ww = w0; ww < w1; ++ww) {
+                                        const double xv = (double)xp[(h + kh - 1) * W + (ww + kw - 1)];
+                                        const double* __restrict__ gr = gT.data() + ((size_t)b * H * W + h * W + ww) * Co;
+                                        for (int64_t co = 0; co < Co; ++co) a[co] += xv * gr[co];
                                     }
+                                for (int64_t co = 0; co < Co; ++co) acc[co] += a[co];
                             }
-                            for (int k = 0; k < 9; ++k) dW[(co * Ci + ci) * 9 + k] = (R)probe(acc[k], (co * Ci + ci) * 9 + k);
+                            for (int64_t co = 0; co < Co; ++co) dW[(co * Ci + ci) * 9 + k] = (R)probe(acc[co], (co * Ci + ci) * 9 + k);
                         }
                     // dgrad: dx[b,ci,y,x] = sum_{co,kh,kw} delta[b,co,y-kh+1,x-kw+1] * W[co,ci,kh,kw]
+                    std::vector<double> wT2((size_t)Co * 9 * Ci);        // [co][tap][ci]
+                    for (int64_t co = 0; co < Co; ++co)
+                        for (int64_t ci = 0; ci < Ci; ++ci)
+                            for (int k = 0; k < 9; ++k) wT2[((size_t)co * 9 + k) * Ci + ci] = (double)Wt[(co * Ci + ci) * 9 + k];
 #pragma omp parallel for collapse(2)
                     for (int64_t b = 0; b < B; ++b)
-                        for (int64_t ci = 0; ci < Ci; ++ci) {
-                            double acc[32 * 32];
-                            for (int64_t p = 0; p < H * W; ++p) acc[p] = 0.0;
+                        for (int64_t q = 0; q < H * W; ++q) {
+                            const int64_t qh = q / W, qw = q - qh * W;
+                            std::vector<double> accv((size_t)Ci, 0.0);
+                            double* __restrict__ acc = accv.data();
                             for (int64_t co = 0; co < Co; ++co) {
                                 const R* gp = gin.data() + (b * Co + co) * H * W;
-                                const R* wp = Wt + (co * Ci + ci) * 9;
-                                for (int kh = 0; kh < 3; ++kh)
+                                for (int kh = 0; kh < 3; ++kh) {
+                                    const int64_t h = qh - kh + 1;      // the output pixel (h,w) whose tap (kh,kw) reads input pixel q
+                                    if (h < 0 || h >= H) continue;
                                     for (int kw = 0; kw < 3; ++kw) {
-                                        const double w = (double)wp[kh * 3 + kw];
-                                        // output pixel (h,w) reads input (h+kh-1, w+kw-1)
-                                        const int64_t h0 = std::max<int64_t>(0, 1 - kh), h1 = std::min<int64_t>(H, H + 1 - kh);
-                                        const int64_t w0 = std::max<int64_t>(0, 1 - kw), w1 = std::min<int64_t>(W, W + 1 - kw);
-                                        for (int64_t h = h0; h < h1; ++h)
-                                            for (int64_t ww = w0; ww < w1; ++ww)
-                                                acc[(h + kh - 1) * W + (ww + kw - 1)] += w * (double)gp[h * W + ww];
+                                        const int64_t ww = qw - kw + 1;
+                                        if (ww < 0 || ww >= W) continue;
+                                        const double gv = (double)gp[h * W + ww];
+                                        const double* __restrict__ wr = wT2.data() + ((size_t)co * 9 + kh * 3 + kw) * Ci;
+                                        for (int64_t ci = 0; ci < Ci; ++ci) acc[ci] += wr[ci] * gv;
                                     }
+                                }
                             }
-                            R* op = gout.data() + (b * Ci + ci) * H * W;
-                            for (int64_t p = 0; p < H * W; ++p) op[p] = (R)probe(acc[p], (b * Ci + ci) * H * W + p);
+                            for (int64_t ci = 0; ci < Ci; ++ci) {
+                                const int64_t idx = (b * Ci + ci) * H * W + q;
+                                gout[idx] = (R)probe(acc[ci], idx);
+                            }
                         }
                     break;
                 }
