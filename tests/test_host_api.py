@@ -169,6 +169,22 @@ def test_bench_reference_arm_contract():
     assert "workload" in line["config"]
 
 
+def test_bench_reference_arm_under_torchrun_prints_once():
+    """Launched the way the driver launches N > 1 (torchrun, one process per rank): rank 0 alone runs the CPU arm and prints the
+    line, the other ranks exit 0 without work."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29541",
+           os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["config"]["global_batch"] == 256
+
+
 def test_output_type_inference_mirrors_reference():
     """OdeVertex.getOutputType (conf/OdeVertex.java:151-154) -> FixedStep / InputStep.getOutputType
     (conf/helper/forward/FixedStep.java:55-67, InputStep.java:50-66, OutputTypeAddTimeAsDimension.java:25-53, OutputTypeFromConfig.java:27-35)."""
