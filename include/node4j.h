@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define N4J_ABI_VERSION 1
+#define N4J_ABI_VERSION 2
 
 /* ---- status codes; the Java shim maps them onto the reference's exception types ---------------- */
 enum {
@@ -48,7 +48,7 @@ enum {
                                      (MultiStep.java:57-59) */
     N4J_ERR_CUDA = 4,             /* CUDA runtime failure or no device */
     N4J_ERR_MAX_STEPS = 5,        /* step guard tripped (the reference would loop forever) */
-    N4J_ERR_COMM = 6              /* NCCL failure */
+    N4J_ERR_COMM = 6              /* multi-GPU exchange: a peer did not show up within the spin limit, or the IPC setup failed */
 };
 
 /* ---- inner graph description (what OdeVertex.Builder assembled; chain of DL4J layers) ---------- */
@@ -95,6 +95,7 @@ enum {
     N4J_FLAG_NO_MLP_FUSION = 1u << 10,     /* small dense inner graphs layer by layer instead of one fused launch per evaluation */
     N4J_FLAG_NO_DEFERRED_STATS = 1u << 9,  /* BatchNorm statistics finalised by the last block of the producing kernel (always so on multi-GPU) instead of by the consumers */
     N4J_FLAG_NO_BWD_STATS_FUSION = 1u << 8, /* reduce BatchNorm backward statistics in their own kernel instead of the dgrad conv epilogue */
+    N4J_FLAG_SIMT_WGRAD = 1u << 11,        /* conv weight gradients on the fp32 FMA kernel (k_conv_wgrad64) instead of the tcgen05 one (A/B, cross-check) */
     N4J_FLAG_NO_PDL = 1u << 5,            /* launch kernels without programmatic dependent launch (debug / A-B timing) */
     N4J_FLAG_EXACT_CONTRACTIONS = 1u << 3 /* parity mode: every dense/conv contraction accumulates exact fp32 products in
                                              double and rounds once (order-independent, bit-comparable with the CPU oracle);
@@ -125,6 +126,7 @@ typedef struct n4j_step_rec { /* one entry per TRIAL step, in order */
     float h;  /* step size that was tried */
     float err;
     int32_t accepted;
+    int32_t solve; /* which integrate() call (segment) of this API call the trial belongs to, 0-based: listener begin/done boundaries */
 } n4j_step_rec;
 
 enum { N4J_TIMEGRAD_NONE = 0, /* FixedStep: NoTimeGrad.java:26-28 */

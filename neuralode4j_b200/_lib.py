@@ -15,7 +15,7 @@ N4J_OK, ERR_INVALID_ARGUMENT, ERR_ILLEGAL_STATE, ERR_UNSUPPORTED, ERR_CUDA, ERR_
 
 LAYER_DENSE, LAYER_CONV3X3, LAYER_BATCHNORM, LAYER_ACTIVATION, LAYER_TIME_CONCAT = 1, 2, 3, 4, 5
 ACT = {"identity": 0, "relu": 1, "elu": 2, "tanh": 3}
-FLAG_EXACT_STAGE_TIMES, FLAG_NO_GRAPH, FLAG_FAST_TF32, FLAG_EXACT_CONTRACTIONS, FLAG_NO_TENSOR, FLAG_NO_PDL, FLAG_FORCE_TENSOR, FLAG_NO_PROLOGUE_FUSION, FLAG_NO_BWD_STATS_FUSION, FLAG_NO_DEFERRED_STATS, FLAG_NO_MLP_FUSION = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024
+FLAG_EXACT_STAGE_TIMES, FLAG_NO_GRAPH, FLAG_FAST_TF32, FLAG_EXACT_CONTRACTIONS, FLAG_NO_TENSOR, FLAG_NO_PDL, FLAG_FORCE_TENSOR, FLAG_NO_PROLOGUE_FUSION, FLAG_NO_BWD_STATS_FUSION, FLAG_NO_DEFERRED_STATS, FLAG_NO_MLP_FUSION, FLAG_SIMT_WGRAD = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048
 TIMEGRAD_NONE, TIMEGRAD_ZERO, TIMEGRAD_CALC = 0, 1, 2
 
 EXPORTS = [
@@ -48,7 +48,7 @@ class Stats(C.Structure):
 
 
 class StepRec(C.Structure):
-    _fields_ = [("t", C.c_float), ("h", C.c_float), ("err", C.c_float), ("accepted", C.c_int32)]
+    _fields_ = [("t", C.c_float), ("h", C.c_float), ("err", C.c_float), ("accepted", C.c_int32), ("solve", C.c_int32)]
 
 
 class Node4jError(RuntimeError):
@@ -113,7 +113,7 @@ def load():
     L.node4j_bench_piece.argtypes = [vp, i32, i32, C.POINTER(f32)]
     L.node4j_get_stream.restype = i32
     L.node4j_get_stream.argtypes = [vp, C.POINTER(vp)]
-    if L.node4j_abi_version() != 1:
+    if L.node4j_abi_version() != 2:
         raise RuntimeError("libnode4j_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnode4j_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "solver_kernels.cuh", "layer_kernels.cuh", "tc_common.cuh", "conv_tc.cuh", "gemm_tc.cuh", "mlp_small.cuh", "engine.cuh", "../../include/node4j.h"]
+HEADERS = ["common.cuh", "solver_kernels.cuh", "layer_kernels.cuh", "tc_common.cuh", "conv_tc.cuh", "conv_wgrad_tc.cuh", "gemm_tc.cuh", "mlp_small.cuh", "engine.cuh", "../../include/node4j.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--fmad=true",
@@ -25,16 +25,29 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Concurrent callers (torchrun ranks importing the package at once) serialise on a lock file; the library is written to a
+    temporary name and renamed into place, so nobody ever dlopens a half-written file."""
     if not force and not _stale():
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    env = dict(os.environ)
-    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if verbose:
-        sys.stderr.write(r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():      # another process built it while this one waited
+                return LIB
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            tmp = f"{LIB}.{os.getpid()}.tmp"
+            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
+            r = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ))
+            if verbose:
+                sys.stderr.write(r.stderr)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+            os.replace(tmp, LIB)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

@@ -248,6 +248,14 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
                 wgrad_smem_ *= wgrad_nbuf_;
                 N4J_CUDA(cudaFuncSetAttribute(k_conv_wgrad64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_));
                 ensure(wpart_, (long long)B_ * 9 * 4096);
+                // tensor-core weight gradient (conv_wgrad_tc.cuh): per-tile partials, tiles of 128 shared-border padded pixels
+                wgeom_ = make_wgrad_tc_geom((int)B_, H_, W_);
+                wgrad_tc_smem_ = conv_wgrad_tc_smem_bytes(wgeom_);
+                wgrad_tc_ = !(cfg_.flags & N4J_FLAG_SIMT_WGRAD) && wgrad_tc_smem_ <= 227 * 1024;
+                if (wgrad_tc_) {
+                    N4J_CUDA(cudaFuncSetAttribute(k_conv_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_tc_smem_));
+                    ensure(wpart_, (long long)wgeom_.tiles * 9 * 4096);
+                }
             }
         }
         if (l.d.kind == N4J_LAYER_DENSE && !l.exact && !exact_ && !(cfg_.flags & N4J_FLAG_NO_TENSOR) && l.c_in % 32 == 0 && l.c_out % 32 == 0 &&
@@ -860,8 +868,14 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                     // ... except the very last weight gradient of a trial step: the main chain has nothing heavy left and waits for
                     // the join, so that launch takes one image per CTA (half the latency)
                     const bool wide = last_of_trial && i == first_conv_;
-                    const int ipc = wide ? 1 : (int)((B_ + 63) / 64), wg_ctas = (int)((B_ + ipc - 1) / ipc);
-                    k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, side_>>>(x, d, geom_, wpart_.p, ipc, wgrad_nbuf_);
+                    const int ipc = wide ? 1 : (int)((B_ + 63) / 64);
+                    int wg_ctas = (int)((B_ + ipc - 1) / ipc);
+                    if (wgrad_tc_) {      // tcgen05: one CTA per 128 padded pixels
+                        wg_ctas = wgeom_.tiles;
+                        k_conv_wgrad_tc<<<dim3(wgeom_.tiles), WGRAD_TC_THREADS, wgrad_tc_smem_, side_>>>(x, d, wgeom_, wpart_.p, (long long*)nullptr);
+                    } else {
+                        k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, side_>>>(x, d, geom_, wpart_.p, ipc, wgrad_nbuf_);
+                    }
                     ++launches_;
                     // sharded path: the sum over the ranks rides on the reduction (LL exchange of every finished float4)
                     const bool ll = comm_dev_ && vec_allreduce_ll_ && l.g_len <= comm_xll_cap_ && !skip_vec_allreduce_;
@@ -1019,6 +1033,24 @@ SolveGraph& Engine::get_graph(bool aug, int tslot, bool dense_out, int nt) {
     // eager paths (host-driven loop, RHS probes) and switched off while capturing.
     const bool saved_pdl = t_pdl;
     t_pdl = false;
+    // A throw inside the capture (an ILLEGAL_STATE check of enqueue_trial, any CUDA failure) must not leave stream2_ capturing,
+    // leak the graph or lose the launch counter / PDL switch: every later call on the handle would fail.
+    struct CaptureGuard {
+        Engine* e; SolveGraph* g; cudaStream_t s; int launches; bool pdl; bool armed = true;
+        ~CaptureGuard() {
+            if (!armed) return;
+            cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+            if (cudaStreamIsCapturing(s, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+                cudaGraph_t dead = nullptr;
+                cudaStreamEndCapture(s, &dead);      // ends (and invalidates) the capture; a captured-to-graph body belongs to g->graph
+                if (dead && dead != g->graph) cudaGraphDestroy(dead);
+            }
+            if (g->graph) { cudaGraphDestroy(g->graph); g->graph = nullptr; }
+            cudaGetLastError();
+            e->launches_ = launches;
+            t_pdl = pdl;
+        }
+    } guard{this, &sg, stream2_, saved, saved_pdl};
     N4J_CUDA(cudaGraphCreate(&sg.graph, 0));
     // prologue as a child graph
     cudaGraph_t pro = nullptr, epi = nullptr;
@@ -1059,6 +1091,7 @@ SolveGraph& Engine::get_graph(bool aug, int tslot, bool dense_out, int nt) {
     launches_ = saved;
     t_pdl = saved_pdl;
     N4J_CUDA(cudaGraphInstantiate(&sg.exec, sg.graph, 0));
+    guard.armed = false;
     if (pro) cudaGraphDestroy(pro);
     if (epi) cudaGraphDestroy(epi);
     return graphs_.emplace(key, sg).first->second;
@@ -1132,6 +1165,12 @@ void Engine::finish_call(n4j_stats* st, int) {
         cudaEventElapsedTime(&ms, ev0_, ev1_);
         st->gpu_ms = ms;
         st->gpu_launches = launches;
+    }
+    if (comm_dev_) {      // a peer timeout anywhere in the call (statistics, weight-gradient or error-norm exchange) is an error, never a silent wrong sum
+        int comm_status = 0;
+        N4J_CUDA(cudaMemcpy(&comm_status, reinterpret_cast<const char*>(comm_dev_) + offsetof(CommDev, status), sizeof(int), cudaMemcpyDeviceToHost));
+        if (comm_status != 0 || c.status == N4J_ERR_COMM)
+            throw Error{N4J_ERR_COMM, "multi-GPU exchange timed out: a peer rank did not publish its contribution within the spin limit"};
     }
     if (c.status == N4J_ERR_ILLEGAL_STATE) throw Error{N4J_ERR_ILLEGAL_STATE, "Detected NaN!"};   // NanWatchSolver.java:22
     if (c.status == N4J_ERR_MAX_STEPS) throw Error{N4J_ERR_MAX_STEPS, "step guard tripped: " + std::to_string(cfg_.max_trials) + " trial steps in one solve"};
@@ -1333,8 +1372,10 @@ void Engine::backward(const float* last_output, const float* dLdz, const float* 
     const int tslot = tg ? 1 : 0;
     const long long T = nt == 2 ? 1 : nt;          // stored time slices
     reset_ctrl();
-    // the forward of this iteration already uploaded the parameters (the updater only runs after the backward pass)
-    if (!params_fresh_) upload_params();
+    // The bound buffer is re-read at every call (node4j.h).  One exception: a backward that continues the forward of the same handle
+    // (last_output == NULL, the OdeGraphHelper.doForward/doBackward pairing: the updater only runs after the backward pass) reuses
+    // the weight images that forward built.  An explicit last_output (gradient checks, inference forwards in between) always re-uploads.
+    if (!(params_fresh_ && !last_output)) upload_params();
     params_fresh_ = false;
     ensure_zt(std::max<long long>(T, 2) * nz_);
     ensure(gt_, T * nz_);
@@ -1560,8 +1601,15 @@ void Engine::bench_piece(int what, int iters, float* us) {
                     q.H = l.H; q.W = l.W; q.Ci = l.c_in; q.Co = l.c_out; q.splits = 1;
                     launch_gemm<G_CONV_DGRAD>(stream_, q, launches_, exact_);
                 } else if (l.tc) {
-                    const int ipc = (int)((B_ + 63) / 64), wg_ctas = (int)((B_ + ipc - 1) / ipc);
-                    k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, stream_>>>(fixed_ref(gb_[0].p), fixed_ref(gb_[1].p), geom_, wpart_.p, ipc, wgrad_nbuf_);
+                    const int ipc = (int)((B_ + 63) / 64);
+                    int wg_ctas = (int)((B_ + ipc - 1) / ipc);
+                    if (wgrad_tc_) {
+                        wg_ctas = wgeom_.tiles;
+                        k_conv_wgrad_tc<<<dim3(wgeom_.tiles), WGRAD_TC_THREADS, wgrad_tc_smem_, stream_>>>(fixed_ref(gb_[0].p), fixed_ref(gb_[1].p), wgeom_, wpart_.p,
+                                                                                                              (long long*)nullptr);
+                    } else {
+                        k_conv_wgrad64<<<wg_ctas, 256, wgrad_smem_, stream_>>>(fixed_ref(gb_[0].p), fixed_ref(gb_[1].p), geom_, wpart_.p, ipc, wgrad_nbuf_);
+                    }
                     ++launches_;
                     LAUNCH(k_wgrad_reduce, 144, 256, stream_, wpart_.p, fixed_ref(theta_tmp_.p), wg_ctas, (CommDev*)nullptr);
                 } else {

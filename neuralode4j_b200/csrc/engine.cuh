@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "conv_tc.cuh"
+#include "conv_wgrad_tc.cuh"
 #include "gemm_tc.cuh"
 #include "layer_kernels.cuh"
 #include "mlp_small.cuh"
@@ -116,6 +117,9 @@ private:
     bool side_capable_ = false;
     size_t wgrad_smem_ = 0;
     int wgrad_nbuf_ = 1;
+    WgradTcGeom wgeom_{};            // tensor-core weight gradient (conv_wgrad_tc.cuh)
+    size_t wgrad_tc_smem_ = 0;
+    bool wgrad_tc_ = false;
     // k_stage_combine_last: the evaluation of stages 1-5 leaves its last elementwise kernel (forward: the last BatchNorm's apply,
     // adjoint: the first BatchNorm's backward dx) to the stage combination that follows
     bool leave_last_ = false;        // request to the evaluation being enqueued

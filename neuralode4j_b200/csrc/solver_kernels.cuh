@@ -348,7 +348,7 @@ __device__ __forceinline__ void controller_after_error(Ctrl* c, double sum, cons
     }
     if (log && c->log_n < p.log_cap) {
         n4j_step_rec r;
-        r.t = c->t; r.h = h; r.err = err; r.accepted = ok ? 1 : 0;
+        r.t = c->t; r.h = h; r.err = err; r.accepted = ok ? 1 : 0; r.solve = (int)c->solves - 1;
         log[c->log_n] = r;
     }
     c->log_n += 1;
@@ -357,6 +357,8 @@ __device__ __forceinline__ void controller_after_error(Ctrl* c, double sum, cons
     if (!done) clamp_to_end(c);                                          // :149 of the next iteration
     if (!(err == err) || !(c->h == c->h)) { c->status = N4J_ERR_ILLEGAL_STATE; done = 1; }   // NaN guard
     if (!done && c->trials_this_solve >= p.max_trials) { c->status = N4J_ERR_MAX_STEPS; done = 1; }
+    // multi-GPU: a peer that did not show up within the spin limit leaves stale sums behind — stop the solve instead of stepping on them
+    if (c->comm && *((volatile int*)&c->comm->status) != 0) { c->status = N4J_ERR_COMM; done = 1; }
     c->done = done;
 }
 

@@ -285,19 +285,19 @@ class OdeVertexImpl:
         n = self._L.node4j_get_step_log(self._h, None, 0)
         buf = (_lib.StepRec * max(int(n), 1))()
         self._L.node4j_get_step_log(self._h, buf, n)
-        # the log is one record per trial; a solve ends at its first accepted record that reaches the pair's end time
+        # one record per trial, tagged with the solve (segment) it belongs to: begin/done boundaries come from that tag, not from
+        # comparing times (t + (t_end - t) need not equal t_end in fp32).  Records beyond the engine's log capacity are not replayed.
+        held = min(int(n), len(buf))
         i = 0
-        for (t0, t1) in t_pairs:
+        for k, (t0, t1) in enumerate(t_pairs):
             for l in solver.listeners:
                 l.begin(np.array([t0, t1], dtype=np.float32), None)
-            while i < n:
+            while i < held and buf[i].solve == k and buf[i].h != 0.0:     # h == 0: past the engine's log capacity
                 r = buf[i]
                 i += 1
                 if r.accepted:
                     for l in solver.listeners:
                         l.step(_ReplayState(r.t), r.h, r.err)
-                    if r.t == np.float32(t1):
-                        break
             for l in solver.listeners:
                 l.done()
 
@@ -363,18 +363,34 @@ class OdeVertexImpl:
         return self._grad, epsilons
 
     # ---- multi-GPU ---------------------------------------------------------------------------------------------
-    def init_comm(self, group=None):
-        """Row-sharded minibatch over the ranks of a torch.distributed process group (one process per GPU, one box).
-        torch.distributed is only the host-side plumbing that carries the 64-byte IPC handles; the data path exchanges
-        run inside the engine's kernels over NVLink peer memory."""
-        import torch.distributed as dist
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    def comm_export(self) -> bytes:
+        """node4j_comm_export: the 64-byte IPC handle of this rank's exchange region.  The host framework all-gathers the handles
+        of all ranks (any transport: MPI, a file, torch.distributed, the JVM's own RPC) and passes them to `init_comm_handles`."""
         mine = C.create_string_buffer(64)
         _lib.check(self._L.node4j_comm_export(self._h, mine))
-        gathered = [None] * world
-        dist.all_gather_object(gathered, mine.raw, group=group)
-        allh = C.create_string_buffer(b"".join(gathered), 64 * world)
+        return mine.raw
+
+    def init_comm_handles(self, rank: int, world: int, handles) -> None:
+        """node4j_comm_init with pre-gathered handles (rank order): no torch on this path.  `handles` is a sequence of `world`
+        64-byte strings or one bytes object of 64 * world bytes.  Every rank must have called `comm_export` first and must not
+        launch work on the handle until all ranks have returned from this call (the caller's barrier)."""
+        raw = bytes(handles) if isinstance(handles, (bytes, bytearray)) else b"".join(bytes(h) for h in handles)
+        if len(raw) != 64 * world:
+            raise ValueError(f"expected {world} handles of 64 bytes, got {len(raw)} bytes")
+        if not 0 <= rank < world:
+            raise ValueError("rank out of range")
+        allh = C.create_string_buffer(raw, 64 * world)
         _lib.check(self._L.node4j_comm_init(self._h, rank, world, allh, self.shape[0] * world))
+
+    def init_comm(self, group=None):
+        """Convenience for hosts that already run torch.distributed (bench.py, the tests): row-sharded minibatch over the ranks of a
+        process group (one process per GPU, one box).  torch.distributed only carries the 64-byte IPC handles and the barrier; the data
+        path exchanges run inside the engine's kernels over NVLink peer memory.  Hosts without torch use comm_export / init_comm_handles."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, self.comm_export(), group=group)
+        self.init_comm_handles(rank, world, gathered)
         dist.barrier(group)
         return rank, world
 

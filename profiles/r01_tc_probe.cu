@@ -5,7 +5,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "conv_tc.cuh"
+#include "../neuralode4j_b200/csrc/conv_tc.cuh"
 #include "solver_kernels.cuh"
 
 using namespace n4j;

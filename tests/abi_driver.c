@@ -34,7 +34,7 @@ static int read_doubles(FILE* f, double* dst, int n) {
 }
 
 int main(int argc, char** argv) {
-    if (node4j_abi_version() != 1) { fprintf(stderr, "ABI version %d\n", (int)node4j_abi_version()); return 1; }
+    if (node4j_abi_version() != N4J_ABI_VERSION) { fprintf(stderr, "ABI version %d\n", (int)node4j_abi_version()); return 1; }
 
     n4j_layer_desc layer;
     memset(&layer, 0, sizeof(layer));

@@ -13,10 +13,14 @@ def pytest_configure(config):
 
 
 def _has_gpu():
+    """True when the engine sees a CUDA device.  A box that HAS a GPU but cannot load the library (stale .so, ABI mismatch,
+    missing build) must fail loudly, never skip: a silent skip would read as 'GPU tests green'."""
     try:
         from neuralode4j_b200 import _lib
         return _lib.load().node4j_device_count() > 0
-    except Exception:
+    except Exception as e:
+        if os.path.exists("/dev/nvidia0") or os.path.exists("/dev/nvidiactl"):
+            raise pytest.UsageError(f"a CUDA device is present but libnode4j_b200.so cannot be used: {e!r}")
         return False
 
 

@@ -124,6 +124,28 @@ def test_tensor_core_conv_matches_simt_conv(act):
             assert np.abs(a - b).max() <= 3e-5 * np.abs(b).max(), name
 
 
+@pytest.mark.parametrize("batch,hw", [(128, 7), (5, 5), (33, 4), (16, 9), (3, 14)])
+def test_tensor_core_wgrad_matches_simt_wgrad(batch, hw):
+    """k_conv_wgrad_tc (tcgen05, MN-major SWIZZLE_128B_BASE32B operands, hi/lo split stacked in one M128 N128 instruction, shared-border
+    padding) against the fp32 FMA kernel k_conv_wgrad64 (N4J_FLAG_SIMT_WGRAD) on the same engine and the same evaluation: everything
+    in front of the weight gradient is the same code, so f and g^T df/dz are bitwise equal and g^T df/dtheta agrees to fp32 summation
+    noise; both sit within 3e-5 of the oracle's maximum."""
+    w = W.mnist_block(batch=batch, channels=64, hw=hw)
+    rng = np.random.default_rng(23)
+    g = rng.standard_normal(w.shape).astype(np.float32)
+    res = []
+    for flags in (0, _lib.FLAG_SIMT_WGRAD):
+        v = w.conf.instantiate(w.shape, flags=flags)
+        v.setParams(w.params)
+        res.append(v.rhs_vjp(w.y0, g))
+        v.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.abs(res[0][2] - res[1][2]).max() <= 5e-6 * np.abs(res[1][2]).max()
+    odreal = H.oracle_for(w).rhs_vjp(w.params, w.y0, g)[2]
+    for r in res:
+        assert np.abs(r[2] - odreal).max() <= 3e-5 * np.abs(odreal).max()
+
+
 def test_rhs_conv_bn_ragged_channels():
     _rhs_case(W.mnist_block(batch=5, channels=24, hw=5), exact=False)
 

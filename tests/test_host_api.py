@@ -21,7 +21,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), f"libnode4j_b200.so does not export {name}"
     assert sorted(_lib.EXPORTS) == declared
-    assert L.node4j_abi_version() == 1
+    assert L.node4j_abi_version() == 2
 
 
 def test_library_is_built_for_sm_100a_only():
