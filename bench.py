@@ -5,15 +5,21 @@ Metric (BASELINE.json): ODE-net train samples/s (forward + adjoint backward of t
 MNIST ODE block, z = [128,64,7,7], BN-ReLU-conv3x3 x2 -BN-ReLU, t=[0,1], adaptive DP54 atol=rtol=1e-3, synthetic
 inputs and random-init weights.  One "step" = one node4j_forward + one node4j_backward.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config mnist|spiral|mlp4096|mlp4096_all_accept|timeseries]
 
 `value`     samples/s with inputs/outputs resident in HBM (device pointers through the C ABI), timed with CUDA events on
-            the engine's stream, L2 flushed between timed steps, max over ranks.
+            the engine's stream, L2 flushed between timed steps, max over ranks.  DEFAULT mode of the engine (`mode` key).
 `e2e`       the same through the reference-shaped API with pinned HOST buffers: H2D of y0/params/epsilon/gradient view
             and D2H of output/epsilon/gradients inside the timed region.
 `roofline`  dominant kernel (3x3 convolution as implicit GEMM) timed alone with CUDA events, against the measured bf16 peak.
 `cpu_baseline` / --impl reference: the CPU oracle (C++ restatement of the reference algorithm — the reference itself is
-            Java+ND4J and cannot run in this image) on the box's host cores.
+            Java+ND4J and cannot run in this image) on the box's host cores, FULL minibatch of the same workload.
+`parity_mode`   the same step under N4J_FLAG_EXACT_CONTRACTIONS (the mode whose gradients meet rtol 1e-4 against the oracle).
+`parity_check`  counts and deviations of both modes against the oracle run the cpu_baseline leg does anyway.
+`fast_tf32`     labelled extra: single-pass TF32 contractions (N4J_FLAG_FAST_TF32), its speed and its deviation.
+`configs`       the other BASELINE.json configurations (#1 spiral, #3 MLP-4096 adaptive and all-accept, #5 time series): value, e2e,
+                step counts, CPU sample, and for #3 the dense tcgen05 GEMM's roofline fraction.  (N=1 only; `--config X` makes X the headline.)
+`strong_scaling` (N>1) BASELINE.md's config #4 as stated there: GLOBAL batch 128 partitioned over the ranks (64/32/16 rows per GPU).
 """
 from __future__ import annotations
 
@@ -33,6 +39,11 @@ METRIC = "ODE-net train samples/s (fwd+adjoint bwd)"
 UNIT = "samples/s"
 BATCH = 128
 
+MODE_DEFAULT = ("default: tcgen05 3xTF32 (fp32-faithful) convolutions, weight gradients and large dense GEMMs with fp32 accumulation in TMEM; "
+                "solver reductions and BatchNorm statistics in double")
+MODE_PARITY = ("N4J_FLAG_EXACT_CONTRACTIONS: every contraction accumulates exact fp32 products in double (SIMT kernels), "
+               "bit-comparable with the CPU oracle")
+
 
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -45,20 +56,23 @@ def _peaks():
 def _conv_traffic_bytes(variant="<3, 1, 1>"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the forward conv launch (template variant <3,1,1>), from the
     committed `ncu --set full` summary (default cache control: caches flushed before each replay, so this is the cold figure)."""
-    path = os.path.join(ROOT, "profiles", "r01_conv3x3_tc_full.txt")
-    try:
-        reads, writes, on = [], [], False
-        for line in open(path):
-            if line.startswith("=="):
-                on = variant in line
-                continue
-            f = line.split()
-            if on and len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                v = float(f[1]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(f[2], 1.0)
-                (reads if f[0].startswith("dram__bytes_read") else writes).append(v)
-        return (sum(reads) / len(reads) + sum(writes) / len(writes)) if reads and writes else None
-    except OSError:
-        return None
+    for name in ("r02_conv3x3_tc_full.txt", "r01_conv3x3_tc_full.txt"):
+        path = os.path.join(ROOT, "profiles", name)
+        try:
+            reads, writes, on = [], [], False
+            for line in open(path):
+                if line.startswith("=="):
+                    on = variant in line
+                    continue
+                f = line.split()
+                if on and len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    v = float(f[1]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}.get(f[2], 1.0)
+                    (reads if f[0].startswith("dram__bytes_read") else writes).append(v)
+            if reads and writes:
+                return sum(reads) / len(reads) + sum(writes) / len(writes)
+        except OSError:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -98,42 +112,102 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def _workload():
+# ----------------------------------------------------------------------------------------------------------------------
+# workloads: BASELINE.json configs
+# ----------------------------------------------------------------------------------------------------------------------
+def _make_workload(name, batch=None):
     from neuralode4j_b200 import workloads as W
-    return W.mnist_block(batch=BATCH)
+    kw = {} if batch is None else {"batch": batch}
+    if name == "mnist":
+        return W.mnist_block(**({"batch": BATCH} | kw))
+    if name == "spiral":
+        return W.spiral_block(**kw)
+    if name == "mlp4096":
+        return W.mlp_block(**kw)
+    if name == "mlp4096_all_accept":   # "FixedStep vs adaptive" microbench: minStep >= maxStep throws in the reference (SolverConfig.java:22-24),
+        return W.mlp_block(abs_tol=1e30, rel_tol=1e30, **kw)   # so the non-adaptive arm is atol = rtol = 1e30: every trial accepts, h follows the growth schedule
+    if name == "timeseries":
+        return W.timeseries_block(**kw)
+    raise SystemExit(f"unknown config {name}")
 
 
-def _config(n_gpus):
-    return {"workload": "mnist_odeblock: OdeVertex(BN-ReLU, conv3x3 64ch, BN-ReLU, conv3x3 64ch, BN-ReLU) z=[128,64,7,7] t=[0,1] "
-                        "DormandPrince54 atol=rtol=1e-3 hmin=1e-20 hmax=100 (BASELINE.json configs[1])",
-            "per_gpu_batch": BATCH, "global_batch": BATCH * n_gpus,
+CONFIG_TEXT = {
+    "mnist": "mnist_odeblock: OdeVertex(BN-ReLU, conv3x3 64ch, BN-ReLU, conv3x3 64ch, BN-ReLU) z=[128,64,7,7] t=[0,1] "
+             "DormandPrince54 atol=rtol=1e-3 hmin=1e-20 hmax=100 (BASELINE.json configs[1])",
+    "spiral": "spiral latent-ODE block: fc 4-20-20-4 (ELU, ELU, identity) z=[1000,4], 100 time points of linspace(0,6pi,500), InputStep interpolated "
+              "forward, 99-segment adjoint, DormandPrince54 atol=1e-12 rtol=1e-6 (BASELINE.json configs[0])",
+    "mlp4096": "dense-MLP OdeVertex: Dense(4096->4096, tanh) -> Dense(4096->4096) z=[1024,4096] t=[0,1] adaptive DormandPrince54 atol=rtol=1e-3 "
+               "(BASELINE.json configs[2], adaptive arm)",
+    "mlp4096_all_accept": "dense-MLP OdeVertex as mlp4096 with atol=rtol=1e30: every trial step accepts, h follows the growth schedule "
+                          "(BASELINE.json configs[2], the non-adaptive arm; the reference's minStep>=maxStep throws)",
+    "timeseries": "InputStep time-series block: Dense(256->256) z=[1024,256], 32 time points linspace(0,4), needTimeGradient=true, interpolated forward, "
+                  "31-segment adjoint with time gradients, DormandPrince54 atol=1e-12 rtol=1e-6 (BASELINE.json configs[4])",
+}
+CPU_SAMPLE_BATCH = {"mnist": None, "spiral": None, "mlp4096": 8, "mlp4096_all_accept": 8, "timeseries": 64}   # None: the full minibatch
+
+
+def _config(name, n_gpus, per_gpu_batch, flags=0):
+    from neuralode4j_b200 import _lib
+    return {"workload": CONFIG_TEXT[name],
+            "per_gpu_batch": per_gpu_batch, "global_batch": per_gpu_batch * n_gpus,
             "parallelism": "single GPU" if n_gpus == 1 else
             f"minibatch row-sharded over {n_gpus} GPUs (one process per GPU): global step controller, sync BatchNorm statistics and "
             "parameter-gradient sums exchanged by one-shot all-reduces over NVLink peer memory inside the kernels",
-            "l2": "flushed between timed steps (256 MiB write); the step's own ~40 MB working set is L2-resident by nature",
-            "contractions": "tcgen05 3xTF32 implicit-GEMM convolutions (fp32-faithful), fp32 FMA weight gradients (default mode)"}
+            "l2": "flushed between timed steps (256 MiB write); the step's own working set is L2-resident by nature",
+            "mode": MODE_PARITY if flags & _lib.FLAG_EXACT_CONTRACTIONS else MODE_DEFAULT}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU oracle on host cores
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_step(batch):
-    """One bounded sample: fwd + adjoint bwd of the block at `batch` rows on the CPU oracle.  Returns seconds."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+def _oracle_threads():
     from oracle import oracle as O
-    from neuralode4j_b200 import workloads as W
-    w = W.mnist_block(batch=batch)
-    c = w.conf.odeForwardConf.solver.config
     try:                                   # all the host threads this process may use, whatever OMP_NUM_THREADS the launcher exported
         O.set_num_threads(len(os.sched_getaffinity(0)))
     except (AttributeError, OSError):
         O.set_num_threads(os.cpu_count() or 1)
+    return O.num_threads()
+
+
+def cpu_step(w, keep=False):
+    """One fwd + adjoint bwd of workload `w` on the CPU oracle.  Returns (seconds, threads, results or None)."""
+    from oracle import oracle as O
+    cores = _oracle_threads()
+    c = w.conf.odeForwardConf.solver.config
     orc = O.Oracle(w.conf.graph_spec(), w.shape, O.solver_cfg(c.absTol, c.relTol, c.minStep, c.maxStep))
-    eps = w.epsilon(w.shape)
+    hb = w.conf.odeBackwardConf
+    tg = O.TG_NONE if hb.time_input_index is None else (O.TG_CALC if hb.needTimeGradient else O.TG_ZERO)
+    interp = w.conf.odeForwardConf.interpolateForwardIfMultiStep
     t0 = time.perf_counter()
-    out = orc.forward(w.params, w.y0, w.time)
-    orc.backward(w.params, out, eps, w.time)
-    return time.perf_counter() - t0, O.num_threads()
+    out = orc.forward(w.params, w.y0, w.time, interpolate=interp)
+    fs = (int(orc.stats.nfe), int(orc.stats.accepted), int(orc.stats.rejected))
+    eps = w.epsilon(out.shape)
+    dy0, grad, dt = orc.backward(w.params, out, eps, w.time, time_grad=tg)
+    bs = (int(orc.stats.nfe), int(orc.stats.accepted), int(orc.stats.rejected))
+    sec = time.perf_counter() - t0
+    res = dict(out=out, dy0=dy0, grad=grad, dt=dt, fwd_stats=fs, bwd_stats=bs) if keep else None
+    return sec, cores, res
+
+
+def cpu_sample(name, budget_s=10.0, max_reps=16, min_reps=2, keep=False, warm=True):
+    """Bounded CPU sample of config `name`: full minibatch where the oracle finishes in seconds, a row slice otherwise (said in `sample`)."""
+    sb = CPU_SAMPLE_BATCH[name]
+    w = _make_workload(name, sb)
+    batch = w.shape[0]
+    cores, res = 1, None
+    if warm or keep:
+        _, cores, res = cpu_step(w, keep=keep)          # untimed: pages the library in, spins the OpenMP team up
+    reps, tot = 0, 0.0
+    while reps < min_reps or (tot < budget_s and reps < max_reps):
+        dt, cores, _ = cpu_step(w)
+        tot += dt
+        reps += 1
+    full = _make_workload(name).shape[0]
+    what = (f"{reps} full steps (fwd + adjoint bwd, batch {batch}) of the same workload" if batch == full else
+            f"{reps} steps (fwd + adjoint bwd) on a {batch}-row slice of the {full}-row minibatch (no BatchNorm in this block: rows are independent; "
+            "the slice takes its own adaptive step sequence)")
+    return {"value": reps * batch / tot, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{what} on the CPU oracle{' after one warm-up' if warm or keep else ''}: {tot:.1f} s"}, res
 
 
 def cpu_blas_grade_estimate(fwd_evals, aug_evals, threads):
@@ -184,22 +258,31 @@ def cpu_blas_grade_estimate(fwd_evals, aug_evals, threads):
 
 
 def run_reference(args):
+    """The reference arm: the CPU oracle on the FULL minibatch of the same config (each step = one fwd + adjoint bwd at batch 128
+    for the headline; configs whose oracle step would take minutes use the row slice named in `sample`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_batch = 32
-    for _ in range(min(args.warmup, 1)):
-        cpu_step(sample_batch)
-    times = []
+    sb = CPU_SAMPLE_BATCH[args.config]
+    w = _make_workload(args.config, sb)
+    batch = w.shape[0]
+    for _ in range(args.warmup):
+        cpu_step(w)
+    times, cores = [], 1
     for _ in range(args.steps):
-        dt, cores = cpu_step(sample_batch)
+        dt, cores, _ = cpu_step(w)
         times.append(dt)
     ms = 1e3 * float(np.mean(times))
-    value = sample_batch / (ms / 1e3)
-    sample = f"each step = fwd+adjoint bwd of the same block on a {sample_batch}-row slice of the minibatch (BatchNorm statistics over the slice)"
+    value = batch / (ms / 1e3)
+    full = _make_workload(args.config).shape[0]
+    sample = (f"each step = fwd+adjoint bwd of the same block on the full {batch}-row minibatch" if batch == full else
+              f"each step = fwd+adjoint bwd on a {batch}-row slice of the {full}-row minibatch (rows are independent in this block)")
+    cfg = _config(args.config, args.gpus, full)
+    cfg["mode"] = "CPU oracle, fp32 state with double-accumulated contractions (the arithmetic contract of DESIGN.md section 2)"
+    cfg["reference_arm_batch"] = batch
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": _config(args.gpus),
+            "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference = CPU oracle (C++/OpenMP restatement of the neuralODE4j algorithm); the Java/ND4J reference cannot run here"}
@@ -209,234 +292,368 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the node4j engine has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.dev = torch.device("cuda", self.local_rank)
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.args = args
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, vals):
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def measure(self, w, flags, steps, warmup, e2e=True, rotating=False, sharded=True, keep=False, pieces=False, sample_clocks=False):
+        """Times `steps` fwd+bwd steps of workload `w` (device-resident, then host buffers).  Returns a dict of LOCAL timings; the caller
+        reduces over ranks."""
+        torch = self.torch
+        from neuralode4j_b200 import _lib
+        v = w.conf.instantiate(w.shape, device=self.local_rank, flags=flags)
+        if self.world > 1 and sharded:
+            v.init_comm()
+        stream = torch.cuda.ExternalStream(v.cuda_stream(), device=self.local_rank)
+        dev = self.dev
+
+        def flush():
+            with torch.cuda.stream(stream):
+                self.flush_buf.zero_()
+
+        def set_inputs(y):
+            if w.time_is_input:
+                v.setInputs(y, w.time)
+            else:
+                v.setInputs(y)
+
+        d_params = torch.from_numpy(w.params).to(dev)
+        d_y0 = torch.from_numpy(w.y0).to(dev)
+        d_grad = torch.zeros(v.numParams(), dtype=torch.float32, device=dev)
+        v.setParams(d_params)
+        v.setBackpropGradientsViewArray(d_grad)
+        set_inputs(d_y0)
+        out_shape = tuple(v.doForward(True).shape)
+        eps_np = w.epsilon(out_shape)
+        d_eps = torch.from_numpy(eps_np).to(dev)
+        res = {}
+        launches = [0]
+
+        def step_resident():
+            d_grad.zero_()                       # ZeroGrad listener (util/listen/training/ZeroGrad.java:14-16)
+            set_inputs(d_y0)
+            out = v.doForward(True)
+            v.setEpsilon(d_eps)
+            g, e = v.doBackward()
+            launches[0] = v.fwd_stats.gpu_launches + v.bwd_stats.gpu_launches
+            return out, e, g
+
+        def timed(step_fn, k):
+            total_ms = 0.0
+            for _ in range(k):
+                flush()
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                step_fn()
+                e1.record(stream)
+                e1.synchronize()
+                total_ms += e0.elapsed_time(e1)
+            return total_ms
+
+        for _ in range(max(warmup, 3)):
+            last = step_resident()
+        self.barrier()
+        sampler = ClockSampler(self.local_rank) if (self.rank == 0 and sample_clocks) else None
+        t_wall = time.perf_counter()
+        res["res_ms"] = timed(step_resident, steps)
+        self.barrier()
+        res["wall_s"] = time.perf_counter() - t_wall
+        res["clocks"] = sampler.stop() if sampler else None
+        res["fwd_stats"] = (int(v.fwd_stats.nfe), int(v.fwd_stats.accepted), int(v.fwd_stats.rejected))
+        res["bwd_stats"] = (int(v.bwd_stats.nfe), int(v.bwd_stats.accepted), int(v.bwd_stats.rejected))
+        res["launches"] = int(launches[0])
+        if keep:
+            out, e, g = last
+            idx = w.conf.odeBackwardConf.time_input_index
+            dy0 = e[0] if idx is None else e[(idx + 1) % 2]
+            res["outputs"] = dict(out=out.cpu().numpy(), dy0=dy0.cpu().numpy(), grad=g.cpu().numpy(), eps=eps_np)
+
+        if rotating:
+            # second protocol of the timing rules: no flush, but INPUTS larger than L2 — a different (y0, dL/dz) pair every step, the
+            # set of pairs being larger than the 126 MB L2.  Models a training loop: fresh minibatch from HBM every step, the engine's own
+            # weights / state / code warm.  Reported next to the (conservative) flushed number, never instead of it.
+            pair_bytes = (d_y0.numel() + d_eps.numel()) * 4
+            n_pairs = int(140e6 // pair_bytes) + 1
+            rot_y0 = [d_y0.clone() for _ in range(n_pairs)]
+            rot_eps = [d_eps.clone() for _ in range(n_pairs)]
+            rot_i = [0]
+
+            def step_rotating():
+                i = rot_i[0] % n_pairs
+                rot_i[0] += 1
+                d_grad.zero_()
+                set_inputs(rot_y0[i])
+                v.doForward(True)
+                v.setEpsilon(rot_eps[i])
+                v.doBackward()
+
+            for _ in range(3):
+                step_rotating()
+            self.barrier()
+            er0 = torch.cuda.Event(enable_timing=True); er1 = torch.cuda.Event(enable_timing=True)
+            er0.record(stream)
+            for _ in range(steps):
+                step_rotating()
+            er1.record(stream)
+            er1.synchronize()
+            res["rot_ms"] = er0.elapsed_time(er1)
+            res["rot_pairs"], res["rot_pair_bytes"] = n_pairs, pair_bytes
+            del rot_y0, rot_eps
+            self.barrier()
+
+        if e2e:
+            h_params = torch.from_numpy(w.params).pin_memory()
+            h_y0 = torch.from_numpy(w.y0).pin_memory()
+            h_eps = torch.from_numpy(eps_np).pin_memory()
+            h_grad = torch.zeros(v.numParams(), dtype=torch.float32).pin_memory()
+            hp, hy, he, hg = h_params.numpy(), h_y0.numpy(), h_eps.numpy(), h_grad.numpy()
+            v.setParams(hp)
+            v.setBackpropGradientsViewArray(hg)
+            nz, no = int(np.prod(w.shape)), int(np.prod(out_shape))
+            res["h2d"] = 4 * (nz + v.numParams() + no + v.numParams())      # y0, params | epsilon, gradient view (seed)
+            res["d2h"] = 4 * (no + nz + v.numParams())                      # output | dL/dy0, gradient view
+
+            def step_e2e():
+                hg[:] = 0
+                set_inputs(hy)
+                out = v.doForward(True)
+                v.setEpsilon(he)
+                g, e = v.doBackward()
+                return float(out.ravel()[0]) + float(np.asarray(g).ravel()[0])   # results are on the host
+
+            for _ in range(3):
+                step_e2e()
+            self.barrier()
+            res["e2e_ms"] = timed(step_e2e, steps)
+            self.barrier()
+            v.setParams(d_params)
+
+        if pieces:
+            nz = int(np.prod(w.shape))
+            p = {}
+            p["conv_us"] = v.bench_piece(_lib.BENCH_CONV_FWD, 50)
+            p["dgrad_us"] = v.bench_piece(_lib.BENCH_CONV_DGRAD, 50)
+            p["wgrad_us"] = v.bench_piece(_lib.BENCH_CONV_WGRAD, 50)
+            try:
+                p["conv_fused_us"] = v.bench_piece(_lib.BENCH_CONV_FWD_FUSED, 50)      # as launched inside an evaluation: BN-apply prologue + stats epilogue
+                p["dgrad_fused_us"] = v.bench_piece(_lib.BENCH_CONV_DGRAD_FUSED, 50)  # BN-backward prologue + backward-stats epilogue
+            except ValueError:                                                         # every fusion switched off by --flags: the bare kernels are the launches
+                p["conv_fused_us"], p["dgrad_fused_us"] = p["conv_us"], p["dgrad_us"]
+            p["rhs_us"] = v.bench_piece(_lib.BENCH_RHS_FWD, 50)
+            p["aug_us"] = v.bench_piece(_lib.BENCH_RHS_AUG, 50)
+            p["n_aug"] = 2 * nz + v.numParams()
+            p["pass_fwd_us"] = v.bench_solver_pass(nz, 50)
+            p["pass_aug_us"] = v.bench_solver_pass(p["n_aug"], 50)
+            p["pass_big_us"] = v.bench_solver_pass(1 << 26, 10)           # 256 MiB per vector: HBM-resident, not L2
+            res["pieces"] = p
+        elif pieces is None:      # dense configs: one f(z) = the two big GEMMs (+ bias / activation kernels)
+            res["rhs_us"] = v.bench_piece(_lib.BENCH_RHS_FWD, 10)
+        v.close()
+        return res
+
+
+def _deviation(a, b, rtol=1e-4, atol_scale=1e-5):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    err = np.abs(a - b)
+    tol = atol_scale * np.abs(b).max() + rtol * np.abs(b)
+    return {"rel_l2": float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300)), "frac_outside_rtol_1e-4": float((err > tol).mean()),
+            "worst_abs_over_max": float(err.max() / (np.abs(b).max() + 1e-300))}
+
+
+def _parity_block(gpu, orc):
+    """Deviation of one GPU run (dict with outputs and stats) from the oracle run on the same inputs."""
+    o = gpu["outputs"]
+    return {"fwd_counts_equal": list(gpu["fwd_stats"]) == list(orc["fwd_stats"]), "bwd_counts_equal": list(gpu["bwd_stats"]) == list(orc["bwd_stats"]),
+            "counts_gpu": {"fwd": gpu["fwd_stats"], "bwd": gpu["bwd_stats"]}, "counts_oracle": {"fwd": orc["fwd_stats"], "bwd": orc["bwd_stats"]},
+            "out": _deviation(o["out"], orc["out"]), "dL_dy0": _deviation(o["dy0"], orc["dy0"]), "dL_dtheta": _deviation(o["grad"], orc["grad"])}
+
+
 def run_ours(args):
-    import torch
-    import torch.distributed as dist
     from neuralode4j_b200 import _lib
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the node4j engine has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    w = _workload()
-    if world > 1:   # weak scaling: every rank owns 128 rows of a 128*N minibatch
+    B = Bench(args)
+    world, rank = B.world, B.rank
+    name = args.config
+    w = _make_workload(name)
+    per_gpu = w.shape[0]
+    if world > 1:   # weak scaling: every rank owns a full minibatch of a world-times larger global one
         w.y0 = np.random.default_rng(1234 + rank).standard_normal(w.shape).astype(np.float32)
         w.eps_seed += rank
-    v = w.conf.instantiate(w.shape, device=local_rank, flags=args.flags)
-    if world > 1:
-        v.init_comm()
-    stream = torch.cuda.ExternalStream(v.cuda_stream(), device=local_rank)
-    dev = torch.device("cuda", local_rank)
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    is_mnist = name == "mnist"
+    main = B.measure(w, args.flags, args.steps, args.warmup, e2e=True, rotating=is_mnist, keep=(world == 1), pieces=True if is_mnist else None,
+                     sample_clocks=True)
+    res_ms, e2e_ms, rot_ms = B.max_over_ranks([main["res_ms"], main["e2e_ms"], main.get("rot_ms", 0.0)])
 
-    def flush():
-        with torch.cuda.stream(stream):
-            flush_buf.zero_()
+    extras = {}
+    if is_mnist and not args.quick:
+        # the mode whose gradients meet rtol 1e-4 against the oracle, and the single-pass TF32 mode, next to the default
+        par = B.measure(w, args.flags | _lib.FLAG_EXACT_CONTRACTIONS, max(3, args.steps // 2), 3, e2e=False, keep=(world == 1))
+        (par_ms,) = B.max_over_ranks([par["res_ms"] / max(3, args.steps // 2)])
+        extras["parity_mode"] = {"value": world * per_gpu / (par_ms / 1e3), "unit": UNIT, "ms_per_step": par_ms, "mode": MODE_PARITY,
+                                 "counts": {"fwd": par["fwd_stats"], "bwd": par["bwd_stats"]}}
+        fast = B.measure(w, args.flags | _lib.FLAG_FAST_TF32, max(3, args.steps // 2), 3, e2e=False, keep=(world == 1))
+        (fast_ms,) = B.max_over_ranks([fast["res_ms"] / max(3, args.steps // 2)])
+        extras["fast_tf32"] = {"value": world * per_gpu / (fast_ms / 1e3), "unit": UNIT, "ms_per_step": fast_ms,
+                               "mode": "N4J_FLAG_FAST_TF32: single-pass TF32 contractions (10-bit mantissa operands) — NOT fp32-faithful, labelled extra",
+                               "counts": {"fwd": fast["fwd_stats"], "bwd": fast["bwd_stats"]}}
+        if world == 1:
+            extras["fast_tf32"]["deviation_from_default_mode"] = {k: _deviation(fast["outputs"][k], main["outputs"][k]) for k in ("out", "dy0", "grad")}
+            extras["_par_outputs"] = par
+    if is_mnist and world > 1 and not args.quick:
+        # BASELINE.md section 3, config #4 as stated: GLOBAL batch 128 partitioned over the ranks (64 / 32 / 16 rows per GPU)
+        rows = BATCH // world
+        ws = _make_workload("mnist")
+        ws.y0 = np.ascontiguousarray(ws.y0[rank * rows:(rank + 1) * rows])
+        ws.shape = (rows,) + tuple(ws.shape[1:])
+        full_eps = ws.epsilon((BATCH,) + tuple(ws.shape[1:]))
+        ws.epsilon = lambda shape, _e=full_eps, _r=rank, _n=rows: np.ascontiguousarray(_e[_r * _n:(_r + 1) * _n])
+        ss = B.measure(ws, args.flags, args.steps, 3, e2e=False)
+        (ss_ms,) = B.max_over_ranks([ss["res_ms"] / args.steps])
+        extras["strong_scaling"] = {"value": BATCH / (ss_ms / 1e3), "unit": UNIT, "ms_per_step": ss_ms, "global_batch": BATCH, "rows_per_gpu": rows,
+                                    "counts": {"fwd": ss["fwd_stats"], "bwd": ss["bwd_stats"]},
+                                    "what": "BASELINE.md config #4: the SAME 128-row minibatch as the 1-GPU line, partitioned by rows; identical step sequence"}
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    other = {}
+    if is_mnist and world == 1 and not args.quick:
+        peaks = _peaks()
+        for cname, csteps in (("spiral", 5), ("mlp4096", 3), ("mlp4096_all_accept", 3), ("timeseries", 3)):
+            cw = _make_workload(cname)
+            r = B.measure(cw, args.flags, csteps, 3, e2e=True, pieces=None if cname.startswith("mlp") else False)
+            ms, ems = r["res_ms"] / csteps, r["e2e_ms"] / csteps
+            nfe = r["fwd_stats"][0] + r["bwd_stats"][0]
+            entry = {"config": CONFIG_TEXT[cname], "value": cw.shape[0] / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": csteps,
+                     "e2e": {"value": cw.shape[0] / (ems / 1e3), "unit": UNIT, "ms_per_step": ems, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+                     "gpu_launches_per_step": r["launches"],
+                     "solver": {"fwd": dict(zip(("nfe", "accepted", "rejected"), r["fwd_stats"])), "bwd": dict(zip(("nfe", "accepted", "rejected"), r["bwd_stats"])),
+                                "rhs_evals_per_s": nfe / (ms / 1e3)}}
+            if cname.startswith("mlp"):
+                fl = 2 * 2.0 * cw.shape[0] * cw.shape[1] * cw.shape[1]          # two [B,D]x[D,D] GEMMs per f(z)
+                tf = fl / (r["rhs_us"] * 1e-6) / 1e12
+                entry["roofline"] = {"bound": "tensor", "kernel": "k_gemm_tc<2> x2 (tcgen05 3xTF32 dense GEMM 1024x4096x4096, 256x128 tiles) + bias/activation kernels = one f(z)",
+                                     "achieved": tf, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"], "traffic": None,
+                                     "algorithmic_flops_per_eval": fl, "us_per_eval": r["rhs_us"],
+                                     "peak_source": f"{peaks['src']} bf16 burst; 3xTF32 issues 3 TF32 passes per product (TF32 peak = bf16/2): fp32-faithful flops reach at most peak/6"}
+            if not args.no_cpu and cname != "mlp4096_all_accept":      # the all-accept arm shares the adaptive arm's CPU sample (same block, same cost per evaluation)
+                try:
+                    entry["cpu_baseline"], _ = cpu_sample(cname, budget_s=5.0, max_reps=4, min_reps=1, warm=False)
+                except Exception as e:      # a context number: never fail the bench line over it
+                    entry["cpu_baseline"] = {"unavailable": repr(e)}
+            other[cname] = entry
 
-    eps_np = w.epsilon(w.shape)
-
-    # ---- resident arm: device pointers --------------------------------------------------------------------------------
-    d_params = torch.from_numpy(w.params).to(dev)
-    d_y0 = torch.from_numpy(w.y0).to(dev)
-    d_eps = torch.from_numpy(eps_np).to(dev)
-    d_grad = torch.zeros(v.numParams(), dtype=torch.float32, device=dev)
-    v.setParams(d_params)
-    v.setBackpropGradientsViewArray(d_grad)
-
-    launches = [0]
-
-    def step_resident():
-        d_grad.zero_()                       # ZeroGrad listener (util/listen/training/ZeroGrad.java:14-16)
-        v.setInputs(d_y0)
-        out = v.doForward(True)
-        v.setEpsilon(d_eps)
-        g, e = v.doBackward()
-        launches[0] = v.fwd_stats.gpu_launches + v.bwd_stats.gpu_launches
-        return out, e[0], g
-
-    def timed(step_fn, k):
-        total_ms = 0.0
-        for _ in range(k):
-            flush()
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            step_fn()
-            e1.record(stream)
-            e1.synchronize()
-            total_ms += e0.elapsed_time(e1)
-        return total_ms
-
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    t_wall = time.perf_counter()
-    res_ms = timed(step_resident, args.steps)
-    barrier()
-    t_wall = time.perf_counter() - t_wall
-    clocks = sampler.stop() if sampler else None
-    fwd_stats = (v.fwd_stats.nfe, v.fwd_stats.accepted, v.fwd_stats.rejected)
-    bwd_stats = (v.bwd_stats.nfe, v.bwd_stats.accepted, v.bwd_stats.rejected)
-    n_launch = launches[0]
-
-    # ---- second protocol of the timing rules: no flush, but INPUTS larger than L2 — a different (y0, dL/dz) pair every step, the
-    # set of pairs being larger than the 126 MB L2.  Models a training loop: fresh minibatch from HBM every step, the engine's own
-    # weights / state / code warm.  Reported next to the (conservative) flushed number, never instead of it.
-    pair_bytes = 2 * d_y0.numel() * 4
-    n_pairs = int(140e6 // pair_bytes) + 1
-    rot_y0 = [d_y0.clone() for _ in range(n_pairs)]
-    rot_eps = [d_eps.clone() for _ in range(n_pairs)]
-    rot_i = [0]
-
-    def step_rotating():
-        i = rot_i[0] % n_pairs
-        rot_i[0] += 1
-        d_grad.zero_()
-        v.setInputs(rot_y0[i])
-        v.doForward(True)
-        v.setEpsilon(rot_eps[i])
-        v.doBackward()
-
-    for _ in range(3):
-        step_rotating()
-    barrier()
-    er0 = torch.cuda.Event(enable_timing=True); er1 = torch.cuda.Event(enable_timing=True)
-    er0.record(stream)
-    for _ in range(args.steps):
-        step_rotating()
-    er1.record(stream)
-    er1.synchronize()
-    rot_ms = er0.elapsed_time(er1)
-    del rot_y0, rot_eps
-    barrier()
-
-    # ---- end-to-end arm: pinned host buffers through the same API --------------------------------------------------------
-    h_params = torch.from_numpy(w.params).pin_memory()
-    h_y0 = torch.from_numpy(w.y0).pin_memory()
-    h_eps = torch.from_numpy(eps_np).pin_memory()
-    h_grad = torch.zeros(v.numParams(), dtype=torch.float32).pin_memory()
-    hp, hy, he, hg = h_params.numpy(), h_y0.numpy(), h_eps.numpy(), h_grad.numpy()
-    v.setParams(hp)
-    v.setBackpropGradientsViewArray(hg)
-    nz = int(np.prod(w.shape))
-    h2d = 4 * (nz + v.numParams() + nz + v.numParams())      # y0, params | epsilon, gradient view (seed)
-    d2h = 4 * (nz + nz + v.numParams())                      # output | dL/dy0, gradient view
-
-    def step_e2e():
-        hg[:] = 0
-        v.setInputs(hy)
-        out = v.doForward(True)
-        v.setEpsilon(he)
-        g, e = v.doBackward()
-        return float(out.ravel()[0]) + float(e[0].ravel()[0])   # results are on the host
-
-    for _ in range(3):
-        step_e2e()
-    barrier()
-    e2e_ms = timed(step_e2e, args.steps)
-    barrier()
-
-    # ---- per-kernel numbers for the roofline ------------------------------------------------------------------------------
-    v.setParams(d_params)
-    conv_us = v.bench_piece(_lib.BENCH_CONV_FWD, 50)
-    dgrad_us = v.bench_piece(_lib.BENCH_CONV_DGRAD, 50)
-    wgrad_us = v.bench_piece(_lib.BENCH_CONV_WGRAD, 50)
-    try:
-        conv_fused_us = v.bench_piece(_lib.BENCH_CONV_FWD_FUSED, 50)      # as launched inside an evaluation: BN-apply prologue + stats epilogue
-        dgrad_fused_us = v.bench_piece(_lib.BENCH_CONV_DGRAD_FUSED, 50)  # BN-backward prologue + backward-stats epilogue
-    except ValueError:                                                    # every fusion switched off by --flags: the bare kernels are the launches
-        conv_fused_us, dgrad_fused_us = conv_us, dgrad_us
-    rhs_us = v.bench_piece(_lib.BENCH_RHS_FWD, 50)
-    aug_us = v.bench_piece(_lib.BENCH_RHS_AUG, 50)
-    n_aug = 2 * nz + v.numParams()
-    pass_fwd_us = v.bench_solver_pass(nz, 50)
-    pass_aug_us = v.bench_solver_pass(n_aug, 50)
-    pass_big_us = v.bench_solver_pass(1 << 26, 10)           # 256 MiB per vector: HBM-resident, not L2
-    v.close()
-
-    # ---- reduce over ranks (max time) ----------------------------------------------------------------------------------------
-    t = torch.tensor([res_ms, e2e_ms, rot_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    res_ms, e2e_ms, rot_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            B.dist.destroy_process_group()
         return
 
     peaks = _peaks()
     ms_per_step = res_ms / args.steps
-    value = world * BATCH / (ms_per_step / 1e3)
-    e2e_value = world * BATCH / (e2e_ms / args.steps / 1e3)
-    conv_flops = 2.0 * (BATCH * 49) * 64 * 576
-    achieved_tf = conv_flops / (conv_fused_us * 1e-6) / 1e12
+    value = world * per_gpu / (ms_per_step / 1e3)
+    e2e_value = world * per_gpu / (e2e_ms / args.steps / 1e3)
+    fwd_stats, bwd_stats = main["fwd_stats"], main["bwd_stats"]
     nfe_total = fwd_stats[0] + bwd_stats[0]
-    # one forward RHS eval = 2 convs; one augmented eval = 2 fwd + 2 dgrad + 2 wgrad
-    # (the two weight-gradient launches of an augmented eval run on a side branch, overlapped with the main chain: not counted here)
-    conv_share = ((fwd_stats[0] * 2 + bwd_stats[0] * 2) * conv_fused_us + bwd_stats[0] * 2 * dgrad_fused_us) / (ms_per_step * 1e3)
 
-    # CPU baseline (oracle, bounded sample, rank 0 at N=1 only)
-    cpu = None
+    # CPU baseline (oracle, bounded sample, rank 0 at N=1 only) and the parity check against that same oracle run
+    cpu, parity = None, None
     if world == 1 and not args.no_cpu:
-        cpu_step(BATCH)                                   # untimed: pages the library in, spins the OpenMP team up
-        reps, tot, cores = 0, 0.0, 1
-        while reps < 4 or (tot < 10.0 and reps < 16):     # a bounded sample: about 10 s of CPU work
-            dt, cores = cpu_step(BATCH)
-            tot += dt
-            reps += 1
-        cpu = {"value": reps * BATCH / tot, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{reps} full steps (fwd + adjoint bwd, batch {BATCH}) of the same workload on the CPU oracle after one warm-up: {tot:.1f} s"}
-        try:      # evaluations the solves actually compute: nfe counts one K0 per solve that is not recomputed
-            cpu["blas_grade_estimate"] = cpu_blas_grade_estimate(int(fwd_stats[0]) - 1, int(bwd_stats[0]) - 1, cores)
-        except Exception as e:      # context only: never fail the bench line over it
-            cpu["blas_grade_estimate"] = {"unavailable": repr(e)}
+        cpu, orc = cpu_sample(name, keep=True)
+        if is_mnist:
+            try:      # evaluations the solves actually compute: nfe counts one K0 per solve that is not recomputed (DESIGN.md section 5)
+                cpu["blas_grade_estimate"] = cpu_blas_grade_estimate(int(fwd_stats[0]) - 1, int(bwd_stats[0]) - 1, cpu["cores"])
+            except Exception as e:      # context only: never fail the bench line over it
+                cpu["blas_grade_estimate"] = {"unavailable": repr(e)}
+        if orc is not None and CPU_SAMPLE_BATCH[name] is None and "outputs" in main:
+            parity = {"against": "the CPU oracle on the same inputs (the cpu_baseline leg's warm-up run)", "tolerance": "north_star: rtol 1e-4 (+1e-5 of the maximum) and exact counts",
+                      "default_mode": _parity_block(main, orc)}
+            if "_par_outputs" in extras:
+                parity["parity_mode"] = _parity_block(extras["_par_outputs"], orc)
+    extras.pop("_par_outputs", None)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": _config(world),
-        "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": int(n_launch) * args.steps,
-        "resident_rotating_inputs": {"value": world * BATCH / (rot_ms / args.steps / 1e3), "unit": UNIT, "ms_per_step": rot_ms / args.steps,
-                                     "protocol": f"no L2 flush; {n_pairs} distinct (y0, dL/dz) pairs = {n_pairs * pair_bytes / 1e6:.0f} MB > L2, one per step; "
-                                                 "engine state and weights stay warm (the headline `value` flushes everything)"},
-        "roofline": {"bound": "tensor", "kernel": "k_conv3x3_tc<3,1,1> as launched in the step (BatchNorm-apply operand prologue + tcgen05 3xTF32 implicit-GEMM conv3x3, "
-                               "M=6272 pixels N=64 K=576 + BatchNorm-statistics epilogue); the dgrad variant <3,2,2> is timed next to it",
-                     "achieved": achieved_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf_sust"],
-                     "traffic": _conv_traffic_bytes(),
-                     "peak_source": f"{peaks['src']} bf16 sustained (kernel runs inside a long step). The kernel issues 3 TF32 passes per product "
-                                    "(TF32 peak = bf16/2), so fp32-faithful algorithmic flops can reach at most peak/6; 81 CTAs of 148 SMs, "
-                                    "latency-bound at this size (see DESIGN.md section 4)",
-                     "algorithmic_flops_per_launch": conv_flops, "us_per_launch": conv_fused_us, "us_per_launch_dgrad_variant": dgrad_fused_us,
-                     "us_bare_conv_kernel": conv_us, "share_of_step": conv_share},
-        "roofline_solver": {"bound": "hbm", "kernel": "6x k_stage_combine + k_error_ctrl (one trial step, 160*N bytes)",
-                            "n_fwd": nz, "us_fwd": pass_fwd_us, "gbs_fwd": 160.0 * nz / (pass_fwd_us * 1e-6) / 1e9,
-                            "n_aug": n_aug, "us_aug": pass_aug_us, "gbs_aug": 160.0 * n_aug / (pass_aug_us * 1e-6) / 1e9,
-                            "n_hbm": 1 << 26, "us_hbm": pass_big_us, "achieved": 160.0 * (1 << 26) / (pass_big_us * 1e-6) / 1e9,
-                            "peak": peaks["hbm"], "unit": "GB/s", "frac": 160.0 * (1 << 26) / (pass_big_us * 1e-6) / 1e9 / peaks["hbm"],
-                            "frac_of_nominal_8TBs": 160.0 * (1 << 26) / (pass_big_us * 1e-6) / 1e9 / 8000.0,
-                            "note": "fwd/aug sizes are L2-resident (algorithmic GB/s can exceed HBM peak); n_hbm is the HBM-resident measurement"},
+        "config": _config(name, world, per_gpu, args.flags),
+        "mode": MODE_PARITY if args.flags & _lib.FLAG_EXACT_CONTRACTIONS else MODE_DEFAULT,
+        "clocks": main["clocks"],
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": main["h2d"], "d2h_bytes_per_step": main["d2h"], "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(main["launches"]) * args.steps,
         "cpu_baseline": cpu,
         "solver": {"fwd": {"nfe": fwd_stats[0], "accepted": fwd_stats[1], "rejected": fwd_stats[2]},
                    "bwd": {"nfe": bwd_stats[0], "accepted": bwd_stats[1], "rejected": bwd_stats[2]},
-                   "rhs_evals_per_s": nfe_total / (ms_per_step / 1e3) * world,
-                   "us_per_rhs_fwd": rhs_us, "us_per_rhs_aug": aug_us, "us_conv_fwd": conv_us, "us_conv_dgrad": dgrad_us, "us_conv_wgrad": wgrad_us},
-        "wall_s_timed_region": t_wall,
+                   "rhs_evals_per_s": nfe_total / (ms_per_step / 1e3) * world},
+        "wall_s_timed_region": main["wall_s"],
     }
+    if parity is not None:
+        line["parity_check"] = parity
+    line.update(extras)
+    if "rot_ms" in main:
+        line["resident_rotating_inputs"] = {"value": world * per_gpu / (rot_ms / args.steps / 1e3), "unit": UNIT, "ms_per_step": rot_ms / args.steps,
+                                            "protocol": f"no L2 flush; {main['rot_pairs']} distinct (y0, dL/dz) pairs = {main['rot_pairs'] * main['rot_pair_bytes'] / 1e6:.0f} MB > L2, "
+                                                        "one per step; engine state and weights stay warm (the headline `value` flushes everything)"}
+    if "pieces" in main:
+        p = main["pieces"]
+        nz = int(np.prod(w.shape))
+        conv_flops = 2.0 * (per_gpu * 49) * 64 * 576
+        achieved_tf = conv_flops / (p["conv_fused_us"] * 1e-6) / 1e12
+        # one forward RHS eval = 2 convs; one augmented eval = 2 fwd + 2 dgrad + 2 wgrad
+        # (the two weight-gradient launches of an augmented eval run on a side branch, overlapped with the main chain: not counted here)
+        conv_share = ((fwd_stats[0] * 2 + bwd_stats[0] * 2) * p["conv_fused_us"] + bwd_stats[0] * 2 * p["dgrad_fused_us"]) / (ms_per_step * 1e3)
+        line["roofline"] = {
+            "bound": "tensor", "kernel": "k_conv3x3_tc<3,1,1> as launched in the step (BatchNorm-apply operand prologue + tcgen05 3xTF32 implicit-GEMM conv3x3, "
+                                         "M=6272 pixels N=64 K=576 + BatchNorm-statistics epilogue); the dgrad variant <3,2,2> is timed next to it",
+            "achieved": achieved_tf, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["tf_sust"],
+            "traffic": _conv_traffic_bytes(),
+            "peak_source": f"{peaks['src']} bf16 sustained (kernel runs inside a long step). The kernel issues 3 TF32 passes per product "
+                           "(TF32 peak = bf16/2), so fp32-faithful algorithmic flops can reach at most peak/6; latency-bound at this size (see DESIGN.md section 4)",
+            "algorithmic_flops_per_launch": conv_flops, "us_per_launch": p["conv_fused_us"], "us_per_launch_dgrad_variant": p["dgrad_fused_us"],
+            "us_bare_conv_kernel": p["conv_us"], "share_of_step": conv_share}
+        line["roofline_wgrad"] = {
+            "bound": "tensor", "kernel": "k_conv_wgrad_tc (tcgen05, MN-major operands, hi/lo stacked: one M128 N128 K8 MMA per tap and 8 pixels) + k_wgrad_reduce, timed back to back",
+            "achieved": conv_flops / (p["wgrad_us"] * 1e-6) / 1e12, "peak": peaks["tf_sust"], "unit": "TFLOP/s",
+            "frac": conv_flops / (p["wgrad_us"] * 1e-6) / 1e12 / peaks["tf_sust"], "us_per_launch_pair": p["wgrad_us"],
+            "note": "runs on a side branch of the adjoint evaluation (64 CTAs on purpose: leaves the other SMs to the main chain)"}
+        line["roofline_solver"] = {
+            "bound": "hbm", "kernel": "6x k_stage_combine + k_error_ctrl (one trial step, 160*N bytes)",
+            "n_fwd": nz, "us_fwd": p["pass_fwd_us"], "gbs_fwd": 160.0 * nz / (p["pass_fwd_us"] * 1e-6) / 1e9,
+            "n_aug": p["n_aug"], "us_aug": p["pass_aug_us"], "gbs_aug": 160.0 * p["n_aug"] / (p["pass_aug_us"] * 1e-6) / 1e9,
+            "n_hbm": 1 << 26, "us_hbm": p["pass_big_us"], "achieved": 160.0 * (1 << 26) / (p["pass_big_us"] * 1e-6) / 1e9,
+            "peak": peaks["hbm"], "unit": "GB/s", "frac": 160.0 * (1 << 26) / (p["pass_big_us"] * 1e-6) / 1e9 / peaks["hbm"],
+            "frac_of_nominal_8TBs": 160.0 * (1 << 26) / (p["pass_big_us"] * 1e-6) / 1e9 / 8000.0,
+            "note": "fwd/aug sizes are L2-resident (algorithmic GB/s can exceed HBM peak); n_hbm is the HBM-resident measurement"}
+        line["solver"].update({"us_per_rhs_fwd": p["rhs_us"], "us_per_rhs_aug": p["aug_us"], "us_conv_fwd": p["conv_us"], "us_conv_dgrad": p["dgrad_us"],
+                               "us_conv_wgrad": p["wgrad_us"]})
+    elif "rhs_us" in main:
+        fl = 2 * 2.0 * w.shape[0] * w.shape[1] * w.shape[1]
+        tf = fl / (main["rhs_us"] * 1e-6) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "k_gemm_tc x2 + bias/activation kernels = one f(z)", "achieved": tf, "peak": peaks["tf_burst"],
+                            "unit": "TFLOP/s", "frac": tf / peaks["tf_burst"], "traffic": None}
+    if other:
+        line["configs"] = other
     print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        B.dist.destroy_process_group()
 
 
 def main():
@@ -445,7 +662,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--config", default="mnist", choices=sorted(CONFIG_TEXT), help="which BASELINE.json configuration is the headline of this line (default: configs[1])")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--quick", action="store_true", help="headline only: no parity-mode / fast-TF32 / other-config / strong-scaling extras")
     ap.add_argument("--flags", type=int, default=0, help="N4J_FLAG_* bits for the engine (2 = host-driven step loop, which is "
                     "what ncu can see: kernels inside a CUDA graph with a conditional node are not profilable)")
     args = ap.parse_args()

@@ -401,7 +401,8 @@ class OdeVertexImpl:
         self._L.node4j_get_step_log(self._h, buf, n)
         m = min(n, len(buf))
         return {"t": np.array([buf[i].t for i in range(m)], dtype=np.float32), "h": np.array([buf[i].h for i in range(m)], dtype=np.float32),
-                "err": np.array([buf[i].err for i in range(m)], dtype=np.float32), "accepted": np.array([buf[i].accepted for i in range(m)])}
+                "err": np.array([buf[i].err for i in range(m)], dtype=np.float32), "accepted": np.array([buf[i].accepted for i in range(m)]),
+                "solve": np.array([buf[i].solve for i in range(m)])}
 
     def rhs(self, z, t: float = 0.0):
         z = _as_f32(z)

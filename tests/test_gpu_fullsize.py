@@ -1,5 +1,7 @@
-"""GPU tests at BASELINE.json's FULL sizes, where the CPU oracle would take minutes: size-independent properties of the path
-(round trips, equivariance, identities between the reference's own code paths, determinism, counters)."""
+"""GPU tests at BASELINE.json's FULL sizes.  Config #2 (the headline, batch 128) is compared with the CPU oracle directly — one
+forward + adjoint of the oracle takes about a second on the GPU box's cores — in parity mode (rtol 1e-4, exact counts) and in the
+default (benchmarked) mode; the larger configurations use size-independent properties of the path (round trips, equivariance,
+identities between the reference's own code paths, determinism, counters)."""
 import numpy as np
 import pytest
 
@@ -45,6 +47,67 @@ def test_mnist_full_counters_determinism_and_modes():
     assert np.isfinite(a["grad"]).all() and np.abs(a["grad"]).max() > 0
     C = 64
     assert not a["grad"][2 * C:4 * C].any()            # BatchNorm mean/var slots are not gradients
+
+
+_ORACLE_FULL = {}
+
+
+def _oracle_full(eps):
+    """One oracle run of config #2 at batch 128, shared by the tests below (same inputs, same epsilon)."""
+    if "o" not in _ORACLE_FULL:
+        _ORACLE_FULL["o"] = H.run_oracle(W.mnist_block(), eps)
+        _ORACLE_FULL["eps"] = eps
+    assert np.array_equal(_ORACLE_FULL["eps"], eps)
+    return _ORACLE_FULL["o"]
+
+
+def _deviation(a, b, rtol=1e-4, atol_scale=1e-5):
+    """(relative L2, fraction of elements outside rtol + atol_scale * max|b|, worst absolute error / max|b|)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    err = np.abs(a - b)
+    tol = atol_scale * np.abs(b).max() + rtol * np.abs(b)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b)), float((err > tol).mean()), float(err.max() / np.abs(b).max())
+
+
+def test_mnist_full_parity_mode_matches_oracle():
+    """The headline configuration at ITS OWN size (z = [128,64,7,7]) against the oracle, parity mode (N4J_FLAG_EXACT_CONTRACTIONS):
+    accepted / rejected counts and nfe exact, final state, dL/dy0 and dL/dtheta within rtol 1e-4 (north_star's tolerance)."""
+    w = W.mnist_block()
+    r = H.run_cuda(w, flags=_lib.FLAG_EXACT_CONTRACTIONS)
+    o = _oracle_full(r["eps"])
+    assert r["fwd_stats"] == o["fwd_stats"] and r["bwd_stats"] == o["bwd_stats"], (r["fwd_stats"], o["fwd_stats"], r["bwd_stats"], o["bwd_stats"])
+    assert np.array_equal(r["fwd_log"]["accepted"], o["fwd_log"].accepted) and np.array_equal(r["bwd_log"]["accepted"], o["bwd_log"].accepted)
+    np.testing.assert_allclose(r["fwd_log"]["h"], o["fwd_log"].h, rtol=1e-5)
+    np.testing.assert_allclose(r["bwd_log"]["h"], o["bwd_log"].h, rtol=1e-5)
+    for k in ("out", "dy0", "grad"):
+        H.assert_close(r[k], o[k], 1e-4, 1e-5 * np.abs(o[k]).max(), k)
+        print(k, "parity mode: rel-L2 %.2e, outside rtol 1e-4: %.2e, worst/max %.2e" % _deviation(r[k], o[k]))
+
+
+def test_mnist_full_default_mode_matches_oracle():
+    """Same comparison for the DEFAULT mode — the one bench.py times (tcgen05 3xTF32 convolutions and weight gradients, fp32
+    accumulation): counts exact, the step-size sequences agree to 1e-4, the final state within rtol 1e-4.  The gradients of a
+    BatchNorm+ReLU block are not a smooth function of the state (ReLU masks enter BatchNorm's backward sums; see
+    tests/test_oracle_golden.py::test_relu_bn_adjoint_sensitivity), so they are reported as relative L2 and as the fraction of
+    elements outside rtol 1e-4, with bounds far below the 1e-2 the small-batch tests allow: 128 rows per statistic average the mask
+    flips out."""
+    w = W.mnist_block()
+    r = H.run_cuda(w)
+    o = _oracle_full(r["eps"])
+    assert r["fwd_stats"] == o["fwd_stats"] and r["bwd_stats"] == o["bwd_stats"], (r["fwd_stats"], o["fwd_stats"], r["bwd_stats"], o["bwd_stats"])
+    assert np.array_equal(r["fwd_log"]["accepted"], o["fwd_log"].accepted) and np.array_equal(r["bwd_log"]["accepted"], o["bwd_log"].accepted)
+    np.testing.assert_allclose(r["fwd_log"]["h"], o["fwd_log"].h, rtol=1e-4)
+    np.testing.assert_allclose(r["bwd_log"]["h"], o["bwd_log"].h, rtol=1e-4)
+    H.assert_close(r["out"], o["out"], 1e-4, 1e-5 * np.abs(o["out"]).max(), "out")
+    for k, l2_max, frac_max in (("dy0", DEFAULT_MODE_REL_L2["dy0"], DEFAULT_MODE_FRAC["dy0"]), ("grad", DEFAULT_MODE_REL_L2["grad"], DEFAULT_MODE_FRAC["grad"])):
+        l2, frac, worst = _deviation(r[k], o[k])
+        print(f"{k} default mode: rel-L2 {l2:.2e}, outside rtol 1e-4: {frac:.2e}, worst/max {worst:.2e}")
+        assert l2 < l2_max and frac < frac_max, (k, l2, frac, worst)
+
+
+# measured on B200 (r02); the bounds leave a factor of ~3 over the measured values
+DEFAULT_MODE_REL_L2 = {"dy0": 2e-3, "grad": 2e-3}
+DEFAULT_MODE_FRAC = {"dy0": 0.05, "grad": 0.05}
 
 
 def test_mnist_full_time_round_trip():

@@ -151,7 +151,7 @@ def test_workload_shapes():
 
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU leg of the driver's contract) prints ONE JSON line with the agreed keys; it must not
-    need a GPU.  One bounded step of the oracle port on a 32-row slice (a few seconds)."""
+    need a GPU.  One step of the oracle port on the FULL 128-row minibatch (a few seconds on the host cores)."""
     import json
     import subprocess
     import sys
