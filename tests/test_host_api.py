@@ -213,3 +213,60 @@ def test_output_type_inference_mirrors_reference():
     with pytest.raises(ValueError, match="must match output shape"):
         widening.getOutputType(0, ff)
     assert FixedStep(solver, [0, 1]).nrofTimeInputs() == 0 and InputStep(solver, 1).nrofTimeInputs() == 1
+
+
+def test_java_shim_matches_header():
+    """java/src/main/java/.../Node4j.java (the Panama binding a neuralODE4j maintainer adds; not compilable here: no JDK) must agree
+    with include/node4j.h: every struct layout field by field (name, order, width) and every downcall handle's symbol and arity."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "node4j.h")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    java = open(os.path.join(ROOT, "java", "src", "main", "java", "ode", "vertex", "impl", "helper", "nativeb200", "Node4j.java")).read()
+    jtype = {"int32_t": "JAVA_INT", "uint32_t": "JAVA_INT", "int64_t": "JAVA_LONG", "float": "JAVA_FLOAT", "double": "JAVA_DOUBLE"}
+    pairs = {"n4j_layer_desc": "LAYER", "n4j_graph_desc": "GRAPH", "n4j_solver_cfg": "CFG", "n4j_stats": "STATS", "n4j_step_rec": "STEP_REC"}
+    for cname, jname in pairs.items():
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr_nc, flags=re.S).group(1)
+        want = []
+        for decl in [d.strip() for d in body.split(";") if d.strip()]:
+            m = re.match(r"(const\s+)?(\w+)\s*(\*?)\s*(.+)$", decl)
+            ctype, ptr, names = m.group(2), m.group(3), m.group(4)
+            for nm in [x.strip() for x in names.split(",")]:
+                arr = re.match(r"(\w+)\[(\d+)\]", nm)
+                if ptr or nm.startswith("*"):
+                    want.append((nm.lstrip("* "), "ADDRESS"))
+                elif arr:
+                    want.append((arr.group(1), "SEQ%s:%s" % (arr.group(2), jtype[ctype])))
+                else:
+                    want.append((nm, jtype[ctype]))
+        jbody = re.search(r"StructLayout %s = MemoryLayout\.structLayout\((.*?)\);" % jname, java, flags=re.S).group(1)
+        got = []
+        for m in re.finditer(r"(MemoryLayout\.sequenceLayout\((\d+), (\w+)\)|\b(JAVA_\w+|ADDRESS))\.withName\(\"(\w+)\"\)", jbody):
+            got.append((m.group(5), "SEQ%s:%s" % (m.group(2), m.group(3)) if m.group(2) else m.group(4)))
+        assert got == want, (cname, got, want)
+    # downcalls: symbol exists in the header with the same number of parameters
+    for m in re.finditer(r"h\(\"(node4j_\w+)\",\s*FunctionDescriptor\.of\(([^;]*?)\)\);", java, flags=re.S):
+        sym, desc = m.group(1), [x.strip() for x in m.group(2).split(",") if x.strip()]
+        proto = re.search(r"\b%s\s*\(([^)]*)\)\s*;" % sym, hdr_nc, flags=re.S)
+        assert proto, f"{sym} is not declared in node4j.h"
+        params = [p.strip() for p in proto.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(desc) - 1 == len(params), (sym, desc, params)
+        for d, p in zip(desc[1:], params):
+            if "*" in p:
+                assert d == "ADDRESS", (sym, p, d)
+            else:
+                assert d == jtype[p.split()[0] if p.split()[0] != "const" else p.split()[1]], (sym, p, d)
+    assert "ABI_VERSION = %d" % int(re.search(r"#define N4J_ABI_VERSION (\d+)", hdr).group(1)) in java
+    # status codes and enums used by the shim carry the header's values
+    for name in ("LAYER_DENSE", "LAYER_CONV3X3", "LAYER_BATCHNORM", "LAYER_ACTIVATION", "LAYER_TIME_CONCAT", "ACT_RELU", "ACT_ELU", "ACT_TANH",
+                 "ERR_INVALID_ARGUMENT", "ERR_ILLEGAL_STATE", "ERR_UNSUPPORTED", "ERR_CUDA", "ERR_MAX_STEPS", "ERR_COMM",
+                 "TIMEGRAD_ZERO", "TIMEGRAD_CALC"):
+        hv = int(re.search(r"N4J_%s = (\d+)" % name, hdr_nc).group(1))
+        jv = int(re.search(r"\b%s = (\d+)" % name, java).group(1))
+        assert hv == jv, name
+    # byte offsets the helper writes the structs at (NativeOdeHelper.create) equal the ctypes layout of the same structs
+    from neuralode4j_b200 import _lib
+    helper = open(os.path.join(ROOT, "java", "src", "main", "java", "ode", "vertex", "impl", "helper", "nativeb200", "NativeOdeHelper.java")).read()
+    assert _lib.LayerDesc.has_bias.offset == 24 and _lib.LayerDesc.eps.offset == 28 and "s.set(JAVA_FLOAT, 28, l.eps)" in helper
+    assert _lib.GraphDesc.layers.offset == 40 and "g.set(ADDRESS, 40, layers)" in helper
+    assert _lib.SolverCfg.order.offset == 56 and _lib.SolverCfg.flags.offset == 60 and _lib.SolverCfg.max_trials.offset == 64
+    assert ctypes.sizeof(_lib.StepRec) == 20 and "i * 20 + 16" in helper
