@@ -224,6 +224,33 @@ int32_t node4j_bench_piece(n4j_handle* h, int32_t what, int32_t iters, float* us
  * events around calls or order its own work after them. */
 int32_t node4j_get_stream(n4j_handle* h, void** stream);
 
+/* ---- the network around the ODE block -------------------------------------------------------------
+ * One full training step of the reference's MNIST ODE-net (examples/mnist/OdeNetModel.java:60-88) on the device: ResBlockStem
+ * (examples/mnist/ResBlockStem.java:25-48), the OdeVertex above, Output (examples/mnist/Output.java:27-35: BN-ReLU, global average
+ * pooling, Dense(10) softmax + LossMCXENT), gradients divided by the minibatch size, Nesterovs(momentum) and the BatchNorm
+ * running-statistics update — what ComputationGraph.fit(DataSet) does for that model.  `params` / `updater_state` are the model's
+ * flat vectors in DL4J order (what ModelSerializer stores as coefficients.bin / updaterState.bin; see neuralode4j_b200/dl4j_zip.py),
+ * host or device pointers, updated in place.  images [B,1,28,28], labels one-hot [B,10]. */
+typedef struct n4j_net n4j_net;
+typedef struct n4j_net_desc {
+    int32_t batch;
+    int32_t channels;      /* nrofKernels: 64 in the reference (examples/mnist/OdeNetModel.java:40) */
+    n4j_solver_cfg solver; /* of the ODE block */
+    float t0, t1;          /* FixedStep time of the block: 0, 1 (OdeNetModel.java:86) */
+} n4j_net_desc;
+int32_t node4j_net_create(const n4j_net_desc* desc, int32_t device, n4j_net** out);
+int32_t node4j_net_destroy(n4j_net* net);
+int64_t node4j_net_num_params(const n4j_net* net);
+/* offset and length of the ODE block's slice inside the flat vectors */
+int32_t node4j_net_ode_slice(const n4j_net* net, int64_t* offset, int64_t* length);
+/* score = LossMCXENT / B of the minibatch BEFORE the update; grad_out (optional, [num_params]) receives the gradient view as the
+ * updater saw it (sums over the minibatch; BatchNorm mean/var slots = (running - batch) * (1 - decay)). */
+int32_t node4j_net_train_step(n4j_net* net, float* params, float* updater_state, const float* images, const float* labels, float lr,
+                              float momentum, float* score, float* grad_out, n4j_stats* ode_forward, n4j_stats* ode_backward);
+/* ComputationGraph.output: probabilities [B,10].  train != 0 uses batch statistics in the outer BatchNorm layers (what fit sees),
+ * train == 0 their running statistics; the ODE block always runs in training mode (SingleStep.java:37). */
+int32_t node4j_net_output(n4j_net* net, const float* params, const float* images, float* probs, int32_t train);
+
 #ifdef __cplusplus
 }
 #endif

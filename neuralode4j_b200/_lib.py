@@ -23,6 +23,7 @@ EXPORTS = [
     "node4j_num_params", "node4j_num_real_params", "node4j_state_len", "node4j_bind_params", "node4j_forward",
     "node4j_backward", "node4j_get_step_log", "node4j_rhs", "node4j_rhs_vjp", "node4j_rhs_vjp_time", "node4j_error_norm",
     "node4j_comm_init", "node4j_comm_export", "node4j_bench_solver_pass", "node4j_bench_piece", "node4j_get_stream",
+    "node4j_net_create", "node4j_net_destroy", "node4j_net_num_params", "node4j_net_ode_slice", "node4j_net_train_step", "node4j_net_output",
 ]
 BENCH_RHS_FWD, BENCH_RHS_AUG, BENCH_CONV_FWD, BENCH_CONV_DGRAD, BENCH_CONV_WGRAD, BENCH_CONV_FWD_FUSED, BENCH_CONV_DGRAD_FUSED = 1, 2, 3, 4, 5, 6, 7
 
@@ -40,6 +41,10 @@ class SolverCfg(C.Structure):
     _fields_ = [("abs_tol", C.c_double), ("rel_tol", C.c_double), ("min_step", C.c_double), ("max_step", C.c_double),
                 ("safety", C.c_double), ("max_growth", C.c_double), ("min_reduction", C.c_double),
                 ("order", C.c_int32), ("flags", C.c_uint32), ("max_trials", C.c_int64)]
+
+
+class NetDesc(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("channels", C.c_int32), ("solver", SolverCfg), ("t0", C.c_float), ("t1", C.c_float)]
 
 
 class Stats(C.Structure):
@@ -113,6 +118,18 @@ def load():
     L.node4j_bench_piece.argtypes = [vp, i32, i32, C.POINTER(f32)]
     L.node4j_get_stream.restype = i32
     L.node4j_get_stream.argtypes = [vp, C.POINTER(vp)]
+    L.node4j_net_create.restype = i32
+    L.node4j_net_create.argtypes = [C.POINTER(NetDesc), i32, C.POINTER(vp)]
+    L.node4j_net_destroy.restype = i32
+    L.node4j_net_destroy.argtypes = [vp]
+    L.node4j_net_num_params.restype = i64
+    L.node4j_net_num_params.argtypes = [vp]
+    L.node4j_net_ode_slice.restype = i32
+    L.node4j_net_ode_slice.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.node4j_net_train_step.restype = i32
+    L.node4j_net_train_step.argtypes = [vp, vp, vp, vp, vp, f32, f32, C.POINTER(f32), vp, C.POINTER(Stats), C.POINTER(Stats)]
+    L.node4j_net_output.restype = i32
+    L.node4j_net_output.argtypes = [vp, vp, vp, vp, i32]
     if L.node4j_abi_version() != 2:
         raise RuntimeError("libnode4j_b200.so ABI version mismatch")
     _lib = L

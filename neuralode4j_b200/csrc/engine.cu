@@ -7,6 +7,7 @@
 //   vertex/impl/helper/backward/BackpropagateAdjoint.java:63-143                   -> Engine::enqueue_rhs_aug
 //   solve/impl/AdaptiveRungeKuttaSolver.java:107-181                               -> Engine::run_solve (+ kernels)
 #include "engine.cuh"
+#include "outer_net.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -1771,6 +1772,44 @@ int32_t node4j_bench_piece(n4j_handle* h, int32_t what, int32_t iters, float* us
 }
 int32_t node4j_get_stream(n4j_handle* h, void** stream) {
     return guarded([&] { *stream = (void*)h->eng->stream(); });
+}
+
+// ---- the network around the ODE block (outer_net.cuh) ----
+struct n4j_net {
+    std::unique_ptr<n4j::OuterNet> net;
+};
+int32_t node4j_net_create(const n4j_net_desc* d, int32_t device, n4j_net** out) {
+    return guarded([&] {
+        if (!d || !out) throw n4j::Error{N4J_ERR_INVALID_ARGUMENT, "null argument"};
+        int n = 0;
+        if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) { cudaGetLastError(); throw n4j::Error{N4J_ERR_CUDA, "no usable CUDA device: the node4j engine has no CPU fallback"}; }
+        std::unique_ptr<n4j_net> h(new n4j_net);
+        h->net.reset(new n4j::OuterNet(d->batch, d->channels, d->solver, d->t0, d->t1, device));
+        *out = h.release();
+    });
+}
+int32_t node4j_net_destroy(n4j_net* net) {
+    return guarded([&] { delete net; });
+}
+int64_t node4j_net_num_params(const n4j_net* net) { return net ? net->net->num_params() : -1; }
+int32_t node4j_net_ode_slice(const n4j_net* net, int64_t* offset, int64_t* length) {
+    return guarded([&] {
+        if (!net || !offset || !length) throw n4j::Error{N4J_ERR_INVALID_ARGUMENT, "null argument"};
+        *offset = net->net->ode_offset(); *length = net->net->ode_num_params();
+    });
+}
+int32_t node4j_net_train_step(n4j_net* net, float* params, float* updater_state, const float* images, const float* labels, float lr, float momentum,
+                              float* score, float* grad_out, n4j_stats* ode_forward, n4j_stats* ode_backward) {
+    return guarded([&] {
+        if (!net || !params || !updater_state || !images || !labels) throw n4j::Error{N4J_ERR_INVALID_ARGUMENT, "null argument"};
+        net->net->train_step(params, updater_state, images, labels, lr, momentum, score, grad_out, ode_forward, ode_backward);
+    });
+}
+int32_t node4j_net_output(n4j_net* net, const float* params, const float* images, float* probs, int32_t train) {
+    return guarded([&] {
+        if (!net || !params || !images || !probs) throw n4j::Error{N4J_ERR_INVALID_ARGUMENT, "null argument"};
+        net->net->output(params, images, probs, train);
+    });
 }
 
 }  // extern "C"

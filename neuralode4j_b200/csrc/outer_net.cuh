@@ -1,0 +1,521 @@
+// outer_net.cuh — the network AROUND the ODE block, so that one full training step of the reference's MNIST ODE-net runs on the
+// device ("the callers either side of the path").
+//
+// Replaces, for the model of examples/mnist/OdeNetModel.java:60-88, what DL4J's ComputationGraph.fit does around OdeVertex:
+//   stem     examples/mnist/ResBlockStem.java:25-48   inputConv 3x3 (Truncate, bias) -> 2 x { BN-ReLU ; 1x1 stride 2  +  3x3 stride 2
+//                                                     Same ReLU -> BN-ReLU -> 3x3 Same }                        28 -> 26 -> 13 -> 7
+//   block    ode/vertex/impl/OdeVertex.java:111-140   Engine::forward / Engine::backward (the hot path, engine.cu)
+//   output   examples/mnist/Output.java:27-35         BN-ReLU -> GlobalPooling(AVG) -> Dense(10) softmax + LossMCXENT
+//   updater  examples/mnist/LayerUtil.java:30-47      Nesterovs(momentum) on the flat gradient view divided by the minibatch size;
+//            BatchNorm running mean / var through the gradient view with a NoOp updater (OdeGraphHelper.java:105-119)
+// Layer arithmetic is DL4J's (third party in the reference); conventions as restated in oracle/outer_oracle.py, which this file is
+// checked against (tests/test_outer_net.py).  Tensors are NCHW fp32; every reduction accumulates exact fp32 products in double and
+// rounds once, elementwise expressions keep the oracle's order (no FMA contraction), so the two agree to rounding.
+// These layers are NOT the hot path (about 13 GFLOP per step next to the ODE block's ~250): plain direct kernels, no tensor cores.
+#pragma once
+
+#include <algorithm>
+#include <memory>
+#include <vector>
+
+#include "engine.cuh"
+
+namespace n4j {
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------------------------
+struct ConvShape {
+    int B, Ci, H, W, Co, K, S, Ho, Wo, pt, pl;
+};
+
+inline ConvShape make_conv_shape(int B, int Ci, int H, int W, int Co, int K, int S, bool same) {
+    ConvShape c{B, Ci, H, W, Co, K, S, 0, 0, 0, 0};
+    if (same) {
+        c.Ho = (H + S - 1) / S; c.Wo = (W + S - 1) / S;
+        const int th = std::max((c.Ho - 1) * S + K - H, 0), tw = std::max((c.Wo - 1) * S + K - W, 0);
+        c.pt = th / 2; c.pl = tw / 2;
+    } else {
+        c.Ho = (H - K) / S + 1; c.Wo = (W - K) / S + 1;
+    }
+    return c;
+}
+
+// y[b,co,oh,ow] = act( (float)sum_{ci,kh,kw} x[b,ci,oh*S+kh-pt,ow*S+kw-pl] * w[co,ci,kh,kw]  + bias[co] )
+__global__ void __launch_bounds__(256) k_outer_conv_fwd(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                         float* __restrict__ y, ConvShape c, int relu) {
+    const long long n = (long long)c.B * c.Co * c.Ho * c.Wo;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int ow = (int)(i % c.Wo), oh = (int)((i / c.Wo) % c.Ho), co = (int)((i / ((long long)c.Wo * c.Ho)) % c.Co), b = (int)(i / ((long long)c.Wo * c.Ho * c.Co));
+        double acc = 0.0;
+        for (int ci = 0; ci < c.Ci; ++ci) {
+            const float* xb = x + ((long long)b * c.Ci + ci) * c.H * c.W;
+            const float* wb = w + ((long long)co * c.Ci + ci) * c.K * c.K;
+            for (int kh = 0; kh < c.K; ++kh) {
+                const int ih = oh * c.S + kh - c.pt;
+                if (ih < 0 || ih >= c.H) continue;
+                for (int kw = 0; kw < c.K; ++kw) {
+                    const int iw = ow * c.S + kw - c.pl;
+                    if (iw < 0 || iw >= c.W) continue;
+                    acc += (double)xb[ih * c.W + iw] * (double)wb[kh * c.K + kw];
+                }
+            }
+        }
+        float v = (float)acc;
+        if (bias) v = __fadd_rn(v, bias[co]);
+        if (relu && !(v > 0.f)) v = 0.f;
+        y[i] = v;
+    }
+}
+
+// dx[b,ci,h,w] = (float)sum_{co,kh,kw} dz[b,co,oh,ow] * w[co,ci,kh,kw],  oh*S + kh - pt = h;  dz = relu ? (y > 0 ? dy : 0) : dy
+__global__ void __launch_bounds__(256) k_outer_conv_dgrad(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ w,
+                                                           float* __restrict__ dx, ConvShape c, int relu) {
+    const long long n = (long long)c.B * c.Ci * c.H * c.W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int iw = (int)(i % c.W), ih = (int)((i / c.W) % c.H), ci = (int)((i / ((long long)c.W * c.H)) % c.Ci), b = (int)(i / ((long long)c.W * c.H * c.Ci));
+        double acc = 0.0;
+        for (int kh = 0; kh < c.K; ++kh) {
+            const int th = ih + c.pt - kh;
+            if (th < 0 || th % c.S) continue;
+            const int oh = th / c.S;
+            if (oh >= c.Ho) continue;
+            for (int kw = 0; kw < c.K; ++kw) {
+                const int tw = iw + c.pl - kw;
+                if (tw < 0 || tw % c.S) continue;
+                const int ow = tw / c.S;
+                if (ow >= c.Wo) continue;
+                for (int co = 0; co < c.Co; ++co) {
+                    const long long o = (((long long)b * c.Co + co) * c.Ho + oh) * c.Wo + ow;
+                    float g = dy[o];
+                    if (relu && !(y[o] > 0.f)) g = 0.f;
+                    acc += (double)g * (double)w[(((long long)co * c.Ci + ci) * c.K + kh) * c.K + kw];
+                }
+            }
+        }
+        dx[i] = (float)acc;
+    }
+}
+
+// One block per (co, ci): dw[co,ci,kh,kw] = (float)sum_{b,oh,ow} dz[b,co,oh,ow] * x[b,ci,oh*S+kh-pt,ow*S+kw-pl]; blocks with ci == 0 also
+// produce db[co] = (float)sum dz.  Per-thread double partials, combined by a fixed shared-memory tree (deterministic).
+__global__ void __launch_bounds__(128) k_outer_conv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
+                                                           float* __restrict__ dw, float* __restrict__ db, ConvShape c, int relu) {
+    const int co = blockIdx.x / c.Ci, ci = blockIdx.x % c.Ci;
+    double acc[10];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) acc[k] = 0.0;
+    const int per = c.Ho * c.Wo;
+    const long long n = (long long)c.B * per;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const int b = (int)(i / per), r = (int)(i % per), oh = r / c.Wo, ow = r % c.Wo;
+        const long long o = ((long long)b * c.Co + co) * per + r;
+        float g = dy[o];
+        if (relu && !(y[o] > 0.f)) g = 0.f;
+        if (g == 0.f) continue;
+        acc[9] += (double)g;
+        const float* xb = x + ((long long)b * c.Ci + ci) * c.H * c.W;
+        for (int kh = 0; kh < c.K; ++kh) {
+            const int ih = oh * c.S + kh - c.pt;
+            if (ih < 0 || ih >= c.H) continue;
+            for (int kw = 0; kw < c.K; ++kw) {
+                const int iw = ow * c.S + kw - c.pl;
+                if (iw < 0 || iw >= c.W) continue;
+                acc[kh * c.K + kw] += (double)g * (double)xb[ih * c.W + iw];
+            }
+        }
+    }
+    __shared__ double sm[10][128];
+#pragma unroll
+    for (int k = 0; k < 10; ++k) sm[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int s = 64; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + s];
+        }
+        __syncthreads();
+    }
+    if ((int)threadIdx.x < c.K * c.K) dw[((long long)co * c.Ci + ci) * c.K * c.K + threadIdx.x] = (float)sm[threadIdx.x][0];
+    if (db && ci == 0 && threadIdx.x == 0) db[co] = (float)sm[9][0];
+}
+
+// BatchNorm (training), NCHW, one block per channel.  st: [mean | invstd | batch var] x C
+__global__ void __launch_bounds__(256) k_outer_bn_fwd(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float* __restrict__ y, float* __restrict__ st, int B, int C, int HW, float eps, int relu) {
+    const int ch = blockIdx.x;
+    double s1 = 0.0, s2 = 0.0;
+    const long long n = (long long)B * HW;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = (double)x[((i / HW) * C + ch) * HW + i % HW];
+        s1 += v; s2 += v * v;
+    }
+    double r[2] = {s1, s2};
+    block_sum<2>(r);
+    __shared__ float s_m, s_i;
+    if (threadIdx.x == 0) {
+        const double m = r[0] / (double)n;
+        double var = r[1] / (double)n - m * m;
+        if (var < 0) var = 0;
+        s_m = (float)m; s_i = (float)(1.0 / sqrt(var + (double)eps));
+        st[ch] = s_m; st[C + ch] = s_i; st[2 * C + ch] = (float)var;
+    }
+    __syncthreads();
+    const float m = s_m, inv = s_i, ga = gamma[ch], be = beta[ch];
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long o = ((i / HW) * C + ch) * HW + i % HW;
+        float v = __fadd_rn(__fmul_rn(ga, __fmul_rn(__fsub_rn(x[o], m), inv)), be);
+        if (relu && !(v > 0.f)) v = 0.f;
+        y[o] = v;
+    }
+}
+// inference: y = act(gamma * (x - running mean) / sqrt(running var + eps) + beta)
+__global__ void __launch_bounds__(256) k_outer_bn_infer(const float* __restrict__ x, const float* __restrict__ bn /*gamma,beta,mean,var*/, float* __restrict__ y,
+                                                         long long n, int C, int HW, float eps, int relu) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)((i / HW) % C);
+        const float inv = (float)(1.0 / sqrt((double)bn[3 * C + ch] + (double)eps));
+        float v = __fadd_rn(__fmul_rn(bn[ch], __fmul_rn(__fsub_rn(x[i], bn[2 * C + ch]), inv)), bn[C + ch]);
+        if (relu && !(v > 0.f)) v = 0.f;
+        y[i] = v;
+    }
+}
+// backward; also the running-statistics "gradient" (run - batch) * (1 - decay) into the mean / var slots of the gradient view
+__global__ void __launch_bounds__(256) k_outer_bn_bwd(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ dy,
+                                                       const float* __restrict__ bn /*gamma,beta,mean,var (params)*/, const float* __restrict__ st,
+                                                       float* __restrict__ dx, float* __restrict__ gbn /*gradient view of this layer*/, int B, int C, int HW,
+                                                       int relu, float one_minus_decay) {
+    const int ch = blockIdx.x;
+    const float m = st[ch], inv = st[C + ch];
+    const long long n = (long long)B * HW;
+    double s1 = 0.0, s2 = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long o = ((i / HW) * C + ch) * HW + i % HW;
+        float g = dy[o];
+        if (relu && !(y[o] > 0.f)) g = 0.f;
+        const float xh = __fmul_rn(__fsub_rn(x[o], m), inv);
+        s1 += (double)g; s2 += (double)g * (double)xh;
+    }
+    double r[2] = {s1, s2};
+    block_sum<2>(r);
+    __shared__ float s_m1, s_m2;
+    if (threadIdx.x == 0) {
+        gbn[ch] = (float)r[1]; gbn[C + ch] = (float)r[0];
+        gbn[2 * C + ch] = __fmul_rn(__fsub_rn(bn[2 * C + ch], m), one_minus_decay);
+        gbn[3 * C + ch] = __fmul_rn(__fsub_rn(bn[3 * C + ch], st[2 * C + ch]), one_minus_decay);
+        s_m1 = (float)(r[0] / (double)n); s_m2 = (float)(r[1] / (double)n);
+    }
+    __syncthreads();
+    const float m1 = s_m1, m2 = s_m2, k = __fmul_rn(bn[ch], inv);
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long o = ((i / HW) * C + ch) * HW + i % HW;
+        float g = dy[o];
+        if (relu && !(y[o] > 0.f)) g = 0.f;
+        const float xh = __fmul_rn(__fsub_rn(x[o], m), inv);
+        dx[o] = __fmul_rn(k, __fsub_rn(__fsub_rn(g, m1), __fmul_rn(xh, m2)));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_outer_add(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) o[i] = __fadd_rn(a[i], b[i]);
+}
+
+// global average pooling: one warp per (b, c)
+__global__ void __launch_bounds__(256) k_outer_pool_fwd(const float* __restrict__ x, float* __restrict__ p, int BC, int HW) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= BC) return;
+    double s = 0.0;
+    for (int i = lane; i < HW; i += 32) s += (double)x[(long long)w * HW + i];
+    s = warp_sum(s);
+    if (lane == 0) p[w] = (float)(s / (double)HW);
+}
+__global__ void __launch_bounds__(256) k_outer_pool_bwd(const float* __restrict__ dp, float* __restrict__ dx, long long n, int HW) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dx[i] = __fdiv_rn(dp[i / HW], (float)HW);
+}
+
+// OutputLayer: logits = pool W + b (W [C,10] f-order), softmax, LossMCXENT score; one thread per example, then one block reduces the score
+__global__ void __launch_bounds__(256) k_outer_output_fwd(const float* __restrict__ pool, const float* __restrict__ W, const float* __restrict__ bias,
+                                                           const float* __restrict__ labels, float* __restrict__ probs, double* __restrict__ score_parts, int B, int C) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float lg[10];
+    float mx = -INFINITY;
+    for (int j = 0; j < 10; ++j) {
+        double acc = 0.0;
+        for (int c = 0; c < C; ++c) acc += (double)pool[(long long)b * C + c] * (double)W[c + (long long)C * j];
+        lg[j] = __fadd_rn((float)acc, bias[j]);
+        mx = fmaxf(mx, lg[j]);
+    }
+    double se = 0.0;
+    for (int j = 0; j < 10; ++j) { lg[j] = expf(__fsub_rn(lg[j], mx)); se += (double)lg[j]; }
+    const float den = (float)se;
+    double sc = 0.0;
+    for (int j = 0; j < 10; ++j) {
+        const float p = __fdiv_rn(lg[j], den);
+        probs[b * 10 + j] = p;
+        if (labels) {
+            double pc = (double)p;
+            pc = pc < 1e-10 ? 1e-10 : (pc > 1.0 - 1e-10 ? 1.0 - 1e-10 : pc);
+            sc -= (double)labels[b * 10 + j] * log(pc);
+        }
+    }
+    if (score_parts) score_parts[b] = sc;
+}
+// backward of the output layer: single block (10 x C weights, B examples)
+__global__ void __launch_bounds__(256) k_outer_output_bwd(const float* __restrict__ pool, const float* __restrict__ W, const float* __restrict__ probs,
+                                                           const float* __restrict__ labels, const double* __restrict__ score_parts, float* __restrict__ dW,
+                                                           float* __restrict__ db, float* __restrict__ dpool, float* __restrict__ score, int B, int C) {
+    for (int i = threadIdx.x; i < C * 10; i += blockDim.x) {       // dW[c + C*j] = sum_b pool[b,c] * (p - y)[b,j]
+        const int c = i % C, j = i / C;
+        double acc = 0.0;
+        for (int b = 0; b < B; ++b) acc += (double)pool[(long long)b * C + c] * (double)__fsub_rn(probs[b * 10 + j], labels[b * 10 + j]);
+        dW[i] = (float)acc;
+    }
+    for (int j = threadIdx.x; j < 10; j += blockDim.x) {
+        double acc = 0.0;
+        for (int b = 0; b < B; ++b) acc += (double)__fsub_rn(probs[b * 10 + j], labels[b * 10 + j]);
+        db[j] = (float)acc;
+    }
+    for (int i = threadIdx.x; i < B * C; i += blockDim.x) {        // dpool[b,c] = sum_j (p - y)[b,j] * W[c,j]
+        const int b = i / C, c = i % C;
+        double acc = 0.0;
+        for (int j = 0; j < 10; ++j) acc += (double)__fsub_rn(probs[b * 10 + j], labels[b * 10 + j]) * (double)W[c + (long long)C * j];
+        dpool[i] = (float)acc;
+    }
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int b = 0; b < B; ++b) s += score_parts[b];
+        *score = (float)(s / (double)B);
+    }
+}
+
+// Updater.  kind 0: Nesterovs on g / B  (v' = mu v - lr g/B;  p += -mu v + (1 + mu) v');  kind 1: NoOp — the "gradient" is subtracted as is
+// (BatchNorm running statistics).
+__global__ void __launch_bounds__(256) k_outer_update(float* __restrict__ p, float* __restrict__ v, const float* __restrict__ g, const unsigned char* __restrict__ kind,
+                                                       long long n, float batch, float lr, float mu, float one_plus_mu) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        if (kind[i]) { p[i] = __fsub_rn(p[i], g[i]); continue; }
+        const float gb = __fdiv_rn(g[i], batch);
+        const float vo = v[i];
+        const float vn = __fsub_rn(__fmul_rn(mu, vo), __fmul_rn(lr, gb));
+        p[i] = __fadd_rn(p[i], __fadd_rn(__fmul_rn(-mu, vo), __fmul_rn(one_plus_mu, vn)));
+        v[i] = vn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// the network
+// ---------------------------------------------------------------------------------------------------------------------------
+class OuterNet {
+public:
+    OuterNet(int batch, int channels, const n4j_solver_cfg& cfg, float t0, float t1, int device);
+    ~OuterNet();
+    long long num_params() const { return n_; }
+    long long ode_offset() const { return off_ode_; }
+    long long ode_num_params() const { return n_ode_; }
+    // one training step: params / updater state are read and written in place (host or device pointers)
+    void train_step(float* params, float* updater_state, const float* images, const float* labels, float lr, float mu, float* score,
+                    float* grad_out, n4j_stats* ode_fwd, n4j_stats* ode_bwd);
+    // forward only; train != 0: BatchNorm batch statistics everywhere (what fit() sees), else running statistics in the outer layers
+    void output(const float* params, const float* images, float* probs, int train);
+
+private:
+    struct Block {
+        ConvShape ds, c1, c2;
+        long long o_bn1, o_ds, o_c1, o_bn2, o_c2;     // parameter offsets
+        float *n1, *dsy, *f1, *n2, *f2, *a_out, *st1, *st2;
+        int Hin, Hout;
+    };
+    void forward(const float* p, const float* images, const float* labels, bool train, n4j_stats* ode_fwd);
+    float* dev_alloc(long long n);
+    bool is_dev(const void* p) const;
+    int grid(long long n) const { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 8)); }
+
+    int device_, B_, C_;
+    float time_[2];
+    std::unique_ptr<Engine> ode_;
+    cudaStream_t s_ = nullptr;
+    ConvShape cin_;
+    Block blk_[2];
+    long long n_ = 0, off_in_b_ = 0, off_in_w_ = 0, off_ode_ = 0, n_ode_ = 0, off_bno_ = 0, off_ow_ = 0, off_ob_ = 0;
+    float *p_ = nullptr, *v_ = nullptr, *g_ = nullptr;     // device copies: params, updater state, gradient view
+    unsigned char* kind_ = nullptr;
+    float *img_ = nullptr, *lab_ = nullptr, *a0_ = nullptr, *z1_ = nullptr, *no_ = nullptr, *sto_ = nullptr, *pool_ = nullptr, *probs_ = nullptr;
+    float *d1_ = nullptr, *d2_ = nullptr, *d3_ = nullptr, *dpool_ = nullptr, *score_ = nullptr, *tdev_ = nullptr;
+    double* score_parts_ = nullptr;
+    std::vector<void*> allocs_;
+};
+
+inline float* OuterNet::dev_alloc(long long n) {
+    float* p = nullptr;
+    N4J_CUDA(cudaMalloc(&p, sizeof(float) * std::max<long long>(n, 1)));
+    allocs_.push_back(p);
+    return p;
+}
+inline bool OuterNet::is_dev(const void* p) const {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+inline OuterNet::OuterNet(int batch, int channels, const n4j_solver_cfg& cfg, float t0, float t1, int device) : device_(device), B_(batch), C_(channels) {
+    if (batch < 1 || channels < 1) throw Error{N4J_ERR_INVALID_ARGUMENT, "batch and channels must be positive"};
+    N4J_CUDA(cudaSetDevice(device));
+    time_[0] = t0; time_[1] = t1;
+    const int C = C_;
+    // the ODE block: BN-ReLU, conv3x3, BN-ReLU, conv3x3, BN-ReLU on [B,C,7,7] (examples/mnist/OdeNetModel.java:72-88)
+    n4j_layer_desc L[5];
+    for (int i = 0; i < 5; ++i) {
+        L[i] = n4j_layer_desc{};
+        L[i].kind = (i % 2 == 0) ? N4J_LAYER_BATCHNORM : N4J_LAYER_CONV3X3;
+        L[i].activation = (i % 2 == 0) ? N4J_ACT_RELU : N4J_ACT_IDENTITY;
+        L[i].n_in = C; L[i].n_out = C; L[i].has_bias = 0; L[i].eps = 1e-5f;
+    }
+    n4j_graph_desc g{};
+    g.n_layers = 5; g.rank = 4; g.shape[0] = batch; g.shape[1] = C; g.shape[2] = 7; g.shape[3] = 7; g.layers = L;
+    ode_.reset(new Engine(g, cfg, device));
+    s_ = ode_->stream();
+    n_ode_ = ode_->num_params();
+    // parameter layout (DL4J order; oracle/outer_oracle.py: OuterLayout)
+    long long off = 0;
+    off_in_b_ = off; off += C; off_in_w_ = off; off += (long long)C * 9;
+    cin_ = make_conv_shape(batch, 1, 28, 28, C, 3, 1, false);
+    int H = cin_.Ho;
+    for (int r = 0; r < 2; ++r) {
+        Block& b = blk_[r];
+        b.Hin = H;
+        b.o_bn1 = off; off += 4 * C;
+        b.o_ds = off; off += (long long)C * C;
+        b.o_c1 = off; off += (long long)C * C * 9;
+        b.o_bn2 = off; off += 4 * C;
+        b.o_c2 = off; off += (long long)C * C * 9;
+        b.ds = make_conv_shape(batch, C, H, H, C, 1, 2, false);
+        b.c1 = make_conv_shape(batch, C, H, H, C, 3, 2, true);
+        b.Hout = b.c1.Ho;
+        b.c2 = make_conv_shape(batch, C, b.Hout, b.Hout, C, 3, 1, true);
+        if (b.ds.Ho != b.Hout) throw Error{N4J_ERR_ILLEGAL_STATE, "stem branches disagree on the downsampled size"};
+        const long long nin = (long long)batch * C * H * H, nout = (long long)batch * C * b.Hout * b.Hout;
+        b.n1 = dev_alloc(nin); b.dsy = dev_alloc(nout); b.f1 = dev_alloc(nout); b.n2 = dev_alloc(nout); b.f2 = dev_alloc(nout); b.a_out = dev_alloc(nout);
+        b.st1 = dev_alloc(3 * C); b.st2 = dev_alloc(3 * C);
+        H = b.Hout;
+    }
+    if (H != 7) throw Error{N4J_ERR_ILLEGAL_STATE, "stem does not end at 7x7"};
+    off_ode_ = off; off += n_ode_;
+    off_bno_ = off; off += 4 * C;
+    off_ow_ = off; off += (long long)C * 10; off_ob_ = off; off += 10;
+    n_ = off;
+    p_ = dev_alloc(n_); v_ = dev_alloc(n_); g_ = dev_alloc(n_);
+    N4J_CUDA(cudaMalloc(&kind_, n_)); allocs_.push_back(kind_);
+    std::vector<unsigned char> kind(n_, 0);
+    auto noop = [&](long long o) { for (int i = 2 * C; i < 4 * C; ++i) kind[o + i] = 1; };
+    for (int r = 0; r < 2; ++r) { noop(blk_[r].o_bn1); noop(blk_[r].o_bn2); }
+    noop(off_bno_);
+    N4J_CUDA(cudaMemcpy(kind_, kind.data(), n_, cudaMemcpyHostToDevice));
+    const long long n0 = (long long)batch * C * 26 * 26, nz = (long long)batch * C * 49;
+    img_ = dev_alloc((long long)batch * 28 * 28); lab_ = dev_alloc((long long)batch * 10);
+    a0_ = dev_alloc(n0); z1_ = dev_alloc(nz); no_ = dev_alloc(nz); sto_ = dev_alloc(3 * C);
+    pool_ = dev_alloc((long long)batch * C); probs_ = dev_alloc((long long)batch * 10); dpool_ = dev_alloc((long long)batch * C);
+    d1_ = dev_alloc(n0); d2_ = dev_alloc(n0); d3_ = dev_alloc(n0);
+    score_ = dev_alloc(1); tdev_ = dev_alloc(2);
+    N4J_CUDA(cudaMalloc(&score_parts_, sizeof(double) * batch)); allocs_.push_back(score_parts_);
+    N4J_CUDA(cudaMemcpy(tdev_, time_, sizeof(time_), cudaMemcpyHostToDevice));
+}
+
+inline OuterNet::~OuterNet() {
+    cudaSetDevice(device_);
+    for (void* p : allocs_) cudaFree(p);
+}
+
+inline void OuterNet::forward(const float* p, const float* images, const float* labels, bool train, n4j_stats* ode_fwd) {
+    const int C = C_, B = B_;
+    k_outer_conv_fwd<<<grid((long long)B * C * 26 * 26), 256, 0, s_>>>(images, p + off_in_w_, p + off_in_b_, a0_, cin_, 0);
+    const float* a = a0_;
+    for (int r = 0; r < 2; ++r) {
+        Block& b = blk_[r];
+        const int HWi = b.Hin * b.Hin, HWo = b.Hout * b.Hout;
+        const long long nin = (long long)B * C * HWi, nout = (long long)B * C * HWo;
+        if (train) k_outer_bn_fwd<<<C, 256, 0, s_>>>(a, p + b.o_bn1, p + b.o_bn1 + C, b.n1, b.st1, B, C, HWi, 1e-5f, 1);
+        else k_outer_bn_infer<<<grid(nin), 256, 0, s_>>>(a, p + b.o_bn1, b.n1, nin, C, HWi, 1e-5f, 1);
+        k_outer_conv_fwd<<<grid(nout), 256, 0, s_>>>(b.n1, p + b.o_ds, nullptr, b.dsy, b.ds, 0);
+        k_outer_conv_fwd<<<grid(nout), 256, 0, s_>>>(b.n1, p + b.o_c1, nullptr, b.f1, b.c1, 1);      // ReLU: examples/mnist/LayerUtil.java:111-116
+        if (train) k_outer_bn_fwd<<<C, 256, 0, s_>>>(b.f1, p + b.o_bn2, p + b.o_bn2 + C, b.n2, b.st2, B, C, HWo, 1e-5f, 1);
+        else k_outer_bn_infer<<<grid(nout), 256, 0, s_>>>(b.f1, p + b.o_bn2, b.n2, nout, C, HWo, 1e-5f, 1);
+        k_outer_conv_fwd<<<grid(nout), 256, 0, s_>>>(b.n2, p + b.o_c2, nullptr, b.f2, b.c2, 0);
+        k_outer_add<<<grid(nout), 256, 0, s_>>>(b.dsy, b.f2, b.a_out, nout);                          // ElementWiseVertex(Add): stemAdd_r
+        a = b.a_out;
+    }
+    N4J_CUDA(cudaGetLastError());
+    // the ODE block (training mode always: SingleStep.java:37)
+    ode_->bind_params(p + off_ode_, n_ode_);
+    ode_->forward(a, time_, 2, 0, z1_, ode_fwd);
+    const long long nz = (long long)B * C * 49;
+    if (train) k_outer_bn_fwd<<<C, 256, 0, s_>>>(z1_, p + off_bno_, p + off_bno_ + C, no_, sto_, B, C, 49, 1e-5f, 1);
+    else k_outer_bn_infer<<<grid(nz), 256, 0, s_>>>(z1_, p + off_bno_, no_, nz, C, 49, 1e-5f, 1);
+    k_outer_pool_fwd<<<(B * C * 32 + 255) / 256, 256, 0, s_>>>(no_, pool_, B * C, 49);
+    k_outer_output_fwd<<<(B + 255) / 256, 256, 0, s_>>>(pool_, p + off_ow_, p + off_ob_, labels, probs_, labels ? score_parts_ : nullptr, B, C);
+    N4J_CUDA(cudaGetLastError());
+}
+
+inline void OuterNet::output(const float* params, const float* images, float* probs, int train) {
+    N4J_CUDA(cudaSetDevice(device_));
+    N4J_CUDA(cudaMemcpyAsync(p_, params, sizeof(float) * n_, cudaMemcpyDefault, s_));
+    N4J_CUDA(cudaMemcpyAsync(img_, images, sizeof(float) * B_ * 28 * 28, cudaMemcpyDefault, s_));
+    forward(p_, img_, nullptr, train != 0, nullptr);
+    N4J_CUDA(cudaMemcpyAsync(probs, probs_, sizeof(float) * B_ * 10, cudaMemcpyDefault, s_));
+    N4J_CUDA(cudaStreamSynchronize(s_));
+}
+
+inline void OuterNet::train_step(float* params, float* updater_state, const float* images, const float* labels, float lr, float mu, float* score,
+                                 float* grad_out, n4j_stats* ode_fwd, n4j_stats* ode_bwd) {
+    N4J_CUDA(cudaSetDevice(device_));
+    const int C = C_, B = B_;
+    N4J_CUDA(cudaMemcpyAsync(p_, params, sizeof(float) * n_, cudaMemcpyDefault, s_));
+    N4J_CUDA(cudaMemcpyAsync(v_, updater_state, sizeof(float) * n_, cudaMemcpyDefault, s_));
+    N4J_CUDA(cudaMemcpyAsync(img_, images, sizeof(float) * B * 28 * 28, cudaMemcpyDefault, s_));
+    N4J_CUDA(cudaMemcpyAsync(lab_, labels, sizeof(float) * B * 10, cudaMemcpyDefault, s_));
+    N4J_CUDA(cudaMemsetAsync(g_, 0, sizeof(float) * n_, s_));          // ZeroGrad (util/listen/training/ZeroGrad.java:14-16): the theta-adjoint is seeded from the view
+    forward(p_, img_, lab_, true, ode_fwd);
+    // ---- backward --------------------------------------------------------------------------------------------------------------
+    const long long nz = (long long)B * C * 49;
+    k_outer_output_bwd<<<1, 256, 0, s_>>>(pool_, p_ + off_ow_, probs_, lab_, score_parts_, g_ + off_ow_, g_ + off_ob_, dpool_, score_, B, C);
+    k_outer_pool_bwd<<<grid(nz), 256, 0, s_>>>(dpool_, d1_, nz, 49);
+    k_outer_bn_bwd<<<C, 256, 0, s_>>>(z1_, no_, d1_, p_ + off_bno_, sto_, d2_, g_ + off_bno_, B, C, 49, 1, 0.1f);
+    N4J_CUDA(cudaGetLastError());
+    // the adjoint solve: continues the forward of this handle (lastOutput stays on the device), gradient view slice seeded (zero) and written in place
+    ode_->backward(nullptr, d2_, time_, 2, N4J_TIMEGRAD_NONE, g_ + off_ode_, d1_, nullptr, ode_bwd);
+    float* da = d1_;              // dL/d(stem output)
+    float* t1 = d2_;
+    float* t2 = d3_;
+    for (int r = 1; r >= 0; --r) {
+        Block& b = blk_[r];
+        const float* a_in = r == 0 ? a0_ : blk_[0].a_out;
+        const int HWi = b.Hin * b.Hin, HWo = b.Hout * b.Hout;
+        const long long nin = (long long)B * C * HWi;
+        // secondConv (identity): weight gradient, then dL/dn2 into t1
+        k_outer_conv_wgrad<<<C * C, 128, 0, s_>>>(b.n2, da, b.f2, g_ + b.o_c2, nullptr, b.c2, 0);
+        k_outer_conv_dgrad<<<grid((long long)B * C * HWo), 256, 0, s_>>>(da, b.f2, p_ + b.o_c2, t1, b.c2, 0);
+        // secondNorm: dL/df1 into t2
+        k_outer_bn_bwd<<<C, 256, 0, s_>>>(b.f1, b.n2, t1, p_ + b.o_bn2, b.st2, t2, g_ + b.o_bn2, B, C, HWo, 1, 0.1f);
+        // firstConv (ReLU) and downSample (identity) both read n1: dL/dn1 = downSample's epsilon + firstConv's epsilon
+        k_outer_conv_wgrad<<<C * C, 128, 0, s_>>>(b.n1, t2, b.f1, g_ + b.o_c1, nullptr, b.c1, 1);
+        k_outer_conv_wgrad<<<C * C, 128, 0, s_>>>(b.n1, da, b.dsy, g_ + b.o_ds, nullptr, b.ds, 0);
+        k_outer_conv_dgrad<<<grid(nin), 256, 0, s_>>>(t2, b.f1, p_ + b.o_c1, t1, b.c1, 1);             // t1: firstConv's epsilon  [B,C,Hin,Hin]
+        k_outer_conv_dgrad<<<grid(nin), 256, 0, s_>>>(da, b.dsy, p_ + b.o_ds, t2, b.ds, 0);            // t2: downSample's epsilon
+        k_outer_add<<<grid(nin), 256, 0, s_>>>(t2, t1, t1, nin);
+        // firstNorm: dL/d(block input) into da's next buffer
+        k_outer_bn_bwd<<<C, 256, 0, s_>>>(a_in, b.n1, t1, p_ + b.o_bn1, b.st1, t2, g_ + b.o_bn1, B, C, HWi, 1, 0.1f);
+        std::swap(da, t2);
+        // keep three distinct buffers: da (new epsilon), t1, t2 (scratch)
+    }
+    k_outer_conv_wgrad<<<C, 128, 0, s_>>>(img_, da, a0_, g_ + off_in_w_, g_ + off_in_b_, cin_, 0);
+    // ---- update ----------------------------------------------------------------------------------------------------------------
+    if (grad_out) N4J_CUDA(cudaMemcpyAsync(grad_out, g_, sizeof(float) * n_, cudaMemcpyDefault, s_));
+    k_outer_update<<<grid(n_), 256, 0, s_>>>(p_, v_, g_, kind_, n_, (float)B, lr, mu, (float)(1.0 + (double)mu));
+    N4J_CUDA(cudaGetLastError());
+    N4J_CUDA(cudaMemcpyAsync(params, p_, sizeof(float) * n_, cudaMemcpyDefault, s_));
+    N4J_CUDA(cudaMemcpyAsync(updater_state, v_, sizeof(float) * n_, cudaMemcpyDefault, s_));
+    if (score) N4J_CUDA(cudaMemcpyAsync(score, score_, sizeof(float), cudaMemcpyDefault, s_));
+    N4J_CUDA(cudaStreamSynchronize(s_));
+}
+
+}  // namespace n4j

@@ -1,0 +1,182 @@
+"""SURVEY.md section 8 row f3 — the outer network step around the ODE block (MNIST stem, output block, loss, updater).
+
+CPU part: the numpy restatement (oracle/outer_oracle.py) against an independent implementation of the same textbook layers
+(torch.nn.functional + autograd in fp64): loss, every parameter gradient, the BatchNorm running-statistics update and the Nesterov
+step.  DL4J itself cannot run here: what stays unpinned is whether DL4J 1.0.0-beta3 deviates from these definitions."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import outer_oracle as OO
+
+
+class _IdentityOde:
+    """Stands in for the ODE block in the CPU test of the OUTER layers (the block itself is pinned in test_oracle_golden.py)."""
+    n_params = 0
+
+    class _S:
+        nfe = accepted = rejected = 0
+    stats = _S()
+
+    def forward(self, params, y0, t):
+        return y0.copy()
+
+    def backward(self, params, z_out, dL_dz, t, grad_inout=None):
+        return dL_dz.copy(), np.zeros(0, dtype=np.float32), None
+
+
+def _random_params(layout, rng):
+    p = np.zeros(layout.n, dtype=np.float32)
+    for name, (o, n) in layout.slices.items():
+        if name in layout.bn_names():
+            C = layout.C
+            p[o:o + C] = 1 + 0.1 * rng.standard_normal(C)
+            p[o + C:o + 2 * C] = 0.1 * rng.standard_normal(C)
+            p[o + 2 * C:o + 3 * C] = 0.05 * rng.standard_normal(C)
+            p[o + 3 * C:o + 4 * C] = 1 + 0.05 * rng.random(C)
+        elif n:
+            p[o:o + n] = rng.uniform(-1, 1, n) / np.sqrt(max(n // layout.C, 1))
+    return p
+
+
+def _torch_step(layout, p64, images, labels):
+    C = layout.C
+    P = {k: torch.tensor(layout.get(p64, k), dtype=torch.float64, requires_grad=True) for k in layout.slices if layout.slices[k][1]}
+    bn_stats = {}
+
+    def bn(x, name):
+        q = P[name]
+        m = x.mean(dim=(0, 2, 3)); v = x.var(dim=(0, 2, 3), unbiased=False)
+        bn_stats[name] = (m.detach().numpy(), v.detach().numpy())
+        xh = (x - m.view(1, -1, 1, 1)) / torch.sqrt(v.view(1, -1, 1, 1) + OO.BN_EPS)
+        return torch.relu(q[:C].view(1, -1, 1, 1) * xh + q[C:2 * C].view(1, -1, 1, 1))
+
+    def conv_same(x, w, s):
+        H = x.shape[2]
+        out, front = OO.same_pad(H, w.shape[2], s)
+        total = max((out - 1) * s + w.shape[2] - H, 0)
+        return F.conv2d(F.pad(x, (front, total - front, front, total - front)), w, stride=s)
+
+    x = torch.tensor(images, dtype=torch.float64)
+    a = F.conv2d(x, P["inputConv.W"].view(C, 1, 3, 3), P["inputConv.b"])
+    for r in (0, 1):
+        n1 = bn(a, f"firstNorm{r}")
+        ds = F.conv2d(n1, P[f"downSample{r}.W"].view(C, C, 1, 1), stride=2)
+        f1 = torch.relu(conv_same(n1, P[f"firstConv{r}.W"].view(C, C, 3, 3), 2))
+        n2 = bn(f1, f"secondNorm{r}")
+        a = ds + conv_same(n2, P[f"secondConv{r}.W"].view(C, C, 3, 3), 1)
+    no = bn(a, "normOutput")
+    pool = no.mean(dim=(2, 3))
+    Wo = P["output.W"].view(10, C).t()                     # f-order [C,10]
+    logits = pool @ Wo + P["output.b"]
+    logp = torch.log_softmax(logits, dim=1)
+    y = torch.tensor(labels, dtype=torch.float64)
+    loss_sum = -(y * logp).sum()
+    loss_sum.backward()
+    grad = np.zeros(layout.n)
+    for k, t in P.items():
+        o, n = layout.slices[k]
+        grad[o:o + n] = t.grad.numpy()
+    return float(loss_sum) / images.shape[0], torch.softmax(logits, 1).detach().numpy(), grad, bn_stats, a.detach().numpy()
+
+
+@pytest.mark.parametrize("C,B", [(4, 3), (8, 2)])
+def test_outer_oracle_matches_torch_autograd(C, B):
+    rng = np.random.default_rng(C * 10 + B)
+    orc = OO.OuterOracle(_IdentityOde(), [0.0, 1.0], C, B)
+    L = orc.layout
+    p = _random_params(L, rng)
+    v = (0.01 * rng.standard_normal(L.n)).astype(np.float32)
+    images = rng.standard_normal((B, 1, 28, 28)).astype(np.float32)
+    labels = np.eye(10, dtype=np.float32)[rng.integers(0, 10, B)]
+    out = orc.train_step(p, v, images, labels, lr=0.1, mu=0.9)
+    loss, probs, grad, bn_stats, z0 = _torch_step(L, p.astype(np.float64), images, labels)
+    assert out["z0"].shape == (B, C, 7, 7)                                       # 28 -> 26 -> 13 -> 7 (ResBlockStem.java:25-28)
+    np.testing.assert_allclose(out["z0"], z0, rtol=2e-4, atol=2e-5)
+    assert abs(out["score"] - loss) < 1e-5 * max(1.0, abs(loss))
+    np.testing.assert_allclose(out["probs"], probs, rtol=1e-4, atol=1e-6)
+    noop = L.noop_mask()
+    g, go = grad[~noop], out["grad"][~noop].astype(np.float64)
+    assert np.abs(g - go).max() <= 2e-4 * np.abs(g).max(), np.abs(g - go).max() / np.abs(g).max()
+    # running statistics: mean <- decay*mean + (1-decay)*batch (the "gradient" is subtracted as it is, NoOp updater)
+    for nm in L.bn_names():
+        o, _ = L.slices[nm]
+        bm, bv = bn_stats[nm]
+        np.testing.assert_allclose(out["params"][o + 2 * C:o + 3 * C], 0.9 * p[o + 2 * C:o + 3 * C] + 0.1 * bm, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(out["params"][o + 3 * C:o + 4 * C], 0.9 * p[o + 3 * C:o + 4 * C] + 0.1 * bv, rtol=1e-4, atol=1e-5)
+    # Nesterovs: v' = mu v - lr g/B;  p' = p - mu v + (1 + mu) v'
+    gB = grad / B
+    v_new = 0.9 * v - 0.1 * gB
+    p_new = p - 0.9 * v + 1.9 * v_new
+    np.testing.assert_allclose(out["updater_state"][~noop], v_new[~noop], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(out["params"][~noop], p_new[~noop], rtol=1e-3, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# GPU: node4j_net_train_step against the oracle (outer layers in numpy, the ODE block on oracle/node_oracle.cpp)
+# ---------------------------------------------------------------------------------------------------------------------------
+def _model_and_oracle(C, B, flags):
+    from neuralode4j_b200 import workloads as W
+    from neuralode4j_b200.net import OdeNetModel
+    import helpers as H
+    w = W.mnist_block(batch=B, channels=C)
+    ode = H.oracle_for(w)
+    orc = OO.OuterOracle(ode, [0.0, 1.0], C, B)
+    rng = np.random.default_rng(C + B)
+    p = _random_params(orc.layout, rng)
+    o, n = orc.layout.slices["ode"]
+    p[o:o + n] = w.params
+    model = OdeNetModel(batch=B, nrofKernels=C, flags=flags)
+    assert model.numParams() == orc.layout.n and model.ode_slice == (o, n)
+    return model, orc, p, rng
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,B", [(8, 4), (64, 8)])
+def test_train_step_matches_oracle(C, B):
+    """One full training step on the device (stem, ODE block forward + adjoint backward, output block, loss, Nesterovs, running
+    statistics) against the oracle on the same images, labels, parameters and momentum: score, gradient view, updated parameters
+    and updater state within rtol 1e-4, accepted / rejected counts of both solves exact.  Parity mode for the 64-channel block (its
+    default mode runs the tcgen05 convolutions, whose gradients are only comparable in relative L2: test_gpu_parity.py)."""
+    from neuralode4j_b200 import _lib
+    model, orc, p, rng = _model_and_oracle(C, B, _lib.FLAG_EXACT_CONTRACTIONS)
+    try:
+        v = (0.01 * rng.standard_normal(p.size)).astype(np.float32)
+        images = rng.standard_normal((B, 1, 28, 28)).astype(np.float32)
+        labels = np.eye(10, dtype=np.float32)[rng.integers(0, 10, B)]
+        want = orc.train_step(p, v, images, labels, lr=0.1, mu=0.9)
+        model.setParams(p)
+        model.updater_state = v.copy()
+        score = model.fit(images, labels, lr=0.1, keep_gradient=True)
+        fs, bs = model.ode_fwd_stats, model.ode_bwd_stats
+        assert (fs.nfe, fs.accepted, fs.rejected) == want["ode_fwd_stats"] and (bs.nfe, bs.accepted, bs.rejected) == want["ode_bwd_stats"]
+        assert abs(score - want["score"]) <= 1e-5 * max(1.0, abs(want["score"]))
+        for name, got, ref in (("gradient", model.last_gradient, want["grad"]), ("params", model.params, want["params"]),
+                               ("updater state", model.updater_state, want["updater_state"])):
+            err = np.abs(got.astype(np.float64) - ref)
+            tol = 1e-4 * np.abs(ref) + 1e-5 * np.abs(ref).max()
+            assert (err <= tol).all(), f"{name}: {(err > tol).sum()} of {err.size} outside rtol 1e-4; worst {err.max():.3e} (max |ref| {np.abs(ref).max():.3e})"
+        # forward only, batch statistics: the probabilities the loss was computed from
+        probs = model.output(images, train=True)
+        assert probs.shape == (B, 10) and np.allclose(probs.sum(axis=1), 1.0, atol=1e-5)
+    finally:
+        model.close()
+
+
+@pytest.mark.gpu
+def test_training_reduces_the_loss_and_inference_uses_running_statistics():
+    """A few steps of fit() on one fixed minibatch (default mode, 64 channels, batch 32): the score goes down, parameters stay finite,
+    and output(train=False) (running statistics in the outer BatchNorm layers) differs from output(train=True) but is a distribution."""
+    model, orc, p, rng = _model_and_oracle(64, 32, 0)
+    try:
+        images = rng.standard_normal((32, 1, 28, 28)).astype(np.float32)
+        labels = np.eye(10, dtype=np.float32)[rng.integers(0, 10, 32)]
+        model.setParams(p)
+        scores = [model.fit(images, labels, lr=0.05) for _ in range(6)]
+        assert np.isfinite(model.params).all() and np.isfinite(scores).all()
+        assert scores[-1] < scores[0], scores
+        a, b = model.output(images, train=True), model.output(images, train=False)
+        assert np.allclose(a.sum(axis=1), 1.0, atol=1e-5) and np.allclose(b.sum(axis=1), 1.0, atol=1e-5) and not np.array_equal(a, b)
+    finally:
+        model.close()
