@@ -484,6 +484,26 @@ def _deviation(a, b, rtol=1e-4, atol_scale=1e-5):
             "worst_abs_over_max": float(err.max() / (np.abs(b).max() + 1e-300))}
 
 
+def _oracle_sensitivity(name, orc):
+    """How far the ORACLE's own gradients move when its contractions are perturbed at fp32 rounding level (relative 1e-8) and when
+    it runs in fp64: the yardstick for the default mode's gradient deviation on a BatchNorm+ReLU block (ReLU mask flips at elements
+    below the rounding noise change BatchNorm's backward sums by whole terms)."""
+    import ctypes
+    from oracle import oracle as O
+    L = O.lib()
+    L.orc_set_probe_noise.argtypes = [ctypes.c_double]
+    w = _make_workload(name, CPU_SAMPLE_BATCH[name])
+    out = {}
+    try:
+        L.orc_set_probe_noise(1e-8)
+        _, _, p = cpu_step(w, keep=True)
+    finally:
+        L.orc_set_probe_noise(0.0)
+    out["contractions_perturbed_1e-8"] = {"dL_dy0": _deviation(p["dy0"], orc["dy0"]), "dL_dtheta": _deviation(p["grad"], orc["grad"]),
+                                          "counts_equal": list(p["bwd_stats"]) == list(orc["bwd_stats"])}
+    return out
+
+
 def _parity_block(gpu, orc):
     """Deviation of one GPU run (dict with outputs and stats) from the oracle run on the same inputs."""
     o = gpu["outputs"]
@@ -589,6 +609,8 @@ def run_ours(args):
                       "default_mode": _parity_block(main, orc)}
             if "_par_outputs" in extras:
                 parity["parity_mode"] = _parity_block(extras["_par_outputs"], orc)
+            if is_mnist:
+                parity["oracle_self_sensitivity"] = _oracle_sensitivity(name, orc)
     extras.pop("_par_outputs", None)
 
     line = {
