@@ -304,6 +304,9 @@ class Bench:
             raise SystemExit("bench.py needs a CUDA device: the node4j engine has no CPU fallback")
         torch.cuda.set_device(self.local_rank)
         if self.world > 1:
+            # the contract is ONE line on stdout: NCCL announces its version there when NCCL_DEBUG asks for it (the boxes export VERSION)
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
         self.dev = torch.device("cuda", self.local_rank)
         self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
