@@ -119,6 +119,7 @@ struct CommDev {
     long long xcap;                   // floats per parity in xbuf
     long long xll_off;                // LL vector exchange: uint64 cell[2 parities][8 ranks][xll_cap] at this byte offset of every comm region
     long long xll_cap;                // cells (floats) per (parity, rank); 0: no LL buffer
+    long long stat_off;               // BatchNorm statistics mailboxes (sharded deferred scheme, layer_kernels.cuh: BnScratch) at this byte offset of every comm region
     char* peer[COMM_MAX_WORLD];       // base of every rank's comm region (peer[rank] is the local one)
 };
 

@@ -204,9 +204,18 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         __shared__ float s_fin[4][64];     // mean, invstd, mean(dy), mean(dy*xhat)
         double raw[4] = {0.0, 0.0, 0.0, 0.0};
         if (PRO == 1 && a.prearm && blockIdx.x == 0 && warp >= 2 && warp < 6) a.pbn.accf_other[(threadIdx.x - 64) * ACC_STRIDE] = 0.0;
+        unsigned int tagf = 0u, tagb = 0u;
         if (a.pbn.deferred && warp < 2) {      // warp-uniform on purpose: a real branch, not predicated double-precision code in all warps
             raw[0] = a.pbn.accf[threadIdx.x * ACC_STRIDE]; raw[1] = a.pbn.accf[(64 + threadIdx.x) * ACC_STRIDE];
             if (PRO == 2) { raw[2] = a.pbn.accb[threadIdx.x * ACC_STRIDE]; raw[3] = a.pbn.accb[(64 + threadIdx.x) * ACC_STRIDE]; }
+            if (a.pbn.cm) {      // sharded: CTA 0 sends this rank's local sums on their way now; the peers' sums are collected right before the finalisation
+                tagf = *((volatile unsigned int*)a.pbn.seqf);
+                if (PRO == 2) tagb = *((volatile unsigned int*)a.pbn.seqb);
+                if (blockIdx.x == 0) {
+                    bn_push2(a.pbn.cm, a.pbn.mbf, tagf, threadIdx.x, raw[0], raw[1]);
+                    if (PRO == 2) bn_push2(a.pbn.cm, a.pbn.mbb, tagb, threadIdx.x, raw[2], raw[3]);
+                }
+            }
         }
         float mean[4], inv[4], gam[4], bet[4], mdy[4], mdyxh[4];
 #pragma unroll
@@ -248,8 +257,12 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             }
             if (threadIdx.x == 0) conv_stamp(a, 2);
             if (a.pbn.deferred && rr == rbase) {       // first (for W <= 14: only) pass; every thread of the CTA gets here
+                if (warp < 2 && a.pbn.cm) {
+                    bn_gather2(a.pbn.cm, a.pbn.mbf, tagf, threadIdx.x, raw[0], raw[1]);
+                    if (PRO == 2) bn_gather2(a.pbn.cm, a.pbn.mbb, tagb, threadIdx.x, raw[2], raw[3]);
+                }
                 if (warp < 2)
-                    conv_finalize_stats<PRO>(raw[0], raw[1], raw[2], raw[3], a.pbn.rows, a.pbn.eps, s_fin,
+                    conv_finalize_stats<PRO>(raw[0], raw[1], raw[2], raw[3], a.pbn.cm ? a.pbn.rows_total : a.pbn.rows, a.pbn.eps, s_fin,
                                              (PRO == 2 && blockIdx.x == 0) ? resolve(a.pdgamma) : nullptr, (PRO == 2 && blockIdx.x == 0) ? resolve(a.pdbeta) : nullptr);
                 __syncthreads();
                 if (threadIdx.x == 0) conv_stamp(a, 3);
@@ -467,6 +480,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 if (a.bn.deferred) {      // accumulate only; the consumers finalise, CTA 0 re-arms the next evaluation's set
                     atomicAdd((EPI == 1 ? a.bn.accf : a.bn.accb) + et * ACC_STRIDE, tsum);
                     bn_rearm(EPI == 1 ? a.bn.accf_other : a.bn.accb_other, et);
+                    bn_bump(a.bn.cm ? (EPI == 1 ? a.bn.seqf : a.bn.seqb) : nullptr, et);
                 } else {                  // legacy / multi-GPU: the last CTA finalises (and exchanges the sums between the ranks)
                     atomicAdd(a.bn.acc + et * ACC_STRIDE, tsum);
                     __threadfence();

@@ -178,7 +178,13 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
     N4J_CUDA(cudaSetDevice(device_));
     N4J_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     N4J_CUDA(cudaStreamCreateWithFlags(&stream2_, cudaStreamNonBlocking));
-    N4J_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    {   // the side branch (weight gradients) yields to the main chain when both have blocks pending (N4J_SIDE_PRIO=0 switches it off, A/B)
+        int lo = 0, hi = 0;
+        N4J_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const char* sp = getenv("N4J_SIDE_PRIO");
+        if (sp && atoi(sp) == 0) N4J_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+        else N4J_CUDA(cudaStreamCreateWithPriority(&side_, cudaStreamNonBlocking, lo));
+    }
     for (auto& e : ev_pool_) N4J_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (auto& e : slot_event_) N4J_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     N4J_CUDA(cudaEventCreate(&ev0_));
@@ -356,7 +362,7 @@ Engine::~Engine() {
         for (int sl = 0; sl < 2; ++sl) { cudaFree(l.act2[sl]); cudaFree(l.gin2[sl]); }
         cudaFree(l.ximg); cudaFree(l.dimg); cudaFree(l.dTimg); cudaFree(l.xTimg); cudaFree(l.wsf); cudaFree(l.wsb);
         cudaFree(l.wf); cudaFree(l.wb); cudaFree(l.img); cudaFree(l.gimg); cudaFree(l.wimg_f); cudaFree(l.wimg_b);
-        if (l.d.kind == N4J_LAYER_BATCHNORM) { cudaFree(l.bn.acc); cudaFree(l.bn.ticket); cudaFree(l.bn.mean); }
+        if (l.d.kind == N4J_LAYER_BATCHNORM) { cudaFree(l.bn.acc); cudaFree(l.bn.ticket); cudaFree(l.bn.mean); cudaFree(l.bn_seq); }
     }
     for (DevBuf* b : {&params_, &gradflat_, &zt_, &gt_, &io_, &io2_, &gb_[0], &gb_[1], &gb_[2], &theta_tmp_, &wpart_, &dldt_}) cudaFree(b->p);
     for (void* pp : peer_ptrs_) cudaIpcCloseMemHandle(pp);
@@ -430,6 +436,11 @@ void Engine::set_bn_slot(int slot) {
         l.bn.accf_other = base + (size_t)(0 * 2 + (slot ^ 1)) * set;
         l.bn.accb = base + (size_t)(1 * 2 + slot) * set;
         l.bn.accb_other = base + (size_t)(1 * 2 + (slot ^ 1)) * set;
+        if (l.bn_seq) {     // sharded: this set's sequence counters and mailboxes
+            const long long mset = (long long)COMM_MAX_WORLD * 128 * 16;
+            l.bn.seqf = l.bn_seq + (0 * 2 + slot); l.bn.seqb = l.bn_seq + (1 * 2 + slot);
+            l.bn.mbf = l.bn_mb + (0 * 2 + slot) * mset; l.bn.mbb = l.bn_mb + (1 * 2 + slot) * mset;
+        }
     }
 }
 void Engine::begin_eval() {
@@ -952,7 +963,7 @@ void Engine::enqueue_trial(cudaStream_t s, bool aug, long long n4, const SolverP
     BnFuse nobf{};
     // Stages 1-5 of a 64-channel BatchNorm-first / BatchNorm-last block on one GPU: the evaluation leaves its last elementwise kernel
     // to the combination of the next stage (k_stage_combine_last).  The adjoint form needs the split layout (z | a combined here, theta late).
-    const bool can_leave = combine_fusion_ && bf0.enabled && bf0.sc.deferred == 1 && !comm_dev_ && nz_ % 64 == 0 && off_a_ % 4 == 0 &&
+    const bool can_leave = combine_fusion_ && bf0.enabled && bf0.sc.deferred == 1 && (!comm_dev_ || mgpu_deferred_) && nz_ % 64 == 0 && off_a_ % 4 == 0 &&
                            L_.size() >= 2 && L_.back().d.kind == N4J_LAYER_BATCHNORM && L_.back().c_out == 64 &&
                            (!aug || (split && L_[1].d.kind == N4J_LAYER_CONV3X3 && L_[1].tc && !(cfg_.flags & N4J_FLAG_NO_PROLOGUE_FUSION) &&
                                      (L_[0].d.activation == N4J_ACT_RELU || L_[0].d.activation == N4J_ACT_IDENTITY)));   // the operand prologue of that conv takes the re-arm
@@ -1033,7 +1044,7 @@ SolveGraph& Engine::get_graph(bool aug, int tslot, bool dense_out, int nt) {
     // replay already hides the launch latency and early-resident dependents only take SM slots — so PDL is used for the
     // eager paths (host-driven loop, RHS probes) and switched off while capturing.
     const bool saved_pdl = t_pdl;
-    t_pdl = false;
+    t_pdl = getenv("N4J_GRAPH_PDL") != nullptr && saved_pdl;      // A/B switch: programmatic edges inside the captured graph (re-measured in r02)
     // A throw inside the capture (an ILLEGAL_STATE check of enqueue_trial, any CUDA failure) must not leave stream2_ capturing,
     // leak the graph or lose the launch counter / PDL switch: every later call on the handle would fail.
     struct CaptureGuard {
@@ -1203,6 +1214,13 @@ void Engine::comm_export(void* handle64) {
         comm_xll_cap_ = std::min<long long>(xcap, 1LL << 18);
         comm_xll_off_ = (long long)comm_bytes_;
         comm_bytes_ += (size_t)2 * COMM_MAX_WORLD * (size_t)comm_xll_cap_ * 8;
+        // BatchNorm statistics mailboxes of the sharded deferred scheme: 64 KB per deferred-capable layer
+        comm_bytes_ = (comm_bytes_ + 255) & ~(size_t)255;
+        comm_stat_off_ = (long long)comm_bytes_;
+        long long mb = 0;
+        for (auto& l : L_)
+            if (l.d.kind == N4J_LAYER_BATCHNORM && l.bn_deferred_ok) { l.bn_mb = mb; mb += 2LL * 2 * COMM_MAX_WORLD * 128 * 16; }
+        comm_bytes_ += (size_t)mb;
         N4J_CUDA(cudaMalloc(&comm_region_, comm_bytes_));
         N4J_CUDA(cudaMemset(comm_region_, 0, comm_bytes_));
     }
@@ -1222,7 +1240,7 @@ void Engine::comm_init(int rank, int world, const void* handles, long long globa
             throw Error{N4J_ERR_UNSUPPORTED, "sharded BatchNorm needs a channel count that is a multiple of 4, divides 1024 and is <= 128"};
     CommDev cd;
     std::memset(&cd, 0, sizeof(cd));
-    cd.rank = rank; cd.world = world; cd.xcap = comm_xcap_; cd.xll_off = comm_xll_off_; cd.xll_cap = comm_xll_cap_;
+    cd.rank = rank; cd.world = world; cd.xcap = comm_xcap_; cd.xll_off = comm_xll_off_; cd.xll_cap = comm_xll_cap_; cd.stat_off = comm_stat_off_;
     for (int r = 0; r < world; ++r) {
         if (r == rank) { cd.peer[r] = (char*)comm_region_; continue; }
         cudaIpcMemHandle_t hnd;
@@ -1237,7 +1255,23 @@ void Engine::comm_init(int rank, int world, const void* handles, long long globa
     world_ = world; rank_id_ = rank;
     if (world > 1) {
         N4J_CUDA(cudaMemcpy(&ctrl_->comm, &comm_dev_, sizeof(CommDev*), cudaMemcpyHostToDevice));
-        for (auto& l : L_) { l.bn.cm = comm_dev_; l.bn.rows_total = l.rows * world; l.bn.deferred = 0; }   // the last block exchanges the sums: legacy finalisation
+        const char* md = getenv("N4J_MGPU_DEFERRED");
+        mgpu_deferred_ = !(md && atoi(md) == 0);
+        for (auto& l : L_) {
+            if (l.d.kind != N4J_LAYER_BATCHNORM) continue;
+            l.bn.cm = comm_dev_; l.bn.rows_total = l.rows * world;
+            if (mgpu_deferred_ && l.bn_deferred_ok && l.bn_pool && l.bn_mb >= 0) {
+                // sharded deferred statistics: producers accumulate local sums only, consumers exchange and finalise (layer_kernels.cuh: BnScratch)
+                l.bn.deferred = 1;
+                if (!l.bn_seq) {
+                    N4J_CUDA(cudaMalloc(&l.bn_seq, sizeof(unsigned int) * 4));
+                    N4J_CUDA(cudaMemset(l.bn_seq, 0, sizeof(unsigned int) * 4));
+                }
+            } else {
+                l.bn.deferred = 0;   // the last block of the producer exchanges the sums and finalises (legacy path)
+            }
+        }
+        set_bn_slot(bn_slot_);
     } else {
         cudaFree(comm_dev_); comm_dev_ = nullptr;
     }

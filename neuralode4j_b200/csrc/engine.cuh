@@ -51,6 +51,8 @@ struct LayerPlan {
     BnScratch bn{};
     double* bn_pool = nullptr;     // deferred statistics: this layer's four accumulator sets inside Engine::bn_pool_
     bool bn_deferred_ok = false;
+    unsigned int* bn_seq = nullptr; // sharded deferred statistics: sequence counters [forward|backward][set 0|1] of this layer (device)
+    long long bn_mb = -1;          // ... and the byte offset of its mailboxes inside the statistics area of a comm region
 };
 
 struct DevBuf {
@@ -138,6 +140,8 @@ private:
     void* comm_region_ = nullptr;
     size_t comm_bytes_ = 0;
     long long comm_xcap_ = 0, comm_xll_off_ = 0, comm_xll_cap_ = 0;
+    long long comm_stat_off_ = 0;      // BatchNorm statistics mailboxes: [layer][forward|backward][set][source rank][128 cells of 16 bytes]
+    bool mgpu_deferred_ = false;       // sharded path keeps the deferred statistics (and the combine fusion) — N4J_MGPU_DEFERRED=0 switches back to the last-block exchange
     bool vec_allreduce_ll_ = getenv("N4J_NO_LL_VEC_ALLREDUCE") == nullptr;        // A/B switch: pull exchange through xbuf instead
     bool skip_vec_allreduce_ = getenv("N4J_DBG_SKIP_VEC_ALLREDUCE") != nullptr;   // timing experiments only
     void enqueue_vec_allreduce(cudaStream_t s, Ref slot, long long n);

@@ -215,19 +215,82 @@ struct BnScratch {
     double* accb_other;
     float eps;
     long long rows;         // local rows (B*H*W)
+    // Sharded deferred scheme (cm != nullptr && deferred): every rank's producers only accumulate their LOCAL raw sums, exactly as on one
+    // GPU — no ticket, no last-block read-back, no exchange inside the producer.  The exchange rides on the CONSUMER kernels: block 0
+    // of every consumer pushes its rank's local sums of the set (two 16-byte LL cells per channel: payload halves + the set's sequence
+    // number as tag) straight into every peer's mailbox, and every block adds the peers' cells to its local sums in rank order
+    // (bitwise identical totals on all ranks).  The push is issued in the first instructions of the consumer, the totals are needed
+    // only after its operand loads are in flight, so the NVLink flight (~1 us) hides behind work the kernel does anyway.
+    // The tag is the number of times the set has been produced: its producer kernel bumps the counter (block 0), all ranks run the
+    // same kernel sequence, consumers start after the producer finished (stream order).  Pushing is idempotent (later consumers of
+    // the same set repeat it with the same values).
+    unsigned int* seqf;     // sequence counters of THIS evaluation's forward / backward set (device memory of this rank)
+    unsigned int* seqb;
+    long long mbf, mbb;     // byte offsets inside a comm region of the two sets' mailboxes: cell[source rank][128], 16 bytes each
 };
 
+// thread c (< 64) of one block: local sums s0 (slot c) and s1 (slot 64 + c) of a set -> every peer's mailbox
+__device__ __forceinline__ void bn_push2(CommDev* cm, long long mb, unsigned int tag, int c, double s0, double s1) {
+    const int me = cm->rank, W = cm->world;
+    const unsigned long long hi = (unsigned long long)tag << 32;
+    const unsigned long long b0 = (unsigned long long)__double_as_longlong(s0), b1 = (unsigned long long)__double_as_longlong(s1);
+#pragma unroll
+    for (int q = 0; q < COMM_MAX_WORLD; ++q) {
+        if (q < W && q != me) {
+            unsigned long long* cell = reinterpret_cast<unsigned long long*>(cm->peer[q] + cm->stat_off + mb) + ((long long)me * 128 + c) * 2;
+            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(cell), "l"(hi | (b0 & 0xFFFFFFFFull)), "l"(hi | (b0 >> 32)) : "memory");
+            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(cell + 128), "l"(hi | (b1 & 0xFFFFFFFFull)), "l"(hi | (b1 >> 32)) : "memory");
+        }
+    }
+}
+// any thread c (< 64): s0 / s1 (local sums in, global totals out), peers' contributions added in rank order
+__device__ __forceinline__ void bn_gather2(CommDev* cm, long long mb, unsigned int tag, int c, double& s0, double& s1) {
+    const int me = cm->rank, W = cm->world;
+    const unsigned long long* mbox = reinterpret_cast<const unsigned long long*>(cm->peer[me] + cm->stat_off + mb);
+    double t0 = 0.0, t1 = 0.0;
+    for (int q = 0; q < W; ++q) {
+        if (q == me) { t0 += s0; t1 += s1; continue; }
+        const unsigned long long* cell = mbox + ((long long)q * 128 + c) * 2;
+        unsigned long long a0 = 0, a1 = 0, b0 = 0, b1 = 0;
+        bool ok = false;
+        for (unsigned int spin = 0; spin < (1u << 26); ++spin) {
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(cell) : "memory");
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "l"(cell + 128) : "memory");
+            if ((unsigned int)(a0 >> 32) == tag && (unsigned int)(a1 >> 32) == tag && (unsigned int)(b0 >> 32) == tag && (unsigned int)(b1 >> 32) == tag) { ok = true; break; }
+            if ((spin & 255) == 255) __nanosleep(32);
+        }
+        if (!ok) cm->status = 1;      // the controller turns this into N4J_ERR_COMM at the next error norm
+        t0 += __longlong_as_double((long long)((a0 & 0xFFFFFFFFull) | (a1 << 32)));
+        t1 += __longlong_as_double((long long)((b0 & 0xFFFFFFFFull) | (b1 << 32)));
+    }
+    s0 = t0; s1 = t1;
+}
+__device__ __forceinline__ bool bn_first_block() { return blockIdx.x == 0 && blockIdx.y == 0; }
+
 __device__ __forceinline__ void bn_fwd_final(const BnScratch& sc, int c, float& mean, float& inv) {
-    const double M = (double)sc.rows;
-    const double m = sc.accf[c * ACC_STRIDE] / M;
-    double var = sc.accf[(64 + c) * ACC_STRIDE] / M - m * m;
+    double s0 = sc.accf[c * ACC_STRIDE], s1 = sc.accf[(64 + c) * ACC_STRIDE];
+    double M = (double)sc.rows;
+    if (sc.cm) {
+        const unsigned int tag = *((volatile unsigned int*)sc.seqf);
+        if (bn_first_block()) bn_push2(sc.cm, sc.mbf, tag, c, s0, s1);
+        bn_gather2(sc.cm, sc.mbf, tag, c, s0, s1);
+        M = (double)sc.rows_total;
+    }
+    const double m = s0 / M;
+    double var = s1 / M - m * m;
     if (var < 0) var = 0;
     mean = (float)m;
     inv = (float)(1.0 / sqrt(var + (double)sc.eps));
 }
 __device__ __forceinline__ void bn_bwd_final(const BnScratch& sc, int c, float& m_dy, float& m_dyxh, float& dgamma, float& dbeta) {
-    const double M = (double)sc.rows;
-    const double sdy = sc.accb[c * ACC_STRIDE], sdyxh = sc.accb[(64 + c) * ACC_STRIDE];
+    double sdy = sc.accb[c * ACC_STRIDE], sdyxh = sc.accb[(64 + c) * ACC_STRIDE];
+    double M = (double)sc.rows;
+    if (sc.cm) {
+        const unsigned int tag = *((volatile unsigned int*)sc.seqb);
+        if (bn_first_block()) bn_push2(sc.cm, sc.mbb, tag, c, sdy, sdyxh);
+        bn_gather2(sc.cm, sc.mbb, tag, c, sdy, sdyxh);
+        M = (double)sc.rows_total;
+    }
     dgamma = (float)sdyxh;
     dbeta = (float)sdy;
     m_dy = (float)(sdy / M);
@@ -235,6 +298,8 @@ __device__ __forceinline__ void bn_bwd_final(const BnScratch& sc, int c, float& 
 }
 // producers: block 0 re-arms the accumulator set of the NEXT evaluation (all its readers finished before this kernel started)
 __device__ __forceinline__ void bn_rearm(double* other, int tid) { if (blockIdx.x == 0 && tid < 128) other[tid * ACC_STRIDE] = 0.0; }
+// ... and, on the sharded path, announces that the set it accumulates into has been produced once more (the consumers' tag)
+__device__ __forceinline__ void bn_bump(unsigned int* seq, int tid) { if (seq && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *seq += 1u; }
 
 // Last block, all threads: gather the 2*C strided accumulators into tot[] (shared), re-arm them, and (multi-GPU) sum over the ranks.
 __device__ __forceinline__ void bn_collect(const BnScratch& sc, int C, double* tot) {
@@ -277,7 +342,7 @@ __global__ void __launch_bounds__(256) k_bn_stats(Ref xin, long long M, int C, f
         }
         __threadfence();
     }
-    if (sc.deferred) { bn_rearm(sc.accf_other, threadIdx.x); return; }
+    if (sc.deferred) { bn_rearm(sc.accf_other, threadIdx.x); bn_bump(sc.cm ? sc.seqf : nullptr, threadIdx.x); return; }
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int tk = atomicAdd(sc.ticket, 1u);
@@ -551,7 +616,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_stats64(Ref gin, float gscale, R
         }
         __threadfence();
     }
-    if (sc.deferred) { bn_rearm(sc.accb_other, threadIdx.x); return; }   // dgamma / dbeta / means: written by the dx kernel behind this one
+    if (sc.deferred) { bn_rearm(sc.accb_other, threadIdx.x); bn_bump(sc.cm ? sc.seqb : nullptr, threadIdx.x); return; }   // dgamma / dbeta / means: written by the dx kernel behind this one
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int tk = atomicAdd(sc.ticket, 1u);

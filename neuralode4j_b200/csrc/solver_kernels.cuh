@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) k_stage_combine(const Ctrl* __restrict__ 
             }
             __threadfence();
         }
-        if (bf.sc.deferred) { bn_rearm(bf.sc.accf_other, threadIdx.x); return; }   // the consumers finalise (layer_kernels.cuh: BnScratch)
+        if (bf.sc.deferred) { bn_rearm(bf.sc.accf_other, threadIdx.x); bn_bump(bf.sc.cm ? bf.sc.seqf : nullptr, threadIdx.x); return; }   // the consumers finalise (layer_kernels.cuh: BnScratch)
         __syncthreads();
         if (threadIdx.x == 0) {
             const unsigned int tk = atomicAdd(bf.sc.ticket, 1u);
@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(256) k_stage_combine_last(const Ctrl* __restri
     // MODE 2 still reads the set behind accf_other (the first BatchNorm's sums of the evaluation being finished) in every block:
     // the operand prologue of the next convolution re-arms it instead (ConvTcArgs::prearm)
     if (MODE == 1) bn_rearm(bf.sc.accf_other, threadIdx.x);
+    bn_bump(bf.sc.cm ? bf.sc.seqf : nullptr, threadIdx.x);
 }
 
 // ---------------------------------------------------------------------------------------------------
