@@ -258,9 +258,8 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             if (threadIdx.x == 0) conv_stamp(a, 2);
             if (a.pbn.deferred && rr == rbase) {       // first (for W <= 14: only) pass; every thread of the CTA gets here
                 if (warp < 2 && a.pbn.cm) {
-                    const double2 gf = bn_gather2(a.pbn.cm, a.pbn.mbf, tagf, threadIdx.x, raw[0], raw[1]);
-                    raw[0] = gf.x; raw[1] = gf.y;
-                    if (PRO == 2) { const double2 gb = bn_gather2(a.pbn.cm, a.pbn.mbb, tagb, threadIdx.x, raw[2], raw[3]); raw[2] = gb.x; raw[3] = gb.y; }
+                    bn_gather2(a.pbn.cm, a.pbn.mbf, tagf, threadIdx.x, raw[0], raw[1]);
+                    if (PRO == 2) bn_gather2(a.pbn.cm, a.pbn.mbb, tagb, threadIdx.x, raw[2], raw[3]);
                 }
                 if (warp < 2)
                     conv_finalize_stats<PRO>(raw[0], raw[1], raw[2], raw[3], a.pbn.cm ? a.pbn.rows_total : a.pbn.rows, a.pbn.eps, s_fin,

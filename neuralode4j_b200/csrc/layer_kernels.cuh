@@ -229,7 +229,7 @@ struct BnScratch {
     long long mbf, mbb;     // byte offsets inside a comm region of the two sets' mailboxes: cell[source rank][128], 16 bytes each
 };
 
-// thread c (< 64) of one block: local sums s0 / s1 of channel c -> every peer's mailbox (one 32-byte group of four LL cells per channel)
+// thread c (< 64) of one block: local sums s0 (slot c) and s1 (slot 64 + c) of a set -> every peer's mailbox
 __device__ __forceinline__ void bn_push2(CommDev* cm, long long mb, unsigned int tag, int c, double s0, double s1) {
     const int me = cm->rank, W = cm->world;
     const unsigned long long hi = (unsigned long long)tag << 32;
@@ -237,52 +237,33 @@ __device__ __forceinline__ void bn_push2(CommDev* cm, long long mb, unsigned int
 #pragma unroll
     for (int q = 0; q < COMM_MAX_WORLD; ++q) {
         if (q < W && q != me) {
-            unsigned long long* cell = reinterpret_cast<unsigned long long*>(cm->peer[q] + cm->stat_off + mb) + ((long long)me * 64 + c) * 4;
+            unsigned long long* cell = reinterpret_cast<unsigned long long*>(cm->peer[q] + cm->stat_off + mb) + ((long long)me * 128 + c) * 2;
             asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(cell), "l"(hi | (b0 & 0xFFFFFFFFull)), "l"(hi | (b0 >> 32)) : "memory");
-            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(cell + 2), "l"(hi | (b1 & 0xFFFFFFFFull)), "l"(hi | (b1 >> 32)) : "memory");
+            asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(cell + 128), "l"(hi | (b1 & 0xFFFFFFFFull)), "l"(hi | (b1 >> 32)) : "memory");
         }
     }
 }
-// any thread c (< 64): s0 / s1 (local sums in, global totals out), peers' contributions added in rank order.  The cells of up to four
-// peers are requested together (one L2 round trip per group, not per peer) and re-requested until all carry the tag.
-__device__ __noinline__ double2 bn_gather2(CommDev* cm, long long mb, unsigned int tag, int c, double s0, double s1) {
+// any thread c (< 64): s0 / s1 (local sums in, global totals out), peers' contributions added in rank order
+__device__ __forceinline__ void bn_gather2(CommDev* cm, long long mb, unsigned int tag, int c, double& s0, double& s1) {
     const int me = cm->rank, W = cm->world;
-    const unsigned long long* mbox = reinterpret_cast<const unsigned long long*>(cm->peer[me] + cm->stat_off + mb) + (long long)c * 4;
+    const unsigned long long* mbox = reinterpret_cast<const unsigned long long*>(cm->peer[me] + cm->stat_off + mb);
     double t0 = 0.0, t1 = 0.0;
-    for (int q0 = 0; q0 < W; q0 += 4) {
-        unsigned long long v[4][4];
+    for (int q = 0; q < W; ++q) {
+        if (q == me) { t0 += s0; t1 += s1; continue; }
+        const unsigned long long* cell = mbox + ((long long)q * 128 + c) * 2;
+        unsigned long long a0 = 0, a1 = 0, b0 = 0, b1 = 0;
         bool ok = false;
-        for (unsigned int spin = 0; spin < (1u << 26) && !ok; ++spin) {
-            ok = true;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int q = q0 + j;
-                if (q < W && q != me) {
-                    const unsigned long long* cell = mbox + (long long)q * 64 * 4;
-                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v[j][0]), "=l"(v[j][1]) : "l"(cell) : "memory");
-                    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v[j][2]), "=l"(v[j][3]) : "l"(cell + 2) : "memory");
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int q = q0 + j;
-                if (q < W && q != me &&
-                    ((unsigned int)(v[j][0] >> 32) != tag || (unsigned int)(v[j][1] >> 32) != tag || (unsigned int)(v[j][2] >> 32) != tag || (unsigned int)(v[j][3] >> 32) != tag))
-                    ok = false;
-            }
-            if (!ok && (spin & 255) == 255) __nanosleep(32);
+        for (unsigned int spin = 0; spin < (1u << 26); ++spin) {
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(cell) : "memory");
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(b0), "=l"(b1) : "l"(cell + 128) : "memory");
+            if ((unsigned int)(a0 >> 32) == tag && (unsigned int)(a1 >> 32) == tag && (unsigned int)(b0 >> 32) == tag && (unsigned int)(b1 >> 32) == tag) { ok = true; break; }
+            if ((spin & 255) == 255) __nanosleep(32);
         }
         if (!ok) cm->status = 1;      // the controller turns this into N4J_ERR_COMM at the next error norm
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int q = q0 + j;
-            if (q >= W) continue;
-            if (q == me) { t0 += s0; t1 += s1; continue; }
-            t0 += __longlong_as_double((long long)((v[j][0] & 0xFFFFFFFFull) | (v[j][1] << 32)));
-            t1 += __longlong_as_double((long long)((v[j][2] & 0xFFFFFFFFull) | (v[j][3] << 32)));
-        }
+        t0 += __longlong_as_double((long long)((a0 & 0xFFFFFFFFull) | (a1 << 32)));
+        t1 += __longlong_as_double((long long)((b0 & 0xFFFFFFFFull) | (b1 << 32)));
     }
-    return make_double2(t0, t1);
+    s0 = t0; s1 = t1;
 }
 __device__ __forceinline__ bool bn_first_block() { return blockIdx.x == 0 && blockIdx.y == 0; }
 
@@ -292,8 +273,7 @@ __device__ __forceinline__ void bn_fwd_final(const BnScratch& sc, int c, float& 
     if (sc.cm) {
         const unsigned int tag = *((volatile unsigned int*)sc.seqf);
         if (bn_first_block()) bn_push2(sc.cm, sc.mbf, tag, c, s0, s1);
-        const double2 g = bn_gather2(sc.cm, sc.mbf, tag, c, s0, s1);
-        s0 = g.x; s1 = g.y;
+        bn_gather2(sc.cm, sc.mbf, tag, c, s0, s1);
         M = (double)sc.rows_total;
     }
     const double m = s0 / M;
@@ -308,8 +288,7 @@ __device__ __forceinline__ void bn_bwd_final(const BnScratch& sc, int c, float& 
     if (sc.cm) {
         const unsigned int tag = *((volatile unsigned int*)sc.seqb);
         if (bn_first_block()) bn_push2(sc.cm, sc.mbb, tag, c, sdy, sdyxh);
-        const double2 g = bn_gather2(sc.cm, sc.mbb, tag, c, sdy, sdyxh);
-        sdy = g.x; sdyxh = g.y;
+        bn_gather2(sc.cm, sc.mbb, tag, c, sdy, sdyxh);
         M = (double)sc.rows_total;
     }
     dgamma = (float)sdyxh;
