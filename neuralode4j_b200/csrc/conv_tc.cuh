@@ -144,7 +144,9 @@ __device__ __forceinline__ void conv_stamp_max(const ConvTcArgs& a, int slot) {
     if (a.dbg && blockIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long*>(a.dbg + slot), (unsigned long long)clock64());
 }
 
-template <int PASSES, int EPI, int PRO>
+// SH: sharded (multi-GPU) instantiation — the cross-rank statistics exchange of the deferred scheme is compiled in only there, so the
+// single-GPU kernels carry none of its code or registers (measured: +0.3 us per launch when it was a run-time branch).
+template <int PASSES, int EPI, int PRO, int SH = 0>
 __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcArgs a) {
     if (threadIdx.x == 0) conv_stamp(a, 0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // dependents may be scheduled; they park in their own wait
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         if (a.pbn.deferred && warp < 2) {      // warp-uniform on purpose: a real branch, not predicated double-precision code in all warps
             raw[0] = a.pbn.accf[threadIdx.x * ACC_STRIDE]; raw[1] = a.pbn.accf[(64 + threadIdx.x) * ACC_STRIDE];
             if (PRO == 2) { raw[2] = a.pbn.accb[threadIdx.x * ACC_STRIDE]; raw[3] = a.pbn.accb[(64 + threadIdx.x) * ACC_STRIDE]; }
-            if (a.pbn.cm) {      // sharded: CTA 0 sends this rank's local sums on their way now; the peers' sums are collected right before the finalisation
+            if (SH && a.pbn.cm) {      // sharded: CTA 0 sends this rank's local sums on their way now; the peers' sums are collected right before the finalisation
                 tagf = *((volatile unsigned int*)a.pbn.seqf);
                 if (PRO == 2) tagb = *((volatile unsigned int*)a.pbn.seqb);
                 if (blockIdx.x == 0) {
@@ -257,12 +259,12 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             }
             if (threadIdx.x == 0) conv_stamp(a, 2);
             if (a.pbn.deferred && rr == rbase) {       // first (for W <= 14: only) pass; every thread of the CTA gets here
-                if (warp < 2 && a.pbn.cm) {
+                if (SH && warp < 2 && a.pbn.cm) {
                     bn_gather2(a.pbn.cm, a.pbn.mbf, tagf, threadIdx.x, raw[0], raw[1]);
                     if (PRO == 2) bn_gather2(a.pbn.cm, a.pbn.mbb, tagb, threadIdx.x, raw[2], raw[3]);
                 }
                 if (warp < 2)
-                    conv_finalize_stats<PRO>(raw[0], raw[1], raw[2], raw[3], a.pbn.cm ? a.pbn.rows_total : a.pbn.rows, a.pbn.eps, s_fin,
+                    conv_finalize_stats<PRO>(raw[0], raw[1], raw[2], raw[3], (SH && a.pbn.cm) ? a.pbn.rows_total : a.pbn.rows, a.pbn.eps, s_fin,
                                              (PRO == 2 && blockIdx.x == 0) ? resolve(a.pdgamma) : nullptr, (PRO == 2 && blockIdx.x == 0) ? resolve(a.pdbeta) : nullptr);
                 __syncthreads();
                 if (threadIdx.x == 0) conv_stamp(a, 3);
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         if constexpr (EPI == 2) {
             __shared__ float s_mi[256];      // mean, invstd, gamma, beta of the BatchNorm in front
             if (a.bn.deferred) {
-                if (et < 64) bn_fwd_final(a.bn, et, s_mi[et], s_mi[64 + et]);
+                if (et < 64) bn_fwd_final<SH != 0>(a.bn, et, s_mi[et], s_mi[64 + et]);
             } else {
                 if (et < 64) s_mi[et] = a.bn.mean[et]; else if (et < 128) s_mi[et] = a.bn.invstd[et - 64];
             }
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 if (a.bn.deferred) {      // accumulate only; the consumers finalise, CTA 0 re-arms the next evaluation's set
                     atomicAdd((EPI == 1 ? a.bn.accf : a.bn.accb) + et * ACC_STRIDE, tsum);
                     bn_rearm(EPI == 1 ? a.bn.accf_other : a.bn.accb_other, et);
-                    bn_bump(a.bn.cm ? (EPI == 1 ? a.bn.seqf : a.bn.seqb) : nullptr, et);
+                    if (SH) bn_bump(a.bn.cm ? (EPI == 1 ? a.bn.seqf : a.bn.seqb) : nullptr, et);
                 } else {                  // legacy / multi-GPU: the last CTA finalises (and exchanges the sums between the ranks)
                     atomicAdd(a.bn.acc + et * ACC_STRIDE, tsum);
                     __threadfence();

@@ -561,13 +561,21 @@ void Engine::launch_gemm_tc(cudaStream_t s, const CUtensorMap&, const CUtensorMa
 
 template <int PRO, int EPI>
 static void launch_conv_variant(const ConvTcArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, bool fast) {
-    if (fast) launch_k(k_conv3x3_tc<1, EPI, PRO>, grid, block, smem, s, pdl, a);
-    else launch_k(k_conv3x3_tc<3, EPI, PRO>, grid, block, smem, s, pdl, a);
+    const bool sh = a.pbn.cm != nullptr || a.bn.cm != nullptr;      // sharded instantiation: carries the cross-rank statistics exchange
+    if (sh) {
+        if (fast) launch_k(k_conv3x3_tc<1, EPI, PRO, 1>, grid, block, smem, s, pdl, a);
+        else launch_k(k_conv3x3_tc<3, EPI, PRO, 1>, grid, block, smem, s, pdl, a);
+    } else {
+        if (fast) launch_k(k_conv3x3_tc<1, EPI, PRO, 0>, grid, block, smem, s, pdl, a);
+        else launch_k(k_conv3x3_tc<3, EPI, PRO, 0>, grid, block, smem, s, pdl, a);
+    }
 }
 template <int PRO, int EPI>
 static void set_conv_smem(size_t smem) {
-    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, EPI, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, EPI, PRO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, EPI, PRO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, EPI, PRO, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, EPI, PRO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, EPI, PRO, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 }
 // the (prologue, epilogue) combinations the engine launches: forward convs take PRO 0/1 with EPI 0/1, dgrad convs PRO 0/2 with EPI 0/2
 static void set_conv_smem_all(size_t smem) {

@@ -267,10 +267,11 @@ __device__ __forceinline__ void bn_gather2(CommDev* cm, long long mb, unsigned i
 }
 __device__ __forceinline__ bool bn_first_block() { return blockIdx.x == 0 && blockIdx.y == 0; }
 
+template <bool SH = true>
 __device__ __forceinline__ void bn_fwd_final(const BnScratch& sc, int c, float& mean, float& inv) {
     double s0 = sc.accf[c * ACC_STRIDE], s1 = sc.accf[(64 + c) * ACC_STRIDE];
     double M = (double)sc.rows;
-    if (sc.cm) {
+    if (SH && sc.cm) {
         const unsigned int tag = *((volatile unsigned int*)sc.seqf);
         if (bn_first_block()) bn_push2(sc.cm, sc.mbf, tag, c, s0, s1);
         bn_gather2(sc.cm, sc.mbf, tag, c, s0, s1);
