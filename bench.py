@@ -515,6 +515,48 @@ def _parity_block(gpu, orc):
             "out": _deviation(o["out"], orc["out"]), "dL_dy0": _deviation(o["dy0"], orc["dy0"]), "dL_dtheta": _deviation(o["grad"], orc["grad"])}
 
 
+def _full_train_step(args):
+    """one whole training step of the reference's MNIST model (stem + ODE block + output block + loss +
+    Nesterovs) through node4j_net_train_step, host buffers in and out (images, labels, parameters, updater state), wall clock."""
+    from neuralode4j_b200.net import OdeNetModel
+    from neuralode4j_b200 import workloads as W
+    try:
+        model = OdeNetModel(batch=BATCH, nrofKernels=64, flags=args.flags)
+        rng = np.random.default_rng(7)
+        p = (rng.uniform(-1, 1, model.numParams()) * 0.05).astype(np.float32)
+        o, n = model.ode_slice
+        p[o:o + n] = W.mnist_block(batch=BATCH).params
+        C = 64
+        # BatchNorm layers of the outer network: gamma 1, beta 0, running mean 0, var 1 (the order OuterLayout of oracle/outer_oracle.py documents)
+        offs, off = [], 10 * C
+        for _ in range(2):
+            offs.append(off); off += 4 * C + C * C + C * C * 9
+            offs.append(off); off += 4 * C + C * C * 9
+        offs.append(o + n)
+        for b in offs:
+            p[b:b + C] = 1; p[b + C:b + 3 * C] = 0; p[b + 3 * C:b + 4 * C] = 1
+        model.setParams(p)
+        images = rng.standard_normal((BATCH, 1, 28, 28)).astype(np.float32)
+        labels = np.eye(10, dtype=np.float32)[rng.integers(0, 10, BATCH)]
+        scores = [model.fit(images, labels, lr=0.01) for _ in range(2)]
+        t0 = time.perf_counter()
+        k = 5
+        for _ in range(k):
+            scores.append(model.fit(images, labels, lr=0.01))
+        ms = (time.perf_counter() - t0) / k * 1e3
+        fs, bs = model.ode_fwd_stats, model.ode_bwd_stats
+        out = {"config": "whole MNIST ODE-net training step (examples/mnist/OdeNetModel.java:60-88): ResBlockStem + OdeVertex + Output, LossMCXENT, Nesterovs; batch 128, "
+                         "64 kernels; host buffers through node4j_net_train_step, wall clock",
+               "value": BATCH / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": k, "scores": [float(x) for x in scores],
+               "ode_block": {"fwd": [int(fs.nfe), int(fs.accepted), int(fs.rejected)], "bwd": [int(bs.nfe), int(bs.accepted), int(bs.rejected)],
+                             "gpu_ms": float(fs.gpu_ms + bs.gpu_ms)},
+               "note": "the layers around the block are plain direct kernels with double accumulation (not the hot path, DESIGN.md section 10)"}
+        model.close()
+        return out
+    except Exception as e:      # an extra: never fail the bench line over it
+        return {"unavailable": repr(e)}
+
+
 def run_ours(args):
     from neuralode4j_b200 import _lib
     B = Bench(args)
@@ -585,6 +627,9 @@ def run_ours(args):
                 except Exception as e:      # a context number: never fail the bench line over it
                     entry["cpu_baseline"] = {"unavailable": repr(e)}
             other[cname] = entry
+
+    if is_mnist and world == 1 and not args.quick:
+        other["mnist_full_train_step"] = _full_train_step(args)
 
     if rank != 0:
         if world > 1:

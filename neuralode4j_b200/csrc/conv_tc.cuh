@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
         if constexpr (EPI == 2) {
             __shared__ float s_mi[256];      // mean, invstd, gamma, beta of the BatchNorm in front
             if (a.bn.deferred) {
-                if (et < 64) bn_fwd_final<SH != 0, false>(a.bn, et, s_mi[et], s_mi[64 + et]);   // runs while the tensor core works: the per-peer gather is off the critical path
+                if (et < 64) bn_fwd_final<SH != 0, true>(a.bn, et, s_mi[et], s_mi[64 + et]);   // all peers requested at once (per-peer polling cost +2 us at eight ranks)
             } else {
                 if (et < 64) s_mi[et] = a.bn.mean[et]; else if (et < 128) s_mi[et] = a.bn.invstd[et - 64];
             }
