@@ -42,39 +42,67 @@ inline ConvShape make_conv_shape(int B, int Ci, int H, int W, int Co, int K, int
 }
 
 // y[b,co,oh,ow] = act( (float)sum_{ci,kh,kw} x[b,ci,oh*S+kh-pt,ow*S+kw-pl] * w[co,ci,kh,kw]  + bias[co] )
+// One thread = one output pixel x OUTER_CT output channels (the x value is loaded once per (ci, tap) and used OUTER_CT times); the
+// weights of the block's channel tile sit in shared memory and are read as warp broadcasts.  blockIdx.y = channel tile.
+constexpr int OUTER_CT = 8;
 __global__ void __launch_bounds__(256) k_outer_conv_fwd(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                                                          float* __restrict__ y, ConvShape c, int relu) {
-    const long long n = (long long)c.B * c.Co * c.Ho * c.Wo;
+    extern __shared__ float s_w[];                       // [OUTER_CT][Ci*K*K]
+    const int co0 = blockIdx.y * OUTER_CT, wlen = c.Ci * c.K * c.K;
+    for (int i = threadIdx.x; i < OUTER_CT * wlen; i += blockDim.x) {
+        const int t = i / wlen;
+        s_w[i] = co0 + t < c.Co ? w[(long long)(co0 + t) * wlen + (i - t * wlen)] : 0.f;
+    }
+    __syncthreads();
+    const long long n = (long long)c.B * c.Ho * c.Wo;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int ow = (int)(i % c.Wo), oh = (int)((i / c.Wo) % c.Ho), co = (int)((i / ((long long)c.Wo * c.Ho)) % c.Co), b = (int)(i / ((long long)c.Wo * c.Ho * c.Co));
-        double acc = 0.0;
+        const int ow = (int)(i % c.Wo), oh = (int)((i / c.Wo) % c.Ho), b = (int)(i / ((long long)c.Wo * c.Ho));
+        double acc[OUTER_CT];
+#pragma unroll
+        for (int t = 0; t < OUTER_CT; ++t) acc[t] = 0.0;
         for (int ci = 0; ci < c.Ci; ++ci) {
             const float* xb = x + ((long long)b * c.Ci + ci) * c.H * c.W;
-            const float* wb = w + ((long long)co * c.Ci + ci) * c.K * c.K;
             for (int kh = 0; kh < c.K; ++kh) {
                 const int ih = oh * c.S + kh - c.pt;
                 if (ih < 0 || ih >= c.H) continue;
                 for (int kw = 0; kw < c.K; ++kw) {
                     const int iw = ow * c.S + kw - c.pl;
                     if (iw < 0 || iw >= c.W) continue;
-                    acc += (double)xb[ih * c.W + iw] * (double)wb[kh * c.K + kw];
+                    const double xv = (double)xb[ih * c.W + iw];
+                    const float* wp = s_w + (ci * c.K + kh) * c.K + kw;
+#pragma unroll
+                    for (int t = 0; t < OUTER_CT; ++t) acc[t] += xv * (double)wp[t * wlen];
                 }
             }
         }
-        float v = (float)acc;
-        if (bias) v = __fadd_rn(v, bias[co]);
-        if (relu && !(v > 0.f)) v = 0.f;
-        y[i] = v;
+#pragma unroll
+        for (int t = 0; t < OUTER_CT; ++t) {
+            if (co0 + t >= c.Co) break;
+            float v = (float)acc[t];
+            if (bias) v = __fadd_rn(v, bias[co0 + t]);
+            if (relu && !(v > 0.f)) v = 0.f;
+            y[(((long long)b * c.Co + co0 + t) * c.Ho + oh) * c.Wo + ow] = v;
+        }
     }
 }
 
 // dx[b,ci,h,w] = (float)sum_{co,kh,kw} dz[b,co,oh,ow] * w[co,ci,kh,kw],  oh*S + kh - pt = h;  dz = relu ? (y > 0 ? dy : 0) : dy
+// One thread = one input pixel x OUTER_CT input channels; blockIdx.y = input-channel tile, its weights [Co][OUTER_CT][K*K] in shared memory.
 __global__ void __launch_bounds__(256) k_outer_conv_dgrad(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ w,
                                                            float* __restrict__ dx, ConvShape c, int relu) {
-    const long long n = (long long)c.B * c.Ci * c.H * c.W;
+    extern __shared__ float s_w[];                       // [Co][OUTER_CT][K*K]
+    const int ci0 = blockIdx.y * OUTER_CT, kk = c.K * c.K;
+    for (int i = threadIdx.x; i < c.Co * OUTER_CT * kk; i += blockDim.x) {
+        const int co = i / (OUTER_CT * kk), r = i - co * OUTER_CT * kk, t = r / kk, k = r - t * kk;
+        s_w[i] = ci0 + t < c.Ci ? w[((long long)co * c.Ci + ci0 + t) * kk + k] : 0.f;
+    }
+    __syncthreads();
+    const long long n = (long long)c.B * c.H * c.W;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int iw = (int)(i % c.W), ih = (int)((i / c.W) % c.H), ci = (int)((i / ((long long)c.W * c.H)) % c.Ci), b = (int)(i / ((long long)c.W * c.H * c.Ci));
-        double acc = 0.0;
+        const int iw = (int)(i % c.W), ih = (int)((i / c.W) % c.H), b = (int)(i / ((long long)c.W * c.H));
+        double acc[OUTER_CT];
+#pragma unroll
+        for (int t = 0; t < OUTER_CT; ++t) acc[t] = 0.0;
         for (int kh = 0; kh < c.K; ++kh) {
             const int th = ih + c.pt - kh;
             if (th < 0 || th % c.S) continue;
@@ -89,55 +117,65 @@ __global__ void __launch_bounds__(256) k_outer_conv_dgrad(const float* __restric
                     const long long o = (((long long)b * c.Co + co) * c.Ho + oh) * c.Wo + ow;
                     float g = dy[o];
                     if (relu && !(y[o] > 0.f)) g = 0.f;
-                    acc += (double)g * (double)w[(((long long)co * c.Ci + ci) * c.K + kh) * c.K + kw];
+                    if (g == 0.f) continue;
+                    const double gd = (double)g;
+                    const float* wp = s_w + co * OUTER_CT * kk + kh * c.K + kw;
+#pragma unroll
+                    for (int t = 0; t < OUTER_CT; ++t) acc[t] += gd * (double)wp[t * kk];
                 }
             }
         }
-        dx[i] = (float)acc;
+#pragma unroll
+        for (int t = 0; t < OUTER_CT; ++t)
+            if (ci0 + t < c.Ci) dx[(((long long)b * c.Ci + ci0 + t) * c.H + ih) * c.W + iw] = (float)acc[t];
     }
 }
 
-// One block per (co, ci): dw[co,ci,kh,kw] = (float)sum_{b,oh,ow} dz[b,co,oh,ow] * x[b,ci,oh*S+kh-pt,ow*S+kw-pl]; blocks with ci == 0 also
-// produce db[co] = (float)sum dz.  Per-thread double partials, combined by a fixed shared-memory tree (deterministic).
-__global__ void __launch_bounds__(128) k_outer_conv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
-                                                           float* __restrict__ dw, float* __restrict__ db, ConvShape c, int relu) {
-    const int co = blockIdx.x / c.Ci, ci = blockIdx.x % c.Ci;
-    double acc[10];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) acc[k] = 0.0;
+// Weight gradient.  grid = (Co, OUTER_WSPLIT): one block per output channel and batch slice; thread = (ci, tap) — every thread of the
+// block reads the same dz value (broadcast) and its own x value, so dz is read once per (co, slice) instead of once per (co, ci).
+// part[slice][co][ci][tap] (and part_b[slice][co]) hold double partials; k_outer_wgrad_finish adds the slices in a fixed order.
+constexpr int OUTER_WSPLIT = 8;
+__global__ void __launch_bounds__(640) k_outer_conv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
+                                                           double* __restrict__ part, double* __restrict__ part_b, ConvShape c, int relu) {
+    const int co = blockIdx.x, slice = blockIdx.y, kk = c.K * c.K, nout = c.Ci * kk;
     const int per = c.Ho * c.Wo;
-    const long long n = (long long)c.B * per;
-    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-        const int b = (int)(i / per), r = (int)(i % per), oh = r / c.Wo, ow = r % c.Wo;
-        const long long o = ((long long)b * c.Co + co) * per + r;
-        float g = dy[o];
-        if (relu && !(y[o] > 0.f)) g = 0.f;
-        if (g == 0.f) continue;
-        acc[9] += (double)g;
-        const float* xb = x + ((long long)b * c.Ci + ci) * c.H * c.W;
-        for (int kh = 0; kh < c.K; ++kh) {
-            const int ih = oh * c.S + kh - c.pt;
-            if (ih < 0 || ih >= c.H) continue;
-            for (int kw = 0; kw < c.K; ++kw) {
-                const int iw = ow * c.S + kw - c.pl;
-                if (iw < 0 || iw >= c.W) continue;
-                acc[kh * c.K + kw] += (double)g * (double)xb[ih * c.W + iw];
+    const int b0 = (int)((long long)c.B * slice / OUTER_WSPLIT), b1 = (int)((long long)c.B * (slice + 1) / OUTER_WSPLIT);
+    for (int o = threadIdx.x; o < nout + 1; o += blockDim.x) {      // the extra "output" is the bias gradient
+        const int ci = o / kk, k = o - ci * kk, kh = k / c.K, kw = k - kh * c.K;
+        double acc = 0.0;
+        for (int b = b0; b < b1; ++b) {
+            const float* dyb = dy + ((long long)b * c.Co + co) * per;
+            const float* yb = y + ((long long)b * c.Co + co) * per;
+            const float* xb = x + ((long long)b * c.Ci + (o < nout ? ci : 0)) * c.H * c.W;
+            for (int oh = 0; oh < c.Ho; ++oh) {
+                const int ih = oh * c.S + kh - c.pt;
+                if (o < nout && (ih < 0 || ih >= c.H)) continue;
+                for (int ow = 0; ow < c.Wo; ++ow) {
+                    float g = dyb[oh * c.Wo + ow];
+                    if (relu && !(yb[oh * c.Wo + ow] > 0.f)) g = 0.f;
+                    if (o == nout) { acc += (double)g; continue; }
+                    const int iw = ow * c.S + kw - c.pl;
+                    if (iw < 0 || iw >= c.W) continue;
+                    acc += (double)g * (double)xb[ih * c.W + iw];
+                }
             }
         }
+        if (o < nout) part[((long long)slice * c.Co + co) * nout + o] = acc;
+        else if (part_b) part_b[slice * c.Co + co] = acc;
     }
-    __shared__ double sm[10][128];
-#pragma unroll
-    for (int k = 0; k < 10; ++k) sm[k][threadIdx.x] = acc[k];
-    __syncthreads();
-    for (int s = 64; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) {
-#pragma unroll
-            for (int k = 0; k < 10; ++k) sm[k][threadIdx.x] += sm[k][threadIdx.x + s];
+}
+__global__ void __launch_bounds__(256) k_outer_wgrad_finish(const double* __restrict__ part, const double* __restrict__ part_b, float* __restrict__ dw,
+                                                             float* __restrict__ db, long long n, int Co) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n + (db ? Co : 0); i += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        if (i < n) {
+            for (int q = 0; q < OUTER_WSPLIT; ++q) s += part[q * n + i];
+            dw[i] = (float)s;
+        } else {
+            for (int q = 0; q < OUTER_WSPLIT; ++q) s += part_b[q * Co + (i - n)];
+            db[i - n] = (float)s;
         }
-        __syncthreads();
     }
-    if ((int)threadIdx.x < c.K * c.K) dw[((long long)co * c.Ci + ci) * c.K * c.K + threadIdx.x] = (float)sm[threadIdx.x][0];
-    if (db && ci == 0 && threadIdx.x == 0) db[co] = (float)sm[9][0];
 }
 
 // BatchNorm (training), NCHW, one block per channel.  st: [mean | invstd | batch var] x C
@@ -328,6 +366,9 @@ private:
     };
     void forward(const float* p, const float* images, const float* labels, bool train, n4j_stats* ode_fwd);
     float* dev_alloc(long long n);
+    void conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvShape& c, int relu);
+    void conv_dgrad(const float* dy, const float* y, const float* w, float* dx, const ConvShape& c, int relu);
+    void conv_wgrad(const float* x, const float* dy, const float* y, float* dw, float* db, const ConvShape& c, int relu);
     bool is_dev(const void* p) const;
     int grid(long long n) const { return (int)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 8)); }
 
@@ -343,6 +384,7 @@ private:
     float *img_ = nullptr, *lab_ = nullptr, *a0_ = nullptr, *z1_ = nullptr, *no_ = nullptr, *sto_ = nullptr, *pool_ = nullptr, *probs_ = nullptr;
     float *d1_ = nullptr, *d2_ = nullptr, *d3_ = nullptr, *dpool_ = nullptr, *score_ = nullptr, *tdev_ = nullptr;
     double* score_parts_ = nullptr;
+    double *wpart_ = nullptr, *wpart_b_ = nullptr;      // weight-gradient partials of the outer convolutions [OUTER_WSPLIT][Co][Ci*K*K]
     std::vector<void*> allocs_;
 };
 
@@ -351,6 +393,23 @@ inline float* OuterNet::dev_alloc(long long n) {
     N4J_CUDA(cudaMalloc(&p, sizeof(float) * std::max<long long>(n, 1)));
     allocs_.push_back(p);
     return p;
+}
+inline void OuterNet::conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvShape& c, int relu) {
+    const long long n = (long long)c.B * c.Ho * c.Wo;
+    const dim3 g((unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 4)), (unsigned)((c.Co + OUTER_CT - 1) / OUTER_CT));
+    k_outer_conv_fwd<<<g, 256, sizeof(float) * OUTER_CT * c.Ci * c.K * c.K, s_>>>(x, w, bias, y, c, relu);
+}
+inline void OuterNet::conv_dgrad(const float* dy, const float* y, const float* w, float* dx, const ConvShape& c, int relu) {
+    const long long n = (long long)c.B * c.H * c.W;
+    const dim3 g((unsigned)std::max<long long>(1, std::min<long long>((n + 255) / 256, 148LL * 4)), (unsigned)((c.Ci + OUTER_CT - 1) / OUTER_CT));
+    k_outer_conv_dgrad<<<g, 256, sizeof(float) * c.Co * OUTER_CT * c.K * c.K, s_>>>(dy, y, w, dx, c, relu);
+}
+inline void OuterNet::conv_wgrad(const float* x, const float* dy, const float* y, float* dw, float* db, const ConvShape& c, int relu) {
+    const int nout = c.Ci * c.K * c.K;
+    const int threads = std::min(640, ((nout + 1 + 31) / 32) * 32);
+    k_outer_conv_wgrad<<<dim3(c.Co, OUTER_WSPLIT), threads, 0, s_>>>(x, dy, y, wpart_, db ? wpart_b_ : nullptr, c, relu);
+    const long long n = (long long)c.Co * nout;
+    k_outer_wgrad_finish<<<grid(n + c.Co), 256, 0, s_>>>(wpart_, wpart_b_, dw, db, n, c.Co);
 }
 inline bool OuterNet::is_dev(const void* p) const {
     cudaPointerAttributes a{};
@@ -418,6 +477,8 @@ inline OuterNet::OuterNet(int batch, int channels, const n4j_solver_cfg& cfg, fl
     d1_ = dev_alloc(n0); d2_ = dev_alloc(n0); d3_ = dev_alloc(n0);
     score_ = dev_alloc(1); tdev_ = dev_alloc(2);
     N4J_CUDA(cudaMalloc(&score_parts_, sizeof(double) * batch)); allocs_.push_back(score_parts_);
+    N4J_CUDA(cudaMalloc(&wpart_, sizeof(double) * OUTER_WSPLIT * (size_t)C * C * 9)); allocs_.push_back(wpart_);
+    N4J_CUDA(cudaMalloc(&wpart_b_, sizeof(double) * OUTER_WSPLIT * (size_t)C)); allocs_.push_back(wpart_b_);
     N4J_CUDA(cudaMemcpy(tdev_, time_, sizeof(time_), cudaMemcpyHostToDevice));
 }
 
@@ -428,7 +489,7 @@ inline OuterNet::~OuterNet() {
 
 inline void OuterNet::forward(const float* p, const float* images, const float* labels, bool train, n4j_stats* ode_fwd) {
     const int C = C_, B = B_;
-    k_outer_conv_fwd<<<grid((long long)B * C * 26 * 26), 256, 0, s_>>>(images, p + off_in_w_, p + off_in_b_, a0_, cin_, 0);
+    conv_fwd(images, p + off_in_w_, p + off_in_b_, a0_, cin_, 0);
     const float* a = a0_;
     for (int r = 0; r < 2; ++r) {
         Block& b = blk_[r];
@@ -436,11 +497,11 @@ inline void OuterNet::forward(const float* p, const float* images, const float* 
         const long long nin = (long long)B * C * HWi, nout = (long long)B * C * HWo;
         if (train) k_outer_bn_fwd<<<C, 256, 0, s_>>>(a, p + b.o_bn1, p + b.o_bn1 + C, b.n1, b.st1, B, C, HWi, 1e-5f, 1);
         else k_outer_bn_infer<<<grid(nin), 256, 0, s_>>>(a, p + b.o_bn1, b.n1, nin, C, HWi, 1e-5f, 1);
-        k_outer_conv_fwd<<<grid(nout), 256, 0, s_>>>(b.n1, p + b.o_ds, nullptr, b.dsy, b.ds, 0);
-        k_outer_conv_fwd<<<grid(nout), 256, 0, s_>>>(b.n1, p + b.o_c1, nullptr, b.f1, b.c1, 1);      // ReLU: examples/mnist/LayerUtil.java:111-116
+        conv_fwd(b.n1, p + b.o_ds, nullptr, b.dsy, b.ds, 0);
+        conv_fwd(b.n1, p + b.o_c1, nullptr, b.f1, b.c1, 1);      // ReLU: examples/mnist/LayerUtil.java:111-116
         if (train) k_outer_bn_fwd<<<C, 256, 0, s_>>>(b.f1, p + b.o_bn2, p + b.o_bn2 + C, b.n2, b.st2, B, C, HWo, 1e-5f, 1);
         else k_outer_bn_infer<<<grid(nout), 256, 0, s_>>>(b.f1, p + b.o_bn2, b.n2, nout, C, HWo, 1e-5f, 1);
-        k_outer_conv_fwd<<<grid(nout), 256, 0, s_>>>(b.n2, p + b.o_c2, nullptr, b.f2, b.c2, 0);
+        conv_fwd(b.n2, p + b.o_c2, nullptr, b.f2, b.c2, 0);
         k_outer_add<<<grid(nout), 256, 0, s_>>>(b.dsy, b.f2, b.a_out, nout);                          // ElementWiseVertex(Add): stemAdd_r
         a = b.a_out;
     }
@@ -492,22 +553,22 @@ inline void OuterNet::train_step(float* params, float* updater_state, const floa
         const int HWi = b.Hin * b.Hin, HWo = b.Hout * b.Hout;
         const long long nin = (long long)B * C * HWi;
         // secondConv (identity): weight gradient, then dL/dn2 into t1
-        k_outer_conv_wgrad<<<C * C, 128, 0, s_>>>(b.n2, da, b.f2, g_ + b.o_c2, nullptr, b.c2, 0);
-        k_outer_conv_dgrad<<<grid((long long)B * C * HWo), 256, 0, s_>>>(da, b.f2, p_ + b.o_c2, t1, b.c2, 0);
+        conv_wgrad(b.n2, da, b.f2, g_ + b.o_c2, nullptr, b.c2, 0);
+        conv_dgrad(da, b.f2, p_ + b.o_c2, t1, b.c2, 0);
         // secondNorm: dL/df1 into t2
         k_outer_bn_bwd<<<C, 256, 0, s_>>>(b.f1, b.n2, t1, p_ + b.o_bn2, b.st2, t2, g_ + b.o_bn2, B, C, HWo, 1, 0.1f);
         // firstConv (ReLU) and downSample (identity) both read n1: dL/dn1 = downSample's epsilon + firstConv's epsilon
-        k_outer_conv_wgrad<<<C * C, 128, 0, s_>>>(b.n1, t2, b.f1, g_ + b.o_c1, nullptr, b.c1, 1);
-        k_outer_conv_wgrad<<<C * C, 128, 0, s_>>>(b.n1, da, b.dsy, g_ + b.o_ds, nullptr, b.ds, 0);
-        k_outer_conv_dgrad<<<grid(nin), 256, 0, s_>>>(t2, b.f1, p_ + b.o_c1, t1, b.c1, 1);             // t1: firstConv's epsilon  [B,C,Hin,Hin]
-        k_outer_conv_dgrad<<<grid(nin), 256, 0, s_>>>(da, b.dsy, p_ + b.o_ds, t2, b.ds, 0);            // t2: downSample's epsilon
+        conv_wgrad(b.n1, t2, b.f1, g_ + b.o_c1, nullptr, b.c1, 1);
+        conv_wgrad(b.n1, da, b.dsy, g_ + b.o_ds, nullptr, b.ds, 0);
+        conv_dgrad(t2, b.f1, p_ + b.o_c1, t1, b.c1, 1);             // t1: firstConv's epsilon  [B,C,Hin,Hin]
+        conv_dgrad(da, b.dsy, p_ + b.o_ds, t2, b.ds, 0);            // t2: downSample's epsilon
         k_outer_add<<<grid(nin), 256, 0, s_>>>(t2, t1, t1, nin);
         // firstNorm: dL/d(block input) into da's next buffer
         k_outer_bn_bwd<<<C, 256, 0, s_>>>(a_in, b.n1, t1, p_ + b.o_bn1, b.st1, t2, g_ + b.o_bn1, B, C, HWi, 1, 0.1f);
         std::swap(da, t2);
         // keep three distinct buffers: da (new epsilon), t1, t2 (scratch)
     }
-    k_outer_conv_wgrad<<<C, 128, 0, s_>>>(img_, da, a0_, g_ + off_in_w_, g_ + off_in_b_, cin_, 0);
+    conv_wgrad(img_, da, a0_, g_ + off_in_w_, g_ + off_in_b_, cin_, 0);
     // ---- update ----------------------------------------------------------------------------------------------------------------
     if (grad_out) N4J_CUDA(cudaMemcpyAsync(grad_out, g_, sizeof(float) * n_, cudaMemcpyDefault, s_));
     k_outer_update<<<grid(n_), 256, 0, s_>>>(p_, v_, g_, kind_, n_, (float)B, lr, mu, (float)(1.0 + (double)mu));
