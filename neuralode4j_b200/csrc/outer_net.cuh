@@ -131,37 +131,53 @@ __global__ void __launch_bounds__(256) k_outer_conv_dgrad(const float* __restric
     }
 }
 
-// Weight gradient.  grid = (Co, OUTER_WSPLIT): one block per output channel and batch slice; thread = (ci, tap) — every thread of the
-// block reads the same dz value (broadcast) and its own x value, so dz is read once per (co, slice) instead of once per (co, ci).
-// part[slice][co][ci][tap] (and part_b[slice][co]) hold double partials; k_outer_wgrad_finish adds the slices in a fixed order.
+// Weight gradient.  grid = (Co, ceil(Ci / 16), OUTER_WSPLIT), block = 16 warps: one WARP per (co, ci, batch slice).  The lanes stride over
+// the slice's output pixels — dz and x are read along their contiguous dimension — with K*K (<= 9) double accumulators each, combined
+// by a shuffle butterfly (fixed order: deterministic).  part[slice][co][ci][tap] / part_b[slice][co] hold double partials;
+// k_outer_wgrad_finish adds the slices in a fixed order.
 constexpr int OUTER_WSPLIT = 8;
-__global__ void __launch_bounds__(640) k_outer_conv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
+__global__ void __launch_bounds__(512) k_outer_conv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
                                                            double* __restrict__ part, double* __restrict__ part_b, ConvShape c, int relu) {
-    const int co = blockIdx.x, slice = blockIdx.y, kk = c.K * c.K, nout = c.Ci * kk;
+    const int co = blockIdx.x, slice = blockIdx.z, kk = c.K * c.K, nout = c.Ci * kk;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci = blockIdx.y * 16 + warp;
+    if (ci >= c.Ci) return;
     const int per = c.Ho * c.Wo;
     const int b0 = (int)((long long)c.B * slice / OUTER_WSPLIT), b1 = (int)((long long)c.B * (slice + 1) / OUTER_WSPLIT);
-    for (int o = threadIdx.x; o < nout + 1; o += blockDim.x) {      // the extra "output" is the bias gradient
-        const int ci = o / kk, k = o - ci * kk, kh = k / c.K, kw = k - kh * c.K;
-        double acc = 0.0;
-        for (int b = b0; b < b1; ++b) {
-            const float* dyb = dy + ((long long)b * c.Co + co) * per;
-            const float* yb = y + ((long long)b * c.Co + co) * per;
-            const float* xb = x + ((long long)b * c.Ci + (o < nout ? ci : 0)) * c.H * c.W;
-            for (int oh = 0; oh < c.Ho; ++oh) {
-                const int ih = oh * c.S + kh - c.pt;
-                if (o < nout && (ih < 0 || ih >= c.H)) continue;
-                for (int ow = 0; ow < c.Wo; ++ow) {
-                    float g = dyb[oh * c.Wo + ow];
-                    if (relu && !(yb[oh * c.Wo + ow] > 0.f)) g = 0.f;
-                    if (o == nout) { acc += (double)g; continue; }
-                    const int iw = ow * c.S + kw - c.pl;
-                    if (iw < 0 || iw >= c.W) continue;
-                    acc += (double)g * (double)xb[ih * c.W + iw];
-                }
+    double acc[9], accb = 0.0;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+    const int n = (b1 - b0) * per;
+    for (int i = lane; i < n; i += 32) {
+        const int b = b0 + i / per, r = i % per, oh = r / c.Wo, ow = r - oh * c.Wo;
+        const long long o = ((long long)b * c.Co + co) * per + r;
+        float g = dy[o];
+        if (relu && !(y[o] > 0.f)) g = 0.f;
+        if (g == 0.f) continue;
+        const double gd = (double)g;
+        accb += gd;
+        const float* xb = x + ((long long)b * c.Ci + ci) * c.H * c.W;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            if (kh >= c.K) break;
+            const int ih = oh * c.S + kh - c.pt;
+            if (ih < 0 || ih >= c.H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                if (kw >= c.K) break;
+                const int iw = ow * c.S + kw - c.pl;
+                if (iw < 0 || iw >= c.W) continue;
+                acc[kh * 3 + kw] += gd * (double)xb[ih * c.W + iw];
             }
         }
-        if (o < nout) part[((long long)slice * c.Co + co) * nout + o] = acc;
-        else if (part_b) part_b[slice * c.Co + co] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = warp_sum(acc[k]);
+    accb = warp_sum(accb);
+    if (lane == 0) {
+        for (int kh = 0; kh < c.K; ++kh)
+            for (int kw = 0; kw < c.K; ++kw) part[((long long)slice * c.Co + co) * nout + ci * kk + kh * c.K + kw] = acc[kh * 3 + kw];
+        if (part_b && ci == 0) part_b[slice * c.Co + co] = accb;
     }
 }
 __global__ void __launch_bounds__(256) k_outer_wgrad_finish(const double* __restrict__ part, const double* __restrict__ part_b, float* __restrict__ dw,
@@ -405,9 +421,9 @@ inline void OuterNet::conv_dgrad(const float* dy, const float* y, const float* w
     k_outer_conv_dgrad<<<g, 256, sizeof(float) * c.Co * OUTER_CT * c.K * c.K, s_>>>(dy, y, w, dx, c, relu);
 }
 inline void OuterNet::conv_wgrad(const float* x, const float* dy, const float* y, float* dw, float* db, const ConvShape& c, int relu) {
+    if (c.K > 3) throw Error{N4J_ERR_UNSUPPORTED, "outer convolutions: kernel size up to 3"};
     const int nout = c.Ci * c.K * c.K;
-    const int threads = std::min(640, ((nout + 1 + 31) / 32) * 32);
-    k_outer_conv_wgrad<<<dim3(c.Co, OUTER_WSPLIT), threads, 0, s_>>>(x, dy, y, wpart_, db ? wpart_b_ : nullptr, c, relu);
+    k_outer_conv_wgrad<<<dim3(c.Co, (c.Ci + 15) / 16, OUTER_WSPLIT), 512, 0, s_>>>(x, dy, y, wpart_, db ? wpart_b_ : nullptr, c, relu);
     const long long n = (long long)c.Co * nout;
     k_outer_wgrad_finish<<<grid(n + c.Co), 256, 0, s_>>>(wpart_, wpart_b_, dw, db, n, c.Co);
 }
