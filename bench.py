@@ -53,7 +53,7 @@ def _peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
-def _conv_traffic_bytes(variant="<3, 1, 1>"):
+def _conv_traffic_bytes(variant="<3, 1, 1"):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the forward conv launch (template variant <3,1,1>), from the
     committed `ncu --set full` summary (default cache control: caches flushed before each replay, so this is the cold figure)."""
     for name in ("r02_conv3x3_tc_full.txt", "r01_conv3x3_tc_full.txt"):

@@ -15,6 +15,9 @@
 #pragma once
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <vector>
 
@@ -97,9 +100,15 @@ __global__ void __launch_bounds__(256) k_outer_conv_dgrad(const float* __restric
         s_w[i] = ci0 + t < c.Ci ? w[((long long)co * c.Ci + ci0 + t) * kk + k] : 0.f;
     }
     __syncthreads();
-    const long long n = (long long)c.B * c.H * c.W;
+    // pixels are enumerated parity class by parity class ((ih % S, iw % S) outermost): the lanes of a warp then share the set of taps that
+    // reach them, so a strided convolution's tap tests do not diverge
+    const int Hc = (c.H + c.S - 1) / c.S, Wc = (c.W + c.S - 1) / c.S;
+    const long long cls = (long long)c.B * Hc * Wc, n = cls * c.S * c.S;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int iw = (int)(i % c.W), ih = (int)((i / c.W) % c.H), b = (int)(i / ((long long)c.W * c.H));
+        const int pc = (int)(i / cls);
+        const long long j = i - (long long)pc * cls;
+        const int iw = (int)(j % Wc) * c.S + pc % c.S, ih = (int)((j / Wc) % Hc) * c.S + pc / c.S, b = (int)(j / ((long long)Wc * Hc));
+        if (ih >= c.H || iw >= c.W) continue;
         double acc[OUTER_CT];
 #pragma unroll
         for (int t = 0; t < OUTER_CT; ++t) acc[t] = 0.0;
@@ -138,37 +147,43 @@ __global__ void __launch_bounds__(256) k_outer_conv_dgrad(const float* __restric
 constexpr int OUTER_WSPLIT = 8;
 __global__ void __launch_bounds__(512) k_outer_conv_wgrad(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
                                                            double* __restrict__ part, double* __restrict__ part_b, ConvShape c, int relu) {
+    extern __shared__ int s_tab[];                       // per output pixel of one image: [0] offset of its top-left input pixel, [1] tap validity mask
     const int co = blockIdx.x, slice = blockIdx.z, kk = c.K * c.K, nout = c.Ci * kk;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = c.Ho * c.Wo;
+    for (int r = threadIdx.x; r < per; r += blockDim.x) {
+        const int oh = r / c.Wo, ow = r - oh * c.Wo;
+        const int ih0 = oh * c.S - c.pt, iw0 = ow * c.S - c.pl;
+        int mask = 0;
+        for (int kh = 0; kh < c.K; ++kh)
+            for (int kw = 0; kw < c.K; ++kw)
+                if (ih0 + kh >= 0 && ih0 + kh < c.H && iw0 + kw >= 0 && iw0 + kw < c.W) mask |= 1 << (kh * 3 + kw);
+        s_tab[2 * r] = ih0 * c.W + iw0;
+        s_tab[2 * r + 1] = mask;
+    }
+    __syncthreads();
     const int ci = blockIdx.y * 16 + warp;
     if (ci >= c.Ci) return;
-    const int per = c.Ho * c.Wo;
     const int b0 = (int)((long long)c.B * slice / OUTER_WSPLIT), b1 = (int)((long long)c.B * (slice + 1) / OUTER_WSPLIT);
     double acc[9], accb = 0.0;
 #pragma unroll
     for (int k = 0; k < 9; ++k) acc[k] = 0.0;
-    const int n = (b1 - b0) * per;
-    for (int i = lane; i < n; i += 32) {
-        const int b = b0 + i / per, r = i % per, oh = r / c.Wo, ow = r - oh * c.Wo;
-        const long long o = ((long long)b * c.Co + co) * per + r;
-        float g = dy[o];
-        if (relu && !(y[o] > 0.f)) g = 0.f;
-        if (g == 0.f) continue;
-        const double gd = (double)g;
-        accb += gd;
+    for (int b = b0; b < b1; ++b) {
+        const float* dyb = dy + ((long long)b * c.Co + co) * per;
+        const float* yb = y + ((long long)b * c.Co + co) * per;
         const float* xb = x + ((long long)b * c.Ci + ci) * c.H * c.W;
+        for (int r = lane; r < per; r += 32) {
+            float g = dyb[r];
+            if (relu && !(yb[r] > 0.f)) g = 0.f;
+            if (g == 0.f) continue;
+            const double gd = (double)g;
+            accb += gd;
+            const int off = s_tab[2 * r], mask = s_tab[2 * r + 1];
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            if (kh >= c.K) break;
-            const int ih = oh * c.S + kh - c.pt;
-            if (ih < 0 || ih >= c.H) continue;
+            for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                if (kw >= c.K) break;
-                const int iw = ow * c.S + kw - c.pl;
-                if (iw < 0 || iw >= c.W) continue;
-                acc[kh * 3 + kw] += gd * (double)xb[ih * c.W + iw];
-            }
+                for (int kw = 0; kw < 3; ++kw)
+                    if (mask & (1 << (kh * 3 + kw))) acc[kh * 3 + kw] += gd * (double)xb[off + kh * c.W + kw];
         }
     }
 #pragma unroll
@@ -423,7 +438,7 @@ inline void OuterNet::conv_dgrad(const float* dy, const float* y, const float* w
 inline void OuterNet::conv_wgrad(const float* x, const float* dy, const float* y, float* dw, float* db, const ConvShape& c, int relu) {
     if (c.K > 3) throw Error{N4J_ERR_UNSUPPORTED, "outer convolutions: kernel size up to 3"};
     const int nout = c.Ci * c.K * c.K;
-    k_outer_conv_wgrad<<<dim3(c.Co, (c.Ci + 15) / 16, OUTER_WSPLIT), 512, 0, s_>>>(x, dy, y, wpart_, db ? wpart_b_ : nullptr, c, relu);
+    k_outer_conv_wgrad<<<dim3(c.Co, (c.Ci + 15) / 16, OUTER_WSPLIT), 512, sizeof(int) * 2 * c.Ho * c.Wo, s_>>>(x, dy, y, wpart_, db ? wpart_b_ : nullptr, c, relu);
     const long long n = (long long)c.Co * nout;
     k_outer_wgrad_finish<<<grid(n + c.Co), 256, 0, s_>>>(wpart_, wpart_b_, dw, db, n, c.Co);
 }
@@ -546,12 +561,24 @@ inline void OuterNet::train_step(float* params, float* updater_state, const floa
                                  float* grad_out, n4j_stats* ode_fwd, n4j_stats* ode_bwd) {
     N4J_CUDA(cudaSetDevice(device_));
     const int C = C_, B = B_;
+    // N4J_NET_DBG=1: wall-clock phase times of one step on stderr (each phase ends with a stream synchronisation: debugging aid only)
+    const bool dbg = getenv("N4J_NET_DBG") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto phase = [&](const char* name) {
+        if (!dbg) return;
+        cudaStreamSynchronize(s_);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[node4j_net] %-28s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     N4J_CUDA(cudaMemcpyAsync(p_, params, sizeof(float) * n_, cudaMemcpyDefault, s_));
     N4J_CUDA(cudaMemcpyAsync(v_, updater_state, sizeof(float) * n_, cudaMemcpyDefault, s_));
     N4J_CUDA(cudaMemcpyAsync(img_, images, sizeof(float) * B * 28 * 28, cudaMemcpyDefault, s_));
     N4J_CUDA(cudaMemcpyAsync(lab_, labels, sizeof(float) * B * 10, cudaMemcpyDefault, s_));
     N4J_CUDA(cudaMemsetAsync(g_, 0, sizeof(float) * n_, s_));          // ZeroGrad (util/listen/training/ZeroGrad.java:14-16): the theta-adjoint is seeded from the view
+    phase("copies in");
     forward(p_, img_, lab_, true, ode_fwd);
+    phase("forward (stem, block, output)");
     // ---- backward --------------------------------------------------------------------------------------------------------------
     const long long nz = (long long)B * C * 49;
     k_outer_output_bwd<<<1, 256, 0, s_>>>(pool_, p_ + off_ow_, probs_, lab_, score_parts_, g_ + off_ow_, g_ + off_ob_, dpool_, score_, B, C);
@@ -559,7 +586,9 @@ inline void OuterNet::train_step(float* params, float* updater_state, const floa
     k_outer_bn_bwd<<<C, 256, 0, s_>>>(z1_, no_, d1_, p_ + off_bno_, sto_, d2_, g_ + off_bno_, B, C, 49, 1, 0.1f);
     N4J_CUDA(cudaGetLastError());
     // the adjoint solve: continues the forward of this handle (lastOutput stays on the device), gradient view slice seeded (zero) and written in place
+    phase("output block backward");
     ode_->backward(nullptr, d2_, time_, 2, N4J_TIMEGRAD_NONE, g_ + off_ode_, d1_, nullptr, ode_bwd);
+    phase("ODE block adjoint");
     float* da = d1_;              // dL/d(stem output)
     float* t1 = d2_;
     float* t2 = d3_;
@@ -585,6 +614,7 @@ inline void OuterNet::train_step(float* params, float* updater_state, const floa
         // keep three distinct buffers: da (new epsilon), t1, t2 (scratch)
     }
     conv_wgrad(img_, da, a0_, g_ + off_in_w_, g_ + off_in_b_, cin_, 0);
+    phase("stem backward");
     // ---- update ----------------------------------------------------------------------------------------------------------------
     if (grad_out) N4J_CUDA(cudaMemcpyAsync(grad_out, g_, sizeof(float) * n_, cudaMemcpyDefault, s_));
     k_outer_update<<<grid(n_), 256, 0, s_>>>(p_, v_, g_, kind_, n_, (float)B, lr, mu, (float)(1.0 + (double)mu));
@@ -593,6 +623,7 @@ inline void OuterNet::train_step(float* params, float* updater_state, const floa
     N4J_CUDA(cudaMemcpyAsync(updater_state, v_, sizeof(float) * n_, cudaMemcpyDefault, s_));
     if (score) N4J_CUDA(cudaMemcpyAsync(score, score_, sizeof(float), cudaMemcpyDefault, s_));
     N4J_CUDA(cudaStreamSynchronize(s_));
+    phase("update + copies out");
 }
 
 }  // namespace n4j
