@@ -115,6 +115,7 @@ struct ConvTcArgs {
     int eact;             // its activation (ReLU or identity)
     Ref edgamma, edbeta;
     long long* dbg;       // optional (N4J_CONV_DBG): SM-clock timestamps of CTA 0's phases, see engine.cu: bench_piece
+    int dbg_nowstream;    // timing experiment only (N4J_DBG_CONV_NOWSTREAM, wrong results): taps 4-8 reuse the first four weight stages, nothing streams during the MMA phase
 };
 
 // Finalisation of the deferred BatchNorm statistics for the operand prologue: one channel per thread of warps 0-1.  Deliberately
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                         tc::bulk_g2s(sA + hl * a_img_bytes + c * a_chunk_bytes, a.img + (((long long)hl * 16 + c) * g.rows + row0) * 4,
                                      a_chunk_bytes, a_full);
             }
-            for (int tap = PRO == 0 ? 0 : CONV_TC_STAGES; tap < 9; ++tap) {   // with a prologue the first STAGES taps are already in flight
+            for (int tap = PRO == 0 ? 0 : CONV_TC_STAGES; tap < (a.dbg_nowstream ? CONV_TC_STAGES : 9); ++tap) {   // with a prologue the first STAGES taps are already in flight
                 const int s = tap % CONV_TC_STAGES;
                 if (tap >= CONV_TC_STAGES) tc::mbar_wait(&w_empty[s], ((tap / CONV_TC_STAGES) - 1) & 1);
                 tc::mbar_arrive_expect_tx(&w_full[s], CONV_TC_WSTAGE_BYTES);
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             uint32_t acc = 0;
             for (int tap = 0; tap < 9; ++tap) {
                 const int s = tap % CONV_TC_STAGES;
-                tc::mbar_wait(&w_full[s], (tap / CONV_TC_STAGES) & 1);
+                if (!a.dbg_nowstream || tap < CONV_TC_STAGES) tc::mbar_wait(&w_full[s], (tap / CONV_TC_STAGES) & 1);
                 tc::tc_fence_after();
                 const int shift = (tap / 3 - 1) * g.PW + (tap % 3 - 1);
                 const uint32_t a_row = (uint32_t)(g.halo + shift) * 16;

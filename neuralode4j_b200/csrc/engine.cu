@@ -590,6 +590,7 @@ void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg,
     ConvTcArgs a{};
     if (extra) a = *extra;
     a.img = img; a.wimg = wimg; a.out = out; a.g = geom_; a.act = act;
+    a.dbg_nowstream = getenv("N4J_DBG_CONV_NOWSTREAM") ? 1 : 0;
     if (next_bn) { epi_kind = 1; a.bn = next_bn->bn; a.bn_eps = next_bn->d.eps; a.bn_rows = next_bn->rows; }
     a.fuse_stats = epi_kind;
     if (conv_rec_) conv_rec_->push_back(ConvRec{a, pro_kind, epi_kind});
