@@ -14,7 +14,7 @@ using namespace n4j;
 constexpr int K = 32;        // one 128-byte swizzle atom of tf32 = 4 K steps
 constexpr int ROWS = 128 + 16;
 
-__global__ void k_probe(const float* A /*[ROWS][K] row-major, logical rows*/, const float* B_km, float* D, long long* cycles, int swz, int shift, int reps) {
+__global__ void k_probe(const float* A /*[ROWS][K] row-major, logical rows*/, const float* B_km, float* D, long long* cycles, int swz, int shift, int reps, int nmode) {
     extern __shared__ __align__(1024) uint8_t sm[];
     float* sA = reinterpret_cast<float*>(sm);                       // none: [K/4][ROWS][4]; swizzled: [ROWS][32 floats]
     float* sB = sA + ROWS * K;                                      // [K/4][128][4]
@@ -43,7 +43,9 @@ __global__ void k_probe(const float* A /*[ROWS][K] row-major, logical rows*/, co
                 if (swz) da = tc::smem_desc(tc::smem_u32(sA) + shift * 128 + ks * 32, 16, 1024) | (2ull << 61);      // SWIZZLE_128B, SBO = 8 rows
                 else da = tc::smem_desc(tc::smem_u32(sA) + (ks * 2 * ROWS + shift) * 16, ROWS * 16, 128);
                 const uint64_t db = tc::smem_desc(tc::smem_u32(sB) + ks * 2 * 128 * 16, 128 * 16, 128);
-                tc::mma_tf32(tmem, da, db, idesc, (r | ks) ? 1u : 0u);
+                // nmode 0: N128 only; 1: N64 only; 2: the conv kernels' pair per K step (N128 then N64 into the first 64 columns)
+                if (nmode != 1) tc::mma_tf32(tmem, da, db, idesc, (r | ks) ? 1u : 0u);
+                if (nmode != 0) tc::mma_tf32(tmem, da, db, tc::idesc_tf32(128, 64, 0, 0), (nmode == 2 || (r | ks)) ? 1u : 0u);
             }
         tc::mma_commit(&bar);
     }
@@ -80,7 +82,7 @@ int main() {
             for (int reps : {1, 128}) {
                 for (int m = 0; m < 128; ++m) for (int n = 0; n < 128; ++n) { double s = 0; for (int k = 0; k < K; ++k) s += (double)a[(m + shift) * K + k] * b[n * K + k]; ref[m * 128 + n] = (float)s; }
                 cudaMemset(dD, 0xFF, sizeof(float) * 128 * 128);
-                k_probe<<<1, 128, smem>>>(dA, dB, dD, dC, swz, shift, reps);
+                k_probe<<<1, 128, smem>>>(dA, dB, dD, dC, swz, shift, reps, 0);
                 cudaError_t e = cudaDeviceSynchronize();
                 long long cyc = 0;
                 cudaMemcpy(&cyc, dC, sizeof(cyc), cudaMemcpyDeviceToHost);
@@ -91,5 +93,12 @@ int main() {
                 else printf("   %.1f cycles per M128 N128 K8 instruction (err %.2e of %.0f)\n", (double)cyc / (reps * (K / 8)), err, mx);
                 if (e != cudaSuccess) return 1;
             }
+    for (int nmode = 0; nmode < 3; ++nmode) {
+        k_probe<<<1, 128, smem>>>(dA, dB, dD, dC, 0, 9, 128, nmode);
+        cudaDeviceSynchronize();
+        long long cyc = 0;
+        cudaMemcpy(&cyc, dC, sizeof(cyc), cudaMemcpyDeviceToHost);
+        printf("per K step, shift 9, no swizzle: %-34s %.1f cycles\n", nmode == 0 ? "M128 N128" : nmode == 1 ? "M128 N64" : "M128 N128 + M128 N64 (conv kernels)", (double)cyc / (128 * (K / 8)));
+    }
     return 0;
 }
