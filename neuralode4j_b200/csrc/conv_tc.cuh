@@ -115,14 +115,6 @@ struct ConvTcArgs {
     int eact;             // its activation (ReLU or identity)
     Ref edgamma, edbeta;
     long long* dbg;       // optional (N4J_CONV_DBG): SM-clock timestamps of CTA 0's phases, see engine.cu: bench_piece
-    // EPI == 3 (last conv of an augmented evaluation, one GPU): everything EPI 1 does for the BatchNorm behind the conv (`bn`), then —
-    // behind a grid barrier, all CTAs being co-resident — that BatchNorm is APPLIED to the tile still sitting in shared memory
-    // (y = act(gamma * xhat + beta) -> eout2, the K row of f(z)) and its BACKWARD statistics (sums of dy and dy*xhat with
-    // dy = act'(y) * egscale * eg) are reduced: the work of k_bn_bwd_stats64 without its launch, its loads of x and its start-up latency.
-    // egamma / ebeta / eact describe that BatchNorm, gb = {arrival counter, release generation}.
-    Ref eg, eout2;
-    float egscale;
-    unsigned int* gb;
     int dbg_nowstream;    // timing experiment only (N4J_DBG_CONV_NOWSTREAM, wrong results): taps 4-8 reuse the first four weight stages, nothing streams during the MMA phase
 };
 
@@ -464,20 +456,6 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 mask = 0u;
             }
         }
-        // EPI 3: the gradient rows this thread needs after the grid barrier are requested now (they arrive while the tensor core works),
-        // and the barrier's release generation is read before any CTA of this launch can have passed it
-        float gq[EPI == 3 ? 32 : 1];
-        unsigned int gb_gen = 0u;
-        if constexpr (EPI == 3) {
-            if (et == 0) gb_gen = *((volatile unsigned int*)(a.gb + 1));
-#pragma unroll
-            for (int j = 0; j < 32; ++j) gq[j] = 0.f;
-            if (valid) {
-                const float4* __restrict__ gp = reinterpret_cast<const float4*>(resolve(a.eg) + crow * 64 + half * 32);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { const float4 t = gp[j]; gq[4 * j] = t.x; gq[4 * j + 1] = t.y; gq[4 * j + 2] = t.z; gq[4 * j + 3] = t.w; }
-            }
-        }
         tc::mbar_wait(d_full, 0);
         if (threadIdx.x == 64) conv_stamp(a, 8);
         tc::tc_fence_after();
@@ -495,7 +473,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
-            if constexpr (EPI == 1 || EPI == 3) {
+            if constexpr (EPI == 1) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) sT[row * 65 + half * 32 + j] = valid ? v[j] : 0.f;
             }
@@ -513,7 +491,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             {   // column sums: 256 threads = 64 columns x 4 row quarters, combined through shared memory (one atomic per address and CTA)
                 const int c = et & 63, r0 = (et >> 6) * 32;
                 double p1 = 0.0, p2 = 0.0;
-                if constexpr (EPI == 1 || EPI == 3) {
+                if constexpr (EPI == 1) {
                     for (int r = r0; r < r0 + 32; ++r) { const double x = (double)sT[r * 65 + c]; p1 += x; p2 += x * x; }
                 } else {
                     for (int r = r0; r < r0 + 32; ++r) { const double dy = (double)sT[r * 65 + c]; p1 += dy; p2 += dy * (double)sT2[r * 65 + c]; }
@@ -525,9 +503,9 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             if (et < 128) {
                 const double tsum = (sP[et] + sP[128 + et]) + (sP[256 + et] + sP[384 + et]);     // et < 64: first sums, else second sums
                 if (a.bn.deferred) {      // accumulate only; the consumers finalise, CTA 0 re-arms the next evaluation's set
-                    atomicAdd((EPI != 2 ? a.bn.accf : a.bn.accb) + et * ACC_STRIDE, tsum);
-                    bn_rearm(EPI != 2 ? a.bn.accf_other : a.bn.accb_other, et);
-                    if (SH) bn_bump(a.bn.cm ? (EPI != 2 ? a.bn.seqf : a.bn.seqb) : nullptr, et);
+                    atomicAdd((EPI == 1 ? a.bn.accf : a.bn.accb) + et * ACC_STRIDE, tsum);
+                    bn_rearm(EPI == 1 ? a.bn.accf_other : a.bn.accb_other, et);
+                    if (SH) bn_bump(a.bn.cm ? (EPI == 1 ? a.bn.seqf : a.bn.seqb) : nullptr, et);
                 } else {                  // legacy / multi-GPU: the last CTA finalises (and exchanges the sums between the ranks)
                     atomicAdd(a.bn.acc + et * ACC_STRIDE, tsum);
                     __threadfence();
@@ -547,7 +525,7 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                         if (a.bn.cm) comm_allreduce_epilogue(a.bn.cm, tot, 128, et);
                         const double Mt = a.bn.cm ? (double)a.bn.rows_total : (double)a.bn_rows;
                         if (et < 64) {
-                            if constexpr (EPI != 2) {
+                            if constexpr (EPI == 1) {
                                 const double mean = tot[et] / Mt;
                                 double var = tot[64 + et] / Mt - mean * mean;
                                 if (var < 0) var = 0;
@@ -564,77 +542,6 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                         if (et == 0) *a.bn.ticket = 0u;
                     }
                 }
-            }
-        }
-        if constexpr (EPI == 3) {
-            // ---- grid barrier: every CTA's column sums are in the accumulators (all CTAs of the launch are co-resident: the engine only
-            // selects this variant for grids that fit beside the side branch's weight-gradient CTAs; the wait is bounded) ----
-            __threadfence();
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (et == 0) {
-                const unsigned int tk = atomicAdd(a.gb, 1u);
-                if (tk == gridDim.x - 1) {
-                    *((volatile unsigned int*)a.gb) = 0u;
-                    __threadfence();
-                    atomicAdd(a.gb + 1, 1u);
-                } else {
-                    bool ok = false;
-                    for (unsigned int spin = 0; spin < (1u << 26); ++spin) {
-                        if (*((volatile unsigned int*)(a.gb + 1)) != gb_gen) { ok = true; break; }
-                        if ((spin & 63) == 63) __nanosleep(20);
-                    }
-                    if (!ok) __trap();
-                }
-                __threadfence();
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            // ---- statistics of the BatchNorm behind the conv, finalised from the now complete sums (one channel per thread) ----
-            __shared__ float s_b3[4][64];      // mean, invstd, gamma, beta
-            if (et < 64) {
-                const double M = (double)a.bn.rows;
-                const double m = *((volatile double*)(a.bn.accf + et * ACC_STRIDE)) / M;
-                double var = *((volatile double*)(a.bn.accf + (64 + et) * ACC_STRIDE)) / M - m * m;
-                if (var < 0) var = 0;
-                s_b3[0][et] = (float)m;
-                s_b3[1][et] = (float)(1.0 / sqrt(var + (double)a.bn.eps));
-            } else if (et < 128) {
-                s_b3[2][et - 64] = a.egamma[et - 64];
-            } else if (et < 192) {
-                s_b3[3][et - 128] = a.ebeta[et - 128];
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            {   // ---- apply (the K row of f(z)) and dy / xhat of this thread's half row ----
-                const bool relu = a.eact == N4J_ACT_RELU;
-                float* __restrict__ yout = resolve(a.eout2);
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    float yy[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int j = 4 * j4 + k, c = half * 32 + j;
-                        const float xh = __fmul_rn(__fsub_rn(sT[row * 65 + c], s_b3[0][c]), s_b3[1][c]);
-                        float y = __fadd_rn(__fmul_rn(s_b3[2][c], xh), s_b3[3][c]);
-                        const bool off = relu && !(y > 0.f);
-                        if (off) y = 0.f;
-                        yy[k] = y;
-                        sT[row * 65 + c] = (valid && !off) ? __fmul_rn(a.egscale, gq[j]) : 0.f;      // dy = act'(y) * gscale * g
-                        sT2[row * 65 + c] = valid ? xh : 0.f;
-                    }
-                    if (valid) reinterpret_cast<float4*>(yout + crow * 64 + half * 32)[j4] = make_float4(yy[0], yy[1], yy[2], yy[3]);
-                }
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            {   // ---- backward sums of that BatchNorm: same column-sum scheme as EPI 2 ----
-                const int c = et & 63, r0 = (et >> 6) * 32;
-                double p1 = 0.0, p2 = 0.0;
-                for (int r = r0; r < r0 + 32; ++r) { const double dy = (double)sT[r * 65 + c]; p1 += dy; p2 += dy * (double)sT2[r * 65 + c]; }
-                sP[(et >> 6) * 128 + c] = p1;
-                sP[(et >> 6) * 128 + 64 + c] = p2;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (et < 128) {
-                atomicAdd(a.bn.accb + et * ACC_STRIDE, (sP[et] + sP[128 + et]) + (sP[256 + et] + sP[384 + et]));
-                bn_rearm(a.bn.accb_other, et);
             }
         }
     }

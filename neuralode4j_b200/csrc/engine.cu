@@ -210,14 +210,6 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
     N4J_CUDA(cudaMalloc(&tg_, sizeof(float) * 4));
     N4J_CUDA(cudaMalloc(&tcat_acc_, sizeof(double) * ACC_SLOTS * ACC_STRIDE));
     N4J_CUDA(cudaMemsetAsync(tcat_acc_, 0, sizeof(double) * ACC_SLOTS * ACC_STRIDE, stream_));
-    N4J_CUDA(cudaMalloc(&grid_barrier_, 2 * sizeof(unsigned int)));      // {arrival counter, release generation} of the conv kernels' EPI 3 barrier
-    N4J_CUDA(cudaMemsetAsync(grid_barrier_, 0, 2 * sizeof(unsigned int), stream_));
-    {
-        cudaDeviceProp prop{};
-        N4J_CUDA(cudaGetDeviceProperties(&prop, device_));
-        sm_count_ = prop.multiProcessorCount;
-        bn3_fusion_ = getenv("N4J_NO_BN3_FUSION") == nullptr && !(cfg_.flags & N4J_FLAG_NO_BWD_STATS_FUSION);
-    }
     N4J_CUDA(cudaMalloc(&tcat_misc_, 16));      // [0]: ticket, [1]: last g^T df/dt
     N4J_CUDA(cudaMemsetAsync(tcat_misc_, 0, 16, stream_));
     ensure(params_, std::max<long long>(n_params_, 1));
@@ -375,7 +367,7 @@ Engine::~Engine() {
     for (DevBuf* b : {&params_, &gradflat_, &zt_, &gt_, &io_, &io2_, &gb_[0], &gb_[1], &gb_[2], &theta_tmp_, &wpart_, &dldt_}) cudaFree(b->p);
     for (void* pp : peer_ptrs_) cudaIpcCloseMemHandle(pp);
     cudaFree(comm_region_); cudaFree(comm_dev_);
-    cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(red_acc_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_); cudaFree(tcat_acc_); cudaFree(tcat_misc_); cudaFree(grid_barrier_); cudaFree(bn_pool_); cudaFree(mlp_part_); cudaFree(mlp_ticket_);
+    cudaFree(Y_); cudaFree(K_); cudaFree(ctrl_); cudaFree(red_acc_); cudaFree(log_); cudaFree(tpair_); cudaFree(wanted_); cudaFree(dot_acc_); cudaFree(tg_); cudaFree(tcat_acc_); cudaFree(tcat_misc_); cudaFree(bn_pool_); cudaFree(mlp_part_); cudaFree(mlp_ticket_);
     cudaFreeHost(ctrl_host_); cudaFreeHost(tpair_host_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -588,7 +580,7 @@ static void set_conv_smem(size_t smem) {
 // the (prologue, epilogue) combinations the engine launches: forward convs take PRO 0/1 with EPI 0/1, dgrad convs PRO 0/2 with EPI 0/2
 static void set_conv_smem_all(size_t smem) {
     set_conv_smem<0, 0>(smem); set_conv_smem<0, 1>(smem); set_conv_smem<1, 0>(smem); set_conv_smem<1, 1>(smem);
-    set_conv_smem<0, 2>(smem); set_conv_smem<2, 0>(smem); set_conv_smem<2, 2>(smem); set_conv_smem<1, 3>(smem);
+    set_conv_smem<0, 2>(smem); set_conv_smem<2, 0>(smem); set_conv_smem<2, 2>(smem);
 }
 
 // pro_kind: fused operand prologue (1 = BatchNorm apply in front of a forward conv, 2 = BatchNorm backward in front of a dgrad)
@@ -599,7 +591,7 @@ void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg,
     if (extra) a = *extra;
     a.img = img; a.wimg = wimg; a.out = out; a.g = geom_; a.act = act;
     a.dbg_nowstream = getenv("N4J_DBG_CONV_NOWSTREAM") ? 1 : 0;
-    if (next_bn) { if (epi_kind != 3) epi_kind = 1; a.bn = next_bn->bn; a.bn_eps = next_bn->d.eps; a.bn_rows = next_bn->rows; }
+    if (next_bn) { epi_kind = 1; a.bn = next_bn->bn; a.bn_eps = next_bn->d.eps; a.bn_rows = next_bn->rows; }
     a.fuse_stats = epi_kind;
     if (conv_rec_) conv_rec_->push_back(ConvRec{a, pro_kind, epi_kind});
     launch_conv_args(s, a, pro_kind, epi_kind);
@@ -607,16 +599,15 @@ void Engine::launch_conv_tc(cudaStream_t s, const float* img, const float* wimg,
 void Engine::launch_conv_args(cudaStream_t s, const ConvTcArgs& a, int pro_kind, int epi_kind) {
     const bool fast = (cfg_.flags & N4J_FLAG_FAST_TF32) != 0;
     const dim3 grid(geom_.tiles), block(conv_tc_threads(pro_kind));
-    const int combo = pro_kind * 4 + epi_kind;
+    const int combo = pro_kind * 3 + epi_kind;
     switch (combo) {
         case 0: launch_conv_variant<0, 0>(a, grid, block, conv_smem_, s, pdl_, fast); break;
         case 1: launch_conv_variant<0, 1>(a, grid, block, conv_smem_, s, pdl_, fast); break;
         case 2: launch_conv_variant<0, 2>(a, grid, block, conv_smem_, s, pdl_, fast); break;
-        case 4: launch_conv_variant<1, 0>(a, grid, block, conv_smem_, s, pdl_, fast); break;
-        case 5: launch_conv_variant<1, 1>(a, grid, block, conv_smem_, s, pdl_, fast); break;
-        case 7: launch_conv_variant<1, 3>(a, grid, block, conv_smem_, s, pdl_, fast); break;
-        case 8: launch_conv_variant<2, 0>(a, grid, block, conv_smem_, s, pdl_, fast); break;
-        case 10: launch_conv_variant<2, 2>(a, grid, block, conv_smem_, s, pdl_, fast); break;
+        case 3: launch_conv_variant<1, 0>(a, grid, block, conv_smem_, s, pdl_, fast); break;
+        case 4: launch_conv_variant<1, 1>(a, grid, block, conv_smem_, s, pdl_, fast); break;
+        case 6: launch_conv_variant<2, 0>(a, grid, block, conv_smem_, s, pdl_, fast); break;
+        case 8: launch_conv_variant<2, 2>(a, grid, block, conv_smem_, s, pdl_, fast); break;
         default: throw Error{N4J_ERR_ILLEGAL_STATE, "conv kernel variant not instantiated"};
     }
     ++launches_;
@@ -660,22 +651,8 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                     if (!image_ready) LAUNCH(k_compact_to_image, grid_for(l.in_len / 4), 256, s, cur, geom_, l.img);
                     // a BatchNorm right after the conv gets its batch statistics from the conv epilogue
                     const bool bn_next = i + 1 < L_.size() && L_[i + 1].d.kind == N4J_LAYER_BATCHNORM && L_[i + 1].c_out == 64;
-                    // Augmented evaluation on one GPU: the conv in front of the LAST BatchNorm also applies that BatchNorm (the K row of f(z))
-                    // and reduces its backward statistics behind a grid barrier (EPI 3) — k_bn_bwd_stats64 disappears from the chain.
-                    // Needs every CTA of the launch co-resident next to the side branch's 64 weight-gradient CTAs.
-                    int epi = 0;
-                    if (bn3_fusion_ && in_aug_ && need_compact && fuse_last_bn_ok_ && bn_next && i + 2 == L_.size() && pro_pending && !comm_dev_ &&
-                        L_[i + 1].bn.deferred == 1 && geom_.tiles + 64 <= sm_count_ &&
-                        (L_[i + 1].d.activation == N4J_ACT_RELU || L_[i + 1].d.activation == N4J_ACT_IDENTITY)) {
-                        const LayerPlan& b3 = L_[i + 1];
-                        pro_args.eg = aug_g_; pro_args.egscale = -1.f; pro_args.eout2 = out;
-                        pro_args.egamma = params_.p + b3.p_off; pro_args.ebeta = params_.p + b3.p_off + 64; pro_args.eact = b3.d.activation;
-                        pro_args.gb = grid_barrier_;
-                        epi = 3;
-                        bn3_fused_ = true;
-                    }
                     launch_conv_tc(s, l.img, l.wimg_f, dst, l.d.activation, bn_next ? &L_[i + 1] : nullptr, pro_pending ? &pro_args : nullptr,
-                                   pro_pending ? 1 : 0, epi);
+                                   pro_pending ? 1 : 0);
                     pro_pending = false;
                     image_ready = false;
                     stats_ready = bn_next;
@@ -713,8 +690,6 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                     LAUNCH(k_bn_apply_to_image, grid_for(l.out_len / 4), 256, s, cur, params_.p + l.p_off, params_.p + l.p_off + cc, l.bn,
                            l.d.activation, geom_, L_[i + 1].img, need_compact ? l.act : (float*)nullptr);
                     image_ready = true;
-                } else if (bn3_fused_ && i + 1 == L_.size()) {
-                    // augmented evaluation: the conv in front already applied this BatchNorm and reduced its backward statistics (EPI 3)
                 } else if (need_compact && fuse_last_bn_ok_ && i + 1 == L_.size() && cc == 64) {
                     // augmented evaluation: the last BatchNorm's apply is done by the first backward kernel (k_bn_bwd_stats64)
                     fwd_left_last_bn_ = true;
@@ -769,8 +744,6 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
     }
     fwd_left_last_bn_ = false;
     fuse_last_bn_ok_ = true;
-    bn3_fused_ = false;
-    aug_g_ = with_off(in, off_a_);
     begin_eval();
     in_aug_ = true;
     enqueue_rhs_fwd(s, in, out, true, bn1_ready);
@@ -783,7 +756,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
     bool bpro_pending = false;   // ... or left its backward to the dgrad kernel's operand prologue
     ConvTcArgs bpro_args{};
     bool forked = false;
-    bool bstats_ready = bn3_fused_;   // the dgrad kernel behind this BatchNorm (EPI 2) — or, for the last one, the conv in front of it (EPI 3) — already reduced its backward statistics
+    bool bstats_ready = false;   // the dgrad kernel behind this BatchNorm already reduced its backward statistics (EPI 2)
     for (int i = last; i >= 0; --i) {
         LayerPlan& l = L_[i];
         Ref x = i == 0 ? in : fixed_ref(L_[i - 1].act);

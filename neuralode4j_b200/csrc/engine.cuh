@@ -122,10 +122,6 @@ private:
     WgradTcGeom wgeom_{};            // tensor-core weight gradient (conv_wgrad_tc.cuh)
     size_t wgrad_tc_smem_ = 0;
     bool wgrad_tc_ = false;
-    unsigned int* grid_barrier_ = nullptr;   // conv EPI 3 (conv + last BatchNorm apply + its backward statistics behind a grid barrier)
-    int sm_count_ = 0;
-    bool bn3_fusion_ = false, bn3_fused_ = false;
-    Ref aug_g_{};                    // gradient w.r.t. f(z) of the augmented evaluation being enqueued (the a block of the stage state)
     // k_stage_combine_last: the evaluation of stages 1-5 leaves its last elementwise kernel (forward: the last BatchNorm's apply,
     // adjoint: the first BatchNorm's backward dx) to the stage combination that follows
     bool leave_last_ = false;        // request to the evaluation being enqueued
