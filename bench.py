@@ -697,6 +697,7 @@ def run_ours(args):
             "traffic": _conv_traffic_bytes(),
             "peak_source": f"{peaks['src']} bf16 sustained (kernel runs inside a long step). The kernel issues 3 TF32 passes per product "
                            "(TF32 peak = bf16/2), so fp32-faithful algorithmic flops can reach at most peak/6; latency-bound at this size (see DESIGN.md section 4)",
+            "frac_of_3xtf32_ceiling": achieved_tf / (peaks["tf_sust"] / 6.0),
             "algorithmic_flops_per_launch": conv_flops, "us_per_launch": p["conv_fused_us"], "us_per_launch_dgrad_variant": p["dgrad_fused_us"],
             "us_bare_conv_kernel": p["conv_us"], "share_of_step": conv_share}
         line["roofline_wgrad"] = {
