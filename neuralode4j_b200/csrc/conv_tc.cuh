@@ -115,7 +115,6 @@ struct ConvTcArgs {
     int eact;             // its activation (ReLU or identity)
     Ref edgamma, edbeta;
     long long* dbg;       // optional (N4J_CONV_DBG): SM-clock timestamps of CTA 0's phases, see engine.cu: bench_piece
-    int push_at_end;      // sharded deferred statistics: the last CTA of this (producer) launch pushes the local sums to the peers (see the epilogue)
     int dbg_nowstream;    // timing experiment only (N4J_DBG_CONV_NOWSTREAM, wrong results): taps 4-8 reuse the first four weight stages, nothing streams during the MMA phase
 };
 
@@ -504,33 +503,9 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             if (et < 128) {
                 const double tsum = (sP[et] + sP[128 + et]) + (sP[256 + et] + sP[384 + et]);     // et < 64: first sums, else second sums
                 if (a.bn.deferred) {      // accumulate only; the consumers finalise, CTA 0 re-arms the next evaluation's set
-                    double* accp = EPI == 1 ? a.bn.accf : a.bn.accb;
-                    atomicAdd(accp + et * ACC_STRIDE, tsum);
+                    atomicAdd((EPI == 1 ? a.bn.accf : a.bn.accb) + et * ACC_STRIDE, tsum);
                     bn_rearm(EPI == 1 ? a.bn.accf_other : a.bn.accb_other, et);
-                    if constexpr (SH != 0) {
-                        if (a.bn.cm && a.push_at_end) {
-                            // Sharded, and the first consumer of this set is an ELEMENTWISE kernel (nothing to hide the exchange behind):
-                            // the last CTA of this launch sends the finished local sums to the peers itself — the NVLink flight then
-                            // overlaps the kernel boundary and the consumers find the cells waiting.  It also announces the set (tag).
-                            __threadfence();
-                            asm volatile("bar.sync 2, 128;" ::: "memory");
-                            __shared__ int s_last_push;
-                            if (et == 0) s_last_push = (atomicAdd(a.bn.ticket, 1u) == gridDim.x - 1);
-                            asm volatile("bar.sync 2, 128;" ::: "memory");
-                            if (s_last_push) {
-                                __threadfence();
-                                unsigned int* seqp = EPI == 1 ? a.bn.seqf : a.bn.seqb;
-                                const unsigned int tag = *((volatile unsigned int*)seqp) + 1u;
-                                if (et < 64)
-                                    bn_push2(a.bn.cm, EPI == 1 ? a.bn.mbf : a.bn.mbb, tag, et, *((volatile double*)(accp + et * ACC_STRIDE)),
-                                             *((volatile double*)(accp + (64 + et) * ACC_STRIDE)));
-                                asm volatile("bar.sync 2, 128;" ::: "memory");
-                                if (et == 0) { *seqp = tag; *a.bn.ticket = 0u; }
-                            }
-                        } else {
-                            bn_bump(a.bn.cm ? (EPI == 1 ? a.bn.seqf : a.bn.seqb) : nullptr, et);
-                        }
-                    }
+                    if (SH) bn_bump(a.bn.cm ? (EPI == 1 ? a.bn.seqf : a.bn.seqb) : nullptr, et);
                 } else {                  // legacy / multi-GPU: the last CTA finalises (and exchanges the sums between the ranks)
                     atomicAdd(a.bn.acc + et * ACC_STRIDE, tsum);
                     __threadfence();

@@ -651,8 +651,6 @@ void Engine::enqueue_rhs_fwd(cudaStream_t s, Ref in, Ref out, bool need_compact,
                     if (!image_ready) LAUNCH(k_compact_to_image, grid_for(l.in_len / 4), 256, s, cur, geom_, l.img);
                     // a BatchNorm right after the conv gets its batch statistics from the conv epilogue
                     const bool bn_next = i + 1 < L_.size() && L_[i + 1].d.kind == N4J_LAYER_BATCHNORM && L_[i + 1].c_out == 64;
-                    // sharded: the statistics this conv produces for the LAST BatchNorm are consumed by an elementwise kernel -> pushed by the producer
-                    if (pro_pending) pro_args.push_at_end = (comm_dev_ && mgpu_push_at_end_ && bn_next && i + 2 == L_.size()) ? 1 : 0;
                     launch_conv_tc(s, l.img, l.wimg_f, dst, l.d.activation, bn_next ? &L_[i + 1] : nullptr, pro_pending ? &pro_args : nullptr,
                                    pro_pending ? 1 : 0);
                     pro_pending = false;
@@ -879,8 +877,6 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                             bpro_args.bn = b.bn; bpro_args.bn_rows = b.rows;
                             epi = 2;
                             bstats_ready = true;
-                            // sharded: the first BatchNorm's backward sums are consumed by the next stage combination (elementwise) -> pushed by the producer
-                            bpro_args.push_at_end = (comm_dev_ && mgpu_push_at_end_ && i - 1 == 0) ? 1 : 0;
                         }
                     }
                     launch_conv_tc(s, l.gimg, l.wimg_b, dx, N4J_ACT_IDENTITY, nullptr, (bpro_pending || epi) ? &bpro_args : nullptr, bpro_pending ? 2 : 0, epi);
@@ -1270,8 +1266,6 @@ void Engine::comm_init(int rank, int world, const void* handles, long long globa
         N4J_CUDA(cudaMemcpy(&ctrl_->comm, &comm_dev_, sizeof(CommDev*), cudaMemcpyHostToDevice));
         const char* md = getenv("N4J_MGPU_DEFERRED");
         mgpu_deferred_ = !(md && atoi(md) == 0);
-        const char* mp = getenv("N4J_MGPU_PUSH_AT_END");
-        mgpu_push_at_end_ = mgpu_deferred_ && !(mp && atoi(mp) == 0);
         for (auto& l : L_) {
             if (l.d.kind != N4J_LAYER_BATCHNORM) continue;
             l.bn.cm = comm_dev_; l.bn.rows_total = l.rows * world;

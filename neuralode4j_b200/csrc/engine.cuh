@@ -141,7 +141,6 @@ private:
     size_t comm_bytes_ = 0;
     long long comm_xcap_ = 0, comm_xll_off_ = 0, comm_xll_cap_ = 0;
     long long comm_stat_off_ = 0;      // BatchNorm statistics mailboxes: [layer][forward|backward][set][source rank][128 cells of 16 bytes]
-    bool mgpu_push_at_end_ = false;    // ... and producers whose first consumer is an elementwise kernel push their sums themselves (N4J_MGPU_PUSH_AT_END=0: off)
     bool mgpu_deferred_ = false;       // sharded path keeps the deferred statistics (and the combine fusion) — N4J_MGPU_DEFERRED=0 switches back to the last-block exchange
     bool vec_allreduce_ll_ = getenv("N4J_NO_LL_VEC_ALLREDUCE") == nullptr;        // A/B switch: pull exchange through xbuf instead
     bool skip_vec_allreduce_ = getenv("N4J_DBG_SKIP_VEC_ALLREDUCE") != nullptr;   // timing experiments only
