@@ -114,6 +114,10 @@ struct ConvTcArgs {
     const float* ebeta;
     int eact;             // its activation (ReLU or identity)
     Ref edgamma, edbeta;
+    // SUB instantiation (the stem's stride-2 convolutions, outer_net_tc.cuh): the launch computes the stride-1 "same" convolution of the
+    // full-resolution image and stores only the pixels a stride-`sub_s` convolution samples, h = oh * sub_s + sub_off (same for w),
+    // as compact rows of a [B, sub_H, sub_W] tensor; `act` (ReLU) is applied there.
+    int sub_s, sub_off, sub_H, sub_W;
     long long* dbg;       // optional (N4J_CONV_DBG): SM-clock timestamps of CTA 0's phases, see engine.cu: bench_piece
     int dbg_nowstream;    // timing experiment only (N4J_DBG_CONV_NOWSTREAM, wrong results): taps 4-8 reuse the first four weight stages, nothing streams during the MMA phase
 };
@@ -147,7 +151,7 @@ __device__ __forceinline__ void conv_stamp_max(const ConvTcArgs& a, int slot) {
 
 // SH: sharded (multi-GPU) instantiation — the cross-rank statistics exchange of the deferred scheme is compiled in only there, so the
 // single-GPU kernels carry none of its code or registers (measured: +0.3 us per launch when it was a run-time branch).
-template <int PASSES, int EPI, int PRO, int SH = 0>
+template <int PASSES, int EPI, int PRO, int SH = 0, int SUB = 0>
 __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcArgs a) {
     if (threadIdx.x == 0) conv_stamp(a, 0);
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // dependents may be scheduled; they park in their own wait
@@ -411,6 +415,12 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
             const int ph = rem / g.PW, pw = rem - ph * g.PW;
             valid = ph >= 1 && ph <= g.H && pw >= 1 && pw <= g.W;
             crow = ((long long)b * g.H + (ph - 1)) * g.W + (pw - 1);
+            if constexpr (SUB != 0) {      // keep only the pixels the strided convolution samples
+                const int dh = ph - 1 - a.sub_off, dw = pw - 1 - a.sub_off;
+                const int oh = dh / a.sub_s, ow = dw / a.sub_s;
+                valid = valid && dh >= 0 && dw >= 0 && oh * a.sub_s == dh && ow * a.sub_s == dw && oh < a.sub_H && ow < a.sub_W;
+                crow = ((long long)b * a.sub_H + oh) * a.sub_W + ow;
+            }
         }
         float* __restrict__ out = resolve(a.out);
         float* sT = reinterpret_cast<float*>(sW);      // [128][65] transpose buffer(s); the weight ring is idle once d_full fires
@@ -468,7 +478,13 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] += u[j];
             }
-            if (valid) {   // the tensor path only takes identity-activation convolutions (the reference's blocks)
+            if constexpr (SUB != 0) {
+                if (a.act == N4J_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+                }
+            }
+            if (valid) {   // the ODE block's tensor path only takes identity-activation convolutions (the reference's blocks)
                 float4* dst = reinterpret_cast<float4*>(out + crow * 64 + half * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);

@@ -501,13 +501,13 @@ void Engine::upload_params() {
 }
 
 void Engine::state_in(const float* user, float* internal) {
-    if (rank_ == 2) { to_device(internal, user, nz_); return; }
+    if (rank_ == 2 || nhwc_io_) { to_device(internal, user, nz_); return; }
     ensure(io2_, nz_);
     to_device(io2_.p, user, nz_);
     LAUNCH(k_nchw_to_nhwc, grid_for(nz_), 256, stream_, io2_.p, internal, (int)B_, C_, H_ * W_);
 }
 void Engine::state_out(const float* internal, float* user_dev) {
-    if (rank_ == 2) { N4J_CUDA(cudaMemcpyAsync(user_dev, internal, sizeof(float) * nz_, cudaMemcpyDeviceToDevice, stream_)); return; }
+    if (rank_ == 2 || nhwc_io_) { N4J_CUDA(cudaMemcpyAsync(user_dev, internal, sizeof(float) * nz_, cudaMemcpyDeviceToDevice, stream_)); return; }
     LAUNCH(k_nhwc_to_nchw, grid_for(nz_), 256, stream_, internal, user_dev, (int)B_, C_, H_ * W_);
 }
 void Engine::theta_flat_to_internal(const float* flat, float* theta) {

@@ -88,10 +88,14 @@ public:
     void comm_export(void* handle64);
     void comm_init(int rank, int world, const void* handles, long long global_batch);
     cudaStream_t stream() const { return stream_; }
+    // rank-4 states cross forward / backward in the engine's internal NHWC layout instead of the reference's NCHW (callers inside
+    // the library whose own tensors are NHWC: outer_net.cuh's tensor-core path)
+    void set_nhwc_io(bool on) { nhwc_io_ = on; }
 
 private:
     // ---- plan ------------------------------------------------------------------------------------
     int device_;
+    bool nhwc_io_ = false;
     n4j_solver_cfg cfg_;
     bool exact_ = false;       // N4J_FLAG_EXACT_CONTRACTIONS
     bool pdl_ = true;          // programmatic dependent launch on every kernel (N4J_FLAG_NO_PDL turns it off)

@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "engine.cuh"
+#include "outer_net_tc.cuh"
 
 namespace n4j {
 
@@ -417,6 +418,33 @@ private:
     double* score_parts_ = nullptr;
     double *wpart_ = nullptr, *wpart_b_ = nullptr;      // weight-gradient partials of the outer convolutions [OUTER_WSPLIT][Co][Ci*K*K]
     std::vector<void*> allocs_;
+
+    // ---- fast path (outer_net_tc.cuh): 64 kernels, default mode — NHWC activations, the 64 -> 64 convolutions on the tcgen05 kernels ----
+    struct TcBlock {
+        ConvGeom gi, go;               // operand-image geometries at the block's input / output resolution
+        WgradTcGeom wi, wo;
+        int sub_off;                   // sampled pixel of the stride-2 firstConv: h = 2 * oh + sub_off
+        float *n1, *n1img, *dsy, *f1, *n2, *n2img, *f2, *a_out;
+        float *w1f, *w1b, *w2f, *w2b;  // per-tap hi/lo weight images, forward / dgrad
+        float *t1, *gup, *gupimg, *dn1, *daimg, *da_in;
+        double *acc1, *acc2;
+    };
+    bool tc_ = false;
+    int passes_ = 3;
+    TcBlock tb_[2];
+    float *a0n_ = nullptr, *z1n_ = nullptr, *non_ = nullptr, *dA_ = nullptr, *dB_ = nullptr, *dC_ = nullptr;
+    double *acc_pool_ = nullptr, *acco_ = nullptr, *dspart_ = nullptr, *inpart_ = nullptr;
+    size_t acc_pool_bytes_ = 0;
+    float *wpart_tc_ = nullptr, *wmid_ = nullptr;
+    size_t conv_smem_max_ = 0, wgrad_smem_max_ = 0;
+    static constexpr int WMID = 32;
+    void init_tc();
+    void set_tc_attributes();
+    void conv_tc(const float* img, const float* wimg, float* out, const ConvGeom& g, int act, bool sub, int sub_off, int Ho);
+    void wgrad_tc(const float* x, const float* g, const WgradTcGeom& wg, float* dw_flat);
+    void forward_tc(const float* p, const float* images, const float* labels, n4j_stats* ode_fwd);
+    void backward_tc(const float* images, n4j_stats* ode_bwd);
+    int grid_rows(long long rows) const { return (int)std::max<long long>(1, std::min<long long>((rows + 15) / 16, 148LL * 4)); }
 };
 
 inline float* OuterNet::dev_alloc(long long n) {
@@ -511,6 +539,13 @@ inline OuterNet::OuterNet(int batch, int channels, const n4j_solver_cfg& cfg, fl
     N4J_CUDA(cudaMalloc(&wpart_, sizeof(double) * OUTER_WSPLIT * (size_t)C * C * 9)); allocs_.push_back(wpart_);
     N4J_CUDA(cudaMalloc(&wpart_b_, sizeof(double) * OUTER_WSPLIT * (size_t)C)); allocs_.push_back(wpart_b_);
     N4J_CUDA(cudaMemcpy(tdev_, time_, sizeof(time_), cudaMemcpyHostToDevice));
+    // fast path: the reference's 64 kernels, tensor cores allowed, not the parity mode (which keeps the exact-accumulation kernels above)
+    // (N4J_NET_NO_TC=1 / N4J_NET_FORCE_TC=1: A/B switches — the second one keeps the fast stem next to an exact-mode ODE block, which
+    // isolates the stem's own deviation from the block's gradient sensitivity)
+    tc_ = channels == 64 && !(cfg.flags & (N4J_FLAG_EXACT_CONTRACTIONS | N4J_FLAG_NO_TENSOR)) && getenv("N4J_NET_NO_TC") == nullptr;
+    if (channels == 64 && getenv("N4J_NET_FORCE_TC") != nullptr) tc_ = true;
+    passes_ = (cfg.flags & N4J_FLAG_FAST_TF32) ? 1 : 3;
+    if (tc_) init_tc();
 }
 
 inline OuterNet::~OuterNet() {
@@ -552,6 +587,7 @@ inline void OuterNet::output(const float* params, const float* images, float* pr
     N4J_CUDA(cudaSetDevice(device_));
     N4J_CUDA(cudaMemcpyAsync(p_, params, sizeof(float) * n_, cudaMemcpyDefault, s_));
     N4J_CUDA(cudaMemcpyAsync(img_, images, sizeof(float) * B_ * 28 * 28, cudaMemcpyDefault, s_));
+    ode_->set_nhwc_io(false);
     forward(p_, img_, nullptr, train != 0, nullptr);
     N4J_CUDA(cudaMemcpyAsync(probs, probs_, sizeof(float) * B_ * 10, cudaMemcpyDefault, s_));
     N4J_CUDA(cudaStreamSynchronize(s_));
@@ -577,6 +613,13 @@ inline void OuterNet::train_step(float* params, float* updater_state, const floa
     N4J_CUDA(cudaMemcpyAsync(lab_, labels, sizeof(float) * B * 10, cudaMemcpyDefault, s_));
     N4J_CUDA(cudaMemsetAsync(g_, 0, sizeof(float) * n_, s_));          // ZeroGrad (util/listen/training/ZeroGrad.java:14-16): the theta-adjoint is seeded from the view
     phase("copies in");
+    if (tc_) {
+        forward_tc(p_, img_, lab_, ode_fwd);
+        phase("forward (stem, block, output)");
+        backward_tc(img_, ode_bwd);
+        phase("backward");
+    } else {
+    ode_->set_nhwc_io(false);
     forward(p_, img_, lab_, true, ode_fwd);
     phase("forward (stem, block, output)");
     // ---- backward --------------------------------------------------------------------------------------------------------------
@@ -615,6 +658,7 @@ inline void OuterNet::train_step(float* params, float* updater_state, const floa
     }
     conv_wgrad(img_, da, a0_, g_ + off_in_w_, g_ + off_in_b_, cin_, 0);
     phase("stem backward");
+    }
     // ---- update ----------------------------------------------------------------------------------------------------------------
     if (grad_out) N4J_CUDA(cudaMemcpyAsync(grad_out, g_, sizeof(float) * n_, cudaMemcpyDefault, s_));
     k_outer_update<<<grid(n_), 256, 0, s_>>>(p_, v_, g_, kind_, n_, (float)B, lr, mu, (float)(1.0 + (double)mu));
@@ -624,6 +668,158 @@ inline void OuterNet::train_step(float* params, float* updater_state, const floa
     if (score) N4J_CUDA(cudaMemcpyAsync(score, score_, sizeof(float), cudaMemcpyDefault, s_));
     N4J_CUDA(cudaStreamSynchronize(s_));
     phase("update + copies out");
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// fast path
+// ---------------------------------------------------------------------------------------------------------------------------
+inline void OuterNet::init_tc() {
+    const int B = B_;
+    auto zeroed = [&](long long n) { float* p = dev_alloc(n); N4J_CUDA(cudaMemset(p, 0, sizeof(float) * n)); return p; };
+    acc_pool_bytes_ = sizeof(double) * 5 * ON_BN_ACCS * ACC_STRIDE;
+    N4J_CUDA(cudaMalloc(&acc_pool_, acc_pool_bytes_)); allocs_.push_back(acc_pool_);
+    int max_tiles = 0;
+    for (int r = 0; r < 2; ++r) {
+        TcBlock& t = tb_[r];
+        const Block& b = blk_[r];
+        t.gi = make_conv_geom(B, b.Hin, b.Hin); t.go = make_conv_geom(B, b.Hout, b.Hout);
+        t.wi = make_wgrad_tc_geom(B, b.Hin, b.Hin); t.wo = make_wgrad_tc_geom(B, b.Hout, b.Hout);
+        t.sub_off = 1 - b.c1.pt;
+        const long long nin = (long long)B * 64 * b.Hin * b.Hin, nout = (long long)B * 64 * b.Hout * b.Hout;
+        t.n1 = dev_alloc(nin); t.n1img = zeroed(conv_image_floats(t.gi));
+        t.dsy = dev_alloc(nout); t.f1 = dev_alloc(nout); t.n2 = dev_alloc(nout); t.n2img = zeroed(conv_image_floats(t.go));
+        t.f2 = dev_alloc(nout); t.a_out = dev_alloc(nout);
+        t.w1f = dev_alloc(9 * 8192); t.w1b = dev_alloc(9 * 8192); t.w2f = dev_alloc(9 * 8192); t.w2b = dev_alloc(9 * 8192);
+        t.t1 = dev_alloc(nout); t.gup = zeroed(nin); t.gupimg = zeroed(conv_image_floats(t.gi)); t.dn1 = dev_alloc(nin);
+        t.daimg = zeroed(conv_image_floats(t.go)); t.da_in = dev_alloc(nin);
+        t.acc1 = acc_pool_ + (size_t)(2 * r) * ON_BN_ACCS * ACC_STRIDE; t.acc2 = acc_pool_ + (size_t)(2 * r + 1) * ON_BN_ACCS * ACC_STRIDE;
+        conv_smem_max_ = std::max(conv_smem_max_, std::max(conv_tc_smem_bytes(t.gi), conv_tc_smem_bytes(t.go)));
+        wgrad_smem_max_ = std::max(wgrad_smem_max_, std::max(conv_wgrad_tc_smem_bytes(t.wi), conv_wgrad_tc_smem_bytes(t.wo)));
+        max_tiles = std::max(max_tiles, std::max(t.wi.tiles, t.wo.tiles));
+    }
+    if (conv_smem_max_ > 227 * 1024 || wgrad_smem_max_ > 227 * 1024) throw Error{N4J_ERR_UNSUPPORTED, "stem maps too wide for the tensor-core convolutions"};
+    acco_ = acc_pool_ + (size_t)4 * ON_BN_ACCS * ACC_STRIDE;
+    const long long n0 = (long long)B * 64 * 26 * 26, nz = (long long)B * 64 * 49;
+    a0n_ = dev_alloc(n0); z1n_ = dev_alloc(nz); non_ = dev_alloc(nz); dA_ = dev_alloc(nz); dB_ = dev_alloc(nz); dC_ = dev_alloc(nz);
+    wpart_tc_ = dev_alloc((long long)max_tiles * 36864); wmid_ = dev_alloc((long long)WMID * 36864);
+    const long long ds_blocks = ((long long)B * 13 * 13 + ON_DS_WG_PIX - 1) / ON_DS_WG_PIX, in_blocks = ((long long)B * 26 * 26 + ON_IN_WG_PIX - 1) / ON_IN_WG_PIX;
+    N4J_CUDA(cudaMalloc(&dspart_, sizeof(double) * ds_blocks * 4096)); allocs_.push_back(dspart_);
+    N4J_CUDA(cudaMalloc(&inpart_, sizeof(double) * in_blocks * 640)); allocs_.push_back(inpart_);
+}
+
+// The dynamic shared-memory limits are per-function attributes shared with every Engine of the process (whose own maps are smaller):
+// raised before each step's launches.
+inline void OuterNet::set_tc_attributes() {
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, 0, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_max_));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, 0, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_max_));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<3, 0, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_max_));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv3x3_tc<1, 0, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_max_));
+    N4J_CUDA(cudaFuncSetAttribute(k_conv_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wgrad_smem_max_));
+}
+
+inline void OuterNet::conv_tc(const float* img, const float* wimg, float* out, const ConvGeom& g, int act, bool sub, int sub_off, int Ho) {
+    ConvTcArgs a{};
+    a.img = img; a.wimg = wimg; a.out = fixed_ref(out); a.g = g; a.act = act;
+    a.sub_s = 2; a.sub_off = sub_off; a.sub_H = Ho; a.sub_W = Ho;
+    const size_t smem = conv_tc_smem_bytes(g);
+    const dim3 grid(g.tiles), block(CONV_TC_THREADS);
+    if (sub) {
+        if (passes_ == 1) k_conv3x3_tc<1, 0, 0, 0, 1><<<grid, block, smem, s_>>>(a);
+        else k_conv3x3_tc<3, 0, 0, 0, 1><<<grid, block, smem, s_>>>(a);
+    } else {
+        if (passes_ == 1) k_conv3x3_tc<1, 0, 0, 0, 0><<<grid, block, smem, s_>>>(a);
+        else k_conv3x3_tc<3, 0, 0, 0, 0><<<grid, block, smem, s_>>>(a);
+    }
+}
+
+// dw_flat: DL4J's [co][ci][3][3] slot of the gradient view
+inline void OuterNet::wgrad_tc(const float* x, const float* g, const WgradTcGeom& wg, float* dw_flat) {
+    k_conv_wgrad_tc<<<dim3(wg.tiles), WGRAD_TC_THREADS, conv_wgrad_tc_smem_bytes(wg), s_>>>(fixed_ref(const_cast<float*>(x)), fixed_ref(const_cast<float*>(g)), wg,
+                                                                                             wpart_tc_, (long long*)nullptr);
+    const int per = (wg.tiles + WMID - 1) / WMID, nq = (wg.tiles + per - 1) / per;
+    k_on_wgrad_sum1<<<dim3(36, nq), 256, 0, s_>>>(wpart_tc_, wmid_, wg.tiles, per);
+    k_on_wgrad_sum2<<<144, 256, 0, s_>>>(wmid_, dw_flat, nq);
+}
+
+inline void OuterNet::forward_tc(const float* p, const float* images, const float* labels, n4j_stats* ode_fwd) {
+    const int B = B_, C = 64;
+    set_tc_attributes();
+    N4J_CUDA(cudaMemsetAsync(acc_pool_, 0, acc_pool_bytes_, s_));
+    const long long r0 = (long long)B * 26 * 26;
+    k_on_in_conv_fwd<<<grid_rows(r0), 256, 0, s_>>>(images, p + off_in_w_, p + off_in_b_, a0n_, B, 28, 28, tb_[0].acc1);
+    const float* a = a0n_;
+    for (int r = 0; r < 2; ++r) {
+        TcBlock& t = tb_[r];
+        const Block& b = blk_[r];
+        const long long ri = (long long)B * b.Hin * b.Hin, ro = (long long)B * b.Hout * b.Hout;
+        k_conv_w_to_tc<<<72, 256, 0, s_>>>(p + b.o_c1, t.w1f, 0); k_conv_w_to_tc<<<72, 256, 0, s_>>>(p + b.o_c1, t.w1b, 1);
+        k_conv_w_to_tc<<<72, 256, 0, s_>>>(p + b.o_c2, t.w2f, 0); k_conv_w_to_tc<<<72, 256, 0, s_>>>(p + b.o_c2, t.w2b, 1);
+        if (r > 0) k_on_bn_stats<<<grid_rows(ri), 256, 0, s_>>>(a, ri, t.acc1);        // (block 0: the input convolution accumulated them)
+        k_on_bn_apply<<<grid(ri * 16), 256, 0, s_>>>(a, t.acc1, ri, 1e-5f, p + b.o_bn1, p + b.o_bn1 + C, t.n1, t.n1img, t.gi);
+        k_on_ds_fwd<<<(unsigned)((ro + 31) / 32), 256, 0, s_>>>(t.n1, p + b.o_ds, t.dsy, B, b.Hin, b.Hout);
+        conv_tc(t.n1img, t.w1f, t.f1, t.gi, N4J_ACT_RELU, true, t.sub_off, b.Hout);                      // firstConvStem: stride 2, ReLU
+        k_on_bn_stats<<<grid_rows(ro), 256, 0, s_>>>(t.f1, ro, t.acc2);
+        k_on_bn_apply<<<grid(ro * 16), 256, 0, s_>>>(t.f1, t.acc2, ro, 1e-5f, p + b.o_bn2, p + b.o_bn2 + C, t.n2, t.n2img, t.go);
+        conv_tc(t.n2img, t.w2f, t.f2, t.go, N4J_ACT_IDENTITY, false, 0, 0);                              // secondConvStem
+        k_outer_add<<<grid(ro * 64), 256, 0, s_>>>(t.dsy, t.f2, t.a_out, ro * 64);                       // stemAdd_r
+        a = t.a_out;
+    }
+    N4J_CUDA(cudaGetLastError());
+    ode_->set_nhwc_io(true);
+    ode_->bind_params(p + off_ode_, n_ode_);
+    ode_->forward(a, time_, 2, 0, z1n_, ode_fwd);
+    const long long rz = (long long)B * 49;
+    k_on_bn_stats<<<grid_rows(rz), 256, 0, s_>>>(z1n_, rz, acco_);
+    k_on_bn_apply<<<grid(rz * 16), 256, 0, s_>>>(z1n_, acco_, rz, 1e-5f, p + off_bno_, p + off_bno_ + C, non_, (float*)nullptr, ConvGeom{});
+    k_on_pool_fwd<<<(B * 64 + 255) / 256, 256, 0, s_>>>(non_, pool_, B, 49);
+    k_outer_output_fwd<<<(B + 255) / 256, 256, 0, s_>>>(pool_, p + off_ow_, p + off_ob_, labels, probs_, labels ? score_parts_ : nullptr, B, C);
+    N4J_CUDA(cudaGetLastError());
+}
+
+inline void OuterNet::backward_tc(const float* images, n4j_stats* ode_bwd) {
+    const int B = B_, C = 64;
+    const long long rz = (long long)B * 49;
+    k_outer_output_bwd<<<1, 256, 0, s_>>>(pool_, p_ + off_ow_, probs_, lab_, score_parts_, g_ + off_ow_, g_ + off_ob_, dpool_, score_, B, C);
+    k_on_pool_bwd<<<grid(rz * 64), 256, 0, s_>>>(dpool_, dA_, rz * 64, 49);
+    k_on_bn_bwd_stats<<<grid_rows(rz), 256, 0, s_>>>(z1n_, non_, dA_, acco_, rz, 1e-5f);
+    OnBnBwdOut oo{dB_, nullptr, ConvGeom{}, 7, 7, 1, 0, 0};
+    k_on_bn_bwd_dx<<<grid(rz * 16), 256, 0, s_>>>(z1n_, non_, dA_, acco_, rz, 1e-5f, p_ + off_bno_, g_ + off_bno_, 0.1f, oo);
+    N4J_CUDA(cudaGetLastError());
+    ode_->backward(nullptr, dB_, time_, 2, N4J_TIMEGRAD_NONE, g_ + off_ode_, dC_, nullptr, ode_bwd);
+    const float* da = dC_;            // epsilon at the output of block r
+    k_compact_to_image<<<grid(rz * 16), 256, 0, s_>>>(fixed_ref(dC_), tb_[1].go, tb_[1].daimg);
+    for (int r = 1; r >= 0; --r) {
+        TcBlock& t = tb_[r];
+        const Block& b = blk_[r];
+        const float* a_in = r == 0 ? a0n_ : tb_[0].a_out;
+        const long long ri = (long long)B * b.Hin * b.Hin, ro = (long long)B * b.Hout * b.Hout;
+        // secondConvStem: weight gradient, epsilon of secondNorm's output
+        wgrad_tc(t.n2, da, t.wo, g_ + b.o_c2);
+        conv_tc(t.daimg, t.w2b, t.t1, t.go, N4J_ACT_IDENTITY, false, 0, 0);
+        // secondNorm backward; its dx, masked by firstConvStem's ReLU, scattered to the sampled pixels of the full-resolution map
+        k_on_bn_bwd_stats<<<grid_rows(ro), 256, 0, s_>>>(t.f1, t.n2, t.t1, t.acc2, ro, 1e-5f);
+        OnBnBwdOut o2{t.gup, t.gupimg, t.gi, b.Hout, b.Hin, 2, t.sub_off, 1};
+        k_on_bn_bwd_dx<<<grid(ro * 16), 256, 0, s_>>>(t.f1, t.n2, t.t1, t.acc2, ro, 1e-5f, p_ + b.o_bn2, g_ + b.o_bn2, 0.1f, o2);
+        // firstConvStem and downSample both read n1
+        wgrad_tc(t.n1, t.gup, t.wi, g_ + b.o_c1);
+        const int dsb = (int)((ro + ON_DS_WG_PIX - 1) / ON_DS_WG_PIX);
+        k_on_ds_wgrad<<<dsb, 256, 0, s_>>>(t.n1, da, dspart_, B, b.Hin, b.Hout);
+        k_on_sum_parts<<<16, 256, 0, s_>>>(dspart_, g_ + b.o_ds, 4096, dsb, 4096);
+        conv_tc(t.gupimg, t.w1b, t.dn1, t.gi, N4J_ACT_IDENTITY, false, 0, 0);
+        k_on_ds_dgrad_add<<<(unsigned)((ro + 31) / 32), 256, 0, s_>>>(da, p_ + b.o_ds, t.dn1, B, b.Hin, b.Hout);
+        // firstNorm backward -> epsilon at the block's input (and, for block 1, its operand image for block 0's secondConvStem dgrad)
+        k_on_bn_bwd_stats<<<grid_rows(ri), 256, 0, s_>>>(a_in, t.n1, t.dn1, t.acc1, ri, 1e-5f);
+        OnBnBwdOut o1{t.da_in, r == 1 ? tb_[0].daimg : nullptr, r == 1 ? tb_[0].go : ConvGeom{}, b.Hin, b.Hin, 1, 0, 0};
+        k_on_bn_bwd_dx<<<grid(ri * 16), 256, 0, s_>>>(a_in, t.n1, t.dn1, t.acc1, ri, 1e-5f, p_ + b.o_bn1, g_ + b.o_bn1, 0.1f, o1);
+        da = t.da_in;
+    }
+    const long long r0 = (long long)B * 26 * 26;
+    const int inb = (int)((r0 + ON_IN_WG_PIX - 1) / ON_IN_WG_PIX);
+    k_on_in_conv_wgrad<<<inb, 256, 0, s_>>>(images, da, inpart_, B, 28, 28);
+    // inpart: [co][tap] then [co] per block; the gradient view stores the bias first (bias-first convolution parameters)
+    k_on_sum_parts<<<3, 256, 0, s_>>>(inpart_, g_ + off_in_w_, 576, inb, 640);
+    k_on_sum_parts<<<1, 256, 0, s_>>>(inpart_ + 576, g_ + off_in_b_, 64, inb, 640);
+    N4J_CUDA(cudaGetLastError());
 }
 
 }  // namespace n4j

@@ -1,0 +1,402 @@
+// outer_net_tc.cuh — kernels of the FAST path of the network around the ODE block, 64 kernels per layer.
+//
+// Same layers as outer_net.cuh (examples/mnist/ResBlockStem.java:25-48, Output.java:27-35), other data path: activations are NHWC
+// ([B*H*W][64], the ODE engine's internal layout, so the block takes and returns them without a permutation), and every 64 -> 64
+// 3x3 convolution of the stem — forward, input gradient and weight gradient — runs on the tcgen05 kernels of the hot path
+// (conv_tc.cuh, conv_wgrad_tc.cuh; 3xTF32, fp32-faithful):
+//   * stride 1 (secondConvStem): as in the ODE block, from a prepared operand image;
+//   * stride 2 (firstConvStem, ConvolutionMode.Same): the launch computes the stride-1 "same" convolution of the full-resolution
+//     image and its epilogue stores only the sampled pixels (k_conv3x3_tc<.., SUB = 1>); backward, the gradient is scattered into a
+//     zero full-resolution tensor (compact + operand image), which turns dgrad and wgrad into the stride-1 kernels as well.
+// What stays on the CUDA cores is small: the 1 -> 64 input convolution (9 products per output), the 1x1 stride-2 downSample
+// (64 products), BatchNorm, pooling, the output layer.  Reductions accumulate exact fp32 products in double as everywhere else;
+// elementwise expressions keep the oracle's order (oracle/outer_oracle.py).  BatchNorm statistics are raw double sums that every
+// consumer finalises itself (the engine's deferred scheme, layer_kernels.cuh), so no kernel waits for a last block.
+#pragma once
+
+#include "conv_tc.cuh"
+#include "conv_wgrad_tc.cuh"
+
+namespace n4j {
+
+// accumulators of one BatchNorm layer: [0,64) sum x, [64,128) sum x^2, [128,192) sum dy, [192,256) sum dy*xhat — ACC_STRIDE doubles apart
+constexpr int ON_BN_ACCS = 256;
+
+__device__ __forceinline__ void on_bn_final(const double* __restrict__ acc, long long M, float eps, int c, float& mean, float& inv, float& var_f) {
+    const double m = acc[c * ACC_STRIDE] / (double)M;
+    double var = acc[(64 + c) * ACC_STRIDE] / (double)M - m * m;
+    if (var < 0) var = 0;
+    mean = (float)m;
+    inv = (float)(1.0 / sqrt(var + (double)eps));
+    var_f = (float)var;
+}
+
+// inputConv: y[(b,oh,ow)][co] = (float)sum_{kh,kw} x[b,oh+kh,ow+kw] * w[co,kh,kw] + bias[co]      (1 -> 64, 3x3, Truncate)
+// thread = (output pixel, 4-channel chunk); also accumulates the statistics of the BatchNorm behind it (acc may be null)
+__global__ void __launch_bounds__(256) k_on_in_conv_fwd(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                         float* __restrict__ y, int B, int H, int W, double* __restrict__ acc) {
+    __shared__ float s_w[9][64];
+    __shared__ float s_b[64];
+    __shared__ double s_red[2][16][64];
+    for (int i = threadIdx.x; i < 576; i += 256) s_w[i % 9][i / 9] = w[i];
+    if (threadIdx.x < 64) s_b[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const int Ho = H - 2, Wo = W - 2;
+    const long long n = (long long)B * Ho * Wo;
+    const int chunk = threadIdx.x & 15, c0 = chunk * 4;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (long long p = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); p < n; p += (long long)gridDim.x * 16) {
+        const int ow = (int)(p % Wo), oh = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
+        const float* xb = x + ((long long)b * H + oh) * W + ow;
+        double a[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const double xv = (double)xb[(t / 3) * W + (t % 3)];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] += xv * (double)s_w[t][c0 + k];
+        }
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            o[k] = __fadd_rn((float)a[k], s_b[c0 + k]);
+            s1[k] += (double)o[k]; s2[k] += (double)o[k] * (double)o[k];
+        }
+        reinterpret_cast<float4*>(y)[p * 16 + chunk] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    if (acc) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s_red[0][threadIdx.x >> 4][c0 + k] = s1[k]; s_red[1][threadIdx.x >> 4][c0 + k] = s2[k]; }
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            const int q = threadIdx.x >> 6, c = threadIdx.x & 63;
+            double t = 0;
+            for (int r = 0; r < 16; ++r) t += s_red[q][r][c];
+            atomicAdd(acc + (q * 64 + c) * ACC_STRIDE, t);
+        }
+    }
+}
+
+// column sums of an NHWC tensor [M][64]: acc[c] += sum x, acc[64 + c] += sum x^2
+__global__ void __launch_bounds__(256) k_on_bn_stats(const float* __restrict__ x, long long M, double* __restrict__ acc) {
+    __shared__ double s_red[2][16][64];
+    const int chunk = threadIdx.x & 15, c0 = chunk * 4;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (long long r = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); r < M; r += (long long)gridDim.x * 16) {
+        const float4 v = reinterpret_cast<const float4*>(x)[r * 16 + chunk];
+        const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { s1[k] += (double)a[k]; s2[k] += (double)a[k] * (double)a[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s_red[0][threadIdx.x >> 4][c0 + k] = s1[k]; s_red[1][threadIdx.x >> 4][c0 + k] = s2[k]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int q = threadIdx.x >> 6, c = threadIdx.x & 63;
+        double t = 0;
+        for (int r = 0; r < 16; ++r) t += s_red[q][r][c];
+        atomicAdd(acc + (q * 64 + c) * ACC_STRIDE, t);
+    }
+}
+
+// y = relu(gamma * ((x - mean) * invstd) + beta): compact NHWC and (img != null) the zero-padded hi/lo operand image of the convolution behind
+__global__ void __launch_bounds__(256) k_on_bn_apply(const float* __restrict__ x, const double* __restrict__ acc, long long M, float eps,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
+                                                      float* __restrict__ img, ConvGeom g) {
+    __shared__ float s_m[64], s_i[64], s_g[64], s_b[64];
+    if (threadIdx.x < 64) {
+        float var;
+        on_bn_final(acc, M, eps, threadIdx.x, s_m[threadIdx.x], s_i[threadIdx.x], var);
+        s_g[threadIdx.x] = gamma[threadIdx.x]; s_b[threadIdx.x] = beta[threadIdx.x];
+    }
+    __syncthreads();
+    const long long n4 = M * 16;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int chunk = (int)(i & 15), c = chunk * 4;
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        const float a[4] = {v.x, v.y, v.z, v.w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float t = __fadd_rn(__fmul_rn(s_g[c + k], __fmul_rn(__fsub_rn(a[k], s_m[c + k]), s_i[c + k])), s_b[c + k]);
+            o[k] = t > 0.f ? t : 0.f;
+        }
+        const float4 ov = make_float4(o[0], o[1], o[2], o[3]);
+        reinterpret_cast<float4*>(y)[i] = ov;
+        if (img) store_split4(img, g, chunk, padded_row(g, i >> 4), ov);
+    }
+}
+
+// downSample: 1x1 convolution, stride 2, no bias: y[(b,oh,ow)][co] = (float)sum_ci x[(b,2oh,2ow)][ci] * w[co][ci]
+// block = 32 output pixels; thread = (pixel pair, 4 output channels)
+__global__ void __launch_bounds__(256) k_on_ds_fwd(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int B, int Hi, int Ho) {
+    __shared__ float s_w[64][65];      // [ci][co]
+    __shared__ float s_x[32][64];
+    for (int i = threadIdx.x; i < 4096; i += 256) s_w[i & 63][i >> 6] = w[i];      // w[co][ci]
+    const long long P = (long long)B * Ho * Ho, p0 = (long long)blockIdx.x * 32;
+    for (int i = threadIdx.x; i < 32 * 16; i += 256) {
+        const long long p = p0 + (i >> 4);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < P) {
+            const int ow = (int)(p % Ho), oh = (int)((p / Ho) % Ho), b = (int)(p / ((long long)Ho * Ho));
+            v = reinterpret_cast<const float4*>(x)[(((long long)b * Hi + 2 * oh) * Hi + 2 * ow) * 16 + (i & 15)];
+        }
+        reinterpret_cast<float4*>(&s_x[i >> 4][0])[i & 15] = v;
+    }
+    __syncthreads();
+    const int c0 = (threadIdx.x & 15) * 4;
+    for (int r = threadIdx.x >> 4; r < 32; r += 16) {
+        if (p0 + r >= P) break;
+        double a[4] = {0, 0, 0, 0};
+        for (int ci = 0; ci < 64; ++ci) {
+            const double xv = (double)s_x[r][ci];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] += xv * (double)s_w[ci][c0 + k];
+        }
+        reinterpret_cast<float4*>(y)[(p0 + r) * 16 + (threadIdx.x & 15)] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
+    }
+}
+
+// dn1[(b,2oh,2ow)][ci] += (float)sum_co g[(b,oh,ow)][co] * w[co][ci]       (downSample's epsilon added onto firstConv's, in place)
+__global__ void __launch_bounds__(256) k_on_ds_dgrad_add(const float* __restrict__ g, const float* __restrict__ w, float* __restrict__ dx, int B, int Hi, int Ho) {
+    __shared__ float s_w[64][64];      // [co][ci]
+    __shared__ float s_g[32][64];
+    for (int i = threadIdx.x; i < 4096; i += 256) s_w[i >> 6][i & 63] = w[i];
+    const long long P = (long long)B * Ho * Ho, p0 = (long long)blockIdx.x * 32;
+    for (int i = threadIdx.x; i < 32 * 16; i += 256) {
+        const long long p = p0 + (i >> 4);
+        reinterpret_cast<float4*>(&s_g[i >> 4][0])[i & 15] = p < P ? reinterpret_cast<const float4*>(g)[p * 16 + (i & 15)] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const int c0 = (threadIdx.x & 15) * 4;
+    for (int r = threadIdx.x >> 4; r < 32; r += 16) {
+        const long long p = p0 + r;
+        if (p >= P) break;
+        double a[4] = {0, 0, 0, 0};
+        for (int co = 0; co < 64; ++co) {
+            const double gv = (double)s_g[r][co];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] += gv * (double)s_w[co][c0 + k];
+        }
+        const int ow = (int)(p % Ho), oh = (int)((p / Ho) % Ho), b = (int)(p / ((long long)Ho * Ho));
+        float4* d = reinterpret_cast<float4*>(dx) + (((long long)b * Hi + 2 * oh) * Hi + 2 * ow) * 16 + (threadIdx.x & 15);
+        const float4 u = *d;
+        *d = make_float4(__fadd_rn((float)a[0], u.x), __fadd_rn((float)a[1], u.y), __fadd_rn((float)a[2], u.z), __fadd_rn((float)a[3], u.w));
+    }
+}
+
+// downSample weight gradient: dw[co][ci] = sum_p x[(b,2oh,2ow)][ci] * g[p][co]; block = 64 pixels, thread = 4 ci x 4 co, double partials per block
+constexpr int ON_DS_WG_PIX = 64;
+__global__ void __launch_bounds__(256) k_on_ds_wgrad(const float* __restrict__ x, const float* __restrict__ g, double* __restrict__ part, int B, int Hi, int Ho) {
+    __shared__ float s_x[ON_DS_WG_PIX][64], s_g[ON_DS_WG_PIX][64];
+    const long long P = (long long)B * Ho * Ho, p0 = (long long)blockIdx.x * ON_DS_WG_PIX;
+    for (int i = threadIdx.x; i < ON_DS_WG_PIX * 16; i += 256) {
+        const long long p = p0 + (i >> 4);
+        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+        if (p < P) {
+            const int ow = (int)(p % Ho), oh = (int)((p / Ho) % Ho), b = (int)(p / ((long long)Ho * Ho));
+            xv = reinterpret_cast<const float4*>(x)[(((long long)b * Hi + 2 * oh) * Hi + 2 * ow) * 16 + (i & 15)];
+            gv = reinterpret_cast<const float4*>(g)[p * 16 + (i & 15)];
+        }
+        reinterpret_cast<float4*>(&s_x[i >> 4][0])[i & 15] = xv;
+        reinterpret_cast<float4*>(&s_g[i >> 4][0])[i & 15] = gv;
+    }
+    __syncthreads();
+    const int ci0 = (threadIdx.x >> 4) * 4, co0 = (threadIdx.x & 15) * 4;
+    double a[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[i][j] = 0.0;
+    for (int r = 0; r < ON_DS_WG_PIX; ++r) {
+        const float4 xv = *reinterpret_cast<const float4*>(&s_x[r][ci0]);
+        const float4 gv = *reinterpret_cast<const float4*>(&s_g[r][co0]);
+        const double xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[i][j] += xs[i] * gs[j];
+    }
+    double* o = part + (long long)blockIdx.x * 4096;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[(co0 + j) * 64 + ci0 + i] = a[i][j];      // [co][ci], DL4J's order
+}
+// dst[i] = (float) sum_q part[q][i] in block order (deterministic)
+__global__ void __launch_bounds__(256) k_on_sum_parts(const double* __restrict__ part, float* __restrict__ dst, int n, int nparts, int stride) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int q = 0; q < nparts; ++q) s += part[(long long)q * stride + i];
+    dst[i] = (float)s;
+}
+
+// inputConv weight / bias gradient: dw[co][t] = sum x[b,oh+kh,ow+kw] * g[(b,oh,ow)][co], db[co] = sum g.  block = 256 pixels, partial [640] doubles per block
+constexpr int ON_IN_WG_PIX = 256;
+__global__ void __launch_bounds__(256) k_on_in_conv_wgrad(const float* __restrict__ x, const float* __restrict__ g, double* __restrict__ part, int B, int H, int W) {
+    __shared__ double s_red[16][64];
+    const int Ho = H - 2, Wo = W - 2;
+    const long long n = (long long)B * Ho * Wo, p0 = (long long)blockIdx.x * ON_IN_WG_PIX;
+    const int chunk = threadIdx.x & 15, c0 = chunk * 4, sub = threadIdx.x >> 4;
+    double a[10][4];
+#pragma unroll
+    for (int t = 0; t < 10; ++t)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[t][k] = 0.0;
+    for (int r = sub; r < ON_IN_WG_PIX; r += 16) {
+        const long long p = p0 + r;
+        if (p >= n) break;
+        const int ow = (int)(p % Wo), oh = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
+        const float4 gv = reinterpret_cast<const float4*>(g)[p * 16 + chunk];
+        const double gs[4] = {gv.x, gv.y, gv.z, gv.w};
+        const float* xb = x + ((long long)b * H + oh) * W + ow;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const double xv = (double)xb[(t / 3) * W + (t % 3)];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[t][k] += xv * gs[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[9][k] += gs[k];
+    }
+    double* o = part + (long long)blockIdx.x * 640;
+#pragma unroll
+    for (int t = 0; t < 10; ++t) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_red[sub][c0 + k] = a[t][k];
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            double s = 0.0;
+            for (int r = 0; r < 16; ++r) s += s_red[r][threadIdx.x];
+            o[t < 9 ? threadIdx.x * 9 + t : 576 + threadIdx.x] = s;       // dw [co][tap] then db [co]
+        }
+        __syncthreads();
+    }
+}
+
+// global average pooling, NHWC: pool[b][c] = (float)(sum_p x[(b,p)][c] / HW)
+__global__ void __launch_bounds__(256) k_on_pool_fwd(const float* __restrict__ x, float* __restrict__ p, int B, int HW) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 64) return;
+    const int b = i >> 6, c = i & 63;
+    double s = 0.0;
+    for (int q = 0; q < HW; ++q) s += (double)x[((long long)b * HW + q) * 64 + c];
+    p[i] = (float)(s / (double)HW);
+}
+__global__ void __launch_bounds__(256) k_on_pool_bwd(const float* __restrict__ dp, float* __restrict__ dx, long long n, int HW) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dx[i] = __fdiv_rn(dp[(i / (64LL * HW)) * 64 + (i & 63)], (float)HW);
+}
+
+// BatchNorm backward statistics: dy = y > 0 ? g : 0;  acc[128 + c] += sum dy, acc[192 + c] += sum dy * xhat
+__global__ void __launch_bounds__(256) k_on_bn_bwd_stats(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ g,
+                                                          double* __restrict__ acc, long long M, float eps) {
+    __shared__ float s_m[64], s_i[64];
+    __shared__ double s_red[2][16][64];
+    if (threadIdx.x < 64) { float var; on_bn_final(acc, M, eps, threadIdx.x, s_m[threadIdx.x], s_i[threadIdx.x], var); }
+    __syncthreads();
+    const int chunk = threadIdx.x & 15, c0 = chunk * 4;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    for (long long r = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); r < M; r += (long long)gridDim.x * 16) {
+        const float4 xv = reinterpret_cast<const float4*>(x)[r * 16 + chunk], yv = reinterpret_cast<const float4*>(y)[r * 16 + chunk],
+                     gv = reinterpret_cast<const float4*>(g)[r * 16 + chunk];
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float dy = ys[k] > 0.f ? gs[k] : 0.f;
+            const float xh = __fmul_rn(__fsub_rn(xs[k], s_m[c0 + k]), s_i[c0 + k]);
+            s1[k] += (double)dy; s2[k] += (double)dy * (double)xh;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s_red[0][threadIdx.x >> 4][c0 + k] = s1[k]; s_red[1][threadIdx.x >> 4][c0 + k] = s2[k]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int q = threadIdx.x >> 6, c = threadIdx.x & 63;
+        double t = 0;
+        for (int r = 0; r < 16; ++r) t += s_red[q][r][c];
+        atomicAdd(acc + (128 + q * 64 + c) * ACC_STRIDE, t);
+    }
+}
+
+// BatchNorm backward dx = gamma*invstd * ((dy - mean(dy)) - xhat * mean(dy*xhat)); block 0 also writes the layer's slice of the gradient view
+// (dgamma, dbeta, and the running-statistics "gradients" (running - batch) * (1 - decay), OdeGraphHelper.java:105-119).
+// Destination: compact NHWC `dx` (and, img != null, the operand image of geometry gi) of a [B, Hd, Hd] tensor; the source pixel (b, h, w) of the
+// [B, Hs, Hs] tensor goes to (b, h * up_s + up_off, w * up_s + up_off) — up_s = 1: same place; up_s = 2: the zero-upsampled gradient of a
+// stride-2 convolution (the other pixels of dx / img stay zero: they were zeroed once and are never written).  xmask: additionally multiply by
+// (x > 0): x is the ReLU output of the convolution in front (firstConvStem), whose epsilon this then is.
+struct OnBnBwdOut {
+    float* dx;
+    float* img;
+    ConvGeom gi;
+    int Hs, Hd, up_s, up_off, xmask;
+};
+__global__ void __launch_bounds__(256) k_on_bn_bwd_dx(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ g,
+                                                       const double* __restrict__ acc, long long M, float eps, const float* __restrict__ bn /*gamma,beta,mean,var*/,
+                                                       float* __restrict__ gbn, float one_minus_decay, OnBnBwdOut o) {
+    __shared__ float s_m[64], s_i[64], s_k[64], s_m1[64], s_m2[64];
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        float var;
+        on_bn_final(acc, M, eps, c, s_m[c], s_i[c], var);
+        const double sdy = acc[(128 + c) * ACC_STRIDE], sdyxh = acc[(192 + c) * ACC_STRIDE];
+        s_m1[c] = (float)(sdy / (double)M); s_m2[c] = (float)(sdyxh / (double)M);
+        s_k[c] = __fmul_rn(bn[c], s_i[c]);
+        if (blockIdx.x == 0) {
+            gbn[c] = (float)sdyxh; gbn[64 + c] = (float)sdy;
+            gbn[128 + c] = __fmul_rn(__fsub_rn(bn[128 + c], s_m[c]), one_minus_decay);
+            gbn[192 + c] = __fmul_rn(__fsub_rn(bn[192 + c], var), one_minus_decay);
+        }
+    }
+    __syncthreads();
+    const long long n4 = M * 16;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int chunk = (int)(i & 15), c = chunk * 4;
+        const float4 xv = reinterpret_cast<const float4*>(x)[i], yv = reinterpret_cast<const float4*>(y)[i], gv = reinterpret_cast<const float4*>(g)[i];
+        const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float dy = ys[k] > 0.f ? gs[k] : 0.f;
+            const float xh = __fmul_rn(__fsub_rn(xs[k], s_m[c + k]), s_i[c + k]);
+            r[k] = __fmul_rn(s_k[c + k], __fsub_rn(__fsub_rn(dy, s_m1[c + k]), __fmul_rn(xh, s_m2[c + k])));
+            if (o.xmask && !(xs[k] > 0.f)) r[k] = 0.f;
+        }
+        long long row = i >> 4;
+        if (o.up_s != 1) {
+            const int w = (int)(row % o.Hs), h = (int)((row / o.Hs) % o.Hs);
+            const long long b = row / ((long long)o.Hs * o.Hs);
+            row = (b * o.Hd + h * o.up_s + o.up_off) * o.Hd + w * o.up_s + o.up_off;
+        }
+        const float4 ov = make_float4(r[0], r[1], r[2], r[3]);
+        reinterpret_cast<float4*>(o.dx)[row * 16 + chunk] = ov;
+        if (o.img) store_split4(o.img, o.gi, chunk, padded_row(o.gi, row), ov);
+    }
+}
+
+// sum of the per-tile partials of k_conv_wgrad_tc in tile order (deterministic) straight into DL4J's [co][ci][3][3] gradient slots:
+// two levels, so that hundreds of tiles (26 x 26 maps) do not become one long dependent chain per thread
+// level 1: mid[q][i] = sum of partials [q*per, (q+1)*per);  level 2: dst[co][ci][tap] = sum_q mid[q][tap][ci][co]
+__global__ void __launch_bounds__(256) k_on_wgrad_sum1(const float* __restrict__ part, float* __restrict__ mid, int nparts, int per) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // float4 index, 9216 per partial
+    const int q = blockIdx.y;
+    if (i >= 9216) return;
+    const int b0 = q * per, b1 = min(nparts, b0 + per);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int b = b0; b < b1; ++b) {
+        const float4 v = reinterpret_cast<const float4*>(part)[(long long)b * 9216 + i];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(mid)[(long long)q * 9216 + i] = s;
+}
+__global__ void __launch_bounds__(256) k_on_wgrad_sum2(const float* __restrict__ mid, float* __restrict__ dst, int nq) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;      // element of [tap][ci][co]
+    if (i >= 36864) return;
+    float s = 0.f;
+    for (int q = 0; q < nq; ++q) s += mid[(long long)q * 36864 + i];
+    const int co = i & 63, ci = (i >> 6) & 63, tap = i >> 12;
+    dst[(co * 64 + ci) * 9 + tap] = s;
+}
+
+}  // namespace n4j

@@ -164,6 +164,92 @@ def test_train_step_matches_oracle(C, B):
         model.close()
 
 
+def _neutral_ode_block(p, layout, C):
+    """ODE-block parameters that make f(z) = 0 exactly: convolution weights 0, gamma 1, beta 0.  Then z(t1) = z(t0), the adjoint passes
+    the epsilon through unchanged and every block gradient is exactly 0 in any implementation — the step compares the layers AROUND
+    the block without the block's own gradient sensitivity in between."""
+    o, n = layout.slices["ode"]
+    q = o
+    for kind in ("bn", "conv", "bn", "conv", "bn"):
+        if kind == "bn":
+            p[q:q + C] = 1; p[q + C:q + 3 * C] = 0; p[q + 3 * C:q + 4 * C] = 1; q += 4 * C
+        else:
+            p[q:q + C * C * 9] = 0; q += C * C * 9
+    assert q == o + n
+    return p
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B", [8, 32])
+def test_fast_stem_matches_oracle(B):
+    """The default-mode network around the block (outer_net_tc.cuh: NHWC, stem convolutions 64 -> 64 on the tcgen05 kernels, the stride-2
+    ones through the sub-sampling epilogue / zero-upsampled gradients) against the oracle, with a neutral ODE block in between: score,
+    every gradient slot, updated parameters and updater state within rtol 1e-4.  (The input convolution's bias gradient is structurally
+    zero — a BatchNorm follows — so it is checked against the weight gradient's scale instead of its own.)"""
+    C = 64
+    model, orc, p, rng = _model_and_oracle(C, B, 0)
+    try:
+        p = _neutral_ode_block(p, orc.layout, C)
+        v = (0.01 * rng.standard_normal(p.size)).astype(np.float32)
+        images = rng.standard_normal((B, 1, 28, 28)).astype(np.float32)
+        labels = np.eye(10, dtype=np.float32)[rng.integers(0, 10, B)]
+        want = orc.train_step(p, v, images, labels, lr=0.1, mu=0.9)
+        model.setParams(p)
+        model.updater_state = v.copy()
+        score = model.fit(images, labels, lr=0.1, keep_gradient=True)
+        fs, bs = model.ode_fwd_stats, model.ode_bwd_stats
+        assert (fs.nfe, fs.accepted, fs.rejected) == want["ode_fwd_stats"] and (bs.nfe, bs.accepted, bs.rejected) == want["ode_bwd_stats"]
+        assert abs(score - want["score"]) <= 1e-5 * max(1.0, abs(want["score"]))
+        got, ref = model.last_gradient.astype(np.float64), want["grad"]
+        o, n = orc.layout.slices["ode"]
+        assert not got[o:o + n].any() and not ref[o:o + n].any()
+        wmax = np.abs(ref[C:10 * C]).max()
+        assert np.abs(got[:C]).max() <= 1e-5 * wmax and np.abs(ref[:C]).max() <= 1e-5 * wmax      # inputConv bias gradient: zero up to rounding
+        for name, (a, b) in orc.layout.slices.items():
+            if name == "ode" or (a, b) == (0, C):
+                continue
+            err = np.abs(got[a:a + b] - ref[a:a + b])
+            tol = 1e-4 * np.abs(ref[a:a + b]) + 1e-5 * np.abs(ref[a:a + b]).max()
+            assert (err <= tol).all(), f"{name}: {(err > tol).sum()} of {err.size} outside rtol 1e-4; worst {err.max():.3e} (max |ref| {np.abs(ref[a:a + b]).max():.3e})"
+        mask = np.ones(p.size, dtype=bool); mask[:C] = False
+        for name, gotv, refv in (("params", model.params, want["params"]), ("updater state", model.updater_state, want["updater_state"])):
+            err = np.abs(gotv.astype(np.float64) - refv)[mask]
+            tol = (1e-4 * np.abs(refv) + 1e-5 * np.abs(refv).max())[mask]
+            assert (err <= tol).all(), f"{name}: {(err > tol).sum()} outside rtol 1e-4"
+    finally:
+        model.close()
+
+
+@pytest.mark.gpu
+def test_train_step_default_mode_matches_oracle_within_block_sensitivity():
+    """The whole default-mode step with a live ODE block (fast stem + tcgen05 block): identical accepted / rejected counts, score to 1e-5,
+    output-layer gradients to rtol 1e-4 (they do not pass through the block's adjoint); everything upstream inherits the block's
+    ReLU / BatchNorm gradient sensitivity (the oracle itself moves by 5e-3 when its contractions move by 1e-8), so
+    it is only held to a coarse relative L2 bound here (measured 0.08 at this batch of 8; a wrong layout or a missing term gives O(1)) —
+    the layers around the block are pinned tightly by test_fast_stem_matches_oracle, the block itself by test_gpu_parity / test_gpu_fullsize."""
+    C, B = 64, 8
+    model, orc, p, rng = _model_and_oracle(C, B, 0)
+    try:
+        v = np.zeros(p.size, dtype=np.float32)
+        images = rng.standard_normal((B, 1, 28, 28)).astype(np.float32)
+        labels = np.eye(10, dtype=np.float32)[rng.integers(0, 10, B)]
+        want = orc.train_step(p, v, images, labels, lr=0.1, mu=0.9)
+        model.setParams(p)
+        score = model.fit(images, labels, lr=0.1, keep_gradient=True)
+        fs, bs = model.ode_fwd_stats, model.ode_bwd_stats
+        assert (fs.nfe, fs.accepted, fs.rejected) == want["ode_fwd_stats"] and (bs.nfe, bs.accepted, bs.rejected) == want["ode_bwd_stats"]
+        assert abs(score - want["score"]) <= 1e-5 * max(1.0, abs(want["score"]))
+        got, ref = model.last_gradient.astype(np.float64), want["grad"]
+        noop = orc.layout.noop_mask()
+        for name in ("output.W", "output.b"):
+            a, b = orc.layout.slices[name]
+            np.testing.assert_allclose(got[a:a + b], ref[a:a + b], rtol=1e-4, atol=1e-5 * np.abs(ref[a:a + b]).max())
+        rel = np.linalg.norm((got - ref)[~noop]) / np.linalg.norm(ref[~noop])
+        assert rel < 0.2, rel
+    finally:
+        model.close()
+
+
 @pytest.mark.gpu
 def test_training_reduces_the_loss_and_inference_uses_running_statistics():
     """A few steps of fit() on one fixed minibatch (default mode, 64 channels, batch 32): the score goes down, parameters stay finite,
