@@ -702,7 +702,7 @@ inline void OuterNet::init_tc() {
     const long long n0 = (long long)B * 64 * 26 * 26, nz = (long long)B * 64 * 49;
     a0n_ = dev_alloc(n0); z1n_ = dev_alloc(nz); non_ = dev_alloc(nz); dA_ = dev_alloc(nz); dB_ = dev_alloc(nz); dC_ = dev_alloc(nz);
     wpart_tc_ = dev_alloc((long long)max_tiles * 36864); wmid_ = dev_alloc((long long)WMID * 36864);
-    const long long ds_blocks = ((long long)B * 13 * 13 + ON_DS_WG_PIX - 1) / ON_DS_WG_PIX, in_blocks = ((long long)B * 26 * 26 + ON_IN_WG_PIX - 1) / ON_IN_WG_PIX;
+    const long long ds_blocks = 148, in_blocks = 148 * 2;
     N4J_CUDA(cudaMalloc(&dspart_, sizeof(double) * ds_blocks * 4096)); allocs_.push_back(dspart_);
     N4J_CUDA(cudaMalloc(&inpart_, sizeof(double) * in_blocks * 640)); allocs_.push_back(inpart_);
 }
@@ -747,16 +747,26 @@ inline void OuterNet::forward_tc(const float* p, const float* images, const floa
     N4J_CUDA(cudaMemsetAsync(acc_pool_, 0, acc_pool_bytes_, s_));
     const long long r0 = (long long)B * 26 * 26;
     k_on_in_conv_fwd<<<grid_rows(r0), 256, 0, s_>>>(images, p + off_in_w_, p + off_in_b_, a0n_, B, 28, 28, tb_[0].acc1);
+    {
+        OnWeightJobs jobs{};
+        for (int r = 0; r < 2; ++r) {
+            const float* w1 = p + blk_[r].o_c1;
+            const float* w2 = p + blk_[r].o_c2;
+            jobs.w[4 * r] = w1; jobs.img[4 * r] = tb_[r].w1f; jobs.mode[4 * r] = 0;
+            jobs.w[4 * r + 1] = w1; jobs.img[4 * r + 1] = tb_[r].w1b; jobs.mode[4 * r + 1] = 1;
+            jobs.w[4 * r + 2] = w2; jobs.img[4 * r + 2] = tb_[r].w2f; jobs.mode[4 * r + 2] = 0;
+            jobs.w[4 * r + 3] = w2; jobs.img[4 * r + 3] = tb_[r].w2b; jobs.mode[4 * r + 3] = 1;
+        }
+        k_on_weights_to_tc<<<dim3(36, 8), 256, 0, s_>>>(jobs);
+    }
     const float* a = a0n_;
     for (int r = 0; r < 2; ++r) {
         TcBlock& t = tb_[r];
         const Block& b = blk_[r];
         const long long ri = (long long)B * b.Hin * b.Hin, ro = (long long)B * b.Hout * b.Hout;
-        k_conv_w_to_tc<<<72, 256, 0, s_>>>(p + b.o_c1, t.w1f, 0); k_conv_w_to_tc<<<72, 256, 0, s_>>>(p + b.o_c1, t.w1b, 1);
-        k_conv_w_to_tc<<<72, 256, 0, s_>>>(p + b.o_c2, t.w2f, 0); k_conv_w_to_tc<<<72, 256, 0, s_>>>(p + b.o_c2, t.w2b, 1);
         if (r > 0) k_on_bn_stats<<<grid_rows(ri), 256, 0, s_>>>(a, ri, t.acc1);        // (block 0: the input convolution accumulated them)
         k_on_bn_apply<<<grid(ri * 16), 256, 0, s_>>>(a, t.acc1, ri, 1e-5f, p + b.o_bn1, p + b.o_bn1 + C, t.n1, t.n1img, t.gi);
-        k_on_ds_fwd<<<(unsigned)((ro + 31) / 32), 256, 0, s_>>>(t.n1, p + b.o_ds, t.dsy, B, b.Hin, b.Hout);
+        k_on_ds_fwd<<<(unsigned)((ro + ON_DS_PIX - 1) / ON_DS_PIX), 256, 0, s_>>>(t.n1, p + b.o_ds, t.dsy, B, b.Hin, b.Hout);
         conv_tc(t.n1img, t.w1f, t.f1, t.gi, N4J_ACT_RELU, true, t.sub_off, b.Hout);                      // firstConvStem: stride 2, ReLU
         k_on_bn_stats<<<grid_rows(ro), 256, 0, s_>>>(t.f1, ro, t.acc2);
         k_on_bn_apply<<<grid(ro * 16), 256, 0, s_>>>(t.f1, t.acc2, ro, 1e-5f, p + b.o_bn2, p + b.o_bn2 + C, t.n2, t.n2img, t.go);
@@ -772,14 +782,14 @@ inline void OuterNet::forward_tc(const float* p, const float* images, const floa
     k_on_bn_stats<<<grid_rows(rz), 256, 0, s_>>>(z1n_, rz, acco_);
     k_on_bn_apply<<<grid(rz * 16), 256, 0, s_>>>(z1n_, acco_, rz, 1e-5f, p + off_bno_, p + off_bno_ + C, non_, (float*)nullptr, ConvGeom{});
     k_on_pool_fwd<<<(B * 64 + 255) / 256, 256, 0, s_>>>(non_, pool_, B, 49);
-    k_outer_output_fwd<<<(B + 255) / 256, 256, 0, s_>>>(pool_, p + off_ow_, p + off_ob_, labels, probs_, labels ? score_parts_ : nullptr, B, C);
+    k_on_output_fwd<<<(B * 32 + 255) / 256, 256, 0, s_>>>(pool_, p + off_ow_, p + off_ob_, labels, probs_, labels ? score_parts_ : nullptr, B);
     N4J_CUDA(cudaGetLastError());
 }
 
 inline void OuterNet::backward_tc(const float* images, n4j_stats* ode_bwd) {
     const int B = B_, C = 64;
     const long long rz = (long long)B * 49;
-    k_outer_output_bwd<<<1, 256, 0, s_>>>(pool_, p_ + off_ow_, probs_, lab_, score_parts_, g_ + off_ow_, g_ + off_ob_, dpool_, score_, B, C);
+    k_on_output_bwd<<<(704 + B * 64 + 255) / 256, 256, 0, s_>>>(pool_, p_ + off_ow_, probs_, lab_, score_parts_, g_ + off_ow_, g_ + off_ob_, dpool_, score_, B);
     k_on_pool_bwd<<<grid(rz * 64), 256, 0, s_>>>(dpool_, dA_, rz * 64, 49);
     k_on_bn_bwd_stats<<<grid_rows(rz), 256, 0, s_>>>(z1n_, non_, dA_, acco_, rz, 1e-5f);
     OnBnBwdOut oo{dB_, nullptr, ConvGeom{}, 7, 7, 1, 0, 0};
@@ -802,11 +812,11 @@ inline void OuterNet::backward_tc(const float* images, n4j_stats* ode_bwd) {
         k_on_bn_bwd_dx<<<grid(ro * 16), 256, 0, s_>>>(t.f1, t.n2, t.t1, t.acc2, ro, 1e-5f, p_ + b.o_bn2, g_ + b.o_bn2, 0.1f, o2);
         // firstConvStem and downSample both read n1
         wgrad_tc(t.n1, t.gup, t.wi, g_ + b.o_c1);
-        const int dsb = (int)((ro + ON_DS_WG_PIX - 1) / ON_DS_WG_PIX);
+        const int dsb = (int)std::min<long long>((ro + ON_DS_WG_PIX - 1) / ON_DS_WG_PIX, 148);
         k_on_ds_wgrad<<<dsb, 256, 0, s_>>>(t.n1, da, dspart_, B, b.Hin, b.Hout);
-        k_on_sum_parts<<<16, 256, 0, s_>>>(dspart_, g_ + b.o_ds, 4096, dsb, 4096);
+        k_on_sum_parts<<<128, 256, 0, s_>>>(dspart_, g_ + b.o_ds, 4096, dsb, 4096);
         conv_tc(t.gupimg, t.w1b, t.dn1, t.gi, N4J_ACT_IDENTITY, false, 0, 0);
-        k_on_ds_dgrad_add<<<(unsigned)((ro + 31) / 32), 256, 0, s_>>>(da, p_ + b.o_ds, t.dn1, B, b.Hin, b.Hout);
+        k_on_ds_dgrad_add<<<(unsigned)((ro + ON_DS_PIX - 1) / ON_DS_PIX), 256, 0, s_>>>(da, p_ + b.o_ds, t.dn1, B, b.Hin, b.Hout);
         // firstNorm backward -> epsilon at the block's input (and, for block 1, its operand image for block 0's secondConvStem dgrad)
         k_on_bn_bwd_stats<<<grid_rows(ri), 256, 0, s_>>>(a_in, t.n1, t.dn1, t.acc1, ri, 1e-5f);
         OnBnBwdOut o1{t.da_in, r == 1 ? tb_[0].daimg : nullptr, r == 1 ? tb_[0].go : ConvGeom{}, b.Hin, b.Hin, 1, 0, 0};
@@ -814,11 +824,11 @@ inline void OuterNet::backward_tc(const float* images, n4j_stats* ode_bwd) {
         da = t.da_in;
     }
     const long long r0 = (long long)B * 26 * 26;
-    const int inb = (int)((r0 + ON_IN_WG_PIX - 1) / ON_IN_WG_PIX);
+    const int inb = (int)std::min<long long>((r0 + 15) / 16, 148 * 2);
     k_on_in_conv_wgrad<<<inb, 256, 0, s_>>>(images, da, inpart_, B, 28, 28);
     // inpart: [co][tap] then [co] per block; the gradient view stores the bias first (bias-first convolution parameters)
-    k_on_sum_parts<<<3, 256, 0, s_>>>(inpart_, g_ + off_in_w_, 576, inb, 640);
-    k_on_sum_parts<<<1, 256, 0, s_>>>(inpart_ + 576, g_ + off_in_b_, 64, inb, 640);
+    k_on_sum_parts<<<18, 256, 0, s_>>>(inpart_, g_ + off_in_w_, 576, inb, 640);
+    k_on_sum_parts<<<2, 256, 0, s_>>>(inpart_ + 576, g_ + off_in_b_, 64, inb, 640);
     N4J_CUDA(cudaGetLastError());
 }
 

@@ -127,13 +127,14 @@ __global__ void __launch_bounds__(256) k_on_bn_apply(const float* __restrict__ x
 }
 
 // downSample: 1x1 convolution, stride 2, no bias: y[(b,oh,ow)][co] = (float)sum_ci x[(b,2oh,2ow)][ci] * w[co][ci]
-// block = 32 output pixels; thread = (pixel pair, 4 output channels)
+// block = 64 output pixels; thread = 4 pixels x 4 output channels (one 128-bit weight load and four broadcast activation loads per 16 products)
+constexpr int ON_DS_PIX = 64;
 __global__ void __launch_bounds__(256) k_on_ds_fwd(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int B, int Hi, int Ho) {
-    __shared__ float s_w[64][65];      // [ci][co]
-    __shared__ float s_x[32][64];
+    __shared__ __align__(16) float s_w[64][68];      // [ci][co]
+    __shared__ __align__(16) float s_x[ON_DS_PIX][64];
     for (int i = threadIdx.x; i < 4096; i += 256) s_w[i & 63][i >> 6] = w[i];      // w[co][ci]
-    const long long P = (long long)B * Ho * Ho, p0 = (long long)blockIdx.x * 32;
-    for (int i = threadIdx.x; i < 32 * 16; i += 256) {
+    const long long P = (long long)B * Ho * Ho, p0 = (long long)blockIdx.x * ON_DS_PIX;
+    for (int i = threadIdx.x; i < ON_DS_PIX * 16; i += 256) {
         const long long p = p0 + (i >> 4);
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p < P) {
@@ -143,78 +144,101 @@ __global__ void __launch_bounds__(256) k_on_ds_fwd(const float* __restrict__ x, 
         reinterpret_cast<float4*>(&s_x[i >> 4][0])[i & 15] = v;
     }
     __syncthreads();
-    const int c0 = (threadIdx.x & 15) * 4;
-    for (int r = threadIdx.x >> 4; r < 32; r += 16) {
-        if (p0 + r >= P) break;
-        double a[4] = {0, 0, 0, 0};
-        for (int ci = 0; ci < 64; ++ci) {
-            const double xv = (double)s_x[r][ci];
+    const int c0 = (threadIdx.x & 15) * 4, r0 = (threadIdx.x >> 4) * 4;
+    double a[4][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] += xv * (double)s_w[ci][c0 + k];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[i][k] = 0.0;
+    for (int ci = 0; ci < 64; ++ci) {
+        const float4 wv = *reinterpret_cast<const float4*>(&s_w[ci][c0]);
+        const double ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double xv = (double)s_x[r0 + i][ci];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[i][k] += xv * ws[k];
         }
-        reinterpret_cast<float4*>(y)[(p0 + r) * 16 + (threadIdx.x & 15)] = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (p0 + r0 + i < P)
+            reinterpret_cast<float4*>(y)[(p0 + r0 + i) * 16 + (threadIdx.x & 15)] = make_float4((float)a[i][0], (float)a[i][1], (float)a[i][2], (float)a[i][3]);
 }
 
 // dn1[(b,2oh,2ow)][ci] += (float)sum_co g[(b,oh,ow)][co] * w[co][ci]       (downSample's epsilon added onto firstConv's, in place)
 __global__ void __launch_bounds__(256) k_on_ds_dgrad_add(const float* __restrict__ g, const float* __restrict__ w, float* __restrict__ dx, int B, int Hi, int Ho) {
-    __shared__ float s_w[64][64];      // [co][ci]
-    __shared__ float s_g[32][64];
-    for (int i = threadIdx.x; i < 4096; i += 256) s_w[i >> 6][i & 63] = w[i];
-    const long long P = (long long)B * Ho * Ho, p0 = (long long)blockIdx.x * 32;
-    for (int i = threadIdx.x; i < 32 * 16; i += 256) {
+    __shared__ __align__(16) float s_w[64][64];      // [co][ci]
+    __shared__ __align__(16) float s_g[ON_DS_PIX][64];
+    for (int i = threadIdx.x; i < 1024; i += 256) reinterpret_cast<float4*>(&s_w[0][0])[i] = reinterpret_cast<const float4*>(w)[i];
+    const long long P = (long long)B * Ho * Ho, p0 = (long long)blockIdx.x * ON_DS_PIX;
+    for (int i = threadIdx.x; i < ON_DS_PIX * 16; i += 256) {
         const long long p = p0 + (i >> 4);
         reinterpret_cast<float4*>(&s_g[i >> 4][0])[i & 15] = p < P ? reinterpret_cast<const float4*>(g)[p * 16 + (i & 15)] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
-    const int c0 = (threadIdx.x & 15) * 4;
-    for (int r = threadIdx.x >> 4; r < 32; r += 16) {
-        const long long p = p0 + r;
-        if (p >= P) break;
-        double a[4] = {0, 0, 0, 0};
-        for (int co = 0; co < 64; ++co) {
-            const double gv = (double)s_g[r][co];
+    const int c0 = (threadIdx.x & 15) * 4, r0 = (threadIdx.x >> 4) * 4;
+    double a[4][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] += gv * (double)s_w[co][c0 + k];
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[i][k] = 0.0;
+    for (int co = 0; co < 64; ++co) {
+        const float4 wv = *reinterpret_cast<const float4*>(&s_w[co][c0]);
+        const double ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double gv = (double)s_g[r0 + i][co];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[i][k] += gv * ws[k];
         }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long p = p0 + r0 + i;
+        if (p >= P) break;
         const int ow = (int)(p % Ho), oh = (int)((p / Ho) % Ho), b = (int)(p / ((long long)Ho * Ho));
         float4* d = reinterpret_cast<float4*>(dx) + (((long long)b * Hi + 2 * oh) * Hi + 2 * ow) * 16 + (threadIdx.x & 15);
         const float4 u = *d;
-        *d = make_float4(__fadd_rn((float)a[0], u.x), __fadd_rn((float)a[1], u.y), __fadd_rn((float)a[2], u.z), __fadd_rn((float)a[3], u.w));
+        *d = make_float4(__fadd_rn((float)a[i][0], u.x), __fadd_rn((float)a[i][1], u.y), __fadd_rn((float)a[i][2], u.z), __fadd_rn((float)a[i][3], u.w));
     }
 }
 
-// downSample weight gradient: dw[co][ci] = sum_p x[(b,2oh,2ow)][ci] * g[p][co]; block = 64 pixels, thread = 4 ci x 4 co, double partials per block
+// downSample weight gradient: dw[co][ci] = sum_p x[(b,2oh,2ow)][ci] * g[p][co]; a block walks 64-pixel slices (grid stride), thread = 4 ci x 4 co,
+// one double partial [co][ci] per block
 constexpr int ON_DS_WG_PIX = 64;
 __global__ void __launch_bounds__(256) k_on_ds_wgrad(const float* __restrict__ x, const float* __restrict__ g, double* __restrict__ part, int B, int Hi, int Ho) {
-    __shared__ float s_x[ON_DS_WG_PIX][64], s_g[ON_DS_WG_PIX][64];
-    const long long P = (long long)B * Ho * Ho, p0 = (long long)blockIdx.x * ON_DS_WG_PIX;
-    for (int i = threadIdx.x; i < ON_DS_WG_PIX * 16; i += 256) {
-        const long long p = p0 + (i >> 4);
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
-        if (p < P) {
-            const int ow = (int)(p % Ho), oh = (int)((p / Ho) % Ho), b = (int)(p / ((long long)Ho * Ho));
-            xv = reinterpret_cast<const float4*>(x)[(((long long)b * Hi + 2 * oh) * Hi + 2 * ow) * 16 + (i & 15)];
-            gv = reinterpret_cast<const float4*>(g)[p * 16 + (i & 15)];
-        }
-        reinterpret_cast<float4*>(&s_x[i >> 4][0])[i & 15] = xv;
-        reinterpret_cast<float4*>(&s_g[i >> 4][0])[i & 15] = gv;
-    }
-    __syncthreads();
+    __shared__ __align__(16) float s_x[ON_DS_WG_PIX][64], s_g[ON_DS_WG_PIX][64];
+    const long long P = (long long)B * Ho * Ho;
     const int ci0 = (threadIdx.x >> 4) * 4, co0 = (threadIdx.x & 15) * 4;
     double a[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) a[i][j] = 0.0;
-    for (int r = 0; r < ON_DS_WG_PIX; ++r) {
-        const float4 xv = *reinterpret_cast<const float4*>(&s_x[r][ci0]);
-        const float4 gv = *reinterpret_cast<const float4*>(&s_g[r][co0]);
-        const double xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+    for (long long p0 = (long long)blockIdx.x * ON_DS_WG_PIX; p0 < P; p0 += (long long)gridDim.x * ON_DS_WG_PIX) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < ON_DS_WG_PIX * 16; i += 256) {
+            const long long p = p0 + (i >> 4);
+            float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), gv = xv;
+            if (p < P) {
+                const int ow = (int)(p % Ho), oh = (int)((p / Ho) % Ho), b = (int)(p / ((long long)Ho * Ho));
+                xv = reinterpret_cast<const float4*>(x)[(((long long)b * Hi + 2 * oh) * Hi + 2 * ow) * 16 + (i & 15)];
+                gv = reinterpret_cast<const float4*>(g)[p * 16 + (i & 15)];
+            }
+            reinterpret_cast<float4*>(&s_x[i >> 4][0])[i & 15] = xv;
+            reinterpret_cast<float4*>(&s_g[i >> 4][0])[i & 15] = gv;
+        }
+        __syncthreads();
+        for (int r = 0; r < ON_DS_WG_PIX; ++r) {
+            const float4 xv = *reinterpret_cast<const float4*>(&s_x[r][ci0]);
+            const float4 gv = *reinterpret_cast<const float4*>(&s_g[r][co0]);
+            const double xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) a[i][j] += xs[i] * gs[j];
+                for (int j = 0; j < 4; ++j) a[i][j] += xs[i] * gs[j];
+        }
     }
     double* o = part + (long long)blockIdx.x * 4096;
 #pragma unroll
@@ -222,30 +246,36 @@ __global__ void __launch_bounds__(256) k_on_ds_wgrad(const float* __restrict__ x
 #pragma unroll
         for (int i = 0; i < 4; ++i) o[(co0 + j) * 64 + ci0 + i] = a[i][j];      // [co][ci], DL4J's order
 }
-// dst[i] = (float) sum_q part[q][i] in block order (deterministic)
+// dst[i] = (float) sum_q part[q * stride + i]: eight lanes per output stride over the partials, combined in lane order (deterministic)
 __global__ void __launch_bounds__(256) k_on_sum_parts(const double* __restrict__ part, float* __restrict__ dst, int n, int nparts, int stride) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    __shared__ double s_p[8][32];
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31), ql = threadIdx.x >> 5;
     double s = 0.0;
-    for (int q = 0; q < nparts; ++q) s += part[(long long)q * stride + i];
-    dst[i] = (float)s;
+    if (i < n)
+        for (int q = ql; q < nparts; q += 8) s += part[(long long)q * stride + i];
+    s_p[ql][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (ql == 0 && i < n) {
+        double t = s_p[0][threadIdx.x];
+#pragma unroll
+        for (int k = 1; k < 8; ++k) t += s_p[k][threadIdx.x];
+        dst[i] = (float)t;
+    }
 }
 
-// inputConv weight / bias gradient: dw[co][t] = sum x[b,oh+kh,ow+kw] * g[(b,oh,ow)][co], db[co] = sum g.  block = 256 pixels, partial [640] doubles per block
-constexpr int ON_IN_WG_PIX = 256;
+// inputConv weight / bias gradient: dw[co][t] = sum x[b,oh+kh,ow+kw] * g[(b,oh,ow)][co], db[co] = sum g.  A block walks pixels with a grid
+// stride (thread = 4-channel chunk x 16 pixel lanes), one partial of 640 doubles per block: dw [co][tap], then db [co]
 __global__ void __launch_bounds__(256) k_on_in_conv_wgrad(const float* __restrict__ x, const float* __restrict__ g, double* __restrict__ part, int B, int H, int W) {
     __shared__ double s_red[16][64];
     const int Ho = H - 2, Wo = W - 2;
-    const long long n = (long long)B * Ho * Wo, p0 = (long long)blockIdx.x * ON_IN_WG_PIX;
+    const long long n = (long long)B * Ho * Wo;
     const int chunk = threadIdx.x & 15, c0 = chunk * 4, sub = threadIdx.x >> 4;
     double a[10][4];
 #pragma unroll
     for (int t = 0; t < 10; ++t)
 #pragma unroll
         for (int k = 0; k < 4; ++k) a[t][k] = 0.0;
-    for (int r = sub; r < ON_IN_WG_PIX; r += 16) {
-        const long long p = p0 + r;
-        if (p >= n) break;
+    for (long long p = (long long)blockIdx.x * 16 + sub; p < n; p += (long long)gridDim.x * 16) {
         const int ow = (int)(p % Wo), oh = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
         const float4 gv = reinterpret_cast<const float4*>(g)[p * 16 + chunk];
         const double gs[4] = {gv.x, gv.y, gv.z, gv.w};
@@ -266,9 +296,9 @@ __global__ void __launch_bounds__(256) k_on_in_conv_wgrad(const float* __restric
         for (int k = 0; k < 4; ++k) s_red[sub][c0 + k] = a[t][k];
         __syncthreads();
         if (threadIdx.x < 64) {
-            double s = 0.0;
-            for (int r = 0; r < 16; ++r) s += s_red[r][threadIdx.x];
-            o[t < 9 ? threadIdx.x * 9 + t : 576 + threadIdx.x] = s;       // dw [co][tap] then db [co]
+            double sm = 0.0;
+            for (int r = 0; r < 16; ++r) sm += s_red[r][threadIdx.x];
+            o[t < 9 ? threadIdx.x * 9 + t : 576 + threadIdx.x] = sm;       // dw [co][tap] then db [co]
         }
         __syncthreads();
     }
@@ -286,6 +316,85 @@ __global__ void __launch_bounds__(256) k_on_pool_fwd(const float* __restrict__ x
 __global__ void __launch_bounds__(256) k_on_pool_bwd(const float* __restrict__ dp, float* __restrict__ dx, long long n, int HW) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dx[i] = __fdiv_rn(dp[(i / (64LL * HW)) * 64 + (i & 63)], (float)HW);
+}
+
+// OutputLayer forward: one warp per example.  logits = pool W + b (W [C,10] f-order), softmax, LossMCXENT term of the example
+__global__ void __launch_bounds__(256) k_on_output_fwd(const float* __restrict__ pool, const float* __restrict__ W, const float* __restrict__ bias,
+                                                        const float* __restrict__ labels, float* __restrict__ probs, double* __restrict__ score_parts, int B) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
+    const double p0 = (double)pool[b * 64 + lane], p1 = (double)pool[b * 64 + 32 + lane];
+    float lg[10];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const double acc = warp_sum(p0 * (double)W[lane + 64 * j] + p1 * (double)W[32 + lane + 64 * j]);
+        lg[j] = __fadd_rn((float)acc, bias[j]);
+        mx = fmaxf(mx, lg[j]);
+    }
+    if (lane != 0) return;
+    double se = 0.0;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) { lg[j] = expf(__fsub_rn(lg[j], mx)); se += (double)lg[j]; }
+    const float den = (float)se;
+    double sc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+        const float p = __fdiv_rn(lg[j], den);
+        probs[b * 10 + j] = p;
+        if (labels) {
+            double pc = (double)p;
+            pc = pc < 1e-10 ? 1e-10 : (pc > 1.0 - 1e-10 ? 1.0 - 1e-10 : pc);
+            sc -= (double)labels[b * 10 + j] * log(pc);
+        }
+    }
+    if (score_parts) score_parts[b] = sc;
+}
+// OutputLayer backward, one thread per result: dW[c + 64 j], db[j], dpool[b][c], and the score
+__global__ void __launch_bounds__(256) k_on_output_bwd(const float* __restrict__ pool, const float* __restrict__ W, const float* __restrict__ probs,
+                                                        const float* __restrict__ labels, const double* __restrict__ score_parts, float* __restrict__ dW,
+                                                        float* __restrict__ db, float* __restrict__ dpool, float* __restrict__ score, int B) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 640) {
+        const int c = i & 63, j = i >> 6;
+        double acc = 0.0;
+        for (int b = 0; b < B; ++b) acc += (double)pool[b * 64 + c] * (double)__fsub_rn(probs[b * 10 + j], labels[b * 10 + j]);
+        dW[i] = (float)acc;
+    } else if (i < 650) {
+        const int j = i - 640;
+        double acc = 0.0;
+        for (int b = 0; b < B; ++b) acc += (double)__fsub_rn(probs[b * 10 + j], labels[b * 10 + j]);
+        db[j] = (float)acc;
+    } else if (i == 650) {
+        double sm = 0.0;
+        for (int b = 0; b < B; ++b) sm += score_parts[b];
+        *score = (float)(sm / (double)B);
+    } else if (i >= 704 && i < 704 + B * 64) {
+        const int k = i - 704, b = k >> 6, c = k & 63;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 10; ++j) acc += (double)__fsub_rn(probs[b * 10 + j], labels[b * 10 + j]) * (double)W[c + 64 * j];
+        dpool[k] = (float)acc;
+    }
+}
+
+// the hi/lo weight images of several convolutions in one launch: blockIdx.y selects (weights, image, mode)
+struct OnWeightJobs { const float* w[8]; float* img[8]; int mode[8]; };
+__global__ void __launch_bounds__(256) k_on_weights_to_tc(OnWeightJobs jobs) {
+    const float* __restrict__ w = jobs.w[blockIdx.y];
+    float* __restrict__ wimg = jobs.img[blockIdx.y];
+    const int mode = jobs.mode[blockIdx.y];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 64 * 64 * 9; i += gridDim.x * blockDim.x) {
+        const int tap = i % 9; const int r = i / 9; const int ci = r % 64; const int co = r / 64;
+        float hi, lo;
+        tc::split_tf32(w[i], hi, lo);
+        const int t2 = mode == 0 ? tap : 8 - tap;
+        const int n = mode == 0 ? co : ci;
+        const int k = mode == 0 ? ci : co;
+        const long long base = (long long)t2 * 8192 + ((k >> 2) * 128 + n) * 4 + (k & 3);
+        wimg[base] = hi;
+        wimg[base + 64 * 4] = lo;
+    }
 }
 
 // BatchNorm backward statistics: dy = y > 0 ? g : 0;  acc[128 + c] += sum dy, acc[192 + c] += sum dy * xhat
