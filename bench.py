@@ -540,7 +540,7 @@ def _full_train_step(args):
         labels = np.eye(10, dtype=np.float32)[rng.integers(0, 10, BATCH)]
         scores = [model.fit(images, labels, lr=0.01) for _ in range(2)]
         t0 = time.perf_counter()
-        k = 5
+        k = 10
         for _ in range(k):
             scores.append(model.fit(images, labels, lr=0.01))
         ms = (time.perf_counter() - t0) / k * 1e3
@@ -550,7 +550,22 @@ def _full_train_step(args):
                "value": BATCH / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "steps": k, "scores": [float(x) for x in scores],
                "ode_block": {"fwd": [int(fs.nfe), int(fs.accepted), int(fs.rejected)], "bwd": [int(bs.nfe), int(bs.accepted), int(bs.rejected)],
                              "gpu_ms": float(fs.gpu_ms + bs.gpu_ms)},
-               "note": "the layers around the block are plain direct kernels with double accumulation (not the hot path, DESIGN.md section 10)"}
+               "note": "default mode: the layers around the block run NHWC with their 64->64 convolutions (stride 1 and 2; forward, dgrad, wgrad) on the same tcgen05 "
+                       "kernels as the block (outer_net_tc.cuh, DESIGN.md section 10)"}
+        # A/B: the same step with the stem on the exact-accumulation CUDA-core kernels (what r02's first build and the parity mode run)
+        os.environ["N4J_NET_NO_TC"] = "1"
+        try:
+            ref = OdeNetModel(batch=BATCH, nrofKernels=64, flags=args.flags)
+        finally:
+            os.environ.pop("N4J_NET_NO_TC", None)
+        ref.setParams(p)
+        for _ in range(2):
+            ref.fit(images, labels, lr=0.01)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ref.fit(images, labels, lr=0.01)
+        out["cuda_core_stem_ms_per_step"] = (time.perf_counter() - t0) / 3 * 1e3
+        ref.close()
         model.close()
         return out
     except Exception as e:      # an extra: never fail the bench line over it

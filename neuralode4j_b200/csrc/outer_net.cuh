@@ -442,7 +442,7 @@ private:
     void set_tc_attributes();
     void conv_tc(const float* img, const float* wimg, float* out, const ConvGeom& g, int act, bool sub, int sub_off, int Ho);
     void wgrad_tc(const float* x, const float* g, const WgradTcGeom& wg, float* dw_flat);
-    void forward_tc(const float* p, const float* images, const float* labels, n4j_stats* ode_fwd);
+    void forward_tc(const float* p, const float* images, const float* labels, bool train, n4j_stats* ode_fwd);
     void backward_tc(const float* images, n4j_stats* ode_bwd);
     int grid_rows(long long rows) const { return (int)std::max<long long>(1, std::min<long long>((rows + 15) / 16, 148LL * 4)); }
 };
@@ -587,8 +587,8 @@ inline void OuterNet::output(const float* params, const float* images, float* pr
     N4J_CUDA(cudaSetDevice(device_));
     N4J_CUDA(cudaMemcpyAsync(p_, params, sizeof(float) * n_, cudaMemcpyDefault, s_));
     N4J_CUDA(cudaMemcpyAsync(img_, images, sizeof(float) * B_ * 28 * 28, cudaMemcpyDefault, s_));
-    ode_->set_nhwc_io(false);
-    forward(p_, img_, nullptr, train != 0, nullptr);
+    if (tc_) forward_tc(p_, img_, nullptr, train != 0, nullptr);
+    else { ode_->set_nhwc_io(false); forward(p_, img_, nullptr, train != 0, nullptr); }
     N4J_CUDA(cudaMemcpyAsync(probs, probs_, sizeof(float) * B_ * 10, cudaMemcpyDefault, s_));
     N4J_CUDA(cudaStreamSynchronize(s_));
 }
@@ -614,7 +614,7 @@ inline void OuterNet::train_step(float* params, float* updater_state, const floa
     N4J_CUDA(cudaMemsetAsync(g_, 0, sizeof(float) * n_, s_));          // ZeroGrad (util/listen/training/ZeroGrad.java:14-16): the theta-adjoint is seeded from the view
     phase("copies in");
     if (tc_) {
-        forward_tc(p_, img_, lab_, ode_fwd);
+        forward_tc(p_, img_, lab_, true, ode_fwd);
         phase("forward (stem, block, output)");
         backward_tc(img_, ode_bwd);
         phase("backward");
@@ -741,12 +741,12 @@ inline void OuterNet::wgrad_tc(const float* x, const float* g, const WgradTcGeom
     k_on_wgrad_sum2<<<144, 256, 0, s_>>>(wmid_, dw_flat, nq);
 }
 
-inline void OuterNet::forward_tc(const float* p, const float* images, const float* labels, n4j_stats* ode_fwd) {
+inline void OuterNet::forward_tc(const float* p, const float* images, const float* labels, bool train, n4j_stats* ode_fwd) {
     const int B = B_, C = 64;
     set_tc_attributes();
     N4J_CUDA(cudaMemsetAsync(acc_pool_, 0, acc_pool_bytes_, s_));
     const long long r0 = (long long)B * 26 * 26;
-    k_on_in_conv_fwd<<<grid_rows(r0), 256, 0, s_>>>(images, p + off_in_w_, p + off_in_b_, a0n_, B, 28, 28, tb_[0].acc1);
+    k_on_in_conv_fwd<<<grid_rows(r0), 256, 0, s_>>>(images, p + off_in_w_, p + off_in_b_, a0n_, B, 28, 28, train ? tb_[0].acc1 : (double*)nullptr);
     {
         OnWeightJobs jobs{};
         for (int r = 0; r < 2; ++r) {
@@ -764,12 +764,12 @@ inline void OuterNet::forward_tc(const float* p, const float* images, const floa
         TcBlock& t = tb_[r];
         const Block& b = blk_[r];
         const long long ri = (long long)B * b.Hin * b.Hin, ro = (long long)B * b.Hout * b.Hout;
-        if (r > 0) k_on_bn_stats<<<grid_rows(ri), 256, 0, s_>>>(a, ri, t.acc1);        // (block 0: the input convolution accumulated them)
-        k_on_bn_apply<<<grid(ri * 16), 256, 0, s_>>>(a, t.acc1, ri, 1e-5f, p + b.o_bn1, p + b.o_bn1 + C, t.n1, t.n1img, t.gi);
+        if (r > 0 && train) k_on_bn_stats<<<grid_rows(ri), 256, 0, s_>>>(a, ri, t.acc1);        // (block 0: the input convolution accumulated them)
+        k_on_bn_apply<<<grid(ri * 16), 256, 0, s_>>>(a, t.acc1, ri, 1e-5f, p + b.o_bn1, p + b.o_bn1 + C, train ? nullptr : p + b.o_bn1 + 2 * C, t.n1, t.n1img, t.gi);
         k_on_ds_fwd<<<(unsigned)((ro + ON_DS_PIX - 1) / ON_DS_PIX), 256, 0, s_>>>(t.n1, p + b.o_ds, t.dsy, B, b.Hin, b.Hout);
         conv_tc(t.n1img, t.w1f, t.f1, t.gi, N4J_ACT_RELU, true, t.sub_off, b.Hout);                      // firstConvStem: stride 2, ReLU
-        k_on_bn_stats<<<grid_rows(ro), 256, 0, s_>>>(t.f1, ro, t.acc2);
-        k_on_bn_apply<<<grid(ro * 16), 256, 0, s_>>>(t.f1, t.acc2, ro, 1e-5f, p + b.o_bn2, p + b.o_bn2 + C, t.n2, t.n2img, t.go);
+        if (train) k_on_bn_stats<<<grid_rows(ro), 256, 0, s_>>>(t.f1, ro, t.acc2);
+        k_on_bn_apply<<<grid(ro * 16), 256, 0, s_>>>(t.f1, t.acc2, ro, 1e-5f, p + b.o_bn2, p + b.o_bn2 + C, train ? nullptr : p + b.o_bn2 + 2 * C, t.n2, t.n2img, t.go);
         conv_tc(t.n2img, t.w2f, t.f2, t.go, N4J_ACT_IDENTITY, false, 0, 0);                              // secondConvStem
         k_outer_add<<<grid(ro * 64), 256, 0, s_>>>(t.dsy, t.f2, t.a_out, ro * 64);                       // stemAdd_r
         a = t.a_out;
@@ -779,8 +779,8 @@ inline void OuterNet::forward_tc(const float* p, const float* images, const floa
     ode_->bind_params(p + off_ode_, n_ode_);
     ode_->forward(a, time_, 2, 0, z1n_, ode_fwd);
     const long long rz = (long long)B * 49;
-    k_on_bn_stats<<<grid_rows(rz), 256, 0, s_>>>(z1n_, rz, acco_);
-    k_on_bn_apply<<<grid(rz * 16), 256, 0, s_>>>(z1n_, acco_, rz, 1e-5f, p + off_bno_, p + off_bno_ + C, non_, (float*)nullptr, ConvGeom{});
+    if (train) k_on_bn_stats<<<grid_rows(rz), 256, 0, s_>>>(z1n_, rz, acco_);
+    k_on_bn_apply<<<grid(rz * 16), 256, 0, s_>>>(z1n_, acco_, rz, 1e-5f, p + off_bno_, p + off_bno_ + C, train ? nullptr : p + off_bno_ + 2 * C, non_, (float*)nullptr, ConvGeom{});
     k_on_pool_fwd<<<(B * 64 + 255) / 256, 256, 0, s_>>>(non_, pool_, B, 49);
     k_on_output_fwd<<<(B * 32 + 255) / 256, 256, 0, s_>>>(pool_, p + off_ow_, p + off_ob_, labels, probs_, labels ? score_parts_ : nullptr, B);
     N4J_CUDA(cudaGetLastError());

@@ -98,14 +98,20 @@ __global__ void __launch_bounds__(256) k_on_bn_stats(const float* __restrict__ x
     }
 }
 
-// y = relu(gamma * ((x - mean) * invstd) + beta): compact NHWC and (img != null) the zero-padded hi/lo operand image of the convolution behind
+// y = relu(gamma * ((x - mean) * invstd) + beta): compact NHWC and (img != null) the zero-padded hi/lo operand image of the convolution behind.
+// run == null: batch statistics from the raw sums in acc (training); else the layer's running mean / var (inference, ComputationGraph.output)
 __global__ void __launch_bounds__(256) k_on_bn_apply(const float* __restrict__ x, const double* __restrict__ acc, long long M, float eps,
-                                                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ y,
-                                                      float* __restrict__ img, ConvGeom g) {
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ run,
+                                                      float* __restrict__ y, float* __restrict__ img, ConvGeom g) {
     __shared__ float s_m[64], s_i[64], s_g[64], s_b[64];
     if (threadIdx.x < 64) {
-        float var;
-        on_bn_final(acc, M, eps, threadIdx.x, s_m[threadIdx.x], s_i[threadIdx.x], var);
+        if (run) {
+            s_m[threadIdx.x] = run[threadIdx.x];
+            s_i[threadIdx.x] = (float)(1.0 / sqrt((double)run[64 + threadIdx.x] + (double)eps));
+        } else {
+            float var;
+            on_bn_final(acc, M, eps, threadIdx.x, s_m[threadIdx.x], s_i[threadIdx.x], var);
+        }
         s_g[threadIdx.x] = gamma[threadIdx.x]; s_b[threadIdx.x] = beta[threadIdx.x];
     }
     __syncthreads();

@@ -251,6 +251,34 @@ def test_train_step_default_mode_matches_oracle_within_block_sensitivity():
 
 
 @pytest.mark.gpu
+def test_fast_path_output_matches_exact_path():
+    """ComputationGraph.output through the fast path (running statistics in the outer BatchNorm layers, and batch statistics) against the
+    exact-accumulation CUDA-core path of the same model: probabilities within 1e-5."""
+    import os
+    C, B = 64, 16
+    fast, orc, p, rng = _model_and_oracle(C, B, 0)
+    os.environ["N4J_NET_NO_TC"] = "1"
+    try:
+        from neuralode4j_b200.net import OdeNetModel
+        slow = OdeNetModel(batch=B, nrofKernels=C, flags=0)
+    finally:
+        os.environ.pop("N4J_NET_NO_TC", None)
+    try:
+        for nm in orc.layout.bn_names():          # running statistics that differ from the batch's
+            o, _ = orc.layout.slices[nm]
+            p[o + 2 * C:o + 3 * C] = 0.1 * rng.standard_normal(C)
+            p[o + 3 * C:o + 4 * C] = 1.0 + 0.2 * rng.random(C)
+        images = rng.standard_normal((B, 1, 28, 28)).astype(np.float32)
+        fast.setParams(p); slow.setParams(p)
+        for train in (False, True):
+            a, b = fast.output(images, train=train), slow.output(images, train=train)
+            assert np.allclose(a.sum(axis=1), 1.0, atol=1e-5)
+            np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
+    finally:
+        fast.close(); slow.close()
+
+
+@pytest.mark.gpu
 def test_training_reduces_the_loss_and_inference_uses_running_statistics():
     """A few steps of fit() on one fixed minibatch (default mode, 64 channels, batch 32): the score goes down, parameters stay finite,
     and output(train=False) (running statistics in the outer BatchNorm layers) differs from output(train=True) but is a distribution."""
