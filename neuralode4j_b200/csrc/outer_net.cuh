@@ -438,10 +438,17 @@ private:
     float *wpart_tc_ = nullptr, *wmid_ = nullptr;
     size_t conv_smem_max_ = 0, wgrad_smem_max_ = 0;
     static constexpr int WMID = 32;
+    // side branch: the weight gradients (and downSample's forward) are off the chain of dependent kernels — they run on a second stream
+    // beside the dgrad / BatchNorm chain, like the block's own weight gradients (engine.cu: side_)
+    cudaStream_t s2_ = nullptr;
+    cudaEvent_t ev_fork_[8] = {}, ev_join_ = nullptr, ev_ds_[2] = {};
+    int fork_n_ = 0;
+    void fork_side();      // side branch continues from here (everything enqueued on s_ so far is visible to it)
+    void join_side();
     void init_tc();
     void set_tc_attributes();
     void conv_tc(const float* img, const float* wimg, float* out, const ConvGeom& g, int act, bool sub, int sub_off, int Ho);
-    void wgrad_tc(const float* x, const float* g, const WgradTcGeom& wg, float* dw_flat);
+    void wgrad_tc(cudaStream_t st, const float* x, const float* g, const WgradTcGeom& wg, float* dw_flat);
     void forward_tc(const float* p, const float* images, const float* labels, bool train, n4j_stats* ode_fwd);
     void backward_tc(const float* images, n4j_stats* ode_bwd);
     int grid_rows(long long rows) const { return (int)std::max<long long>(1, std::min<long long>((rows + 15) / 16, 148LL * 4)); }
@@ -550,6 +557,12 @@ inline OuterNet::OuterNet(int batch, int channels, const n4j_solver_cfg& cfg, fl
 
 inline OuterNet::~OuterNet() {
     cudaSetDevice(device_);
+    if (s2_) {
+        cudaStreamSynchronize(s2_); cudaStreamDestroy(s2_);
+        for (auto& e : ev_fork_) cudaEventDestroy(e);
+        for (auto& e : ev_ds_) cudaEventDestroy(e);
+        cudaEventDestroy(ev_join_);
+    }
     for (void* p : allocs_) cudaFree(p);
 }
 
@@ -705,6 +718,19 @@ inline void OuterNet::init_tc() {
     const long long ds_blocks = 148, in_blocks = 148 * 2;
     N4J_CUDA(cudaMalloc(&dspart_, sizeof(double) * ds_blocks * 4096)); allocs_.push_back(dspart_);
     N4J_CUDA(cudaMalloc(&inpart_, sizeof(double) * in_blocks * 640)); allocs_.push_back(inpart_);
+    N4J_CUDA(cudaStreamCreateWithFlags(&s2_, cudaStreamNonBlocking));
+    for (auto& e : ev_fork_) N4J_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ev_ds_) N4J_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    N4J_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+}
+inline void OuterNet::fork_side() {
+    cudaEvent_t e = ev_fork_[fork_n_++ & 7];
+    N4J_CUDA(cudaEventRecord(e, s_));
+    N4J_CUDA(cudaStreamWaitEvent(s2_, e, 0));
+}
+inline void OuterNet::join_side() {
+    N4J_CUDA(cudaEventRecord(ev_join_, s2_));
+    N4J_CUDA(cudaStreamWaitEvent(s_, ev_join_, 0));
 }
 
 // The dynamic shared-memory limits are per-function attributes shared with every Engine of the process (whose own maps are smaller):
@@ -733,12 +759,12 @@ inline void OuterNet::conv_tc(const float* img, const float* wimg, float* out, c
 }
 
 // dw_flat: DL4J's [co][ci][3][3] slot of the gradient view
-inline void OuterNet::wgrad_tc(const float* x, const float* g, const WgradTcGeom& wg, float* dw_flat) {
-    k_conv_wgrad_tc<<<dim3(wg.tiles), WGRAD_TC_THREADS, conv_wgrad_tc_smem_bytes(wg), s_>>>(fixed_ref(const_cast<float*>(x)), fixed_ref(const_cast<float*>(g)), wg,
+inline void OuterNet::wgrad_tc(cudaStream_t st, const float* x, const float* g, const WgradTcGeom& wg, float* dw_flat) {
+    k_conv_wgrad_tc<<<dim3(wg.tiles), WGRAD_TC_THREADS, conv_wgrad_tc_smem_bytes(wg), st>>>(fixed_ref(const_cast<float*>(x)), fixed_ref(const_cast<float*>(g)), wg,
                                                                                              wpart_tc_, (long long*)nullptr);
     const int per = (wg.tiles + WMID - 1) / WMID, nq = (wg.tiles + per - 1) / per;
-    k_on_wgrad_sum1<<<dim3(36, nq), 256, 0, s_>>>(wpart_tc_, wmid_, wg.tiles, per);
-    k_on_wgrad_sum2<<<144, 256, 0, s_>>>(wmid_, dw_flat, nq);
+    k_on_wgrad_sum1<<<dim3(36, nq), 256, 0, st>>>(wpart_tc_, wmid_, wg.tiles, per);
+    k_on_wgrad_sum2<<<144, 256, 0, st>>>(wmid_, dw_flat, nq);
 }
 
 inline void OuterNet::forward_tc(const float* p, const float* images, const float* labels, bool train, n4j_stats* ode_fwd) {
@@ -766,11 +792,14 @@ inline void OuterNet::forward_tc(const float* p, const float* images, const floa
         const long long ri = (long long)B * b.Hin * b.Hin, ro = (long long)B * b.Hout * b.Hout;
         if (r > 0 && train) k_on_bn_stats<<<grid_rows(ri), 256, 0, s_>>>(a, ri, t.acc1);        // (block 0: the input convolution accumulated them)
         k_on_bn_apply<<<grid(ri * 16), 256, 0, s_>>>(a, t.acc1, ri, 1e-5f, p + b.o_bn1, p + b.o_bn1 + C, train ? nullptr : p + b.o_bn1 + 2 * C, t.n1, t.n1img, t.gi);
-        k_on_ds_fwd<<<(unsigned)((ro + ON_DS_PIX - 1) / ON_DS_PIX), 256, 0, s_>>>(t.n1, p + b.o_ds, t.dsy, B, b.Hin, b.Hout);
+        fork_side();                                                                                     // downSample beside firstConvStem
+        k_on_ds_fwd<<<(unsigned)((ro + ON_DS_PIX - 1) / ON_DS_PIX), 256, 0, s2_>>>(t.n1, p + b.o_ds, t.dsy, B, b.Hin, b.Hout);
+        N4J_CUDA(cudaEventRecord(ev_ds_[r], s2_));
         conv_tc(t.n1img, t.w1f, t.f1, t.gi, N4J_ACT_RELU, true, t.sub_off, b.Hout);                      // firstConvStem: stride 2, ReLU
         if (train) k_on_bn_stats<<<grid_rows(ro), 256, 0, s_>>>(t.f1, ro, t.acc2);
         k_on_bn_apply<<<grid(ro * 16), 256, 0, s_>>>(t.f1, t.acc2, ro, 1e-5f, p + b.o_bn2, p + b.o_bn2 + C, train ? nullptr : p + b.o_bn2 + 2 * C, t.n2, t.n2img, t.go);
         conv_tc(t.n2img, t.w2f, t.f2, t.go, N4J_ACT_IDENTITY, false, 0, 0);                              // secondConvStem
+        N4J_CUDA(cudaStreamWaitEvent(s_, ev_ds_[r], 0));
         k_outer_add<<<grid(ro * 64), 256, 0, s_>>>(t.dsy, t.f2, t.a_out, ro * 64);                       // stemAdd_r
         a = t.a_out;
     }
@@ -803,18 +832,20 @@ inline void OuterNet::backward_tc(const float* images, n4j_stats* ode_bwd) {
         const Block& b = blk_[r];
         const float* a_in = r == 0 ? a0n_ : tb_[0].a_out;
         const long long ri = (long long)B * b.Hin * b.Hin, ro = (long long)B * b.Hout * b.Hout;
-        // secondConvStem: weight gradient, epsilon of secondNorm's output
-        wgrad_tc(t.n2, da, t.wo, g_ + b.o_c2);
+        // secondConvStem: weight gradient (side branch, with downSample's: both only need the block's output epsilon), epsilon of secondNorm's output
+        fork_side();
+        wgrad_tc(s2_, t.n2, da, t.wo, g_ + b.o_c2);
+        const int dsb = (int)std::min<long long>((ro + ON_DS_WG_PIX - 1) / ON_DS_WG_PIX, 148);
+        k_on_ds_wgrad<<<dsb, 256, 0, s2_>>>(t.n1, da, dspart_, B, b.Hin, b.Hout);
+        k_on_sum_parts<<<128, 256, 0, s2_>>>(dspart_, g_ + b.o_ds, 4096, dsb, 4096);
         conv_tc(t.daimg, t.w2b, t.t1, t.go, N4J_ACT_IDENTITY, false, 0, 0);
         // secondNorm backward; its dx, masked by firstConvStem's ReLU, scattered to the sampled pixels of the full-resolution map
         k_on_bn_bwd_stats<<<grid_rows(ro), 256, 0, s_>>>(t.f1, t.n2, t.t1, t.acc2, ro, 1e-5f);
         OnBnBwdOut o2{t.gup, t.gupimg, t.gi, b.Hout, b.Hin, 2, t.sub_off, 1};
         k_on_bn_bwd_dx<<<grid(ro * 16), 256, 0, s_>>>(t.f1, t.n2, t.t1, t.acc2, ro, 1e-5f, p_ + b.o_bn2, g_ + b.o_bn2, 0.1f, o2);
-        // firstConvStem and downSample both read n1
-        wgrad_tc(t.n1, t.gup, t.wi, g_ + b.o_c1);
-        const int dsb = (int)std::min<long long>((ro + ON_DS_WG_PIX - 1) / ON_DS_WG_PIX, 148);
-        k_on_ds_wgrad<<<dsb, 256, 0, s_>>>(t.n1, da, dspart_, B, b.Hin, b.Hout);
-        k_on_sum_parts<<<128, 256, 0, s_>>>(dspart_, g_ + b.o_ds, 4096, dsb, 4096);
+        // firstConvStem: weight gradient on the side branch, epsilon of n1 on the chain (downSample's epsilon is added onto it)
+        fork_side();
+        wgrad_tc(s2_, t.n1, t.gup, t.wi, g_ + b.o_c1);
         conv_tc(t.gupimg, t.w1b, t.dn1, t.gi, N4J_ACT_IDENTITY, false, 0, 0);
         k_on_ds_dgrad_add<<<(unsigned)((ro + ON_DS_PIX - 1) / ON_DS_PIX), 256, 0, s_>>>(da, p_ + b.o_ds, t.dn1, B, b.Hin, b.Hout);
         // firstNorm backward -> epsilon at the block's input (and, for block 1, its operand image for block 0's secondConvStem dgrad)
@@ -829,6 +860,7 @@ inline void OuterNet::backward_tc(const float* images, n4j_stats* ode_bwd) {
     // inpart: [co][tap] then [co] per block; the gradient view stores the bias first (bias-first convolution parameters)
     k_on_sum_parts<<<18, 256, 0, s_>>>(inpart_, g_ + off_in_w_, 576, inb, 640);
     k_on_sum_parts<<<2, 256, 0, s_>>>(inpart_ + 576, g_ + off_in_b_, 64, inb, 640);
+    join_side();
     N4J_CUDA(cudaGetLastError());
 }
 
