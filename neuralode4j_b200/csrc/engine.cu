@@ -337,9 +337,13 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
             mlp_smem_ = mlp_small_smem_bytes(m);
             if (mlp_smem_ <= 200 * 1024 && feat == C_) {
                 const int blocks = (int)((B_ + MLP_ROWS - 1) / MLP_ROWS);
-                N4J_CUDA(cudaMalloc(&mlp_part_, sizeof(double) * (size_t)blocks * (n_params_ + 1)));
-                N4J_CUDA(cudaMalloc(&mlp_ticket_, sizeof(unsigned int)));
-                N4J_CUDA(cudaMemsetAsync(mlp_ticket_, 0, sizeof(unsigned int), stream_));
+                int group = 1;
+                while (group * group < blocks) ++group;                      // ~sqrt(blocks) blocks per group, as many groups
+                const int groups = (blocks + group - 1) / group;
+                m.group = group;
+                N4J_CUDA(cudaMalloc(&mlp_part_, sizeof(double) * (size_t)(blocks + groups) * (n_params_ + 1)));
+                N4J_CUDA(cudaMalloc(&mlp_ticket_, sizeof(unsigned int) * (1 + groups)));
+                N4J_CUDA(cudaMemsetAsync(mlp_ticket_, 0, sizeof(unsigned int) * (1 + groups), stream_));
                 N4J_CUDA(cudaFuncSetAttribute(k_mlp_small<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem_));
                 N4J_CUDA(cudaFuncSetAttribute(k_mlp_small<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mlp_smem_));
                 m.part = mlp_part_; m.ticket = mlp_ticket_; m.dt_out = tcat_misc_ + 1; m.c = ctrl_;
