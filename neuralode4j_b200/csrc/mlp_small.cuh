@@ -22,8 +22,8 @@ constexpr int MLP_MAX_LAYERS = 6;
 constexpr int MLP_ROWS = 16;         // batch rows per block (compile-time: the code is latency-bound and wants its loops unrolled).
                                      // Measured on B200, spiral block, 1000 rows: 16 rows x 128 threads -> 29 us per augmented
                                      // evaluation; 128 rows x 512 threads (8 blocks) -> 72 us
-constexpr int MLP_U = 2;             // independent accumulation chains per thread (double-precision FMA latency is long)
-constexpr int MLP_THREADS = 256;     // the (row, feature) items of every layer are spread over all threads of the block
+constexpr int MLP_U = 1;             // independent accumulation chains per thread (double-precision FMA latency is long)
+constexpr int MLP_THREADS = 512;     // the (row, feature) items of every layer are spread over all threads of the block
 constexpr int MLP_LD = MLP_ROWS + 1; // doubles between consecutive features of the activation / delta records: the parameter-gradient pass reads
                                      // one ROW of many FEATURES per warp — with a stride of 16 doubles (128 B) every lane hit the same bank
                                      // (measured: 69 % of the kernel's shared-memory wavefronts were conflict replays, the pass 39 % of its samples)
