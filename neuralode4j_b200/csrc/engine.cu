@@ -844,7 +844,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                         wa.M = l.c_out; wa.N = l.c_in; wa.kblocks = (int)(l.img_rows / 32); wa.a_nch = (int)(l.img_rows / 4); wa.out = dth;
                         wa.a_img = l.dTimg; wa.a_rows = (long long)((l.c_out + 127) / 128 * 128); wa.b_img = l.xTimg; wa.b_nch = (int)(l.img_rows / 4);
                         launch_gemm_tc(s, l.tm_dT, l.tm_xT, wa);
-                        if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 256, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
+                        if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 32 * COLSUM_RG, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
                         if (comm_dev_) enqueue_vec_allreduce(s, dth, l.g_len);
                         GemmTcArgs qa{};     // dx[b,i] = sum_o delta[b,o] W(i,o)
                         qa.M = (int)l.rows; qa.N = l.c_in; qa.kblocks = l.c_out / 32; qa.a_nch = l.c_out / 4; qa.out = dx;
@@ -858,7 +858,7 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                         }
                         launch_gemm<G_DENSE_WGRAD>(s, w, launches_, exact_);
                         if (w.splits > 1) LAUNCH(k_splitk_reduce, grid_for((long long)l.c_in * l.c_out), 256, s, wpart_.p, dth, (long long)l.c_in * l.c_out, 8);
-                        if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 256, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
+                        if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 32 * COLSUM_RG, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
                         if (comm_dev_) enqueue_vec_allreduce(s, dth, l.g_len);
                         GemmArgs q{}; q.a = d; q.c = dx; q.w = Wt; q.M = (int)l.rows; q.N = l.c_in; q.K = l.c_out; q.splits = 1;
                         launch_gemm<G_DENSE_DGRAD>(s, q, launches_, exact_);
