@@ -876,15 +876,18 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
     // dimension: k for the dense forward / dgrad A operand (rows of x / delta) and the dense forward B operand (columns of the f-order
     // weights), m / n elsewhere.  (The m-fastest mapping on a k-contiguous operand made every lane of a warp touch its own cache line:
     // measured 32 us for the 1024 x 256 x 256 forward GEMM of the time-series block against 13.5 us for its weight-gradient GEMM.)
-    constexpr bool A_KFAST = MODE == G_DENSE_FWD || MODE == G_DENSE_DGRAD;
+    constexpr bool A_KFAST = MODE == G_DENSE_FWD || MODE == G_DENSE_DGRAD || MODE == G_CONV_FWD || MODE == G_CONV_DGRAD;   // conv: channels of one tap
     constexpr bool B_KFAST = MODE == G_DENSE_FWD;
     const int la_m = A_KFAST ? threadIdx.x / BK : threadIdx.x % BM, la_k = A_KFAST ? threadIdx.x % BK : threadIdx.x / BM;
     const int lb_n = B_KFAST ? threadIdx.x / BK : threadIdx.x % BN, lb_k = B_KFAST ? threadIdx.x % BK : threadIdx.x / BN;
-    int hh = 0, ww = 0;
+    int hh[4] = {0, 0, 0, 0}, ww[4] = {0, 0, 0, 0};      // conv: pixel coordinates of the four rows this thread loads
     if (MODE == G_CONV_FWD || MODE == G_CONV_DGRAD) {
-        const int m = m0 + la_m;
-        const int s = m % (g.H * g.W);
-        hh = s / g.W; ww = s % g.W;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int m = m0 + la_m + 16 * j;
+            const int s = m % (g.H * g.W);
+            hh[j] = s / g.W; ww[j] = s % g.W;
+        }
     }
     AccT acc[4][4];
 #pragma unroll
@@ -898,7 +901,7 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = A_KFAST ? k0 + la_k : k0 + la_k + 4 * j, m = A_KFAST ? m0 + la_m + 16 * j : m0 + la_m;
-            ra[j] = (m < g.M && k < kend) ? Addr<MODE>::A(g, pa, m, k, hh, ww) : 0.f;
+            ra[j] = (m < g.M && k < kend) ? Addr<MODE>::A(g, pa, m, k, hh[j], ww[j]) : 0.f;
             const int kb = B_KFAST ? k0 + lb_k : k0 + lb_k + 4 * j, n = B_KFAST ? n0 + lb_n + 16 * j : n0 + lb_n;
             rb[j] = (n < g.N && kb < kend) ? Addr<MODE>::B(g, pb, kb, n) : 0.f;
         }
