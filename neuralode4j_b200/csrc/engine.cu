@@ -911,8 +911,14 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                 } else {
                     GemmArgs w{}; w.a = x; w.b = d; w.c = fixed_ref(wpart_.p); w.M = 9 * l.c_in; w.N = l.c_out; w.K = (int)l.rows;
                     w.H = l.H; w.W = l.W; w.Ci = l.c_in; w.Co = l.c_out; w.splits = 16;
-                    if (exact_) w.c = dth;
-                    launch_gemm<G_CONV_WGRAD>(s, w, launches_, exact_);
+                    if (exact_ && l.H * l.W <= 1024) {      // parity mode: same sums in the same order on 16 x 16 output tiles (144 blocks instead of 9)
+                        w.c = dth; w.splits = 1;
+                        launch_k(k_conv_wgrad_exact, dim3((w.N + 15) / 16, (w.M + 15) / 16), dim3(256), 0, s, true, w);
+                        ++launches_;
+                    } else {
+                        if (exact_) w.c = dth;
+                        launch_gemm<G_CONV_WGRAD>(s, w, launches_, exact_);
+                    }
                     if (!exact_) LAUNCH(k_splitk_reduce, grid_for(l.g_len), 256, s, wpart_.p, dth, l.g_len, 16);
                     if (comm_dev_) enqueue_vec_allreduce(s, dth, l.g_len);
                     GemmArgs q{}; q.a = d; q.c = dx; q.w = l.wb; q.M = (int)l.rows; q.N = l.c_in; q.K = 9 * l.c_out;

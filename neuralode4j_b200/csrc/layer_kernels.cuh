@@ -860,8 +860,10 @@ template <int MODE, typename AccT>
 __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
     pdl_begin();
     constexpr int BM = 64, BN = 64, BK = 16;
-    __shared__ float As[BK][BM + 4];
-    __shared__ float Bs[BK][BN + 4];
+    // the tiles are held in the accumulation type: in parity mode (double) every element is converted ONCE when it is stored, not once
+    // per product (F2F.F64.F32 is a slow instruction: 128 conversions per thread and K tile next to 256 DFMA)
+    __shared__ __align__(16) AccT As[BK][BM + 4];
+    __shared__ __align__(16) AccT Bs[BK][BN + 4];
     const float* __restrict__ pa = (MODE == G_DENSE_WGRAD || MODE == G_CONV_WGRAD || MODE == G_DENSE_FWD || MODE == G_CONV_FWD || MODE == G_DENSE_DGRAD ||
                                     MODE == G_CONV_DGRAD)
                                        ? resolve(g.a) : nullptr;
@@ -910,22 +912,22 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (A_KFAST) As[la_k][la_m + 16 * j] = ra[j]; else As[la_k + 4 * j][la_m] = ra[j];
-            if (B_KFAST) Bs[lb_k][lb_n + 16 * j] = rb[j]; else Bs[lb_k + 4 * j][lb_n] = rb[j];
+            if (A_KFAST) As[la_k][la_m + 16 * j] = (AccT)ra[j]; else As[la_k + 4 * j][la_m] = (AccT)ra[j];
+            if (B_KFAST) Bs[lb_k][lb_n + 16 * j] = (AccT)rb[j]; else Bs[lb_k + 4 * j][lb_n] = (AccT)rb[j];
         }
         __syncthreads();
         if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-            const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-            const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
+            AccT a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }      // 128-bit shared loads (rows are 16-byte aligned)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (sizeof(AccT) == 8) acc[i][j] += (AccT)a[i] * (AccT)b[j];
-                    else acc[i][j] = (AccT)fmaf(a[i], b[j], (float)acc[i][j]);
+                    if (sizeof(AccT) == 8) acc[i][j] += a[i] * b[j];
+                    else acc[i][j] = (AccT)fmaf((float)a[i], (float)b[j], (float)acc[i][j]);
                 }
         }
         __syncthreads();
@@ -950,6 +952,70 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
             out[(long long)m * g.N + n] = v;
         }
     }
+}
+
+// Parity-mode weight gradient of the 3x3 convolution: dW[tap][ci][co] = sum_p X[p + shift(tap)][ci] * G[p][co], exact products accumulated in
+// double in ASCENDING PIXEL ORDER per output (the order of k_gemm_tiled<G_CONV_WGRAD, double> and of the oracle: the result is bitwise the
+// same), but on 16 x 16 output tiles with 2 x 2 outputs per thread: 9*Ci*Co/256 blocks (144 for 64 channels) instead of the nine 64 x 64
+// tiles of the generic kernel, whose 6272-long chains on nine SMs were 70 % of the parity-mode step.  K cannot be split: a double sum is
+// only reproducible inside one sequential chain.
+constexpr int WGX_BK = 32;
+__global__ void __launch_bounds__(256) k_conv_wgrad_exact(GemmArgs g) {
+    pdl_begin();
+    __shared__ double As[WGX_BK][16];
+    __shared__ double Bs[WGX_BK][16];
+    __shared__ unsigned short s_mask[1024];         // per pixel of one image: which of the nine taps stay inside the image
+    const float* __restrict__ pa = resolve(g.a);
+    const float* __restrict__ pb = resolve(g.b);
+    float* __restrict__ pc = resolve(g.c);
+    const int HW = g.H * g.W;
+    for (int s = threadIdx.x; s < HW; s += 256) {
+        const int h = s / g.W, w = s - h * g.W;
+        unsigned int mk = 0;
+        for (int t = 0; t < 9; ++t) {
+            const int h2 = h + t / 3 - 1, w2 = w + t % 3 - 1;
+            if ((unsigned)h2 < (unsigned)g.H && (unsigned)w2 < (unsigned)g.W) mk |= 1u << t;
+        }
+        s_mask[s] = (unsigned short)mk;
+    }
+    const int m0 = blockIdx.y * 16, n0 = blockIdx.x * 16;
+    // ONE output per thread (tx: output channel, ty: tap * Ci + ci): the machine has only 9*Ci*Co independent chains to work on, and a
+    // double-precision FMA re-issues slowly from the same warp (measured: four chains per thread on two warps took 126 cycles per pixel) —
+    // sixteen warps with one chain each use all four schedulers
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    // loader: column (m or n) = tid % 16, pixel = tid / 16 + 16 j
+    const int lc = tx, lk = ty;
+    const int lm = m0 + lc, ln = n0 + lc;
+    const bool m_ok = lm < g.M, n_ok = ln < g.N;
+    const int tap = m_ok ? lm / g.Ci : 0, ci = m_ok ? lm - tap * g.Ci : 0;
+    const long long shift = (long long)((tap / 3 - 1) * g.W + (tap % 3 - 1)) * g.Ci + ci;
+    __syncthreads();
+    double acc = 0.0;
+    float ra[2], rb[2];
+    auto fetch = [&](int k0) {
+        int sp = (k0 + lk) % HW;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int k = k0 + lk + 16 * j;
+            const bool in = k < g.K;
+            ra[j] = (in && m_ok && ((s_mask[sp] >> tap) & 1)) ? pa[(long long)k * g.Ci + shift] : 0.f;
+            rb[j] = (in && n_ok) ? pb[(long long)k * g.N + ln] : 0.f;
+            sp += 16;
+            while (sp >= HW) sp -= HW;
+        }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < g.K; k0 += WGX_BK) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) { As[lk + 16 * j][lc] = (double)ra[j]; Bs[lk + 16 * j][lc] = (double)rb[j]; }
+        __syncthreads();
+        if (k0 + WGX_BK < g.K) fetch(k0 + WGX_BK);
+#pragma unroll
+        for (int k = 0; k < WGX_BK; ++k) acc += As[k][ty] * Bs[k][tx];
+        __syncthreads();
+    }
+    const int m = m0 + ty, n = n0 + tx;
+    if (m < g.M && n < g.N) pc[(long long)m * g.N + n] = (float)acc;
 }
 
 // deterministic split-K reduction: dst[i] = sum_z part[z][i]
