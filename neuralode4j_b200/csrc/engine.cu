@@ -545,6 +545,8 @@ template <int MODE>
 static void launch_gemm(cudaStream_t s, GemmArgs g, int& launches, bool exact) {
     if (exact) g.splits = 1;   // double accumulation is only order-independent inside one accumulator chain
     dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.splits);
+    // (16-row tiles for parity mode — k_gemm_tiled<MODE, double, 1>, four times the blocks — were measured and are slower: 8.2 vs 5.4 ms
+    // for the forward solve; with 1 x 4 outputs per thread the shared-memory loads, not the FP64 pipe, become the bound)
     if (exact) launch_k(k_gemm_tiled<MODE, double>, grid, dim3(256), 0, s, true, g);
     else launch_k(k_gemm_tiled<MODE, float>, grid, dim3(256), 0, s, true, g);
     ++launches;

@@ -856,17 +856,17 @@ template <int MODE> struct Addr {
 
 // AccT = float: fp32 FMA accumulation (default).  AccT = double: exact products, double accumulation, one rounding —
 // order-independent and therefore bit-compatible with the oracle (N4J_FLAG_EXACT_CONTRACTIONS, parity mode).
-template <int MODE, typename AccT>
+// TM: rows of the block tile / 16 (4: 64 x 64 tile, 4 x 4 outputs per thread; 1: 16 x 64 tile, 1 x 4 outputs per thread — four times as many
+// blocks, for the double-precision forms whose 98 tiles of 64 rows left a third of the SMs idle while the FP64 pipe was the bound).
+template <int MODE, typename AccT, int TM = 4>
 __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
     pdl_begin();
-    constexpr int BM = 64, BN = 64, BK = 16;
+    constexpr int BM = 16 * TM, BN = 64, BK = 16;
     // the tiles are held in the accumulation type: in parity mode (double) every element is converted ONCE when it is stored, not once
     // per product (F2F.F64.F32 is a slow instruction: 128 conversions per thread and K tile next to 256 DFMA)
     __shared__ __align__(16) AccT As[BK][BM + 4];
     __shared__ __align__(16) AccT Bs[BK][BN + 4];
-    const float* __restrict__ pa = (MODE == G_DENSE_WGRAD || MODE == G_CONV_WGRAD || MODE == G_DENSE_FWD || MODE == G_CONV_FWD || MODE == G_DENSE_DGRAD ||
-                                    MODE == G_CONV_DGRAD)
-                                       ? resolve(g.a) : nullptr;
+    const float* __restrict__ pa = resolve(g.a);
     const float* __restrict__ pb = g.w ? g.w : resolve(g.b);
     float* __restrict__ pc = resolve(g.c);
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -874,36 +874,43 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
     // K range of this split
     const int kchunk = (g.K + g.splits - 1) / g.splits;
     const int kbeg = blockIdx.z * kchunk, kend = min(g.K, kbeg + kchunk);
-    // loader mapping: a tile is 64 x 16 = 1024 elements, 4 per thread.  The fastest-varying thread index follows the operand's contiguous
-    // dimension: k for the dense forward / dgrad A operand (rows of x / delta) and the dense forward B operand (columns of the f-order
-    // weights), m / n elsewhere.  (The m-fastest mapping on a k-contiguous operand made every lane of a warp touch its own cache line:
-    // measured 32 us for the 1024 x 256 x 256 forward GEMM of the time-series block against 13.5 us for its weight-gradient GEMM.)
-    constexpr bool A_KFAST = MODE == G_DENSE_FWD || MODE == G_DENSE_DGRAD || MODE == G_CONV_FWD || MODE == G_CONV_DGRAD;   // conv: channels of one tap
+    // loader mapping: the A tile is BM x 16 (TM elements per thread), the B tile 16 x 64 (4 per thread).  The fastest-varying thread index
+    // follows the operand's contiguous dimension: k for the dense forward / dgrad A operand (rows of x / delta), the conv forward / dgrad A
+    // operand (channels of one tap) and the dense forward B operand (columns of the f-order weights), m / n elsewhere.  (The m-fastest
+    // mapping on a k-contiguous operand made every lane of a warp touch its own cache line: measured 32 us for the 1024 x 256 x 256
+    // forward GEMM of the time-series block against 13.5 us for its weight-gradient GEMM.)
+    constexpr bool A_KFAST = MODE == G_DENSE_FWD || MODE == G_DENSE_DGRAD || MODE == G_CONV_FWD || MODE == G_CONV_DGRAD;
     constexpr bool B_KFAST = MODE == G_DENSE_FWD;
+    constexpr int AKS = 256 / BM;        // k rows covered per pass of the m-fastest A loader
     const int la_m = A_KFAST ? threadIdx.x / BK : threadIdx.x % BM, la_k = A_KFAST ? threadIdx.x % BK : threadIdx.x / BM;
     const int lb_n = B_KFAST ? threadIdx.x / BK : threadIdx.x % BN, lb_k = B_KFAST ? threadIdx.x % BK : threadIdx.x / BN;
-    int hh[4] = {0, 0, 0, 0}, ww[4] = {0, 0, 0, 0};      // conv: pixel coordinates of the four rows this thread loads
+    int hh[TM], ww[TM];      // conv: pixel coordinates of the rows this thread loads
+#pragma unroll
+    for (int j = 0; j < TM; ++j) { hh[j] = 0; ww[j] = 0; }
     if (MODE == G_CONV_FWD || MODE == G_CONV_DGRAD) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < TM; ++j) {
             const int m = m0 + la_m + 16 * j;
             const int s = m % (g.H * g.W);
             hh[j] = s / g.W; ww[j] = s % g.W;
         }
     }
-    AccT acc[4][4];
+    AccT acc[TM][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = (AccT)0;
 
     // register prefetch: the loads of K tile i+1 are in flight while tile i is multiplied (the summation order is unchanged)
-    float ra[4], rb[4];
+    float ra[TM], rb[4];
     auto fetch = [&](int k0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int k = A_KFAST ? k0 + la_k : k0 + la_k + 4 * j, m = A_KFAST ? m0 + la_m + 16 * j : m0 + la_m;
+        for (int j = 0; j < TM; ++j) {
+            const int k = A_KFAST ? k0 + la_k : k0 + la_k + AKS * j, m = A_KFAST ? m0 + la_m + 16 * j : m0 + la_m;
             ra[j] = (m < g.M && k < kend) ? Addr<MODE>::A(g, pa, m, k, hh[j], ww[j]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
             const int kb = B_KFAST ? k0 + lb_k : k0 + lb_k + 4 * j, n = B_KFAST ? n0 + lb_n + 16 * j : n0 + lb_n;
             rb[j] = (n < g.N && kb < kend) ? Addr<MODE>::B(g, pb, kb, n) : 0.f;
         }
@@ -911,19 +918,24 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
     fetch(kbeg);
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
+        for (int j = 0; j < TM; ++j) {
+            if (A_KFAST) As[la_k][la_m + 16 * j] = (AccT)ra[j]; else As[la_k + AKS * j][la_m] = (AccT)ra[j];
+        }
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (A_KFAST) As[la_k][la_m + 16 * j] = (AccT)ra[j]; else As[la_k + 4 * j][la_m] = (AccT)ra[j];
             if (B_KFAST) Bs[lb_k][lb_n + 16 * j] = (AccT)rb[j]; else Bs[lb_k + 4 * j][lb_n] = (AccT)rb[j];
         }
         __syncthreads();
         if (k0 + BK < kend) fetch(k0 + BK);
 #pragma unroll
         for (int k = 0; k < BK; ++k) {
-            AccT a[4], b[4];
+            AccT a[TM], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }      // 128-bit shared loads (rows are 16-byte aligned)
+            for (int i = 0; i < TM; ++i) a[i] = As[k][ty * TM + i];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) b[i] = Bs[k][tx * 4 + i];      // 128-bit shared loads (rows are 16-byte aligned)
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (sizeof(AccT) == 8) acc[i][j] += a[i] * b[j];
@@ -934,8 +946,8 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
     }
     float* __restrict__ out = pc + (g.splits > 1 ? (long long)blockIdx.z * g.M * g.N : 0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = m0 + ty * 4 + i;
+    for (int i = 0; i < TM; ++i) {
+        const int m = m0 + ty * TM + i;
         if (m >= g.M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
