@@ -9,8 +9,10 @@
 //     image and its epilogue stores only the sampled pixels (k_conv3x3_tc<.., SUB = 1>); backward, the gradient is scattered into a
 //     zero full-resolution tensor (compact + operand image), which turns dgrad and wgrad into the stride-1 kernels as well.
 // What stays on the CUDA cores is small: the 1 -> 64 input convolution (9 products per output), the 1x1 stride-2 downSample
-// (64 products), BatchNorm, pooling, the output layer.  Reductions accumulate exact fp32 products in double as everywhere else;
-// elementwise expressions keep the oracle's order (oracle/outer_oracle.py).  BatchNorm statistics are raw double sums that every
+// (64 products), BatchNorm, pooling, the output layer.  Their short contractions (9 / 64 products, a slice of pixels) use fp32 FMA like the
+// tensor-core accumulators beside them — B200's FP64 pipe is an order of magnitude slower — while every long reduction (BatchNorm
+// statistics, sums over blocks of pixels, the output layer) accumulates in double; elementwise expressions keep the oracle's order
+// (oracle/outer_oracle.py).  BatchNorm statistics are raw double sums that every
 // consumer finalises itself (the engine's deferred scheme, layer_kernels.cuh), so no kernel waits for a last block.
 #pragma once
 
@@ -48,17 +50,17 @@ __global__ void __launch_bounds__(256) k_on_in_conv_fwd(const float* __restrict_
     for (long long p = (long long)blockIdx.x * 16 + (threadIdx.x >> 4); p < n; p += (long long)gridDim.x * 16) {
         const int ow = (int)(p % Wo), oh = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
         const float* xb = x + ((long long)b * H + oh) * W + ow;
-        double a[4] = {0, 0, 0, 0};
+        float a[4] = {0.f, 0.f, 0.f, 0.f};       // nine products: fp32 FMA (the FP64 pipe of this part is an order of magnitude slower)
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-            const double xv = (double)xb[(t / 3) * W + (t % 3)];
+            const float xv = xb[(t / 3) * W + (t % 3)];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] += xv * (double)s_w[t][c0 + k];
+            for (int k = 0; k < 4; ++k) a[k] = fmaf(xv, s_w[t][c0 + k], a[k]);
         }
         float o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            o[k] = __fadd_rn((float)a[k], s_b[c0 + k]);
+            o[k] = __fadd_rn(a[k], s_b[c0 + k]);
             s1[k] += (double)o[k]; s2[k] += (double)o[k] * (double)o[k];
         }
         reinterpret_cast<float4*>(y)[p * 16 + chunk] = make_float4(o[0], o[1], o[2], o[3]);
@@ -151,25 +153,25 @@ __global__ void __launch_bounds__(256) k_on_ds_fwd(const float* __restrict__ x, 
     }
     __syncthreads();
     const int c0 = (threadIdx.x & 15) * 4, r0 = (threadIdx.x >> 4) * 4;
-    double a[4][4];
+    float a[4][4];      // 64 products per output: fp32 FMA, like the TMEM accumulators of the 3x3 convolutions beside it
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a[i][k] = 0.0;
+        for (int k = 0; k < 4; ++k) a[i][k] = 0.f;
     for (int ci = 0; ci < 64; ++ci) {
         const float4 wv = *reinterpret_cast<const float4*>(&s_w[ci][c0]);
-        const double ws[4] = {wv.x, wv.y, wv.z, wv.w};
+        const float ws[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const double xv = (double)s_x[r0 + i][ci];
+            const float xv = s_x[r0 + i][ci];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[i][k] += xv * ws[k];
+            for (int k = 0; k < 4; ++k) a[i][k] = fmaf(xv, ws[k], a[i][k]);
         }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i)
         if (p0 + r0 + i < P)
-            reinterpret_cast<float4*>(y)[(p0 + r0 + i) * 16 + (threadIdx.x & 15)] = make_float4((float)a[i][0], (float)a[i][1], (float)a[i][2], (float)a[i][3]);
+            reinterpret_cast<float4*>(y)[(p0 + r0 + i) * 16 + (threadIdx.x & 15)] = make_float4(a[i][0], a[i][1], a[i][2], a[i][3]);
 }
 
 // dn1[(b,2oh,2ow)][ci] += (float)sum_co g[(b,oh,ow)][co] * w[co][ci]       (downSample's epsilon added onto firstConv's, in place)
@@ -184,19 +186,19 @@ __global__ void __launch_bounds__(256) k_on_ds_dgrad_add(const float* __restrict
     }
     __syncthreads();
     const int c0 = (threadIdx.x & 15) * 4, r0 = (threadIdx.x >> 4) * 4;
-    double a[4][4];
+    float a[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a[i][k] = 0.0;
+        for (int k = 0; k < 4; ++k) a[i][k] = 0.f;
     for (int co = 0; co < 64; ++co) {
         const float4 wv = *reinterpret_cast<const float4*>(&s_w[co][c0]);
-        const double ws[4] = {wv.x, wv.y, wv.z, wv.w};
+        const float ws[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const double gv = (double)s_g[r0 + i][co];
+            const float gv = s_g[r0 + i][co];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[i][k] += gv * ws[k];
+            for (int k = 0; k < 4; ++k) a[i][k] = fmaf(gv, ws[k], a[i][k]);
         }
     }
 #pragma unroll
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(256) k_on_ds_dgrad_add(const float* __restrict
         const int ow = (int)(p % Ho), oh = (int)((p / Ho) % Ho), b = (int)(p / ((long long)Ho * Ho));
         float4* d = reinterpret_cast<float4*>(dx) + (((long long)b * Hi + 2 * oh) * Hi + 2 * ow) * 16 + (threadIdx.x & 15);
         const float4 u = *d;
-        *d = make_float4(__fadd_rn((float)a[i][0], u.x), __fadd_rn((float)a[i][1], u.y), __fadd_rn((float)a[i][2], u.z), __fadd_rn((float)a[i][3], u.w));
+        *d = make_float4(__fadd_rn(a[i][0], u.x), __fadd_rn(a[i][1], u.y), __fadd_rn(a[i][2], u.z), __fadd_rn(a[i][3], u.w));
     }
 }
 
@@ -236,15 +238,24 @@ __global__ void __launch_bounds__(256) k_on_ds_wgrad(const float* __restrict__ x
             reinterpret_cast<float4*>(&s_g[i >> 4][0])[i & 15] = gv;
         }
         __syncthreads();
+        float f[4][4];      // the 64 pixels of a slice in fp32 FMA, slices and blocks in double
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) f[i][j] = 0.f;
         for (int r = 0; r < ON_DS_WG_PIX; ++r) {
             const float4 xv = *reinterpret_cast<const float4*>(&s_x[r][ci0]);
             const float4 gv = *reinterpret_cast<const float4*>(&s_g[r][co0]);
-            const double xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, gs[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) a[i][j] += xs[i] * gs[j];
+                for (int j = 0; j < 4; ++j) f[i][j] = fmaf(xs[i], gs[j], f[i][j]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[i][j] += (double)f[i][j];
     }
     double* o = part + (long long)blockIdx.x * 4096;
 #pragma unroll
@@ -276,21 +287,21 @@ __global__ void __launch_bounds__(256) k_on_in_conv_wgrad(const float* __restric
     const int Ho = H - 2, Wo = W - 2;
     const long long n = (long long)B * Ho * Wo;
     const int chunk = threadIdx.x & 15, c0 = chunk * 4, sub = threadIdx.x >> 4;
-    double a[10][4];
+    float a[10][4];      // a thread's own pixels (a few dozen) in fp32 FMA; the 16 pixel lanes and the blocks are summed in double
 #pragma unroll
     for (int t = 0; t < 10; ++t)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a[t][k] = 0.0;
+        for (int k = 0; k < 4; ++k) a[t][k] = 0.f;
     for (long long p = (long long)blockIdx.x * 16 + sub; p < n; p += (long long)gridDim.x * 16) {
         const int ow = (int)(p % Wo), oh = (int)((p / Wo) % Ho), b = (int)(p / ((long long)Wo * Ho));
         const float4 gv = reinterpret_cast<const float4*>(g)[p * 16 + chunk];
-        const double gs[4] = {gv.x, gv.y, gv.z, gv.w};
+        const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
         const float* xb = x + ((long long)b * H + oh) * W + ow;
 #pragma unroll
         for (int t = 0; t < 9; ++t) {
-            const double xv = (double)xb[(t / 3) * W + (t % 3)];
+            const float xv = xb[(t / 3) * W + (t % 3)];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[t][k] += xv * gs[k];
+            for (int k = 0; k < 4; ++k) a[t][k] = fmaf(xv, gs[k], a[t][k]);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) a[9][k] += gs[k];
@@ -299,7 +310,7 @@ __global__ void __launch_bounds__(256) k_on_in_conv_wgrad(const float* __restric
 #pragma unroll
     for (int t = 0; t < 10; ++t) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s_red[sub][c0 + k] = a[t][k];
+        for (int k = 0; k < 4; ++k) s_red[sub][c0 + k] = (double)a[t][k];
         __syncthreads();
         if (threadIdx.x < 64) {
             double sm = 0.0;
