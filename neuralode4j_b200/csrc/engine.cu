@@ -825,7 +825,9 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
             case N4J_LAYER_DENSE:
             case N4J_LAYER_CONV3X3: {
                 Ref d = g;
-                if (l.d.activation != N4J_ACT_IDENTITY || gscale != 1.f) {
+                // identity-activation dense layer on the generic GEMM path whose epsilon is -a: the sign rides on the GEMMs' stores
+                const bool neg = l.d.kind == N4J_LAYER_DENSE && l.d.activation == N4J_ACT_IDENTITY && gscale == -1.f && !l.exact && !l.tcd;
+                if (!neg && (l.d.activation != N4J_ACT_IDENTITY || gscale != 1.f)) {
                     d = fixed_ref(gb_[2].p);
                     LAUNCH(k_act_bwd, grid_for(l.out_len), 256, s, g, gscale, y, l.d.activation, d, l.out_len);
                     gimg_ready = false;
@@ -846,23 +848,23 @@ void Engine::enqueue_rhs_aug(cudaStream_t s, Ref in, Ref out, bool bn1_ready, in
                         wa.M = l.c_out; wa.N = l.c_in; wa.kblocks = (int)(l.img_rows / 32); wa.a_nch = (int)(l.img_rows / 4); wa.out = dth;
                         wa.a_img = l.dTimg; wa.a_rows = (long long)((l.c_out + 127) / 128 * 128); wa.b_img = l.xTimg; wa.b_nch = (int)(l.img_rows / 4);
                         launch_gemm_tc(s, l.tm_dT, l.tm_xT, wa);
-                        if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 32 * COLSUM_RG, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
+                        if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 32 * COLSUM_RG, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out, 0);
                         if (comm_dev_) enqueue_vec_allreduce(s, dth, l.g_len);
                         GemmTcArgs qa{};     // dx[b,i] = sum_o delta[b,o] W(i,o)
                         qa.M = (int)l.rows; qa.N = l.c_in; qa.kblocks = l.c_out / 32; qa.a_nch = l.c_out / 4; qa.out = dx;
                         qa.a_img = l.dimg; qa.a_rows = l.img_rows; qa.b_img = l.wsb; qa.b_nch = l.c_out / 4;
                         launch_gemm_tc(s, l.tm_d_k, l.tm_wb, qa);
                     } else {
-                        GemmArgs w{}; w.a = d; w.b = x; w.c = dth; w.M = l.c_out; w.N = l.c_in; w.K = (int)l.rows; w.splits = 1;
+                        GemmArgs w{}; w.a = d; w.b = x; w.c = dth; w.M = l.c_out; w.N = l.c_in; w.K = (int)l.rows; w.splits = 1; w.negate = neg ? 1 : 0;
                         const long long tiles = (long long)((l.c_out + 63) / 64) * ((l.c_in + 63) / 64);
                         if (!exact_ && tiles < 148 && l.rows >= 256 && wpart_.n >= 8LL * l.c_in * l.c_out) {   // few output tiles, long K: split the batch
                             w.splits = 8; w.c = fixed_ref(wpart_.p);
                         }
                         launch_gemm<G_DENSE_WGRAD>(s, w, launches_, exact_);
                         if (w.splits > 1) LAUNCH(k_splitk_reduce, grid_for((long long)l.c_in * l.c_out), 256, s, wpart_.p, dth, (long long)l.c_in * l.c_out, 8);
-                        if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 32 * COLSUM_RG, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out);
+                        if (l.d.has_bias) LAUNCH(k_colsum, (l.c_out + 31) / 32, 32 * COLSUM_RG, s, d, with_off(dth, (long long)l.c_in * l.c_out), l.rows, l.c_out, neg ? 1 : 0);
                         if (comm_dev_) enqueue_vec_allreduce(s, dth, l.g_len);
-                        GemmArgs q{}; q.a = d; q.c = dx; q.w = Wt; q.M = (int)l.rows; q.N = l.c_in; q.K = l.c_out; q.splits = 1;
+                        GemmArgs q{}; q.a = d; q.c = dx; q.w = Wt; q.M = (int)l.rows; q.N = l.c_in; q.K = l.c_out; q.splits = 1; q.negate = neg ? 1 : 0;
                         launch_gemm<G_DENSE_DGRAD>(s, q, launches_, exact_);
                     }
                 } else if (l.tc) {

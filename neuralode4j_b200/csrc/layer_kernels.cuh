@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(256) k_dense_dgrad_exact(Ref din, const float*
     }
 }
 constexpr int COLSUM_RG = 32;      // row groups per block (block = 32 columns x COLSUM_RG row groups)
-__global__ void __launch_bounds__(32 * COLSUM_RG) k_colsum(Ref din, Ref out, long long B, int n) {   // bias gradient: column sums in double
+__global__ void __launch_bounds__(32 * COLSUM_RG) k_colsum(Ref din, Ref out, long long B, int n, int negate) {   // bias gradient: column sums in double
     pdl_begin();
     const float* __restrict__ d = resolve(din);
     float* __restrict__ o = resolve(out);
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(32 * COLSUM_RG) k_colsum(Ref din, Ref out, lon
         double t = 0;
 #pragma unroll
         for (int r = 0; r < COLSUM_RG; ++r) t += sm[r][threadIdx.x];
-        o[c] = (float)t;
+        o[c] = negate ? -(float)t : (float)t;
     }
 }
 
@@ -820,6 +820,8 @@ struct GemmArgs {
     int act;
     int H, W, Ci, Co;      // conv geometry
     int splits;            // split-K factor (grid.z); partials go to c + z*M*N when splits > 1
+    int negate;            // store -C: the epsilon of the block's last layer is -a (BackpropagateAdjoint.java:75); folding the sign into the
+                           // weight-gradient / dgrad GEMMs saves the kernel that would materialise -a first (exact: a sign flip does not round)
 };
 
 template <int MODE> struct Addr {
@@ -961,7 +963,7 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
             } else {
                 v = (float)acc[i][j];
             }
-            out[(long long)m * g.N + n] = v;
+            out[(long long)m * g.N + n] = g.negate ? -v : v;
         }
     }
 }
