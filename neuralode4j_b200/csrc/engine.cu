@@ -547,7 +547,9 @@ static void launch_gemm(cudaStream_t s, GemmArgs g, int& launches, bool exact) {
     dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, g.splits);
     // (16-row tiles for parity mode — k_gemm_tiled<MODE, double, 1>, four times the blocks — were measured and are slower: 8.2 vs 5.4 ms
     // for the forward solve; with 1 x 4 outputs per thread the shared-memory loads, not the FP64 pipe, become the bound)
+    constexpr bool dense = MODE == G_DENSE_FWD || MODE == G_DENSE_DGRAD || MODE == G_DENSE_WGRAD;
     if (exact) launch_k(k_gemm_tiled<MODE, double>, grid, dim3(256), 0, s, true, g);
+    else if (dense && g.K / g.splits >= 64) launch_k(k_gemm_tiled<MODE, float, 4, 32>, grid, dim3(256), 0, s, true, g);   // half as many dependent trips to L2
     else launch_k(k_gemm_tiled<MODE, float>, grid, dim3(256), 0, s, true, g);
     ++launches;
 }

@@ -860,10 +860,10 @@ template <int MODE> struct Addr {
 // order-independent and therefore bit-compatible with the oracle (N4J_FLAG_EXACT_CONTRACTIONS, parity mode).
 // TM: rows of the block tile / 16 (4: 64 x 64 tile, 4 x 4 outputs per thread; 1: 16 x 64 tile, 1 x 4 outputs per thread — four times as many
 // blocks, for the double-precision forms whose 98 tiles of 64 rows left a third of the SMs idle while the FP64 pipe was the bound).
-template <int MODE, typename AccT, int TM = 4>
+template <int MODE, typename AccT, int TM = 4, int BK = 16>
 __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
     pdl_begin();
-    constexpr int BM = 16 * TM, BN = 64, BK = 16;
+    constexpr int BM = 16 * TM, BN = 64;
     // the tiles are held in the accumulation type: in parity mode (double) every element is converted ONCE when it is stored, not once
     // per product (F2F.F64.F32 is a slow instruction: 128 conversions per thread and K tile next to 256 DFMA)
     __shared__ __align__(16) AccT As[BK][BM + 4];
@@ -876,23 +876,26 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
     // K range of this split
     const int kchunk = (g.K + g.splits - 1) / g.splits;
     const int kbeg = blockIdx.z * kchunk, kend = min(g.K, kbeg + kchunk);
-    // loader mapping: the A tile is BM x 16 (TM elements per thread), the B tile 16 x 64 (4 per thread).  The fastest-varying thread index
+    // loader mapping: the A tile is BM x BK (EA elements per thread), the B tile BK x 64 (EB per thread).  The fastest-varying thread index
     // follows the operand's contiguous dimension: k for the dense forward / dgrad A operand (rows of x / delta), the conv forward / dgrad A
     // operand (channels of one tap) and the dense forward B operand (columns of the f-order weights), m / n elsewhere.  (The m-fastest
     // mapping on a k-contiguous operand made every lane of a warp touch its own cache line: measured 32 us for the 1024 x 256 x 256
-    // forward GEMM of the time-series block against 13.5 us for its weight-gradient GEMM.)
+    // forward GEMM of the time-series block against 13.5 us for its weight-gradient GEMM.)  BK = 32 (dense modes with a long K): these
+    // GEMMs are a chain of K/BK dependent trips to L2 — one tile ahead in registers — so fewer, larger trips.
     constexpr bool A_KFAST = MODE == G_DENSE_FWD || MODE == G_DENSE_DGRAD || MODE == G_CONV_FWD || MODE == G_CONV_DGRAD;
     constexpr bool B_KFAST = MODE == G_DENSE_FWD;
-    constexpr int AKS = 256 / BM;        // k rows covered per pass of the m-fastest A loader
+    constexpr int EA = BM * BK / 256, EB = BN * BK / 256;
+    constexpr int ARS = 256 / BK;        // rows (m or n) covered per pass of a k-fastest loader
+    constexpr int AKS = 256 / BM, BKS = 256 / BN;   // k rows covered per pass of an m- / n-fastest loader
     const int la_m = A_KFAST ? threadIdx.x / BK : threadIdx.x % BM, la_k = A_KFAST ? threadIdx.x % BK : threadIdx.x / BM;
     const int lb_n = B_KFAST ? threadIdx.x / BK : threadIdx.x % BN, lb_k = B_KFAST ? threadIdx.x % BK : threadIdx.x / BN;
-    int hh[TM], ww[TM];      // conv: pixel coordinates of the rows this thread loads
+    int hh[EA], ww[EA];      // conv: pixel coordinates of the rows this thread loads
 #pragma unroll
-    for (int j = 0; j < TM; ++j) { hh[j] = 0; ww[j] = 0; }
+    for (int j = 0; j < EA; ++j) { hh[j] = 0; ww[j] = 0; }
     if (MODE == G_CONV_FWD || MODE == G_CONV_DGRAD) {
 #pragma unroll
-        for (int j = 0; j < TM; ++j) {
-            const int m = m0 + la_m + 16 * j;
+        for (int j = 0; j < EA; ++j) {
+            const int m = m0 + la_m + ARS * j;
             const int s = m % (g.H * g.W);
             hh[j] = s / g.W; ww[j] = s % g.W;
         }
@@ -904,28 +907,28 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
         for (int j = 0; j < 4; ++j) acc[i][j] = (AccT)0;
 
     // register prefetch: the loads of K tile i+1 are in flight while tile i is multiplied (the summation order is unchanged)
-    float ra[TM], rb[4];
+    float ra[EA], rb[EB];
     auto fetch = [&](int k0) {
 #pragma unroll
-        for (int j = 0; j < TM; ++j) {
-            const int k = A_KFAST ? k0 + la_k : k0 + la_k + AKS * j, m = A_KFAST ? m0 + la_m + 16 * j : m0 + la_m;
+        for (int j = 0; j < EA; ++j) {
+            const int k = A_KFAST ? k0 + la_k : k0 + la_k + AKS * j, m = A_KFAST ? m0 + la_m + ARS * j : m0 + la_m;
             ra[j] = (m < g.M && k < kend) ? Addr<MODE>::A(g, pa, m, k, hh[j], ww[j]) : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int kb = B_KFAST ? k0 + lb_k : k0 + lb_k + 4 * j, n = B_KFAST ? n0 + lb_n + 16 * j : n0 + lb_n;
+        for (int j = 0; j < EB; ++j) {
+            const int kb = B_KFAST ? k0 + lb_k : k0 + lb_k + BKS * j, n = B_KFAST ? n0 + lb_n + ARS * j : n0 + lb_n;
             rb[j] = (n < g.N && kb < kend) ? Addr<MODE>::B(g, pb, kb, n) : 0.f;
         }
     };
     fetch(kbeg);
     for (int k0 = kbeg; k0 < kend; k0 += BK) {
 #pragma unroll
-        for (int j = 0; j < TM; ++j) {
-            if (A_KFAST) As[la_k][la_m + 16 * j] = (AccT)ra[j]; else As[la_k + AKS * j][la_m] = (AccT)ra[j];
+        for (int j = 0; j < EA; ++j) {
+            if (A_KFAST) As[la_k][la_m + ARS * j] = (AccT)ra[j]; else As[la_k + AKS * j][la_m] = (AccT)ra[j];
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (B_KFAST) Bs[lb_k][lb_n + 16 * j] = (AccT)rb[j]; else Bs[lb_k + 4 * j][lb_n] = (AccT)rb[j];
+        for (int j = 0; j < EB; ++j) {
+            if (B_KFAST) Bs[lb_k][lb_n + ARS * j] = (AccT)rb[j]; else Bs[lb_k + BKS * j][lb_n] = (AccT)rb[j];
         }
         __syncthreads();
         if (k0 + BK < kend) fetch(k0 + BK);
