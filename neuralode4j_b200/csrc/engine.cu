@@ -548,6 +548,17 @@ static void launch_gemm(cudaStream_t s, GemmArgs g, int& launches, bool exact) {
     // (16-row tiles for parity mode — k_gemm_tiled<MODE, double, 1>, four times the blocks — were measured and are slower: 8.2 vs 5.4 ms
     // for the forward solve; with 1 x 4 outputs per thread the shared-memory loads, not the FP64 pipe, become the bound)
     constexpr bool dense = MODE == G_DENSE_FWD || MODE == G_DENSE_DGRAD || MODE == G_DENSE_WGRAD;
+    constexpr bool a_kfast = MODE == G_DENSE_FWD || MODE == G_DENSE_DGRAD || MODE == G_CONV_FWD || MODE == G_CONV_DGRAD;
+    const long long b64 = (long long)grid.x * grid.y, b48 = (long long)grid.x * ((g.M + 47) / 48);
+    if constexpr (a_kfast) {
+        // parity mode, FP64-pipe-bound: 48-row tiles when they still fit one wave and the 64-row tiles leave SMs idle (same sums, same order)
+        if (exact && b64 < 148 && b48 <= 148 && b48 > b64) {
+            grid.y = (g.M + 47) / 48;
+            launch_k(k_gemm_tiled<MODE, double, 3>, grid, dim3(256), 0, s, true, g);
+            ++launches;
+            return;
+        }
+    }
     if (exact) launch_k(k_gemm_tiled<MODE, double>, grid, dim3(256), 0, s, true, g);
     else if (dense && g.K / g.splits >= 64) launch_k(k_gemm_tiled<MODE, float, 4, 32>, grid, dim3(256), 0, s, true, g);   // half as many dependent trips to L2
     else launch_k(k_gemm_tiled<MODE, float>, grid, dim3(256), 0, s, true, g);

@@ -858,8 +858,9 @@ template <int MODE> struct Addr {
 
 // AccT = float: fp32 FMA accumulation (default).  AccT = double: exact products, double accumulation, one rounding —
 // order-independent and therefore bit-compatible with the oracle (N4J_FLAG_EXACT_CONTRACTIONS, parity mode).
-// TM: rows of the block tile / 16 (4: 64 x 64 tile, 4 x 4 outputs per thread; 1: 16 x 64 tile, 1 x 4 outputs per thread — four times as many
-// blocks, for the double-precision forms whose 98 tiles of 64 rows left a third of the SMs idle while the FP64 pipe was the bound).
+// TM: rows of the block tile / 16 (4: 64 x 64 tile, 4 x 4 outputs per thread; 3: 48 x 64 — parity mode is bound by the FP64 pipe, and the 98
+// tiles of 64 rows of the MNIST convolutions leave a third of the SMs idle where 131 tiles of 48 rows still are one wave; 1: 16 x 64,
+// measured slower: its shared-memory loads become the bound).
 template <int MODE, typename AccT, int TM = 4, int BK = 16>
 __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
     pdl_begin();
@@ -887,6 +888,7 @@ __global__ void __launch_bounds__(256) k_gemm_tiled(GemmArgs g) {
     constexpr int EA = BM * BK / 256, EB = BN * BK / 256;
     constexpr int ARS = 256 / BK;        // rows (m or n) covered per pass of a k-fastest loader
     constexpr int AKS = 256 / BM, BKS = 256 / BN;   // k rows covered per pass of an m- / n-fastest loader
+    static_assert(A_KFAST || 256 % BM == 0, "the m-fastest A loader needs a row tile that divides 256 (TM = 3 only with k-fastest A operands)");
     const int la_m = A_KFAST ? threadIdx.x / BK : threadIdx.x % BM, la_k = A_KFAST ? threadIdx.x % BK : threadIdx.x / BM;
     const int lb_n = B_KFAST ? threadIdx.x / BK : threadIdx.x % BN, lb_k = B_KFAST ? threadIdx.x % BK : threadIdx.x / BN;
     int hh[EA], ww[EA];      // conv: pixel coordinates of the rows this thread loads
