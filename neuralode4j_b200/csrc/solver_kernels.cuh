@@ -173,6 +173,51 @@ __global__ void __launch_bounds__(256) k_stage_combine_last(const Ctrl* __restri
     float* __restrict__ klast = Kbase + (long long)c->krow[S - 1] * stride;
     const int c0 = (threadIdx.x & 15) * 4;      // grid stride is a multiple of 16 float4: a thread stays on one 4-channel chunk
     __shared__ float s_st[4][64];               // mean, invstd, mean(dy), mean(dy*xhat) of the BatchNorm being finished
+    const float* __restrict__ xin = MODE == 1 ? resolve(fl.x) : yw;
+    const float* __restrict__ gin = MODE == 2 ? resolve(fl.g) : nullptr;
+    const float* __restrict__ yin = MODE == 2 ? resolve(fl.y) : nullptr;
+    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
+    const long long step = (long long)gridDim.x * blockDim.x;
+    const long long i_first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // z block of the stage state (and the next evaluation's first-BatchNorm sums); kl: the fresh K value when this very kernel produced it (MODE 1)
+    auto z_part = [&](long long i, const float* kl) {
+        const float4 yv0 = ld4(y, i);
+        const float4 k0 = ld4(kr[0], i);
+        float4 acc = make_float4(__fmul_rn(coef[0], k0.x), __fmul_rn(coef[0], k0.y), __fmul_rn(coef[0], k0.z), __fmul_rn(coef[0], k0.w));
+#pragma unroll
+        for (int j = 1; j < S; ++j) {
+            if (S == 6 && j == 1) continue;   // a_62 == 0
+            const float4 kj = (MODE == 1 && j == S - 1) ? make_float4(kl[0], kl[1], kl[2], kl[3]) : ld4(kr[j], i);
+            acc.x = __fmaf_rn(coef[j], kj.x, acc.x);
+            acc.y = __fmaf_rn(coef[j], kj.y, acc.y);
+            acc.z = __fmaf_rn(coef[j], kj.z, acc.z);
+            acc.w = __fmaf_rn(coef[j], kj.w, acc.w);
+        }
+        const float4 o = make_float4(__fadd_rn(yv0.x, acc.x), __fadd_rn(yv0.y, acc.y), __fadd_rn(yv0.z, acc.z), __fadd_rn(yv0.w, acc.w));
+        st4(yw, i, o);
+        s1[0] += (double)o.x; s2[0] += (double)o.x * (double)o.x;
+        s1[1] += (double)o.y; s2[1] += (double)o.y * (double)o.y;
+        s1[2] += (double)o.z; s2[2] += (double)o.z * (double)o.z;
+        s1[3] += (double)o.w; s2[3] += (double)o.w * (double)o.w;
+    };
+    // MODE 2: the z block does not depend on the statistics this kernel has to wait for (the backward sums the dgrad launch in front of it
+    // produced — on the sharded path also the peers' share of them, one NVLink flight away): a thread's first ZIT items are combined BEFORE
+    // the finalisation, with the BatchNorm input x — which lives in the z block of yWorking and is overwritten by that very store — kept in
+    // registers for the a block afterwards.  The sums are pushed to the peers first of all.  Same expressions, same per-thread order of the
+    // statistics accumulation: bit-identical results.
+    constexpr int ZIT = 2;
+    float4 xs[ZIT];
+    if (MODE == 2) {
+        if (fl.bn.deferred && fl.bn.cm && bn_first_block() && threadIdx.x < 64) {
+            const unsigned int tagb = *((volatile unsigned int*)fl.bn.seqb);
+            bn_push2(fl.bn.cm, fl.bn.mbb, tagb, threadIdx.x, fl.bn.accb[threadIdx.x * ACC_STRIDE], fl.bn.accb[(64 + threadIdx.x) * ACC_STRIDE]);
+        }
+#pragma unroll
+        for (int it = 0; it < ZIT; ++it) {
+            const long long i = i_first + it * step;
+            if (i < bf.nz4) { xs[it] = ld4(xin, i); z_part(i, nullptr); }
+        }
+    }
     if (threadIdx.x < 64) {
         const int ch = threadIdx.x;
         bn_fwd_final(fl.bn, ch, s_st[0][ch], s_st[1][ch]);
@@ -191,64 +236,54 @@ __global__ void __launch_bounds__(256) k_stage_combine_last(const Ctrl* __restri
         mdy[k] = MODE == 2 ? s_st[2][c0 + k] : 0.f; mdyxh[k] = MODE == 2 ? s_st[3][c0 + k] : 0.f;
         kk[k] = __fmul_rn(ga[k], inv[k]);
     }
-    const float* __restrict__ xin = MODE == 1 ? resolve(fl.x) : yw;
-    const float* __restrict__ gin = MODE == 2 ? resolve(fl.g) : nullptr;
-    const float* __restrict__ yin = MODE == 2 ? resolve(fl.y) : nullptr;
-    double s1[4] = {0, 0, 0, 0}, s2[4] = {0, 0, 0, 0};
-    const long long step = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < bf.nz4; i += step) {
-        const float4 xv = ld4(xin, i);
+    // MODE 2: K value of the a block (the first BatchNorm's backward dx) and the a block of the stage state
+    auto a_part = [&](long long i, const float4 xv) {
         const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+        const float4 gv = ld4(gin, i), yv = ld4(yin, i);
+        const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w};
         float kl[4];
-        if (MODE == 1) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) kl[k] = act_fwd(fl.act, __fadd_rn(__fmul_rn(ga[k], __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k])), be[k]));
-            st4(klast, i, make_float4(kl[0], kl[1], kl[2], kl[3]));
-        } else {
-            const float4 gv = ld4(gin, i), yv = ld4(yin, i);
-            const float gg[4] = {gv.x, gv.y, gv.z, gv.w}, yy[4] = {yv.x, yv.y, yv.z, yv.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float dy = act_bwd(fl.act, yy[k], __fmul_rn(fl.gscale, gg[k]));
-                const float xh = __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k]);
-                kl[k] = __fmul_rn(kk[k], __fsub_rn(__fsub_rn(dy, mdy[k]), __fmul_rn(xh, mdyxh[k])));
-            }
-            st4(klast, fl.a4 + i, make_float4(kl[0], kl[1], kl[2], kl[3]));
+        for (int k = 0; k < 4; ++k) {
+            const float dy = act_bwd(fl.act, yy[k], __fmul_rn(fl.gscale, gg[k]));
+            const float xh = __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k]);
+            kl[k] = __fmul_rn(kk[k], __fsub_rn(__fsub_rn(dy, mdy[k]), __fmul_rn(xh, mdyxh[k])));
         }
-        // z block
-        const float4 yv0 = ld4(y, i);
-        float4 k0 = ld4(kr[0], i);
+        const long long ia = fl.a4 + i;
+        st4(klast, ia, make_float4(kl[0], kl[1], kl[2], kl[3]));
+        const float4 ya = ld4(y, ia);
+        const float4 k0 = ld4(kr[0], ia);
         float4 acc = make_float4(__fmul_rn(coef[0], k0.x), __fmul_rn(coef[0], k0.y), __fmul_rn(coef[0], k0.z), __fmul_rn(coef[0], k0.w));
 #pragma unroll
         for (int j = 1; j < S; ++j) {
-            if (S == 6 && j == 1) continue;   // a_62 == 0
-            const float4 kj = (MODE == 1 && j == S - 1) ? make_float4(kl[0], kl[1], kl[2], kl[3]) : ld4(kr[j], i);
+            if (S == 6 && j == 1) continue;
+            const float4 kj = j == S - 1 ? make_float4(kl[0], kl[1], kl[2], kl[3]) : ld4(kr[j], ia);
             acc.x = __fmaf_rn(coef[j], kj.x, acc.x);
             acc.y = __fmaf_rn(coef[j], kj.y, acc.y);
             acc.z = __fmaf_rn(coef[j], kj.z, acc.z);
             acc.w = __fmaf_rn(coef[j], kj.w, acc.w);
         }
-        const float4 o = make_float4(__fadd_rn(yv0.x, acc.x), __fadd_rn(yv0.y, acc.y), __fadd_rn(yv0.z, acc.z), __fadd_rn(yv0.w, acc.w));
-        st4(yw, i, o);
-        s1[0] += (double)o.x; s2[0] += (double)o.x * (double)o.x;
-        s1[1] += (double)o.y; s2[1] += (double)o.y * (double)o.y;
-        s1[2] += (double)o.z; s2[2] += (double)o.z * (double)o.z;
-        s1[3] += (double)o.w; s2[3] += (double)o.w * (double)o.w;
-        if (MODE == 2) {      // a block
-            const long long ia = fl.a4 + i;
-            const float4 ya = ld4(y, ia);
-            k0 = ld4(kr[0], ia);
-            acc = make_float4(__fmul_rn(coef[0], k0.x), __fmul_rn(coef[0], k0.y), __fmul_rn(coef[0], k0.z), __fmul_rn(coef[0], k0.w));
+        st4(yw, ia, make_float4(__fadd_rn(ya.x, acc.x), __fadd_rn(ya.y, acc.y), __fadd_rn(ya.z, acc.z), __fadd_rn(ya.w, acc.w)));
+    };
+    if (MODE == 1) {
+        for (long long i = i_first; i < bf.nz4; i += step) {
+            const float4 xv = ld4(xin, i);
+            const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+            float kl[4];
 #pragma unroll
-            for (int j = 1; j < S; ++j) {
-                if (S == 6 && j == 1) continue;
-                const float4 kj = j == S - 1 ? make_float4(kl[0], kl[1], kl[2], kl[3]) : ld4(kr[j], ia);
-                acc.x = __fmaf_rn(coef[j], kj.x, acc.x);
-                acc.y = __fmaf_rn(coef[j], kj.y, acc.y);
-                acc.z = __fmaf_rn(coef[j], kj.z, acc.z);
-                acc.w = __fmaf_rn(coef[j], kj.w, acc.w);
-            }
-            st4(yw, ia, make_float4(__fadd_rn(ya.x, acc.x), __fadd_rn(ya.y, acc.y), __fadd_rn(ya.z, acc.z), __fadd_rn(ya.w, acc.w)));
+            for (int k = 0; k < 4; ++k) kl[k] = act_fwd(fl.act, __fadd_rn(__fmul_rn(ga[k], __fmul_rn(__fsub_rn(xx[k], mean[k]), inv[k])), be[k]));
+            st4(klast, i, make_float4(kl[0], kl[1], kl[2], kl[3]));
+            z_part(i, kl);
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < ZIT; ++it) {
+            const long long i = i_first + it * step;
+            if (i < bf.nz4) a_part(i, xs[it]);
+        }
+        for (long long i = i_first + ZIT * step; i < bf.nz4; i += step) {      // states longer than ZIT items per thread: x, then z, then a
+            const float4 xv = ld4(xin, i);
+            z_part(i, nullptr);
+            a_part(i, xv);
         }
     }
     // statistics of the first BatchNorm for the evaluation that follows: accumulate only (deferred statistics, BnScratch)
