@@ -207,23 +207,37 @@ __device__ __forceinline__ float4 comm_ll_allreduce4(const CommDev* cm, unsigned
             dst[1] = c23;
         }
     }
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < W; ++q) {
-        float4 u = v;
-        if (q != me) {
-            const unsigned long long* src = reinterpret_cast<const unsigned long long*>(cm->peer[me] + cm->xll_off +
-                                                                                        ((long long)(par * COMM_MAX_WORLD + q) * cm->xll_cap + i) * 8);
-            unsigned long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-            bool ok = false;
-            for (unsigned int spin = 0; spin < (1u << 26); ++spin) {
-                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a0), "=l"(a1) : "l"(src) : "memory");
-                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a2), "=l"(a3) : "l"(src + 2) : "memory");
-                if ((unsigned int)(a0 >> 32) == tag && (unsigned int)(a1 >> 32) == tag && (unsigned int)(a2 >> 32) == tag && (unsigned int)(a3 >> 32) == tag) { ok = true; break; }
-                if ((spin & 255) == 255) __nanosleep(32);
+    // the cells of ALL peers are requested before the first tag is looked at: one L2 round trip per attempt whatever the number of ranks
+    // (peer after peer it was seven dependent round trips at eight ranks, by 9216 threads spinning beside the main chain's convolutions)
+    const unsigned long long* base = reinterpret_cast<const unsigned long long*>(cm->peer[me] + cm->xll_off);
+    unsigned long long a[COMM_MAX_WORLD][4];
+    bool ok = false;
+    for (unsigned int spin = 0; spin < (1u << 26) && !ok; ++spin) {
+        ok = true;
+#pragma unroll
+        for (int q = 0; q < COMM_MAX_WORLD; ++q) {
+            if (q < W && q != me) {
+                const unsigned long long* src = base + ((long long)(par * COMM_MAX_WORLD + q) * cm->xll_cap + i);
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a[q][0]), "=l"(a[q][1]) : "l"(src) : "memory");
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a[q][2]), "=l"(a[q][3]) : "l"(src + 2) : "memory");
             }
-            if (!ok) const_cast<CommDev*>(cm)->status = 1;
-            u = make_float4(__uint_as_float((unsigned int)a0), __uint_as_float((unsigned int)a1), __uint_as_float((unsigned int)a2), __uint_as_float((unsigned int)a3));
         }
+#pragma unroll
+        for (int q = 0; q < COMM_MAX_WORLD; ++q)
+            if (q < W && q != me &&
+                ((unsigned int)(a[q][0] >> 32) != tag || (unsigned int)(a[q][1] >> 32) != tag || (unsigned int)(a[q][2] >> 32) != tag || (unsigned int)(a[q][3] >> 32) != tag))
+                ok = false;
+        if (!ok && (spin & 15) == 15) __nanosleep(64);
+    }
+    if (!ok) const_cast<CommDev*>(cm)->status = 1;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < COMM_MAX_WORLD; ++q) {
+        if (q >= W) continue;
+        float4 u = v;
+        if (q != me)
+            u = make_float4(__uint_as_float((unsigned int)a[q][0]), __uint_as_float((unsigned int)a[q][1]), __uint_as_float((unsigned int)a[q][2]),
+                            __uint_as_float((unsigned int)a[q][3]));
         t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
     }
     return t;
