@@ -11,7 +11,9 @@
 // Layer arithmetic is DL4J's (third party in the reference); conventions as restated in oracle/outer_oracle.py, which this file is
 // checked against (tests/test_outer_net.py).  Tensors are NCHW fp32; every reduction accumulates exact fp32 products in double and
 // rounds once, elementwise expressions keep the oracle's order (no FMA contraction), so the two agree to rounding.
-// These layers are NOT the hot path (about 13 GFLOP per step next to the ODE block's ~250): plain direct kernels, no tensor cores.
+// Two data paths: the EXACT path in this file (any channel count; always in parity mode) — plain direct CUDA-core kernels, every
+// reduction in double — and, for the reference's 64 kernels in the default mode, the FAST path of outer_net_tc.cuh (NHWC, the stem's
+// 64 -> 64 convolutions on the block's tcgen05 kernels), which OuterNet::train_step / output dispatch to (tc_).
 #pragma once
 
 #include <algorithm>
@@ -397,6 +399,7 @@ private:
         int Hin, Hout;
     };
     void forward(const float* p, const float* images, const float* labels, bool train, n4j_stats* ode_fwd);
+    void backward(n4j_stats* ode_bwd);
     float* dev_alloc(long long n);
     void conv_fwd(const float* x, const float* w, const float* bias, float* y, const ConvShape& c, int relu);
     void conv_dgrad(const float* dy, const float* y, const float* w, float* dx, const ConvShape& c, int relu);
@@ -606,6 +609,44 @@ inline void OuterNet::output(const float* params, const float* images, float* pr
     N4J_CUDA(cudaStreamSynchronize(s_));
 }
 
+// backward of the exact path (NCHW, exact-accumulation CUDA-core kernels): gradient view g_ filled from the activations forward() left behind
+inline void OuterNet::backward(n4j_stats* ode_bwd) {
+    const int C = C_, B = B_;
+    // ---- backward --------------------------------------------------------------------------------------------------------------
+    const long long nz = (long long)B * C * 49;
+    k_outer_output_bwd<<<1, 256, 0, s_>>>(pool_, p_ + off_ow_, probs_, lab_, score_parts_, g_ + off_ow_, g_ + off_ob_, dpool_, score_, B, C);
+    k_outer_pool_bwd<<<grid(nz), 256, 0, s_>>>(dpool_, d1_, nz, 49);
+    k_outer_bn_bwd<<<C, 256, 0, s_>>>(z1_, no_, d1_, p_ + off_bno_, sto_, d2_, g_ + off_bno_, B, C, 49, 1, 0.1f);
+    N4J_CUDA(cudaGetLastError());
+    // the adjoint solve: continues the forward of this handle (lastOutput stays on the device), gradient view slice seeded (zero) and written in place
+    ode_->backward(nullptr, d2_, time_, 2, N4J_TIMEGRAD_NONE, g_ + off_ode_, d1_, nullptr, ode_bwd);
+    float* da = d1_;              // dL/d(stem output)
+    float* t1 = d2_;
+    float* t2 = d3_;
+    for (int r = 1; r >= 0; --r) {
+        Block& b = blk_[r];
+        const float* a_in = r == 0 ? a0_ : blk_[0].a_out;
+        const int HWi = b.Hin * b.Hin, HWo = b.Hout * b.Hout;
+        const long long nin = (long long)B * C * HWi;
+        // secondConv (identity): weight gradient, then dL/dn2 into t1
+        conv_wgrad(b.n2, da, b.f2, g_ + b.o_c2, nullptr, b.c2, 0);
+        conv_dgrad(da, b.f2, p_ + b.o_c2, t1, b.c2, 0);
+        // secondNorm: dL/df1 into t2
+        k_outer_bn_bwd<<<C, 256, 0, s_>>>(b.f1, b.n2, t1, p_ + b.o_bn2, b.st2, t2, g_ + b.o_bn2, B, C, HWo, 1, 0.1f);
+        // firstConv (ReLU) and downSample (identity) both read n1: dL/dn1 = downSample's epsilon + firstConv's epsilon
+        conv_wgrad(b.n1, t2, b.f1, g_ + b.o_c1, nullptr, b.c1, 1);
+        conv_wgrad(b.n1, da, b.dsy, g_ + b.o_ds, nullptr, b.ds, 0);
+        conv_dgrad(t2, b.f1, p_ + b.o_c1, t1, b.c1, 1);             // t1: firstConv's epsilon  [B,C,Hin,Hin]
+        conv_dgrad(da, b.dsy, p_ + b.o_ds, t2, b.ds, 0);            // t2: downSample's epsilon
+        k_outer_add<<<grid(nin), 256, 0, s_>>>(t2, t1, t1, nin);
+        // firstNorm: dL/d(block input) into da's next buffer
+        k_outer_bn_bwd<<<C, 256, 0, s_>>>(a_in, b.n1, t1, p_ + b.o_bn1, b.st1, t2, g_ + b.o_bn1, B, C, HWi, 1, 0.1f);
+        std::swap(da, t2);
+        // keep three distinct buffers: da (new epsilon), t1, t2 (scratch)
+    }
+    conv_wgrad(img_, da, a0_, g_ + off_in_w_, g_ + off_in_b_, cin_, 0);
+}
+
 inline void OuterNet::train_step(float* params, float* updater_state, const float* images, const float* labels, float lr, float mu, float* score,
                                  float* grad_out, n4j_stats* ode_fwd, n4j_stats* ode_bwd) {
     N4J_CUDA(cudaSetDevice(device_));
@@ -632,45 +673,11 @@ inline void OuterNet::train_step(float* params, float* updater_state, const floa
         backward_tc(img_, ode_bwd);
         phase("backward");
     } else {
-    ode_->set_nhwc_io(false);
-    forward(p_, img_, lab_, true, ode_fwd);
-    phase("forward (stem, block, output)");
-    // ---- backward --------------------------------------------------------------------------------------------------------------
-    const long long nz = (long long)B * C * 49;
-    k_outer_output_bwd<<<1, 256, 0, s_>>>(pool_, p_ + off_ow_, probs_, lab_, score_parts_, g_ + off_ow_, g_ + off_ob_, dpool_, score_, B, C);
-    k_outer_pool_bwd<<<grid(nz), 256, 0, s_>>>(dpool_, d1_, nz, 49);
-    k_outer_bn_bwd<<<C, 256, 0, s_>>>(z1_, no_, d1_, p_ + off_bno_, sto_, d2_, g_ + off_bno_, B, C, 49, 1, 0.1f);
-    N4J_CUDA(cudaGetLastError());
-    // the adjoint solve: continues the forward of this handle (lastOutput stays on the device), gradient view slice seeded (zero) and written in place
-    phase("output block backward");
-    ode_->backward(nullptr, d2_, time_, 2, N4J_TIMEGRAD_NONE, g_ + off_ode_, d1_, nullptr, ode_bwd);
-    phase("ODE block adjoint");
-    float* da = d1_;              // dL/d(stem output)
-    float* t1 = d2_;
-    float* t2 = d3_;
-    for (int r = 1; r >= 0; --r) {
-        Block& b = blk_[r];
-        const float* a_in = r == 0 ? a0_ : blk_[0].a_out;
-        const int HWi = b.Hin * b.Hin, HWo = b.Hout * b.Hout;
-        const long long nin = (long long)B * C * HWi;
-        // secondConv (identity): weight gradient, then dL/dn2 into t1
-        conv_wgrad(b.n2, da, b.f2, g_ + b.o_c2, nullptr, b.c2, 0);
-        conv_dgrad(da, b.f2, p_ + b.o_c2, t1, b.c2, 0);
-        // secondNorm: dL/df1 into t2
-        k_outer_bn_bwd<<<C, 256, 0, s_>>>(b.f1, b.n2, t1, p_ + b.o_bn2, b.st2, t2, g_ + b.o_bn2, B, C, HWo, 1, 0.1f);
-        // firstConv (ReLU) and downSample (identity) both read n1: dL/dn1 = downSample's epsilon + firstConv's epsilon
-        conv_wgrad(b.n1, t2, b.f1, g_ + b.o_c1, nullptr, b.c1, 1);
-        conv_wgrad(b.n1, da, b.dsy, g_ + b.o_ds, nullptr, b.ds, 0);
-        conv_dgrad(t2, b.f1, p_ + b.o_c1, t1, b.c1, 1);             // t1: firstConv's epsilon  [B,C,Hin,Hin]
-        conv_dgrad(da, b.dsy, p_ + b.o_ds, t2, b.ds, 0);            // t2: downSample's epsilon
-        k_outer_add<<<grid(nin), 256, 0, s_>>>(t2, t1, t1, nin);
-        // firstNorm: dL/d(block input) into da's next buffer
-        k_outer_bn_bwd<<<C, 256, 0, s_>>>(a_in, b.n1, t1, p_ + b.o_bn1, b.st1, t2, g_ + b.o_bn1, B, C, HWi, 1, 0.1f);
-        std::swap(da, t2);
-        // keep three distinct buffers: da (new epsilon), t1, t2 (scratch)
-    }
-    conv_wgrad(img_, da, a0_, g_ + off_in_w_, g_ + off_in_b_, cin_, 0);
-    phase("stem backward");
+        ode_->set_nhwc_io(false);
+        forward(p_, img_, lab_, true, ode_fwd);
+        phase("forward (stem, block, output)");
+        backward(ode_bwd);
+        phase("backward");
     }
     // ---- update ----------------------------------------------------------------------------------------------------------------
     if (grad_out) N4J_CUDA(cudaMemcpyAsync(grad_out, g_, sizeof(float) * n_, cudaMemcpyDefault, s_));
