@@ -60,6 +60,11 @@ final class Node4j {
     static final StructLayout STEP_REC = MemoryLayout.structLayout(
             JAVA_FLOAT.withName("t"), JAVA_FLOAT.withName("h"), JAVA_FLOAT.withName("err"), JAVA_INT.withName("accepted"), JAVA_INT.withName("solve"));
 
+    /** n4j_net_desc: the whole MNIST ODE-net behind node4j_net_* (batch, nrofKernels, the block's solver, its FixedStep time) */
+    static final StructLayout NET_DESC = MemoryLayout.structLayout(
+            JAVA_INT.withName("batch"), JAVA_INT.withName("channels"), CFG.withName("solver"),
+            JAVA_FLOAT.withName("t0"), JAVA_FLOAT.withName("t1"));
+
     private static MethodHandle h(String name, FunctionDescriptor d) {
         return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), d);
     }
@@ -79,6 +84,14 @@ final class Node4j {
     static final MethodHandle GET_STEP_LOG = h("node4j_get_step_log", FunctionDescriptor.of(JAVA_LONG, ADDRESS, ADDRESS, JAVA_LONG));
     static final MethodHandle COMM_EXPORT = h("node4j_comm_export", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS));
     static final MethodHandle COMM_INIT = h("node4j_comm_init", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, JAVA_INT, ADDRESS, JAVA_LONG));
+    // the network around the block (SURVEY.md section 8, row f3): what ComputationGraph.fit / output do for examples.mnist.OdeNetModel
+    static final MethodHandle NET_CREATE = h("node4j_net_create", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT, ADDRESS));
+    static final MethodHandle NET_DESTROY = h("node4j_net_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    static final MethodHandle NET_NUM_PARAMS = h("node4j_net_num_params", FunctionDescriptor.of(JAVA_LONG, ADDRESS));
+    static final MethodHandle NET_ODE_SLICE = h("node4j_net_ode_slice", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle NET_TRAIN_STEP = h("node4j_net_train_step",
+            FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_FLOAT, JAVA_FLOAT, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    static final MethodHandle NET_OUTPUT = h("node4j_net_output", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT));
 
     static {
         try {

@@ -289,3 +289,10 @@ def test_java_shim_matches_header():
     assert _lib.GraphDesc.layers.offset == 40 and "g.set(ADDRESS, 40, layers)" in helper
     assert _lib.SolverCfg.order.offset == 56 and _lib.SolverCfg.flags.offset == 60 and _lib.SolverCfg.max_trials.offset == 64
     assert ctypes.sizeof(_lib.StepRec) == 20 and "i * 20 + 16" in helper
+    # the network entry points: NET_DESC nests the solver configuration; NativeOdeNet writes it at the ctypes offsets
+    net = open(os.path.join(ROOT, "java", "src", "main", "java", "ode", "vertex", "impl", "helper", "nativeb200", "NativeOdeNet.java")).read()
+    assert 'CFG.withName("solver")' in java
+    assert _lib.NetDesc.solver.offset == 8 and _lib.NetDesc.t0.offset == 80 and _lib.NetDesc.t1.offset == 84 and ctypes.sizeof(_lib.NetDesc) == 88
+    assert "d.set(JAVA_DOUBLE, 8, absTol)" in net and "d.set(JAVA_INT, 68, flags)" in net and "d.set(JAVA_LONG, 72, 0L)" in net
+    assert "d.set(JAVA_FLOAT, 80, 0f)" in net and "d.set(JAVA_FLOAT, 84, 1f)" in net
+    assert _lib.Stats.accepted.offset == 8 and "fwdStats.get(JAVA_LONG, 8)" in net
