@@ -825,6 +825,7 @@ inline void OuterNet::forward_tc(const float* p, const float* images, const floa
 inline void OuterNet::backward_tc(const float* images, n4j_stats* ode_bwd) {
     const int B = B_, C = 64;
     const long long rz = (long long)B * 49;
+    set_tc_attributes();      // (an Engine constructed since forward_tc would have lowered the shared limits again)
     k_on_output_bwd<<<(704 + B * 64 + 255) / 256, 256, 0, s_>>>(pool_, p_ + off_ow_, probs_, lab_, score_parts_, g_ + off_ow_, g_ + off_ob_, dpool_, score_, B);
     k_on_pool_bwd<<<grid(rz * 64), 256, 0, s_>>>(dpool_, dA_, rz * 64, 49);
     k_on_bn_bwd_stats<<<grid_rows(rz), 256, 0, s_>>>(z1n_, non_, dA_, acco_, rz, 1e-5f);
