@@ -127,8 +127,21 @@ struct ConvTcArgs {
 // operand loads of ALL warps (measured: the loads were issued 2700 cycles after kernel entry instead of ~1000).
 template <int PRO>
 __device__ __noinline__ void conv_finalize_stats(double r0, double r1, double r2, double r3, long long rows, float eps, float (*s_fin)[64],
-                                                  float* dgamma, float* dbeta) {      // everything by value: no local copy of the kernel arguments
+                                                  float* dgamma, float* dbeta, int fast, double inv_rows) {      // everything by value: no local copy of the kernel arguments
     const int c = threadIdx.x;
+    if (fast) {      // default mode: the forms of bn_fwd_final / bn_bwd_final with fast_final (layer_kernels.cuh: BnScratch)
+        const double m = r0 * inv_rows;
+        double var = r1 * inv_rows - m * m;
+        if (var < 0) var = 0;
+        s_fin[0][c] = (float)m;
+        s_fin[1][c] = (float)rsqrt(var + (double)eps);
+        if (PRO == 2) {
+            s_fin[2][c] = (float)(r2 * inv_rows);
+            s_fin[3][c] = (float)(r3 * inv_rows);
+            if (dgamma) { dgamma[c] = (float)r3; dbeta[c] = (float)r2; }
+        }
+        return;
+    }
     const double M = (double)rows;
     const double m = r0 / M;
     double var = r1 / M - m * m;
@@ -292,7 +305,8 @@ __global__ void __launch_bounds__(conv_tc_threads(PRO), 1) k_conv3x3_tc(ConvTcAr
                 }
                 if (warp < 2)
                     conv_finalize_stats<PRO>(raw[0], raw[1], raw[2], raw[3], (SH && a.pbn.cm) ? a.pbn.rows_total : a.pbn.rows, a.pbn.eps, s_fin,
-                                             (PRO == 2 && blockIdx.x == 0) ? resolve(a.pdgamma) : nullptr, (PRO == 2 && blockIdx.x == 0) ? resolve(a.pdbeta) : nullptr);
+                                             (PRO == 2 && blockIdx.x == 0) ? resolve(a.pdgamma) : nullptr, (PRO == 2 && blockIdx.x == 0) ? resolve(a.pdbeta) : nullptr,
+                                             a.pbn.fast_final, a.pbn.inv_rows);
                 __syncthreads();
                 if (threadIdx.x == 0) conv_stamp(a, 3);
 #pragma unroll

@@ -301,6 +301,8 @@ Engine::Engine(const n4j_graph_desc& g, const n4j_solver_cfg& cfg, int device) :
             N4J_CUDA(cudaMalloc(&f, sizeof(float) * 4 * cc));
             l.bn.mean = f; l.bn.invstd = f + cc; l.bn.m_dy = f + 2 * cc; l.bn.m_dyxh = f + 3 * cc;
             l.bn.eps = l.d.eps; l.bn.rows = l.rows;
+            l.bn.fast_final = (exact_ || getenv("N4J_EXACT_BN_FINAL")) ? 0 : 1;     // parity mode keeps the oracle's divisions (env: A/B switch)
+            l.bn.inv_rows = 1.0 / (double)l.rows;
             l.bn_deferred_ok = (cc == 64) && !(cfg_.flags & N4J_FLAG_NO_DEFERRED_STATS);
             if (l.bn_deferred_ok) ++n_def;
         }
@@ -1296,6 +1298,7 @@ void Engine::comm_init(int rank, int world, const void* handles, long long globa
         for (auto& l : L_) {
             if (l.d.kind != N4J_LAYER_BATCHNORM) continue;
             l.bn.cm = comm_dev_; l.bn.rows_total = l.rows * world;
+            l.bn.inv_rows = 1.0 / (double)l.bn.rows_total;
             if (mgpu_deferred_ && l.bn_deferred_ok && l.bn_pool && l.bn_mb >= 0) {
                 // sharded deferred statistics: producers accumulate local sums only, consumers exchange and finalise (layer_kernels.cuh: BnScratch)
                 l.bn.deferred = 1;

@@ -224,6 +224,13 @@ struct BnScratch {
     // The tag is the number of times the set has been produced: its producer kernel bumps the counter (block 0), all ranks run the
     // same kernel sequence, consumers start after the producer finished (stream order).  Pushing is idempotent (later consumers of
     // the same set repeat it with the same values).
+    // Default mode only (fast_final != 0; the parity mode keeps the divisions, which are the oracle's): the consumers' finalisation multiplies by
+    // the precomputed 1 / rows and takes rsqrt() instead of 1 / sqrt() — double-precision division and square root are long dependent
+    // instruction sequences on this part's slow FP64 pipe, and the finalisation sits between a consumer's operand loads and their first use.
+    // The results differ from the exact forms in the last bit of a DOUBLE, i.e. the floats are the same up to rare rounding ties; every
+    // consumer of a set goes through the same two functions (bn_fwd_final / bn_bwd_final, conv_finalize_stats), so they agree with each other.
+    int fast_final;
+    double inv_rows;        // 1 / rows, or 1 / rows_total on the sharded path
     unsigned int* seqf;     // sequence counters of THIS evaluation's forward / backward set (device memory of this rank)
     unsigned int* seqb;
     long long mbf, mbb;     // byte offsets inside a comm region of the two sets' mailboxes: cell[source rank][128], 16 bytes each
@@ -317,6 +324,14 @@ __device__ __forceinline__ void bn_fwd_final(const BnScratch& sc, int c, float& 
         bn_gather2<BATCH>(sc.cm, sc.mbf, tag, c, s0, s1);
         M = (double)sc.rows_total;
     }
+    if (sc.fast_final) {
+        const double m = s0 * sc.inv_rows;
+        double var = s1 * sc.inv_rows - m * m;
+        if (var < 0) var = 0;
+        mean = (float)m;
+        inv = (float)rsqrt(var + (double)sc.eps);
+        return;
+    }
     const double m = s0 / M;
     double var = s1 / M - m * m;
     if (var < 0) var = 0;
@@ -334,6 +349,7 @@ __device__ __forceinline__ void bn_bwd_final(const BnScratch& sc, int c, float& 
     }
     dgamma = (float)sdyxh;
     dbeta = (float)sdy;
+    if (sc.fast_final) { m_dy = (float)(sdy * sc.inv_rows); m_dyxh = (float)(sdyxh * sc.inv_rows); return; }
     m_dy = (float)(sdy / M);
     m_dyxh = (float)(sdyxh / M);
 }
