@@ -111,7 +111,7 @@ class StepListener:
 
     The native solve runs on the device without host callbacks; listeners are replayed from the device step log
     after each integrate call, once per ACCEPTED step (rejected steps are invisible, as in the reference).  The
-    replayed ``solverState`` exposes ``time()`` only.
+    replayed ``solverState`` exposes ``time()`` and ``getInterpolationMidpoints()``; the state accessors raise.
     """
 
     def begin(self, t, y0): ...
@@ -120,11 +120,28 @@ class StepListener:
 
 
 class _ReplayState:
+    """ode.solve.impl.util.SolverState as the replayed listeners see it (the Java shim's ReplayedSolverState): time and the solver's
+    dense-output midpoint coefficients are available; the state vectors stay on the device, so their accessors raise (the reference's
+    listeners that only look at time / step / error — StepCounter, Mask, the plotting listeners — work unchanged)."""
+
+    # DormandPrince54Solver.java:44-47 (cMid); the device-side dense output uses the same coefficients
+    _C_MID = (6025192743.0 / 30085553152.0 / 2.0, 0.0, 51252292925.0 / 65400821598.0 / 2.0, -2691868925.0 / 45128329728.0 / 2.0,
+              187940372067.0 / 1594534317056.0 / 2.0, -1776094331.0 / 19743644256.0 / 2.0, 11237099.0 / 235043384.0 / 2.0)
+
     def __init__(self, t):
         self._t = t
 
     def time(self):
         return self._t
+
+    def getInterpolationMidpoints(self):
+        return list(self._C_MID)
+
+    def getCurrentState(self):
+        raise NotImplementedError("native ODE helper: the solver state stays on the device (UnsupportedOperationException in the Java shim)")
+
+    def getStateDot(self, stage):
+        raise NotImplementedError("native ODE helper: stage derivatives stay on the device (UnsupportedOperationException in the Java shim)")
 
 
 class DormandPrince54Solver:

@@ -160,6 +160,24 @@ def test_step_counter_and_mask_semantics():
     assert got == [(7, 2)]
 
 
+def test_replayed_solver_state_surface():
+    """The SolverState the replayed listeners get (ode/solve/impl/util/SolverState.java): time, the DP54 dense-output midpoint coefficients
+    (DormandPrince54Solver.java:44-47 — the same numbers the Java shim's ReplayedSolverState returns), and state accessors that raise."""
+    import re
+    from neuralode4j_b200.conf import _ReplayState
+    st = _ReplayState(0.25)
+    assert st.time() == 0.25
+    mid = st.getInterpolationMidpoints()
+    assert len(mid) == 7 and mid[1] == 0.0 and abs(sum(mid) - 0.5) < 1e-12        # the midpoint weights sum to c = 1/2
+    java = open(os.path.join(ROOT, "java", "src", "main", "java", "ode", "vertex", "impl", "helper", "nativeb200", "ReplayedSolverState.java")).read()
+    nums = re.search(r"new double\[\]\{(.*?)\};", java, flags=re.S).group(1)
+    jvals = [eval(x.replace("d", "")) for x in nums.replace("\n", " ").split(",")]
+    np.testing.assert_allclose(jvals, mid, rtol=1e-15)
+    for call in (st.getCurrentState, lambda: st.getStateDot(0)):
+        with pytest.raises(NotImplementedError):
+            call()
+
+
 def test_workload_shapes():
     w = W.mnist_block()
     assert w.shape == (128, 64, 7, 7) and int(np.prod(w.shape)) == 401408
