@@ -113,6 +113,31 @@ def test_outer_oracle_matches_torch_autograd(C, B):
     np.testing.assert_allclose(out["params"][~noop], p_new[~noop], rtol=1e-3, atol=1e-6)
 
 
+@pytest.mark.parametrize("H", [26, 13])
+def test_stride2_convolution_as_full_resolution_stride1(H):
+    """The formulation the fast path runs the stem's stride-2 convolutions in (outer_net_tc.cuh), checked on the CPU with the oracle's own
+    convolution: a 3x3 stride-2 ConvolutionMode.Same convolution equals the stride-1 "same" convolution of the full-resolution map sampled
+    at h = 2*oh + 1 - pad_top (26 -> 13: pad_top 0, odd pixels; 13 -> 7: pad_top 1, even pixels); its input gradient and weight gradient
+    equal the stride-1 ones of the gradient scattered to those pixels of a zero full-resolution map."""
+    rng = np.random.default_rng(H)
+    B, C = 2, 5
+    x = rng.standard_normal((B, C, H, H)).astype(np.float32)
+    w = (0.2 * rng.standard_normal((C, C, 3, 3))).astype(np.float32)
+    y2, pad2 = OO.conv_fwd(x, w, None, 2, True, False)
+    y1, pad1 = OO.conv_fwd(x, w, None, 1, True, False)
+    Ho = y2.shape[2]
+    off = 1 - pad2[0]
+    assert pad1 == (1, 1) and Ho == (H + 1) // 2 and off == (1 if H == 26 else 0)
+    np.testing.assert_array_equal(y2, y1[:, :, off::2, off::2][:, :, :Ho, :Ho])
+    dy = rng.standard_normal(y2.shape).astype(np.float32)
+    dx2, dw2, _ = OO.conv_bwd(x, w, y2, dy, 2, pad2, False, False)
+    up = np.zeros_like(y1)
+    up[:, :, off::2, off::2][:, :, :Ho, :Ho] = dy
+    dx1, dw1, _ = OO.conv_bwd(x, w, y1, up, 1, pad1, False, False)
+    np.testing.assert_array_equal(dx2, dx1)
+    np.testing.assert_allclose(dw2, dw1, rtol=1e-6, atol=1e-6)
+
+
 # ---------------------------------------------------------------------------------------------------------------------------
 # GPU: node4j_net_train_step against the oracle (outer layers in numpy, the ODE block on oracle/node_oracle.cpp)
 # ---------------------------------------------------------------------------------------------------------------------------
