@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnode4j_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "solver_kernels.cuh", "layer_kernels.cuh", "tc_common.cuh", "conv_tc.cuh", "conv_wgrad_tc.cuh", "gemm_tc.cuh", "mlp_small.cuh", "outer_net.cuh", "engine.cuh", "../../include/node4j.h"]
+HEADERS = ["common.cuh", "solver_kernels.cuh", "layer_kernels.cuh", "tc_common.cuh", "conv_tc.cuh", "conv_wgrad_tc.cuh", "gemm_tc.cuh", "mlp_small.cuh", "outer_net.cuh", "outer_net_tc.cuh", "engine.cuh", "../../include/node4j.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--fmad=true",
