@@ -304,11 +304,10 @@ class Bench:
             raise SystemExit("bench.py needs a CUDA device: the node4j engine has no CPU fallback")
         torch.cuda.set_device(self.local_rank)
         if self.world > 1:
-            # the contract is ONE line on stdout: NCCL prints "NCCL version ..." there at NCCL_DEBUG=VERSION *and* WARN (the boxes export
-            # VERSION).  A value NCCL does not know switches its logging off; anything a user asked for explicitly (INFO, TRACE) goes to stderr.
+            # the contract is ONE line on stdout: NCCL prints "NCCL version ..." there at NCCL_DEBUG=VERSION *and* WARN (some boxes export
+            # VERSION).  A value NCCL does not know switches its logging off; INFO / TRACE stay what the user asked for.
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
                 os.environ["NCCL_DEBUG"] = "NONE"
-            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
         self.dev = torch.device("cuda", self.local_rank)
         self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
