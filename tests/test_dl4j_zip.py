@@ -114,3 +114,61 @@ def test_unsupported_inner_layers_raise():
     ode["conf"]["vertices"]["convFirst"] = _layer_vertex({"@class": "org.deeplearning4j.nn.conf.layers.LSTM", "nin": 4, "nout": 4})
     with pytest.raises(NotImplementedError):
         Z.ode_vertex_from_dl4j(ode)
+
+
+def test_odenet_configuration_matches_the_native_layout(tmp_path):
+    """`net.odenet_configuration` (the configuration.json of a checkpoint of the reference's MNIST ODE-net, as this package reads it) against
+    the flat layout node4j_net_* uses (oracle/outer_oracle.py: OuterLayout, checked against the device in tests/test_outer_net.py): every
+    parameterised vertex sits at the same offset with the same length, downSample in front of firstConvStem (insertion-order tie-break of the
+    topological sort), the OdeVertex JSON parses into the native configuration, and OdeNetModel.save / load round-trip through the zip."""
+    from neuralode4j_b200.net import OdeNetModel, odenet_configuration
+    from oracle import outer_oracle as OO
+    for C in (8, 64):
+        conf = odenet_configuration(C)
+        n_ode = 3 * 4 * C + 2 * C * C * 9
+        L = OO.OuterLayout(C, n_ode)
+        order = [n for n in Z.topological_order(conf) if n in conf["vertices"]]
+        assert order.index("downSample_0") < order.index("firstConvStem_0") < order.index("secondNormStem_0") < order.index("stemAdd_0")
+        off, got = 0, {}
+        for name in order:
+            n = Z.vertex_num_params(conf["vertices"][name])
+            got[name] = (off, n)
+            off += n
+        assert off == L.n
+        assert Z.ode_block_slices(conf) == {"odeBlock": L.slices["ode"]}
+        want = {"inputConv": (L.slices["inputConv.b"][0], 10 * C), "normOutput": L.slices["normOutput"], "output": (L.slices["output.W"][0], 10 * C + 10)}
+        for r in (0, 1):
+            want.update({f"firstNormStem_{r}": L.slices[f"firstNorm{r}"], f"downSample_{r}": L.slices[f"downSample{r}.W"],
+                         f"firstConvStem_{r}": L.slices[f"firstConv{r}.W"], f"secondNormStem_{r}": L.slices[f"secondNorm{r}"],
+                         f"secondConvStem_{r}": L.slices[f"secondConv{r}.W"]})
+        for name, sl in want.items():
+            assert got[name] == sl, (name, got[name], sl)
+        v = Z.ode_vertex_from_dl4j(conf["vertices"]["odeBlock"])
+        assert v.numParams((2, C, 7, 7)) == n_ode
+    # save / load without a device: the methods only touch the host-side vectors
+    C = 8
+    n_ode = 3 * 4 * C + 2 * C * C * 9
+    L = OO.OuterLayout(C, n_ode)
+    rng = np.random.default_rng(0)
+
+    def host_model():
+        m = OdeNetModel.__new__(OdeNetModel)
+        m._h, m.channels, m.batch = None, C, 4
+        m._solver, m._time = None, (0.0, 1.0)
+        m.ode_slice = L.slices["ode"]
+        m.params = rng.standard_normal(L.n).astype(np.float32)
+        m.updater_state = rng.standard_normal(L.n).astype(np.float32)
+        return m
+
+    a, b = host_model(), host_model()
+    path = tmp_path / "odenet.zip"
+    a.save(path)
+    b.load(path)
+    assert np.array_equal(a.params, b.params) and np.array_equal(a.updater_state, b.updater_state)
+    name, vconf, block, upd = Z.extract_ode_block(path)
+    o, n = L.slices["ode"]
+    assert name == "odeBlock" and np.array_equal(block, a.params[o:o + n]) and np.array_equal(upd, a.updater_state[o:o + n])
+    other = OdeNetModel.__new__(OdeNetModel)
+    other._h, other.channels, other.ode_slice, other.params = None, 16, (1, 2), np.zeros(5, dtype=np.float32)
+    with pytest.raises(ValueError):
+        other.load(path)
